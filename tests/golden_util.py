@@ -1,0 +1,34 @@
+"""Helpers shared by the oracle (CPU) and CUDA (GPU) parity tests."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+FIXED = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "fixed_*.npz")))
+FITS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "fit_*.npz")))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    for k in ("kind",):
+        g[k] = str(g[k])
+    for k in ("estimate_trend",):
+        g[k] = bool(g[k])
+    return g
+
+
+def mode_of(g):
+    return "noisy" if float(g["nugget"]) > 0 else "noiseless"
+
+
+def beta_of(g):
+    return 0.0 if g["estimate_trend"] else float(g["beta_in"])
+
+
+def relerr(a, b, floor=0.0):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b) / (np.abs(b) + floor)) if a.size else 0.0
