@@ -1,0 +1,156 @@
+/* mgp.h -- C ABI of libmgp_b200.so: the B200-native Gaussian-process surrogate hot path of
+ * MIP-EGO (wangronin/MIP-EGO, mipego 2.0.0).
+ *
+ * The reference is pure Python and has no FFI for this path: the boundary it exposes is the
+ * duck-typed protocol between its BO loop / acquisition optimisers and
+ * `GaussianProcess` + `InfillCriteria`.  Each entry point below names
+ * the reference code it replaces (paths relative to the reference root).  The Python classes
+ * in mip-ego_b200/ bind these with ctypes and mirror the reference's class surface.
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative MGP_E* code on failure;
+ *    mgp_last_error(h) returns a human-readable message for the last failure on that handle;
+ *  - no exceptions cross the ABI; all pointers are caller-owned; host arrays are C-contiguous
+ *    row-major IEEE float64 (int64 for indices) and read-only unless named out_*;
+ *  - a handle is bound to one CUDA device and owns all device memory it allocates; it is not
+ *    thread-safe (one handle per Python object; the caller serialises calls);
+ *  - functions without the _dev suffix take HOST pointers and are synchronous: host<->device
+ *    copies happen inside the call.  *_dev functions take DEVICE pointers (on the handle's
+ *    device) plus a cudaStream_t (as void*); they enqueue work on that stream and return
+ *    without synchronising;
+ *  - all arithmetic is float64.  There is no CPU fallback: without a CUDA device every compute
+ *    entry point fails with MGP_ECUDA.
+ */
+#ifndef MGP_H_
+#define MGP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGP_ABI_VERSION 1
+
+/* error codes */
+#define MGP_OK 0
+#define MGP_EINVAL (-1)   /* bad argument (shape mismatch, NULL, unknown enum) */
+#define MGP_ECUDA (-2)    /* CUDA runtime failure (message has the CUDA error string) */
+#define MGP_ESTATE (-3)   /* call order: predict before fit / set_state, etc. */
+#define MGP_ENOMEM (-4)   /* device allocation failed */
+#define MGP_ENOTPD (-5)   /* correlation matrix not positive definite (finalize_fit only) */
+#define MGP_ENCCL (-6)    /* NCCL failure */
+
+/* correlation functions: mipego/GaussianProcess/kernel.py */
+#define MGP_CORR_SE 0        /* squared_exponential  kernel.py:277-317 */
+#define MGP_CORR_MATERN32 1  /* matern, nu = 1.5     kernel.py:147-185 */
+#define MGP_CORR_ABSEXP 2    /* absolute_exponential kernel.py:235-274 */
+
+/* trend (prior mean): mipego/GaussianProcess/trend.py:69-88 (constant_trend) */
+#define MGP_TREND_CONST_FIXED 0      /* beta given  -> simple kriging   (gpr.py:693-695) */
+#define MGP_TREND_CONST_ESTIMATED 1  /* beta = None -> ordinary kriging (gpr.py:686-692) */
+
+/* likelihood / estimation mode: gpr.py:246-251 */
+#define MGP_MODE_NOISELESS 0  /* par = theta             gpr.py:814-835 */
+#define MGP_MODE_NOISY 1      /* par = [theta, sigma2]   gpr.py:855-874 */
+
+/* acquisition functions: mipego/InfillCriteria.py */
+#define MGP_ACQ_EI 0    /* EI        InfillCriteria.py:113-148 */
+#define MGP_ACQ_PI 1    /* EpsilonPI InfillCriteria.py:150-187 (param = epsilon; 0 = plain PI) */
+#define MGP_ACQ_UCB 2   /* UCB       InfillCriteria.py:75-111  (param = alpha) */
+#define MGP_ACQ_MGFI 3  /* MGFI      InfillCriteria.py:196-252 (param = t, capped at 22.36) */
+
+typedef struct mgp_handle mgp_t;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int mgp_abi_version(void);
+int mgp_create(int device, mgp_t **out_h);
+int mgp_destroy(mgp_t *h);
+const char *mgp_last_error(const mgp_t *h);
+
+/* ---- training data: GaussianProcess._check_data, gpr.py:263-288 ------------------------
+ * Uploads X (n x d) and y (n).  Returns MGP_EINVAL with "duplicate rows" if two rows of X
+ * coincide (the reference raises Exception, gpr.py:275-277).  `beta0` is used only for
+ * MGP_TREND_CONST_FIXED. */
+int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int corr, int trend,
+                  double beta0);
+
+/* ---- batched marginal likelihood: GaussianProcess.log_likelihood_concentrated,
+ * gpr.py:798-946 (with correlation_matrix :658-668, _compute_aux_var :676-697,
+ * corr_grad_theta :622-656) evaluated for B parameter vectors at once.
+ * params: B x n_par (n_par = d for NOISELESS, d+1 for NOISY).  out_llf: B.  out_grad: B x n_par
+ * (d llf / d par, NOT d/d log10 par -- SURVEY Q5) or NULL when eval_grad == 0.
+ * out_status[b]: 0 ok; k > 0: Cholesky failed at pivot k (llf = -inf, grad = 0,
+ * gpr.py:820-826); -1: llf > 0 rejected (llf = -inf, grad = 0, gpr.py:889-891). */
+int mgp_nll_batch(mgp_t *h, int B, const double *params, int n_par, int mode, double noise_var,
+                  int eval_grad, double *out_llf, double *out_grad, int *out_status);
+
+/* ---- harvest the fitted state for the chosen parameters: the final likelihood call of
+ * _optimize_hyperparameter (gpr.py:1087-1101) + compute_beta_gamma (gpr.py:670-674).
+ * Builds on the device: L = chol(R), L^-1, rho, Yt, Ft, G, sigma2, beta, gamma, and the packed
+ * operands of the posterior kernels.  out_llf (may be NULL) receives the log-likelihood.
+ * Returns MGP_ENOTPD if R is not positive definite. */
+int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double noise_var,
+                     double *out_llf);
+
+/* ---- state exchange (pickling; accepting an externally fitted model).
+ * get: any out pointer may be NULL.  out_L: n x n row-major lower triangle (upper = 0);
+ * out_theta: d; out_gamma, out_rho, out_Yt, out_Ft: n; out_scalars[4] = {sigma2, beta, G, llf}
+ * (Ft and G are meaningful only for MGP_TREND_CONST_ESTIMATED).
+ * set: theta (d), L (n x n row-major, lower), gamma (n), sigma2, beta; everything else
+ * (L^-1, Ft, G, packed operands) is rebuilt on the device.  Requires mgp_set_train first. */
+int mgp_get_state(mgp_t *h, double *out_theta, double *out_L, double *out_gamma, double *out_rho,
+                  double *out_Yt, double *out_Ft, double *out_scalars);
+int mgp_set_state(mgp_t *h, const double *theta, const double *L, const double *gamma,
+                  double sigma2, double beta);
+
+/* ---- posterior: GaussianProcess.predict, gpr.py:392-483.  Xs: m x d.  out_mean: m.
+ * out_mse: m or NULL.  MSE = |sigma2 (1 - |L^-1 r|^2 + u^2)| (gpr.py:471-474). */
+int mgp_predict(mgp_t *h, int64_t m, const double *Xs, double *out_mean, double *out_mse);
+
+/* ---- posterior gradient: GaussianProcess.gradient + corr_dx, gpr.py:511-617, applied to each
+ * of the m rows of Xs.  out_mean_dx, out_mse_dx: m x d. */
+int mgp_gradient(mgp_t *h, int64_t m, const double *Xs, double *out_mean_dx, double *out_mse_dx);
+
+/* ---- fused posterior + acquisition: InfillCriteria.{EI,EpsilonPI,UCB,MGFI}.__call__
+ * (InfillCriteria.py:75-252) applied element-wise to each row of Xs, for n_sets parameter
+ * values sharing one posterior evaluation (ParallelBO, BayesOpt.py:56-101).
+ * set_params: n_sets values (epsilon | alpha | t; ignored for EI).  plugin: user-facing value
+ * (it is negated when minimize == 0, InfillCriteria.py:64-73).  out_val: n_sets x m.
+ * out_dx: n_sets x m x d or NULL (return_dx). */
+int mgp_acq(mgp_t *h, int64_t m, const double *Xs, int kind, int n_sets, const double *set_params,
+            double plugin, int minimize, double *out_val, double *out_dx);
+
+/* Same, returning only the k best (largest) candidates per parameter set: what
+ * argmax_restart (optimizer/utils.py:8-87) extracts from a population.
+ * out_val: n_sets x k (descending); out_idx: n_sets x k row indices into Xs. */
+int mgp_acq_topk(mgp_t *h, int64_t m, const double *Xs, int kind, int n_sets,
+                 const double *set_params, double plugin, int minimize, int k, double *out_val,
+                 int64_t *out_idx);
+
+/* ---- device-resident variants (inputs/outputs already in HBM; no host copies, no sync).
+ * d_* are device pointers on the handle's device; set_params stays a host pointer.
+ * d_out_mean / d_out_mse may be NULL in mgp_acq_dev; d_out_dx may be NULL. */
+int mgp_predict_dev(mgp_t *h, int64_t m, const double *d_Xs, double *d_out_mean, double *d_out_mse,
+                    void *stream);
+int mgp_acq_dev(mgp_t *h, int64_t m, const double *d_Xs, int kind, int n_sets,
+                const double *set_params, double plugin, int minimize, double *d_out_val,
+                double *d_out_dx, void *stream);
+int mgp_acq_topk_dev(mgp_t *h, int64_t m, const double *d_Xs, int kind, int n_sets,
+                     const double *set_params, double plugin, int minimize, int k,
+                     double *d_out_val, int64_t *d_out_idx, void *stream);
+int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mode,
+                      double noise_var, int eval_grad, double *d_out_llf, double *d_out_grad,
+                      int *d_out_status, void *stream);
+
+/* ---- tuning / introspection ------------------------------------------------------------
+ * mgp_set_option: "chunk" = candidates per pass of the posterior pipeline (multiple of 128).
+ * mgp_get_counter: "launches" = kernels launched by this handle so far;
+ * "flops_posterior" etc. are reserved. */
+int mgp_set_option(mgp_t *h, const char *name, int64_t value);
+int64_t mgp_get_counter(const mgp_t *h, const char *name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGP_H_ */

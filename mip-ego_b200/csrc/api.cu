@@ -1,0 +1,695 @@
+// C ABI of libmgp_b200 (see include/mgp.h): handle management and host-side orchestration of
+// the CUDA kernels.  No compute happens on the host; without a CUDA device every entry point
+// fails with MGP_ECUDA.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "linalg.cuh"
+#include "mgp_common.cuh"
+#include "mgp_handle.h"
+#include "nll.cuh"
+#include "posterior.cuh"
+
+int mgp_fail(mgp_handle *h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+int mgp_cuda_fail(mgp_handle *h, cudaError_t e, const char *what) {
+  return mgp_fail(h, e == cudaErrorMemoryAllocation ? MGP_ENOMEM : MGP_ECUDA, "CUDA error '%s' in %s",
+                  cudaGetErrorString(e), what);
+}
+int mgp_ensure(mgp_handle *h, DevBuf &b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return 0;
+  if (b.p) {
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  if (bytes == 0) return 0;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) return mgp_cuda_fail(h, e, "cudaMalloc");
+  b.bytes = bytes;
+  return 0;
+}
+static void freebuf(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+template <typename T>
+static inline T *P(const DevBuf &b) { return reinterpret_cast<T *>(b.p); }
+
+#define CHECK_H(h) \
+  if (!(h)) return MGP_EINVAL; \
+  MGP_CUDA(h, cudaSetDevice((h)->device))
+
+extern "C" {
+
+int mgp_abi_version(void) { return MGP_ABI_VERSION; }
+
+int mgp_create(int device, mgp_t **out_h) {
+  if (!out_h) return MGP_EINVAL;
+  *out_h = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return MGP_ECUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return MGP_ECUDA;
+  mgp_handle *h = new mgp_handle();
+  h->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return MGP_ECUDA; }
+  if (prop.major != 10) {
+    // built for sm_100a only: fail loudly rather than at the first launch
+    delete h;
+    return MGP_ECUDA;
+  }
+  h->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return MGP_ECUDA;
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+  }
+  *out_h = h;
+  return MGP_OK;
+}
+
+int mgp_destroy(mgp_t *h) {
+  if (!h) return MGP_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  DevBuf *all[] = {&h->dXc, &h->dy, &h->dcenter, &h->dtheta, &h->dBop, &h->dan, &h->dL, &h->dMinv,
+                   &h->dTmp, &h->dLinvDiag, &h->dMp, &h->dRinvP, &h->dgamma, &h->davec, &h->dFt,
+                   &h->dYt, &h->drho, &h->dscal, &h->drP, &h->dmeanpart, &h->dftpart, &h->dqpart,
+                   &h->dwP, &h->dXs_stage[0], &h->dXs_stage[1], &h->dout_stage[0],
+                   &h->dout_stage[1], &h->dtopk_val, &h->dtopk_idx, &h->nR, &h->nL, &h->nM, &h->nT,
+                   &h->nLinvDiag, &h->nvec, &h->nscal, &h->npar, &h->ngpart};
+  for (DevBuf *b : all) freebuf(*b);
+  for (int i = 0; i < 2; i++) {
+    if (h->hpin[i]) cudaFreeHost(h->hpin[i]);
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return MGP_OK;
+}
+
+const char *mgp_last_error(const mgp_t *h) { return h ? h->err.c_str() : "null handle"; }
+
+int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
+  if (!h || !name) return MGP_EINVAL;
+  if (!strcmp(name, "chunk")) {
+    if (value < 0) return mgp_fail(h, MGP_EINVAL, "chunk must be >= 0");
+    h->chunk_opt = round_up(value, 128);
+    return MGP_OK;
+  }
+  return mgp_fail(h, MGP_EINVAL, "unknown option '%s'", name);
+}
+int64_t mgp_get_counter(const mgp_t *h, const char *name) {
+  if (!h || !name) return -1;
+  if (!strcmp(name, "launches")) return h->launches;
+  if (!strcmp(name, "npad")) return h->npad;
+  if (!strcmp(name, "chunk")) return h->chunk;
+  if (!strcmp(name, "sm_count")) return h->sm_count;
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// training data
+// ---------------------------------------------------------------------------------------------
+int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int corr, int trend,
+                  double beta0) {
+  CHECK_H(h);
+  if (n < 1 || d < 1 || !X || !y) return mgp_fail(h, MGP_EINVAL, "bad training data");
+  if (d > MGP_MAX_D) return mgp_fail(h, MGP_EINVAL, "d = %d > %d unsupported", d, MGP_MAX_D);
+  if (corr != MGP_CORR_SE && corr != MGP_CORR_MATERN32)
+    return mgp_fail(h, MGP_EINVAL, "correlation type %d not supported by the CUDA path", corr);
+  if (trend != MGP_TREND_CONST_FIXED && trend != MGP_TREND_CONST_ESTIMATED)
+    return mgp_fail(h, MGP_EINVAL, "trend type %d unknown", trend);
+  h->fitted = false;
+  h->rinv_ready = false;
+  h->nll_cap = 0;  // workspaces are re-validated against the new padded size
+  h->n = n; h->d = d; h->corr = corr; h->trend = trend; h->beta0 = beta0;
+  h->npad = (int)round_up(n, MGP_TILE);
+  h->dpad = (int)round_up(d, 4);
+  h->NI = h->npad / MGP_TILE;
+  h->hX.assign(X, X + (size_t)n * d);
+  h->hy.assign(y, y + n);
+  // centring is input marshalling: differences x - x' are translation invariant
+  std::vector<double> center(h->dpad, 0.0), Xc((size_t)h->npad * h->dpad, 0.0), yp(h->npad, 0.0);
+  for (int i = 0; i < d; i++) {
+    double s = 0.0;
+    for (int j = 0; j < n; j++) s += X[(size_t)j * d + i];
+    center[i] = s / n;
+  }
+  for (int j = 0; j < n; j++) {
+    for (int i = 0; i < d; i++) Xc[(size_t)j * h->dpad + i] = X[(size_t)j * d + i] - center[i];
+    yp[j] = y[j];
+  }
+  MGP_TRY(mgp_ensure(h, h->dXc, Xc.size() * 8));
+  MGP_TRY(mgp_ensure(h, h->dy, yp.size() * 8));
+  MGP_TRY(mgp_ensure(h, h->dcenter, center.size() * 8));
+  MGP_TRY(mgp_ensure(h, h->dscal, 4096));
+  MGP_CUDA(h, cudaMemcpyAsync(h->dXc.p, Xc.data(), Xc.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  MGP_CUDA(h, cudaMemcpyAsync(h->dy.p, yp.data(), yp.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  MGP_CUDA(h, cudaMemcpyAsync(h->dcenter.p, center.data(), center.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  // duplicate rows: raise like gpr.py:275-277 (compared on the raw, uncentred coordinates'
+  // differences: x_j == x_k  <=>  xc_j == xc_k up to the same subtraction)
+  int *flag = P<int>(h->dscal);
+  MGP_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+  MGP_CUDA(h, launch_dup_check(P<double>(h->dXc), n, h->dpad, flag, h->stream));
+  h->launches++;
+  int hflag = 0;
+  MGP_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  MGP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (hflag) {
+    h->n = 0;
+    return mgp_fail(h, MGP_EINVAL, "duplicate rows: Multiple input features cannot have the same target value.");
+  }
+  return MGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// likelihood
+// ---------------------------------------------------------------------------------------------
+static int nll_alloc(mgp_handle *h, int B) {
+  if (B <= h->nll_cap) return 0;
+  const size_t mat = (size_t)h->npad * h->npad * 8;
+  const int ntiles = h->NI * (h->NI + 1) / 2;
+  MGP_TRY(mgp_ensure(h, h->nR, mat * B));
+  MGP_TRY(mgp_ensure(h, h->nL, mat * B));
+  MGP_TRY(mgp_ensure(h, h->nM, mat * B));
+  MGP_TRY(mgp_ensure(h, h->nT, mat * B));
+  MGP_TRY(mgp_ensure(h, h->nLinvDiag, (size_t)B * h->NI * 128 * 128 * 8));
+  MGP_TRY(mgp_ensure(h, h->nvec, (size_t)4 * B * h->npad * 8));
+  MGP_TRY(mgp_ensure(h, h->nscal, (size_t)B * nll_scal_doubles() * 8 + (size_t)B * sizeof(int) + 64));
+  MGP_TRY(mgp_ensure(h, h->ngpart, (size_t)B * ntiles * (h->dpad + 1) * 8));
+  h->nll_cap = B;
+  return 0;
+}
+static int *nll_status_ptr(mgp_handle *h, int cap) {
+  return reinterpret_cast<int *>(P<double>(h->nscal) + (size_t)cap * nll_scal_doubles());
+}
+static int nll_max_batch(mgp_handle *h) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 1;
+  const size_t per = (size_t)h->npad * h->npad * 8 * 4 + (size_t)h->NI * 128 * 128 * 8;
+  size_t budget = (free_b + h->nR.bytes + h->nL.bytes + h->nM.bytes + h->nT.bytes) / 2;
+  int cap = (int)std::max<size_t>(1, budget / per);
+  return std::min(cap, 64);
+}
+
+static int check_par(mgp_handle *h, int n_par, int mode) {
+  if (h->n == 0) return mgp_fail(h, MGP_ESTATE, "mgp_set_train must be called first");
+  if (mode != MGP_MODE_NOISELESS && mode != MGP_MODE_NOISY)
+    return mgp_fail(h, MGP_EINVAL, "estimation mode %d not supported", mode);
+  const int want = h->d + (mode == MGP_MODE_NOISY ? 1 : 0);
+  if (n_par != want)
+    return mgp_fail(h, MGP_EINVAL, "n_par = %d, expected %d (anisotropic theta%s)", n_par, want,
+                    mode == MGP_MODE_NOISY ? " + sigma2" : "");
+  return 0;
+}
+
+static void fill_work(mgp_handle *h, NllWork &w, int B, int cap, int n_par, int mode,
+                      double noise_var, int eval_grad, const double *d_params, double *d_llf,
+                      double *d_grad) {
+  memset(&w, 0, sizeof(w));
+  w.n = h->n; w.npad = h->npad; w.dpad = h->dpad; w.B = B; w.n_par = n_par; w.mode = mode;
+  w.corr = h->corr; w.ordinary = h->trend == MGP_TREND_CONST_ESTIMATED; w.eval_grad = eval_grad;
+  w.noise_var = noise_var; w.beta0 = h->beta0;
+  w.Xc = P<double>(h->dXc); w.y = P<double>(h->dy); w.params = d_params;
+  w.R = P<double>(h->nR); w.L = P<double>(h->nL); w.M = P<double>(h->nM); w.T = P<double>(h->nT);
+  w.linv = P<double>(h->nLinvDiag); w.vec = P<double>(h->nvec); w.scal = P<double>(h->nscal);
+  w.gpart = P<double>(h->ngpart); w.status = nll_status_ptr(h, cap);
+  w.out_llf = d_llf; w.out_grad = d_grad;
+}
+
+int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mode,
+                      double noise_var, int eval_grad, double *d_out_llf, double *d_out_grad,
+                      int *d_out_status, void *stream) {
+  CHECK_H(h);
+  MGP_TRY(check_par(h, n_par, mode));
+  if (B < 1 || !d_params || !d_out_llf || (eval_grad && !d_out_grad))
+    return mgp_fail(h, MGP_EINVAL, "bad arguments to mgp_nll_batch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int cap = std::min(B, nll_max_batch(h));
+  if (cap > h->nll_cap) MGP_TRY(nll_alloc(h, cap));
+  const int use = h->nll_cap;
+  for (int b0 = 0; b0 < B; b0 += use) {
+    const int nb = std::min(use, B - b0);
+    NllWork w;
+    fill_work(h, w, nb, use, n_par, mode, noise_var, eval_grad, d_params + (size_t)b0 * n_par,
+              d_out_llf + b0, eval_grad ? d_out_grad + (size_t)b0 * n_par : nullptr);
+    MGP_CUDA(h, nll_pipeline(w, st, &h->launches));
+    if (d_out_status)
+      MGP_CUDA(h, cudaMemcpyAsync(d_out_status + b0, w.status, sizeof(int) * nb, cudaMemcpyDeviceToDevice, st));
+  }
+  return MGP_OK;
+}
+
+int mgp_nll_batch(mgp_t *h, int B, const double *params, int n_par, int mode, double noise_var,
+                  int eval_grad, double *out_llf, double *out_grad, int *out_status) {
+  CHECK_H(h);
+  MGP_TRY(check_par(h, n_par, mode));
+  if (B < 1 || !params || !out_llf || (eval_grad && !out_grad))
+    return mgp_fail(h, MGP_EINVAL, "bad arguments to mgp_nll_batch");
+  const size_t pb = (size_t)B * n_par * 8;
+  MGP_TRY(mgp_ensure(h, h->npar, 2 * pb + (size_t)B * 8 + (size_t)B * sizeof(int) + 256));
+  double *d_par = P<double>(h->npar);
+  double *d_grad = d_par + (size_t)B * n_par;
+  double *d_llf = d_grad + (size_t)B * n_par;
+  int *d_status = reinterpret_cast<int *>(d_llf + B);
+  MGP_CUDA(h, cudaMemcpyAsync(d_par, params, pb, cudaMemcpyHostToDevice, h->stream));
+  MGP_TRY(mgp_nll_batch_dev(h, B, d_par, n_par, mode, noise_var, eval_grad, d_llf, d_grad, d_status,
+                            h->stream));
+  MGP_CUDA(h, cudaMemcpyAsync(out_llf, d_llf, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (eval_grad)
+    MGP_CUDA(h, cudaMemcpyAsync(out_grad, d_grad, pb, cudaMemcpyDeviceToHost, h->stream));
+  if (out_status)
+    MGP_CUDA(h, cudaMemcpyAsync(out_status, d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  MGP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fitted state
+// ---------------------------------------------------------------------------------------------
+static int model_alloc(mgp_handle *h) {
+  const size_t mat = (size_t)h->npad * h->npad * 8, vec = (size_t)h->npad * 8;
+  MGP_TRY(mgp_ensure(h, h->dL, mat));
+  MGP_TRY(mgp_ensure(h, h->dMinv, mat));
+  MGP_TRY(mgp_ensure(h, h->dMp, (size_t)8 * h->NI * (h->NI + 1) * 1024 * 8));
+  MGP_TRY(mgp_ensure(h, h->dtheta, (size_t)h->dpad * 8));
+  MGP_TRY(mgp_ensure(h, h->dBop, (size_t)h->npad * h->dpad * 8));
+  MGP_TRY(mgp_ensure(h, h->dan, vec));
+  MGP_TRY(mgp_ensure(h, h->dgamma, vec));
+  MGP_TRY(mgp_ensure(h, h->davec, vec));
+  MGP_TRY(mgp_ensure(h, h->dFt, vec));
+  MGP_TRY(mgp_ensure(h, h->dYt, vec));
+  MGP_TRY(mgp_ensure(h, h->drho, vec));
+  return 0;
+}
+
+// Common tail of finalize_fit / set_state: the NLL workspace slot 0 holds L, M, Yt, Ft, rho, gamma.
+static int adopt_slot0(mgp_handle *h, const double *theta_host, bool take_gamma) {
+  cudaStream_t st = h->stream;
+  const size_t mat = (size_t)h->npad * h->npad * 8, vec = (size_t)h->npad * 8;
+  const double *v = P<double>(h->nvec);
+  const int B = 1;  // slot 0 of a batch-1 run
+  MGP_CUDA(h, cudaMemcpyAsync(h->dL.p, h->nL.p, mat, cudaMemcpyDeviceToDevice, st));
+  MGP_CUDA(h, cudaMemcpyAsync(h->dMinv.p, h->nM.p, mat, cudaMemcpyDeviceToDevice, st));
+  MGP_CUDA(h, cudaMemcpyAsync(h->dYt.p, v, vec, cudaMemcpyDeviceToDevice, st));
+  MGP_CUDA(h, cudaMemcpyAsync(h->dFt.p, v + (size_t)B * h->npad, vec, cudaMemcpyDeviceToDevice, st));
+  MGP_CUDA(h, cudaMemcpyAsync(h->drho.p, v + (size_t)2 * B * h->npad, vec, cudaMemcpyDeviceToDevice, st));
+  if (take_gamma)
+    MGP_CUDA(h, cudaMemcpyAsync(h->dgamma.p, v + (size_t)3 * B * h->npad, vec, cudaMemcpyDeviceToDevice, st));
+  // a = L^-T Ft  (so that Ft^T L^-1 r = a . r)
+  MGP_CUDA(h, launch_trmv(P<double>(h->dMinv), h->npad, 0, P<double>(h->dFt), 0, P<double>(h->davec), 0,
+                          h->n, 1, 1, st));
+  std::vector<double> th(h->dpad, 0.0);
+  for (int i = 0; i < h->d; i++) th[i] = theta_host[i];
+  MGP_CUDA(h, cudaMemcpyAsync(h->dtheta.p, th.data(), th.size() * 8, cudaMemcpyHostToDevice, st));
+  MGP_CUDA(h, launch_prep_model(P<double>(h->dXc), P<double>(h->dtheta), h->npad, h->dpad,
+                                P<double>(h->dBop), P<double>(h->dan), st));
+  MGP_CUDA(h, launch_pack_tri(P<double>(h->dMinv), h->npad, P<double>(h->dMp), st));
+  h->launches += 3;
+  MGP_CUDA(h, cudaStreamSynchronize(st));  // th is a host temporary
+  h->rinv_ready = false;
+  return 0;
+}
+
+int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double noise_var,
+                     double *out_llf) {
+  CHECK_H(h);
+  MGP_TRY(check_par(h, n_par, mode));
+  if (!par) return mgp_fail(h, MGP_EINVAL, "par is NULL");
+  MGP_TRY(model_alloc(h));
+  if (h->nll_cap < 1) MGP_TRY(nll_alloc(h, 1));
+  MGP_TRY(mgp_ensure(h, h->npar, (size_t)n_par * 8 + 64));
+  cudaStream_t st = h->stream;
+  MGP_CUDA(h, cudaMemcpyAsync(h->npar.p, par, (size_t)n_par * 8, cudaMemcpyHostToDevice, st));
+  NllWork w;
+  fill_work(h, w, 1, h->nll_cap, n_par, mode, noise_var, 0, P<double>(h->npar), nullptr, nullptr);
+  MGP_CUDA(h, nll_pipeline(w, st, &h->launches));
+  std::vector<double> sc(nll_scal_doubles());
+  int status = 0;
+  MGP_CUDA(h, cudaMemcpyAsync(sc.data(), w.scal, sc.size() * 8, cudaMemcpyDeviceToHost, st));
+  MGP_CUDA(h, cudaMemcpyAsync(&status, w.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MGP_CUDA(h, cudaStreamSynchronize(st));
+  if (status > 0) {
+    h->fitted = false;
+    return mgp_fail(h, MGP_ENOTPD, "correlation matrix not positive definite at pivot %d", status);
+  }
+  h->mode = mode;
+  h->noise_var = noise_var;
+  h->sigma2 = sc[NLL_SIGMA2];
+  h->llf = sc[NLL_LLF];
+  h->ftf = sc[NLL_FTF];
+  h->G = -sqrt(sc[NLL_FTF]);  // LAPACK's Householder QR of the positive-leading column Ft
+  h->beta = sc[NLL_BETA];
+  MGP_TRY(adopt_slot0(h, par, true));
+  h->fitted = true;
+  if (out_llf) *out_llf = h->llf;
+  return MGP_OK;
+}
+
+int mgp_set_state(mgp_t *h, const double *theta, const double *L, const double *gamma,
+                  double sigma2, double beta) {
+  CHECK_H(h);
+  if (h->n == 0) return mgp_fail(h, MGP_ESTATE, "mgp_set_train must be called first");
+  if (!theta || !L || !gamma) return mgp_fail(h, MGP_EINVAL, "NULL state array");
+  MGP_TRY(model_alloc(h));
+  if (h->nll_cap < 1) MGP_TRY(nll_alloc(h, 1));
+  cudaStream_t st = h->stream;
+  const int n = h->n, npad = h->npad;
+  // L -> slot 0 (identity on the padding)
+  std::vector<double> Lp((size_t)npad * npad, 0.0), gp(npad, 0.0);
+  for (int j = 0; j < n; j++)
+    for (int k = 0; k <= j; k++) Lp[(size_t)j * npad + k] = L[(size_t)j * n + k];
+  for (int j = n; j < npad; j++) Lp[(size_t)j * npad + j] = 1.0;
+  for (int j = 0; j < n; j++) gp[j] = gamma[j];
+  MGP_CUDA(h, cudaMemcpyAsync(h->nL.p, Lp.data(), Lp.size() * 8, cudaMemcpyHostToDevice, st));
+  MGP_CUDA(h, cudaMemcpyAsync(h->dgamma.p, gp.data(), gp.size() * 8, cudaMemcpyHostToDevice, st));
+  std::vector<double> dummy(h->d + 1, 1.0);
+  MGP_TRY(mgp_ensure(h, h->npar, dummy.size() * 8 + 64));
+  MGP_CUDA(h, cudaMemcpyAsync(h->npar.p, dummy.data(), dummy.size() * 8, cudaMemcpyHostToDevice, st));
+  NllWork w;
+  fill_work(h, w, 1, h->nll_cap, h->d, MGP_MODE_NOISELESS, 0.0, 0, P<double>(h->npar), nullptr, nullptr);
+  w.have_L = 1;
+  MGP_CUDA(h, nll_pipeline(w, st, &h->launches));
+  std::vector<double> sc(nll_scal_doubles());
+  MGP_CUDA(h, cudaMemcpyAsync(sc.data(), w.scal, sc.size() * 8, cudaMemcpyDeviceToHost, st));
+  MGP_CUDA(h, cudaStreamSynchronize(st));
+  h->sigma2 = sigma2;
+  h->beta = beta;
+  h->ftf = sc[NLL_FTF];
+  h->G = -sqrt(sc[NLL_FTF]);
+  h->llf = NAN;
+  MGP_TRY(adopt_slot0(h, theta, false));
+  h->fitted = true;
+  return MGP_OK;
+}
+
+int mgp_get_state(mgp_t *h, double *out_theta, double *out_L, double *out_gamma, double *out_rho,
+                  double *out_Yt, double *out_Ft, double *out_scalars) {
+  CHECK_H(h);
+  if (!h->fitted) return mgp_fail(h, MGP_ESTATE, "model is not fitted");
+  cudaStream_t st = h->stream;
+  const int n = h->n;
+  if (out_theta) MGP_CUDA(h, cudaMemcpyAsync(out_theta, h->dtheta.p, (size_t)h->d * 8, cudaMemcpyDeviceToHost, st));
+  if (out_L)
+    MGP_CUDA(h, cudaMemcpy2DAsync(out_L, (size_t)n * 8, h->dL.p, (size_t)h->npad * 8, (size_t)n * 8, n,
+                                  cudaMemcpyDeviceToHost, st));
+  if (out_gamma) MGP_CUDA(h, cudaMemcpyAsync(out_gamma, h->dgamma.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (out_rho) MGP_CUDA(h, cudaMemcpyAsync(out_rho, h->drho.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (out_Yt) MGP_CUDA(h, cudaMemcpyAsync(out_Yt, h->dYt.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (out_Ft) MGP_CUDA(h, cudaMemcpyAsync(out_Ft, h->dFt.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  MGP_CUDA(h, cudaStreamSynchronize(st));
+  if (out_scalars) {
+    out_scalars[0] = h->sigma2; out_scalars[1] = h->beta; out_scalars[2] = h->G; out_scalars[3] = h->llf;
+  }
+  return MGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// posterior pipeline
+// ---------------------------------------------------------------------------------------------
+struct PostReq {
+  int64_t m;
+  const double *d_Xs;
+  double *d_mean, *d_mse, *d_val, *d_mean_dx, *d_mse_dx, *d_dx;
+  int kind, n_sets, minimize, want_dx, topk;
+  double plugin;
+  const double *params;
+  double *d_topv;
+  int64_t *d_topi;
+  int64_t ld_val;     // elements between parameter sets in d_val (x d in d_dx); 0 -> m
+  int64_t idx_base;   // global index of row 0 (top-k over several calls)
+  int topk_continue;  // 1: merge into the existing running top-k instead of resetting it
+};
+
+static int post_workspace(mgp_handle *h, bool want_dx) {
+  int64_t chunk = h->chunk_opt > 0 ? h->chunk_opt : (int64_t)h->sm_count * 128;
+  h->chunk = chunk;
+  MGP_TRY(mgp_ensure(h, h->drP, (size_t)h->npad * chunk * 8));
+  MGP_TRY(mgp_ensure(h, h->dmeanpart, (size_t)h->NI * chunk * 8));
+  MGP_TRY(mgp_ensure(h, h->dftpart, (size_t)h->NI * chunk * 8));
+  MGP_TRY(mgp_ensure(h, h->dqpart, (size_t)h->NI * chunk * 8));
+  if (want_dx) MGP_TRY(mgp_ensure(h, h->dwP, (size_t)h->npad * chunk * 8));
+  return 0;
+}
+
+static int ensure_rinv(mgp_handle *h, cudaStream_t st) {
+  if (h->rinv_ready) return 0;
+  const size_t mat = (size_t)h->npad * h->npad * 8;
+  MGP_TRY(mgp_ensure(h, h->dTmp, mat));
+  MGP_TRY(mgp_ensure(h, h->dRinvP, mat));
+  MGP_CUDA(h, lauum_blocked(P<double>(h->dMinv), P<double>(h->dTmp), h->npad, 0, 1, st, &h->launches));
+  MGP_CUDA(h, launch_pack_sym(P<double>(h->dTmp), h->npad, P<double>(h->dRinvP), st));
+  h->launches++;
+  h->rinv_ready = true;
+  return 0;
+}
+
+static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
+  if (!h->fitted) return mgp_fail(h, MGP_ESTATE, "model is not fitted");
+  if (q.m < 0) return mgp_fail(h, MGP_EINVAL, "m < 0");
+  if (q.m == 0) return 0;
+  const bool acq = q.d_val || q.topk > 0 || q.d_dx;
+  if (acq) {
+    if (q.kind < MGP_ACQ_EI || q.kind > MGP_ACQ_MGFI) return mgp_fail(h, MGP_EINVAL, "unknown acquisition %d", q.kind);
+    if (q.n_sets < 1 || q.n_sets > MGP_MAX_SETS) return mgp_fail(h, MGP_EINVAL, "n_sets must be in 1..%d", MGP_MAX_SETS);
+    if (q.kind != MGP_ACQ_EI && !q.params) return mgp_fail(h, MGP_EINVAL, "set_params is NULL");
+  }
+  if (q.topk > 64) return mgp_fail(h, MGP_EINVAL, "k must be <= 64");
+  MGP_TRY(post_workspace(h, q.want_dx));
+  if (q.want_dx) MGP_TRY(ensure_rinv(h, st));
+  const int NJ8 = h->npad / 8;
+  const bool ordinary = h->trend == MGP_TREND_CONST_ESTIMATED;
+  double *chunk_val = nullptr;
+  if (q.topk > 0) {
+    MGP_TRY(mgp_ensure(h, h->dtopk_val, (size_t)q.n_sets * h->chunk * 8));
+    chunk_val = P<double>(h->dtopk_val);
+  }
+  for (int64_t c0 = 0; c0 < q.m; c0 += h->chunk) {
+    const int64_t mc = std::min<int64_t>(h->chunk, q.m - c0);
+    const int64_t ldp = round_up(mc, 128);
+    const int nCblk = (int)(ldp / 128);
+    int JS = std::max(1, std::min(h->NI, (2 * h->sm_count) / nCblk));
+    const int jblk = (h->NI + JS - 1) / JS;
+    JS = (h->NI + jblk - 1) / jblk;
+    RgenParams rp;
+    rp.Xs = q.d_Xs + c0 * h->d; rp.mc = mc; rp.d = h->d; rp.dpad = h->dpad; rp.NJ8 = NJ8;
+    rp.jblk_per_cta = jblk;
+    rp.center = P<double>(h->dcenter); rp.theta = P<double>(h->dtheta); rp.Bop = P<double>(h->dBop);
+    rp.an = P<double>(h->dan); rp.gamma = P<double>(h->dgamma); rp.avec = P<double>(h->davec);
+    rp.rP = P<double>(h->drP); rp.meanpart = P<double>(h->dmeanpart); rp.ftpart = P<double>(h->dftpart);
+    rp.ldp = ldp;
+    MGP_CUDA(h, launch_rgen(rp, h->corr, JS, st));
+    h->launches++;
+    if (!q.want_dx) {
+      TrmmParams tp;
+      tp.Mp = P<double>(h->dMp); tp.rP = P<double>(h->drP); tp.qpart = P<double>(h->dqpart);
+      tp.wP = nullptr; tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 0; tp.ldq = ldp;
+      MGP_CUDA(h, launch_trmm(tp, h->sm_count, st));
+      EpiParams ep;
+      ep.qpart = P<double>(h->dqpart); ep.meanpart = P<double>(h->dmeanpart); ep.ftpart = P<double>(h->dftpart);
+      ep.NI = h->NI; ep.JS = JS; ep.ld = ldp; ep.mc = mc;
+      ep.beta = h->beta; ep.sigma2 = h->sigma2; ep.G = h->G; ep.ordinary = ordinary;
+      ep.out_mean = q.d_mean ? q.d_mean + c0 : nullptr;
+      ep.out_mse = q.d_mse ? q.d_mse + c0 : nullptr;
+      ep.out_val = nullptr; ep.ld_val = 0;
+      if (q.topk > 0) { ep.out_val = chunk_val; ep.ld_val = h->chunk; }
+      else if (q.d_val) { ep.out_val = q.d_val + c0; ep.ld_val = q.ld_val ? q.ld_val : q.m; }
+      ep.kind = q.kind; ep.n_sets = acq ? q.n_sets : 0; ep.minimize = q.minimize; ep.plugin = q.plugin;
+      for (int s = 0; s < MGP_MAX_SETS; s++) ep.params[s] = (acq && q.params && s < q.n_sets) ? q.params[s] : 0.0;
+      MGP_CUDA(h, launch_epilogue(ep, st));
+      h->launches += 2;
+    } else {
+      TrmmParams tp;
+      tp.Mp = P<double>(h->dRinvP); tp.rP = P<double>(h->drP); tp.qpart = nullptr;
+      tp.wP = P<double>(h->dwP); tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 1; tp.ldq = ldp;
+      MGP_CUDA(h, launch_trmm(tp, h->sm_count, st));
+      GradParams gp;
+      gp.Xs = q.d_Xs + c0 * h->d; gp.mc = mc; gp.ldp = ldp; gp.n = h->n; gp.d = h->d; gp.dpad = h->dpad;
+      gp.NJ8 = NJ8; gp.Xc = P<double>(h->dXc); gp.center = P<double>(h->dcenter);
+      gp.theta = P<double>(h->dtheta); gp.gamma = P<double>(h->dgamma); gp.avec = P<double>(h->davec);
+      gp.rP = P<double>(h->drP); gp.wP = P<double>(h->dwP);
+      gp.meanpart = P<double>(h->dmeanpart); gp.ftpart = P<double>(h->dftpart); gp.JS = JS;
+      gp.beta = h->beta; gp.sigma2 = h->sigma2; gp.G = h->G; gp.ftf = h->ftf; gp.ordinary = ordinary;
+      gp.out_mean = q.d_mean ? q.d_mean + c0 : nullptr;
+      gp.out_mse = q.d_mse ? q.d_mse + c0 : nullptr;
+      gp.out_mean_dx = q.d_mean_dx ? q.d_mean_dx + c0 * h->d : nullptr;
+      gp.out_mse_dx = q.d_mse_dx ? q.d_mse_dx + c0 * h->d : nullptr;
+      gp.out_val = q.d_val ? q.d_val + c0 : nullptr;
+      gp.out_dx = q.d_dx ? q.d_dx + c0 * h->d : nullptr;
+      gp.ld_val = q.ld_val ? q.ld_val : q.m;
+      gp.kind = q.kind; gp.n_sets = acq ? q.n_sets : 0; gp.minimize = q.minimize; gp.plugin = q.plugin;
+      for (int s = 0; s < MGP_MAX_SETS; s++) gp.params[s] = (acq && q.params && s < q.n_sets) ? q.params[s] : 0.0;
+      MGP_CUDA(h, launch_grad(gp, h->corr, st));
+      h->launches += 2;
+    }
+    if (q.topk > 0) {
+      MGP_CUDA(h, launch_topk_merge(chunk_val, h->chunk, mc, q.idx_base + c0, q.n_sets, q.topk, q.d_topv,
+                                    q.d_topi, c0 == 0 && !q.topk_continue, st));
+      h->launches++;
+    }
+  }
+  return 0;
+}
+
+// ---- device-pointer entry points --------------------------------------------------------------
+int mgp_predict_dev(mgp_t *h, int64_t m, const double *d_Xs, double *d_out_mean, double *d_out_mse,
+                    void *stream) {
+  CHECK_H(h);
+  if (!d_Xs || !d_out_mean) return mgp_fail(h, MGP_EINVAL, "NULL pointer");
+  PostReq q = {};
+  q.m = m; q.d_Xs = d_Xs; q.d_mean = d_out_mean; q.d_mse = d_out_mse; q.minimize = 1;
+  return posterior_run(h, q, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mgp_acq_dev(mgp_t *h, int64_t m, const double *d_Xs, int kind, int n_sets,
+                const double *set_params, double plugin, int minimize, double *d_out_val,
+                double *d_out_dx, void *stream) {
+  CHECK_H(h);
+  if (!d_Xs || !d_out_val) return mgp_fail(h, MGP_EINVAL, "NULL pointer");
+  PostReq q = {};
+  q.m = m; q.d_Xs = d_Xs; q.d_val = d_out_val; q.d_dx = d_out_dx; q.want_dx = d_out_dx != nullptr;
+  q.kind = kind; q.n_sets = n_sets; q.params = set_params; q.plugin = plugin; q.minimize = minimize;
+  return posterior_run(h, q, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mgp_acq_topk_dev(mgp_t *h, int64_t m, const double *d_Xs, int kind, int n_sets,
+                     const double *set_params, double plugin, int minimize, int k,
+                     double *d_out_val, int64_t *d_out_idx, void *stream) {
+  CHECK_H(h);
+  if (!d_Xs || !d_out_val || !d_out_idx || k < 1) return mgp_fail(h, MGP_EINVAL, "bad arguments");
+  PostReq q = {};
+  q.m = m; q.d_Xs = d_Xs; q.topk = k; q.d_topv = d_out_val; q.d_topi = d_out_idx;
+  q.kind = kind; q.n_sets = n_sets; q.params = set_params; q.plugin = plugin; q.minimize = minimize;
+  return posterior_run(h, q, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- host-pointer entry points: double-buffered H2D of candidate super-chunks overlapped with
+// compute; one D2H of the results at the end. ------------------------------------------------------
+struct HostOut {
+  double *mean, *mse, *val, *mean_dx, *mse_dx, *dx;
+};
+
+static int host_run(mgp_handle *h, int64_t m, const double *Xs, PostReq q, const HostOut &o) {
+  if (!h->fitted) return mgp_fail(h, MGP_ESTATE, "model is not fitted");
+  if (m < 0 || !Xs) return mgp_fail(h, MGP_EINVAL, "bad candidates");
+  if (m == 0) return 0;
+  const int d = h->d;
+  const int ns = std::max(1, q.n_sets);
+  MGP_TRY(post_workspace(h, q.want_dx));
+  const int64_t super = std::min<int64_t>(m, h->chunk * 8);
+  for (int i = 0; i < 2; i++) MGP_TRY(mgp_ensure(h, h->dXs_stage[i], (size_t)super * d * 8));
+  // outputs: [mean m][mse m][val ns*m][mean_dx m*d][mse_dx m*d][dx ns*m*d]
+  size_t off = 0;
+  auto take = [&](bool on, size_t cnt) { size_t r = off; if (on) off += cnt; return r; };
+  const size_t o_mean = take(o.mean, m), o_mse = take(o.mse, m), o_val = take(o.val, (size_t)ns * m),
+               o_mdx = take(o.mean_dx, (size_t)m * d), o_sdx = take(o.mse_dx, (size_t)m * d),
+               o_dx = take(o.dx, (size_t)ns * m * d);
+  MGP_TRY(mgp_ensure(h, h->dout_stage[0], std::max<size_t>(off, 1) * 8));
+  double *dout = P<double>(h->dout_stage[0]);
+  if (q.topk > 0) {
+    MGP_TRY(mgp_ensure(h, h->dtopk_idx, (size_t)ns * q.topk * 16));
+    q.d_topi = P<int64_t>(h->dtopk_idx);
+    q.d_topv = reinterpret_cast<double *>(q.d_topi + (size_t)ns * q.topk);
+  }
+  cudaStream_t st = h->stream, cs = h->copy_stream;
+  int it = 0;
+  for (int64_t s0 = 0; s0 < m; s0 += super, it++) {
+    const int64_t ms = std::min(super, m - s0);
+    const int buf = it & 1;
+    if (it >= 2) MGP_CUDA(h, cudaStreamWaitEvent(cs, h->ev_done[buf], 0));
+    MGP_CUDA(h, cudaMemcpyAsync(h->dXs_stage[buf].p, Xs + s0 * d, (size_t)ms * d * 8, cudaMemcpyHostToDevice, cs));
+    MGP_CUDA(h, cudaEventRecord(h->ev_in[buf], cs));
+    MGP_CUDA(h, cudaStreamWaitEvent(st, h->ev_in[buf], 0));
+    PostReq r = q;
+    r.m = ms; r.d_Xs = P<double>(h->dXs_stage[buf]);
+    r.d_mean = o.mean ? dout + o_mean + s0 : nullptr;
+    r.d_mse = o.mse ? dout + o_mse + s0 : nullptr;
+    r.d_mean_dx = o.mean_dx ? dout + o_mdx + s0 * d : nullptr;
+    r.d_mse_dx = o.mse_dx ? dout + o_sdx + s0 * d : nullptr;
+    r.d_val = o.val && q.topk == 0 ? dout + o_val + s0 : nullptr;
+    r.d_dx = o.dx && q.topk == 0 ? dout + o_dx + s0 * d : nullptr;
+    r.ld_val = m;
+    r.idx_base = s0;
+    r.topk_continue = it > 0;
+    MGP_TRY(posterior_run(h, r, st));
+    MGP_CUDA(h, cudaEventRecord(h->ev_done[buf], st));
+  }
+  if (q.topk > 0) {
+    MGP_CUDA(h, cudaMemcpyAsync(o.val, q.d_topv, (size_t)ns * q.topk * 8, cudaMemcpyDeviceToHost, st));
+    MGP_CUDA(h, cudaMemcpyAsync(reinterpret_cast<int64_t *>(o.dx), q.d_topi, (size_t)ns * q.topk * 8, cudaMemcpyDeviceToHost, st));
+  } else {
+    if (o.mean) MGP_CUDA(h, cudaMemcpyAsync(o.mean, dout + o_mean, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    if (o.mse) MGP_CUDA(h, cudaMemcpyAsync(o.mse, dout + o_mse, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    if (o.val) MGP_CUDA(h, cudaMemcpyAsync(o.val, dout + o_val, (size_t)ns * m * 8, cudaMemcpyDeviceToHost, st));
+    if (o.mean_dx) MGP_CUDA(h, cudaMemcpyAsync(o.mean_dx, dout + o_mdx, (size_t)m * d * 8, cudaMemcpyDeviceToHost, st));
+    if (o.mse_dx) MGP_CUDA(h, cudaMemcpyAsync(o.mse_dx, dout + o_sdx, (size_t)m * d * 8, cudaMemcpyDeviceToHost, st));
+    if (o.dx) MGP_CUDA(h, cudaMemcpyAsync(o.dx, dout + o_dx, (size_t)ns * m * d * 8, cudaMemcpyDeviceToHost, st));
+  }
+  MGP_CUDA(h, cudaStreamSynchronize(st));
+  MGP_CUDA(h, cudaStreamSynchronize(cs));
+  return MGP_OK;
+}
+
+int mgp_predict(mgp_t *h, int64_t m, const double *Xs, double *out_mean, double *out_mse) {
+  CHECK_H(h);
+  if (!out_mean) return mgp_fail(h, MGP_EINVAL, "out_mean is NULL");
+  PostReq q = {};
+  q.minimize = 1;
+  HostOut o = {out_mean, out_mse, nullptr, nullptr, nullptr, nullptr};
+  return host_run(h, m, Xs, q, o);
+}
+
+int mgp_gradient(mgp_t *h, int64_t m, const double *Xs, double *out_mean_dx, double *out_mse_dx) {
+  CHECK_H(h);
+  if (!out_mean_dx || !out_mse_dx) return mgp_fail(h, MGP_EINVAL, "NULL output");
+  PostReq q = {};
+  q.minimize = 1; q.want_dx = 1;
+  HostOut o = {nullptr, nullptr, nullptr, out_mean_dx, out_mse_dx, nullptr};
+  return host_run(h, m, Xs, q, o);
+}
+
+int mgp_acq(mgp_t *h, int64_t m, const double *Xs, int kind, int n_sets, const double *set_params,
+            double plugin, int minimize, double *out_val, double *out_dx) {
+  CHECK_H(h);
+  if (!out_val) return mgp_fail(h, MGP_EINVAL, "out_val is NULL");
+  PostReq q = {};
+  q.kind = kind; q.n_sets = n_sets; q.params = set_params; q.plugin = plugin; q.minimize = minimize;
+  q.want_dx = out_dx != nullptr;
+  HostOut o = {nullptr, nullptr, out_val, nullptr, nullptr, out_dx};
+  return host_run(h, m, Xs, q, o);
+}
+
+int mgp_acq_topk(mgp_t *h, int64_t m, const double *Xs, int kind, int n_sets,
+                 const double *set_params, double plugin, int minimize, int k, double *out_val,
+                 int64_t *out_idx) {
+  CHECK_H(h);
+  if (!out_val || !out_idx || k < 1) return mgp_fail(h, MGP_EINVAL, "bad arguments");
+  PostReq q = {};
+  q.kind = kind; q.n_sets = n_sets; q.params = set_params; q.plugin = plugin; q.minimize = minimize;
+  q.topk = k;
+  HostOut o = {nullptr, nullptr, out_val, nullptr, nullptr, reinterpret_cast<double *>(out_idx)};
+  return host_run(h, m, Xs, q, o);
+}
+
+}  // extern "C"

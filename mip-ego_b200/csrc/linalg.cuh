@@ -1,0 +1,53 @@
+// Host-callable launchers of the dense FP64 building blocks (linalg.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// C(i,j) = alpha * sum_k A(i,k) B(k,j) + beta * C(i,j) on DMMA tensor cores.
+//   ta == 0: A stored [M][K] (k contiguous, lda);  ta == 1: A stored [K][M].
+//   tb == 0: B stored [N][K] (k contiguous, ldb);  tb == 1: B stored [K][N].
+// M, N multiples of 128, K multiple of 16.  Two batch levels: z = outer * n_inner + inner.
+// kmode bits: 1 -> k starts at colblk*128; 2 -> k ends at (rowblk+1)*128; 4 -> k starts at
+// rowblk*128 (triangular operands).  lower_only: skip tiles strictly above the block diagonal.
+struct GemmDesc {
+  const double *A, *B;
+  double *C;
+  int lda, ldb, ldc;
+  int M, N, K;
+  int ta, tb;
+  double alpha, beta;
+  int kmode, lower_only;
+  int n_inner, n_outer;
+  int64_t sA_in, sB_in, sC_in, sA_out, sB_out, sC_out;
+};
+cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st);
+
+// In-place Cholesky of the kb-th 128x128 diagonal block of each matrix of the batch
+// (A row-major, ld, batch stride sA), writing L_kk into Lout (same geometry) and L_kk^-1 into
+// linv (batch stride sInv; block kb at linv + kb*128*128).  status[b] is set to the 1-based
+// global pivot index on failure (first failure wins).
+cudaError_t launch_potrf_diag(double *A, double *Lout, int ld, int64_t sA, double *linv,
+                              int64_t sInv, int kb, int *status, int batch, cudaStream_t st);
+// Inverse of every 128x128 diagonal block of a given lower-triangular L (no factorisation).
+cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv, int64_t sInv,
+                              int NI, int batch, cudaStream_t st);
+// Full blocked Cholesky A -> L (lower, row-major npad x npad, A is destroyed) + diag inverses.
+cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
+                         int *status, int batch, cudaStream_t st, int64_t *launches);
+// Minv = L^-1 given L and the diagonal-block inverses; T is scratch (npad x npad per matrix).
+cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, int64_t sMat,
+                          const double *linv, int64_t sInv, int batch, cudaStream_t st,
+                          int64_t *launches);
+// Rinv(lower tiles) = Minv^T Minv.
+cudaError_t lauum_blocked(const double *Minv, double *Rinv, int npad, int64_t sMat, int batch,
+                          cudaStream_t st, int64_t *launches);
+
+// y = M x (trans == 0) or y = M^T x (trans == 1), M lower-triangular row-major npad x npad.
+// x == nullptr means the all-ones vector restricted to the first n entries.
+cudaError_t launch_trmv(const double *M, int npad, int64_t sM, const double *x, int64_t sx,
+                        double *y, int64_t sy, int n, int trans, int batch, cudaStream_t st);
+
+// Pack row-major L^-1 into the slab layout of the posterior kernel (lower block triangle).
+cudaError_t launch_pack_tri(const double *Minv, int npad, double *Mp, cudaStream_t st);
+// Pack a symmetric matrix given by its lower tiles into the full slab layout (all blocks).
+cudaError_t launch_pack_sym(const double *Rinv, int npad, double *Rp, cudaStream_t st);

@@ -1,0 +1,92 @@
+// Shared device/host helpers for libmgp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define MGP_TILE 128  // row / column block of every blocked algorithm (n is padded to it)
+
+// ---- FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4 ----------
+// lane t holds A[t/4][t%4], B[t%4][t/4], C[t/4][2*(t%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---- mbarrier + bulk async copy (TMA engine; SASS: UBLKCP / SYNCS) --------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- Ampere-style async copy (LDGSTS) for strided tiles -------------------------------------
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ---- scalar math shared by the epilogues ------------------------------------------------------
+#define MGP_SQRT3 1.7320508075688772
+#define MGP_INV_SQRT2 0.70710678118654752440
+#define MGP_INV_SQRT2PI 0.39894228040143267794
+
+// standard normal cdf / pdf: scipy.stats.norm.cdf == ndtr (InfillCriteria.py:132)
+__device__ __forceinline__ double norm_cdf(double x) { return 0.5 * erfc(-x * MGP_INV_SQRT2); }
+__device__ __forceinline__ double norm_pdf(double x) { return exp(-0.5 * x * x) * MGP_INV_SQRT2PI; }
+
+// correlation as a function of S = sum_i theta_i (x_i - x'_i)^2  (kernel.py:147-185, 277-317)
+template <int CORR>
+__device__ __forceinline__ double corr_from_S(double S) {
+  S = fmax(S, 0.0);
+  if (CORR == 0) return exp(-S);
+  double s = MGP_SQRT3 * sqrt(S);
+  return (1.0 + s) * exp(-s);
+}
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

@@ -1,0 +1,77 @@
+// Internal handle of libmgp_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mgp.h"
+
+#define MGP_MAX_SETS 16
+#define MGP_MAX_D 64
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct mgp_handle {
+  int device = 0;
+  std::string err;
+  cudaStream_t stream = nullptr;   // internal stream for the host-pointer entry points
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  int64_t launches = 0;
+  int sm_count = 148;
+
+  // ---- training data -------------------------------------------------------------------
+  int n = 0, d = 0, npad = 0, dpad = 0, NI = 0;
+  int corr = 0, trend = 0;
+  double beta0 = 0.0;
+  std::vector<double> hX, hy;   // host copies (state exchange, duplicate check)
+  DevBuf dXc;      // npad x dpad, centred, zero padded
+  DevBuf dy;       // npad
+  DevBuf dcenter;  // dpad
+  // ---- fitted model --------------------------------------------------------------------
+  bool fitted = false;
+  int mode = 0;
+  double sigma2 = 0, beta = 0, G = 0, ftf = 0, llf = 0, noise_var = 0;
+  DevBuf dtheta;   // dpad
+  DevBuf dBop;     // npad x dpad : -2 theta_i xc_ji
+  DevBuf dan;      // npad        : sum_i theta_i xc_ji^2
+  DevBuf dL;       // npad x npad row-major lower Cholesky factor
+  DevBuf dMinv;    // npad x npad row-major L^-1
+  DevBuf dTmp;     // npad x npad scratch
+  DevBuf dLinvDiag;  // NI x 128 x 128 inverses of the diagonal blocks of L
+  DevBuf dMp;      // packed lower-triangular L^-1 (posterior A operand)
+  DevBuf dRinvP;   // packed full R^-1 (gradient path), built lazily
+  bool rinv_ready = false;
+  DevBuf dgamma, davec, dFt, dYt, drho;  // npad each
+  DevBuf dscal;    // small device scalar area
+  // ---- posterior workspace ---------------------------------------------------------------
+  int64_t chunk = 0;       // candidates per pass (multiple of 128)
+  int64_t chunk_opt = 0;   // user override
+  DevBuf drP, dmeanpart, dftpart, dqpart, dwP;
+  DevBuf dXs_stage[2], dout_stage[2];
+  DevBuf dtopk_val, dtopk_idx;
+  void *hpin[2] = {nullptr, nullptr};
+  size_t hpin_bytes = 0;
+  // ---- likelihood workspace --------------------------------------------------------------
+  int nll_cap = 0;  // batch capacity of the buffers below
+  DevBuf nR, nL, nM, nT, nLinvDiag, nvec, nscal, npar, ngpart;
+};
+
+int mgp_fail(mgp_handle *h, int code, const char *fmt, ...);
+int mgp_cuda_fail(mgp_handle *h, cudaError_t e, const char *what);
+int mgp_ensure(mgp_handle *h, DevBuf &b, size_t bytes);
+
+#define MGP_CUDA(h, call)                                          \
+  do {                                                             \
+    cudaError_t e__ = (call);                                      \
+    if (e__ != cudaSuccess) return mgp_cuda_fail((h), e__, #call); \
+  } while (0)
+#define MGP_TRY(call)          \
+  do {                         \
+    int rc__ = (call);         \
+    if (rc__ != 0) return rc__; \
+  } while (0)

@@ -1,0 +1,31 @@
+// Batched likelihood pipeline (nll.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mgp.h"
+
+struct NllWork {
+  int n, npad, dpad, B, n_par, mode, corr, ordinary, eval_grad;
+  int have_L;             // 1: L (B=1) is given in w.L; skip the correlation build and Cholesky
+  double noise_var, beta0;
+  const double *Xc;      // npad x dpad centred training inputs
+  const double *y;       // npad, zero padded
+  const double *params;  // device, B x n_par
+  // workspaces, each B matrices of npad x npad
+  double *R, *L, *M, *T;
+  double *linv;          // B x NI x 128 x 128
+  double *vec;           // 4 x B x npad : Yt, Ft, rho, gamma
+  double *scal;          // B x nll_scal_doubles()
+  double *gpart;         // B x ntiles x (dpad + 1)
+  int *status;           // B
+  double *out_llf;       // device, B (nullable)
+  double *out_grad;      // device, B x n_par (nullable unless eval_grad)
+};
+size_t nll_scal_doubles();
+// scal slots
+enum { NLL_SIGMA2 = 0, NLL_LLF = 1, NLL_FTF = 2, NLL_FTY = 3, NLL_RR = 4, NLL_LOGDET = 5, NLL_S = 6,
+       NLL_V = 7, NLL_BETA = 8 };
+cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches);
+// flag[0] |= 1 if two of the n rows of Xc (npad x dpad) coincide (gpr.py:274-277).
+cudaError_t launch_dup_check(const double *Xc, int n, int dpad, int *flag, cudaStream_t st);

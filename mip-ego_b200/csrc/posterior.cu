@@ -1,0 +1,582 @@
+// Posterior + acquisition kernels (sm_100a).
+//
+// Packed "slab" layout shared by the operands of K2c.  One slab = 16 tiles of 8x8 doubles
+// (1024 doubles, 8 KB); a tile stores, for lane t of a warp, the two doubles that lane needs for
+// two consecutive DMMA k-steps, so one conflict-free LDS.128 per lane feeds two MMAs:
+//   Mp (A operand, L^-1 or R^-1): slab(I, j8) holds rows 128I..128I+127, columns 8j8..8j8+7;
+//       tile i8 is the row-major 8x8 block   M[128I + 8 i8 + ri][8 j8 + kj]  at  ri*8 + kj.
+//       Triangular packing keeps only j8 < 16(I+1): slab index 8 I (I+1) + j8.
+//   rP (B operand, r = corr(X*, X)^T): slab(Cblk, j8) holds training rows 8j8..8j8+7 for the
+//       128 candidates of block Cblk; tile c8 stores r[8 j8 + jj][128 Cblk + 8 c8 + cc] at cc*8 + jj.
+// With this packing the MMA k index kk of step s maps to training index 8 j8 + 2 kk + s for both
+// operands.  A pipeline stage (4 slabs of each operand = 32 k) is one contiguous 32 KB bulk copy
+// per operand (cp.async.bulk -> UBLKCP) completing on an mbarrier.
+#include "posterior.cuh"
+#include "mgp_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// per-fit operand preparation
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prep_model(const double *Xc, const double *theta, int npad, int dpad, double *Bop,
+                             double *an) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npad) return;
+  double s = 0.0;
+  for (int i = 0; i < dpad; i++) {
+    const double x = Xc[(int64_t)j * dpad + i], t = theta[i];
+    Bop[(int64_t)j * dpad + i] = -2.0 * t * x;
+    s = fma(t * x, x, s);
+  }
+  an[j] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: cross-correlation tiles.  S[c][j] = bn_c + an_j + sum_i xs_ci * (-2 theta_i x_ji) as a
+// DMMA GEMM over the (padded) feature dimension, then r = corr(S)  (kernel.py:147-185,277-317;
+// the reference forms |x - x'| component-wise, gpr.py:453-455).  Also accumulates
+// r . gamma (posterior mean, gpr.py:459) and r . a with a = L^-T Ft (Ft^T rt, gpr.py:467).
+// ---------------------------------------------------------------------------------------------
+template <int CORR, int KS>
+__global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lk = lane & 3;
+  const int cb = blockIdx.x;
+  double xa[2][KS], bn[2];
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    const int64_t c = (int64_t)cb * 128 + (2 * warp + u) * 8 + lr;
+    const bool valid = c < p.mc;
+    double part = 0.0;
+#pragma unroll
+    for (int s = 0; s < KS; s++) {
+      const int i = 4 * s + lk;
+      double v = 0.0;
+      if (valid && i < p.d) v = p.Xs[c * p.d + i] - p.center[i];
+      xa[u][s] = v;
+      part = fma(p.theta[i] * v, v, part);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    bn[u] = part;
+  }
+  double macc[2] = {0.0, 0.0}, facc[2] = {0.0, 0.0};
+  const int j8_begin = blockIdx.y * p.jblk_per_cta * 16;
+  const int j8_end = min(p.NJ8, j8_begin + p.jblk_per_cta * 16);
+#pragma unroll 2
+  for (int j8 = j8_begin; j8 < j8_end; j8++) {
+    const int jrow = 8 * j8 + lr, jcol = 8 * j8 + 2 * lk;
+    double bf[KS];
+#pragma unroll
+    for (int s = 0; s < KS; s++) bf[s] = __ldg(p.Bop + (int64_t)jrow * p.dpad + 4 * s + lk);
+    const double2 an2 = __ldg(reinterpret_cast<const double2 *>(p.an + jcol));
+    const double2 g2 = __ldg(reinterpret_cast<const double2 *>(p.gamma + jcol));
+    const double2 a2 = __ldg(reinterpret_cast<const double2 *>(p.avec + jcol));
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      double c0 = bn[u] + an2.x, c1 = bn[u] + an2.y;
+#pragma unroll
+      for (int s = 0; s < KS; s++) dmma884(c0, c1, xa[u][s], bf[s]);
+      const double r0 = corr_from_S<CORR>(c0), r1 = corr_from_S<CORR>(c1);
+      double2 *dst = reinterpret_cast<double2 *>(
+          p.rP + (((int64_t)cb * p.NJ8 + j8) * 16 + (2 * warp + u)) * 64 + lane * 2);
+      *dst = make_double2(r0, r1);
+      macc[u] = fma(g2.x, r0, macc[u]);
+      macc[u] = fma(g2.y, r1, macc[u]);
+      facc[u] = fma(a2.x, r0, facc[u]);
+      facc[u] = fma(a2.y, r1, facc[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; u++) {
+    macc[u] += __shfl_xor_sync(0xffffffffu, macc[u], 1);
+    macc[u] += __shfl_xor_sync(0xffffffffu, macc[u], 2);
+    facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 1);
+    facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 2);
+    if (lk == 0) {
+      const int64_t o = (int64_t)blockIdx.y * p.ldp + (int64_t)cb * 128 + (2 * warp + u) * 8 + lr;
+      p.meanpart[o] = macc[u];
+      p.ftpart[o] = facc[u];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2c: T = L^-1 r on DMMA with the column sums of squares fused (|L^-1 r|^2, gpr.py:463,472);
+// T never leaves registers.  FULL variant: W = R^-1 r written back in the rP layout (gradient
+// path, replaces the d triangular solves of gpr.py:543).
+// Work item = (row block I, candidate block cb); items are dealt round-robin to a persistent
+// grid in order of decreasing cost.  One elected thread drives the bulk-copy pipeline.
+// ---------------------------------------------------------------------------------------------
+constexpr int TS = 3;             // pipeline stages
+constexpr int STAGE_DBL = 4096;   // doubles per operand per stage (4 slabs, 32 KB)
+constexpr int TRMM_SMEM = 2 * TS * STAGE_DBL * 8 + 2 * TS * 8 + 2 * 128 * 8;
+
+template <bool FULL>
+__global__ void __launch_bounds__(256, 1) k_trmm(TrmmParams p) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double *As = reinterpret_cast<double *>(smraw);
+  double *Bs = As + TS * STAGE_DBL;
+  uint64_t *full = reinterpret_cast<uint64_t *>(Bs + TS * STAGE_DBL);
+  uint64_t *empty = full + TS;
+  double *red = reinterpret_cast<double *>(empty + TS);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = warp >> 2, wc = warp & 3, lr = lane >> 2, lk = lane & 3;
+  const int nItems = p.NI * p.nCblk;
+
+  if (tid == 0) {
+    for (int s = 0; s < TS; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // ---- producer cursor (thread 0) ----
+  int p_item = blockIdx.x, p_kc = 0, p_nkc = 0, p_I = 0, p_cb = 0;
+  int64_t p_x = 0;
+  auto p_setup = [&]() {
+    if (p_item < nItems) {
+      p_I = p.NI - 1 - p_item / p.nCblk;
+      p_cb = p_item % p.nCblk;
+      p_nkc = FULL ? p.NJ8 / 4 : 4 * (p_I + 1);
+      p_kc = 0;
+    }
+  };
+  auto issue = [&]() {
+    if (p_item >= nItems) return;
+    const int stage = (int)(p_x % TS);
+    const int64_t slabA =
+        FULL ? ((int64_t)p_I * p.NJ8 + 4 * p_kc) : ((int64_t)8 * p_I * (p_I + 1) + 4 * p_kc);
+    mbar_expect_tx(&full[stage], 2 * STAGE_DBL * 8);
+    bulk_g2s(As + stage * STAGE_DBL, p.Mp + slabA * 1024, STAGE_DBL * 8, &full[stage]);
+    bulk_g2s(Bs + stage * STAGE_DBL, p.rP + ((int64_t)p_cb * p.NJ8 + 4 * p_kc) * 1024,
+             STAGE_DBL * 8, &full[stage]);
+    p_x++;
+    if (++p_kc == p_nkc) {
+      p_item += gridDim.x;
+      p_setup();
+    }
+  };
+  if (tid == 0) {
+    p_setup();
+    for (int s = 0; s < TS; s++) issue();
+  }
+
+  int64_t x = 0;
+  for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+    const int I = p.NI - 1 - item / p.nCblk, cb = item % p.nCblk;
+    const int nkc = FULL ? p.NJ8 / 4 : 4 * (I + 1);
+    double acc[8][4][2];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+    for (int kc = 0; kc < nkc; kc++, x++) {
+      const int stage = (int)(x % TS);
+      mbar_wait(&full[stage], (uint32_t)((x / TS) & 1));
+      const double *as = As + stage * STAGE_DBL, *bs = Bs + stage * STAGE_DBL;
+      const int dl = FULL ? -1 : kc - 4 * I;  // >= 0 inside the diagonal 128x128 block
+#pragma unroll
+      for (int js = 0; js < 4; js++) {
+        int rt_min = 0;
+        if (dl >= 0) rt_min = 4 * dl + js - 8 * wr;  // row tiles above the block diagonal are zero
+        if (rt_min >= 8) continue;
+        double2 b[4], a[8];
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++)
+          b[ct] = *reinterpret_cast<const double2 *>(bs + (js * 16 + wc * 4 + ct) * 64 + lane * 2);
+#pragma unroll
+        for (int rt = 0; rt < 8; rt++)
+          a[rt] = *reinterpret_cast<const double2 *>(as + (js * 16 + wr * 8 + rt) * 64 + lane * 2);
+#pragma unroll
+        for (int rt = 0; rt < 8; rt++)
+          if (rt >= rt_min) {
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt].x, b[ct].x);
+          }
+#pragma unroll
+        for (int rt = 0; rt < 8; rt++)
+          if (rt >= rt_min) {
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt].y, b[ct].y);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (tid == 0 && x >= 1 && p_item < nItems) {
+        const int64_t xs = x - 1;  // refill the stage released one chunk ago
+        mbar_wait(&empty[xs % TS], (uint32_t)((xs / TS) & 1));
+        issue();
+      }
+    }
+
+    if (!FULL) {
+      double qs[4][2];
+#pragma unroll
+      for (int ct = 0; ct < 4; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          double s = 0.0;
+#pragma unroll
+          for (int rt = 0; rt < 8; rt++) s = fma(acc[rt][ct][e], acc[rt][ct][e], s);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          qs[ct][e] = s;
+        }
+      if (lr == 0) {
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+          red[wr * 128 + wc * 32 + ct * 8 + 2 * lk] = qs[ct][0];
+          red[wr * 128 + wc * 32 + ct * 8 + 2 * lk + 1] = qs[ct][1];
+        }
+      }
+      __syncthreads();
+      if (tid < 128) p.qpart[(int64_t)I * p.ldq + (int64_t)cb * 128 + tid] = red[tid] + red[128 + tid];
+      __syncthreads();
+    } else {
+      // W[j][c] for j in row block I: thread holds rows 8(wr*8+rt)+lr, cols 8(wc*4+ct)+2lk+{0,1}.
+      // rP-style layout wants, per (j8, c8) tile, element (cc, jj) at cc*8 + jj.
+#pragma unroll
+      for (int rt = 0; rt < 8; rt++)
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+          const int j8 = I * 16 + wr * 8 + rt, c8 = wc * 4 + ct;
+          double *tile = p.wP + (((int64_t)cb * p.NJ8 + j8) * 16 + c8) * 64;
+          tile[(2 * lk) * 8 + lr] = acc[rt][ct][0];
+          tile[(2 * lk + 1) * 8 + lr] = acc[rt][ct][1];
+        }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// acquisition functions (InfillCriteria.py).  Returns the value and the coefficients A, B of
+//   f_dx = A * yhat_dx + B * sd_dx      (yhat already sign-flipped when maximising)
+// ---------------------------------------------------------------------------------------------
+struct Acq {
+  double val, A, B;
+};
+__device__ __forceinline__ Acq acq_eval(int kind, double par, double plugin, double yhat, double sd,
+                                        double sigma2) {
+  Acq o;
+  o.val = 0.0; o.A = 0.0; o.B = 0.0;
+  if (kind == MGP_ACQ_UCB) {  // InfillCriteria.py:91-111
+    o.val = yhat + par * sd;
+    o.A = 1.0;
+    o.B = par;
+  } else if (kind == MGP_ACQ_EI) {  // InfillCriteria.py:114-148
+    if (sd / sqrt(sigma2) < 1e-6) return o;
+    const double xcr_ = plugin - yhat, xcr = xcr_ / sd;
+    const double cdf = norm_cdf(xcr), pdf = norm_pdf(xcr);
+    o.val = xcr_ * cdf + sd * pdf;
+    o.A = -cdf;
+    o.B = pdf;
+  } else if (kind == MGP_ACQ_PI) {  // EpsilonPI, InfillCriteria.py:167-187
+    const double coef = yhat > 0.0 ? 1.0 - par : 1.0 + par;
+    const double xcr = (plugin - coef * yhat) / sd;
+    const double pdf = norm_pdf(xcr);
+    o.val = norm_cdf(xcr);
+    o.A = -coef * pdf / sd;
+    o.B = -xcr * pdf / sd;
+  } else {  // MGFI, InfillCriteria.py:213-252
+    const double t = fmin(par, 22.36);
+    if (fabs(sd) <= 1e-8) return o;  // np.isclose(sd, 0)
+    const double bp = (plugin - (yhat - t * sd * sd)) / sd;
+    const double expo = t * (plugin - yhat - 1.0) + t * t * sd * sd * 0.5;
+    const double e = exp(expo), cdf = norm_cdf(bp), pdf = norm_pdf(bp);
+    const double v = cdf * e;
+    if (!isfinite(v) || !isfinite(e)) return o;  // overflow / invalid -> 0 (:223-236)
+    o.val = v;
+    o.A = e * (-pdf / sd - t * cdf);
+    o.B = e * (pdf * (2.0 * t * sd - bp) / sd + cdf * t * t * sd);
+  }
+  return o;
+}
+
+// K3: fixed-order reduction of the partial sums, MSE (gpr.py:465-474) and acquisition values.
+__global__ void __launch_bounds__(256) k_epilogue(EpiParams p) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.mc) return;
+  double q = 0.0;
+  for (int I = 0; I < p.NI; I++) q += p.qpart[(int64_t)I * p.ld + c];
+  double md = 0.0, ft = 0.0;
+  for (int y = 0; y < p.JS; y++) {
+    md += p.meanpart[(int64_t)y * p.ld + c];
+    ft += p.ftpart[(int64_t)y * p.ld + c];
+  }
+  const double mean = p.beta + md;
+  double u2 = 0.0;
+  if (p.ordinary) {
+    const double u = (ft - 1.0) / p.G;
+    u2 = u * u;
+  }
+  const double mse = fabs(p.sigma2 * (1.0 - q + u2));
+  if (p.out_mean) p.out_mean[c] = mean;
+  if (p.out_mse) p.out_mse[c] = mse;
+  if (p.out_val) {
+    const double sd = sqrt(mse);
+    const double yhat = p.minimize ? mean : -mean;
+    const double plug = p.minimize ? p.plugin : -p.plugin;
+    for (int s = 0; s < p.n_sets; s++)
+      p.out_val[(int64_t)s * p.ld_val + c] = acq_eval(p.kind, p.params[s], plug, yhat, sd, p.sigma2).val;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// running top-k (what argmax_restart keeps of a population, optimizer/utils.py:66-87)
+// total order: larger value first, NaN last, ties -> smaller index first
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool better(double v, int64_t i, double w, int64_t j) {
+  return (v > w) || (v == w && i < j);
+}
+__global__ void __launch_bounds__(1024) k_topk_merge(const double *vals, int64_t ld, int64_t mc,
+                                                     int64_t base, int k, double *topv,
+                                                     int64_t *topi, int init) {
+  __shared__ double sv[32];
+  __shared__ int64_t si[32];
+  __shared__ double nv[64];
+  __shared__ int64_t ni[64];
+  __shared__ double lastv;
+  __shared__ int64_t lasti;
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double *v = vals + (int64_t)s * ld;
+  double *tv = topv + (int64_t)s * k;
+  int64_t *ti = topi + (int64_t)s * k;
+  const double NEG = -INFINITY;
+  for (int r = 0; r < k; r++) {
+    double bv = NEG;
+    int64_t bi = INT64_MAX;
+    const bool have_last = r > 0;
+    const double lv = have_last ? lastv : 0.0;
+    const int64_t li = have_last ? lasti : 0;
+    auto consider = [&](double cv, int64_t ci) {
+      if (!(cv == cv)) cv = NEG;  // NaN -> -inf
+      if (have_last && !better(lv, li, cv, ci)) return;  // already selected (or before it)
+      if (better(cv, ci, bv, bi)) { bv = cv; bi = ci; }
+    };
+    for (int64_t i = tid; i < mc; i += 1024) consider(v[i], base + i);
+    if (!init)
+      for (int i = tid; i < k; i += 1024)
+        if (ti[i] >= 0) consider(tv[i], ti[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = sv[lane]; bi = si[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        lastv = bv; lasti = bi;
+        nv[r] = bv; ni[r] = (bi == INT64_MAX) ? -1 : bi;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < k; i += 1024) { tv[i] = nv[i]; ti[i] = ni[i]; }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// K5: posterior gradient (GaussianProcess.gradient + corr_dx, gpr.py:511-617) for every candidate
+// and the acquisition gradient (InfillCriteria.py:99-110,139-147,177-186,238-251).
+// With w = R^-1 r and a = L^-T Ft:
+//   mean_dx_i = sum_j gamma_j r_dx[j,i]
+//   mse_dx_i  = 2 sigma2 sum_j (-w_j + kappa a_j) r_dx[j,i],  kappa = (Ft^T rt - 1)/(Ft^T Ft)
+//   r_dx[j,i] = -2 theta_i D_i r_j (SE, gpr.py:592) | -3 theta_i D_i e^{-sqrt3 D} (Matern, :601-602)
+// One warp per candidate; lanes stride over the training points; D = x* - x_j component-wise.
+// A Matern candidate coinciding with a training point zeroes the whole Jacobian (gpr.py:588-615).
+// ---------------------------------------------------------------------------------------------
+template <int CORR, int DP>
+__global__ void __launch_bounds__(256) k_grad(GradParams p) {
+  const int tid = threadIdx.x, lane = tid & 31, cc = tid >> 5;
+  const int64_t c8g = blockIdx.x;            // global 8-candidate group
+  const int cb = (int)(c8g >> 4), c8 = (int)(c8g & 15);
+  const int64_t c = c8g * 8 + cc;
+  if (c >= p.mc) return;
+  double md = 0.0, ft = 0.0;
+  for (int y = 0; y < p.JS; y++) {
+    md += p.meanpart[(int64_t)y * p.ldp + c];
+    ft += p.ftpart[(int64_t)y * p.ldp + c];
+  }
+  const double kappa = p.ordinary ? (ft - 1.0) / p.ftf : 0.0;
+  double xs[DP], th[DP], am[DP], as[DP];
+#pragma unroll
+  for (int i = 0; i < DP; i++) {
+    xs[i] = i < p.d ? p.Xs[c * p.d + i] - p.center[i] : 0.0;
+    th[i] = p.theta[i];
+    am[i] = 0.0;
+    as[i] = 0.0;
+  }
+  double q = 0.0;
+  int coincide = 0;
+  const double *rbase = p.rP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + cc * 8;
+  const double *wbase = p.wP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + cc * 8;
+  for (int j = lane; j < p.n; j += 32) {
+    const int64_t o = (int64_t)(j >> 3) * 1024 + (j & 7);
+    const double r = rbase[o], w = wbase[o];
+    q = fma(r, w, q);
+    const double *xj = p.Xc + (int64_t)j * DP;
+    double df[DP];
+    double S = 0.0;
+#pragma unroll
+    for (int i = 0; i < DP; i++) {
+      df[i] = xs[i] - xj[i];
+      if (CORR == 1) S = fma(th[i] * df[i], df[i], S);
+    }
+    double e = r;
+    if (CORR == 1) {
+      if (S == 0.0) coincide = 1;
+      e = exp(-MGP_SQRT3 * sqrt(S));
+    }
+    const double cm = p.gamma[j] * e, cs = (kappa * p.avec[j] - w) * e;
+#pragma unroll
+    for (int i = 0; i < DP; i++) {
+      am[i] = fma(cm, df[i], am[i]);
+      as[i] = fma(cs, df[i], as[i]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+    coincide |= __shfl_xor_sync(0xffffffffu, coincide, o);
+  }
+  const double fac = CORR == 0 ? -2.0 : -3.0;
+  const double mean = p.beta + md;
+  double u2 = 0.0;
+  if (p.ordinary) {
+    const double u = (ft - 1.0) / p.G;
+    u2 = u * u;
+  }
+  const double mse = fabs(p.sigma2 * (1.0 - q + u2));
+  const double sd = sqrt(mse);
+  if (lane == 0) {
+    if (p.out_mean) p.out_mean[c] = mean;
+    if (p.out_mse) p.out_mse[c] = mse;
+  }
+  // lane i ends up owning component i (static indices keep am/as in registers)
+  double my_m = 0.0, my_s = 0.0;
+#pragma unroll
+  for (int i = 0; i < DP; i++) {
+    double a = am[i], b = as[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((i & 31) == lane) {
+      my_m = coincide ? 0.0 : fac * th[i] * a;
+      my_s = coincide ? 0.0 : 2.0 * p.sigma2 * fac * th[i] * b;
+    }
+    if (i % 32 == 31 || i == DP - 1) {
+      const int comp = (i / 32) * 32 + lane;
+      if (comp < p.d && comp <= i) {
+        if (p.out_mean_dx) p.out_mean_dx[c * p.d + comp] = my_m;
+        if (p.out_mse_dx) p.out_mse_dx[c * p.d + comp] = my_s;
+        if (p.n_sets > 0) {
+          const double yhat = p.minimize ? mean : -mean;
+          const double ydx = p.minimize ? my_m : -my_m;
+          const double plug = p.minimize ? p.plugin : -p.plugin;
+          const double sd_dx = my_s / (2.0 * sd);
+          for (int s = 0; s < p.n_sets; s++) {
+            const Acq a2 = acq_eval(p.kind, p.params[s], plug, yhat, sd, p.sigma2);
+            if (p.out_dx) {
+              double g = a2.A * ydx + a2.B * sd_dx;
+              if (a2.A == 0.0 && a2.B == 0.0) g = 0.0;  // guarded (dead) points: zero gradient
+              p.out_dx[((int64_t)s * p.ld_val + c) * p.d + comp] = g;
+            }
+            if (p.out_val && comp == 0) p.out_val[(int64_t)s * p.ld_val + c] = a2.val;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int CORR>
+static cudaError_t grad_dispatch(const GradParams &p, cudaStream_t st) {
+  const unsigned grid = (unsigned)((p.mc + 7) / 8);
+  switch (p.dpad) {
+#define GD(D) case D: k_grad<CORR, D><<<grid, 256, 0, st>>>(p); break;
+    GD(4) GD(8) GD(12) GD(16) GD(20) GD(24) GD(28) GD(32) GD(36) GD(40) GD(44) GD(48) GD(52) GD(56) GD(60) GD(64)
+#undef GD
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, int dpad,
+                              double *Bop, double *an, cudaStream_t st) {
+  k_prep_model<<<(npad + 127) / 128, 128, 0, st>>>(Xc, theta, npad, dpad, Bop, an);
+  return cudaGetLastError();
+}
+
+template <int CORR>
+static cudaError_t rgen_dispatch(const RgenParams &p, int JS, cudaStream_t st) {
+  dim3 grid((unsigned)(p.ldp / 128), (unsigned)JS);
+  switch (p.dpad / 4) {
+#define RG(K) case K: k_rgen<CORR, K><<<grid, 256, 0, st>>>(p); break;
+    RG(1) RG(2) RG(3) RG(4) RG(5) RG(6) RG(7) RG(8) RG(9) RG(10) RG(11) RG(12) RG(13) RG(14) RG(15) RG(16)
+#undef RG
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_rgen(const RgenParams &p, int corr, int JS, cudaStream_t st) {
+  if (corr == MGP_CORR_SE) return rgen_dispatch<0>(p, JS, st);
+  if (corr == MGP_CORR_MATERN32) return rgen_dispatch<1>(p, JS, st);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_trmm(const TrmmParams &p, int sm_count, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_trmm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRMM_SMEM);
+    cudaFuncSetAttribute(k_trmm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRMM_SMEM);
+    attr_done = true;
+  }
+  const int items = p.NI * p.nCblk;
+  if (items <= 0) return cudaSuccess;
+  const int grid = items < sm_count ? items : sm_count;
+  if (p.full) k_trmm<true><<<grid, 256, TRMM_SMEM, st>>>(p);
+  else k_trmm<false><<<grid, 256, TRMM_SMEM, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_epilogue(const EpiParams &p, cudaStream_t st) {
+  if (p.mc <= 0) return cudaSuccess;
+  k_epilogue<<<(unsigned)((p.mc + 255) / 256), 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_topk_merge(const double *vals, int64_t ld, int64_t mc, int64_t base, int n_sets,
+                              int k, double *topv, int64_t *topi, int init, cudaStream_t st) {
+  if (k > 64) return cudaErrorInvalidValue;
+  k_topk_merge<<<n_sets, 1024, 0, st>>>(vals, ld, mc, base, k, topv, topi, init);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grad(const GradParams &p, int corr, cudaStream_t st) {
+  if (p.mc <= 0) return cudaSuccess;
+  if (corr == MGP_CORR_SE) return grad_dispatch<0>(p, st);
+  if (corr == MGP_CORR_MATERN32) return grad_dispatch<1>(p, st);
+  return cudaErrorInvalidValue;
+}

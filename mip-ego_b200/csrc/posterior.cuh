@@ -1,0 +1,74 @@
+// Launchers of the posterior / acquisition kernels (posterior.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mgp_handle.h"
+
+// Per-fit operand preparation: Bop[j][i] = -2 theta_i xc_ji, an[j] = sum_i theta_i xc_ji^2.
+cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, int dpad,
+                              double *Bop, double *an, cudaStream_t st);
+
+struct RgenParams {
+  const double *Xs;   // chunk base: candidate rows, row-major with leading dimension d
+  int64_t mc;         // valid candidates in the chunk
+  int d, dpad, NJ8, jblk_per_cta;
+  const double *center, *theta, *Bop, *an, *gamma, *avec;
+  double *rP, *meanpart, *ftpart;
+  int64_t ldp;        // mc rounded up to 128
+};
+// K1: r tile generator.  grid = (ldp/128, JS).  corr: MGP_CORR_SE | MGP_CORR_MATERN32.
+cudaError_t launch_rgen(const RgenParams &p, int corr, int JS, cudaStream_t st);
+
+struct TrmmParams {
+  const double *Mp;   // packed operand (triangular L^-1 or full R^-1)
+  const double *rP;   // packed r
+  double *qpart;      // [NI][ldq] partial sums of squares          (full == 0)
+  double *wP;         // packed W = R^-1 r, same layout as rP        (full == 1)
+  int NI, nCblk, NJ8, full;
+  int64_t ldq;
+};
+// K2c: T = L^-1 r with fused column sums of squares (or W = R^-1 r), persistent grid.
+cudaError_t launch_trmm(const TrmmParams &p, int sm_count, cudaStream_t st);
+
+struct EpiParams {
+  const double *qpart, *meanpart, *ftpart;
+  int NI, JS;
+  int64_t ld, mc;
+  double beta, sigma2, G;
+  int ordinary;
+  double *out_mean, *out_mse;   // chunk-offset pointers or nullptr
+  double *out_val;              // chunk-offset pointer or nullptr
+  int64_t ld_val;               // distance between parameter sets in out_val
+  int kind, n_sets, minimize;
+  double plugin;
+  double params[MGP_MAX_SETS];
+};
+// K3: mean / MSE / acquisition per candidate.
+cudaError_t launch_epilogue(const EpiParams &p, cudaStream_t st);
+
+// Running top-k: merges the k best of vals[s][0..mc) (global index = base + i) into
+// topv/topi [n_sets][k] (descending; ties -> lower index first).  init != 0 resets them first.
+cudaError_t launch_topk_merge(const double *vals, int64_t ld, int64_t mc, int64_t base, int n_sets,
+                              int k, double *topv, int64_t *topi, int init, cudaStream_t st);
+
+struct GradParams {
+  const double *Xs;    // chunk base (row-major, ld d)
+  int64_t mc, ldp;
+  int n, d, dpad, NJ8;
+  const double *Xc, *center, *theta, *gamma, *avec;
+  const double *rP, *wP;
+  const double *meanpart, *ftpart;
+  int JS;
+  double beta, sigma2, G, ftf;
+  int ordinary;
+  double *out_mean, *out_mse;         // nullable (chunk-offset)
+  double *out_mean_dx, *out_mse_dx;   // nullable, row-major mc x d (chunk-offset)
+  double *out_val, *out_dx;           // nullable; out_dx is [n_sets][m][d]
+  int64_t ld_val;                     // = m (elements between sets in out_val)
+  int kind, n_sets, minimize;
+  double plugin;
+  double params[MGP_MAX_SETS];
+};
+// K5: gradient contraction + acquisition-with-gradient epilogue.
+cudaError_t launch_grad(const GradParams &p, int corr, cudaStream_t st);

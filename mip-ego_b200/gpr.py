@@ -1,0 +1,435 @@
+"""GaussianProcess: drop-in for mipego.GaussianProcess.GaussianProcess (gpr.py:80-1149) whose
+arithmetic runs on the GPU through libmgp_b200 (include/mgp.h).
+
+Same constructor, `fit / update / predict(eval_MSE) / gradient`, the attributes the BO loop and
+the infill criteria read (`is_fitted`, `y`, `sigma2`, `X`, `theta_`, ...), the same exceptions.
+Supported configuration: corr in {squared_exponential, matern(nu=1.5)},
+`constant_trend` mean (beta given = simple kriging, beta=None = ordinary kriging),
+likelihood='concentrated', estimation modes noiseless (nugget falsy) and noisy (nugget > 0),
+optimizer='BFGS'.  Anything else raises NotImplementedError: there is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+from numpy import log10
+
+from . import _cabi
+from ._mle import multistart_lbfgsb
+from .trend import BasisExpansionTrend, constant_trend
+
+MACHINE_EPSILON = np.finfo(np.double).eps
+
+
+def _check_array(X, name="X"):
+    """sklearn.utils.check_array semantics used by the reference (gpr.py:265,431): 2-D float64,
+    finite; object-dtype `Solution` arrays are coerced (base.py:516-517)."""
+    X = np.asarray(X)
+    if X.dtype == object:
+        X = np.array(X.tolist(), dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    if X.ndim == 1:
+        raise ValueError("Expected 2D array, got 1D array instead")
+    if X.ndim != 2:
+        raise ValueError("Found array with dim %d. Expected 2" % X.ndim)
+    if not np.isfinite(X).all():
+        raise ValueError("Input %s contains NaN or infinity." % name)
+    return X
+
+
+class GaussianProcess(object):
+    _optimizer_types = ["BFGS"]
+    _correlation_types = ("squared_exponential", "matern")
+    _likelihood_functions = ["concentrated"]
+
+    def __init__(self, mean, corr="squared_exponential", theta0=1e-1, thetaL=None, thetaU=None,
+                 sigma2=None, nugget=None, noise_estim=False, optimizer="BFGS",
+                 likelihood="concentrated", random_start=1, wait_iter=5, eval_budget=None,
+                 random_state=None, verbose=False, device=None, restart_mode="batched"):
+        # gpr.py:212-261
+        self.mean = mean
+        self.corr = corr
+        self.sigma2 = sigma2
+        self.verbose = verbose
+        self.corr_type = corr
+        self.is_fitted = False
+
+        self.theta0 = np.array(theta0).flatten()
+        self.thetaL = np.array(thetaL).flatten()
+        self.thetaU = np.array(thetaU).flatten()
+        if not (np.isfinite(self.thetaL.astype(float)).all() and
+                np.isfinite(self.thetaU.astype(float)).all()):
+            raise ValueError("all bounds are required finite.")
+
+        self.optimizer = optimizer
+        self.random_start = random_start
+        self.random_state = random_state
+        self.wait_iter = wait_iter
+        self.eval_budget = eval_budget
+
+        self.noise_var = np.atleast_1d(nugget) if nugget else 0
+        self.noise_estim = True if noise_estim else False
+        self.noisy = True if self.noise_var or self.noise_estim else False
+        if not self.noisy:
+            self.estimation_mode = "noiseless"
+        elif self.noise_estim:
+            self.estimation_mode = "noise_estim"
+        else:
+            self.estimation_mode = "noisy"
+
+        if likelihood not in ("concentrated", "restricted"):
+            raise AssertionError(likelihood)
+        self.likelihood = likelihood
+
+        if isinstance(self.mean, BasisExpansionTrend):
+            self.mean_type = "basis_expansion"
+            self.estimate_trend = True if self.mean.beta is None else False
+        else:
+            raise NotImplementedError("mipego_b200 supports BasisExpansionTrend means only")
+
+        # ---- B200 path ------------------------------------------------------------------
+        self.device = device
+        self.restart_mode = restart_mode
+        self._h = None
+        self._host_state = None   # set by __setstate__, uploaded lazily
+        self._cache = {}
+        self._check_supported()
+
+    # ------------------------------------------------------------------------------------
+    def _check_supported(self):
+        if callable(self.corr) or self.corr not in self._correlation_types:
+            raise NotImplementedError(
+                "corr=%r: the CUDA path implements %s" % (self.corr, self._correlation_types))
+        if not isinstance(self.mean, constant_trend):
+            raise NotImplementedError("only constant_trend is implemented by the CUDA path")
+        if self.likelihood != "concentrated":
+            raise NotImplementedError("likelihood='restricted' is not implemented by the CUDA path")
+        if self.estimation_mode == "noise_estim":
+            raise NotImplementedError("noise_estim=True is not implemented by the CUDA path")
+        if self.optimizer not in self._optimizer_types:
+            raise ValueError("optimizer should be one of %s" % self._optimizer_types)
+
+    def _handle(self):
+        if self._h is None:
+            self._h = _cabi.Handle(self.device)
+        return self._h
+
+    def _check_params(self):
+        # gpr.py:1103-1149 (the parts that can fail)
+        lth = self.theta0.size
+        if self.thetaL is not None and self.thetaU is not None:
+            if self.thetaL.size != lth or self.thetaU.size != lth:
+                raise ValueError("theta0, thetaL and thetaU must have the same length.")
+            if np.any(self.thetaL <= 0) or np.any(self.thetaU < self.thetaL):
+                raise ValueError("The bounds must satisfy O < thetaL <= thetaU.")
+        self.verbose = bool(self.verbose)
+        self.random_start = int(self.random_start)
+
+    def _check_data(self, X, y):
+        # gpr.py:263-288
+        X = _check_array(X)
+        y = np.asarray(y)
+        if y.dtype == object:
+            y = np.array(y.tolist(), dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+        if y.shape[0] != X.shape[0]:
+            raise ValueError("Found input variables with inconsistent numbers of samples: [%d, %d]"
+                             % (X.shape[0], y.shape[0]))
+        if not np.isfinite(y).all():
+            raise ValueError("Input y contains NaN or infinity.")
+        self.X, self.y = X, y.reshape(-1, 1)
+        self._check_params()
+        n, d = X.shape
+        if self.theta0.size not in (d,):
+            raise ValueError("the CUDA path needs one theta per feature (anisotropic): "
+                             "len(theta0)=%d, n_features=%d" % (self.theta0.size, d))
+        h = self._handle()
+        beta0 = 0.0 if self.estimate_trend else float(np.ravel(self.mean.beta)[0])
+        rc = h.lib.mgp_set_train(h.h, n, d, _cabi.dptr(X), _cabi.dptr(y), _cabi.CORR[self.corr],
+                                 1 if self.estimate_trend else 0, beta0)
+        if rc == _cabi.MGP_EINVAL and b"duplicate rows" in h.lib.mgp_last_error(h.h):
+            raise Exception("Multiple input features cannot have the same target value.")
+        h.check(rc)
+        self._cache = {}
+        self._host_state = None
+        if self.estimate_trend:
+            self.F = np.ones((n, 1))
+
+    # ------------------------------------------------------------------------------------
+    # likelihood
+    # ------------------------------------------------------------------------------------
+    def _mode_nv(self):
+        mode = _cabi.MODE[self.estimation_mode]
+        nv = float(np.ravel(self.noise_var)[0]) if self.estimation_mode == "noisy" else 0.0
+        return mode, nv
+
+    def log_likelihood_batch(self, params, eval_grad=True):
+        """(B, n_par) raw parameters -> llf (B,), grad (B, n_par), status (B,) in one launch
+        sequence (the batched form of gpr.py:798-946)."""
+        h = self._handle()
+        P = _cabi.as_f64(params)
+        P = P.reshape(1, -1) if P.ndim == 1 else P
+        B, n_par = P.shape
+        mode, nv = self._mode_nv()
+        llf = np.empty(B)
+        grad = np.zeros((B, n_par)) if eval_grad else None
+        status = np.zeros(B, dtype=np.int32)
+        h.check(h.lib.mgp_nll_batch(h.h, B, _cabi.dptr(P), n_par, mode, nv, 1 if eval_grad else 0,
+                                    _cabi.dptr(llf), _cabi.dptr(grad),
+                                    status.ctypes.data_as(_cabi.c_ip)))
+        return llf, grad, status
+
+    def log_likelihood_concentrated(self, par, env=None, eval_grad=False):
+        """Single-vector form with the reference's return types (gpr.py:798-946)."""
+        par = np.asarray(par, dtype=np.float64).ravel()
+        llf, grad, status = self.log_likelihood_batch(par, eval_grad=eval_grad)
+        if env is not None and status[0] <= 0:
+            self._finalize(par)
+            env.update(sigma2=self.sigma2, noise_var=self.noise_var, rho=self.rho, Yt=self.Yt,
+                       C=self.C, Ft=self.Ft, G=self.G, Q=self.Q)
+        if eval_grad:
+            return float(llf[0]), grad[0].reshape(-1, 1)
+        return float(llf[0])
+
+    def _hyperparameter_bound(self, par_list):
+        # gpr.py:948-962
+        bounds = []
+        for name in par_list:
+            if name == "theta":
+                bounds.append(np.c_[self.thetaL, self.thetaU])
+            elif name == "sigma2":
+                bounds.append(np.atleast_2d([1e-5, self.y.std() ** 2]))
+        return np.concatenate(bounds, axis=0)
+
+    def _optimize_hyperparameter(self):
+        # gpr.py:964-1101
+        par_list = ["theta"]
+        if self.estimation_mode == "noisy":
+            par_list += ["sigma2"]
+        bounds = self._hyperparameter_bound(par_list)
+        log10bounds = log10(bounds)
+        n_theta = len(self.thetaL)
+        if hasattr(self, "theta_"):
+            log10theta0 = log10(self.theta_)
+        else:
+            log10theta0 = log10(self.theta0)
+        if self.estimation_mode == "noiseless":
+            log10param = log10theta0
+        else:
+            log10param = np.r_[log10theta0, np.random.uniform(log10bounds[n_theta:, 0],
+                                                               log10bounds[n_theta:, 1])]
+        n_par = len(log10param)
+        eval_budget = 200 * n_par if self.eval_budget is None else self.eval_budget
+        # restart points are drawn exactly as the sequential loop would (gpr.py:1035-1036)
+        starts = [log10param]
+        for _ in range(1, self.random_start):
+            starts.append(np.random.uniform(log10bounds[:, 0], log10bounds[:, 1]))
+
+        def batch_fn(P):
+            llf, grad, _ = self.log_likelihood_batch(10.0 ** P, eval_grad=True)
+            return -llf, -grad
+
+        param_opt, llf_opt, n_evals, infos = multistart_lbfgsb(
+            batch_fn, np.array(starts), log10bounds, eval_budget, self.wait_iter,
+            mode=self.restart_mode)
+        self.eval_count = n_evals
+        self.opt_info_ = infos
+        optimal_param = 10.0 ** param_opt
+        llf = self._finalize(optimal_param)
+        param = {"theta": optimal_param[:n_theta]}
+        if self.estimation_mode == "noisy":
+            param["sigma2"] = optimal_param[n_theta:n_theta + 1]
+        return param, llf
+
+    def _finalize(self, par):
+        """mgp_finalize_fit: the env-harvesting final likelihood call (gpr.py:1087-1101)."""
+        h = self._handle()
+        par = _cabi.as_f64(par).ravel()
+        mode, nv = self._mode_nv()
+        out = ctypes.c_double(0.0)
+        rc = h.lib.mgp_finalize_fit(h.h, _cabi.dptr(par), par.size, mode, nv, ctypes.byref(out))
+        if rc == _cabi.MGP_ENOTPD:
+            return -np.inf
+        h.check(rc)
+        self._cache = {}
+        self._host_state = None
+        sc = np.zeros(4)
+        h.check(h.lib.mgp_get_state(h.h, None, None, None, None, None, None, _cabi.dptr(sc)))
+        # types follow SURVEY Q10: sigma2 is a (1,) array (noiseless) or a numpy scalar (noisy)
+        self.sigma2 = np.array([sc[0]]) if self.estimation_mode == "noiseless" else np.float64(sc[0])
+        if self.estimate_trend:
+            self.mean.beta = np.array([[sc[1]]])
+        self._par_fitted = par.copy()
+        return float(out.value)
+
+    # ------------------------------------------------------------------------------------
+    def fit(self, X, y):
+        """gpr.py:328-385."""
+        self._check_data(X, y)
+        self.is_fitted = False
+        self.par, llf = self._optimize_hyperparameter()
+        if np.isinf(llf):
+            # gpr.py:359-366
+            print("Doubling theta upper bound. Increasing nugget...")
+            self.thetaU = self.thetaU * 2
+            self.noise_var = self.noise_var * 10
+            self.par, llf = self._optimize_hyperparameter()
+        if not self._fitted_on_device():
+            raise np.linalg.LinAlgError("GP fit failed: correlation matrix is not positive definite")
+        self.log_likelihood_ = llf if self.estimation_mode == "noiseless" else np.array([llf])
+        self.theta_ = self.par["theta"]
+        self.is_fitted = True
+        return self
+
+    def _fitted_on_device(self):
+        h = self._handle()
+        sc = np.zeros(4)
+        return h.lib.mgp_get_state(h.h, None, None, None, None, None, None, _cabi.dptr(sc)) == 0
+
+    def update(self, X, y):
+        self.fit(X, y)
+        return self
+
+    def set_fitted_state(self, X, y, theta, L, gamma, sigma2, beta):
+        """Adopt an externally fitted model (mgp_set_state): used by un-pickling and by the
+        parity tests to give the reference and the CUDA path the identical model."""
+        X = _check_array(X)
+        y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+        self.X, self.y = X, y.reshape(-1, 1)
+        n, d = X.shape
+        h = self._handle()
+        beta0 = 0.0 if self.estimate_trend else float(beta)
+        rc = h.lib.mgp_set_train(h.h, n, d, _cabi.dptr(X), _cabi.dptr(y), _cabi.CORR[self.corr],
+                                 1 if self.estimate_trend else 0, beta0)
+        if rc == _cabi.MGP_EINVAL and b"duplicate rows" in h.lib.mgp_last_error(h.h):
+            raise Exception("Multiple input features cannot have the same target value.")
+        h.check(rc)
+        theta = _cabi.as_f64(theta).ravel()
+        Lc = _cabi.as_f64(L, (n, n))
+        g = _cabi.as_f64(gamma).ravel()
+        h.check(h.lib.mgp_set_state(h.h, _cabi.dptr(theta), _cabi.dptr(Lc), _cabi.dptr(g),
+                                    float(np.ravel(sigma2)[0]), float(beta)))
+        self._cache = {}
+        self._host_state = None
+        self.theta_ = theta.copy()
+        self.par = {"theta": self.theta_}
+        self.sigma2 = np.array([float(np.ravel(sigma2)[0])]) if self.estimation_mode == "noiseless" \
+            else np.float64(np.ravel(sigma2)[0])
+        if self.estimate_trend:
+            self.mean.beta = np.array([[float(beta)]])
+            self.F = np.ones((n, 1))
+        self.is_fitted = True
+        return self
+
+    # ---- fitted arrays, fetched from the device on first access ---------------------------
+    def _state(self, key):
+        if self._host_state is not None and key in self._host_state:
+            return self._host_state[key]
+        if key not in self._cache:
+            h = self._handle()
+            n, d = self.X.shape
+            bufs = dict(theta=np.empty(d), L=np.empty((n, n)), gamma=np.empty(n), rho=np.empty(n),
+                        Yt=np.empty(n), Ft=np.empty(n), sc=np.empty(4))
+            h.check(h.lib.mgp_get_state(h.h, *[_cabi.dptr(bufs[k]) for k in
+                                               ("theta", "L", "gamma", "rho", "Yt", "Ft", "sc")]))
+            self._cache = bufs
+        return self._cache[key]
+
+    @property
+    def C(self):
+        return self._state("L")
+
+    @property
+    def gamma(self):
+        return self._state("gamma").reshape(-1, 1)
+
+    @property
+    def rho(self):
+        return self._state("rho").reshape(-1, 1)
+
+    @property
+    def Yt(self):
+        return self._state("Yt").reshape(-1, 1)
+
+    @property
+    def Ft(self):
+        return self._state("Ft").reshape(-1, 1) if self.estimate_trend else None
+
+    @property
+    def G(self):
+        return np.array([[self._state("sc")[2]]]) if self.estimate_trend else None
+
+    @property
+    def Q(self):
+        return self.Ft / self._state("sc")[2] if self.estimate_trend else None
+
+    # ------------------------------------------------------------------------------------
+    # posterior
+    # ------------------------------------------------------------------------------------
+    def _ensure_device_state(self):
+        """Re-upload after un-pickling (the device handle is not part of the pickle)."""
+        if self._host_state is not None:
+            st = self._host_state
+            self._host_state = None
+            self.set_fitted_state(st["X"], st["y"], st["theta"], st["L"], st["gamma"],
+                                  st["sigma2"], st["beta"])
+
+    def predict(self, X, eval_MSE=False, batch_size=None):
+        """gpr.py:392-483.  `batch_size` is accepted and ignored: the reference's chunking
+        branch is broken on Python 3 and chunking happens on the device here."""
+        assert hasattr(self, "X")
+        X = _check_array(X)
+        n_eval, nf = X.shape
+        if nf != self.X.shape[1]:
+            raise ValueError(("The number of features in X (X.shape[1] = %d) should match the "
+                              "number of features used for fit() which is %d.")
+                             % (nf, self.X.shape[1]))
+        self._ensure_device_state()
+        h = self._handle()
+        y = np.empty(n_eval)
+        mse = np.empty(n_eval) if eval_MSE else None
+        h.check(h.lib.mgp_predict(h.h, n_eval, _cabi.dptr(X), _cabi.dptr(y), _cabi.dptr(mse)))
+        return (y, mse) if eval_MSE else y
+
+    def gradient(self, x):
+        """gpr.py:511-554: single point; returns ((d,1) mean_dx, (d,1) mse_dx)."""
+        x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        if x.shape[1] != self.X.shape[1]:
+            raise Exception("x does not have the right size!")
+        if x.shape[0] != 1:
+            raise Exception("x must be a vector!")
+        a, b = self.gradient_batch(x)
+        return a.T, b.T
+
+    def gradient_batch(self, X):
+        """Row-wise gradient for (m, d) candidates: mean_dx (m, d), mse_dx (m, d)."""
+        X = _check_array(np.atleast_2d(X))
+        self._ensure_device_state()
+        h = self._handle()
+        m, d = X.shape
+        a, b = np.empty((m, d)), np.empty((m, d))
+        h.check(h.lib.mgp_gradient(h.h, m, _cabi.dptr(X), _cabi.dptr(a), _cabi.dptr(b)))
+        return a, b
+
+    # ------------------------------------------------------------------------------------
+    # pickling (base.py:575-608 saves the optimiser with dill; joblib ships models to workers)
+    # ------------------------------------------------------------------------------------
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        host = None
+        if self.is_fitted:
+            if self._host_state is not None:
+                host = self._host_state
+            else:
+                host = dict(X=self.X, y=self.y.ravel(), theta=np.array(self._state("theta")),
+                            L=np.array(self._state("L")), gamma=np.array(self._state("gamma")),
+                            rho=np.array(self._state("rho")), Yt=np.array(self._state("Yt")),
+                            Ft=np.array(self._state("Ft")), sc=np.array(self._state("sc")),
+                            sigma2=float(np.ravel(self.sigma2)[0]),
+                            beta=float(np.ravel(self.mean.beta)[0]))
+        st["_h"] = None
+        st["_cache"] = {}
+        st["_host_state"] = host
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)

@@ -1,0 +1,360 @@
+"""Parity of the CUDA path (through the C ABI / drop-in classes) against the golden fixtures
+produced by the reference itself and against the numpy oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): relative 1e-9 on the posterior mean, 1e-7 on MSE,
+acquisition values and gradients, on well-conditioned models (nugget >= 1e-6), each with an
+absolute floor scaled by the natural magnitude (sigma2 for the MSE, max |value| for the others).
+With nugget 0 the reference's own formulas evaluated in two orders differ by 4e-9 (mean) /
+7e-8 (EI): those fixtures are gated at 1e-6 / 2e-5.
+"""
+import numpy as np
+import pytest
+
+from golden_util import FIXED, FITS, load, mode_of, beta_of
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import mipego_b200 as mb
+    from oracle import gp_oracle as O
+    return mb, O
+
+
+def tol(g, tight, loose):
+    return tight if float(g["nugget"]) > 0 else loose
+
+
+def make_gp(mb, g, fitted=True):
+    d = g["X"].shape[1]
+    beta = None if g["estimate_trend"] else float(g["beta_in"])
+    nug = float(g["nugget"])
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=beta), corr=g["kind"],
+                            theta0=g["theta"] if "theta" in g else g["theta0"],
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d),
+                            nugget=nug if nug > 0 else 0)
+    if fitted:
+        gp.set_fitted_state(g["X"], g["y"], g["theta"], g["L"], g["gamma"], float(g["sigma2"]),
+                            float(g["beta"]))
+    return gp
+
+
+SEMAT = [n for n in FIXED if "absexp" not in n]
+
+
+@pytest.mark.parametrize("name", SEMAT)
+def test_predict_golden(name):
+    mb, O = _mods()
+    g = load(name)
+    gp = make_gp(mb, g)
+    mean, mse = gp.predict(g["Xs"], eval_MSE=True)
+    assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-3)) < tol(g, 1e-9, 1e-6)
+    s2 = float(g["sigma2"])
+    assert np.max(np.abs(mse - g["mse"]) / (np.abs(g["mse"]) + 1e-6 * s2)) < tol(g, 1e-7, 1e-5)
+    only_mean = gp.predict(g["Xs"])
+    assert np.array_equal(only_mean, mean)
+
+
+@pytest.mark.parametrize("name", SEMAT)
+def test_gradient_golden(name):
+    mb, O = _mods()
+    g = load(name)
+    gp = make_gp(mb, g)
+    mdx, sdx = gp.gradient_batch(g["Xs"])
+    sc1, sc2 = np.abs(g["mean_dx"]).max(), np.abs(g["mse_dx"]).max()
+    assert np.max(np.abs(mdx - g["mean_dx"])) < tol(g, 1e-9, 1e-6) * sc1
+    assert np.max(np.abs(sdx - g["mse_dx"])) < tol(g, 1e-7, 1e-5) * sc2
+    a, b = gp.gradient(g["Xs"][4])
+    assert a.shape == (g["X"].shape[1], 1) and b.shape == a.shape
+    assert np.allclose(a.ravel(), mdx[4], rtol=0, atol=1e-12 * sc1)
+
+
+@pytest.mark.parametrize("name", SEMAT)
+@pytest.mark.parametrize("crit", ["EI", "PI", "UCB", "MGFI"])
+@pytest.mark.parametrize("minimize", [True, False])
+def test_acquisition_golden(name, crit, minimize):
+    mb, O = _mods()
+    g = load(name)
+    gp = make_gp(mb, g)
+    tag = "min" if minimize else "max"
+    plugin = float(g["plugin_" + tag])
+    if crit == "EI":
+        c = mb.EI(model=gp, minimize=minimize, plugin=plugin)
+    elif crit == "PI":
+        c = mb.EpsilonPI(model=gp, minimize=minimize, plugin=plugin, epsilon=float(g["param_PI"]))
+    elif crit == "UCB":
+        c = mb.UCB(model=gp, minimize=minimize, alpha=float(g["param_UCB"]))
+    else:
+        c = mb.MGFI(model=gp, minimize=minimize, plugin=plugin, t=float(g["param_MGFI"]))
+    val, dx = c(g["Xs"], return_dx=True)
+    ref_v, ref_dx = g["%s_%s" % (crit, tag)], g["%s_%s_dx" % (crit, tag)]
+    fin = np.isfinite(ref_v) & np.all(np.isfinite(ref_dx), axis=1)
+    noise = g["mse"] < 1e-10 * float(g["sigma2"])   # nugget-0 training points: cancellation noise
+    if crit == "EI":
+        assert np.all(val[noise] == 0.0)
+    fin &= ~noise
+    vs = np.abs(ref_v[fin]).max() + 1e-300
+    assert np.max(np.abs(val[fin] - ref_v[fin]) / (np.abs(ref_v[fin]) + 1e-6 * vs)) < tol(g, 1e-7, 2e-5)
+    rows = np.arange(len(ref_v))
+    easy = fin & (rows >= 3)
+    ds = np.abs(ref_dx[easy]).max() + 1e-300
+    assert np.max(np.abs(dx[easy] - ref_dx[easy])) < tol(g, 1e-7, 2e-5) * ds
+    # the reference's single-point protocol and return types
+    v1 = c(g["Xs"][5])
+    v2, d2 = c(g["Xs"][5], return_dx=True)
+    if crit == "PI":
+        assert isinstance(v1, np.ndarray) and v1.shape == (1,)
+    else:
+        assert isinstance(v1, float)
+    assert d2.shape == (g["X"].shape[1], 1)
+    assert float(np.ravel(v1)[0]) == val[5] and float(np.ravel(v2)[0]) == val[5]
+
+
+@pytest.mark.parametrize("name", SEMAT)
+def test_likelihood_golden(name):
+    mb, O = _mods()
+    g = load(name)
+    gp = make_gp(mb, g, fitted=False)
+    gp._check_data(g["X"], g["y"])
+    par = g["par"]
+    rng = np.random.default_rng(5)
+    P = np.vstack([par] + [par * rng.uniform(0.5, 2.0, par.size) for _ in range(4)])
+    llf, grad, status = gp.log_likelihood_batch(P, eval_grad=True)
+    assert abs(llf[0] - float(g["llf"])) <= 1e-9 * abs(float(g["llf"]))
+    gs = np.abs(g["llf_grad"]).max()
+    assert np.max(np.abs(grad[0] - g["llf_grad"])) <= tol(g, 1e-7, 1e-6) * gs
+    for b in range(1, 5):
+        ref = O.log_likelihood_concentrated(g["X"], g["y"], P[b], g["kind"], g["estimate_trend"],
+                                            beta_of(g), mode_of(g), float(g["nugget"]), eval_grad=True)
+        if np.isinf(ref[0]):
+            assert np.isinf(llf[b]) and status[b] != 0 and np.all(grad[b] == 0)
+            continue
+        assert status[b] == 0
+        assert abs(llf[b] - ref[0]) <= 1e-9 * abs(ref[0])
+        assert np.max(np.abs(grad[b] - ref[1].ravel())) <= tol(g, 1e-7, 1e-6) * np.abs(ref[1]).max()
+    # the fitted state harvested on the device
+    llf1 = gp.log_likelihood_concentrated(par, env={})
+    assert abs(llf1 - float(g["llf_env"])) <= 1e-9 * abs(float(g["llf_env"]))
+    assert np.allclose(gp.C, g["L"], rtol=0, atol=1e-11)
+    assert abs(float(np.ravel(gp.sigma2)[0]) - float(g["sigma2"])) <= 1e-10 * float(g["sigma2"])
+    assert abs(float(np.ravel(gp.mean.beta)[0]) - float(g["beta"])) <= 1e-8 * max(1.0, abs(float(g["beta"])))
+    assert np.max(np.abs(gp.gamma - g["gamma"])) <= tol(g, 1e-8, 1e-6) * np.abs(g["gamma"]).max()
+    assert np.max(np.abs(gp.rho - g["rho"])) <= tol(g, 1e-9, 1e-7) * np.abs(g["rho"]).max()
+    if g["estimate_trend"]:
+        assert np.max(np.abs(gp.Ft - g["Ft"])) <= 1e-9 * np.abs(g["Ft"]).max()
+        assert abs(float(gp.G[0, 0]) - float(g["G"][0, 0])) <= 1e-10 * abs(float(g["G"][0, 0]))
+
+
+def test_not_positive_definite_and_positive_llf_status():
+    mb, O = _mods()
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (60, 2))
+    y = (X ** 2).sum(1)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(2, beta=None), corr="squared_exponential",
+                            theta0=[1e-8, 1e-8], thetaL=[1e-10] * 2, thetaU=[10] * 2, nugget=0)
+    gp._check_data(X, y)
+    llf, grad, status = gp.log_likelihood_batch(np.array([[1e-9, 1e-9], [5.0, 5.0]]))
+    ref0 = O.log_likelihood_concentrated(X, y, [1e-9, 1e-9], eval_grad=True)
+    assert np.isinf(ref0[0]) and np.isinf(llf[0]) and status[0] != 0 and np.all(grad[0] == 0)
+    ref1 = O.log_likelihood_concentrated(X, y, [5.0, 5.0], eval_grad=True)
+    assert status[1] == 0 and abs(llf[1] - ref1[0]) <= 1e-9 * abs(ref1[0])
+
+
+def test_c1_example_config():
+    """BASELINE config 1 (n=50, d=2, EI) against the reference's own per-point outputs."""
+    mb, O = _mods()
+    g = load("c1_example")
+    gp = mb.GaussianProcess(mean=mb.constant_trend(2, beta=None), corr="squared_exponential",
+                            theta0=g["theta_"], thetaL=[1e-9] * 2, thetaU=[100] * 2, nugget=0)
+    gp.set_fitted_state(g["X"], g["y"], g["theta_"], g["L"], g["gamma"], float(g["sigma2"]), float(g["beta"]))
+    mean, mse = gp.predict(g["Xs"], eval_MSE=True)
+    assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-2)) < 1e-5
+    ei = mb.EI(model=gp, minimize=True)
+    v = ei(g["Xs"])
+    assert np.max(np.abs(v - g["EI"])) < 1e-4 * np.abs(g["EI"]).max()
+
+
+def synth_model(O, n, d, kind, seed, nugget=1e-6, estimate_trend=True):
+    """SURVEY section 8d synthetic model (C2/C3 recipe)."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    y = (y - y.mean()) / y.std()
+    theta = (0.12 / d) * rng.uniform(0.5, 1.5, d) * (4.0 if kind == "matern" else 1.0)
+    st = O.fit_state(X, y, np.r_[theta, 0.9], kind, estimate_trend, 0.2, "noisy", nugget)
+    return st
+
+
+@pytest.mark.parametrize("kind,n,d", [("squared_exponential", 500, 10), ("matern", 500, 10),
+                                      ("squared_exponential", 1100, 20)])
+def test_oracle_parity_medium(kind, n, d):
+    """C2-shaped model: full posterior + every criterion against the oracle on 20k candidates."""
+    mb, O = _mods()
+    st = synth_model(O, n, d, kind, seed=10)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr=kind, theta0=st["theta"],
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=1e-6)
+    gp.set_fitted_state(st["X"], st["y"], st["theta"], st["L"], st["gamma"], st["sigma2"], st["beta"])
+    m = 20000 if n <= 500 else 3000
+    Xs = np.random.default_rng(11).uniform(-5, 5, (m, d))
+    Xs[:5] = st["X"][:5] + 1e-4
+    mean, mse = gp.predict(Xs, eval_MSE=True)
+    rm, rs = O.predict(st, Xs)
+    assert np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3)) < 1e-9
+    assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-7
+    plugin = float(st["y"].min())
+    for crit, cls, kw, par in (("EI", mb.EI, {}, None), ("PI", mb.EpsilonPI, {"epsilon": 0.01}, 0.01),
+                               ("UCB", mb.UCB, {"alpha": 0.5}, 0.5), ("MGFI", mb.MGFI, {"t": 2.0}, 2.0)):
+        if crit != "UCB":
+            kw = dict(kw, plugin=plugin)
+        c = cls(model=gp, minimize=True, **kw)
+        v = c(Xs)
+        rv = O.acquisition(st, Xs, crit, par, plugin, True)
+        vs = np.abs(rv).max()
+        assert np.max(np.abs(v - rv) / (np.abs(rv) + 1e-6 * vs)) < 1e-7, crit
+    # gradients on a subset
+    sub = Xs[:512]
+    c = mb.EI(model=gp, minimize=True, plugin=plugin)
+    v, dx = c(sub, return_dx=True)
+    rv, rdx = O.acquisition(st, sub, "EI", None, plugin, True, return_dx=True)
+    assert np.max(np.abs(dx - rdx)) < 1e-7 * np.abs(rdx).max()
+    # multi-parameter evaluation shares one posterior pass (ParallelBO, BayesOpt.py:56-101)
+    ts = np.exp(np.log(2) + 0.5 * np.random.default_rng(22).standard_normal(8))
+    mg = mb.MGFI(model=gp, minimize=True, plugin=plugin, t=1.0)
+    V = mg.evaluate(sub, params=ts)
+    for i, t in enumerate(ts):
+        rv = O.acquisition(st, sub, "MGFI", t, plugin, True)
+        assert np.max(np.abs(V[i] - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())) < 1e-7
+    tv, ti = mg.topk(Xs, k=5, params=ts)
+    Vfull = mg.evaluate(Xs, params=ts)
+    for i in range(len(ts)):
+        order = np.lexsort((np.arange(m), -Vfull[i]))[:5]
+        assert np.array_equal(ti[i], order)
+        assert np.array_equal(tv[i], Vfull[i][order])
+
+
+def test_ragged_and_tiny_inputs():
+    mb, O = _mods()
+    st = synth_model(O, 130, 3, "squared_exponential", seed=3)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(3, beta=None), corr="squared_exponential",
+                            theta0=st["theta"], thetaL=1e-5 * np.ones(3), thetaU=100 * np.ones(3), nugget=1e-6)
+    gp.set_fitted_state(st["X"], st["y"], st["theta"], st["L"], st["gamma"], st["sigma2"], st["beta"])
+    rng = np.random.default_rng(1)
+    for m in (1, 7, 127, 128, 129, 1000):
+        Xs = rng.uniform(-5, 5, (m, 3))
+        mean, mse = gp.predict(Xs, eval_MSE=True)
+        rm, rs = O.predict(st, Xs)
+        assert np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3)) < 1e-9
+        assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-7
+    assert gp.predict(np.empty((0, 3))).shape == (0,)
+    with pytest.raises(ValueError):
+        gp.predict(np.zeros((4, 5)))
+    # chunking must not change results
+    gp._handle().set_option("chunk", 256)
+    Xs = rng.uniform(-5, 5, (1000, 3))
+    a = gp.predict(Xs, eval_MSE=True)
+    gp._handle().set_option("chunk", 0)
+    b = gp.predict(Xs, eval_MSE=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_duplicate_rows_and_errors():
+    mb, O = _mods()
+    X = np.random.default_rng(0).uniform(-1, 1, (20, 2))
+    X[7] = X[3]
+    gp = mb.GaussianProcess(mean=mb.constant_trend(2, beta=None), corr="matern", theta0=[0.1, 0.1],
+                            thetaL=[1e-3] * 2, thetaU=[10] * 2)
+    with pytest.raises(Exception, match="Multiple input features"):
+        gp.fit(X, X.sum(1))
+    with pytest.raises(NotImplementedError):
+        mb.GaussianProcess(mean=mb.constant_trend(2), corr="cubic", theta0=[0.1] * 2, thetaL=[1e-3] * 2, thetaU=[1] * 2)
+    with pytest.raises(ValueError):
+        mb.GaussianProcess(mean=mb.constant_trend(2), theta0=[0.1] * 2, thetaL=[1e-3] * 2, thetaU=[np.inf] * 2)
+
+
+@pytest.mark.parametrize("name", FITS)
+def test_fit_against_reference_fit(name):
+    """End-to-end fit(): same starts, same optimiser; the MLE must reach the reference's
+    likelihood (or better) and, when it lands in the same optimum, the same theta."""
+    mb, O = _mods()
+    g = load(name)
+    d = g["X"].shape[1]
+    beta = None if g["estimate_trend"] else float(g["beta_in"])
+    nug = float(g["nugget"])
+    np.random.seed(int(g["seed"]))
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=beta), corr=g["kind"], theta0=g["theta0"],
+                            thetaL=g["thetaL"], thetaU=g["thetaU"], nugget=nug if nug > 0 else 0,
+                            random_start=int(g["random_start"]), restart_mode="sequential")
+    gp.fit(g["X"], g["y"])
+    llf = float(np.ravel(gp.log_likelihood_)[0])
+    assert llf >= float(g["llf"]) - 1e-6 * abs(float(g["llf"]))
+    if abs(llf - float(g["llf"])) <= 1e-7 * abs(float(g["llf"])):
+        assert np.allclose(gp.theta_, g["theta_"], rtol=1e-4)
+        mean, mse = gp.predict(g["Xs"], eval_MSE=True)
+        assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-2)) < 1e-4
+
+
+def test_batched_restarts_and_pickle():
+    mb, O = _mods()
+    import pickle
+    rng = np.random.default_rng(4)
+    n, d = 90, 3
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + rng.normal(0, 0.1, n)
+    y = (y - y.mean()) / y.std()
+    kw = dict(corr="matern", theta0=[0.05] * d, thetaL=[1e-4] * d, thetaU=[10] * d, nugget=1e-4, random_start=6)
+    np.random.seed(3)
+    g1 = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), restart_mode="sequential", **kw).fit(X, y)
+    np.random.seed(3)
+    g2 = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), restart_mode="batched", **kw).fit(X, y)
+    l1, l2 = float(np.ravel(g1.log_likelihood_)[0]), float(np.ravel(g2.log_likelihood_)[0])
+    assert l2 >= l1 - 1e-8 * abs(l1)
+    # the model the oracle builds from the fitted parameters predicts the same
+    par = np.r_[g2.theta_, float(np.ravel(g2.par["sigma2"])[0])]
+    st = O.fit_state(X, y, par, "matern", True, 0.0, "noisy", 1e-4)
+    Xs = rng.uniform(-5, 5, (300, d))
+    rm, rs = O.predict(st, Xs)
+    mean, mse = g2.predict(Xs, eval_MSE=True)
+    assert np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3)) < 1e-8
+    assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-6
+    g3 = pickle.loads(pickle.dumps(g2))
+    m3, s3 = g3.predict(Xs, eval_MSE=True)
+    assert np.max(np.abs(m3 - mean)) <= 1e-10 * np.abs(mean).max()
+    ei = mb.EI(model=g3, minimize=True)
+    ei2 = pickle.loads(pickle.dumps(ei))
+    assert np.allclose(ei2(Xs[:10]), ei(Xs[:10]), rtol=1e-9, atol=1e-300)
+
+
+def test_bo_shaped_loop():
+    """The call pattern of the reference's BO loop (base.py:375-463 + optimizer/utils.py:25-52):
+    fit, then L-BFGS-B restarts on criterion(x, return_dx=True), one point per call."""
+    mb, O = _mods()
+    from scipy.optimize import fmin_l_bfgs_b
+    dim, lb, ub = 3, -1.0, 5.0
+    rng = np.random.default_rng(123)
+
+    def fitness(x):
+        return float(np.sum(np.asarray(x) ** 2))
+
+    X = rng.uniform(lb, ub, (8, dim))
+    y = np.array([fitness(x) for x in X])
+    thetaL, thetaU = 1e-10 * (ub - lb) * np.ones(dim), 10 * (ub - lb) * np.ones(dim)
+    np.random.seed(123)
+    model = mb.GaussianProcess(mean=mb.constant_trend(dim, beta=None), corr="squared_exponential",
+                               theta0=rng.uniform(size=dim) * (thetaU - thetaL) + thetaL, thetaL=thetaL,
+                               thetaU=thetaU, nugget=1e-6, optimizer="BFGS", wait_iter=3, random_start=dim,
+                               likelihood="concentrated", eval_budget=100 * dim)
+    assert hasattr(model, "gradient") and hasattr(mb.EI, "plugin") and not hasattr(mb.UCB, "plugin")
+    for it in range(4):
+        model.fit(X, y)
+        assert model.is_fitted
+        crit = mb.EI(model=model, minimize=True, plugin=float(y.min()))
+        best_x, best_f = None, -np.inf
+        for r in range(3):
+            x0 = rng.uniform(lb, ub, dim)
+            func = lambda x: tuple(map(lambda v: -1.0 * v, crit(x, return_dx=True)))
+            xo, fo, info = fmin_l_bfgs_b(func, x0, pgtol=1e-8, factr=1e6, bounds=[(lb, ub)] * dim, maxfun=60)
+            if -float(fo) > best_f:
+                best_x, best_f = xo, -float(fo)
+        X = np.vstack([X, best_x])
+        y = np.r_[y, fitness(best_x)]
+    assert y.min() <= np.sort(y[:8])[0]
