@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- GP posterior + EI candidates/s on the BASELINE.json configuration C2
+(n=500, d=10, 10^6 synthetic candidates per GPU, squared-exponential kernel, ordinary kriging).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|nll]
+
+A "step" is one pass of the hot path (K1 cross-correlation tiles -> K2c triangular product with
+fused sum of squares -> K3 MSE + EI epilogue -> top-1) over one batch of candidates.
+  value : candidates/s with the candidates already resident in HBM (device-pointer C ABI,
+          CUDA events on the launching stream, L2 flushed between steps), whole job over N ranks;
+  e2e   : the same through the public host API (EI.evaluate on a pinned host array: H2D of the
+          candidates and D2H of the EI values inside the timed region);
+  roofline : the dominant kernel (k_trmm) timed live with CUDA events inside the library,
+          algorithmic FP64 flops / measured DMMA peak;
+  cpu_baseline : the numpy/scipy oracle port of the reference path timed on the host cores on a
+          bounded sample (reported baseline only).
+N > 1 (torchrun): the model is fitted state on rank 0 and broadcast (NCCL), candidates are
+sharded (weak scaling: 10^6 per rank), per-rank top-1 is all-gathered every step.
+`--impl reference` times the reference's CPU algorithm (oracle port; the reference is pure
+Python and /root/reference does not exist on the GPU box) on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_PEAK_FALLBACK_TFLOPS = 37.0  # measured DMMA m8n8k4 peak on this pool (profiles/fp64_peak_r01.json)
+
+WORKLOADS = {
+    # name: (n, d, m per GPU, kernel, criterion, n_sets)
+    "c2": dict(n=500, d=10, m=1_000_000, kind="squared_exponential", crit="EI", sets=1,
+               desc="GP predict+EI d=10 n=500 over 10^6 synthetic candidates per GPU (BASELINE configs[1])"),
+    "c3": dict(n=4096, d=20, m=1_250_000, kind="squared_exponential", crit="MGFI", sets=8,
+               desc="ParallelBO MGFI n_point=8 d=20 n=4096, 1.25x10^6 candidates per GPU (BASELINE configs[2] shard)"),
+}
+
+
+def fp64_peak():
+    p = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+    try:
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["dmma884_sustained_tflops"]), "measured DMMA m8n8k4 (tools/fp64_peak.cu, %s)" % os.path.basename(p)
+    except Exception:
+        return FP64_PEAK_FALLBACK_TFLOPS, "fallback (earlier DMMA measurement on this pool)"
+
+
+def synth_model(n, d, kind, seed=10, nugget=1e-6):
+    """SURVEY section 8d synthetic model; state built by the oracle's likelihood call (setup only)."""
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    y = (y - y.mean()) / y.std()
+    theta = (0.12 / d) * rng.uniform(0.5, 1.5, d) * (4.0 if kind == "matern" else 1.0)
+    return X, y, theta
+
+
+def flops_per_candidate(n, d):
+    return n * n + 3 * n * d + 6 * n  # SURVEY section 8d F_pred
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def cpu_port_rate(n, d, kind, crit, sets, sample, seed=10):
+    """Reference algorithm (oracle port) on the host cores: vectorised predict + acquisition in
+    chunks of 2000 candidates (the best-case CPU path)."""
+    from oracle import gp_oracle as O
+    X, y, theta = synth_model(n, d, kind, seed)
+    st = O.fit_state(X, y, np.r_[theta, 0.9], kind, True, 0.0, "noisy", 1e-6)
+    Xs = np.random.default_rng(seed + 1).uniform(-5, 5, (sample, d))
+    plugin = float(y.min())
+    ts = np.exp(np.log(2) + 0.5 * np.random.default_rng(22).standard_normal(sets))
+    t0 = time.perf_counter()
+    for s in range(0, sample, 2000):
+        xs = Xs[s:s + 2000]
+        if sets == 1:
+            O.acquisition(st, xs, crit, None if crit == "EI" else float(ts[0]), plugin, True)
+        else:
+            # one posterior, `sets` epilogues
+            for t in ts:
+                O.acquisition(st, xs, crit, float(t), plugin, True)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    sample = 40_000 if wl["n"] <= 1000 else 1000
+    rates = []
+    for _ in range(args.warmup):
+        cpu_port_rate(wl["n"], wl["d"], wl["kind"], wl["crit"], wl["sets"], min(sample, 4000))
+    t_all = 0.0
+    for _ in range(args.steps):
+        r, dt = cpu_port_rate(wl["n"], wl["d"], wl["kind"], wl["crit"], wl["sets"], sample)
+        rates.append(r)
+        t_all += dt
+    value = sample * args.steps / t_all
+    cores = blas_threads()
+    line = {
+        "impl": "reference", "metric": "GP posterior+EI candidates/sec", "value": value, "unit": "candidates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "n": wl["n"], "d": wl["d"], "candidates_per_step": sample,
+                   "criterion": wl["crit"], "n_sets": wl["sets"], "kernel": wl["kind"]},
+        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": cores, "kind": "port",
+                         "sample": "%d candidates per step, vectorised predict+%s in chunks of 2000 "
+                                   "(oracle port of gpr.py:392-483 + InfillCriteria.py; numpy/scipy BLAS threads=%d)"
+                                   % (sample, wl["crit"], cores)},
+        "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mipego_b200 as mb
+    from oracle import gp_oracle as O  # model construction (setup) and the cpu_baseline leg only
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mipego_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, d, m, kind = wl["n"], wl["d"], wl["m"], wl["kind"]
+    # ---- model: built once on rank 0, broadcast so that every rank holds bit-identical state ----
+    X, y, theta = synth_model(n, d, kind)
+    if rank == 0:
+        st = O.fit_state(X, y, np.r_[theta, 0.9], kind, True, 0.0, "noisy", 1e-6)
+        pack = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev) for a in
+                (st["L"], st["gamma"].ravel(), np.array([st["sigma2"], st["beta"]]))]
+    else:
+        pack = [torch.empty((n, n), dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.float64, device=dev),
+                torch.empty(2, dtype=torch.float64, device=dev)]
+    if world > 1:
+        for t in pack:
+            dist.broadcast(t, src=0)
+    L, gamma, sc = [t.cpu().numpy() for t in pack]
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr=kind, theta0=theta,
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=1e-6, device=local)
+    gp.set_fitted_state(X, y, theta, L, gamma, float(sc[0]), float(sc[1]))
+    h = gp._handle()
+    if args.chunk:
+        h.set_option("chunk", args.chunk)
+    plugin = float(y.min())
+    ts = np.exp(np.log(2) + 0.5 * np.random.default_rng(22).standard_normal(wl["sets"]))
+    crit = mb.EI(model=gp, minimize=True, plugin=plugin) if wl["crit"] == "EI" else \
+        mb.MGFI(model=gp, minimize=True, plugin=plugin, t=float(ts[0]))
+    params = None if wl["sets"] == 1 else ts
+
+    # ---- candidates: this rank's shard, pinned host copy + resident device copy -----------------
+    rng = np.random.default_rng(11 + rank)
+    Xs_host = torch.from_numpy(rng.uniform(-5, 5, (m, d))).pin_memory()
+    Xs_dev = Xs_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+    topv = torch.empty((wl["sets"], 1), dtype=torch.float64, device=dev)
+    topi = torch.empty((wl["sets"], 1), dtype=torch.int64, device=dev)
+    gathered = [torch.empty((wl["sets"], 2), dtype=torch.float64, device=dev) for _ in range(world)]
+
+    def step():
+        crit.topk_device(Xs_dev, k=1, params=params, out=(topv, topi))
+        if world > 1:
+            mine = torch.cat([topv, (topi + rank * m).to(torch.float64)], dim=1)
+            dist.all_gather(gathered, mine)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events per step, L2 flushed in between ----------------------
+    def timed_pass():
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for k in range(args.steps):
+            flush.zero_()
+            ev[k][0].record()
+            step()
+            ev[k][1].record()
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in ev)
+
+    launches0 = h.counter("launches")
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed_pass()
+    sampler.stop_flag = True
+    launches = h.counter("launches") - launches0
+    # second, separate pass with CUDA events around every kernel launch (inside the library, on the
+    # launching stream): per-kernel durations for the roofline; not used for `value`
+    h.set_option("time_kernels", 1)
+    ms_k = timed_pass()
+    trmm_ns, trmm_calls = h.counter("trmm_ns"), h.counter("trmm_calls")
+    rgen_ns, epi_ns, topk_ns = h.counter("rgen_ns"), h.counter("epilogue_ns"), h.counter("topk_ns")
+    h.set_option("time_kernels", 0)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * m * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: public host API, pinned host candidates in, EI values out, every step ---------------
+    Xs_np = Xs_host.numpy()
+    crit.evaluate(Xs_np[:200000], params=params)  # warm the staging buffers
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        vals = crit.evaluate(Xs_np, params=params)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * m * args.steps / float(t_e.item())
+
+    if rank == 0:
+        # sanity: the timed path reproduces the oracle on a sample (not timed)
+        sub = Xs_np[:2000]
+        rv = O.acquisition(O.fit_state(X, y, np.r_[theta, 0.9], kind, True, 0.0, "noisy", 1e-6), sub, wl["crit"],
+                           None if wl["crit"] == "EI" else float(ts[0]), plugin, True)
+        err = float(np.max(np.abs(vals[0][:2000] - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())))
+        peak, peak_src = fp64_peak()
+        chunk = h.counter("chunk")
+        per_launch_c = m * args.steps / max(1, trmm_calls)
+        flops_per_launch = per_launch_c * float(n) * n       # the n^2 term of F_pred
+        achieved = flops_per_launch / (trmm_ns / max(1, trmm_calls) * 1e-9) / 1e12 if trmm_ns else None
+        line = {
+            "metric": "GP posterior+EI candidates/sec", "value": value, "unit": "candidates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "n": n, "d": d, "candidates_per_step_per_gpu": m,
+                       "criterion": wl["crit"], "n_sets": wl["sets"], "kernel": kind, "chunk": chunk,
+                       "l2": "256 MB buffer written between timed steps (L2 flush)",
+                       "flops_per_candidate_Fpred": flops_per_candidate(n, d),
+                       "sample_max_rel_err_vs_oracle": err},
+            "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": int(m * d * 8),
+                    "d2h_bytes_per_step": int(m * wl["sets"] * 8),
+                    "api": "%s.evaluate(pinned host ndarray) -> host ndarray (mgp_acq)" % wl["crit"]},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "k_trmm<false> (T = L^-1 r, fused sum of squares)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": "FP64 " + peak_src + "; MEASURED_PEAKS.json has no FP64 entry",
+                         "flops_per_launch": flops_per_launch, "launches_timed": int(trmm_calls),
+                         "avg_launch_ms": trmm_ns / max(1, trmm_calls) * 1e-6,
+                         "share_of_step": {"k_rgen": rgen_ns * 1e-6 / ms_k, "k_trmm": trmm_ns * 1e-6 / ms_k,
+                                           "k_epilogue": epi_ns * 1e-6 / ms_k, "k_topk": topk_ns * 1e-6 / ms_k},
+                         "whole_step_frac_of_peak": value / world * flops_per_candidate(n, d) / (peak * 1e12)},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            sample = 100_000 if n <= 1000 else 1000
+            r, dt = cpu_port_rate(n, d, kind, wl["crit"], wl["sets"], sample)
+            line["cpu_baseline"] = {"value": r, "unit": "candidates/s", "cores": blas_threads(), "kind": "port",
+                                    "sample": "%d candidates, vectorised predict+%s in chunks of 2000 "
+                                              "(oracle port, %.1f s)" % (sample, wl["crit"], dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

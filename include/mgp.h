@@ -144,9 +144,12 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
                       int *d_out_status, void *stream);
 
 /* ---- tuning / introspection ------------------------------------------------------------
- * mgp_set_option: "chunk" = candidates per pass of the posterior pipeline (multiple of 128).
- * mgp_get_counter: "launches" = kernels launched by this handle so far;
- * "flops_posterior" etc. are reserved. */
+ * mgp_set_option: "chunk" = candidates per pass of the posterior pipeline (multiple of 128, 0 =
+ * default); "time_kernels" = 1 brackets every posterior kernel launch with CUDA events on the
+ * launching stream (resets the timers).
+ * mgp_get_counter: "launches" = kernels launched by this handle so far; "npad", "chunk",
+ * "sm_count"; with time_kernels: "<k>_ns" / "<k>_calls" for k in rgen, trmm, epilogue, topk
+ * (accumulated device time in nanoseconds; synchronises on the recorded events). */
 int mgp_set_option(mgp_t *h, const char *name, int64_t value);
 int64_t mgp_get_counter(const mgp_t *h, const char *name);
 

@@ -86,6 +86,45 @@ class InfillCriteria(object):
                                    _cabi.dptr(val), idx.ctypes.data_as(_cabi.c_lp)))
         return val, idx
 
+    # ---- device-resident entry points: torch CUDA tensors in, torch CUDA tensors out ----------
+    # (torch is plumbing for device memory and streams only; work is enqueued on torch's current
+    # stream through mgp_acq_dev / mgp_acq_topk_dev and is NOT synchronised)
+    def _dev_args(self, X, params):
+        import torch
+        h = self._handle()
+        if not (X.is_cuda and X.dtype == torch.float64 and X.is_contiguous() and X.dim() == 2):
+            raise ValueError("X must be a contiguous 2-D float64 CUDA tensor")
+        if X.device.index != h.device:
+            raise ValueError("X is on cuda:%d, the model on cuda:%d" % (X.device.index, h.device))
+        if X.shape[1] != self._model.X.shape[1]:
+            raise ValueError("feature count mismatch")
+        P = _cabi.as_f64([self._param()] if params is None else params).ravel()
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        return torch, h, P, stream
+
+    def evaluate_device(self, X, params=None, out=None):
+        torch, h, P, stream = self._dev_args(X, params)
+        m = X.shape[0]
+        if out is None:
+            out = torch.empty((P.size, m), dtype=torch.float64, device=X.device)
+        h.check(h.lib.mgp_acq_dev(h.h, m, X.data_ptr(), _cabi.ACQ[self._kind], P.size, _cabi.dptr(P),
+                                  float(self._plugin_user()), 1 if self.minimize else 0,
+                                  out.data_ptr(), None, stream))
+        return out
+
+    def topk_device(self, X, k=1, params=None, out=None):
+        torch, h, P, stream = self._dev_args(X, params)
+        m = X.shape[0]
+        k = int(min(k, m))
+        if out is None:
+            out = (torch.empty((P.size, k), dtype=torch.float64, device=X.device),
+                   torch.empty((P.size, k), dtype=torch.int64, device=X.device))
+        h.check(h.lib.mgp_acq_topk_dev(h.h, m, X.data_ptr(), _cabi.ACQ[self._kind], P.size,
+                                       _cabi.dptr(P), float(self._plugin_user()),
+                                       1 if self.minimize else 0, k, out[0].data_ptr(),
+                                       out[1].data_ptr(), stream))
+        return out
+
     # ---- the reference's call protocol ---------------------------------------------------------
     def __call__(self, X, return_dx=False, dx=None):
         if dx is not None:  # older spelling (backup/test_acquisition.py:45)

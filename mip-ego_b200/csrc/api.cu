@@ -48,6 +48,33 @@ static void freebuf(DevBuf &b) {
 template <typename T>
 static inline T *P(const DevBuf &b) { return reinterpret_cast<T *>(b.p); }
 
+struct KTimer {
+  mgp_handle *h; cudaStream_t st; int which; cudaEvent_t a = nullptr, b = nullptr;
+  KTimer(mgp_handle *h_, cudaStream_t st_, int which_) : h(h_), st(st_), which(which_) {
+    if (h->time_kernels) {
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, st);
+    }
+  }
+  ~KTimer() {
+    if (a) {
+      cudaEventRecord(b, st);
+      h->ev_pending.push_back({a, b, which});
+    }
+  }
+};
+static void resolve_timers(mgp_handle *h) {
+  for (auto &e : h->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+      h->kernel_ms[e.which] += ms;
+      h->kernel_calls[e.which]++;
+    }
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  h->ev_pending.clear();
+}
+
 #define CHECK_H(h) \
   if (!(h)) return MGP_EINVAL; \
   MGP_CUDA(h, cudaSetDevice((h)->device))
@@ -117,6 +144,12 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
     h->chunk_opt = round_up(value, 128);
     return MGP_OK;
   }
+  if (!strcmp(name, "time_kernels")) {
+    resolve_timers(h);
+    h->time_kernels = value != 0;
+    for (int i = 0; i < 4; i++) { h->kernel_ms[i] = 0; h->kernel_calls[i] = 0; }
+    return MGP_OK;
+  }
   return mgp_fail(h, MGP_EINVAL, "unknown option '%s'", name);
 }
 int64_t mgp_get_counter(const mgp_t *h, const char *name) {
@@ -125,6 +158,14 @@ int64_t mgp_get_counter(const mgp_t *h, const char *name) {
   if (!strcmp(name, "npad")) return h->npad;
   if (!strcmp(name, "chunk")) return h->chunk;
   if (!strcmp(name, "sm_count")) return h->sm_count;
+  static const char *kn[4] = {"rgen", "trmm", "epilogue", "topk"};
+  for (int i = 0; i < 4; i++) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%s_ns", kn[i]);
+    if (!strcmp(name, buf)) { resolve_timers(const_cast<mgp_handle *>(h)); return (int64_t)(h->kernel_ms[i] * 1e6); }
+    snprintf(buf, sizeof(buf), "%s_calls", kn[i]);
+    if (!strcmp(name, buf)) { resolve_timers(const_cast<mgp_handle *>(h)); return h->kernel_calls[i]; }
+  }
   return -1;
 }
 
@@ -325,7 +366,7 @@ static int adopt_slot0(mgp_handle *h, const double *theta_host, bool take_gamma)
   MGP_CUDA(h, cudaMemcpyAsync(h->dtheta.p, th.data(), th.size() * 8, cudaMemcpyHostToDevice, st));
   MGP_CUDA(h, launch_prep_model(P<double>(h->dXc), P<double>(h->dtheta), h->npad, h->dpad,
                                 P<double>(h->dBop), P<double>(h->dan), st));
-  MGP_CUDA(h, launch_pack_tri(P<double>(h->dMinv), h->npad, P<double>(h->dMp), st));
+  MGP_CUDA(h, launch_pack_tri(P<double>(h->dMinv), h->n, h->npad, P<double>(h->dMp), st));
   h->launches += 3;
   MGP_CUDA(h, cudaStreamSynchronize(st));  // th is a host temporary
   h->rinv_ready = false;
@@ -459,7 +500,7 @@ static int ensure_rinv(mgp_handle *h, cudaStream_t st) {
   MGP_TRY(mgp_ensure(h, h->dTmp, mat));
   MGP_TRY(mgp_ensure(h, h->dRinvP, mat));
   MGP_CUDA(h, lauum_blocked(P<double>(h->dMinv), P<double>(h->dTmp), h->npad, 0, 1, st, &h->launches));
-  MGP_CUDA(h, launch_pack_sym(P<double>(h->dTmp), h->npad, P<double>(h->dRinvP), st));
+  MGP_CUDA(h, launch_pack_sym(P<double>(h->dTmp), h->n, h->npad, P<double>(h->dRinvP), st));
   h->launches++;
   h->rinv_ready = true;
   return 0;
@@ -499,13 +540,13 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     rp.an = P<double>(h->dan); rp.gamma = P<double>(h->dgamma); rp.avec = P<double>(h->davec);
     rp.rP = P<double>(h->drP); rp.meanpart = P<double>(h->dmeanpart); rp.ftpart = P<double>(h->dftpart);
     rp.ldp = ldp;
-    MGP_CUDA(h, launch_rgen(rp, h->corr, JS, st));
+    { KTimer t(h, st, 0); MGP_CUDA(h, launch_rgen(rp, h->corr, JS, st)); }
     h->launches++;
     if (!q.want_dx) {
       TrmmParams tp;
       tp.Mp = P<double>(h->dMp); tp.rP = P<double>(h->drP); tp.qpart = P<double>(h->dqpart);
       tp.wP = nullptr; tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 0; tp.ldq = ldp;
-      MGP_CUDA(h, launch_trmm(tp, h->sm_count, st));
+      { KTimer t(h, st, 1); MGP_CUDA(h, launch_trmm(tp, h->sm_count, st)); }
       EpiParams ep;
       ep.qpart = P<double>(h->dqpart); ep.meanpart = P<double>(h->dmeanpart); ep.ftpart = P<double>(h->dftpart);
       ep.NI = h->NI; ep.JS = JS; ep.ld = ldp; ep.mc = mc;
@@ -517,13 +558,13 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       else if (q.d_val) { ep.out_val = q.d_val + c0; ep.ld_val = q.ld_val ? q.ld_val : q.m; }
       ep.kind = q.kind; ep.n_sets = acq ? q.n_sets : 0; ep.minimize = q.minimize; ep.plugin = q.plugin;
       for (int s = 0; s < MGP_MAX_SETS; s++) ep.params[s] = (acq && q.params && s < q.n_sets) ? q.params[s] : 0.0;
-      MGP_CUDA(h, launch_epilogue(ep, st));
+      { KTimer t(h, st, 2); MGP_CUDA(h, launch_epilogue(ep, st)); }
       h->launches += 2;
     } else {
       TrmmParams tp;
       tp.Mp = P<double>(h->dRinvP); tp.rP = P<double>(h->drP); tp.qpart = nullptr;
       tp.wP = P<double>(h->dwP); tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 1; tp.ldq = ldp;
-      MGP_CUDA(h, launch_trmm(tp, h->sm_count, st));
+      { KTimer t(h, st, 1); MGP_CUDA(h, launch_trmm(tp, h->sm_count, st)); }
       GradParams gp;
       gp.Xs = q.d_Xs + c0 * h->d; gp.mc = mc; gp.ldp = ldp; gp.n = h->n; gp.d = h->d; gp.dpad = h->dpad;
       gp.NJ8 = NJ8; gp.Xc = P<double>(h->dXc); gp.center = P<double>(h->dcenter);
@@ -540,12 +581,13 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       gp.ld_val = q.ld_val ? q.ld_val : q.m;
       gp.kind = q.kind; gp.n_sets = acq ? q.n_sets : 0; gp.minimize = q.minimize; gp.plugin = q.plugin;
       for (int s = 0; s < MGP_MAX_SETS; s++) gp.params[s] = (acq && q.params && s < q.n_sets) ? q.params[s] : 0.0;
-      MGP_CUDA(h, launch_grad(gp, h->corr, st));
+      { KTimer t(h, st, 2); MGP_CUDA(h, launch_grad(gp, h->corr, st)); }
       h->launches += 2;
     }
     if (q.topk > 0) {
+      { KTimer t(h, st, 3);
       MGP_CUDA(h, launch_topk_merge(chunk_val, h->chunk, mc, q.idx_base + c0, q.n_sets, q.topk, q.d_topv,
-                                    q.d_topi, c0 == 0 && !q.topk_continue, st));
+                                    q.d_topi, c0 == 0 && !q.topk_continue, st)); }
       h->launches++;
     }
   }

@@ -241,20 +241,24 @@ __global__ void __launch_bounds__(128) k_trmv_t(const double *M, int npad, int64
 
 // ---- slab packing ---------------------------------------------------------------------------
 // slab = 16 row tiles x (8x8 block, row-major) = 1024 doubles; see posterior.cu for the layout.
-__global__ void __launch_bounds__(1024) k_pack_tri(const double *Minv, int npad, double *Mp) {
+__global__ void __launch_bounds__(1024) k_pack_tri(const double *Minv, int n, int npad, double *Mp) {
   const int I = blockIdx.y, j8 = blockIdx.x;
   if (j8 >= 16 * (I + 1)) return;
   const int w = threadIdx.x, i8 = w >> 6, ri = (w >> 3) & 7, kj = w & 7;
   const int64_t slab = (int64_t)8 * I * (I + 1) + j8;
-  Mp[slab * 1024 + w] = Minv[(int64_t)(128 * I + 8 * i8 + ri) * npad + 8 * j8 + kj];
+  const int row = 128 * I + 8 * i8 + ri, col = 8 * j8 + kj;
+  // padded training slots (identity rows of the padded factor) must not contribute
+  Mp[slab * 1024 + w] = (row < n && col < n) ? Minv[(int64_t)row * npad + col] : 0.0;
 }
-__global__ void __launch_bounds__(1024) k_pack_sym(const double *Rinv, int npad, double *Rp) {
+__global__ void __launch_bounds__(1024) k_pack_sym(const double *Rinv, int n, int npad, double *Rp) {
   const int I = blockIdx.y, j8 = blockIdx.x, NJ8 = npad / 8;
   const int w = threadIdx.x, i8 = w >> 6, ri = (w >> 3) & 7, kj = w & 7;
   const int row = 128 * I + 8 * i8 + ri, col = 8 * j8 + kj;
   const int64_t slab = (int64_t)I * NJ8 + j8;
   const bool lower = (col >> 7) <= I;
-  Rp[slab * 1024 + w] = lower ? Rinv[(int64_t)row * npad + col] : Rinv[(int64_t)col * npad + row];
+  double v = lower ? Rinv[(int64_t)row * npad + col] : Rinv[(int64_t)col * npad + row];
+  if (row >= n || col >= n) v = 0.0;
+  Rp[slab * 1024 + w] = v;
 }
 
 }  // namespace
@@ -412,13 +416,13 @@ cudaError_t launch_trmv(const double *M, int npad, int64_t sM, const double *x, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_pack_tri(const double *Minv, int npad, double *Mp, cudaStream_t st) {
+cudaError_t launch_pack_tri(const double *Minv, int n, int npad, double *Mp, cudaStream_t st) {
   const int NI = npad / 128;
-  k_pack_tri<<<dim3(16 * NI, NI), 1024, 0, st>>>(Minv, npad, Mp);
+  k_pack_tri<<<dim3(16 * NI, NI), 1024, 0, st>>>(Minv, n, npad, Mp);
   return cudaGetLastError();
 }
-cudaError_t launch_pack_sym(const double *Rinv, int npad, double *Rp, cudaStream_t st) {
+cudaError_t launch_pack_sym(const double *Rinv, int n, int npad, double *Rp, cudaStream_t st) {
   const int NI = npad / 128;
-  k_pack_sym<<<dim3(npad / 8, NI), 1024, 0, st>>>(Rinv, npad, Rp);
+  k_pack_sym<<<dim3(npad / 8, NI), 1024, 0, st>>>(Rinv, n, npad, Rp);
   return cudaGetLastError();
 }

@@ -48,6 +48,6 @@ cudaError_t launch_trmv(const double *M, int npad, int64_t sM, const double *x, 
                         double *y, int64_t sy, int n, int trans, int batch, cudaStream_t st);
 
 // Pack row-major L^-1 into the slab layout of the posterior kernel (lower block triangle).
-cudaError_t launch_pack_tri(const double *Minv, int npad, double *Mp, cudaStream_t st);
+cudaError_t launch_pack_tri(const double *Minv, int n, int npad, double *Mp, cudaStream_t st);
 // Pack a symmetric matrix given by its lower tiles into the full slab layout (all blocks).
-cudaError_t launch_pack_sym(const double *Rinv, int npad, double *Rp, cudaStream_t st);
+cudaError_t launch_pack_sym(const double *Rinv, int n, int npad, double *Rp, cudaStream_t st);

@@ -22,6 +22,12 @@ struct mgp_handle {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int64_t launches = 0;
+  // optional per-kernel timing (option "time_kernels"): event pairs resolved lazily
+  int time_kernels = 0;
+  struct EvPair { cudaEvent_t a, b; int which; };
+  std::vector<EvPair> ev_pending;
+  double kernel_ms[4] = {0, 0, 0, 0};   // rgen, trmm, epilogue/grad, topk
+  int64_t kernel_calls[4] = {0, 0, 0, 0};
   int sm_count = 148;
 
   // ---- training data -------------------------------------------------------------------

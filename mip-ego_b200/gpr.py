@@ -390,6 +390,35 @@ class GaussianProcess(object):
         h.check(h.lib.mgp_predict(h.h, n_eval, _cabi.dptr(X), _cabi.dptr(y), _cabi.dptr(mse)))
         return (y, mse) if eval_MSE else y
 
+    def predict_device(self, X, eval_MSE=True):
+        """Device-resident predict: X a contiguous float64 CUDA tensor (m, d); returns CUDA tensors.
+        Enqueued on torch's current stream, not synchronised."""
+        import torch
+        self._ensure_device_state()
+        h = self._handle()
+        m = X.shape[0]
+        mean = torch.empty(m, dtype=torch.float64, device=X.device)
+        mse = torch.empty(m, dtype=torch.float64, device=X.device) if eval_MSE else None
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        h.check(h.lib.mgp_predict_dev(h.h, m, X.data_ptr(), mean.data_ptr(),
+                                      mse.data_ptr() if eval_MSE else None, stream))
+        return (mean, mse) if eval_MSE else mean
+
+    def log_likelihood_batch_device(self, params, eval_grad=True):
+        """Device-resident batched likelihood: params a float64 CUDA tensor (B, n_par)."""
+        import torch
+        h = self._handle()
+        B, n_par = params.shape
+        mode, nv = self._mode_nv()
+        llf = torch.empty(B, dtype=torch.float64, device=params.device)
+        grad = torch.zeros((B, n_par), dtype=torch.float64, device=params.device)
+        status = torch.zeros(B, dtype=torch.int32, device=params.device)
+        stream = torch.cuda.current_stream(params.device).cuda_stream
+        h.check(h.lib.mgp_nll_batch_dev(h.h, B, params.data_ptr(), n_par, mode, nv,
+                                        1 if eval_grad else 0, llf.data_ptr(), grad.data_ptr(),
+                                        status.data_ptr(), stream))
+        return llf, grad, status
+
     def gradient(self, x):
         """gpr.py:511-554: single point; returns ((d,1) mean_dx, (d,1) mse_dx)."""
         x = np.atleast_2d(np.asarray(x, dtype=np.float64))
