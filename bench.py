@@ -158,21 +158,152 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def nll_flops(n, d):
+    return float(n) ** 3 + 3.5 * float(n) ** 2 * d  # SURVEY section 8d F_nll (potrf + inverse + contraction)
+
+
+def nll_problem(n, d, B, seed=30):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    y = (y - y.mean()) / y.std()
+    # log10-uniform around the well-conditioned region of SURVEY 8d (theta ~ 0.12/d), plus sigma2
+    theta = (0.12 / d) * 10.0 ** np.random.default_rng(seed + 1).uniform(-0.5, 0.5, (B, d))
+    P = np.c_[theta, np.random.default_rng(seed + 2).uniform(0.5, 1.0, B)]
+    return X, y, P
+
+
+def cpu_nll_rate(n, d, reps):
+    from oracle import gp_oracle as O
+    X, y, P = nll_problem(n, d, max(1, reps))
+    t0 = time.perf_counter()
+    for b in range(reps):
+        O.log_likelihood_concentrated(X, y, P[b], "squared_exponential", True, 0.0, "noisy", 1e-6, eval_grad=True)
+    dt = time.perf_counter() - t0
+    return reps / dt, dt
+
+
+def run_nll(args, rank, world, local):
+    """BASELINE configs[3]: GP hyper-parameter MLE n=4096 d=20, 64 restarts -> 8 NLL+grad per GPU."""
+    n, d, B = args.nll_n, 20, 8
+    desc = "GP NLL+grad n=%d d=%d, %d theta-vectors per GPU per step (BASELINE configs[3]: 64 over 8 GPUs)" % (n, d, B)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        reps = 1
+        r, dt = cpu_nll_rate(n, d, reps)
+        line = {"impl": "reference", "metric": "GP NLL+grad evals/sec", "value": r, "unit": "evals/s",
+                "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "n": n, "d": d, "evals_per_step": reps},
+                "cpu_baseline": {"value": r, "unit": "evals/s", "cores": blas_threads(), "kind": "port",
+                                 "sample": "%d evaluation(s) of log_likelihood_concentrated(eval_grad=True), oracle port" % reps},
+                "e2e": {"value": r, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    import mipego_b200 as mb
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    X, y, P_all = nll_problem(n, d, B * world)
+    P = P_all[rank * B:(rank + 1) * B]
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential",
+                            theta0=P[0, :d], thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=1e-6,
+                            device=local)
+    gp._check_data(X, y)
+    h = gp._handle()
+    P_dev = torch.from_numpy(P).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for _ in range(args.warmup):
+        out = gp.log_likelihood_batch_device(P_dev)
+    barrier()
+    launches0 = h.counter("launches")
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        ev[k][0].record()
+        out = gp.log_likelihood_batch_device(P_dev)
+        if world > 1:
+            g = [torch.empty_like(out[0]) for _ in range(world)]
+            dist.all_gather(g, out[0])
+        ev[k][1].record()
+    barrier()
+    sampler.stop_flag = True
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = h.counter("launches") - launches0
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    value = world * B * args.steps / (float(t_ms.item()) * 1e-3)
+    # e2e: host API (parameters in, llf + grad + status out)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        llf, grad, status = gp.log_likelihood_batch(P)
+    barrier()
+    t_e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e = world * B * args.steps / float(t_e.item())
+    if rank == 0:
+        peak, peak_src = fp64_peak()
+        achieved = value / world * nll_flops(n, d) / 1e12
+        line = {"metric": "GP NLL+grad evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t_ms.item()) / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "n": n, "d": d, "evals_per_step_per_gpu": B, "mode": "noisy nugget 1e-6",
+                           "status": [int(v) for v in status], "llf0": float(llf[0]),
+                           "l2": "working set 4 x %d MB per evaluation exceeds L2" % (n * n * 8 // 2 ** 20)},
+                "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": int(P.nbytes),
+                        "d2h_bytes_per_step": int(llf.nbytes + grad.nbytes + status.nbytes),
+                        "api": "GaussianProcess.log_likelihood_batch(host ndarray) (mgp_nll_batch)"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "tensor", "kernel": "whole step (k_dgemm family: potrf panels/updates, trtri, M^T M)",
+                             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": "FP64 " + peak_src,
+                             "flops_per_eval_Fnll": nll_flops(n, d)},
+                "clocks": sampler.summary()}
+        if not args.no_cpu_baseline and n <= 2048:
+            r, dt = cpu_nll_rate(n, d, 1)
+            line["cpu_baseline"] = {"value": r, "unit": "evals/s", "cores": blas_threads(), "kind": "port",
+                                    "sample": "1 evaluation at the same n (oracle port, %.1f s)" % dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["nll"])
+    ap.add_argument("--nll-n", type=int, default=4096)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "nll":
+        run_nll(args, rank, world, local)
+        return
+    wl = WORKLOADS[args.workload]
 
     if args.impl == "reference":
         run_reference(args, wl, rank, world)

@@ -101,13 +101,15 @@ int mgp_create(int device, mgp_t **out_h) {
   }
   h->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return MGP_ECUDA;
   }
   for (int i = 0; i < 2; i++) {
     cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
   }
   *out_h = h;
   return MGP_OK;
@@ -128,9 +130,11 @@ int mgp_destroy(mgp_t *h) {
     if (h->hpin[i]) cudaFreeHost(h->hpin[i]);
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
   }
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->out_stream) cudaStreamDestroy(h->out_stream);
   delete h;
   return MGP_OK;
 }
@@ -484,7 +488,11 @@ struct PostReq {
 };
 
 static int post_workspace(mgp_handle *h, bool want_dx) {
-  int64_t chunk = h->chunk_opt > 0 ? h->chunk_opt : (int64_t)h->sm_count * 128;
+  // default: four candidate blocks per SM per pass (amortises launch ramps and the small
+  // epilogue / top-k kernels), bounded so that the r scratch stays below 2 GiB
+  int64_t chunk = (int64_t)h->sm_count * 128 * 4;
+  while (chunk > (int64_t)h->sm_count * 128 && (size_t)h->npad * chunk * 8 > ((size_t)2 << 30)) chunk /= 2;
+  if (h->chunk_opt > 0) chunk = h->chunk_opt;
   h->chunk = chunk;
   MGP_TRY(mgp_ensure(h, h->drP, (size_t)h->npad * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dmeanpart, (size_t)h->NI * chunk * 8));
@@ -639,56 +647,72 @@ static int host_run(mgp_handle *h, int64_t m, const double *Xs, PostReq q, const
   const int d = h->d;
   const int ns = std::max(1, q.n_sets);
   MGP_TRY(post_workspace(h, q.want_dx));
-  const int64_t super = std::min<int64_t>(m, h->chunk * 8);
-  for (int i = 0; i < 2; i++) MGP_TRY(mgp_ensure(h, h->dXs_stage[i], (size_t)super * d * 8));
-  // outputs: [mean m][mse m][val ns*m][mean_dx m*d][mse_dx m*d][dx ns*m*d]
-  size_t off = 0;
-  auto take = [&](bool on, size_t cnt) { size_t r = off; if (on) off += cnt; return r; };
-  const size_t o_mean = take(o.mean, m), o_mse = take(o.mse, m), o_val = take(o.val, (size_t)ns * m),
-               o_mdx = take(o.mean_dx, (size_t)m * d), o_sdx = take(o.mse_dx, (size_t)m * d),
-               o_dx = take(o.dx, (size_t)ns * m * d);
-  MGP_TRY(mgp_ensure(h, h->dout_stage[0], std::max<size_t>(off, 1) * 8));
-  double *dout = P<double>(h->dout_stage[0]);
+  // staging unit: two compute chunks; inputs and outputs are double-buffered so that the H2D of
+  // unit i+1 and the D2H of unit i-1 overlap the kernels of unit i (three streams)
+  const int64_t unit = std::min<int64_t>(m, h->chunk * 2);
+  size_t per = 0;  // output doubles per staged candidate
+  if (o.mean) per += 1;
+  if (o.mse) per += 1;
+  if (o.val && q.topk == 0) per += ns;
+  if (o.mean_dx) per += d;
+  if (o.mse_dx) per += d;
+  if (o.dx && q.topk == 0) per += (size_t)ns * d;
+  for (int i = 0; i < 2; i++) {
+    MGP_TRY(mgp_ensure(h, h->dXs_stage[i], (size_t)unit * d * 8));
+    MGP_TRY(mgp_ensure(h, h->dout_stage[i], std::max<size_t>(per * unit, 1) * 8));
+  }
   if (q.topk > 0) {
     MGP_TRY(mgp_ensure(h, h->dtopk_idx, (size_t)ns * q.topk * 16));
     q.d_topi = P<int64_t>(h->dtopk_idx);
     q.d_topv = reinterpret_cast<double *>(q.d_topi + (size_t)ns * q.topk);
   }
-  cudaStream_t st = h->stream, cs = h->copy_stream;
+  cudaStream_t st = h->stream, cs = h->copy_stream, os = h->out_stream;
   int it = 0;
-  for (int64_t s0 = 0; s0 < m; s0 += super, it++) {
-    const int64_t ms = std::min(super, m - s0);
+  for (int64_t s0 = 0; s0 < m; s0 += unit, it++) {
+    const int64_t ms = std::min(unit, m - s0);
     const int buf = it & 1;
-    if (it >= 2) MGP_CUDA(h, cudaStreamWaitEvent(cs, h->ev_done[buf], 0));
+    if (it >= 2) MGP_CUDA(h, cudaStreamWaitEvent(cs, h->ev_done[buf], 0));   // input buffer free
     MGP_CUDA(h, cudaMemcpyAsync(h->dXs_stage[buf].p, Xs + s0 * d, (size_t)ms * d * 8, cudaMemcpyHostToDevice, cs));
     MGP_CUDA(h, cudaEventRecord(h->ev_in[buf], cs));
     MGP_CUDA(h, cudaStreamWaitEvent(st, h->ev_in[buf], 0));
+    if (it >= 2) MGP_CUDA(h, cudaStreamWaitEvent(st, h->ev_out[buf], 0));    // output buffer drained
+    double *dout = P<double>(h->dout_stage[buf]);
+    size_t off = 0;
+    auto take = [&](bool on, size_t cnt) { double *r = on ? dout + off : nullptr; if (on) off += cnt; return r; };
     PostReq r = q;
     r.m = ms; r.d_Xs = P<double>(h->dXs_stage[buf]);
-    r.d_mean = o.mean ? dout + o_mean + s0 : nullptr;
-    r.d_mse = o.mse ? dout + o_mse + s0 : nullptr;
-    r.d_mean_dx = o.mean_dx ? dout + o_mdx + s0 * d : nullptr;
-    r.d_mse_dx = o.mse_dx ? dout + o_sdx + s0 * d : nullptr;
-    r.d_val = o.val && q.topk == 0 ? dout + o_val + s0 : nullptr;
-    r.d_dx = o.dx && q.topk == 0 ? dout + o_dx + s0 * d : nullptr;
-    r.ld_val = m;
+    r.d_mean = take(o.mean, ms);
+    r.d_mse = take(o.mse, ms);
+    r.d_val = take(o.val && q.topk == 0, (size_t)ns * ms);
+    r.d_mean_dx = take(o.mean_dx, (size_t)ms * d);
+    r.d_mse_dx = take(o.mse_dx, (size_t)ms * d);
+    r.d_dx = take(o.dx && q.topk == 0, (size_t)ns * ms * d);
+    r.ld_val = ms;
     r.idx_base = s0;
     r.topk_continue = it > 0;
     MGP_TRY(posterior_run(h, r, st));
     MGP_CUDA(h, cudaEventRecord(h->ev_done[buf], st));
+    if (per > 0) {
+      MGP_CUDA(h, cudaStreamWaitEvent(os, h->ev_done[buf], 0));
+      if (r.d_mean) MGP_CUDA(h, cudaMemcpyAsync(o.mean + s0, r.d_mean, (size_t)ms * 8, cudaMemcpyDeviceToHost, os));
+      if (r.d_mse) MGP_CUDA(h, cudaMemcpyAsync(o.mse + s0, r.d_mse, (size_t)ms * 8, cudaMemcpyDeviceToHost, os));
+      if (r.d_val)
+        MGP_CUDA(h, cudaMemcpy2DAsync(o.val + s0, (size_t)m * 8, r.d_val, (size_t)ms * 8, (size_t)ms * 8, ns,
+                                      cudaMemcpyDeviceToHost, os));
+      if (r.d_mean_dx) MGP_CUDA(h, cudaMemcpyAsync(o.mean_dx + s0 * d, r.d_mean_dx, (size_t)ms * d * 8, cudaMemcpyDeviceToHost, os));
+      if (r.d_mse_dx) MGP_CUDA(h, cudaMemcpyAsync(o.mse_dx + s0 * d, r.d_mse_dx, (size_t)ms * d * 8, cudaMemcpyDeviceToHost, os));
+      if (r.d_dx)
+        MGP_CUDA(h, cudaMemcpy2DAsync(o.dx + s0 * d, (size_t)m * d * 8, r.d_dx, (size_t)ms * d * 8, (size_t)ms * d * 8, ns,
+                                      cudaMemcpyDeviceToHost, os));
+      MGP_CUDA(h, cudaEventRecord(h->ev_out[buf], os));
+    }
   }
   if (q.topk > 0) {
     MGP_CUDA(h, cudaMemcpyAsync(o.val, q.d_topv, (size_t)ns * q.topk * 8, cudaMemcpyDeviceToHost, st));
     MGP_CUDA(h, cudaMemcpyAsync(reinterpret_cast<int64_t *>(o.dx), q.d_topi, (size_t)ns * q.topk * 8, cudaMemcpyDeviceToHost, st));
-  } else {
-    if (o.mean) MGP_CUDA(h, cudaMemcpyAsync(o.mean, dout + o_mean, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
-    if (o.mse) MGP_CUDA(h, cudaMemcpyAsync(o.mse, dout + o_mse, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
-    if (o.val) MGP_CUDA(h, cudaMemcpyAsync(o.val, dout + o_val, (size_t)ns * m * 8, cudaMemcpyDeviceToHost, st));
-    if (o.mean_dx) MGP_CUDA(h, cudaMemcpyAsync(o.mean_dx, dout + o_mdx, (size_t)m * d * 8, cudaMemcpyDeviceToHost, st));
-    if (o.mse_dx) MGP_CUDA(h, cudaMemcpyAsync(o.mse_dx, dout + o_sdx, (size_t)m * d * 8, cudaMemcpyDeviceToHost, st));
-    if (o.dx) MGP_CUDA(h, cudaMemcpyAsync(o.dx, dout + o_dx, (size_t)ns * m * d * 8, cudaMemcpyDeviceToHost, st));
   }
   MGP_CUDA(h, cudaStreamSynchronize(st));
+  MGP_CUDA(h, cudaStreamSynchronize(os));
   MGP_CUDA(h, cudaStreamSynchronize(cs));
   return MGP_OK;
 }

@@ -19,8 +19,9 @@ struct mgp_handle {
   int device = 0;
   std::string err;
   cudaStream_t stream = nullptr;   // internal stream for the host-pointer entry points
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;  // H2D of staged candidates
+  cudaStream_t out_stream = nullptr;   // D2H of staged results
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int64_t launches = 0;
   // optional per-kernel timing (option "time_kernels"): event pairs resolved lazily
   int time_kernels = 0;

@@ -182,8 +182,11 @@ __global__ void __launch_bounds__(256, 1) k_trmm(TrmmParams p) {
       const int dl = FULL ? -1 : kc - 4 * I;  // >= 0 inside the diagonal 128x128 block
 #pragma unroll
       for (int js = 0; js < 4; js++) {
+        // Row tiles are interleaved between the two row-warps (tile i8 = 2 rt + wr) so that inside
+        // the diagonal block, where tiles above the diagonal (i8 < jl) are zero and skipped, both
+        // warps of every SM sub-partition keep the same amount of work.
         int rt_min = 0;
-        if (dl >= 0) rt_min = 4 * dl + js - 8 * wr;  // row tiles above the block diagonal are zero
+        if (dl >= 0) rt_min = (4 * dl + js - wr + 1) >> 1;  // smallest rt with 2 rt + wr >= jl
         if (rt_min >= 8) continue;
         double2 b[4], a[8];
 #pragma unroll
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(256, 1) k_trmm(TrmmParams p) {
           b[ct] = *reinterpret_cast<const double2 *>(bs + (js * 16 + wc * 4 + ct) * 64 + lane * 2);
 #pragma unroll
         for (int rt = 0; rt < 8; rt++)
-          a[rt] = *reinterpret_cast<const double2 *>(as + (js * 16 + wr * 8 + rt) * 64 + lane * 2);
+          a[rt] = *reinterpret_cast<const double2 *>(as + (js * 16 + 2 * rt + wr) * 64 + lane * 2);
 #pragma unroll
         for (int rt = 0; rt < 8; rt++)
           if (rt >= rt_min) {
@@ -239,13 +242,13 @@ __global__ void __launch_bounds__(256, 1) k_trmm(TrmmParams p) {
       if (tid < 128) p.qpart[(int64_t)I * p.ldq + (int64_t)cb * 128 + tid] = red[tid] + red[128 + tid];
       __syncthreads();
     } else {
-      // W[j][c] for j in row block I: thread holds rows 8(wr*8+rt)+lr, cols 8(wc*4+ct)+2lk+{0,1}.
+      // W[j][c] for j in row block I: thread holds rows 8(2rt+wr)+lr, cols 8(wc*4+ct)+2lk+{0,1}.
       // rP-style layout wants, per (j8, c8) tile, element (cc, jj) at cc*8 + jj.
 #pragma unroll
       for (int rt = 0; rt < 8; rt++)
 #pragma unroll
         for (int ct = 0; ct < 4; ct++) {
-          const int j8 = I * 16 + wr * 8 + rt, c8 = wc * 4 + ct;
+          const int j8 = I * 16 + 2 * rt + wr, c8 = wc * 4 + ct;
           double *tile = p.wP + (((int64_t)cb * p.NJ8 + j8) * 16 + c8) * 64;
           tile[(2 * lk) * 8 + lr] = acc[rt][ct][0];
           tile[(2 * lk + 1) * 8 + lr] = acc[rt][ct][1];

