@@ -538,17 +538,15 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     const int64_t mc = std::min<int64_t>(h->chunk, q.m - c0);
     const int64_t ldp = round_up(mc, 128);
     const int nCblk = (int)(ldp / 128);
-    int JS = std::max(1, std::min(h->NI, (2 * h->sm_count) / nCblk));
-    const int jblk = (h->NI + JS - 1) / JS;
-    JS = (h->NI + jblk - 1) / jblk;
+    const int JS = h->NI;
     RgenParams rp;
     rp.Xs = q.d_Xs + c0 * h->d; rp.mc = mc; rp.d = h->d; rp.dpad = h->dpad; rp.NJ8 = NJ8;
-    rp.jblk_per_cta = jblk;
+    rp.nCblk = nCblk; rp.JS = JS;
     rp.center = P<double>(h->dcenter); rp.theta = P<double>(h->dtheta); rp.Bop = P<double>(h->dBop);
     rp.an = P<double>(h->dan); rp.gamma = P<double>(h->dgamma); rp.avec = P<double>(h->davec);
     rp.rP = P<double>(h->drP); rp.meanpart = P<double>(h->dmeanpart); rp.ftpart = P<double>(h->dftpart);
     rp.ldp = ldp;
-    { KTimer t(h, st, 0); MGP_CUDA(h, launch_rgen(rp, h->corr, JS, st)); }
+    { KTimer t(h, st, 0); MGP_CUDA(h, launch_rgen(rp, h->corr, h->sm_count, st)); }
     h->launches++;
     if (!q.want_dx) {
       TrmmParams tp;

@@ -38,65 +38,85 @@ __global__ void k_prep_model(const double *Xc, const double *theta, int npad, in
 // the reference forms |x - x'| component-wise, gpr.py:453-455).  Also accumulates
 // r . gamma (posterior mean, gpr.py:459) and r . a with a = L^-T Ft (Ft^T rt, gpr.py:467).
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int rgen_stride(int dpad) { return ((dpad + 11) / 16) * 16 + 4; }
+
 template <int CORR, int KS>
 __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
+  // Persistent: work item = (candidate block cb of 128, training block jb of 128).  The operands
+  // of the training block (Bop rows, an, gamma, a) are staged once per item in shared memory.
+  constexpr int DPAD = 4 * KS, SB = rgen_stride(DPAD);   // SB % 16 == 4: conflict-free B fragments
+  extern __shared__ __align__(16) double sm_rg[];
+  double *sB = sm_rg, *sV = sm_rg + 128 * SB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lk = lane & 3;
-  const int cb = blockIdx.x;
-  double xa[2][KS], bn[2];
-#pragma unroll
-  for (int u = 0; u < 2; u++) {
-    const int64_t c = (int64_t)cb * 128 + (2 * warp + u) * 8 + lr;
-    const bool valid = c < p.mc;
-    double part = 0.0;
-#pragma unroll
-    for (int s = 0; s < KS; s++) {
-      const int i = 4 * s + lk;
-      double v = 0.0;
-      if (valid && i < p.d) v = p.Xs[c * p.d + i] - p.center[i];
-      xa[u][s] = v;
-      part = fma(p.theta[i] * v, v, part);
+  const int nItems = p.nCblk * p.JS;
+  for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+    const int jb = item / p.nCblk, cb = item % p.nCblk;
+    __syncthreads();
+    for (int idx = tid; idx < 128 * DPAD; idx += 256) {
+      const int r = idx / DPAD, i = idx % DPAD;
+      sB[r * SB + i] = __ldg(p.Bop + (int64_t)(jb * 128 + r) * DPAD + i);
     }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    bn[u] = part;
-  }
-  double macc[2] = {0.0, 0.0}, facc[2] = {0.0, 0.0};
-  const int j8_begin = blockIdx.y * p.jblk_per_cta * 16;
-  const int j8_end = min(p.NJ8, j8_begin + p.jblk_per_cta * 16);
-#pragma unroll 2
-  for (int j8 = j8_begin; j8 < j8_end; j8++) {
-    const int jrow = 8 * j8 + lr, jcol = 8 * j8 + 2 * lk;
-    double bf[KS];
-#pragma unroll
-    for (int s = 0; s < KS; s++) bf[s] = __ldg(p.Bop + (int64_t)jrow * p.dpad + 4 * s + lk);
-    const double2 an2 = __ldg(reinterpret_cast<const double2 *>(p.an + jcol));
-    const double2 g2 = __ldg(reinterpret_cast<const double2 *>(p.gamma + jcol));
-    const double2 a2 = __ldg(reinterpret_cast<const double2 *>(p.avec + jcol));
+    if (tid < 128) {
+      sV[tid] = __ldg(p.an + jb * 128 + tid);
+      sV[128 + tid] = __ldg(p.gamma + jb * 128 + tid);
+      sV[256 + tid] = __ldg(p.avec + jb * 128 + tid);
+    }
+    double xa[2][KS], bn[2];
 #pragma unroll
     for (int u = 0; u < 2; u++) {
-      double c0 = bn[u] + an2.x, c1 = bn[u] + an2.y;
+      const int64_t c = (int64_t)cb * 128 + (2 * warp + u) * 8 + lr;
+      const bool valid = c < p.mc;
+      double part = 0.0;
 #pragma unroll
-      for (int s = 0; s < KS; s++) dmma884(c0, c1, xa[u][s], bf[s]);
-      const double r0 = corr_from_S<CORR>(c0), r1 = corr_from_S<CORR>(c1);
-      double2 *dst = reinterpret_cast<double2 *>(
-          p.rP + (((int64_t)cb * p.NJ8 + j8) * 16 + (2 * warp + u)) * 64 + lane * 2);
-      *dst = make_double2(r0, r1);
-      macc[u] = fma(g2.x, r0, macc[u]);
-      macc[u] = fma(g2.y, r1, macc[u]);
-      facc[u] = fma(a2.x, r0, facc[u]);
-      facc[u] = fma(a2.y, r1, facc[u]);
+      for (int s = 0; s < KS; s++) {
+        const int i = 4 * s + lk;
+        double v = 0.0;
+        if (valid && i < p.d) v = p.Xs[c * p.d + i] - p.center[i];
+        xa[u][s] = v;
+        part = fma(p.theta[i] * v, v, part);
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      bn[u] = part;
     }
-  }
+    __syncthreads();
+    double macc[2] = {0.0, 0.0}, facc[2] = {0.0, 0.0};
+#pragma unroll 2
+    for (int t8 = 0; t8 < 16; t8++) {
+      const int j8 = jb * 16 + t8;
+      const int jrow = 8 * t8 + lr, jcol = 8 * t8 + 2 * lk;
+      double bf[KS];
 #pragma unroll
-  for (int u = 0; u < 2; u++) {
-    macc[u] += __shfl_xor_sync(0xffffffffu, macc[u], 1);
-    macc[u] += __shfl_xor_sync(0xffffffffu, macc[u], 2);
-    facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 1);
-    facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 2);
-    if (lk == 0) {
-      const int64_t o = (int64_t)blockIdx.y * p.ldp + (int64_t)cb * 128 + (2 * warp + u) * 8 + lr;
-      p.meanpart[o] = macc[u];
-      p.ftpart[o] = facc[u];
+      for (int s = 0; s < KS; s++) bf[s] = sB[jrow * SB + 4 * s + lk];
+      const double2 an2 = *reinterpret_cast<const double2 *>(sV + jcol);
+      const double2 g2 = *reinterpret_cast<const double2 *>(sV + 128 + jcol);
+      const double2 a2 = *reinterpret_cast<const double2 *>(sV + 256 + jcol);
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        double c0 = bn[u] + an2.x, c1 = bn[u] + an2.y;
+#pragma unroll
+        for (int s = 0; s < KS; s++) dmma884(c0, c1, xa[u][s], bf[s]);
+        const double r0 = corr_from_S<CORR>(c0), r1 = corr_from_S<CORR>(c1);
+        double2 *dst = reinterpret_cast<double2 *>(
+            p.rP + (((int64_t)cb * p.NJ8 + j8) * 16 + (2 * warp + u)) * 64 + lane * 2);
+        *dst = make_double2(r0, r1);
+        macc[u] = fma(g2.x, r0, macc[u]);
+        macc[u] = fma(g2.y, r1, macc[u]);
+        facc[u] = fma(a2.x, r0, facc[u]);
+        facc[u] = fma(a2.y, r1, facc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      macc[u] += __shfl_xor_sync(0xffffffffu, macc[u], 1);
+      macc[u] += __shfl_xor_sync(0xffffffffu, macc[u], 2);
+      facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 1);
+      facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 2);
+      if (lk == 0) {
+        const int64_t o = (int64_t)jb * p.ldp + (int64_t)cb * 128 + (2 * warp + u) * 8 + lr;
+        p.meanpart[o] = macc[u];
+        p.ftpart[o] = facc[u];
+      }
     }
   }
 }
@@ -112,8 +132,40 @@ constexpr int TS = 3;             // pipeline stages
 constexpr int STAGE_DBL = 4096;   // doubles per operand per stage (4 slabs, 32 KB)
 constexpr int TRMM_SMEM = 2 * TS * STAGE_DBL * 8 + 2 * TS * 8 + 2 * 128 * 8;
 
+// One 8-k slab of the 128x128 tile for one consumer warp: row tiles RT0..7 (interleaved: tile
+// i8 = 2 rt + wr) times 4 column tiles.  RT0 is a template parameter so that skipping the zero
+// tiles of the diagonal block is a real (warp-uniform) branch: predicated-off DMMAs would still
+// pay their static issue stalls.
+template <int RT0>
+__device__ __forceinline__ void slab_mma(double (&acc)[8][4][2], const double *as_slab,
+                                         const double *bs_slab, int wr, int wc, int lane) {
+  double2 b[4], a[8];
+#pragma unroll
+  for (int ct = 0; ct < 4; ct++)
+    b[ct] = *reinterpret_cast<const double2 *>(bs_slab + (wc * 4 + ct) * 64 + lane * 2);
+#pragma unroll
+  for (int rt = RT0; rt < 8; rt++)
+    a[rt] = *reinterpret_cast<const double2 *>(as_slab + (2 * rt + wr) * 64 + lane * 2);
+#pragma unroll
+  for (int rt = RT0; rt < 8; rt++)
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt].x, b[ct].x);
+#pragma unroll
+  for (int rt = RT0; rt < 8; rt++)
+#pragma unroll
+    for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt].y, b[ct].y);
+}
+
+__device__ __forceinline__ void consumer_sync() {  // named barrier 1: the 8 consumer warps only
+  asm volatile("bar.sync 1, 256;\n" ::: "memory");
+}
+
 template <bool FULL>
-__global__ void __launch_bounds__(256, 1) k_trmm(TrmmParams p) {
+__global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
+  // Warp-specialised: warpgroups 0-1 (warps 0-7) are MMA consumers, warpgroup 2 is the producer.
+  // Registers are partitioned per SM sub-partition (16K each), so the three warps that share a
+  // sub-partition start at 168 registers; the producer group gives most of its share back
+  // (setmaxnreg.dec) and the consumer groups grow to 232 (setmaxnreg.inc).
   extern __shared__ __align__(128) unsigned char smraw[];
   double *As = reinterpret_cast<double *>(smraw);
   double *Bs = As + TS * STAGE_DBL;
@@ -122,7 +174,6 @@ __global__ void __launch_bounds__(256, 1) k_trmm(TrmmParams p) {
   double *red = reinterpret_cast<double *>(empty + TS);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wr = warp >> 2, wc = warp & 3, lr = lane >> 2, lk = lane & 3;
   const int nItems = p.NI * p.nCblk;
 
   if (tid == 0) {
@@ -134,37 +185,47 @@ __global__ void __launch_bounds__(256, 1) k_trmm(TrmmParams p) {
   }
   __syncthreads();
 
-  // ---- producer cursor (thread 0) ----
-  int p_item = blockIdx.x, p_kc = 0, p_nkc = 0, p_I = 0, p_cb = 0;
-  int64_t p_x = 0;
-  auto p_setup = [&]() {
-    if (p_item < nItems) {
-      p_I = p.NI - 1 - p_item / p.nCblk;
-      p_cb = p_item % p.nCblk;
-      p_nkc = FULL ? p.NJ8 / 4 : 4 * (p_I + 1);
-      p_kc = 0;
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    // ---- producer: one lane streams the operand slabs through the TS-stage ring (TMA bulk copies)
+    if (warp == 8 && lane == 0) {
+      int64_t x = 0;
+      for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const int I = p.NI - 1 - item / p.nCblk, cb = item % p.nCblk;
+        const int nkc = FULL ? p.NJ8 / 4 : 4 * (I + 1);
+        for (int kc = 0; kc < nkc; kc++, x++) {
+          const int stage = (int)(x % TS);
+          if (x >= TS) mbar_wait(&empty[stage], (uint32_t)(((x / TS) - 1) & 1));
+          const int64_t slabA =
+              FULL ? ((int64_t)I * p.NJ8 + 4 * kc) : ((int64_t)8 * I * (I + 1) + 4 * kc);
+          const double *srcA = p.Mp + slabA * 1024;
+          const double *srcB = p.rP + ((int64_t)cb * p.NJ8 + 4 * kc) * 1024;
+          double *dstA = As + stage * STAGE_DBL;
+          const int dl = FULL ? -1 : kc - 4 * I;
+          if (dl < 0) {
+            mbar_expect_tx(&full[stage], 2 * STAGE_DBL * 8);
+            bulk_g2s(dstA, srcA, STAGE_DBL * 8, &full[stage]);
+          } else {
+            // diagonal block: row tiles i8 < jl of slab jl are zero and never read -- skip them
+            uint32_t bytes = STAGE_DBL * 8;
+            for (int js = 0; js < 4; js++) bytes += (uint32_t)(16 - (4 * dl + js)) * 512u;
+            mbar_expect_tx(&full[stage], bytes);
+            for (int js = 0; js < 4; js++) {
+              const int jl = 4 * dl + js;
+              bulk_g2s(dstA + js * 1024 + jl * 64, srcA + js * 1024 + jl * 64,
+                       (uint32_t)(16 - jl) * 512u, &full[stage]);
+            }
+          }
+          bulk_g2s(Bs + stage * STAGE_DBL, srcB, STAGE_DBL * 8, &full[stage]);
+        }
+      }
     }
-  };
-  auto issue = [&]() {
-    if (p_item >= nItems) return;
-    const int stage = (int)(p_x % TS);
-    const int64_t slabA =
-        FULL ? ((int64_t)p_I * p.NJ8 + 4 * p_kc) : ((int64_t)8 * p_I * (p_I + 1) + 4 * p_kc);
-    mbar_expect_tx(&full[stage], 2 * STAGE_DBL * 8);
-    bulk_g2s(As + stage * STAGE_DBL, p.Mp + slabA * 1024, STAGE_DBL * 8, &full[stage]);
-    bulk_g2s(Bs + stage * STAGE_DBL, p.rP + ((int64_t)p_cb * p.NJ8 + 4 * p_kc) * 1024,
-             STAGE_DBL * 8, &full[stage]);
-    p_x++;
-    if (++p_kc == p_nkc) {
-      p_item += gridDim.x;
-      p_setup();
-    }
-  };
-  if (tid == 0) {
-    p_setup();
-    for (int s = 0; s < TS; s++) issue();
+    return;
   }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
 
+  // ---- 8 consumer warps: 2 (row parity) x 4 (column groups of 32) over a 128 x 128 tile ----
+  const int wr = warp >> 2, wc = warp & 3, lr = lane >> 2, lk = lane & 3;
   int64_t x = 0;
   for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
     const int I = p.NI - 1 - item / p.nCblk, cb = item % p.nCblk;
@@ -180,41 +241,32 @@ __global__ void __launch_bounds__(256, 1) k_trmm(TrmmParams p) {
       mbar_wait(&full[stage], (uint32_t)((x / TS) & 1));
       const double *as = As + stage * STAGE_DBL, *bs = Bs + stage * STAGE_DBL;
       const int dl = FULL ? -1 : kc - 4 * I;  // >= 0 inside the diagonal 128x128 block
+      if (dl < 0) {
 #pragma unroll
-      for (int js = 0; js < 4; js++) {
-        // Row tiles are interleaved between the two row-warps (tile i8 = 2 rt + wr) so that inside
-        // the diagonal block, where tiles above the diagonal (i8 < jl) are zero and skipped, both
-        // warps of every SM sub-partition keep the same amount of work.
-        int rt_min = 0;
-        if (dl >= 0) rt_min = (4 * dl + js - wr + 1) >> 1;  // smallest rt with 2 rt + wr >= jl
-        if (rt_min >= 8) continue;
-        double2 b[4], a[8];
-#pragma unroll
-        for (int ct = 0; ct < 4; ct++)
-          b[ct] = *reinterpret_cast<const double2 *>(bs + (js * 16 + wc * 4 + ct) * 64 + lane * 2);
-#pragma unroll
-        for (int rt = 0; rt < 8; rt++)
-          a[rt] = *reinterpret_cast<const double2 *>(as + (js * 16 + 2 * rt + wr) * 64 + lane * 2);
-#pragma unroll
-        for (int rt = 0; rt < 8; rt++)
-          if (rt >= rt_min) {
-#pragma unroll
-            for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt].x, b[ct].x);
+        for (int js = 0; js < 4; js++) slab_mma<0>(acc, as + js * 1024, bs + js * 1024, wr, wc, lane);
+      } else {
+        // diagonal block: tiles above the diagonal (i8 < jl) are zero.  Row tiles are interleaved
+        // between the two row-warps (i8 = 2 rt + wr), so both warps of every SM sub-partition
+        // keep the same amount of work; rt0 = smallest rt with 2 rt + wr >= jl.
+#pragma unroll 1
+        for (int js = 0; js < 4; js++) {
+          const int rt0 = (4 * dl + js - wr + 1) >> 1;
+          const double *a_s = as + js * 1024, *b_s = bs + js * 1024;
+          switch (rt0) {
+            case 0: slab_mma<0>(acc, a_s, b_s, wr, wc, lane); break;
+            case 1: slab_mma<1>(acc, a_s, b_s, wr, wc, lane); break;
+            case 2: slab_mma<2>(acc, a_s, b_s, wr, wc, lane); break;
+            case 3: slab_mma<3>(acc, a_s, b_s, wr, wc, lane); break;
+            case 4: slab_mma<4>(acc, a_s, b_s, wr, wc, lane); break;
+            case 5: slab_mma<5>(acc, a_s, b_s, wr, wc, lane); break;
+            case 6: slab_mma<6>(acc, a_s, b_s, wr, wc, lane); break;
+            case 7: slab_mma<7>(acc, a_s, b_s, wr, wc, lane); break;
+            default: break;
           }
-#pragma unroll
-        for (int rt = 0; rt < 8; rt++)
-          if (rt >= rt_min) {
-#pragma unroll
-            for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt].y, b[ct].y);
-          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
-      if (tid == 0 && x >= 1 && p_item < nItems) {
-        const int64_t xs = x - 1;  // refill the stage released one chunk ago
-        mbar_wait(&empty[xs % TS], (uint32_t)((xs / TS) & 1));
-        issue();
-      }
     }
 
     if (!FULL) {
@@ -238,9 +290,9 @@ __global__ void __launch_bounds__(256, 1) k_trmm(TrmmParams p) {
           red[wr * 128 + wc * 32 + ct * 8 + 2 * lk + 1] = qs[ct][1];
         }
       }
-      __syncthreads();
+      consumer_sync();
       if (tid < 128) p.qpart[(int64_t)I * p.ldq + (int64_t)cb * 128 + tid] = red[tid] + red[128 + tid];
-      __syncthreads();
+      consumer_sync();
     } else {
       // W[j][c] for j in row block I: thread holds rows 8(2rt+wr)+lr, cols 8(wc*4+ct)+2lk+{0,1}.
       // rP-style layout wants, per (j8, c8) tile, element (cc, jj) at cc*8 + jj.
@@ -532,20 +584,32 @@ cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, i
   return cudaGetLastError();
 }
 
+template <int CORR, int KS>
+static cudaError_t rgen_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
+  static int occ = 0;
+  const int smem = (128 * rgen_stride(4 * KS) + 3 * 128) * (int)sizeof(double);
+  if (occ == 0) {
+    cudaFuncSetAttribute(k_rgen<CORR, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen<CORR, KS>, 256, smem) != cudaSuccess || occ < 1)
+      occ = 1;
+  }
+  const int items = p.nCblk * p.JS;
+  const int grid = items < sm_count * occ ? items : sm_count * occ;
+  k_rgen<CORR, KS><<<grid, 256, smem, st>>>(p);
+  return cudaGetLastError();
+}
 template <int CORR>
-static cudaError_t rgen_dispatch(const RgenParams &p, int JS, cudaStream_t st) {
-  dim3 grid((unsigned)(p.ldp / 128), (unsigned)JS);
+static cudaError_t rgen_dispatch(const RgenParams &p, int sm_count, cudaStream_t st) {
   switch (p.dpad / 4) {
-#define RG(K) case K: k_rgen<CORR, K><<<grid, 256, 0, st>>>(p); break;
+#define RG(K) case K: return rgen_launch<CORR, K>(p, sm_count, st);
     RG(1) RG(2) RG(3) RG(4) RG(5) RG(6) RG(7) RG(8) RG(9) RG(10) RG(11) RG(12) RG(13) RG(14) RG(15) RG(16)
 #undef RG
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
-cudaError_t launch_rgen(const RgenParams &p, int corr, int JS, cudaStream_t st) {
-  if (corr == MGP_CORR_SE) return rgen_dispatch<0>(p, JS, st);
-  if (corr == MGP_CORR_MATERN32) return rgen_dispatch<1>(p, JS, st);
+cudaError_t launch_rgen(const RgenParams &p, int corr, int sm_count, cudaStream_t st) {
+  if (corr == MGP_CORR_SE) return rgen_dispatch<0>(p, sm_count, st);
+  if (corr == MGP_CORR_MATERN32) return rgen_dispatch<1>(p, sm_count, st);
   return cudaErrorInvalidValue;
 }
 
@@ -559,8 +623,8 @@ cudaError_t launch_trmm(const TrmmParams &p, int sm_count, cudaStream_t st) {
   const int items = p.NI * p.nCblk;
   if (items <= 0) return cudaSuccess;
   const int grid = items < sm_count ? items : sm_count;
-  if (p.full) k_trmm<true><<<grid, 256, TRMM_SMEM, st>>>(p);
-  else k_trmm<false><<<grid, 256, TRMM_SMEM, st>>>(p);
+  if (p.full) k_trmm<true><<<grid, 384, TRMM_SMEM, st>>>(p);
+  else k_trmm<false><<<grid, 384, TRMM_SMEM, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -12,13 +12,13 @@ cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, i
 struct RgenParams {
   const double *Xs;   // chunk base: candidate rows, row-major with leading dimension d
   int64_t mc;         // valid candidates in the chunk
-  int d, dpad, NJ8, jblk_per_cta;
+  int d, dpad, NJ8, nCblk, JS;   // JS = number of 128-row training blocks (= npad / 128)
   const double *center, *theta, *Bop, *an, *gamma, *avec;
   double *rP, *meanpart, *ftpart;
   int64_t ldp;        // mc rounded up to 128
 };
-// K1: r tile generator.  grid = (ldp/128, JS).  corr: MGP_CORR_SE | MGP_CORR_MATERN32.
-cudaError_t launch_rgen(const RgenParams &p, int corr, int JS, cudaStream_t st);
+// K1: r tile generator, persistent over (candidate block, training block) items.
+cudaError_t launch_rgen(const RgenParams &p, int corr, int sm_count, cudaStream_t st);
 
 struct TrmmParams {
   const double *Mp;   // packed operand (triangular L^-1 or full R^-1)
