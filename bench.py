@@ -102,6 +102,7 @@ def cpu_port_rate(n, d, kind, crit, sets, sample, seed=10):
     """Reference algorithm (oracle port) on the host cores: vectorised predict + acquisition in
     chunks of 2000 candidates (the best-case CPU path)."""
     from oracle import gp_oracle as O
+    use_all_host_threads()
     X, y, theta = synth_model(n, d, kind, seed)
     st = O.fit_state(X, y, np.r_[theta, 0.9], kind, True, 0.0, "noisy", 1e-6)
     Xs = np.random.default_rng(seed + 1).uniform(-5, 5, (sample, d))
@@ -118,6 +119,15 @@ def cpu_port_rate(n, d, kind, crit, sets, sample, seed=10):
                 O.acquisition(st, xs, crit, float(t), plugin, True)
     dt = time.perf_counter() - t0
     return sample / dt, dt
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arms are entitled to every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
 
 
 def blas_threads():
@@ -175,6 +185,7 @@ def nll_problem(n, d, B, seed=30):
 
 def cpu_nll_rate(n, d, reps):
     from oracle import gp_oracle as O
+    use_all_host_threads()
     X, y, P = nll_problem(n, d, max(1, reps))
     t0 = time.perf_counter()
     for b in range(reps):
@@ -224,22 +235,26 @@ def run_nll(args, rank, world, local):
         torch.cuda.synchronize()
 
     out = None
-    for _ in range(args.warmup):
-        out = gp.log_likelihood_batch_device(P_dev)
-    barrier()
-    launches0 = h.counter("launches")
+    # an explicit (non-legacy) stream: the legacy default stream implicitly synchronises with other
+    # blocking streams and defeats the library's look-ahead side stream
+    work = torch.cuda.Stream(device=dev)
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for k in range(args.steps):
-        ev[k][0].record()
-        out = gp.log_likelihood_batch_device(P_dev)
-        if world > 1:
-            g = [torch.empty_like(out[0]) for _ in range(world)]
-            dist.all_gather(g, out[0])
-        ev[k][1].record()
-    barrier()
+    with torch.cuda.stream(work):
+        for _ in range(args.warmup):
+            out = gp.log_likelihood_batch_device(P_dev)
+        barrier()
+        launches0 = h.counter("launches")
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for k in range(args.steps):
+            ev[k][0].record()
+            out = gp.log_likelihood_batch_device(P_dev)
+            if world > 1:
+                g = [torch.empty_like(out[0]) for _ in range(world)]
+                dist.all_gather(g, out[0])
+            ev[k][1].record()
+        barrier()
     sampler.stop_flag = True
     ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = h.counter("launches") - launches0
@@ -367,6 +382,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    work = torch.cuda.Stream(device=dev)   # explicit stream (not the legacy default stream)
+    torch.cuda.set_stream(work)
     for _ in range(args.warmup):
         step()
     barrier()

@@ -100,9 +100,14 @@ int mgp_create(int device, mgp_t **out_h) {
     return MGP_ECUDA;
   }
   h->sm_count = prop.multiProcessorCount;
+  // the look-ahead stream runs the short serial diagonal factorisations: highest priority, so its
+  // CTAs are placed as soon as an SM frees up under a concurrent trailing update
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     delete h;
     return MGP_ECUDA;
   }
@@ -110,6 +115,7 @@ int mgp_create(int device, mgp_t **out_h) {
     cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_la[i], cudaEventDisableTiming);
   }
   *out_h = h;
   return MGP_OK;
@@ -131,10 +137,12 @@ int mgp_destroy(mgp_t *h) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    if (h->ev_la[i]) cudaEventDestroy(h->ev_la[i]);
   }
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->out_stream) cudaStreamDestroy(h->out_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   delete h;
   return MGP_OK;
 }
@@ -281,6 +289,8 @@ static void fill_work(mgp_handle *h, NllWork &w, int B, int cap, int n_par, int 
   w.linv = P<double>(h->nLinvDiag); w.vec = P<double>(h->nvec); w.scal = P<double>(h->nscal);
   w.gpart = P<double>(h->ngpart); w.status = nll_status_ptr(h, cap);
   w.out_llf = d_llf; w.out_grad = d_grad;
+  h->la.side = h->side_stream; h->la.ev_a = h->ev_la[0]; h->la.ev_b = h->ev_la[1];
+  w.la = &h->la;
 }
 
 int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mode,

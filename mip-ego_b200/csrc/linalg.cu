@@ -114,16 +114,19 @@ __global__ void __launch_bounds__(256) k_dgemm(GemmDesc g) {
 // ---- 128x128 diagonal block: Cholesky (dpotf2-style, right looking) and in-place inverse ----
 constexpr int DS = 129;  // smem row stride
 
+// 1024 threads: 8 lanes per row (i = tid / 8, part = tid % 8), partial sums combined by shuffles.
 __device__ void diag_inverse_inplace(double *S, int tid) {
   // X = L^-1 in place, columns from last to first:
   //   X_jj = 1/L_jj ;  X_ij = -(sum_{k=j+1..i} X_ik L_kj) / L_jj   (i > j)
-  const int i = tid >> 1, part = tid & 1;
+  const int i = tid >> 3, part = tid & 7;
   for (int j = 127; j >= 0; j--) {
     const double inv = 1.0 / S[j * DS + j];
     double t = 0.0;
     if (i > j)
-      for (int k = j + 1 + part; k <= i; k += 2) t = fma(S[i * DS + k], S[k * DS + j], t);
+      for (int k = j + 1 + part; k <= i; k += 8) t = fma(S[i * DS + k], S[k * DS + j], t);
     t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
     __syncthreads();
     if (part == 0) {
       if (i > j) S[i * DS + j] = -t * inv;
@@ -133,19 +136,21 @@ __device__ void diag_inverse_inplace(double *S, int tid) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_potrf_diag(double *A, double *Lout, int ld, int64_t sA,
-                                                    double *linv, int64_t sInv, int kb,
-                                                    int *status) {
+__global__ void __launch_bounds__(1024) k_potrf_diag(double *A, double *Lout, int ld, int64_t sA,
+                                                     double *linv, int64_t sInv, int kb,
+                                                     int *status) {
   extern __shared__ __align__(16) double S[];
   const int tid = threadIdx.x, b = blockIdx.x;
   const double *Ab = A + b * sA + (int64_t)kb * 128 * ld + kb * 128;
   double *Lb = Lout + b * sA + (int64_t)kb * 128 * ld + kb * 128;
-  for (int idx = tid; idx < 128 * 128; idx += 256) {
+  for (int idx = tid; idx < 128 * 128; idx += 1024) {
     const int r = idx >> 7, c = idx & 127;
     S[r * DS + c] = (c <= r) ? Ab[(int64_t)r * ld + c] : 0.0;
   }
   __syncthreads();
-  const int i = tid & 127, half = tid >> 7;
+  // dpotf2-style right-looking Cholesky; the trailing update of step j is spread over 8 column
+  // phases per row (i = tid % 128, phase = tid / 128) and batched 4 deep to overlap smem latency
+  const int i = tid & 127, ph = tid >> 7;
   for (int j = 0; j < 128; j++) {
     const double ajj = S[j * DS + j];
     if (!(ajj > 0.0)) {
@@ -154,43 +159,54 @@ __global__ void __launch_bounds__(256) k_potrf_diag(double *A, double *Lout, int
     const double dj = sqrt(ajj);
     const double rinv = 1.0 / dj;
     __syncthreads();
-    if (half == 0) {
+    if (ph == 0) {
       if (i > j) S[i * DS + j] *= rinv;
       if (i == j) S[j * DS + j] = dj;
     }
     __syncthreads();
     if (i > j) {
       const double lij = S[i * DS + j];
-      for (int k = j + 1 + half; k <= i; k += 2) S[i * DS + k] = fma(-lij, S[k * DS + j], S[i * DS + k]);
+      int k = j + 1 + ph;
+      for (; k + 24 <= i; k += 32) {
+        const double c0 = S[k * DS + j], c1 = S[(k + 8) * DS + j], c2 = S[(k + 16) * DS + j],
+                     c3 = S[(k + 24) * DS + j];
+        const double a0 = S[i * DS + k], a1 = S[i * DS + k + 8], a2 = S[i * DS + k + 16],
+                     a3 = S[i * DS + k + 24];
+        S[i * DS + k] = fma(-lij, c0, a0);
+        S[i * DS + k + 8] = fma(-lij, c1, a1);
+        S[i * DS + k + 16] = fma(-lij, c2, a2);
+        S[i * DS + k + 24] = fma(-lij, c3, a3);
+      }
+      for (; k <= i; k += 8) S[i * DS + k] = fma(-lij, S[k * DS + j], S[i * DS + k]);
     }
     __syncthreads();
   }
-  for (int idx = tid; idx < 128 * 128; idx += 256) {
+  for (int idx = tid; idx < 128 * 128; idx += 1024) {
     const int r = idx >> 7, c = idx & 127;
     Lb[(int64_t)r * ld + c] = S[r * DS + c];
   }
   __syncthreads();
   diag_inverse_inplace(S, tid);
   double *Ib = linv + b * sInv + (int64_t)kb * 128 * 128;
-  for (int idx = tid; idx < 128 * 128; idx += 256) {
+  for (int idx = tid; idx < 128 * 128; idx += 1024) {
     const int r = idx >> 7, c = idx & 127;
     Ib[idx] = (c <= r) ? S[r * DS + c] : 0.0;
   }
 }
 
-__global__ void __launch_bounds__(256) k_trtri_diag(const double *L, int ld, int64_t sL,
-                                                    double *linv, int64_t sInv) {
+__global__ void __launch_bounds__(1024) k_trtri_diag(const double *L, int ld, int64_t sL,
+                                                     double *linv, int64_t sInv) {
   extern __shared__ __align__(16) double S[];
   const int tid = threadIdx.x, kb = blockIdx.x, b = blockIdx.y;
   const double *Lb = L + b * sL + (int64_t)kb * 128 * ld + kb * 128;
-  for (int idx = tid; idx < 128 * 128; idx += 256) {
+  for (int idx = tid; idx < 128 * 128; idx += 1024) {
     const int r = idx >> 7, c = idx & 127;
     S[r * DS + c] = (c <= r) ? Lb[(int64_t)r * ld + c] : 0.0;
   }
   __syncthreads();
   diag_inverse_inplace(S, tid);
   double *Ib = linv + b * sInv + (int64_t)kb * 128 * 128;
-  for (int idx = tid; idx < 128 * 128; idx += 256) {
+  for (int idx = tid; idx < 128 * 128; idx += 1024) {
     const int r = idx >> 7, c = idx & 127;
     Ib[idx] = (c <= r) ? S[r * DS + c] : 0.0;
   }
@@ -223,20 +239,28 @@ __global__ void __launch_bounds__(256) k_trmv_n(const double *M, int npad, int64
   if (lane == 0) y[b * sy + row] = acc;
 }
 
-__global__ void __launch_bounds__(128) k_trmv_t(const double *M, int npad, int64_t sM,
-                                                const double *x, int64_t sx, double *y, int64_t sy,
-                                                int n) {
-  const int b = blockIdx.y;
-  const int col = blockIdx.x * 128 + threadIdx.x;
-  if (col >= npad) return;
+// y[col] = sum_{k >= col} M[k][col] x[k]: a block owns 32 columns, its 32 warps stride over the
+// rows (coalesced 256-byte row segments), partial sums are combined in a fixed order.
+__global__ void __launch_bounds__(1024) k_trmv_t(const double *M, int npad, int64_t sM,
+                                                 const double *x, int64_t sx, double *y, int64_t sy,
+                                                 int n) {
+  __shared__ double red[32][33];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
   const double *Mb = M + b * sM;
   const double *xb = x ? x + b * sx : nullptr;
   double acc = 0.0;
-  for (int k = col; k < npad; k++) {
+  for (int k = blockIdx.x * 32 + w; k < npad; k += 32) {
     const double xv = xb ? xb[k] : (k < n ? 1.0 : 0.0);
-    acc = fma(Mb[(int64_t)k * npad + col], xv, acc);
+    if (k >= col) acc = fma(Mb[(int64_t)k * npad + col], xv, acc);
   }
-  y[b * sy + col] = acc;
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0) {
+    double t = 0.0;
+    for (int r = 0; r < 32; r++) t += red[r][lane];
+    y[b * sy + col] = t;
+  }
 }
 
 // ---- slab packing ---------------------------------------------------------------------------
@@ -293,7 +317,7 @@ cudaError_t launch_potrf_diag(double *A, double *Lout, int ld, int64_t sA, doubl
     cudaFuncSetAttribute(k_trtri_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     attr_done = true;
   }
-  k_potrf_diag<<<batch, 256, kDiagSmem, st>>>(A, Lout, ld, sA, linv, sInv, kb, status);
+  k_potrf_diag<<<batch, 1024, kDiagSmem, st>>>(A, Lout, ld, sA, linv, sInv, kb, status);
   return cudaGetLastError();
 }
 
@@ -305,7 +329,7 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
     cudaFuncSetAttribute(k_trtri_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     attr_done = true;
   }
-  k_trtri_diag<<<dim3(NI, batch), 256, kDiagSmem, st>>>(L, ld, sL, linv, sInv);
+  k_trtri_diag<<<dim3(NI, batch), 1024, kDiagSmem, st>>>(L, ld, sL, linv, sInv);
   return cudaGetLastError();
 }
 
@@ -316,17 +340,21 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
   } while (0)
 
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
-                         int *status, int batch, cudaStream_t st, int64_t *launches) {
+                         int *status, int batch, cudaStream_t st, int64_t *launches,
+                         const LookAhead *la) {
+  // Right-looking blocked Cholesky, block 128.  With look-ahead the trailing update of step kb is
+  // split: the next block column is updated first, then the (serial, single-CTA) factorisation
+  // of the next diagonal block runs on a side stream while the rest of the update proceeds.
   const int NI = npad / 128;
   for (int b = 0; b < batch; b++)
     LA_TRY(cudaMemsetAsync(L + b * sA, 0, sizeof(double) * (size_t)npad * npad, st));
-  for (int kb = 0; kb < NI; kb++) {
-    LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, kb, status, batch, st));
-    (*launches)++;
+  const bool ahead = la && la->side && NI > 2;
+  LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, 0, status, batch, st));
+  (*launches)++;
+  for (int kb = 0; kb < NI - 1; kb++) {
     const int below = NI - 1 - kb;
-    if (below == 0) break;
-    GemmDesc g = {};
     const int64_t off_panel = (int64_t)(kb + 1) * 128 * npad + (int64_t)kb * 128;
+    GemmDesc g = {};
     // panel: L[kb+1:, kb] = A[kb+1:, kb] * inv(L_kk)^T
     g.A = A + off_panel; g.lda = npad; g.ta = 0;
     g.B = linv + (int64_t)kb * 128 * 128; g.ldb = 128; g.tb = 0;
@@ -336,7 +364,8 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
     g.n_inner = 1; g.n_outer = batch;
     g.sA_out = sA; g.sB_out = sInv; g.sC_out = sA;
     LA_TRY(launch_dgemm(g, st));
-    // trailing update: A[i,j] -= L[i,kb] L[j,kb]^T, lower tiles only
+    (*launches)++;
+    // trailing update: A[i,j] -= L[i,kb] L[j,kb]^T on the lower tiles
     GemmDesc u = {};
     u.A = L + off_panel; u.lda = npad; u.ta = 0;
     u.B = L + off_panel; u.ldb = npad; u.tb = 0;
@@ -345,8 +374,26 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
     u.alpha = -1.0; u.beta = 1.0; u.kmode = 0; u.lower_only = 1;
     u.n_inner = 1; u.n_outer = batch;
     u.sA_out = sA; u.sB_out = sA; u.sC_out = sA;
-    LA_TRY(launch_dgemm(u, st));
-    (*launches) += 2;
+    if (!ahead || below < 2) {
+      LA_TRY(launch_dgemm(u, st));
+      LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, kb + 1, status, batch, st));
+      (*launches) += 2;
+    } else {
+      GemmDesc c1 = u;   // (i) block column kb+1 (all rows below the diagonal of step kb)
+      c1.N = 128; c1.lower_only = 0;
+      LA_TRY(launch_dgemm(c1, st));
+      LA_TRY(cudaEventRecord(la->ev_a, st));
+      LA_TRY(cudaStreamWaitEvent(la->side, la->ev_a, 0));
+      LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, kb + 1, status, batch, la->side));
+      LA_TRY(cudaEventRecord(la->ev_b, la->side));
+      GemmDesc c2 = u;   // (ii) the remaining lower tiles: rows/cols from block kb+2
+      c2.A = u.A + (int64_t)128 * npad; c2.B = u.B + (int64_t)128 * npad;
+      c2.C = u.C + (int64_t)128 * (npad + 1);
+      c2.M = (below - 1) * 128; c2.N = (below - 1) * 128;
+      LA_TRY(launch_dgemm(c2, st));
+      LA_TRY(cudaStreamWaitEvent(st, la->ev_b, 0));
+      (*launches) += 3;
+    }
   }
   return cudaSuccess;
 }
@@ -412,7 +459,7 @@ cudaError_t lauum_blocked(const double *Minv, double *Rinv, int npad, int64_t sM
 cudaError_t launch_trmv(const double *M, int npad, int64_t sM, const double *x, int64_t sx,
                         double *y, int64_t sy, int n, int trans, int batch, cudaStream_t st) {
   if (!trans) k_trmv_n<<<dim3(npad / 8, batch), 256, 0, st>>>(M, npad, sM, x, sx, y, sy, n);
-  else k_trmv_t<<<dim3(npad / 128, batch), 128, 0, st>>>(M, npad, sM, x, sx, y, sy, n);
+  else k_trmv_t<<<dim3(npad / 32, batch), 1024, 0, st>>>(M, npad, sM, x, sx, y, sy, n);
   return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/mgp.h"
+#include "linalg.cuh"
 
 #define MGP_MAX_SETS 16
 #define MGP_MAX_D 64
@@ -30,6 +31,9 @@ struct mgp_handle {
   double kernel_ms[4] = {0, 0, 0, 0};   // rgen, trmm, epilogue/grad, topk
   int64_t kernel_calls[4] = {0, 0, 0, 0};
   int sm_count = 148;
+  cudaStream_t side_stream = nullptr;  // look-ahead stream of the blocked Cholesky
+  cudaEvent_t ev_la[2] = {nullptr, nullptr};
+  LookAhead la = {nullptr, nullptr, nullptr};
 
   // ---- training data -------------------------------------------------------------------
   int n = 0, d = 0, npad = 0, dpad = 0, NI = 0;

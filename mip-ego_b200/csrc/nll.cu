@@ -299,7 +299,7 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
     (*launches)++;
   }
   if (!w.have_L)
-    NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches));
+    NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches, w.la));
   NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches));
   double *Yt = w.vec, *Ft = w.vec + (int64_t)B * npad, *rho = w.vec + (int64_t)2 * B * npad,
          *gamma = w.vec + (int64_t)3 * B * npad;
