@@ -69,33 +69,58 @@ def flops_per_candidate(n, d):
 
 
 class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """One `nvidia-smi --query-gpu=... -lms 100` process started BEFORE the timed region (the recipe
+    of B200_PROFILING.md) and read line by line: no fork happens while steps are being launched."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows, self.proc = index, False, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        super().start()
+
+    def run(self):
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) >= 7 and not self.stop_flag:
+                self.rows.append(f)
+            if self.stop_flag:
+                break
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in out.stdout.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                self.proc.terminate()
+                self.proc.wait(timeout=5)
             except Exception:
                 pass
-            time.sleep(0.1)
 
     def summary(self):
-        if not self.rows:
+        rows = []
+        for r in self.rows:
+            try:
+                rows.append((float(r[0]), float(r[1]), float(r[2]), r[3:7]))
+            except ValueError:
+                pass
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(r[0] for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+        reasons = [nm for i, nm in enumerate(names) if any(r[3][i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][1], "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(r[2] for r in rows)}
 
 
 def cpu_port_rate(n, d, kind, crit, sets, sample, seed=10):
@@ -227,6 +252,8 @@ def run_nll(args, rank, world, local):
                             device=local)
     gp._check_data(X, y)
     h = gp._handle()
+    if args.nll_groups:
+        h.set_option("nll_groups", args.nll_groups)
     P_dev = torch.from_numpy(P).to(dev)
 
     def barrier():
@@ -255,8 +282,10 @@ def run_nll(args, rank, world, local):
                 dist.all_gather(g, out[0])
             ev[k][1].record()
         barrier()
-    sampler.stop_flag = True
+    sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in ev)
+    if os.environ.get("MGP_BENCH_DEBUG"):
+        print("per-step ms:", [round(a.elapsed_time(b), 2) for a, b in ev], file=sys.stderr)
     launches = h.counter("launches") - launches0
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -309,6 +338,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["nll"])
     ap.add_argument("--nll-n", type=int, default=4096)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--nll-groups", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -404,7 +434,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ms = timed_pass()
-    sampler.stop_flag = True
+    sampler.stop()
     launches = h.counter("launches") - launches0
     # second, separate pass with CUDA events around every kernel launch (inside the library, on the
     # launching stream): per-kernel durations for the roofline; not used for `value`

@@ -111,6 +111,11 @@ int mgp_create(int device, mgp_t **out_h) {
     delete h;
     return MGP_ECUDA;
   }
+  for (int i = 0; i < MGP_NLL_STREAMS; i++) {
+    cudaStreamCreateWithFlags(&h->nll_stream[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   for (int i = 0; i < 2; i++) {
     cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
@@ -139,6 +144,11 @@ int mgp_destroy(mgp_t *h) {
     if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     if (h->ev_la[i]) cudaEventDestroy(h->ev_la[i]);
   }
+  for (int i = 0; i < MGP_NLL_STREAMS; i++) {
+    if (h->nll_stream[i]) cudaStreamDestroy(h->nll_stream[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->out_stream) cudaStreamDestroy(h->out_stream);
@@ -154,6 +164,11 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
   if (!strcmp(name, "chunk")) {
     if (value < 0) return mgp_fail(h, MGP_EINVAL, "chunk must be >= 0");
     h->chunk_opt = round_up(value, 128);
+    return MGP_OK;
+  }
+  if (!strcmp(name, "nll_groups")) {
+    if (value < 0 || value > MGP_NLL_STREAMS) return mgp_fail(h, MGP_EINVAL, "nll_groups must be in 0..%d", MGP_NLL_STREAMS);
+    h->nll_groups_opt = (int)value;
     return MGP_OK;
   }
   if (!strcmp(name, "time_kernels")) {
@@ -277,20 +292,38 @@ static int check_par(mgp_handle *h, int n_par, int mode) {
   return 0;
 }
 
-static void fill_work(mgp_handle *h, NllWork &w, int B, int cap, int n_par, int mode,
+// Work descriptor for `B` parameter vectors living in workspace slots b_off .. b_off + B - 1 of a
+// workspace with capacity `cap`.  d_params / d_llf / d_grad point at the first vector of the slice.
+static void fill_work(mgp_handle *h, NllWork &w, int b_off, int B, int cap, int n_par, int mode,
                       double noise_var, int eval_grad, const double *d_params, double *d_llf,
                       double *d_grad) {
   memset(&w, 0, sizeof(w));
+  const size_t mat = (size_t)h->npad * h->npad, sec = (size_t)cap * h->npad;
+  const int ntiles = h->NI * (h->NI + 1) / 2;
   w.n = h->n; w.npad = h->npad; w.dpad = h->dpad; w.B = B; w.n_par = n_par; w.mode = mode;
   w.corr = h->corr; w.ordinary = h->trend == MGP_TREND_CONST_ESTIMATED; w.eval_grad = eval_grad;
   w.noise_var = noise_var; w.beta0 = h->beta0;
   w.Xc = P<double>(h->dXc); w.y = P<double>(h->dy); w.params = d_params;
-  w.R = P<double>(h->nR); w.L = P<double>(h->nL); w.M = P<double>(h->nM); w.T = P<double>(h->nT);
-  w.linv = P<double>(h->nLinvDiag); w.vec = P<double>(h->nvec); w.scal = P<double>(h->nscal);
-  w.gpart = P<double>(h->ngpart); w.status = nll_status_ptr(h, cap);
+  w.R = P<double>(h->nR) + b_off * mat; w.L = P<double>(h->nL) + b_off * mat;
+  w.M = P<double>(h->nM) + b_off * mat; w.T = P<double>(h->nT) + b_off * mat;
+  w.linv = P<double>(h->nLinvDiag) + (size_t)b_off * h->NI * 128 * 128;
+  double *v = P<double>(h->nvec) + (size_t)b_off * h->npad;
+  w.Yt = v; w.Ft = v + sec; w.rho = v + 2 * sec; w.gamma = v + 3 * sec;
+  w.scal = P<double>(h->nscal) + (size_t)b_off * nll_scal_doubles();
+  w.gpart = P<double>(h->ngpart) + (size_t)b_off * ntiles * (h->dpad + 1);
+  w.status = nll_status_ptr(h, cap) + b_off;
   w.out_llf = d_llf; w.out_grad = d_grad;
-  h->la.side = h->side_stream; h->la.ev_a = h->ev_la[0]; h->la.ev_b = h->ev_la[1];
-  w.la = &h->la;
+  w.la = nullptr;
+}
+
+// Number of concurrent batch groups: the factorisation of one group has long phases that occupy
+// only a few SMs (diagonal blocks, panel solves); running the groups on separate streams lets the
+// wide kernels of one group fill the machine while another group is in such a phase.
+static int nll_groups(const mgp_handle *h, int nb) {
+  int g = h->nll_groups_opt > 0 ? h->nll_groups_opt : 4;
+  if (g > MGP_NLL_STREAMS) g = MGP_NLL_STREAMS;
+  if (g > nb) g = nb;
+  return g < 1 ? 1 : g;
 }
 
 int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mode,
@@ -306,12 +339,26 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
   const int use = h->nll_cap;
   for (int b0 = 0; b0 < B; b0 += use) {
     const int nb = std::min(use, B - b0);
-    NllWork w;
-    fill_work(h, w, nb, use, n_par, mode, noise_var, eval_grad, d_params + (size_t)b0 * n_par,
-              d_out_llf + b0, eval_grad ? d_out_grad + (size_t)b0 * n_par : nullptr);
-    MGP_CUDA(h, nll_pipeline(w, st, &h->launches));
-    if (d_out_status)
-      MGP_CUDA(h, cudaMemcpyAsync(d_out_status + b0, w.status, sizeof(int) * nb, cudaMemcpyDeviceToDevice, st));
+    const int G = nll_groups(h, nb);
+    if (G > 1) MGP_CUDA(h, cudaEventRecord(h->ev_fork, st));
+    for (int g = 0; g < G; g++) {
+      const int g0 = (int)((int64_t)nb * g / G), g1 = (int)((int64_t)nb * (g + 1) / G);
+      if (g1 == g0) continue;
+      cudaStream_t gs = G > 1 ? h->nll_stream[g] : st;
+      if (G > 1) MGP_CUDA(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
+      NllWork w;
+      fill_work(h, w, g0, g1 - g0, use, n_par, mode, noise_var, eval_grad,
+                d_params + (size_t)(b0 + g0) * n_par, d_out_llf + b0 + g0,
+                eval_grad ? d_out_grad + (size_t)(b0 + g0) * n_par : nullptr);
+      MGP_CUDA(h, nll_pipeline(w, gs, &h->launches));
+      if (d_out_status)
+        MGP_CUDA(h, cudaMemcpyAsync(d_out_status + b0 + g0, w.status, sizeof(int) * (g1 - g0),
+                                    cudaMemcpyDeviceToDevice, gs));
+      if (G > 1) {
+        MGP_CUDA(h, cudaEventRecord(h->ev_join[g], gs));
+        MGP_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[g], 0));
+      }
+    }
   }
   return MGP_OK;
 }
@@ -364,7 +411,7 @@ static int adopt_slot0(mgp_handle *h, const double *theta_host, bool take_gamma)
   cudaStream_t st = h->stream;
   const size_t mat = (size_t)h->npad * h->npad * 8, vec = (size_t)h->npad * 8;
   const double *v = P<double>(h->nvec);
-  const int B = 1;  // slot 0 of a batch-1 run
+  const int B = h->nll_cap;  // section stride of the vector workspace; slot 0 is used
   MGP_CUDA(h, cudaMemcpyAsync(h->dL.p, h->nL.p, mat, cudaMemcpyDeviceToDevice, st));
   MGP_CUDA(h, cudaMemcpyAsync(h->dMinv.p, h->nM.p, mat, cudaMemcpyDeviceToDevice, st));
   MGP_CUDA(h, cudaMemcpyAsync(h->dYt.p, v, vec, cudaMemcpyDeviceToDevice, st));
@@ -398,7 +445,7 @@ int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double no
   cudaStream_t st = h->stream;
   MGP_CUDA(h, cudaMemcpyAsync(h->npar.p, par, (size_t)n_par * 8, cudaMemcpyHostToDevice, st));
   NllWork w;
-  fill_work(h, w, 1, h->nll_cap, n_par, mode, noise_var, 0, P<double>(h->npar), nullptr, nullptr);
+  fill_work(h, w, 0, 1, h->nll_cap, n_par, mode, noise_var, 0, P<double>(h->npar), nullptr, nullptr);
   MGP_CUDA(h, nll_pipeline(w, st, &h->launches));
   std::vector<double> sc(nll_scal_doubles());
   int status = 0;
@@ -443,7 +490,7 @@ int mgp_set_state(mgp_t *h, const double *theta, const double *L, const double *
   MGP_TRY(mgp_ensure(h, h->npar, dummy.size() * 8 + 64));
   MGP_CUDA(h, cudaMemcpyAsync(h->npar.p, dummy.data(), dummy.size() * 8, cudaMemcpyHostToDevice, st));
   NllWork w;
-  fill_work(h, w, 1, h->nll_cap, h->d, MGP_MODE_NOISELESS, 0.0, 0, P<double>(h->npar), nullptr, nullptr);
+  fill_work(h, w, 0, 1, h->nll_cap, h->d, MGP_MODE_NOISELESS, 0.0, 0, P<double>(h->npar), nullptr, nullptr);
   w.have_L = 1;
   MGP_CUDA(h, nll_pipeline(w, st, &h->launches));
   std::vector<double> sc(nll_scal_doubles());

@@ -5,208 +5,476 @@
 //   linalg.cholesky          gpr.py:681      -> chol_blocked
 //   solve_triangular(L, .)   gpr.py:463,685,690,694 -> explicit L^-1 (trtri_blocked) + trmv / TRMM
 //   cho_solve((L,True), I)   gpr.py:899      -> lauum_blocked (R^-1 = L^-T L^-1)
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "linalg.cuh"
 #include "mgp_common.cuh"
 
 namespace {
 
-constexpr int GK = 16;        // k extent of one pipeline stage
-constexpr int GSTAGES = 3;
-constexpr int LDK = 20;       // row stride of a k-contiguous tile  [128][16] (conflict-free frags)
-constexpr int LDM = 132;      // row stride of a k-major tile       [16][128]
-constexpr int TILE_DBL = 2560;
+// ---- persistent, warp-specialised DMMA GEMM ---------------------------------------------------
+// One CTA per SM: 8 consumer warps (2 x 4 over a 128 x 128 output tile, 64 accumulator registers
+// per thread) and a producer warpgroup that streams 16-k stages of both operands into a ring of
+// shared-memory buffers with cp.async, each thread's copies completing on the stage's mbarrier
+// (cp.async.mbarrier.arrive.noinc).  There is no CTA-wide barrier in the loop: consumer warps
+// wait on "full", release on "empty", and the producers run ahead across tile boundaries, so the
+// epilogue (and prologue) of one tile overlaps the loads of the next.  Tiles are handed out
+// dynamically (atomic counter, longest-k tiles first) through a two-slot mailbox in shared memory.
+//
+// Operand staging (strides chosen so that every LDS.128 below is bank-conflict free):
+//   k-contiguous operand ([128][16], row stride LDK = 24): one LDS.128 per lane feeds two MMA
+//     k-steps:  MMA step (p, s), lane k-index lk  <->  stage k = 8 p + 2 lk + s   (both operands);
+//   k-major operand ([16][128], row stride LDM = 130): one LDS.128 at row k(p, s) yields two
+//     neighbouring rows (columns) m, m + 1 which feed two MMAs; the tile's rows (columns) are
+//     therefore processed in the permuted order 16 g + 2 lr + e  (g: pair group, e: even/odd MMA).
+constexpr int GK = 16;         // k extent of one pipeline stage
+constexpr int NST = 4;         // pipeline stages
+constexpr int LDK = 24;
+constexpr int LDM = 130;
+constexpr int OP_DBL = 128 * LDK;   // doubles per operand per stage (>= 16 * LDM)
+constexpr int GEMM_CONSUMERS = 256, GEMM_PRODUCERS = 128;
+constexpr int GEMM_SMEM = NST * 2 * OP_DBL * 8 + (2 * NST + 4) * 8 + 16;
+
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord { int rowblk, colblk, z; };
+__device__ __forceinline__ TileCoord decode_tile(const GemmDesc &g, int id, int tx, int ty, int nz) {
+  TileCoord t;
+  t.z = id % nz;
+  const int r = id / nz;
+  if (g.order == 3) { t.colblk = r / ty; t.rowblk = r % ty; }             // column-major, ascending
+  else if (g.order == 2) { t.rowblk = ty - 1 - r / tx; t.colblk = r % tx; }  // rows descending
+  else { t.rowblk = r / tx; t.colblk = r % tx; }                            // rows ascending
+  return t;
+}
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256) k_dgemm(GemmDesc g) {
-  extern __shared__ __align__(16) double sm[];
-  double *As = sm;
-  double *Bs = sm + GSTAGES * TILE_DBL;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wr = warp >> 2, wc = warp & 3;
-  const int rowblk = blockIdx.y, colblk = blockIdx.x;
-  if (g.lower_only && colblk > rowblk) return;
-  const int inner = blockIdx.z % g.n_inner, outer = blockIdx.z / g.n_inner;
-  const double *A = g.A + inner * g.sA_in + outer * g.sA_out;
-  const double *B = g.B + inner * g.sB_in + outer * g.sB_out;
-  double *C = g.C + inner * g.sC_in + outer * g.sC_out;
-  const int i0 = rowblk * 128, j0 = colblk * 128;
-  int klo = 0, khi = g.K;
-  if (g.kmode & 1) klo = colblk * 128;
-  if (g.kmode & 4) klo = max(klo, rowblk * 128);
-  if (g.kmode & 2) khi = min(khi, (rowblk + 1) * 128);
-  const int nk = max(0, (khi - klo) / GK);
+__global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(GemmDesc g, int *sched_g) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double *As = reinterpret_cast<double *>(smraw);
+  double *Bs = As + NST * OP_DBL;
+  uint64_t *full = reinterpret_cast<uint64_t *>(Bs + NST * OP_DBL);
+  uint64_t *empty = full + NST;
+  uint64_t *sfull = empty + NST;      // tile mailbox: 2 slots
+  uint64_t *sempty = sfull + 2;
+  int *slot_id = reinterpret_cast<int *>(sempty + 2);
 
-  auto load_tile = [&](int stage, int kt) {
-    const int k0 = klo + kt * GK;
-    double *as = As + stage * TILE_DBL, *bs = Bs + stage * TILE_DBL;
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int c = tid + 256 * u;
-      if (!TA) {
-        const int row = c >> 3, kc = c & 7;
-        cp_async16(as + row * LDK + kc * 2, A + (int64_t)(i0 + row) * g.lda + k0 + kc * 2);
-      } else {
-        const int kr = c >> 6, mc = c & 63;
-        cp_async16(as + kr * LDM + mc * 2, A + (int64_t)(k0 + kr) * g.lda + i0 + mc * 2);
-      }
-      if (!TB) {
-        const int row = c >> 3, kc = c & 7;
-        cp_async16(bs + row * LDK + kc * 2, B + (int64_t)(j0 + row) * g.ldb + k0 + kc * 2);
-      } else {
-        const int kr = c >> 6, mc = c & 63;
-        cp_async16(bs + kr * LDM + mc * 2, B + (int64_t)(k0 + kr) * g.ldb + j0 + mc * 2);
-      }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = g.N / 128, ty = g.M / 128, nz = g.n_inner * g.n_outer;
+  const int total = tx * ty * nz;
+  constexpr int NWARPS = (GEMM_CONSUMERS + GEMM_PRODUCERS) / 32;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; s++) {
+      mbar_init(&full[s], GEMM_PRODUCERS);
+      mbar_init(&empty[s], GEMM_CONSUMERS / 32);
     }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&sfull[s], 1);
+      mbar_init(&sempty[s], NWARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const bool producer = warp >= GEMM_CONSUMERS / 32;
+  const bool leader = tid == GEMM_CONSUMERS;   // lane 0 of the first producer warp
+
+  // next tile id through the mailbox (-1: no more tiles); every warp of the CTA calls this once
+  // per tile, the leader thread fetches from the global counter
+  auto next_tile = [&](int q) -> int {
+    const int slot = q & 1;
+    if (leader) {
+      if (q >= 2) mbar_wait(&sempty[slot], (uint32_t)(((q >> 1) - 1) & 1));
+      int id;
+      for (;;) {
+        id = atomicAdd(&sched_g[0], 1);
+        if (id >= total) { id = -1; break; }
+        if (!g.lower_only) break;
+        const TileCoord t = decode_tile(g, id, tx, ty, nz);
+        if (t.colblk <= t.rowblk) break;
+      }
+      slot_id[slot] = id;
+      mbar_arrive(&sfull[slot]);
+    }
+    mbar_wait(&sfull[slot], (uint32_t)((q >> 1) & 1));
+    const int id = slot_id[slot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sempty[slot]);
+    return id;
+  };
+  auto k_range = [&](const TileCoord &t, int &klo, int &nk) {
+    int khi = g.K;
+    klo = 0;
+    if (g.kmode & 1) klo = t.colblk * 128;
+    if (g.kmode & 4) klo = max(klo, t.rowblk * 128);
+    if (g.kmode & 2) khi = min(khi, (t.rowblk + 1) * 128);
+    nk = max(0, (khi - klo) / GK);
   };
 
-  double acc[8][4][2];
+  if (producer) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    const int ptid = tid - GEMM_CONSUMERS;
+    int64_t x = 0;
+    for (int q = 0;; q++) {
+      const int id = next_tile(q);
+      if (id < 0) break;
+      const TileCoord t = decode_tile(g, id, tx, ty, nz);
+      const int inner = t.z % g.n_inner, outer = t.z / g.n_inner;
+      const int i0 = t.rowblk * 128, j0 = t.colblk * 128;
+      int klo, nk;
+      k_range(t, klo, nk);
+      const double *A = g.A + inner * g.sA_in + outer * g.sA_out;
+      const double *B = g.B + inner * g.sB_in + outer * g.sB_out;
+      for (int kt = 0; kt < nk; kt++, x++) {
+        const int stage = (int)(x % NST);
+        if (x >= NST) mbar_wait(&empty[stage], (uint32_t)(((x / NST) - 1) & 1));
+        const int k0 = klo + kt * GK;
+        double *as = As + stage * OP_DBL, *bs = Bs + stage * OP_DBL;
 #pragma unroll
-  for (int r = 0; r < 8; r++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) acc[r][c][0] = acc[r][c][1] = 0.0;
-
-#pragma unroll
-  for (int s = 0; s < GSTAGES - 1; s++) {
-    if (s < nk) load_tile(s, s);
-    cp_async_commit();
-  }
-  const int lr = lane >> 2, lk = lane & 3;
-  for (int kt = 0; kt < nk; kt++) {
-    cp_async_wait<GSTAGES - 2>();
-    __syncthreads();
-    if (kt + GSTAGES - 1 < nk) load_tile((kt + GSTAGES - 1) % GSTAGES, kt + GSTAGES - 1);
-    cp_async_commit();
-    const double *as = As + (kt % GSTAGES) * TILE_DBL, *bs = Bs + (kt % GSTAGES) * TILE_DBL;
-#pragma unroll
-    for (int ks = 0; ks < 4; ks++) {
-      double a[8], b[4];
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-        a[r] = TA ? as[(ks * 4 + lk) * LDM + wr * 64 + r * 8 + lr]
-                  : as[(wr * 64 + r * 8 + lr) * LDK + ks * 4 + lk];
-#pragma unroll
-      for (int c = 0; c < 4; c++)
-        b[c] = TB ? bs[(ks * 4 + lk) * LDM + wc * 32 + c * 8 + lr]
-                  : bs[(wc * 32 + c * 8 + lr) * LDK + ks * 4 + lk];
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) dmma884(acc[r][c][0], acc[r][c][1], a[r], b[c]);
-    }
-  }
-  cp_async_wait<0>();
-#pragma unroll
-  for (int r = 0; r < 8; r++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const int row = i0 + wr * 64 + r * 8 + lr, col = j0 + wc * 32 + c * 8 + 2 * lk;
-      double2 *ptr = reinterpret_cast<double2 *>(C + (int64_t)row * g.ldc + col);
-      double2 v = make_double2(g.alpha * acc[r][c][0], g.alpha * acc[r][c][1]);
-      if (g.beta != 0.0) {
-        const double2 o = *ptr;
-        v.x += g.beta * o.x;
-        v.y += g.beta * o.y;
+        for (int u = 0; u < 8; u++) {
+          const int c = ptid + GEMM_PRODUCERS * u;
+          if (!TA) {
+            const int row = c >> 3, kc = c & 7;
+            cp_async16(as + row * LDK + kc * 2, A + (int64_t)(i0 + row) * g.lda + k0 + kc * 2);
+          } else {
+            const int kr = c >> 6, mc = c & 63;
+            cp_async16(as + kr * LDM + mc * 2, A + (int64_t)(k0 + kr) * g.lda + i0 + mc * 2);
+          }
+          if (!TB) {
+            const int row = c >> 3, kc = c & 7;
+            cp_async16(bs + row * LDK + kc * 2, B + (int64_t)(j0 + row) * g.ldb + k0 + kc * 2);
+          } else {
+            const int kr = c >> 6, mc = c & 63;
+            cp_async16(bs + kr * LDM + mc * 2, B + (int64_t)(k0 + kr) * g.ldb + j0 + mc * 2);
+          }
+        }
+        cp_async_mbar_arrive(&full[stage]);
       }
-      *ptr = v;
     }
+    // the last CTA to finish re-arms the scheduler words for the next launch on this stream
+    if (leader) {
+      __threadfence();
+      if (atomicAdd(&sched_g[1], 1) == (int)gridDim.x - 1) {
+        sched_g[0] = 0;
+        sched_g[1] = 0;
+        __threadfence();
+      }
+    }
+    return;
+  }
+
+  // ---- consumers --------------------------------------------------------------------------------
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+  const int wr = warp >> 2, wc = warp & 3, lr = lane >> 2, lk = lane & 3;
+  int64_t x = 0;
+  for (int q = 0;; q++) {
+    const int id = next_tile(q);
+    if (id < 0) break;
+    const TileCoord t = decode_tile(g, id, tx, ty, nz);
+    const int inner = t.z % g.n_inner, outer = t.z / g.n_inner;
+    const int i0 = t.rowblk * 128, j0 = t.colblk * 128;
+    int klo, nk;
+    k_range(t, klo, nk);
+    double acc[8][4][2];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+    for (int kt = 0; kt < nk; kt++, x++) {
+      const int stage = (int)(x % NST);
+      mbar_wait(&full[stage], (uint32_t)((x / NST) & 1));
+      const double *as = As + stage * OP_DBL, *bs = Bs + stage * OP_DBL;
+#pragma unroll
+      for (int p = 0; p < 2; p++) {
+        double2 a[8], b[4];   // TA/TB == 0: [tile] = (step 0, step 1);  == 1: [2 s + group] = (even, odd)
+        if (!TA) {
+#pragma unroll
+          for (int rt = 0; rt < 8; rt++)
+            a[rt] = *reinterpret_cast<const double2 *>(as + (wr * 64 + rt * 8 + lr) * LDK + 8 * p + 2 * lk);
+        } else {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+            for (int rp = 0; rp < 4; rp++)
+              a[4 * s2 + rp] = *reinterpret_cast<const double2 *>(
+                  as + (8 * p + 2 * lk + s2) * LDM + wr * 64 + 16 * rp + 2 * lr);
+        }
+        if (!TB) {
+#pragma unroll
+          for (int ct = 0; ct < 4; ct++)
+            b[ct] = *reinterpret_cast<const double2 *>(bs + (wc * 32 + ct * 8 + lr) * LDK + 8 * p + 2 * lk);
+        } else {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+            for (int cp = 0; cp < 2; cp++)
+              b[2 * s2 + cp] = *reinterpret_cast<const double2 *>(
+                  bs + (8 * p + 2 * lk + s2) * LDM + wc * 32 + 16 * cp + 2 * lr);
+        }
+#pragma unroll
+        for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+          for (int rt = 0; rt < 8; rt++) {
+            const double av = TA ? ((rt & 1) ? a[4 * s2 + (rt >> 1)].y : a[4 * s2 + (rt >> 1)].x)
+                                 : (s2 ? a[rt].y : a[rt].x);
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) {
+              const double bv = TB ? ((ct & 1) ? b[2 * s2 + (ct >> 1)].y : b[2 * s2 + (ct >> 1)].x)
+                                   : (s2 ? b[ct].y : b[ct].x);
+              dmma884(acc[rt][ct][0], acc[rt][ct][1], av, bv);
+            }
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+
+    // ---- epilogue: C = alpha * acc + beta * C -------------------------------------------------
+    double *C = g.C + inner * g.sC_in + outer * g.sC_out;
+#pragma unroll
+    for (int rt = 0; rt < 8; rt++) {
+      const int row = i0 + wr * 64 + (TA ? 16 * (rt >> 1) + 2 * lr + (rt & 1) : rt * 8 + lr);
+      double *crow = C + (int64_t)row * g.ldc + j0 + wc * 32;
+      if (!TB) {
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+          double2 *ptr = reinterpret_cast<double2 *>(crow + ct * 8 + 2 * lk);
+          double2 v = make_double2(g.alpha * acc[rt][ct][0], g.alpha * acc[rt][ct][1]);
+          if (g.beta != 0.0) {
+            const double2 o = *ptr;
+            v.x += g.beta * o.x;
+            v.y += g.beta * o.y;
+          }
+          *ptr = v;
+        }
+      } else {
+#pragma unroll
+        for (int cp = 0; cp < 2; cp++) {
+          double2 *ptr = reinterpret_cast<double2 *>(crow + 16 * cp + 4 * lk);
+          double2 v0 = make_double2(g.alpha * acc[rt][2 * cp][0], g.alpha * acc[rt][2 * cp + 1][0]);
+          double2 v1 = make_double2(g.alpha * acc[rt][2 * cp][1], g.alpha * acc[rt][2 * cp + 1][1]);
+          if (g.beta != 0.0) {
+            const double2 o0 = ptr[0], o1 = ptr[1];
+            v0.x += g.beta * o0.x; v0.y += g.beta * o0.y;
+            v1.x += g.beta * o1.x; v1.y += g.beta * o1.y;
+          }
+          ptr[0] = v0;
+          ptr[1] = v1;
+        }
+      }
+    }
+  }
+
 }
 
-// ---- 128x128 diagonal block: Cholesky (dpotf2-style, right looking) and in-place inverse ----
-constexpr int DS = 129;  // smem row stride
+// ---- 128x128 diagonal block: Cholesky + inverse, sub-blocked by 32 ---------------------------
+// The serial critical path of the blocked Cholesky.  One CTA (512 threads) per matrix:
+//   for each 32-wide sub-column: warp 0 factors the 32x32 diagonal sub-block in registers (lane =
+//   row, the pivot column travels through 32 doubles of shared memory) and inverts it (lane =
+//   column of the inverse, forward substitution); all warps then form the sub-panel
+//   P = A D^-T and the symmetric update of the remaining rows.
+// The inverse of the whole block follows from the four 32x32 inverses by block rows:
+//   X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj).
+constexpr int DS = 129;   // smem row stride of the 128x128 block
+constexpr int XS = 33;    // row stride of a 32x32 inverse
+constexpr int DIAG_THREADS = 512;
+constexpr int kDiagSmemDbl = 128 * DS + 4 * 32 * XS + 64 + 4 * 32;
 
-// 1024 threads: 8 lanes per row (i = tid / 8, part = tid % 8), partial sums combined by shuffles.
-__device__ void diag_inverse_inplace(double *S, int tid) {
-  // X = L^-1 in place, columns from last to first:
-  //   X_jj = 1/L_jj ;  X_ij = -(sum_{k=j+1..i} X_ik L_kj) / L_jj   (i > j)
-  const int i = tid >> 3, part = tid & 7;
-  for (int j = 127; j >= 0; j--) {
-    const double inv = 1.0 / S[j * DS + j];
-    double t = 0.0;
-    if (i > j)
-      for (int k = j + 1 + part; k <= i; k += 8) t = fma(S[i * DS + k], S[k * DS + j], t);
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    t += __shfl_xor_sync(0xffffffffu, t, 4);
+__device__ __forceinline__ void warp_potrf32(double *D, double *col, int lane, int pivot0,
+                                             int *status) {
+  // Straight-line code (fully unrolled, no branches): the critical path per pivot is
+  // shuffle -> rsqrt -> multiply -> smem broadcast -> one FMA; the remaining updates of the step
+  // overlap the next pivot's latency.  `col` is double-buffered (2 x 32 doubles).
+  double a[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) a[k] = D[lane * DS + k];
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const double d = __shfl_sync(0xffffffffu, a[j], j);
+    bad = (bad == 0 && !(d > 0.0)) ? pivot0 + j + 1 : bad;
+    const double inv = rsqrt(d);
+    const double l = (lane == j) ? d * inv : a[j] * inv;
+    a[j] = l;
+    double *cb = col + (j & 1) * 32;
+    cb[lane] = l;
+    __syncwarp();
+#pragma unroll
+    for (int k = j + 1; k < 32; k++) a[k] = fma(-l, cb[k], a[k]);
+  }
+  if (bad && lane == 0) atomicCAS(status, 0, bad);
+#pragma unroll
+  for (int k = 0; k < 32; k++) D[lane * DS + k] = (k <= lane) ? a[k] : 0.0;
+}
+
+// X = D^-1 for a 32x32 lower-triangular D (stride DS); lane owns column `lane` of X.
+__device__ __forceinline__ void warp_trtri32(const double *D, double *X, double *rdiag, int lane) {
+  rdiag[lane] = 1.0 / D[lane * DS + lane];
+  __syncwarp();
+  double x[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    double s[4] = {(i == lane) ? 1.0 : 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < i; k++) s[k & 3] = fma(-D[i * DS + k], x[k], s[k & 3]);
+    x[i] = ((s[0] + s[1]) + (s[2] + s[3])) * rdiag[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 32; i++) X[i * XS + lane] = (lane <= i) ? x[i] : 0.0;
+}
+
+// S holds L (lower, 128x128, stride DS), Xd the four 32x32 diagonal inverses.  On return S holds
+// L^-1 (lower part; the strictly upper part is unspecified).
+__device__ void diag_block_inverse(double *S, const double *Xd, int tid) {
+  for (int idx = tid; idx < 4 * 32 * 32; idx += DIAG_THREADS) {
+    const int s = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
+    S[(32 * s + r) * DS + 32 * s + c] = Xd[s * 32 * XS + r * XS + c];
+  }
+  __syncthreads();
+  for (int i = 1; i < 4; i++) {
+    // T_ij = sum_{k=j}^{i-1} L_ik X_kj for all j < i, from the untouched L blocks of block row i
+    double t[3][2];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        t[j][u] = 0.0;
+        if (j < i) {
+          const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
+          double acc = 0.0;
+          for (int m = 32 * j; m < 32 * i; m++)
+            acc = fma(S[(32 * i + r) * DS + m], S[m * DS + 32 * j + c], acc);
+          t[j][u] = acc;
+        }
+      }
     __syncthreads();
-    if (part == 0) {
-      if (i > j) S[i * DS + j] = -t * inv;
-      if (i == j) S[j * DS + j] = inv;
-    }
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int u = 0; u < 2; u++)
+        if (j < i) {
+          const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
+          S[(32 * i + r) * DS + 32 * j + c] = t[j][u];
+        }
+    __syncthreads();
+    // X_ij = -X_ii T_ij
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int u = 0; u < 2; u++)
+        if (j < i) {
+          const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
+          double acc = 0.0;
+          for (int q = 0; q <= r; q++)
+            acc = fma(S[(32 * i + r) * DS + 32 * i + q], S[(32 * i + q) * DS + 32 * j + c], acc);
+          t[j][u] = -acc;
+        }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int u = 0; u < 2; u++)
+        if (j < i) {
+          const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
+          S[(32 * i + r) * DS + 32 * j + c] = t[j][u];
+        }
     __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(1024) k_potrf_diag(double *A, double *Lout, int ld, int64_t sA,
-                                                     double *linv, int64_t sInv, int kb,
-                                                     int *status) {
+__global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag(double *A, double *Lout, int ld,
+                                                              int64_t sA, double *linv,
+                                                              int64_t sInv, int kb, int *status) {
   extern __shared__ __align__(16) double S[];
-  const int tid = threadIdx.x, b = blockIdx.x;
+  double *Xd = S + 128 * DS, *col = Xd + 4 * 32 * XS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   const double *Ab = A + b * sA + (int64_t)kb * 128 * ld + kb * 128;
   double *Lb = Lout + b * sA + (int64_t)kb * 128 * ld + kb * 128;
-  for (int idx = tid; idx < 128 * 128; idx += 1024) {
+  for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
     S[r * DS + c] = (c <= r) ? Ab[(int64_t)r * ld + c] : 0.0;
   }
   __syncthreads();
-  // dpotf2-style right-looking Cholesky; the trailing update of step j is spread over 8 column
-  // phases per row (i = tid % 128, phase = tid / 128) and batched 4 deep to overlap smem latency
-  const int i = tid & 127, ph = tid >> 7;
-  for (int j = 0; j < 128; j++) {
-    const double ajj = S[j * DS + j];
-    if (!(ajj > 0.0)) {
-      if (tid == 0) atomicCAS(&status[b], 0, kb * 128 + j + 1);
-    }
-    const double dj = sqrt(ajj);
-    const double rinv = 1.0 / dj;
-    __syncthreads();
-    if (ph == 0) {
-      if (i > j) S[i * DS + j] *= rinv;
-      if (i == j) S[j * DS + j] = dj;
+  for (int s = 0; s < 4; s++) {
+    const int o = 32 * s, nb = 96 - o;   // nb rows below the sub-block
+    if (warp == 0) {
+      warp_potrf32(S + o * DS + o, col, lane, kb * 128 + o, &status[b]);
+      __syncwarp();
+      warp_trtri32(S + o * DS + o, Xd + s * 32 * XS, col + 64, lane);
     }
     __syncthreads();
-    if (i > j) {
-      const double lij = S[i * DS + j];
-      int k = j + 1 + ph;
-      for (; k + 24 <= i; k += 32) {
-        const double c0 = S[k * DS + j], c1 = S[(k + 8) * DS + j], c2 = S[(k + 16) * DS + j],
-                     c3 = S[(k + 24) * DS + j];
-        const double a0 = S[i * DS + k], a1 = S[i * DS + k + 8], a2 = S[i * DS + k + 16],
-                     a3 = S[i * DS + k + 24];
-        S[i * DS + k] = fma(-lij, c0, a0);
-        S[i * DS + k + 8] = fma(-lij, c1, a1);
-        S[i * DS + k + 16] = fma(-lij, c2, a2);
-        S[i * DS + k + 24] = fma(-lij, c3, a3);
+    if (nb > 0) {
+      // sub-panel P = A[below][o:o+32] D^-T : P[r][c] = sum_{k<=c} A[r][o+k] X[c][k]
+      const double *X = Xd + s * 32 * XS;
+      double pv[6];
+#pragma unroll
+      for (int u = 0; u < 6; u++) {
+        const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
+        double acc = 0.0;
+        if (r < nb) {
+          const double *arow = S + (o + 32 + r) * DS + o;
+          for (int k = 0; k <= c; k++) acc = fma(arow[k], X[c * XS + k], acc);
+        }
+        pv[u] = acc;
       }
-      for (; k <= i; k += 8) S[i * DS + k] = fma(-lij, S[k * DS + j], S[i * DS + k]);
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 6; u++) {
+        const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
+        if (r < nb) S[(o + 32 + r) * DS + o + c] = pv[u];
+      }
+      __syncthreads();
+      // symmetric update of the remaining rows: A[r][c] -= sum_k P[r][k] P[c][k]  (c <= r)
+      for (int e = tid; e < nb * nb; e += DIAG_THREADS) {
+        const int r = e / nb, c = e - r * nb;
+        if (c > r) continue;
+        const double *pr = S + (o + 32 + r) * DS + o, *pc = S + (o + 32 + c) * DS + o;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 32; k += 2) {
+          a0 = fma(pr[k], pc[k], a0);
+          a1 = fma(pr[k + 1], pc[k + 1], a1);
+        }
+        S[(o + 32 + r) * DS + o + 32 + c] -= a0 + a1;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
-  for (int idx = tid; idx < 128 * 128; idx += 1024) {
+  for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
-    Lb[(int64_t)r * ld + c] = S[r * DS + c];
+    Lb[(int64_t)r * ld + c] = (c <= r) ? S[r * DS + c] : 0.0;
   }
   __syncthreads();
-  diag_inverse_inplace(S, tid);
+  diag_block_inverse(S, Xd, tid);
   double *Ib = linv + b * sInv + (int64_t)kb * 128 * 128;
-  for (int idx = tid; idx < 128 * 128; idx += 1024) {
+  for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
     Ib[idx] = (c <= r) ? S[r * DS + c] : 0.0;
   }
 }
 
-__global__ void __launch_bounds__(1024) k_trtri_diag(const double *L, int ld, int64_t sL,
-                                                     double *linv, int64_t sInv) {
+__global__ void __launch_bounds__(DIAG_THREADS) k_trtri_diag(const double *L, int ld, int64_t sL,
+                                                              double *linv, int64_t sInv) {
   extern __shared__ __align__(16) double S[];
-  const int tid = threadIdx.x, kb = blockIdx.x, b = blockIdx.y;
+  double *Xd = S + 128 * DS, *col = Xd + 4 * 32 * XS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kb = blockIdx.x, b = blockIdx.y;
   const double *Lb = L + b * sL + (int64_t)kb * 128 * ld + kb * 128;
-  for (int idx = tid; idx < 128 * 128; idx += 1024) {
+  for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
     S[r * DS + c] = (c <= r) ? Lb[(int64_t)r * ld + c] : 0.0;
   }
   __syncthreads();
-  diag_inverse_inplace(S, tid);
+  if (warp < 4) warp_trtri32(S + 32 * warp * DS + 32 * warp, Xd + warp * 32 * XS, col + 64 + 32 * warp, lane);
+  __syncthreads();
+  diag_block_inverse(S, Xd, tid);
   double *Ib = linv + b * sInv + (int64_t)kb * 128 * 128;
-  for (int idx = tid; idx < 128 * 128; idx += 1024) {
+  for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
     Ib[idx] = (c <= r) ? S[r * DS + c] : 0.0;
   }
@@ -288,26 +556,51 @@ __global__ void __launch_bounds__(1024) k_pack_sym(const double *Rinv, int n, in
 }  // namespace
 
 // ---- launchers ------------------------------------------------------------------------------
+// Scheduler words {next tile, finished CTAs} per stream: kernels on one stream run back to back and
+// re-arm the words themselves; concurrent streams (batch groups) must not share them.
+static int *sched_words(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, int *> table;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(dev, st);
+  auto it = table.find(key);
+  if (it != table.end()) return it->second;
+  int *p = nullptr;
+  if (cudaMalloc(&p, 2 * sizeof(int)) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, 2 * sizeof(int));   // synchronous: visible before any later launch
+  table[key] = p;
+  return p;
+}
+
 cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   static bool attr_done = false;
-  const int smem = 2 * GSTAGES * TILE_DBL * sizeof(double);
+  static int sm_count = 0;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_dgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_dgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_dgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_dgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(k_dgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(k_dgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     attr_done = true;
   }
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-  dim3 grid(g.N / 128, g.M / 128, g.n_inner * g.n_outer);
-  if (!g.ta && !g.tb) k_dgemm<false, false><<<grid, 256, smem, st>>>(g);
-  else if (!g.ta && g.tb) k_dgemm<false, true><<<grid, 256, smem, st>>>(g);
-  else if (g.ta && !g.tb) k_dgemm<true, false><<<grid, 256, smem, st>>>(g);
-  else k_dgemm<true, true><<<grid, 256, smem, st>>>(g);
+  int *sched = sched_words(st);
+  if (!sched) return cudaErrorMemoryAllocation;
+  const int total = (g.N / 128) * (g.M / 128) * g.n_inner * g.n_outer;
+  const int grid = total < sm_count ? total : sm_count;
+  const int threads = GEMM_CONSUMERS + GEMM_PRODUCERS;
+  if (!g.ta && !g.tb) k_dgemm<false, false><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  else if (!g.ta && g.tb) k_dgemm<false, true><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  else if (g.ta && !g.tb) k_dgemm<true, false><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  else k_dgemm<true, true><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   return cudaGetLastError();
 }
 
-static const int kDiagSmem = 128 * DS * sizeof(double);
+static const int kDiagSmem = kDiagSmemDbl * sizeof(double);
 
 cudaError_t launch_potrf_diag(double *A, double *Lout, int ld, int64_t sA, double *linv,
                               int64_t sInv, int kb, int *status, int batch, cudaStream_t st) {
@@ -317,7 +610,7 @@ cudaError_t launch_potrf_diag(double *A, double *Lout, int ld, int64_t sA, doubl
     cudaFuncSetAttribute(k_trtri_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     attr_done = true;
   }
-  k_potrf_diag<<<batch, 1024, kDiagSmem, st>>>(A, Lout, ld, sA, linv, sInv, kb, status);
+  k_potrf_diag<<<batch, DIAG_THREADS, kDiagSmem, st>>>(A, Lout, ld, sA, linv, sInv, kb, status);
   return cudaGetLastError();
 }
 
@@ -329,7 +622,7 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
     cudaFuncSetAttribute(k_trtri_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     attr_done = true;
   }
-  k_trtri_diag<<<dim3(NI, batch), 1024, kDiagSmem, st>>>(L, ld, sL, linv, sInv);
+  k_trtri_diag<<<dim3(NI, batch), DIAG_THREADS, kDiagSmem, st>>>(L, ld, sL, linv, sInv);
   return cudaGetLastError();
 }
 
@@ -342,57 +635,62 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
                          const LookAhead *la) {
-  // Right-looking blocked Cholesky, block 128.  With look-ahead the trailing update of step kb is
-  // split: the next block column is updated first, then the (serial, single-CTA) factorisation
-  // of the next diagonal block runs on a side stream while the rest of the update proceeds.
-  const int NI = npad / 128;
+  // Two-level right-looking blocked Cholesky.  Tiles are 128 wide; PB tiles form a panel.  Inside a
+  // panel every tile column is factored (diagonal block, TRSM through the explicit inverse of the
+  // diagonal block) and applied to the remaining columns OF THE PANEL only (k = 128); the matrix
+  // right of the panel then receives one update with k = PB*128, which reads and writes every
+  // trailing tile PB times less often than a tile-by-tile right-looking sweep.
+  (void)la;
+  const int NI = npad / 128, PB = 4;
   for (int b = 0; b < batch; b++)
     LA_TRY(cudaMemsetAsync(L + b * sA, 0, sizeof(double) * (size_t)npad * npad, st));
-  const bool ahead = la && la->side && NI > 2;
-  LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, 0, status, batch, st));
-  (*launches)++;
-  for (int kb = 0; kb < NI - 1; kb++) {
-    const int below = NI - 1 - kb;
-    const int64_t off_panel = (int64_t)(kb + 1) * 128 * npad + (int64_t)kb * 128;
-    GemmDesc g = {};
-    // panel: L[kb+1:, kb] = A[kb+1:, kb] * inv(L_kk)^T
-    g.A = A + off_panel; g.lda = npad; g.ta = 0;
-    g.B = linv + (int64_t)kb * 128 * 128; g.ldb = 128; g.tb = 0;
-    g.C = L + off_panel; g.ldc = npad;
-    g.M = below * 128; g.N = 128; g.K = 128;
-    g.alpha = 1.0; g.beta = 0.0; g.kmode = 0; g.lower_only = 0;
-    g.n_inner = 1; g.n_outer = batch;
-    g.sA_out = sA; g.sB_out = sInv; g.sC_out = sA;
-    LA_TRY(launch_dgemm(g, st));
-    (*launches)++;
-    // trailing update: A[i,j] -= L[i,kb] L[j,kb]^T on the lower tiles
-    GemmDesc u = {};
-    u.A = L + off_panel; u.lda = npad; u.ta = 0;
-    u.B = L + off_panel; u.ldb = npad; u.tb = 0;
-    u.C = A + (int64_t)(kb + 1) * 128 * (npad + 1); u.ldc = npad;
-    u.M = below * 128; u.N = below * 128; u.K = 128;
-    u.alpha = -1.0; u.beta = 1.0; u.kmode = 0; u.lower_only = 1;
-    u.n_inner = 1; u.n_outer = batch;
-    u.sA_out = sA; u.sB_out = sA; u.sC_out = sA;
-    if (!ahead || below < 2) {
+  for (int k0 = 0; k0 < NI; k0 += PB) {
+    const int k1 = k0 + PB < NI ? k0 + PB : NI;
+    for (int kb = k0; kb < k1; kb++) {
+      LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, kb, status, batch, st));
+      (*launches)++;
+      const int below = NI - 1 - kb;
+      if (below == 0) break;
+      const int64_t off_panel = (int64_t)(kb + 1) * 128 * npad + (int64_t)kb * 128;
+      GemmDesc g = {};
+      // L[kb+1:, kb] = A[kb+1:, kb] * inv(L_kk)^T
+      g.A = A + off_panel; g.lda = npad; g.ta = 0;
+      g.B = linv + (int64_t)kb * 128 * 128; g.ldb = 128; g.tb = 0;
+      g.C = L + off_panel; g.ldc = npad;
+      g.M = below * 128; g.N = 128; g.K = 128;
+      g.alpha = 1.0; g.beta = 0.0; g.kmode = 0; g.lower_only = 0;
+      g.n_inner = 1; g.n_outer = batch;
+      g.sA_out = sA; g.sB_out = sInv; g.sC_out = sA;
+      LA_TRY(launch_dgemm(g, st));
+      (*launches)++;
+      const int inpanel = k1 - 1 - kb;
+      if (inpanel > 0) {
+        // A[kb+1:, kb+1:k1] -= L[kb+1:, kb] L[kb+1:k1, kb]^T  (lower tiles)
+        GemmDesc u = {};
+        u.A = L + off_panel; u.lda = npad; u.ta = 0;
+        u.B = L + off_panel; u.ldb = npad; u.tb = 0;
+        u.C = A + (int64_t)(kb + 1) * 128 * (npad + 1); u.ldc = npad;
+        u.M = below * 128; u.N = inpanel * 128; u.K = 128;
+        u.alpha = -1.0; u.beta = 1.0; u.kmode = 0; u.lower_only = 1;
+        u.n_inner = 1; u.n_outer = batch;
+        u.sA_out = sA; u.sB_out = sA; u.sC_out = sA;
+        LA_TRY(launch_dgemm(u, st));
+        (*launches)++;
+      }
+    }
+    if (k1 < NI) {
+      // A[k1:, k1:] -= L[k1:, k0:k1] L[k1:, k0:k1]^T  (lower tiles), k = (k1 - k0) * 128
+      const int64_t off = (int64_t)k1 * 128 * npad + (int64_t)k0 * 128;
+      GemmDesc u = {};
+      u.A = L + off; u.lda = npad; u.ta = 0;
+      u.B = L + off; u.ldb = npad; u.tb = 0;
+      u.C = A + (int64_t)k1 * 128 * (npad + 1); u.ldc = npad;
+      u.M = (NI - k1) * 128; u.N = (NI - k1) * 128; u.K = (k1 - k0) * 128;
+      u.alpha = -1.0; u.beta = 1.0; u.kmode = 0; u.lower_only = 1;
+      u.n_inner = 1; u.n_outer = batch;
+      u.sA_out = sA; u.sB_out = sA; u.sC_out = sA;
       LA_TRY(launch_dgemm(u, st));
-      LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, kb + 1, status, batch, st));
-      (*launches) += 2;
-    } else {
-      GemmDesc c1 = u;   // (i) block column kb+1 (all rows below the diagonal of step kb)
-      c1.N = 128; c1.lower_only = 0;
-      LA_TRY(launch_dgemm(c1, st));
-      LA_TRY(cudaEventRecord(la->ev_a, st));
-      LA_TRY(cudaStreamWaitEvent(la->side, la->ev_a, 0));
-      LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, kb + 1, status, batch, la->side));
-      LA_TRY(cudaEventRecord(la->ev_b, la->side));
-      GemmDesc c2 = u;   // (ii) the remaining lower tiles: rows/cols from block kb+2
-      c2.A = u.A + (int64_t)128 * npad; c2.B = u.B + (int64_t)128 * npad;
-      c2.C = u.C + (int64_t)128 * (npad + 1);
-      c2.M = (below - 1) * 128; c2.N = (below - 1) * 128;
-      LA_TRY(launch_dgemm(c2, st));
-      LA_TRY(cudaStreamWaitEvent(st, la->ev_b, 0));
-      (*launches) += 3;
+      (*launches)++;
     }
   }
   return cudaSuccess;
@@ -423,7 +721,7 @@ cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, in
       g.A = L + base + (int64_t)s * npad; g.lda = npad; g.ta = 0;   // C block  [brows][s]
       g.B = Minv + base; g.ldb = npad; g.tb = 1;                   // A^-1     [s][s] k-major
       g.C = T + base + (int64_t)s * npad; g.ldc = npad;
-      g.M = brows; g.N = s; g.K = s; g.alpha = 1.0; g.beta = 0.0; g.kmode = 1;
+      g.M = brows; g.N = s; g.K = s; g.alpha = 1.0; g.beta = 0.0; g.kmode = 1; g.order = 3;
       g.n_inner = pairs; g.n_outer = batch;
       g.sA_in = g.sB_in = g.sC_in = pstride;
       g.sA_out = g.sB_out = g.sC_out = sMat;
@@ -432,7 +730,7 @@ cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, in
       h.A = Minv + base + (int64_t)s * (npad + 1); h.lda = npad; h.ta = 0;  // B^-1 [brows][brows]
       h.B = T + base + (int64_t)s * npad; h.ldb = npad; h.tb = 1;          // T    [brows][s]
       h.C = Minv + base + (int64_t)s * npad; h.ldc = npad;
-      h.M = brows; h.N = s; h.K = brows; h.alpha = -1.0; h.beta = 0.0; h.kmode = 2;
+      h.M = brows; h.N = s; h.K = brows; h.alpha = -1.0; h.beta = 0.0; h.kmode = 2; h.order = 2;
       h.n_inner = pairs; h.n_outer = batch;
       h.sA_in = h.sB_in = h.sC_in = pstride;
       h.sA_out = h.sB_out = h.sC_out = sMat;

@@ -17,6 +17,7 @@ struct GemmDesc {
   int ta, tb;
   double alpha, beta;
   int kmode, lower_only;
+  int order;   // tile hand-out order (longest k first): 0/1 rows ascending, 2 rows descending, 3 columns ascending
   int n_inner, n_outer;
   int64_t sA_in, sB_in, sC_in, sA_out, sB_out, sC_out;
 };

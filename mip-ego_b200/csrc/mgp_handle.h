@@ -10,6 +10,7 @@
 
 #define MGP_MAX_SETS 16
 #define MGP_MAX_D 64
+#define MGP_NLL_STREAMS 4
 
 struct DevBuf {
   void *p = nullptr;
@@ -69,6 +70,9 @@ struct mgp_handle {
   size_t hpin_bytes = 0;
   // ---- likelihood workspace --------------------------------------------------------------
   int nll_cap = 0;  // batch capacity of the buffers below
+  int nll_groups_opt = 0;  // 0 = default
+  cudaStream_t nll_stream[MGP_NLL_STREAMS] = {nullptr, nullptr, nullptr, nullptr};  // batch groups
+  cudaEvent_t ev_fork = nullptr, ev_join[MGP_NLL_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf nR, nL, nM, nT, nLinvDiag, nvec, nscal, npar, ngpart;
 };
 

@@ -301,8 +301,7 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
   if (!w.have_L)
     NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches, w.la));
   NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches));
-  double *Yt = w.vec, *Ft = w.vec + (int64_t)B * npad, *rho = w.vec + (int64_t)2 * B * npad,
-         *gamma = w.vec + (int64_t)3 * B * npad;
+  double *Yt = w.Yt, *Ft = w.Ft, *rho = w.rho, *gamma = w.gamma;
   NL_TRY(launch_trmv(w.M, npad, sM, w.y, 0, Yt, npad, n, 0, B, st));
   NL_TRY(launch_trmv(w.M, npad, sM, nullptr, 0, Ft, npad, n, 0, B, st));
   k_nll_scalars<<<B, 256, 0, st>>>(w.L, npad, sM, n, Yt, Ft, rho, npad, w.params, w.n_par, w.mode,

@@ -15,7 +15,7 @@ struct NllWork {
   // workspaces, each B matrices of npad x npad
   double *R, *L, *M, *T;
   double *linv;          // B x NI x 128 x 128
-  double *vec;           // 4 x B x npad : Yt, Ft, rho, gamma
+  double *Yt, *Ft, *rho, *gamma;  // each B x npad
   double *scal;          // B x nll_scal_doubles()
   double *gpart;         // B x ntiles x (dpad + 1)
   int *status;           // B

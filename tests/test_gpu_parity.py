@@ -248,6 +248,41 @@ def test_oracle_parity_medium(kind, n, d):
         assert np.array_equal(tv[i], Vfull[i][order])
 
 
+@pytest.mark.parametrize("kind,mode,n,d", [("squared_exponential", "noisy", 1100, 20),
+                                           ("matern", "noiseless", 1300, 7),
+                                           ("squared_exponential", "noiseless", 640, 8)])
+def test_likelihood_oracle_larger_n(kind, mode, n, d):
+    """Batched llf + gradient against the oracle at sizes that exercise several Cholesky panels
+    (npad/128 = 9, 11, 5: full and partial panels), the recursive triangular inverse with a ragged
+    last pair, and every operand layout of the GEMM kernel; ordinary and simple kriging."""
+    mb, O = _mods()
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    y = (y - y.mean()) / y.std()
+    nug = 1e-6 if mode == "noisy" else 0.0
+    for estimate_trend in (True, False):
+        beta = None if estimate_trend else 0.1
+        gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=beta), corr=kind,
+                                theta0=0.1 * np.ones(d), thetaL=1e-5 * np.ones(d),
+                                thetaU=100 * np.ones(d), nugget=nug if nug > 0 else 0)
+        gp._check_data(X, y)
+        scale = (0.3 / d) * (4.0 if kind == "matern" else 1.0)
+        B = 5
+        P = scale * 10.0 ** rng.uniform(-0.4, 0.4, (B, d))
+        if mode == "noisy":
+            P = np.c_[P, rng.uniform(0.5, 1.0, B)]
+        llf, grad, status = gp.log_likelihood_batch(P, eval_grad=True)
+        assert np.all(status == 0)
+        for b in range(B):
+            rl, rg = O.log_likelihood_concentrated(X, y, P[b], kind, estimate_trend, 0.1, mode, nug,
+                                                   eval_grad=True)
+            rl = float(np.ravel(rl)[0])
+            assert abs(llf[b] - rl) < 1e-8 * abs(rl) + 1e-7, (b, llf[b], rl)
+            rg = np.ravel(rg)
+            assert np.max(np.abs(grad[b] - rg)) < 1e-6 * np.abs(rg).max() + 1e-7, (b, grad[b], rg)
+
+
 def test_ragged_and_tiny_inputs():
     mb, O = _mods()
     st = synth_model(O, 130, 3, "squared_exponential", seed=3)
