@@ -10,5 +10,7 @@ from .trend import constant_trend, linear_trend, BasisExpansionTrend  # noqa: F4
 from .gpr import GaussianProcess  # noqa: F401
 from . import InfillCriteria  # noqa: F401
 from .InfillCriteria import EI, PI, EpsilonPI, UCB, MGFI  # noqa: F401
+from . import optimizer  # noqa: F401
+from .optimizer import argmax_restart, batch_argmax_restart, BoxSpace  # noqa: F401
 
 __version__ = "0.1.0"

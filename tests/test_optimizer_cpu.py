@@ -1,0 +1,152 @@
+"""Host logic of the batched acquisition maximisers (mip-ego_b200/optimizer.py) on plain Python
+objectives (no GPU): box reflection and penalty against values produced by the reference's own
+functions, lock-step L-BFGS-B against scipy run alone, vectorised MIES and CMA-ES behaviour."""
+import functools
+
+import numpy as np
+import pytest
+from scipy.optimize import fmin_l_bfgs_b
+
+import mipego_b200.optimizer as opt
+
+
+def test_box_reflection_matches_reference_values():
+    # generated with mipego.misc.handle_box_constraint (misc.py:116-152) in the build container
+    x = np.array([[-7.3, 0.2, 5.0, 11.9, -5.0, 26.1], [1.0, -0.5, 2.5, 3.0, 0.0, -4.2]])
+    want = np.array([[-2.7, 0.20000000000000018, 5.0, -1.8999999999999995, -5.0, 3.899999999999997],
+                     [1.0, -0.5, 2.5, 3.0, 0.0, 2.2]])
+    got = opt.handle_box_constraint(x.T, [-5.0, -1.0], [5.0, 3.0]).T
+    assert np.allclose(got, want, rtol=0, atol=1e-15)
+    inside = np.random.default_rng(0).uniform(-5, 5, (100, 2))
+    assert np.array_equal(opt.handle_box_constraint(inside, [-5, -5], [5, 5]), inside)
+
+
+def test_dynamic_penalty_matches_reference_values():
+    # generated with mipego.utils.dynamic_penalty (utils.py:13-30)
+    X = [[0.5, 1.5], [2.0, -1.0], [0.0, 0.0]]
+    p = opt.dynamic_penalty(X, 3, lambda x: x[0] - 0.5, lambda x: x[0] + x[1] - 1.0, minimize=False)
+    assert np.allclose(p, [-1.5, -2.25, -0.75])
+    p = opt.dynamic_penalty(X, 2, None, lambda x: [x[0] - 1.0, x[1]], minimize=True)
+    assert np.allclose(p, [2.25, 1.0, 0.0])
+
+
+def test_box_space_surface():
+    sp = opt.BoxSpace([[-5, 5]] * 3)
+    assert sp.dim == 3 and len(sp.bounds) == 3 and sp.var_name == ["r0", "r1", "r2"]
+    np.random.seed(1)
+    X = np.array(sp.sampling(7))
+    assert X.shape == (7, 3) and np.all(X >= -5) and np.all(X <= 5)
+    assert all(isinstance(v, float) for v in sp.sampling(1)[0])
+    with pytest.raises(ValueError):
+        opt.BoxSpace([[1, 1]])
+
+
+def _quad(x, return_dx=True):
+    """A smooth multimodal test objective to MAXIMISE, with its gradient (d,1) like a criterion."""
+    x = np.asarray(x, dtype=np.float64)
+    f = -np.sum((x - 1.0) ** 2) + np.sum(np.cos(3 * x))
+    g = -2 * (x - 1.0) - 3 * np.sin(3 * x)
+    return (f, g.reshape(-1, 1)) if return_dx else f
+
+
+@pytest.mark.parametrize("mode", ["batched", "sequential"])
+def test_lockstep_bfgs_equals_scipy_alone(mode):
+    d, R = 4, 6
+    sp = opt.BoxSpace([[-5, 5]] * d)
+    np.random.seed(3)
+    starts = [sp.sampling(1)[0] for _ in range(R)]
+    ref = []
+    for x0 in starts:
+        x_, f_, info = fmin_l_bfgs_b(lambda x: tuple(-1.0 * v for v in (_quad(x)[0], _quad(x)[1].ravel())),
+                                     np.array(x0), pgtol=1e-8, factr=1e6, bounds=np.array(sp.bounds),
+                                     maxfun=400)
+        ref.append((-f_, x_))
+    best = max(ref, key=lambda r: r[0])
+    np.random.seed(3)
+    xopt, fopt = opt.argmax_restart(functools.partial(_quad, return_dx=True), sp, eval_budget=400,
+                                    n_restart=R, wait_iter=R, optimizer="BFGS", mode=mode)
+    assert fopt == best[0]
+    assert np.array_equal(np.array(xopt), best[1])
+
+
+def test_batch_argmax_restart_several_objectives():
+    d = 3
+    sp = opt.BoxSpace([[-5, 5]] * d)
+    fs = [functools.partial(_quad, return_dx=True),
+          lambda x: (-(np.sum(np.asarray(x) ** 2)), (-2 * np.asarray(x)).reshape(-1, 1))]
+    np.random.seed(0)
+    xs, vals = opt.batch_argmax_restart(fs, sp, eval_budget=300, n_restart=4, optimizer="BFGS")
+    assert len(xs) == 2 and abs(vals[1]) < 1e-10 and np.allclose(xs[1], 0, atol=1e-5)
+    assert vals[0] >= _quad(np.ones(d))[0] - 1.0
+
+
+def test_mies_vectorised_behaviour():
+    d = 5
+    bounds = np.array([[-5.0, 5.0]] * d)
+    calls = []
+
+    def values(X):
+        calls.append(X.shape[0])
+        assert np.all(X >= -5) and np.all(X <= 5)
+        return -np.sum((X - 1.0) ** 2, axis=1)
+
+    np.random.seed(5)
+    x, f, ev, reasons = opt.mies_argmax(values, bounds, n_restart=6, max_eval=1500)
+    # one call for the initial parents, then one per generation with (live runs) * lambda rows
+    assert calls[0] == 6 * 4 and all(c % 10 == 0 and c <= 60 for c in calls[1:])
+    assert x.shape == (6, d) and f.shape == (6,)
+    assert np.all(f > -1.0), f          # every run got close to the optimum at (1, ..., 1)
+    assert all(r for r in reasons) and np.all(ev >= 4 + 10)
+    for r, e in zip(reasons, ev):
+        if "max_eval" in r and len(r) == 1:
+            assert e > 1500
+    # determinism under the numpy global seed (the reference draws from numpy.random too)
+    np.random.seed(5)
+    x2, f2, _, _ = opt.mies_argmax(values, bounds, n_restart=6, max_eval=1500)
+    assert np.array_equal(x, x2) and np.array_equal(f, f2)
+    # argmax_restart front-end
+    np.random.seed(6)
+    xo, fo = opt.argmax_restart(lambda x: -float(np.sum((np.asarray(x) - 1.0) ** 2)), opt.BoxSpace(bounds),
+                                eval_budget=800, n_restart=3, optimizer="MIES")
+    assert fo > -1.0 and len(xo) == d
+    np.random.seed(6)
+    xo2, fo2 = opt.argmax_restart(lambda x: -float(np.sum((np.asarray(x) - 1.0) ** 2)), opt.BoxSpace(bounds),
+                                  eval_budget=800, n_restart=3, optimizer="MIES", mode="sequential")
+    assert fo2 > -2.0
+
+
+def test_mies_constraints_penalised():
+    bounds = np.array([[-5.0, 5.0]] * 2)
+    np.random.seed(2)
+    # maximise -|x|^2 subject to x0 >= 1  (g(x) = 1 - x0 <= 0)
+    x, f, _, _ = opt.mies_argmax(lambda X: -np.sum(X ** 2, axis=1), bounds, n_restart=4, max_eval=3000,
+                                 ineq_func=lambda x: 1.0 - x[0])
+    i = int(np.argmax(f))
+    assert x[i][0] > 0.5 and abs(x[i][1]) < 0.3   # soft (dynamic) penalty
+
+
+def test_cma_es_population_generator():
+    d = 8
+    bounds = np.array([[-5.0, 5.0]] * d)
+    target = np.linspace(-3, 3, d)
+    n_calls = []
+
+    def values(X):
+        n_calls.append(len(X))
+        return -np.sum((X - target) ** 2, axis=1)
+
+    xb, fb, info = opt.cma_es_argmax(values, bounds, lambda_=256, max_eval=256 * 80, seed=1)
+    assert fb > -1e-6 and np.allclose(xb, target, atol=1e-3)
+    assert set(n_calls) == {256} and info["funcalls"] == 256 * info["generations"]
+
+    def topk(X, k):
+        v = values(X)
+        o = np.argsort(-v, kind="stable")[:k]
+        return v[o], o
+
+    xb2, fb2, info2 = opt.cma_es_argmax(None, bounds, lambda_=512, max_eval=512 * 60, seed=2, topk_fn=topk)
+    assert fb2 > -1e-4
+    # optimum on the boundary: reflection keeps every candidate feasible
+    xb3, fb3, _ = opt.cma_es_argmax(lambda X: X[:, 0] + X[:, 1], np.array([[-5.0, 5.0]] * 2), lambda_=64,
+                                    max_eval=64 * 60, seed=3)
+    assert fb3 > 9.9
