@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MGP_ABI_VERSION 1
+#define MGP_ABI_VERSION 2
 
 /* error codes */
 #define MGP_OK 0
@@ -53,6 +53,11 @@ extern "C" {
 /* likelihood / estimation mode: gpr.py:246-251 */
 #define MGP_MODE_NOISELESS 0  /* par = theta             gpr.py:814-835 */
 #define MGP_MODE_NOISY 1      /* par = [theta, sigma2]   gpr.py:855-874 */
+#define MGP_MODE_NOISE_ESTIM 2  /* par = [theta, alpha], R = alpha R0 + (1 - alpha) I   gpr.py:837-853 */
+/* OR-ed into the mode: log_likelihood_restricted (REML), gpr.py:699-796.
+ * par = [theta, sigma2] (NOISELESS: noise 0; NOISY: the given noise_var) or
+ * [theta, sigma2, noise_var] (NOISE_ESTIM). */
+#define MGP_LIK_RESTRICTED 16
 
 /* acquisition functions: mipego/InfillCriteria.py */
 #define MGP_ACQ_EI 0    /* EI        InfillCriteria.py:113-148 */
@@ -78,10 +83,12 @@ int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int 
 /* ---- batched marginal likelihood: GaussianProcess.log_likelihood_concentrated,
  * gpr.py:798-946 (with correlation_matrix :658-668, _compute_aux_var :676-697,
  * corr_grad_theta :622-656) evaluated for B parameter vectors at once.
- * params: B x n_par (n_par = d for NOISELESS, d+1 for NOISY).  out_llf: B.  out_grad: B x n_par
+ * params: B x n_par (n_par = d for NOISELESS, d+1 for NOISY and NOISE_ESTIM; with
+ * MGP_LIK_RESTRICTED d+1, d+1, d+2).  out_llf: B.  out_grad: B x n_par
  * (d llf / d par, NOT d/d log10 par -- SURVEY Q5) or NULL when eval_grad == 0.
  * out_status[b]: 0 ok; k > 0: Cholesky failed at pivot k (llf = -inf, grad = 0,
- * gpr.py:820-826); -1: llf > 0 rejected (llf = -inf, grad = 0, gpr.py:889-891). */
+ * gpr.py:820-826); -1: llf > 0 rejected (llf = -inf; grad = 0 for the concentrated likelihood,
+ * gpr.py:889-891; the restricted likelihood still returns its gradient, gpr.py:745-783). */
 int mgp_nll_batch(mgp_t *h, int B, const double *params, int n_par, int mode, double noise_var,
                   int eval_grad, double *out_llf, double *out_grad, int *out_status);
 
@@ -95,7 +102,8 @@ int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double no
 
 /* ---- state exchange (pickling; accepting an externally fitted model).
  * get: any out pointer may be NULL.  out_L: n x n row-major lower triangle (upper = 0);
- * out_theta: d; out_gamma, out_rho, out_Yt, out_Ft: n; out_scalars[4] = {sigma2, beta, G, llf}
+ * out_theta: d; out_gamma, out_rho, out_Yt, out_Ft: n;
+ * out_scalars[5] = {sigma2, beta, G, llf, noise_var}
  * (Ft and G are meaningful only for MGP_TREND_CONST_ESTIMATED).
  * set: theta (d), L (n x n row-major, lower), gamma (n), sigma2, beta; everything else
  * (L^-1, Ft, G, packed operands) is rebuilt on the device.  Requires mgp_set_train first. */

@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libmgp_b200.so")
 MGP_OK, MGP_EINVAL, MGP_ECUDA, MGP_ESTATE, MGP_ENOMEM, MGP_ENOTPD, MGP_ENCCL = 0, -1, -2, -3, -4, -5, -6
 CORR = {"squared_exponential": 0, "matern": 1, "absolute_exponential": 2}
 ACQ = {"EI": 0, "PI": 1, "EpsilonPI": 1, "UCB": 2, "MGFI": 3}
-MODE = {"noiseless": 0, "noisy": 1}
+MODE = {"noiseless": 0, "noisy": 1, "noise_estim": 2}
+LIK_RESTRICTED = 16
 MAX_SETS = 16
 
 c_dp = ctypes.POINTER(ctypes.c_double)
@@ -64,7 +65,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mgp_abi_version() != 1:
+    if lib.mgp_abi_version() != 2:
         raise ImportError("libmgp_b200.so ABI version mismatch")
     _lib = lib
     return lib

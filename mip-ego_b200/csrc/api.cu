@@ -204,7 +204,7 @@ int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int 
   CHECK_H(h);
   if (n < 1 || d < 1 || !X || !y) return mgp_fail(h, MGP_EINVAL, "bad training data");
   if (d > MGP_MAX_D) return mgp_fail(h, MGP_EINVAL, "d = %d > %d unsupported", d, MGP_MAX_D);
-  if (corr != MGP_CORR_SE && corr != MGP_CORR_MATERN32)
+  if (corr != MGP_CORR_SE && corr != MGP_CORR_MATERN32 && corr != MGP_CORR_ABSEXP)
     return mgp_fail(h, MGP_EINVAL, "correlation type %d not supported by the CUDA path", corr);
   if (trend != MGP_TREND_CONST_FIXED && trend != MGP_TREND_CONST_ESTIMATED)
     return mgp_fail(h, MGP_EINVAL, "trend type %d unknown", trend);
@@ -263,9 +263,9 @@ static int nll_alloc(mgp_handle *h, int B) {
   MGP_TRY(mgp_ensure(h, h->nM, mat * B));
   MGP_TRY(mgp_ensure(h, h->nT, mat * B));
   MGP_TRY(mgp_ensure(h, h->nLinvDiag, (size_t)B * h->NI * 128 * 128 * 8));
-  MGP_TRY(mgp_ensure(h, h->nvec, (size_t)4 * B * h->npad * 8));
+  MGP_TRY(mgp_ensure(h, h->nvec, (size_t)5 * B * h->npad * 8));
   MGP_TRY(mgp_ensure(h, h->nscal, (size_t)B * nll_scal_doubles() * 8 + (size_t)B * sizeof(int) + 64));
-  MGP_TRY(mgp_ensure(h, h->ngpart, (size_t)B * ntiles * (h->dpad + 1) * 8));
+  MGP_TRY(mgp_ensure(h, h->ngpart, (size_t)B * ntiles * (h->dpad + 2) * 8));
   h->nll_cap = B;
   return 0;
 }
@@ -283,12 +283,13 @@ static int nll_max_batch(mgp_handle *h) {
 
 static int check_par(mgp_handle *h, int n_par, int mode) {
   if (h->n == 0) return mgp_fail(h, MGP_ESTATE, "mgp_set_train must be called first");
-  if (mode != MGP_MODE_NOISELESS && mode != MGP_MODE_NOISY)
+  const int est = mode & 15;
+  if ((mode & ~(15 | MGP_LIK_RESTRICTED)) || est > MGP_MODE_NOISE_ESTIM)
     return mgp_fail(h, MGP_EINVAL, "estimation mode %d not supported", mode);
-  const int want = h->d + (mode == MGP_MODE_NOISY ? 1 : 0);
+  const int want = nll_n_par(mode, h->d);
   if (n_par != want)
-    return mgp_fail(h, MGP_EINVAL, "n_par = %d, expected %d (anisotropic theta%s)", n_par, want,
-                    mode == MGP_MODE_NOISY ? " + sigma2" : "");
+    return mgp_fail(h, MGP_EINVAL, "n_par = %d, expected %d for mode %d (anisotropic theta + %d)", n_par,
+                    want, mode, want - h->d);
   return 0;
 }
 
@@ -308,9 +309,9 @@ static void fill_work(mgp_handle *h, NllWork &w, int b_off, int B, int cap, int 
   w.M = P<double>(h->nM) + b_off * mat; w.T = P<double>(h->nT) + b_off * mat;
   w.linv = P<double>(h->nLinvDiag) + (size_t)b_off * h->NI * 128 * 128;
   double *v = P<double>(h->nvec) + (size_t)b_off * h->npad;
-  w.Yt = v; w.Ft = v + sec; w.rho = v + 2 * sec; w.gamma = v + 3 * sec;
+  w.Yt = v; w.Ft = v + sec; w.rho = v + 2 * sec; w.gamma = v + 3 * sec; w.avec = v + 4 * sec;
   w.scal = P<double>(h->nscal) + (size_t)b_off * nll_scal_doubles();
-  w.gpart = P<double>(h->ngpart) + (size_t)b_off * ntiles * (h->dpad + 1);
+  w.gpart = P<double>(h->ngpart) + (size_t)b_off * ntiles * (h->dpad + 2);
   w.status = nll_status_ptr(h, cap) + b_off;
   w.out_llf = d_llf; w.out_grad = d_grad;
   w.la = nullptr;
@@ -457,7 +458,7 @@ int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double no
     return mgp_fail(h, MGP_ENOTPD, "correlation matrix not positive definite at pivot %d", status);
   }
   h->mode = mode;
-  h->noise_var = noise_var;
+  h->noise_var = sc[NLL_NV];
   h->sigma2 = sc[NLL_SIGMA2];
   h->llf = sc[NLL_LLF];
   h->ftf = sc[NLL_FTF];
@@ -523,6 +524,7 @@ int mgp_get_state(mgp_t *h, double *out_theta, double *out_L, double *out_gamma,
   MGP_CUDA(h, cudaStreamSynchronize(st));
   if (out_scalars) {
     out_scalars[0] = h->sigma2; out_scalars[1] = h->beta; out_scalars[2] = h->G; out_scalars[3] = h->llf;
+    out_scalars[4] = h->noise_var;
   }
   return MGP_OK;
 }
@@ -601,6 +603,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     rp.nCblk = nCblk; rp.JS = JS;
     rp.center = P<double>(h->dcenter); rp.theta = P<double>(h->dtheta); rp.Bop = P<double>(h->dBop);
     rp.an = P<double>(h->dan); rp.gamma = P<double>(h->dgamma); rp.avec = P<double>(h->davec);
+    rp.Xc = P<double>(h->dXc);
     rp.rP = P<double>(h->drP); rp.meanpart = P<double>(h->dmeanpart); rp.ftpart = P<double>(h->dftpart);
     rp.ldp = ldp;
     { KTimer t(h, st, 0); MGP_CUDA(h, launch_rgen(rp, h->corr, h->sm_count, st)); }

@@ -94,11 +94,12 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ double norm_cdf(double x) { return 0.5 * erfc(-x * MGP_INV_SQRT2); }
 __device__ __forceinline__ double norm_pdf(double x) { return exp(-0.5 * x * x) * MGP_INV_SQRT2PI; }
 
-// correlation as a function of S = sum_i theta_i (x_i - x'_i)^2  (kernel.py:147-185, 277-317)
+// correlation as a function of S = sum_i theta_i (x_i - x'_i)^2  (kernel.py:147-185, 277-317);
+// CORR == 2 (absolute exponential, kernel.py:235-274): S = sum_i theta_i |x_i - x'_i|, r = exp(-S)
 template <int CORR>
 __device__ __forceinline__ double corr_from_S(double S) {
   S = fmax(S, 0.0);
-  if (CORR == 0) return exp(-S);
+  if (CORR != 1) return exp(-S);
   double s = MGP_SQRT3 * sqrt(S);
   return (1.0 + s) * exp(-s);
 }

@@ -21,7 +21,35 @@ namespace {
 constexpr int XP = 132;  // padded row length of the transposed X tile in shared memory
 
 // scal layout per batch element (doubles)
-enum { SC_SIGMA2 = 0, SC_LLF, SC_FTF, SC_FTY, SC_RR, SC_LOGDET, SC_S, SC_V, SC_BETA, SC_N };
+enum { SC_SIGMA2 = 0, SC_LLF, SC_FTF, SC_FTY, SC_RR, SC_LOGDET, SC_S, SC_V, SC_BETA, SC_NV, SC_COEFA,
+       SC_THSCALE, SC_N };
+
+// mode = estimation mode | MGP_LIK_RESTRICTED.  Every mode factors
+//   R = c R0 + (1 - c) I,   c = 1 | sigma2 / (sigma2 + noise_var) | alpha      (gpr.py:721-724, 838-839, 861-865)
+struct ModePar { double c, sigma2, nv; };
+__device__ __forceinline__ ModePar mode_params(int mode, const double *par, int n_par, double noise_var) {
+  ModePar m;
+  const int est = mode & 15;
+  if (mode & MGP_LIK_RESTRICTED) {
+    m.sigma2 = est == MGP_MODE_NOISE_ESTIM ? par[n_par - 2] : par[n_par - 1];
+    m.nv = est == MGP_MODE_NOISELESS ? 0.0 : (est == MGP_MODE_NOISY ? noise_var : par[n_par - 1]);
+    m.c = m.sigma2 / (m.sigma2 + m.nv);
+  } else if (est == MGP_MODE_NOISY) {
+    m.sigma2 = par[n_par - 1]; m.nv = noise_var; m.c = m.sigma2 / (m.sigma2 + m.nv);
+  } else if (est == MGP_MODE_NOISE_ESTIM) {
+    m.sigma2 = 0.0; m.nv = 0.0; m.c = par[n_par - 1];
+  } else {
+    m.sigma2 = 0.0; m.nv = 0.0; m.c = 1.0;
+  }
+  return m;
+}
+__host__ __device__ inline int mode_n_theta(int mode, int n_par) {
+  const int est = mode & 15;
+  int extra = 0;
+  if (mode & MGP_LIK_RESTRICTED) extra = est == MGP_MODE_NOISE_ESTIM ? 2 : 1;
+  else extra = est == MGP_MODE_NOISELESS ? 0 : 1;
+  return n_par - extra;
+}
 
 // R tile builder: lower tiles (bi >= bj); padded indices give the identity.
 template <int CORR>
@@ -36,7 +64,7 @@ __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int np
   if (bj > bi) return;
   const int tid = threadIdx.x;
   const double *par = params + (int64_t)b * n_par;
-  const int d = (mode == MGP_MODE_NOISY) ? n_par - 1 : n_par;
+  const int d = mode_n_theta(mode, n_par);
   for (int idx = tid; idx < 128 * dpad; idx += 256) {
     const int r = idx / dpad, i = idx % dpad;
     xjT[i * XP + r] = Xc[(int64_t)(bi * 128 + r) * dpad + i];
@@ -44,11 +72,7 @@ __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int np
   }
   for (int i = tid; i < dpad; i += 256) th[i] = i < d ? par[i] : 0.0;
   __syncthreads();
-  double scale = 1.0;
-  if (mode == MGP_MODE_NOISY) {
-    const double s2 = par[n_par - 1];
-    scale = s2 / (s2 + noise_var);
-  }
+  const double scale = mode_params(mode, par, n_par, noise_var).c;
   double *Rb = R + b * sR;
   const int c = tid & 127;
   const int gk = bj * 128 + c;
@@ -61,7 +85,7 @@ __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int np
       double S = 0.0;
       for (int i = 0; i < dpad; i++) {
         const double df = xjT[i * XP + r] - xkT[i * XP + c];
-        S = fma(th[i] * df, df, S);
+        S = CORR == 2 ? fma(th[i], fabs(df), S) : fma(th[i] * df, df, S);
       }
       v = scale * corr_from_S<CORR>(S);
     }
@@ -111,51 +135,71 @@ __global__ void __launch_bounds__(256) k_nll_scalars(const double *L, int npad, 
   }
   rr = block_sum(rr, red);
   if (tid == 0) {
-    double sigma2, llf, s, v = 0.0;
+    const ModePar mp = mode_params(mode, params + (int64_t)b * n_par, n_par, noise_var);
+    const int est = mode & 15;
+    const bool restricted = (mode & MGP_LIK_RESTRICTED) != 0;
+    double sigma2, llf, s, v = 0.0, nv = 0.0, coefa = 0.0, thscale = 1.0;
     const double two_pi = 6.283185307179586;
-    if (mode == MGP_MODE_NOISELESS) {
+    if (restricted) {
+      // gpr.py:733-743.  F = 1: det(F^T F) = n; diag(G)^2 = Ft^T Ft.  The simple-kriging branch
+      // carries the reference's minus sign on the log-determinant.
+      sigma2 = mp.sigma2; nv = mp.nv; v = sigma2 + nv; s = v;
+      if (ordinary) {
+        llf = -0.5 * ((n - 1) * log(two_pi * v) - log((double)n) + 2.0 * logdet + log(ftf) + rr / v);
+        coefa = v / ftf;     // v q q^T with q = L^-T Ft / G  (gpr.py:754-755)
+      } else {
+        llf = -0.5 * (n * log(two_pi * v) - 2.0 * logdet + rr / v);
+      }
+    } else if (est == MGP_MODE_NOISELESS) {
       const int k = ordinary ? 1 : 0;
       sigma2 = rr / (double)(n - k);                                    // gpr.py:833
       llf = -0.5 * (n * log(two_pi * sigma2) + 2.0 * logdet + n);       // gpr.py:834-835
       s = sigma2;
+    } else if (est == MGP_MODE_NOISE_ESTIM) {
+      const double tot = rr / (double)n;                                // gpr.py:848-851
+      sigma2 = mp.c * tot; nv = (1.0 - mp.c) * tot;
+      llf = -0.5 * (n * log(two_pi * tot) + 2.0 * logdet + n);
+      s = tot; v = tot; thscale = mp.c;
     } else {
-      sigma2 = params[(int64_t)b * n_par + n_par - 1];
-      v = sigma2 + noise_var;
+      sigma2 = mp.sigma2; nv = mp.nv;
+      v = sigma2 + nv;
       llf = -0.5 * (n * log(two_pi * v) + 2.0 * logdet + rr / v);       // gpr.py:872-874
       s = v;
     }
     int st = status[b];
-    if (st == 0 && !(llf <= 0.0)) st = -1;  // llf > 0 (or NaN) rejected, gpr.py:889-891
+    if (st == 0 && !(llf <= 0.0)) st = -1;  // llf > 0 (or NaN) rejected, gpr.py:889-891, 745-748
     if (st != 0) llf = -INFINITY;
     status[b] = st;
     double *sc = scal + (int64_t)b * SC_N;
     sc[SC_SIGMA2] = sigma2; sc[SC_LLF] = llf; sc[SC_FTF] = ftf; sc[SC_FTY] = fty;
     sc[SC_RR] = rr; sc[SC_LOGDET] = logdet; sc[SC_S] = s; sc[SC_V] = v;
     sc[SC_BETA] = ordinary ? fty / ftf : beta0;   // beta = G^-1 Q^T Yt  (gpr.py:673)
+    sc[SC_NV] = nv; sc[SC_COEFA] = coefa; sc[SC_THSCALE] = thscale;
     if (out_llf) out_llf[b] = llf;
   }
 }
 
-// Gradient contraction over the strictly-lower pairs of one 128x128 tile.
-// acc[i] += W_jk * dR0_jk/dtheta_i ; noisy mode adds acc[d] += W_jk * R0_jk (pairs) and the diagonal.
+// Gradient contraction over the lower pairs of one 128x128 tile, with
+//   W_jk = gamma_j gamma_k / s + coefA a_j a_k - Rinv_jk     (a = L^-T Ft; coefA != 0 only for REML)
+// acc[i] += W_jk dR0_jk/dtheta_i (j > k);  acc[DP] += 2 W_jk R0_jk (j > k);  acc[DP+1] += W_jj.
 template <int CORR, int DP>
 __global__ void __launch_bounds__(256) k_nll_grad(const double *Xc, int n, int npad,
                                                   const double *params, int n_par, int mode,
                                                   const double *Rinv, int64_t sR,
-                                                  const double *gamma, int64_t sv,
+                                                  const double *gamma, const double *avec, int64_t sv,
                                                   const double *scal, double *gpart, int ntiles) {
   extern __shared__ double sm[];
   double *xjT = sm;
   double *xkT = sm + DP * XP;
   double *th = xkT + DP * XP;
-  double *red = th + DP;  // [8][DP+1]
+  double *red = th + DP;  // [8][DP+2]
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // tile index -> (bi, bj), bi >= bj
   int t = blockIdx.x, bi = 0;
   while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
   const int bj = t - bi * (bi + 1) / 2;
   const double *par = params + (int64_t)b * n_par;
-  const int d = (mode == MGP_MODE_NOISY) ? n_par - 1 : n_par;
+  const int d = mode_n_theta(mode, n_par);
   for (int idx = tid; idx < 128 * DP; idx += 256) {
     const int r = idx / DP, i = idx % DP;
     xjT[i * XP + r] = Xc[(int64_t)(bi * 128 + r) * DP + i];
@@ -164,20 +208,24 @@ __global__ void __launch_bounds__(256) k_nll_grad(const double *Xc, int n, int n
   for (int i = tid; i < DP; i += 256) th[i] = i < d ? par[i] : 0.0;
   __syncthreads();
   const double s_div = scal[(int64_t)b * SC_N + SC_S];
+  const double coefa = scal[(int64_t)b * SC_N + SC_COEFA];
   const double *Rb = Rinv + b * sR;
   const double *gm = gamma + b * sv;
-  double acc[DP + 1];
+  const double *av = avec + b * sv;
+  double acc[DP + 2];
 #pragma unroll
-  for (int i = 0; i <= DP; i++) acc[i] = 0.0;
+  for (int i = 0; i <= DP + 1; i++) acc[i] = 0.0;
   const int c = tid & 127, gk = bj * 128 + c;
   const double gk_v = gk < n ? gm[gk] : 0.0;
+  const double ak_v = (coefa != 0.0 && gk < n) ? coefa * av[gk] : 0.0;
   for (int r = tid >> 7; r < 128; r += 2) {
     const int gj = bi * 128 + r;
     if (gj >= n || gk >= n || gj < gk) continue;
     const double rinv = Rb[(int64_t)gj * npad + gk];
-    const double W = gm[gj] * gk_v / s_div - rinv;
+    double W = gm[gj] * gk_v / s_div - rinv;
+    if (coefa != 0.0) W = fma(av[gj], ak_v, W);
     if (gj == gk) {
-      acc[DP] += W;  // R0_jj = 1 (sigma2 derivative only)
+      acc[DP + 1] += W;  // R0_jj = 1: sigma2 / noise-variance derivatives only
       continue;
     }
     double df2[DP];
@@ -185,11 +233,11 @@ __global__ void __launch_bounds__(256) k_nll_grad(const double *Xc, int n, int n
 #pragma unroll
     for (int i = 0; i < DP; i++) {
       const double df = xjT[i * XP + r] - xkT[i * XP + c];
-      df2[i] = df * df;
+      df2[i] = CORR == 2 ? fabs(df) : df * df;   // abs-exp: dR0/dtheta_i = -|df_i| R0  (gpr.py:648)
       S = fma(th[i], df2[i], S);
     }
     double R0, fac;
-    if (CORR == 0) {
+    if (CORR != 1) {
       R0 = exp(-S);
       fac = -R0;  // dR0/dtheta_i = -df_i^2 R0            gpr.py:634
     } else {
@@ -203,30 +251,49 @@ __global__ void __launch_bounds__(256) k_nll_grad(const double *Xc, int n, int n
     acc[DP] = fma(2.0 * W, R0, acc[DP]);  // both (j,k) and (k,j)
   }
 #pragma unroll
-  for (int i = 0; i <= DP; i++) {
+  for (int i = 0; i <= DP + 1; i++) {
     double v = acc[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[warp * (DP + 1) + i] = v;
+    if (lane == 0) red[warp * (DP + 2) + i] = v;
   }
   __syncthreads();
-  for (int i = tid; i <= DP; i += 256) {
+  for (int i = tid; i <= DP + 1; i += 256) {
     double v = 0.0;
-    for (int w = 0; w < 8; w++) v += red[w * (DP + 1) + i];
-    gpart[((int64_t)b * ntiles + t) * (DP + 1) + i] = v;
+    for (int w = 0; w < 8; w++) v += red[w * (DP + 2) + i];
+    gpart[((int64_t)b * ntiles + t) * (DP + 2) + i] = v;
   }
 }
 
-__global__ void k_nll_grad_final(const double *gpart, int ntiles, int dp1, int n_par, int mode,
+// Assemble d llf / d par from the tile partials (fixed order over tiles):
+//   theta_i : thscale * sum_{j>k} W dR0/dtheta_i     (thscale = alpha for the estimated noise share, gpr.py:917)
+//   concentrated noisy  sigma2 : (0.5 / v) sum_all W R0                    (gpr.py:938-944)
+//   concentrated noise_estim alpha : sum_{j>k} W R0 = -1/2 (sum Rinv o (R0 - I) - ...)   (gpr.py:927-930)
+//   restricted sigma2 : (0.5 / v) sum_all W R0;  noise_var : (0.5 / v) sum_j W_jj        (gpr.py:762-783)
+__global__ void k_nll_grad_final(const double *gpart, int ntiles, int dp2, int n_par, int mode,
                                  const double *scal, const int *status, double *out_grad) {
   const int b = blockIdx.x, i = threadIdx.x;
   if (i >= n_par) return;
-  const int d = (mode == MGP_MODE_NOISY) ? n_par - 1 : n_par;
+  const int d = mode_n_theta(mode, n_par);
+  const bool restricted = (mode & MGP_LIK_RESTRICTED) != 0;
+  const int est = mode & 15;
   double g = 0.0;
-  if (status[b] == 0) {
-    const int src = i < d ? i : dp1 - 1;
-    for (int t = 0; t < ntiles; t++) g += gpart[((int64_t)b * ntiles + t) * dp1 + src];
-    if (i >= d) g *= 0.5 / scal[(int64_t)b * SC_N + SC_V];  // d llf / d sigma2  (gpr.py:938-944)
+  if (status[b] == 0 || (restricted && status[b] == -1)) {
+    auto col = [&](int src) {
+      double t = 0.0;
+      for (int q = 0; q < ntiles; q++) t += gpart[((int64_t)b * ntiles + q) * dp2 + src];
+      return t;
+    };
+    const double v = scal[(int64_t)b * SC_N + SC_V];
+    if (i < d) {
+      g = col(i) * scal[(int64_t)b * SC_N + SC_THSCALE];
+    } else if (!restricted && est == MGP_MODE_NOISE_ESTIM) {
+      g = 0.5 * col(dp2 - 2);
+    } else if (i == d) {
+      g = (col(dp2 - 2) + col(dp2 - 1)) * 0.5 / v;
+    } else {
+      g = col(dp2 - 1) * 0.5 / v;
+    }
   }
   out_grad[(int64_t)b * n_par + i] = g;
 }
@@ -242,15 +309,15 @@ __global__ void k_dup_check(const double *Xc, int n, int dpad, int *flag) {
 template <int CORR>
 cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, const double *Xc, int n,
                           int npad, const double *params, int n_par, int mode, const double *Rinv,
-                          int64_t sR, const double *gamma, int64_t sv, const double *scal,
-                          double *gpart, int ntiles) {
+                          int64_t sR, const double *gamma, const double *avec, int64_t sv,
+                          const double *scal, double *gpart, int ntiles) {
   switch (dpad) {
 #define NG(D)                                                                                   \
   case D:                                                                                       \
     cudaFuncSetAttribute(k_nll_grad<CORR, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                          (int)smem);                                                            \
     k_nll_grad<CORR, D><<<grid, 256, smem, st>>>(Xc, n, npad, params, n_par, mode, Rinv, sR,    \
-                                                  gamma, sv, scal, gpart, ntiles);              \
+                                                  gamma, avec, sv, scal, gpart, ntiles);        \
     break;
     NG(4) NG(8) NG(12) NG(16) NG(20) NG(24) NG(28) NG(32) NG(36) NG(40) NG(44) NG(48) NG(52) NG(56) NG(60) NG(64)
 #undef NG
@@ -268,6 +335,7 @@ cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, con
   } while (0)
 
 size_t nll_scal_doubles() { return SC_N; }
+int nll_n_par(int mode, int d) { return d + (d - mode_n_theta(mode, d)); }
 
 cudaError_t launch_dup_check(const double *Xc, int n, int dpad, int *flag, cudaStream_t st) {
   k_dup_check<<<dim3((n + 127) / 128, n), 128, 0, st>>>(Xc, n, dpad, flag);
@@ -292,6 +360,10 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
       cudaFuncSetAttribute(k_build_R<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       k_build_R<1><<<grid, 256, smem, st>>>(w.Xc, n, npad, w.dpad, w.params, w.n_par, w.mode,
                                             w.noise_var, w.R, sM);
+    } else if (w.corr == MGP_CORR_ABSEXP) {
+      cudaFuncSetAttribute(k_build_R<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k_build_R<2><<<grid, 256, smem, st>>>(w.Xc, n, npad, w.dpad, w.params, w.n_par, w.mode,
+                                            w.noise_var, w.R, sM);
     } else {
       return cudaErrorInvalidValue;
     }
@@ -310,17 +382,24 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
   NL_TRY(launch_trmv(w.M, npad, sM, rho, npad, gamma, npad, n, 1, B, st));
   (*launches) += 4;
   if (w.eval_grad) {
+    if ((w.mode & MGP_LIK_RESTRICTED) && w.ordinary) {   // a = L^-T Ft for the q q^T term of REML
+      NL_TRY(launch_trmv(w.M, npad, sM, Ft, npad, w.avec, npad, n, 1, B, st));
+      (*launches)++;
+    }
     NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, st, launches));
     const int ntiles = NI * (NI + 1) / 2;
-    const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + 8 * (w.dpad + 1)) * sizeof(double);
+    const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + 8 * (w.dpad + 2)) * sizeof(double);
     dim3 grid(ntiles, B);
     if (w.corr == MGP_CORR_SE)
       NL_TRY(grad_dispatch<0>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
-                              sM, gamma, npad, w.scal, w.gpart, ntiles));
-    else
+                              sM, gamma, w.avec, npad, w.scal, w.gpart, ntiles));
+    else if (w.corr == MGP_CORR_MATERN32)
       NL_TRY(grad_dispatch<1>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
-                              sM, gamma, npad, w.scal, w.gpart, ntiles));
-    k_nll_grad_final<<<B, 128, 0, st>>>(w.gpart, ntiles, w.dpad + 1, w.n_par, w.mode, w.scal,
+                              sM, gamma, w.avec, npad, w.scal, w.gpart, ntiles));
+    else
+      NL_TRY(grad_dispatch<2>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
+                              sM, gamma, w.avec, npad, w.scal, w.gpart, ntiles));
+    k_nll_grad_final<<<B, 128, 0, st>>>(w.gpart, ntiles, w.dpad + 2, w.n_par, w.mode, w.scal,
                                         w.status, w.out_grad);
     NL_TRY(cudaGetLastError());
     (*launches) += 2;

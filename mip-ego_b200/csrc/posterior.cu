@@ -121,6 +121,85 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
   }
 }
 
+// K1 for the absolute-exponential correlation r = exp(-sum_i theta_i |x_i - x'_i|)
+// (kernel.py:235-274): the L1 distance has no GEMM form, so S is accumulated feature by feature on
+// the FP64 pipe from shared-memory copies of the training block (transposed) and the candidate
+// block.  Same work items, outputs and packed layout as k_rgen.
+template <int DPAD>
+__global__ void __launch_bounds__(256) k_rgen_l1(RgenParams p) {
+  constexpr int XS = 132, CS = DPAD + 1;
+  extern __shared__ __align__(16) double sm_rg[];
+  double *sX = sm_rg;                 // [DPAD][XS]   training block, feature-major
+  double *sC = sX + DPAD * XS;        // [128][CS]    candidate block
+  double *sTh = sC + 128 * CS;        // [DPAD]
+  double *sV = sTh + DPAD;            // gamma | avec
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lk = lane & 3;
+  const int nItems = p.nCblk * p.JS;
+  int last_cb = -1;
+  for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+    const int jb = item / p.nCblk, cb = item % p.nCblk;
+    __syncthreads();
+    for (int idx = tid; idx < 128 * DPAD; idx += 256) {
+      const int r = idx / DPAD, i = idx % DPAD;
+      sX[i * XS + r] = __ldg(p.Xc + (int64_t)(jb * 128 + r) * DPAD + i);
+    }
+    if (cb != last_cb) {
+      for (int idx = tid; idx < 128 * DPAD; idx += 256) {
+        const int r = idx / DPAD, i = idx % DPAD;
+        const int64_t c = (int64_t)cb * 128 + r;
+        sC[r * CS + i] = (c < p.mc && i < p.d) ? p.Xs[c * p.d + i] - p.center[i] : 0.0;
+      }
+      last_cb = cb;
+    }
+    for (int i = tid; i < DPAD; i += 256) sTh[i] = p.theta[i];
+    if (tid < 128) {
+      sV[tid] = __ldg(p.gamma + jb * 128 + tid);
+      sV[128 + tid] = __ldg(p.avec + jb * 128 + tid);
+    }
+    __syncthreads();
+    double macc[2] = {0.0, 0.0}, facc[2] = {0.0, 0.0};
+    const double *c0p = sC + ((2 * warp) * 8 + lr) * CS, *c1p = sC + ((2 * warp + 1) * 8 + lr) * CS;
+#pragma unroll 1
+    for (int t8 = 0; t8 < 16; t8++) {
+      const int jcol = 8 * t8 + 2 * lk;
+      double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll 4
+      for (int i = 0; i < DPAD; i++) {
+        const double2 xj = *reinterpret_cast<const double2 *>(sX + i * XS + jcol);
+        const double th = sTh[i], a = c0p[i], b = c1p[i];
+        s00 = fma(th, fabs(a - xj.x), s00);
+        s01 = fma(th, fabs(a - xj.y), s01);
+        s10 = fma(th, fabs(b - xj.x), s10);
+        s11 = fma(th, fabs(b - xj.y), s11);
+      }
+      const double2 g2 = *reinterpret_cast<const double2 *>(sV + jcol);
+      const double2 a2 = *reinterpret_cast<const double2 *>(sV + 128 + jcol);
+      const int j8 = jb * 16 + t8;
+      const double r00 = exp(-s00), r01 = exp(-s01), r10 = exp(-s10), r11 = exp(-s11);
+      *reinterpret_cast<double2 *>(p.rP + (((int64_t)cb * p.NJ8 + j8) * 16 + 2 * warp) * 64 + lane * 2) =
+          make_double2(r00, r01);
+      *reinterpret_cast<double2 *>(p.rP + (((int64_t)cb * p.NJ8 + j8) * 16 + 2 * warp + 1) * 64 + lane * 2) =
+          make_double2(r10, r11);
+      macc[0] = fma(g2.x, r00, macc[0]); macc[0] = fma(g2.y, r01, macc[0]);
+      macc[1] = fma(g2.x, r10, macc[1]); macc[1] = fma(g2.y, r11, macc[1]);
+      facc[0] = fma(a2.x, r00, facc[0]); facc[0] = fma(a2.y, r01, facc[0]);
+      facc[1] = fma(a2.x, r10, facc[1]); facc[1] = fma(a2.y, r11, facc[1]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      macc[u] += __shfl_xor_sync(0xffffffffu, macc[u], 1);
+      macc[u] += __shfl_xor_sync(0xffffffffu, macc[u], 2);
+      facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 1);
+      facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 2);
+      if (lk == 0) {
+        const int64_t o = (int64_t)jb * p.ldp + (int64_t)cb * 128 + (2 * warp + u) * 8 + lr;
+        p.meanpart[o] = macc[u];
+        p.ftpart[o] = facc[u];
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2c: T = L^-1 r on DMMA with the column sums of squares fused (|L^-1 r|^2, gpr.py:463,472);
 // T never leaves registers.  FULL variant: W = R^-1 r written back in the rP layout (gradient
@@ -452,6 +531,7 @@ __global__ void __launch_bounds__(1024) k_topk_merge(const double *vals, int64_t
 //   mean_dx_i = sum_j gamma_j r_dx[j,i]
 //   mse_dx_i  = 2 sigma2 sum_j (-w_j + kappa a_j) r_dx[j,i],  kappa = (Ft^T rt - 1)/(Ft^T Ft)
 //   r_dx[j,i] = -2 theta_i D_i r_j (SE, gpr.py:592) | -3 theta_i D_i e^{-sqrt3 D} (Matern, :601-602)
+//             | -theta_i sign(D_i) r_j (absolute exponential, :606-607)
 // One warp per candidate; lanes stride over the training points; D = x* - x_j component-wise.
 // A Matern candidate coinciding with a training point zeroes the whole Jacobian (gpr.py:588-615).
 // ---------------------------------------------------------------------------------------------
@@ -491,6 +571,8 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
     for (int i = 0; i < DP; i++) {
       df[i] = xs[i] - xj[i];
       if (CORR == 1) S = fma(th[i] * df[i], df[i], S);
+      // absolute exponential: r_dx = -theta_i sign(D_i) r  (gpr.py:606-607; numpy sign(0) = 0)
+      if (CORR == 2) df[i] = df[i] > 0.0 ? 1.0 : (df[i] < 0.0 ? -1.0 : 0.0);
     }
     double e = r;
     if (CORR == 1) {
@@ -509,7 +591,7 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
     q += __shfl_xor_sync(0xffffffffu, q, o);
     coincide |= __shfl_xor_sync(0xffffffffu, coincide, o);
   }
-  const double fac = CORR == 0 ? -2.0 : -3.0;
+  const double fac = CORR == 0 ? -2.0 : (CORR == 1 ? -3.0 : -1.0);
   const double mean = p.beta + md;
   double u2 = 0.0;
   if (p.ordinary) {
@@ -607,9 +689,32 @@ static cudaError_t rgen_dispatch(const RgenParams &p, int sm_count, cudaStream_t
     default: return cudaErrorInvalidValue;
   }
 }
+template <int DPAD>
+static cudaError_t rgen_l1_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
+  static int occ = 0;
+  const int smem = (DPAD * 132 + 128 * (DPAD + 1) + DPAD + 2 * 128) * (int)sizeof(double);
+  if (occ == 0) {
+    cudaFuncSetAttribute(k_rgen_l1<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen_l1<DPAD>, 256, smem) != cudaSuccess || occ < 1)
+      occ = 1;
+  }
+  const int items = p.nCblk * p.JS;
+  const int grid = items < sm_count * occ ? items : sm_count * occ;
+  k_rgen_l1<DPAD><<<grid, 256, smem, st>>>(p);
+  return cudaGetLastError();
+}
+static cudaError_t rgen_l1_dispatch(const RgenParams &p, int sm_count, cudaStream_t st) {
+  switch (p.dpad) {
+#define RL(D) case D: return rgen_l1_launch<D>(p, sm_count, st);
+    RL(4) RL(8) RL(12) RL(16) RL(20) RL(24) RL(28) RL(32) RL(36) RL(40) RL(44) RL(48) RL(52) RL(56) RL(60) RL(64)
+#undef RL
+    default: return cudaErrorInvalidValue;
+  }
+}
 cudaError_t launch_rgen(const RgenParams &p, int corr, int sm_count, cudaStream_t st) {
   if (corr == MGP_CORR_SE) return rgen_dispatch<0>(p, sm_count, st);
   if (corr == MGP_CORR_MATERN32) return rgen_dispatch<1>(p, sm_count, st);
+  if (corr == MGP_CORR_ABSEXP) return rgen_l1_dispatch(p, sm_count, st);
   return cudaErrorInvalidValue;
 }
 
@@ -645,5 +750,6 @@ cudaError_t launch_grad(const GradParams &p, int corr, cudaStream_t st) {
   if (p.mc <= 0) return cudaSuccess;
   if (corr == MGP_CORR_SE) return grad_dispatch<0>(p, st);
   if (corr == MGP_CORR_MATERN32) return grad_dispatch<1>(p, st);
+  if (corr == MGP_CORR_ABSEXP) return grad_dispatch<2>(p, st);
   return cudaErrorInvalidValue;
 }

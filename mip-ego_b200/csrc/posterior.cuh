@@ -14,6 +14,7 @@ struct RgenParams {
   int64_t mc;         // valid candidates in the chunk
   int d, dpad, NJ8, nCblk, JS;   // JS = number of 128-row training blocks (= npad / 128)
   const double *center, *theta, *Bop, *an, *gamma, *avec;
+  const double *Xc;   // centred training inputs (npad x dpad): used by the L1 (absolute-exponential) variant
   double *rP, *meanpart, *ftpart;
   int64_t ldp;        // mc rounded up to 128
 };

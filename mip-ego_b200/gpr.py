@@ -3,10 +3,12 @@ arithmetic runs on the GPU through libmgp_b200 (include/mgp.h).
 
 Same constructor, `fit / update / predict(eval_MSE) / gradient`, the attributes the BO loop and
 the infill criteria read (`is_fitted`, `y`, `sigma2`, `X`, `theta_`, ...), the same exceptions.
-Supported configuration: corr in {squared_exponential, matern(nu=1.5)},
+Supported configuration: corr in {squared_exponential, matern(nu=1.5),
+absolute_exponential},
 `constant_trend` mean (beta given = simple kriging, beta=None = ordinary kriging),
-likelihood='concentrated', estimation modes noiseless (nugget falsy) and noisy (nugget > 0),
-optimizer='BFGS'.  Anything else raises NotImplementedError: there is no CPU fallback.
+likelihood in {'concentrated', 'restricted'}, estimation modes noiseless (nugget falsy), noisy
+(nugget > 0) and noise_estim, optimizer='BFGS'.  Anything else raises NotImplementedError: there
+is no CPU fallback.
 """
 import ctypes
 
@@ -38,8 +40,8 @@ def _check_array(X, name="X"):
 
 class GaussianProcess(object):
     _optimizer_types = ["BFGS"]
-    _correlation_types = ("squared_exponential", "matern")
-    _likelihood_functions = ["concentrated"]
+    _correlation_types = ("squared_exponential", "matern", "absolute_exponential")
+    _likelihood_functions = ["concentrated", "restricted"]
 
     def __init__(self, mean, corr="squared_exponential", theta0=1e-1, thetaL=None, thetaU=None,
                  sigma2=None, nugget=None, noise_estim=False, optimizer="BFGS",
@@ -67,6 +69,7 @@ class GaussianProcess(object):
         self.eval_budget = eval_budget
 
         self.noise_var = np.atleast_1d(nugget) if nugget else 0
+        self._nugget = self.noise_var
         self.noise_estim = True if noise_estim else False
         self.noisy = True if self.noise_var or self.noise_estim else False
         if not self.noisy:
@@ -101,10 +104,6 @@ class GaussianProcess(object):
                 "corr=%r: the CUDA path implements %s" % (self.corr, self._correlation_types))
         if not isinstance(self.mean, constant_trend):
             raise NotImplementedError("only constant_trend is implemented by the CUDA path")
-        if self.likelihood != "concentrated":
-            raise NotImplementedError("likelihood='restricted' is not implemented by the CUDA path")
-        if self.estimation_mode == "noise_estim":
-            raise NotImplementedError("noise_estim=True is not implemented by the CUDA path")
         if self.optimizer not in self._optimizer_types:
             raise ValueError("optimizer should be one of %s" % self._optimizer_types)
 
@@ -159,7 +158,9 @@ class GaussianProcess(object):
     # ------------------------------------------------------------------------------------
     def _mode_nv(self):
         mode = _cabi.MODE[self.estimation_mode]
-        nv = float(np.ravel(self.noise_var)[0]) if self.estimation_mode == "noisy" else 0.0
+        if self.likelihood == "restricted":
+            mode |= _cabi.LIK_RESTRICTED
+        nv = float(np.ravel(self._nugget)[0]) if self.estimation_mode == "noisy" else 0.0
         return mode, nv
 
     def log_likelihood_batch(self, params, eval_grad=True):
@@ -178,13 +179,24 @@ class GaussianProcess(object):
                                     status.ctypes.data_as(_cabi.c_ip)))
         return llf, grad, status
 
+    def log_likelihood_restricted(self, par, env=None, eval_grad=False):
+        """gpr.py:699-796 (REML); par = [theta, sigma2 (, noise_var)]."""
+        if self.likelihood != "restricted":
+            raise ValueError("this model was built with likelihood=%r" % self.likelihood)
+        return self._llf_single(par, env, eval_grad)
+
     def log_likelihood_concentrated(self, par, env=None, eval_grad=False):
         """Single-vector form with the reference's return types (gpr.py:798-946)."""
+        if self.likelihood != "concentrated":
+            raise ValueError("this model was built with likelihood=%r" % self.likelihood)
+        return self._llf_single(par, env, eval_grad)
+
+    def _llf_single(self, par, env=None, eval_grad=False):
         par = np.asarray(par, dtype=np.float64).ravel()
         llf, grad, status = self.log_likelihood_batch(par, eval_grad=eval_grad)
         if env is not None and status[0] <= 0:
             self._finalize(par)
-            env.update(sigma2=self.sigma2, noise_var=self.noise_var, rho=self.rho, Yt=self.Yt,
+            env.update(sigma2=self.sigma2, noise_var=self._env_noise_var, rho=self.rho, Yt=self.Yt,
                        C=self.C, Ft=self.Ft, G=self.G, Q=self.Q)
         if eval_grad:
             return float(llf[0]), grad[0].reshape(-1, 1)
@@ -198,13 +210,17 @@ class GaussianProcess(object):
                 bounds.append(np.c_[self.thetaL, self.thetaU])
             elif name == "sigma2":
                 bounds.append(np.atleast_2d([1e-5, self.y.std() ** 2]))
+            elif name in ("alpha", "noise_var"):
+                bounds.append(np.atleast_2d([1e-10, 1.0 - 1e-10]))
         return np.concatenate(bounds, axis=0)
 
     def _optimize_hyperparameter(self):
         # gpr.py:964-1101
         par_list = ["theta"]
-        if self.estimation_mode == "noisy":
+        if self.likelihood == "restricted" or self.estimation_mode == "noisy":
             par_list += ["sigma2"]
+        if self.estimation_mode == "noise_estim":
+            par_list += ["alpha"] if self.likelihood == "concentrated" else ["noise_var"]
         bounds = self._hyperparameter_bound(par_list)
         log10bounds = log10(bounds)
         n_theta = len(self.thetaL)
@@ -212,7 +228,7 @@ class GaussianProcess(object):
             log10theta0 = log10(self.theta_)
         else:
             log10theta0 = log10(self.theta0)
-        if self.estimation_mode == "noiseless":
+        if self.estimation_mode == "noiseless" and self.likelihood == "concentrated":
             log10param = log10theta0
         else:
             log10param = np.r_[log10theta0, np.random.uniform(log10bounds[n_theta:, 0],
@@ -236,8 +252,8 @@ class GaussianProcess(object):
         optimal_param = 10.0 ** param_opt
         llf = self._finalize(optimal_param)
         param = {"theta": optimal_param[:n_theta]}
-        if self.estimation_mode == "noisy":
-            param["sigma2"] = optimal_param[n_theta:n_theta + 1]
+        for k, name in enumerate(par_list[1:]):
+            param[name] = optimal_param[n_theta + k:n_theta + k + 1]
         return param, llf
 
     def _finalize(self, par):
@@ -252,10 +268,17 @@ class GaussianProcess(object):
         h.check(rc)
         self._cache = {}
         self._host_state = None
-        sc = np.zeros(4)
+        sc = np.zeros(5)
         h.check(h.lib.mgp_get_state(h.h, None, None, None, None, None, None, _cabi.dptr(sc)))
-        # types follow SURVEY Q10: sigma2 is a (1,) array (noiseless) or a numpy scalar (noisy)
-        self.sigma2 = np.array([sc[0]]) if self.estimation_mode == "noiseless" else np.float64(sc[0])
+        # types follow SURVEY Q10: sigma2 is a (1,) array where the reference derives it from rho
+        # (concentrated noiseless / noise_estim, gpr.py:833,849) and a numpy scalar where it is a
+        # parameter (concentrated noisy, restricted)
+        derived = self.likelihood == "concentrated" and self.estimation_mode != "noisy"
+        self.sigma2 = np.array([sc[0]]) if derived else np.float64(sc[0])
+        if self.estimation_mode == "noise_estim":
+            self._env_noise_var = np.array([sc[4]]) if derived else np.float64(sc[4])
+        else:
+            self._env_noise_var = self._nugget if self.estimation_mode == "noisy" else 0
         if self.estimate_trend:
             self.mean.beta = np.array([[sc[1]]])
         self._par_fitted = par.copy()
@@ -271,18 +294,20 @@ class GaussianProcess(object):
             # gpr.py:359-366
             print("Doubling theta upper bound. Increasing nugget...")
             self.thetaU = self.thetaU * 2
-            self.noise_var = self.noise_var * 10
+            self._nugget = self._nugget * 10
             self.par, llf = self._optimize_hyperparameter()
         if not self._fitted_on_device():
             raise np.linalg.LinAlgError("GP fit failed: correlation matrix is not positive definite")
-        self.log_likelihood_ = llf if self.estimation_mode == "noiseless" else np.array([llf])
+        scalar_llf = self.likelihood == "restricted" or self.estimation_mode == "noiseless"
+        self.log_likelihood_ = llf if scalar_llf else np.array([llf])
         self.theta_ = self.par["theta"]
+        self.noise_var = self._env_noise_var     # gpr.py:371
         self.is_fitted = True
         return self
 
     def _fitted_on_device(self):
         h = self._handle()
-        sc = np.zeros(4)
+        sc = np.zeros(5)
         return h.lib.mgp_get_state(h.h, None, None, None, None, None, None, _cabi.dptr(sc)) == 0
 
     def update(self, X, y):
@@ -328,7 +353,7 @@ class GaussianProcess(object):
             h = self._handle()
             n, d = self.X.shape
             bufs = dict(theta=np.empty(d), L=np.empty((n, n)), gamma=np.empty(n), rho=np.empty(n),
-                        Yt=np.empty(n), Ft=np.empty(n), sc=np.empty(4))
+                        Yt=np.empty(n), Ft=np.empty(n), sc=np.empty(5))
             h.check(h.lib.mgp_get_state(h.h, *[_cabi.dptr(bufs[k]) for k in
                                                ("theta", "L", "gamma", "rho", "Yt", "Ft", "sc")]))
             self._cache = bufs

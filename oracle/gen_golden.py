@@ -37,12 +37,12 @@ def make_data(seed, n, d, lb=-5.0, ub=5.0, standardize=True):
     return X, y
 
 
-def ref_model(kind, d, beta, nugget, theta0, thetaL, thetaU, **kw):
+def ref_model(kind, d, beta, nugget, theta0, thetaL, thetaU, likelihood="concentrated", **kw):
     from mipego.GaussianProcess import GaussianProcess
     from mipego.GaussianProcess.trend import constant_trend
     return GaussianProcess(mean=constant_trend(d, beta=beta), corr=kind, theta0=theta0,
                            thetaL=thetaL, thetaU=thetaU, nugget=nugget, optimizer="BFGS",
-                           likelihood="concentrated", **kw)
+                           likelihood=likelihood, **kw)
 
 
 def ref_set_par(gp, X, y, par):
@@ -53,9 +53,10 @@ def ref_set_par(gp, X, y, par):
     env = {}
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        llf, grad = gp.log_likelihood_concentrated(np.asarray(par, dtype=float), env=None,
-                                                   eval_grad=True)
-        llf2 = gp.log_likelihood_concentrated(np.asarray(par, dtype=float), env=env)
+        fn = gp.log_likelihood_restricted if gp.likelihood == "restricted" else \
+            gp.log_likelihood_concentrated
+        llf, grad = fn(np.asarray(par, dtype=float), env=None, eval_grad=True)
+        llf2 = fn(np.asarray(par, dtype=float), env=env)
     n_theta = len(gp.thetaL)
     gp.par = {"theta": np.asarray(par[:n_theta], dtype=float)}
     gp.theta_ = gp.par["theta"]
@@ -80,16 +81,22 @@ def per_point(fn, Xs, d):
     return np.array(vals), np.array(dxs)
 
 
-def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12):
+def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12,
+                   likelihood="concentrated", noise_estim=False):
     """Model state at fixed hyper-parameters + all posterior / acquisition outputs."""
     from mipego import InfillCriteria as IC
     X, y = make_data(seed, n, d)
     rng = np.random.default_rng(seed + 1000)
     theta = (theta_scale / d) * rng.uniform(0.5, 1.5, d) * (4.0 if kind == "matern" else 1.0)
     noisy = bool(nugget)
-    par = np.r_[theta, 0.8] if noisy else theta
+    if likelihood == "restricted":          # [theta, sigma2 (, noise_var)]  gpr.py:712-719
+        par = np.r_[theta, 0.8, 0.01] if noise_estim else np.r_[theta, 0.8]
+    elif noise_estim:                       # [theta, alpha]                 gpr.py:837
+        par = np.r_[theta, 0.95]
+    else:
+        par = np.r_[theta, 0.8] if noisy else theta
     gp = ref_model(kind, d, beta, nugget, theta0=theta, thetaL=1e-5 * np.ones(d),
-                   thetaU=100 * np.ones(d))
+                   thetaU=100 * np.ones(d), likelihood=likelihood, noise_estim=noise_estim)
     llf, grad, llf2 = ref_set_par(gp, X, y, par)
     Xs = rng.uniform(-5, 5, (m, d))
     # a few candidates close to / on training points exercise the small-variance guards
@@ -102,7 +109,7 @@ def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12)
         a, b = gp.gradient(x)
         mdx.append(np.ravel(a)); sdx.append(np.ravel(b))
     out = dict(X=X, y=y, par=par, theta=theta, kind=kind, nugget=float(nugget or 0.0),
-               estimate_trend=beta is None, beta_in=np.nan if beta is None else float(beta),
+               likelihood=likelihood, mode=gp.estimation_mode, estimate_trend=beta is None, beta_in=np.nan if beta is None else float(beta),
                llf=llf, llf_env=llf2, llf_grad=grad,
                sigma2=float(np.ravel(gp.sigma2)[0]), noise_var=float(np.ravel(gp.noise_var)[0]),
                L=gp.C, rho=gp.rho, Yt=gp.Yt, gamma=gp.gamma,
@@ -198,9 +205,31 @@ def case_c1(name="c1_example"):
     print("wrote", name, "theta_=", gp.theta_)
 
 
+def variants():
+    """Estimation-mode / likelihood variants: REML in its three modes
+    (gpr.py:699-796) and the concentrated likelihood with an estimated noise share (:837-853)."""
+    k = 0
+    for kind in ("squared_exponential", "matern"):
+        for beta in (None, 0.3):
+            tr = "ok" if beta is None else "sk"
+            kn = "se" if kind[0] == "s" else "m32"
+            for lik, nugget, ne, tag in (("restricted", 0, False, "reml_noiseless"),
+                                         ("restricted", 1e-4, False, "reml_noisy"),
+                                         ("restricted", 0, True, "reml_noiseestim"),
+                                         ("concentrated", 0, True, "conc_noiseestim")):
+                k += 1
+                case_fixed_par("var_%s_%s_%s" % (kn, tr, tag), seed=300 + k, n=56 + 8 * (k % 3),
+                               d=3 + (k % 2), kind=kind, beta=beta, nugget=nugget, m=16,
+                               likelihood=lik, noise_estim=ne)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        variants()
+        return
+    variants()
     k = 0
     for kind in ("squared_exponential", "matern"):
         for beta in (None, 0.3):

@@ -223,8 +223,75 @@ def log_likelihood_concentrated(X, y, par, kind="squared_exponential", estimate_
     return float(llf), grad
 
 
+def log_likelihood_restricted(X, y, par, kind="squared_exponential", estimate_trend=True,
+                              beta=0.0, mode="noiseless", noise_var=0.0, eval_grad=False, env=None):
+    """Restricted (REML) log-likelihood and gradient, gpr.py:699-796.
+
+    par = [theta, sigma2] ('noiseless': noise 0; 'noisy': the given nugget) or
+    [theta, sigma2, noise_var] ('noise_estim') (gpr.py:712-719);
+    R = (sigma2 R0 + noise_var I) / (sigma2 + noise_var) (:721-724).
+    Ordinary kriging (:733-739): -1/2 ((n-p) log(2 pi v) - log det(F^T F) + 2 sum log L_ii
+    + log(prod diag(G))^2 + rho^T rho / v); simple kriging (:740-743) carries the reference's
+    MINUS sign on the log-determinant term -- reproduced, not corrected.
+    exp(llf) > 1 -> -inf (:745-748; the gradient is still returned).  Gradient (:750-783):
+    g_i = -1/2 (sum C^-1 o dC_i - gamma_^T dC_i gamma_ - sum (qq^T) o dC_i), q = L^-T Q (ordinary
+    kriging only), dC = v dR0/dtheta_i | R0 (sigma2) | I (noise_var).
+    """
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    par = np.asarray(par, dtype=np.float64).ravel()
+    n, d = X.shape
+    n_par = par.size
+    if mode == "noiseless":
+        theta, sigma2, nv = par[:-1], par[-1], 0.0
+    elif mode == "noisy":
+        theta, sigma2, nv = par[:-1], par[-1], float(np.asarray(noise_var).ravel()[0])
+    elif mode == "noise_estim":
+        theta, sigma2, nv = par[:-2], par[-2], par[-1]
+    else:
+        raise ValueError(mode)
+    R0 = correlation_matrix(kind, theta, X)
+    v = sigma2 + nv
+    R = (sigma2 * R0 + nv * np.eye(n)) / v
+    try:
+        L, Ft, Yt, Q, G, rho = compute_aux_var(R, y, estimate_trend, beta)
+    except linalg.LinAlgError:
+        return (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
+    logdet2 = 2.0 * np.log(np.diag(L)).sum()
+    rr = float((rho ** 2.0).sum())
+    if estimate_trend:
+        p = Ft.shape[1]
+        llf = -0.5 * ((n - p) * math.log(2.0 * math.pi * v) - math.log(float(n)) + logdet2
+                      + math.log(float(np.diag(G).prod()) ** 2) + rr / v)
+    else:
+        llf = -0.5 * (n * math.log(2.0 * math.pi * v) - logdet2 + rr / v)
+    if llf > 0 or not np.isfinite(llf):       # np.exp(llf) > 1
+        llf = -np.inf
+    if env is not None:
+        env.update(sigma2=sigma2, noise_var=nv, rho=rho, Yt=Yt, C=L, Ft=Ft, G=G, Q=Q)
+    if not eval_grad:
+        return float(llf)
+    gamma_ = linalg.solve_triangular(L.T, rho, lower=False).reshape(-1, 1) / v
+    Cinv = linalg.cho_solve((L, True), np.eye(n)) / v
+    T = v * corr_grad_theta(kind, theta, X, R0)
+    T = np.concatenate([T, R0[..., None]], axis=2)
+    if mode == "noise_estim":
+        T = np.concatenate([T, np.eye(n)[..., None]], axis=2)
+    if estimate_trend:
+        q = linalg.solve_triangular(L.T, Q, lower=False)
+        term = q.dot(q.T)
+    grad = np.zeros((n_par, 1))
+    for i in range(n_par):
+        Cg = T[:, :, i]
+        gi = np.sum(Cinv * Cg) - gamma_.T.dot(Cg).dot(gamma_).item()
+        if estimate_trend:
+            gi -= np.sum(term * Cg)
+        grad[i] = -0.5 * gi
+    return float(llf), grad
+
+
 def fit_state(X, y, par, kind="squared_exponential", estimate_trend=True, beta=0.0,
-              mode="noiseless", noise_var=0.0):
+              mode="noiseless", noise_var=0.0, likelihood="concentrated"):
     """Fitted-model state for given hyper-parameters: what `fit` harvests after MLE.
 
     gpr.py:1087-1101 (final likelihood call with env), :370-383 (attributes),
@@ -234,15 +301,15 @@ def fit_state(X, y, par, kind="squared_exponential", estimate_trend=True, beta=0
     y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
     par = np.asarray(par, dtype=np.float64).ravel()
     env = {}
-    llf = log_likelihood_concentrated(X, y, par, kind, estimate_trend, beta, mode, noise_var,
-                                      eval_grad=False, env=env)
+    llf_fn = log_likelihood_restricted if likelihood == "restricted" else log_likelihood_concentrated
+    llf = llf_fn(X, y, par, kind, estimate_trend, beta, mode, noise_var, eval_grad=False, env=env)
     if not env:
         raise linalg.LinAlgError("correlation matrix is not positive definite")
     d = X.shape[1]
-    theta = par if mode == "noiseless" else par[:-1]
+    theta = par[:d]
     st = dict(X=X, y=y, kind=kind, theta=np.array(theta, dtype=np.float64),
               estimate_trend=bool(estimate_trend), mode=mode,
-              sigma2=float(env["sigma2"]), noise_var=float(env["noise_var"]),
+              likelihood=likelihood, sigma2=float(env["sigma2"]), noise_var=float(env["noise_var"]),
               L=env["C"], rho=env["rho"], Yt=env["Yt"], Ft=env["Ft"], G=env["G"], Q=env["Q"],
               llf=llf, par=par, d=d)
     if estimate_trend:

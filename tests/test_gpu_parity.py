@@ -10,7 +10,7 @@ With nugget 0 the reference's own formulas evaluated in two orders differ by 4e-
 import numpy as np
 import pytest
 
-from golden_util import FIXED, FITS, load, mode_of, beta_of
+from golden_util import FIXED, FITS, VARS, load, mode_of, beta_of, likelihood_of
 
 pytestmark = pytest.mark.gpu
 
@@ -39,7 +39,7 @@ def make_gp(mb, g, fitted=True):
     return gp
 
 
-SEMAT = [n for n in FIXED if "absexp" not in n]
+SEMAT = list(FIXED)   # squared exponential, Matern-3/2 and absolute exponential fixtures
 
 
 @pytest.mark.parametrize("name", SEMAT)
@@ -152,6 +152,101 @@ def test_likelihood_golden(name):
     if g["estimate_trend"]:
         assert np.max(np.abs(gp.Ft - g["Ft"])) <= 1e-9 * np.abs(g["Ft"]).max()
         assert abs(float(gp.G[0, 0]) - float(g["G"][0, 0])) <= 1e-10 * abs(float(g["G"][0, 0]))
+
+
+@pytest.mark.parametrize("name", VARS)
+def test_variant_modes_golden(name):
+    """REML in its three estimation modes (gpr.py:699-796) and the concentrated likelihood with an
+    estimated noise share (gpr.py:837-853, 915-930): likelihood, gradient, harvested state,
+    posterior and EI against fixtures produced by the reference."""
+    mb, O = _mods()
+    g = load(name)
+    d = g["X"].shape[1]
+    lik, mode = likelihood_of(g), mode_of(g)
+    beta = None if g["estimate_trend"] else float(g["beta_in"])
+    nug = float(g["nugget"])
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=beta), corr=g["kind"], theta0=g["theta"],
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d),
+                            nugget=nug if nug > 0 else 0, noise_estim=(mode == "noise_estim"),
+                            likelihood=lik)
+    assert gp.estimation_mode == mode
+    gp._check_data(g["X"], g["y"])
+    par = g["par"]
+    rng = np.random.default_rng(7)
+    scale = np.ones((4, par.size))
+    scale[:, :d] = rng.uniform(0.6, 1.6, (4, d))
+    P = np.vstack([par, par * scale])
+    llf, grad, status = gp.log_likelihood_batch(P, eval_grad=True)
+    fn = O.log_likelihood_restricted if lik == "restricted" else O.log_likelihood_concentrated
+    ref0 = float(g["llf"])
+    if np.isinf(ref0):
+        assert np.isinf(llf[0]) and status[0] == -1
+    else:
+        assert status[0] == 0 and abs(llf[0] - ref0) <= 1e-9 * abs(ref0)
+    gs = np.abs(g["llf_grad"]).max()
+    assert np.max(np.abs(grad[0] - g["llf_grad"])) <= tol(g, 1e-7, 1e-6) * gs, (grad[0], g["llf_grad"])
+    for b in range(1, 5):
+        rl, rg = fn(g["X"], g["y"], P[b], g["kind"], g["estimate_trend"], beta_of(g), mode, nug,
+                    eval_grad=True)
+        if np.isinf(rl):
+            assert np.isinf(llf[b])
+        else:
+            assert abs(llf[b] - rl) <= 1e-9 * abs(rl)
+        if lik == "restricted" or not np.isinf(rl):
+            assert np.max(np.abs(grad[b] - rg.ravel())) <= tol(g, 1e-7, 1e-6) * np.abs(rg).max()
+    # harvested state (the env of the final likelihood call) + posterior + EI
+    env = {}
+    single = gp.log_likelihood_restricted if lik == "restricted" else gp.log_likelihood_concentrated
+    l1, g1 = single(par, env=env, eval_grad=True)
+    assert g1.shape == (par.size, 1)
+    assert np.allclose(env["C"], g["L"], rtol=0, atol=1e-11)
+    assert abs(float(np.ravel(env["sigma2"])[0]) - float(g["sigma2"])) <= 1e-10 * float(g["sigma2"])
+    assert abs(float(np.ravel(env["noise_var"])[0]) - float(g["noise_var"])) <= \
+        1e-10 * max(float(g["noise_var"]), 1e-300)
+    assert np.max(np.abs(gp.gamma - g["gamma"])) <= tol(g, 1e-8, 1e-6) * np.abs(g["gamma"]).max()
+    gp.theta_, gp.is_fitted = par[:d], True
+    mean, mse = gp.predict(g["Xs"], eval_MSE=True)
+    assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-3)) < tol(g, 1e-9, 1e-6)
+    s2 = float(g["sigma2"])
+    assert np.max(np.abs(mse - g["mse"]) / (np.abs(g["mse"]) + 1e-6 * s2)) < tol(g, 1e-7, 1e-5)
+    ei = mb.EI(model=gp, minimize=True, plugin=float(g["plugin_min"]))
+    v, dx = ei(g["Xs"], return_dx=True)
+    easy = g["mse"] > 1e-4 * s2
+    rv, rdx = g["EI_min"], g["EI_min_dx"]
+    assert np.max(np.abs(v[easy] - rv[easy]) / (np.abs(rv[easy]) + 1e-6 * np.abs(rv).max())) < tol(g, 1e-7, 2e-5)
+    assert np.max(np.abs(dx[easy] - rdx[easy])) < tol(g, 1e-7, 2e-5) * np.abs(rdx[easy]).max()
+
+
+@pytest.mark.parametrize("lik,noise_estim,nugget", [("restricted", False, 0), ("restricted", False, 1e-4),
+                                                    ("restricted", True, 0), ("concentrated", True, 0)])
+def test_variant_modes_fit(lik, noise_estim, nugget):
+    """A full fit in each variant: the MLE found through the batched likelihood is a stationary
+    point of the oracle's likelihood at least as good as the oracle's value at the start."""
+    mb, O = _mods()
+    rng = np.random.default_rng(3)
+    n, d = 70, 3
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0]) + 0.05 * rng.standard_normal(n)
+    y = (y - y.mean()) / y.std()
+    np.random.seed(4)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential",
+                            theta0=[0.05] * d, thetaL=[1e-4] * d, thetaU=[10.0] * d, nugget=nugget,
+                            noise_estim=noise_estim, likelihood=lik, random_start=3)
+    gp.fit(X, y)
+    mode = gp.estimation_mode
+    par = np.concatenate([np.ravel(v) for v in gp.par.values()])
+    fn = O.log_likelihood_restricted if lik == "restricted" else O.log_likelihood_concentrated
+    rl = fn(X, y, par, "squared_exponential", True, 0.0, mode, float(nugget))
+    assert abs(float(np.ravel(gp.log_likelihood_)[0]) - rl) <= 1e-8 * abs(rl)
+    start = np.r_[[0.05] * d, [0.5] * (par.size - d)]
+    assert rl >= fn(X, y, start, "squared_exponential", True, 0.0, mode, float(nugget)) - 1e-9
+    st = O.fit_state(X, y, par, "squared_exponential", True, 0.0, mode, float(nugget), likelihood=lik)
+    Xs = rng.uniform(-5, 5, (200, d))
+    rm, rs = O.predict(st, Xs)
+    mean, mse = gp.predict(Xs, eval_MSE=True)
+    assert np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3)) < 1e-8
+    assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-6
+    assert abs(float(np.ravel(gp.noise_var)[0]) - st["noise_var"]) <= 1e-9 * max(st["noise_var"], 1e-300)
 
 
 def test_not_positive_definite_and_positive_llf_status():

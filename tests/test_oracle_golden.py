@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import gp_oracle as O
-from golden_util import FIXED, FITS, load, mode_of, beta_of, relerr
+from golden_util import FIXED, FITS, VARS, load, mode_of, beta_of, likelihood_of, relerr
 
 # Same formulas, possibly different summation order than the reference: tolerances are
 # rounding-level on the well-conditioned (nugget) cases and looser on nugget-0 cases where the
@@ -110,3 +110,35 @@ def test_fit_state_reproduces_reference_fit(name):
     assert abs(st["llf"] - float(g["llf"])) <= 1e-9 * abs(float(g["llf"]))
     mean, mse = O.predict(st, g["Xs"])
     assert relerr(mean, g["mean"], floor=1e-2) < 1e-7
+
+
+# ---- estimation-mode / likelihood variants (REML, estimated noise share) ---------------------
+@pytest.mark.parametrize("name", VARS)
+def test_variant_likelihood_state_posterior(name):
+    g = load(name)
+    fn = O.log_likelihood_restricted if likelihood_of(g) == "restricted" else O.log_likelihood_concentrated
+    llf, grad = fn(g["X"], g["y"], g["par"], g["kind"], g["estimate_trend"], beta_of(g), mode_of(g),
+                   float(g["nugget"]), eval_grad=True)
+    ref = float(g["llf"])
+    if np.isinf(ref):
+        assert np.isinf(llf) and llf < 0
+    else:
+        assert abs(llf - ref) <= 1e-10 * abs(ref)
+    assert relerr(grad.ravel(), g["llf_grad"], floor=1e-6 * np.abs(g["llf_grad"]).max()) < 1e-8
+    st = O.fit_state(g["X"], g["y"], g["par"], g["kind"], g["estimate_trend"], beta_of(g), mode_of(g),
+                     float(g["nugget"]), likelihood=likelihood_of(g))
+    assert np.allclose(st["L"], g["L"], rtol=0, atol=1e-13)
+    assert abs(st["sigma2"] - float(g["sigma2"])) <= 1e-12 * float(g["sigma2"])
+    assert abs(st["noise_var"] - float(g["noise_var"])) <= 1e-12 * max(float(g["noise_var"]), 1e-300)
+    assert abs(st["beta"] - float(g["beta"])) <= 1e-9 * max(1.0, abs(float(g["beta"])))
+    assert np.max(np.abs(st["gamma"] - g["gamma"])) <= 1e-9 * np.abs(g["gamma"]).max()
+    mean, mse = O.predict(st, g["Xs"])
+    assert relerr(mean, g["mean"], floor=1e-3) < 1e-9
+    assert np.max(np.abs(mse - g["mse"]) / (np.abs(g["mse"]) + 1e-6 * float(g["sigma2"]))) < 1e-7
+    mdx, sdx = O.gradient(st, g["Xs"])
+    assert np.max(np.abs(mdx - g["mean_dx"])) < 1e-9 * np.abs(g["mean_dx"]).max()
+    assert np.max(np.abs(sdx - g["mse_dx"])) < 1e-7 * np.abs(g["mse_dx"]).max()
+    val = O.acquisition(st, g["Xs"], "EI", None, float(g["plugin_min"]), True)
+    rv = g["EI_min"]
+    easy = g["mse"] > 1e-6 * float(g["sigma2"])
+    assert np.max(np.abs(val[easy] - rv[easy]) / (np.abs(rv[easy]) + 1e-6 * np.abs(rv).max())) < 1e-6
