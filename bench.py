@@ -2,7 +2,7 @@
 """bench.py -- GP posterior + EI candidates/s on the BASELINE.json configuration C2
 (n=500, d=10, 10^6 synthetic candidates per GPU, squared-exponential kernel, ordinary kriging).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|nll]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1|c2|c3|c5|nll]
 
 A "step" is one pass of the hot path (K1 cross-correlation tiles -> K2c triangular product with
 fused sum of squares -> K3 MSE + EI epilogue -> top-1) over one batch of candidates.
@@ -35,11 +35,16 @@ sys.path.insert(0, ROOT)
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # measured DMMA m8n8k4 peak on this pool (profiles/fp64_peak_r01.json)
 
 WORKLOADS = {
-    # name: (n, d, m per GPU, kernel, criterion, n_sets)
-    "c2": dict(n=500, d=10, m=1_000_000, kind="squared_exponential", crit="EI", sets=1,
+    # BASELINE.json configs; m = candidates per GPU per step
+    "c1": dict(n=50, d=2, m=10_000, kind="squared_exponential", crit="EI", sets=1, nugget=1e-6, beta=None,
+               desc="GP fit n=50 d=2, EI over 10^4 candidates (BASELINE configs[0], the reference's CPU-runnable case)"),
+    "c2": dict(n=500, d=10, m=1_000_000, kind="squared_exponential", crit="EI", sets=1, nugget=1e-6, beta=None,
                desc="GP predict+EI d=10 n=500 over 10^6 synthetic candidates per GPU (BASELINE configs[1])"),
-    "c3": dict(n=4096, d=20, m=1_250_000, kind="squared_exponential", crit="MGFI", sets=8,
+    "c3": dict(n=4096, d=20, m=1_250_000, kind="squared_exponential", crit="MGFI", sets=8, nugget=1e-6, beta=None,
                desc="ParallelBO MGFI n_point=8 d=20 n=4096, 1.25x10^6 candidates per GPU (BASELINE configs[2] shard)"),
+    "c5": dict(n=8192, d=40, m=262_144, kind="matern", crit="EI", sets=1, nugget=0.0, beta=0.0,
+               desc="BBOB-shaped surrogate d=40 n=8192 Matern-3/2 simple kriging, EI over CMA-ES-sized "
+                    "populations, 2^18 candidates per GPU (BASELINE configs[4])"),
 }
 
 
@@ -53,9 +58,8 @@ def fp64_peak():
         return FP64_PEAK_FALLBACK_TFLOPS, "fallback (earlier DMMA measurement on this pool)"
 
 
-def synth_model(n, d, kind, seed=10, nugget=1e-6):
-    """SURVEY section 8d synthetic model; state built by the oracle's likelihood call (setup only)."""
-    from oracle import gp_oracle as O
+def synth_model(n, d, kind, seed=10):
+    """SURVEY section 8d synthetic training set and hyper-parameters (no fitting here)."""
     rng = np.random.default_rng(seed)
     X = rng.uniform(-5, 5, (n, d))
     y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
@@ -82,7 +86,7 @@ class ClockSampler(threading.Thread):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -97,6 +101,12 @@ class ClockSampler(threading.Thread):
                 self.rows.append(f)
             if self.stop_flag:
                 break
+
+    def wait_first(self, timeout=2.0):
+        """Block (before the timed region) until nvidia-smi has delivered its first sample."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
 
     def stop(self):
         self.stop_flag = True
@@ -123,13 +133,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(rows), "power_w_max": max(r[2] for r in rows)}
 
 
-def cpu_port_rate(n, d, kind, crit, sets, sample, seed=10):
+def model_par(wl, theta):
+    """Hyper-parameter vector of a workload in the reference's layout (gpr.py:814,855)."""
+    return np.r_[theta, 0.9] if wl["nugget"] > 0 else np.asarray(theta)
+
+
+def oracle_state(wl, X, y, theta):
+    from oracle import gp_oracle as O
+    return O.fit_state(X, y, model_par(wl, theta), wl["kind"], wl["beta"] is None, wl["beta"] or 0.0,
+                       "noisy" if wl["nugget"] > 0 else "noiseless", wl["nugget"])
+
+
+def cpu_port_rate(wl, sample, seed=10):
     """Reference algorithm (oracle port) on the host cores: vectorised predict + acquisition in
     chunks of 2000 candidates (the best-case CPU path)."""
     from oracle import gp_oracle as O
     use_all_host_threads()
+    n, d, kind, crit, sets = wl["n"], wl["d"], wl["kind"], wl["crit"], wl["sets"]
     X, y, theta = synth_model(n, d, kind, seed)
-    st = O.fit_state(X, y, np.r_[theta, 0.9], kind, True, 0.0, "noisy", 1e-6)
+    st = oracle_state(wl, X, y, theta)
     Xs = np.random.default_rng(seed + 1).uniform(-5, 5, (sample, d))
     plugin = float(y.min())
     ts = np.exp(np.log(2) + 0.5 * np.random.default_rng(22).standard_normal(sets))
@@ -166,13 +188,13 @@ def blas_threads():
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    sample = 40_000 if wl["n"] <= 1000 else 1000
+    sample = min(wl["m"], 40_000) if wl["n"] <= 1000 else (1000 if wl["n"] <= 4096 else 400)
     rates = []
     for _ in range(args.warmup):
-        cpu_port_rate(wl["n"], wl["d"], wl["kind"], wl["crit"], wl["sets"], min(sample, 4000))
+        cpu_port_rate(wl, min(sample, 4000))
     t_all = 0.0
     for _ in range(args.steps):
-        r, dt = cpu_port_rate(wl["n"], wl["d"], wl["kind"], wl["crit"], wl["sets"], sample)
+        r, dt = cpu_port_rate(wl, sample)
         rates.append(r)
         t_all += dt
     value = sample * args.steps / t_all
@@ -267,6 +289,7 @@ def run_nll(args, rank, world, local):
     work = torch.cuda.Stream(device=dev)
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.wait_first()
     with torch.cuda.stream(work):
         for _ in range(args.warmup):
             out = gp.log_likelihood_batch_device(P_dev)
@@ -357,7 +380,7 @@ def main():
     import torch
     import torch.distributed as dist
     import mipego_b200 as mb
-    from oracle import gp_oracle as O  # model construction (setup) and the cpu_baseline leg only
+    from oracle import gp_oracle as O  # the untimed sanity check and the cpu_baseline leg only
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: mipego_b200 has no CPU fallback")
@@ -367,22 +390,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n, d, m, kind = wl["n"], wl["d"], wl["m"], wl["kind"]
-    # ---- model: built once on rank 0, broadcast so that every rank holds bit-identical state ----
+    # ---- model: hyper-parameters fixed by the workload, state built by the library itself on rank 0
+    # (mgp_finalize_fit) and broadcast so that every rank holds the bit-identical model ------------
+    from mipego_b200.dist import broadcast_fitted_state
     X, y, theta = synth_model(n, d, kind)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=wl["beta"]), corr=kind, theta0=theta,
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d),
+                            nugget=wl["nugget"] if wl["nugget"] > 0 else None, device=local)
     if rank == 0:
-        st = O.fit_state(X, y, np.r_[theta, 0.9], kind, True, 0.0, "noisy", 1e-6)
-        pack = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev) for a in
-                (st["L"], st["gamma"].ravel(), np.array([st["sigma2"], st["beta"]]))]
+        gp.fit_fixed(X, y, model_par(wl, theta))
     else:
-        pack = [torch.empty((n, n), dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.float64, device=dev),
-                torch.empty(2, dtype=torch.float64, device=dev)]
+        gp._check_data(X, y)
     if world > 1:
-        for t in pack:
-            dist.broadcast(t, src=0)
-    L, gamma, sc = [t.cpu().numpy() for t in pack]
-    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr=kind, theta0=theta,
-                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=1e-6, device=local)
-    gp.set_fitted_state(X, y, theta, L, gamma, float(sc[0]), float(sc[1]))
+        broadcast_fitted_state(gp, src=0, device=dev)
     h = gp._handle()
     if args.chunk:
         h.set_option("chunk", args.chunk)
@@ -433,6 +453,7 @@ def main():
     launches0 = h.counter("launches")
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.wait_first()
     ms = timed_pass()
     sampler.stop()
     launches = h.counter("launches") - launches0
@@ -451,11 +472,12 @@ def main():
 
     # ---- e2e: public host API, pinned host candidates in, EI values out, every step ---------------
     Xs_np = Xs_host.numpy()
-    crit.evaluate(Xs_np[:200000], params=params)  # warm the staging buffers
+    vals = torch.empty((wl["sets"], m), dtype=torch.float64).pin_memory().numpy()   # pinned result buffer
+    crit.evaluate(Xs_np[:min(m, 200000)], params=params)  # warm the staging buffers
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        vals = crit.evaluate(Xs_np, params=params)
+        crit.evaluate(Xs_np, params=params, out=vals)
     barrier()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -465,10 +487,10 @@ def main():
 
     if rank == 0:
         # sanity: the timed path reproduces the oracle on a sample (not timed)
-        sub = Xs_np[:2000]
-        rv = O.acquisition(O.fit_state(X, y, np.r_[theta, 0.9], kind, True, 0.0, "noisy", 1e-6), sub, wl["crit"],
+        sub = Xs_np[:2000 if n <= 4096 else 500]
+        rv = O.acquisition(oracle_state(wl, X, y, theta), sub, wl["crit"],
                            None if wl["crit"] == "EI" else float(ts[0]), plugin, True)
-        err = float(np.max(np.abs(vals[0][:2000] - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())))
+        err = float(np.max(np.abs(vals[0][:len(sub)] - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())))
         peak, peak_src = fp64_peak()
         chunk = h.counter("chunk")
         per_launch_c = m * args.steps / max(1, trmm_calls)
@@ -485,7 +507,7 @@ def main():
                        "sample_max_rel_err_vs_oracle": err},
             "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": int(m * d * 8),
                     "d2h_bytes_per_step": int(m * wl["sets"] * 8),
-                    "api": "%s.evaluate(pinned host ndarray) -> host ndarray (mgp_acq)" % wl["crit"]},
+                    "api": "%s.evaluate(pinned host ndarray, out=pinned host ndarray) (mgp_acq)" % wl["crit"]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "k_trmm<false> (T = L^-1 r, fused sum of squares)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -499,8 +521,8 @@ def main():
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
-            sample = 100_000 if n <= 1000 else 1000
-            r, dt = cpu_port_rate(n, d, kind, wl["crit"], wl["sets"], sample)
+            sample = min(m, 100_000) if n <= 1000 else (1000 if n <= 4096 else 400)
+            r, dt = cpu_port_rate(wl, sample)
             line["cpu_baseline"] = {"value": r, "unit": "candidates/s", "cores": blas_threads(), "kind": "port",
                                     "sample": "%d candidates, vectorised predict+%s in chunks of 2000 "
                                               "(oracle port, %.1f s)" % (sample, wl["crit"], dt)}

@@ -54,9 +54,11 @@ class InfillCriteria(object):
         return m._handle()
 
     # ---- batched entry points (new capability) ----------------------------------------------
-    def evaluate(self, X, params=None, return_dx=False):
+    def evaluate(self, X, params=None, return_dx=False, out=None, out_dx=None):
         """Values (n_sets, m) [and gradients (n_sets, m, d)] for `params` (a list of t / alpha /
-        epsilon values sharing one posterior evaluation; default: this object's own parameter)."""
+        epsilon values sharing one posterior evaluation; default: this object's own parameter).
+        `out` / `out_dx`: optional preallocated C-contiguous float64 result arrays (e.g. views of
+        pinned host memory, so that the device-to-host copies run asynchronously)."""
         X = self.check_X(X)
         h = self._handle()
         m, d = X.shape
@@ -64,8 +66,15 @@ class InfillCriteria(object):
             raise ValueError("feature count mismatch")
         P = _cabi.as_f64([self._param()] if params is None else params).ravel()
         ns = P.size
-        val = np.empty((ns, m))
-        dx = np.empty((ns, m, d)) if return_dx else None
+
+        def _buf(a, shape):
+            if a is None:
+                return np.empty(shape)
+            if a.shape != shape or a.dtype != np.float64 or not a.flags.c_contiguous:
+                raise ValueError("output buffer must be a C-contiguous float64 array of shape %r" % (shape,))
+            return a
+        val = _buf(out, (ns, m))
+        dx = _buf(out_dx, (ns, m, d)) if return_dx else None
         h.check(h.lib.mgp_acq(h.h, m, _cabi.dptr(X), _cabi.ACQ[self._kind], ns, _cabi.dptr(P),
                               float(self._plugin_user()), 1 if self.minimize else 0,
                               _cabi.dptr(val), _cabi.dptr(dx)))

@@ -134,7 +134,7 @@ int mgp_destroy(mgp_t *h) {
                    &h->dTmp, &h->dLinvDiag, &h->dMp, &h->dRinvP, &h->dgamma, &h->davec, &h->dFt,
                    &h->dYt, &h->drho, &h->dscal, &h->drP, &h->dmeanpart, &h->dftpart, &h->dqpart,
                    &h->dwP, &h->dXs_stage[0], &h->dXs_stage[1], &h->dout_stage[0],
-                   &h->dout_stage[1], &h->dtopk_val, &h->dtopk_idx, &h->nR, &h->nL, &h->nM, &h->nT,
+                   &h->dout_stage[1], &h->dtopk_val, &h->dtopk_idx, &h->dtopk_blk, &h->nR, &h->nL, &h->nM, &h->nT,
                    &h->nLinvDiag, &h->nvec, &h->nscal, &h->npar, &h->ngpart};
   for (DevBuf *b : all) freebuf(*b);
   for (int i = 0; i < 2; i++) {
@@ -589,9 +589,16 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
   const int NJ8 = h->npad / 8;
   const bool ordinary = h->trend == MGP_TREND_CONST_ESTIMATED;
   double *chunk_val = nullptr;
+  int64_t *blk_idx = nullptr;
+  const bool top1 = q.topk == 1 && !q.want_dx;   // per-block arg-max fused into the epilogue
+  const int64_t nblk_max = (h->chunk + 255) / 256;
   if (q.topk > 0) {
     MGP_TRY(mgp_ensure(h, h->dtopk_val, (size_t)q.n_sets * h->chunk * 8));
     chunk_val = P<double>(h->dtopk_val);
+    if (top1) {
+      MGP_TRY(mgp_ensure(h, h->dtopk_blk, (size_t)q.n_sets * nblk_max * 8));
+      blk_idx = P<int64_t>(h->dtopk_blk);
+    }
   }
   for (int64_t c0 = 0; c0 < q.m; c0 += h->chunk) {
     const int64_t mc = std::min<int64_t>(h->chunk, q.m - c0);
@@ -620,7 +627,9 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       ep.out_mean = q.d_mean ? q.d_mean + c0 : nullptr;
       ep.out_mse = q.d_mse ? q.d_mse + c0 : nullptr;
       ep.out_val = nullptr; ep.ld_val = 0;
-      if (q.topk > 0) { ep.out_val = chunk_val; ep.ld_val = h->chunk; }
+      ep.blk_val = nullptr; ep.blk_idx = nullptr; ep.ld_blk = nblk_max; ep.idx_base = q.idx_base + c0;
+      if (top1) { ep.blk_val = chunk_val; ep.blk_idx = blk_idx; }
+      else if (q.topk > 0) { ep.out_val = chunk_val; ep.ld_val = h->chunk; }
       else if (q.d_val) { ep.out_val = q.d_val + c0; ep.ld_val = q.ld_val ? q.ld_val : q.m; }
       ep.kind = q.kind; ep.n_sets = acq ? q.n_sets : 0; ep.minimize = q.minimize; ep.plugin = q.plugin;
       for (int s = 0; s < MGP_MAX_SETS; s++) ep.params[s] = (acq && q.params && s < q.n_sets) ? q.params[s] : 0.0;
@@ -652,8 +661,12 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     }
     if (q.topk > 0) {
       { KTimer t(h, st, 3);
-      MGP_CUDA(h, launch_topk_merge(chunk_val, h->chunk, mc, q.idx_base + c0, q.n_sets, q.topk, q.d_topv,
-                                    q.d_topi, c0 == 0 && !q.topk_continue, st)); }
+      if (top1)
+        MGP_CUDA(h, launch_topk_merge(chunk_val, blk_idx, nblk_max, (mc + 255) / 256, 0, q.n_sets, 1, q.d_topv,
+                                      q.d_topi, c0 == 0 && !q.topk_continue, st));
+      else
+        MGP_CUDA(h, launch_topk_merge(chunk_val, nullptr, h->chunk, mc, q.idx_base + c0, q.n_sets, q.topk,
+                                      q.d_topv, q.d_topi, c0 == 0 && !q.topk_continue, st)); }
       h->launches++;
     }
   }

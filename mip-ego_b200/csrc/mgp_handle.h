@@ -65,7 +65,7 @@ struct mgp_handle {
   int64_t chunk_opt = 0;   // user override
   DevBuf drP, dmeanpart, dftpart, dqpart, dwP;
   DevBuf dXs_stage[2], dout_stage[2];
-  DevBuf dtopk_val, dtopk_idx;
+  DevBuf dtopk_val, dtopk_idx, dtopk_blk;
   void *hpin[2] = {nullptr, nullptr};
   size_t hpin_bytes = 0;
   // ---- likelihood workspace --------------------------------------------------------------

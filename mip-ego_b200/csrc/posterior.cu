@@ -432,32 +432,67 @@ __device__ __forceinline__ Acq acq_eval(int kind, double par, double plugin, dou
   return o;
 }
 
+// total order of the top-k selection: larger value first, ties -> smaller index first
+__device__ __forceinline__ bool better(double v, int64_t i, double w, int64_t j) {
+  return (v > w) || (v == w && i < j);
+}
+
 // K3: fixed-order reduction of the partial sums, MSE (gpr.py:465-474) and acquisition values.
+// With blk_val != nullptr (top-1 requests) the block also reduces its 256 candidates to the best
+// (value, global index) per parameter set, so that the selection kernel scans one entry per block
+// instead of one per candidate.
 __global__ void __launch_bounds__(256) k_epilogue(EpiParams p) {
+  __shared__ double sbv[8];
+  __shared__ int64_t sbi[8];
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= p.mc) return;
-  double q = 0.0;
-  for (int I = 0; I < p.NI; I++) q += p.qpart[(int64_t)I * p.ld + c];
-  double md = 0.0, ft = 0.0;
-  for (int y = 0; y < p.JS; y++) {
-    md += p.meanpart[(int64_t)y * p.ld + c];
-    ft += p.ftpart[(int64_t)y * p.ld + c];
+  const bool valid = c < p.mc;
+  if (!valid && !p.blk_val) return;
+  double mean = 0.0, mse = 0.0;
+  if (valid) {
+    double q = 0.0;
+    for (int I = 0; I < p.NI; I++) q += p.qpart[(int64_t)I * p.ld + c];
+    double md = 0.0, ft = 0.0;
+    for (int y = 0; y < p.JS; y++) {
+      md += p.meanpart[(int64_t)y * p.ld + c];
+      ft += p.ftpart[(int64_t)y * p.ld + c];
+    }
+    mean = p.beta + md;
+    double u2 = 0.0;
+    if (p.ordinary) {
+      const double u = (ft - 1.0) / p.G;
+      u2 = u * u;
+    }
+    mse = fabs(p.sigma2 * (1.0 - q + u2));
+    if (p.out_mean) p.out_mean[c] = mean;
+    if (p.out_mse) p.out_mse[c] = mse;
   }
-  const double mean = p.beta + md;
-  double u2 = 0.0;
-  if (p.ordinary) {
-    const double u = (ft - 1.0) / p.G;
-    u2 = u * u;
-  }
-  const double mse = fabs(p.sigma2 * (1.0 - q + u2));
-  if (p.out_mean) p.out_mean[c] = mean;
-  if (p.out_mse) p.out_mse[c] = mse;
-  if (p.out_val) {
-    const double sd = sqrt(mse);
-    const double yhat = p.minimize ? mean : -mean;
-    const double plug = p.minimize ? p.plugin : -p.plugin;
-    for (int s = 0; s < p.n_sets; s++)
-      p.out_val[(int64_t)s * p.ld_val + c] = acq_eval(p.kind, p.params[s], plug, yhat, sd, p.sigma2).val;
+  if (!p.out_val && !p.blk_val) return;
+  const double sd = sqrt(mse);
+  const double yhat = p.minimize ? mean : -mean;
+  const double plug = p.minimize ? p.plugin : -p.plugin;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int s = 0; s < p.n_sets; s++) {
+    double v = valid ? acq_eval(p.kind, p.params[s], plug, yhat, sd, p.sigma2).val : -INFINITY;
+    if (p.out_val && valid) p.out_val[(int64_t)s * p.ld_val + c] = v;
+    if (!p.blk_val) continue;
+    // block arg-max (every thread of the block takes part; padding threads carry -inf)
+    double bv = (v == v) ? v : -INFINITY;   // NaN -> -inf, like the selection kernel
+    int64_t bi = valid ? p.idx_base + c : INT64_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { sbv[warp] = bv; sbi[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; w++)
+        if (better(sbv[w], sbi[w], bv, bi)) { bv = sbv[w]; bi = sbi[w]; }
+      p.blk_val[(int64_t)s * p.ld_blk + blockIdx.x] = bv;
+      p.blk_idx[(int64_t)s * p.ld_blk + blockIdx.x] = bi;
+    }
   }
 }
 
@@ -465,12 +500,9 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiParams p) {
 // running top-k (what argmax_restart keeps of a population, optimizer/utils.py:66-87)
 // total order: larger value first, NaN last, ties -> smaller index first
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool better(double v, int64_t i, double w, int64_t j) {
-  return (v > w) || (v == w && i < j);
-}
-__global__ void __launch_bounds__(1024) k_topk_merge(const double *vals, int64_t ld, int64_t mc,
-                                                     int64_t base, int k, double *topv,
-                                                     int64_t *topi, int init) {
+__global__ void __launch_bounds__(1024) k_topk_merge(const double *vals, const int64_t *idxs,
+                                                     int64_t ld, int64_t mc, int64_t base, int k,
+                                                     double *topv, int64_t *topi, int init) {
   __shared__ double sv[32];
   __shared__ int64_t si[32];
   __shared__ double nv[64];
@@ -493,7 +525,7 @@ __global__ void __launch_bounds__(1024) k_topk_merge(const double *vals, int64_t
       if (have_last && !better(lv, li, cv, ci)) return;  // already selected (or before it)
       if (better(cv, ci, bv, bi)) { bv = cv; bi = ci; }
     };
-    for (int64_t i = tid; i < mc; i += 1024) consider(v[i], base + i);
+    for (int64_t i = tid; i < mc; i += 1024) consider(v[i], idxs ? idxs[(int64_t)s * ld + i] : base + i);
     if (!init)
       for (int i = tid; i < k; i += 1024)
         if (ti[i] >= 0) consider(tv[i], ti[i]);
@@ -739,10 +771,11 @@ cudaError_t launch_epilogue(const EpiParams &p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_topk_merge(const double *vals, int64_t ld, int64_t mc, int64_t base, int n_sets,
-                              int k, double *topv, int64_t *topi, int init, cudaStream_t st) {
+cudaError_t launch_topk_merge(const double *vals, const int64_t *idxs, int64_t ld, int64_t mc,
+                              int64_t base, int n_sets, int k, double *topv, int64_t *topi, int init,
+                              cudaStream_t st) {
   if (k > 64) return cudaErrorInvalidValue;
-  k_topk_merge<<<n_sets, 1024, 0, st>>>(vals, ld, mc, base, k, topv, topi, init);
+  k_topk_merge<<<n_sets, 1024, 0, st>>>(vals, idxs, ld, mc, base, k, topv, topi, init);
   return cudaGetLastError();
 }
 

@@ -44,14 +44,20 @@ struct EpiParams {
   int kind, n_sets, minimize;
   double plugin;
   double params[MGP_MAX_SETS];
+  // top-1 fast path: per-block best (value, global index) per set, [n_sets][ld_blk]; nullable
+  double *blk_val;
+  int64_t *blk_idx;
+  int64_t ld_blk, idx_base;
 };
 // K3: mean / MSE / acquisition per candidate.
 cudaError_t launch_epilogue(const EpiParams &p, cudaStream_t st);
 
-// Running top-k: merges the k best of vals[s][0..mc) (global index = base + i) into
-// topv/topi [n_sets][k] (descending; ties -> lower index first).  init != 0 resets them first.
-cudaError_t launch_topk_merge(const double *vals, int64_t ld, int64_t mc, int64_t base, int n_sets,
-                              int k, double *topv, int64_t *topi, int init, cudaStream_t st);
+// Running top-k: merges the k best of vals[s][0..mc) (global index = idxs[s][i], or base + i when
+// idxs is null) into topv/topi [n_sets][k] (descending; ties -> lower index first).
+// init != 0 resets them first.
+cudaError_t launch_topk_merge(const double *vals, const int64_t *idxs, int64_t ld, int64_t mc,
+                              int64_t base, int n_sets, int k, double *topv, int64_t *topi, int init,
+                              cudaStream_t st);
 
 struct GradParams {
   const double *Xs;    // chunk base (row-major, ld d)

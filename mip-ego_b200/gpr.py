@@ -305,6 +305,24 @@ class GaussianProcess(object):
         self.is_fitted = True
         return self
 
+    def fit_fixed(self, X, y, par):
+        """Fit at GIVEN hyper-parameters (no MLE): the final likelihood call of
+        _optimize_hyperparameter + compute_beta_gamma (gpr.py:1087-1101, 670-674) for
+        par = [theta (, sigma2 | alpha) (, noise_var)] in the layout of the chosen likelihood /
+        estimation mode.  Used to adopt known hyper-parameters and by the benchmarks."""
+        self._check_data(X, y)
+        par = np.asarray(par, dtype=np.float64).ravel()
+        llf = self._finalize(par)
+        if not self._fitted_on_device():
+            raise np.linalg.LinAlgError("correlation matrix is not positive definite")
+        n_theta = self.X.shape[1]
+        self.par = {"theta": par[:n_theta]}
+        self.theta_ = self.par["theta"]
+        self.log_likelihood_ = llf
+        self.noise_var = self._env_noise_var
+        self.is_fitted = True
+        return self
+
     def _fitted_on_device(self):
         h = self._handle()
         sc = np.zeros(5)
