@@ -276,6 +276,8 @@ def run_nll(args, rank, world, local):
     h = gp._handle()
     if args.nll_groups:
         h.set_option("nll_groups", args.nll_groups)
+    if args.gemm_cta_cap:
+        h.set_option("gemm_cta_cap", args.gemm_cta_cap)
     P_dev = torch.from_numpy(P).to(dev)
 
     def barrier():
@@ -362,6 +364,7 @@ def main():
     ap.add_argument("--nll-n", type=int, default=4096)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--nll-groups", type=int, default=0)
+    ap.add_argument("--gemm-cta-cap", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

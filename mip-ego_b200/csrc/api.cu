@@ -171,6 +171,11 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
     h->nll_groups_opt = (int)value;
     return MGP_OK;
   }
+  if (!strcmp(name, "gemm_cta_cap")) {
+    h->gemm_cap_opt = (int)value;
+    set_dgemm_cta_cap((int)value);
+    return MGP_OK;
+  }
   if (!strcmp(name, "time_kernels")) {
     resolve_timers(h);
     h->time_kernels = value != 0;
@@ -321,7 +326,7 @@ static void fill_work(mgp_handle *h, NllWork &w, int b_off, int B, int cap, int 
 // only a few SMs (diagonal blocks, panel solves); running the groups on separate streams lets the
 // wide kernels of one group fill the machine while another group is in such a phase.
 static int nll_groups(const mgp_handle *h, int nb) {
-  int g = h->nll_groups_opt > 0 ? h->nll_groups_opt : 4;
+  int g = h->nll_groups_opt > 0 ? h->nll_groups_opt : MGP_NLL_STREAMS;
   if (g > MGP_NLL_STREAMS) g = MGP_NLL_STREAMS;
   if (g > nb) g = nb;
   return g < 1 ? 1 : g;
@@ -341,6 +346,9 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
   for (int b0 = 0; b0 < B; b0 += use) {
     const int nb = std::min(use, B - b0);
     const int G = nll_groups(h, nb);
+    // with concurrent groups no GEMM launch takes every SM: the short kernels of the other groups
+    // (diagonal blocks, panel solves) then start without waiting for a machine-wide GEMM to drain
+    if (G > 1 && h->gemm_cap_opt == 0) set_dgemm_cta_cap(h->sm_count * 3 / 4);
     if (G > 1) MGP_CUDA(h, cudaEventRecord(h->ev_fork, st));
     for (int g = 0; g < G; g++) {
       const int g0 = (int)((int64_t)nb * g / G), g1 = (int)((int64_t)nb * (g + 1) / G);
@@ -360,6 +368,7 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
         MGP_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[g], 0));
       }
     }
+    if (G > 1 && h->gemm_cap_opt == 0) set_dgemm_cta_cap(0);
   }
   return MGP_OK;
 }

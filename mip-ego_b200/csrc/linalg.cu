@@ -574,6 +574,9 @@ static int *sched_words(cudaStream_t st) {
   return p;
 }
 
+static int g_gemm_cta_cap = 0;   // 0 = one CTA per SM
+void set_dgemm_cta_cap(int cap) { g_gemm_cta_cap = cap; }
+
 cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   static bool attr_done = false;
   static int sm_count = 0;
@@ -591,7 +594,8 @@ cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   int *sched = sched_words(st);
   if (!sched) return cudaErrorMemoryAllocation;
   const int total = (g.N / 128) * (g.M / 128) * g.n_inner * g.n_outer;
-  const int grid = total < sm_count ? total : sm_count;
+  int grid = total < sm_count ? total : sm_count;
+  if (g_gemm_cta_cap > 0 && grid > g_gemm_cta_cap) grid = g_gemm_cta_cap;
   const int threads = GEMM_CONSUMERS + GEMM_PRODUCERS;
   if (!g.ta && !g.tb) k_dgemm<false, false><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else if (!g.ta && g.tb) k_dgemm<false, true><<<grid, threads, GEMM_SMEM, st>>>(g, sched);

@@ -22,6 +22,9 @@ struct GemmDesc {
   int64_t sA_in, sB_in, sC_in, sA_out, sB_out, sC_out;
 };
 cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st);
+// Upper bound on the CTAs of one GEMM launch (0 = one per SM): leaves SMs to kernels of other
+// streams when several batch groups run concurrently.
+void set_dgemm_cta_cap(int cap);
 
 // In-place Cholesky of the kb-th 128x128 diagonal block of each matrix of the batch
 // (A row-major, ld, batch stride sA), writing L_kk into Lout (same geometry) and L_kk^-1 into

@@ -10,7 +10,7 @@
 
 #define MGP_MAX_SETS 16
 #define MGP_MAX_D 64
-#define MGP_NLL_STREAMS 4
+#define MGP_NLL_STREAMS 8
 
 struct DevBuf {
   void *p = nullptr;
@@ -71,8 +71,9 @@ struct mgp_handle {
   // ---- likelihood workspace --------------------------------------------------------------
   int nll_cap = 0;  // batch capacity of the buffers below
   int nll_groups_opt = 0;  // 0 = default
-  cudaStream_t nll_stream[MGP_NLL_STREAMS] = {nullptr, nullptr, nullptr, nullptr};  // batch groups
-  cudaEvent_t ev_fork = nullptr, ev_join[MGP_NLL_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+  int gemm_cap_opt = 0;    // user override of the per-launch CTA cap (0 = automatic)
+  cudaStream_t nll_stream[MGP_NLL_STREAMS] = {};  // batch groups
+  cudaEvent_t ev_fork = nullptr, ev_join[MGP_NLL_STREAMS] = {};
   DevBuf nR, nL, nM, nT, nLinvDiag, nvec, nscal, npar, ngpart;
 };
 
