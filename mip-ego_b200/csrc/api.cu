@@ -556,9 +556,9 @@ struct PostReq {
 };
 
 static int post_workspace(mgp_handle *h, bool want_dx) {
-  // default: four candidate blocks per SM per pass (amortises launch ramps and the small
+  // default: eight candidate blocks per SM per pass (amortises launch ramps and the small
   // epilogue / top-k kernels), bounded so that the r scratch stays below 2 GiB
-  int64_t chunk = (int64_t)h->sm_count * 128 * 4;
+  int64_t chunk = (int64_t)h->sm_count * 128 * 8;
   while (chunk > (int64_t)h->sm_count * 128 && (size_t)h->npad * chunk * 8 > ((size_t)2 << 30)) chunk /= 2;
   if (h->chunk_opt > 0) chunk = h->chunk_opt;
   h->chunk = chunk;
@@ -727,9 +727,9 @@ static int host_run(mgp_handle *h, int64_t m, const double *Xs, PostReq q, const
   const int d = h->d;
   const int ns = std::max(1, q.n_sets);
   MGP_TRY(post_workspace(h, q.want_dx));
-  // staging unit: two compute chunks; inputs and outputs are double-buffered so that the H2D of
+  // staging unit: one compute chunk; inputs and outputs are double-buffered so that the H2D of
   // unit i+1 and the D2H of unit i-1 overlap the kernels of unit i (three streams)
-  const int64_t unit = std::min<int64_t>(m, h->chunk * 2);
+  const int64_t unit = std::min<int64_t>(m, h->chunk);
   size_t per = 0;  // output doubles per staged candidate
   if (o.mean) per += 1;
   if (o.mse) per += 1;

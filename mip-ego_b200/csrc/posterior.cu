@@ -46,9 +46,10 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
   // of the training block (Bop rows, an, gamma, a) are staged once per item in shared memory.
   constexpr int DPAD = 4 * KS, SB = rgen_stride(DPAD);   // SB % 16 == 4: conflict-free B fragments
   extern __shared__ __align__(16) double sm_rg[];
-  double *sB = sm_rg, *sV = sm_rg + 128 * SB;
+  double *sB = sm_rg, *sV = sm_rg + 128 * SB, *sTab = sV + 3 * 128;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lk = lane & 3;
   const int nItems = p.nCblk * p.JS;
+  if (tid < 32) sTab[tid] = c_exp2_tab[tid];
   for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
     const int jb = item / p.nCblk, cb = item % p.nCblk;
     __syncthreads();
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
         double c0 = bn[u] + an2.x, c1 = bn[u] + an2.y;
 #pragma unroll
         for (int s = 0; s < KS; s++) dmma884(c0, c1, xa[u][s], bf[s]);
-        const double r0 = corr_from_S<CORR>(c0), r1 = corr_from_S<CORR>(c1);
+        const double r0 = corr_from_S_tab<CORR>(c0, sTab), r1 = corr_from_S_tab<CORR>(c1, sTab);
         double2 *dst = reinterpret_cast<double2 *>(
             p.rP + (((int64_t)cb * p.NJ8 + j8) * 16 + (2 * warp + u)) * 64 + lane * 2);
         *dst = make_double2(r0, r1);
@@ -133,6 +134,8 @@ __global__ void __launch_bounds__(256) k_rgen_l1(RgenParams p) {
   double *sC = sX + DPAD * XS;        // [128][CS]    candidate block
   double *sTh = sC + 128 * CS;        // [DPAD]
   double *sV = sTh + DPAD;            // gamma | avec
+  double *sTab = sV + 2 * 128;        // 2^(j/32)
+  if (threadIdx.x < 32) sTab[threadIdx.x] = c_exp2_tab[threadIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lk = lane & 3;
   const int nItems = p.nCblk * p.JS;
   int last_cb = -1;
@@ -175,7 +178,8 @@ __global__ void __launch_bounds__(256) k_rgen_l1(RgenParams p) {
       const double2 g2 = *reinterpret_cast<const double2 *>(sV + jcol);
       const double2 a2 = *reinterpret_cast<const double2 *>(sV + 128 + jcol);
       const int j8 = jb * 16 + t8;
-      const double r00 = exp(-s00), r01 = exp(-s01), r10 = exp(-s10), r11 = exp(-s11);
+      const double r00 = exp_neg_tab(s00, sTab), r01 = exp_neg_tab(s01, sTab), r10 = exp_neg_tab(s10, sTab),
+                   r11 = exp_neg_tab(s11, sTab);
       *reinterpret_cast<double2 *>(p.rP + (((int64_t)cb * p.NJ8 + j8) * 16 + 2 * warp) * 64 + lane * 2) =
           make_double2(r00, r01);
       *reinterpret_cast<double2 *>(p.rP + (((int64_t)cb * p.NJ8 + j8) * 16 + 2 * warp + 1) * 64 + lane * 2) =
@@ -701,7 +705,7 @@ cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, i
 template <int CORR, int KS>
 static cudaError_t rgen_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
   static int occ = 0;
-  const int smem = (128 * rgen_stride(4 * KS) + 3 * 128) * (int)sizeof(double);
+  const int smem = (128 * rgen_stride(4 * KS) + 3 * 128 + 32) * (int)sizeof(double);
   if (occ == 0) {
     cudaFuncSetAttribute(k_rgen<CORR, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen<CORR, KS>, 256, smem) != cudaSuccess || occ < 1)
@@ -724,7 +728,7 @@ static cudaError_t rgen_dispatch(const RgenParams &p, int sm_count, cudaStream_t
 template <int DPAD>
 static cudaError_t rgen_l1_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
   static int occ = 0;
-  const int smem = (DPAD * 132 + 128 * (DPAD + 1) + DPAD + 2 * 128) * (int)sizeof(double);
+  const int smem = (DPAD * 132 + 128 * (DPAD + 1) + DPAD + 2 * 128 + 32) * (int)sizeof(double);
   if (occ == 0) {
     cudaFuncSetAttribute(k_rgen_l1<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen_l1<DPAD>, 256, smem) != cudaSuccess || occ < 1)
