@@ -1,0 +1,134 @@
+"""BASELINE.json full-size configurations checked through size-independent properties (the oracle
+needs minutes at these sizes): bitwise invariance to chunking and to the order of candidates,
+interpolation at the training points, top-k == sort of the full evaluation, the likelihood
+gradient against central differences of the likelihood itself, shard-count independence."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    return X, (y - y.mean()) / y.std(), rng
+
+
+@pytest.fixture(scope="module")
+def c3_model():
+    """BASELINE configs[2]/[3] shape: n=4096, d=20, squared exponential, nugget 1e-6."""
+    import mipego_b200 as mb
+    n, d = 4096, 20
+    X, y, rng = _data(n, d, 20)
+    theta = (0.12 / d) * rng.uniform(0.5, 1.5, d)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential", theta0=theta,
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=1e-6)
+    gp.fit_fixed(X, y, np.r_[theta, 0.9])
+    return mb, gp, X, y, theta
+
+
+def test_c3_chunk_and_order_invariance(c3_model):
+    mb, gp, X, y, theta = c3_model
+    d = X.shape[1]
+    rng = np.random.default_rng(21)
+    m = 30000
+    Xs = rng.uniform(-5, 5, (m, d))
+    ts = np.exp(np.log(2) + 0.5 * np.random.default_rng(22).standard_normal(8))
+    crit = mb.MGFI(model=gp, minimize=True, plugin=float(y.min()), t=float(ts[0]))
+    h = gp._handle()
+    h.set_option("chunk", 0)
+    V0 = crit.evaluate(Xs, params=ts)
+    mean0, mse0 = gp.predict(Xs, eval_MSE=True)
+    h.set_option("chunk", 4096)          # many passes, ragged last one
+    V1 = crit.evaluate(Xs, params=ts)
+    mean1, mse1 = gp.predict(Xs, eval_MSE=True)
+    assert np.array_equal(V0, V1) and np.array_equal(mean0, mean1) and np.array_equal(mse0, mse1)
+    perm = rng.permutation(m)
+    V2 = crit.evaluate(Xs[perm], params=ts)
+    assert np.array_equal(V2, V0[:, perm])
+    # top-k of the population == stable sort of the full evaluation, for every parameter set
+    tv, ti = crit.topk(Xs, k=16, params=ts)
+    for s in range(len(ts)):
+        order = np.lexsort((np.arange(m), -V0[s]))[:16]
+        assert np.array_equal(ti[s], order) and np.array_equal(tv[s], V0[s][order])
+    h.set_option("chunk", 0)
+    # "shards": evaluating two halves separately gives the same numbers as one call
+    Va = crit.evaluate(Xs[:m // 2 + 17], params=ts)
+    Vb = crit.evaluate(Xs[m // 2 + 17:], params=ts)
+    assert np.array_equal(np.c_[Va, Vb], V0)
+    assert np.all(np.isfinite(V0)) and np.all(V0 >= 0)
+
+
+def test_c3_interpolation_and_gradient_consistency(c3_model):
+    mb, gp, X, y, theta = c3_model
+    # at the training points a GP with a 1e-6 nugget reproduces y and has (almost) no variance
+    mean, mse = gp.predict(X[:2048], eval_MSE=True)
+    s2 = float(np.ravel(gp.sigma2)[0])
+    assert np.max(np.abs(mean - y[:2048])) < 1e-4
+    assert np.max(mse) < 1e-4 * s2
+    # posterior gradient vs central differences of the posterior itself
+    rng = np.random.default_rng(5)
+    x0 = rng.uniform(-4, 4, (6, X.shape[1]))
+    gm, gs = gp.gradient_batch(x0)
+    eps = 1e-5
+    for i in (0, 7, 19):
+        e = np.zeros(X.shape[1]); e[i] = eps
+        mp, sp = gp.predict(x0 + e, eval_MSE=True)
+        mm, sm = gp.predict(x0 - e, eval_MSE=True)
+        assert np.max(np.abs((mp - mm) / (2 * eps) - gm[:, i])) < 1e-6 * max(1.0, np.abs(gm).max())
+        assert np.max(np.abs((sp - sm) / (2 * eps) - gs[:, i])) < 1e-6 * max(1.0, np.abs(gs).max())
+
+
+def test_c4_likelihood_gradient_vs_differences():
+    """BASELINE configs[3]: n=4096, d=20 likelihood.  In noisy mode the reference's gradient is the
+    true derivative, so central differences of the batched llf must reproduce it;
+    the batch layout (groups on streams) must not change any value."""
+    import mipego_b200 as mb
+    n, d = 4096, 20
+    X, y, rng = _data(n, d, 30)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential",
+                            theta0=0.01 * np.ones(d), thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d),
+                            nugget=1e-6)
+    gp._check_data(X, y)
+    par = np.r_[(0.12 / d) * rng.uniform(0.5, 1.5, d), 0.8]
+    comps = [0, 11, d]
+    P = [par]
+    for i in comps:
+        hstep = 1e-4 * par[i]
+        for sgn in (1, -1):
+            q = par.copy(); q[i] += sgn * hstep
+            P.append(q)
+    P = np.array(P)
+    llf, grad, status = gp.log_likelihood_batch(P, eval_grad=True)
+    assert np.all(status == 0) and np.all(np.isfinite(llf))
+    for k, i in enumerate(comps):
+        fd = (llf[1 + 2 * k] - llf[2 + 2 * k]) / (2e-4 * par[i])
+        assert abs(fd - grad[0, i]) <= 2e-5 * abs(grad[0, i]) + 1e-6, (i, fd, grad[0, i])
+    # same vectors, different batch composition / group layout: bitwise identical rows
+    h = gp._handle()
+    h.set_option("nll_groups", 1)
+    llf1, grad1, _ = gp.log_likelihood_batch(P[:3], eval_grad=True)
+    h.set_option("nll_groups", 0)
+    assert np.array_equal(llf1, llf[:3]) and np.array_equal(grad1, grad[:3])
+
+
+def test_c5_shape_runs_and_is_consistent():
+    """BASELINE configs[4] shape: n=8192, d=40, Matern-3/2, simple kriging, nugget 0."""
+    import mipego_b200 as mb
+    n, d = 8192, 40
+    X, y, rng = _data(n, d, 40)
+    theta = (0.12 / d) * rng.uniform(0.5, 1.5, d) * 4.0
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=0.0), corr="matern", theta0=theta,
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d))
+    gp.fit_fixed(X, y, theta)
+    mean, mse = gp.predict(X[:1024], eval_MSE=True)
+    s2 = float(np.ravel(gp.sigma2)[0])
+    assert np.max(np.abs(mean - y[:1024])) < 1e-6 and np.max(mse) < 1e-8 * s2   # exact interpolation
+    Xs = rng.uniform(-5, 5, (5000, d))
+    ei = mb.EI(model=gp, minimize=True, plugin=float(y.min()))
+    v = ei(Xs)
+    v2 = ei(Xs[::-1].copy())
+    assert np.array_equal(v2[::-1], v) and np.all(v >= 0) and np.all(np.isfinite(v))
+    m2, s2_ = gp.predict(Xs, eval_MSE=True)
+    assert np.all(s2_ <= s2 * (1 + 1e-9))      # simple kriging: posterior variance <= prior variance
