@@ -125,3 +125,47 @@ def sharded_nll(gp, params, eval_grad=True, device=None):
         blk = out[r].cpu().numpy()
         llf_all[a:b], st_all[a:b], g_all[a:b] = blk[:b - a, 0], blk[:b - a, 1].astype(np.int32), blk[:b - a, 2:]
     return llf_all, (g_all if eval_grad else None), st_all
+
+
+def sharded_multistart(batch_fn, starts, log10bounds, eval_budget, wait_iter, device=None):
+    """Multi-start L-BFGS-B with the restarts partitioned over ranks ("MLE:
+    partition the B restart vectors by rank"): rank r runs rows shard_range(R, r, world) of
+    `starts` in lock-step on its own GPU, the per-rank winners (f, x) are all-gathered and reduced
+    in rank order with the reference's `<=` rule (gpr.py:1045-1052), so every rank returns the
+    result a single process would get from all R restarts.  Same signature/return as
+    _mle.multistart_lbfgsb."""
+    from ._mle import multistart_lbfgsb
+    torch, dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    starts = np.atleast_2d(np.asarray(starts, dtype=np.float64))
+    R, n_par = starts.shape
+    lo, hi = shard_range(R, rank, world)
+    row = np.full(n_par + 3, np.nan)
+    infos = []
+    if hi > lo:
+        p, f, n_evals, infos = multistart_lbfgsb(batch_fn, starts[lo:hi], log10bounds, eval_budget,
+                                                 wait_iter, mode="batched")
+        row[0], row[1], row[2], row[3:] = f, n_evals, 1.0, p
+    else:
+        row[0], row[1], row[2] = np.inf, 0.0, 0.0
+    dev = device if device is not None else "cpu"
+    mine = torch.from_numpy(row).to(dev)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    best_p, best_f, total = None, np.inf, 0
+    for r in range(world):
+        blk = out[r].cpu().numpy()
+        if blk[2] == 0.0:
+            continue
+        total += int(blk[1])
+        if best_p is None or blk[0] <= best_f:
+            best_p, best_f = blk[3:].copy(), float(blk[0])
+    return best_p, best_f, total, infos
+
+
+def sharded_fit(gp, X, y, device=None):
+    """GaussianProcess.fit with the MLE restarts sharded over the ranks.  Every rank must pass the
+    same X, y and hold the same numpy global RNG state (the restart points are drawn from it,
+    gpr.py:1035-1036, identically on every rank).  Each rank then builds the fitted state for the
+    winning hyper-parameters itself -- same inputs, same kernels, hence the bit-identical model."""
+    return gp.fit(X, y, _solve=lambda *a: sharded_multistart(*a, device=device))

@@ -214,8 +214,9 @@ class GaussianProcess(object):
                 bounds.append(np.atleast_2d([1e-10, 1.0 - 1e-10]))
         return np.concatenate(bounds, axis=0)
 
-    def _optimize_hyperparameter(self):
-        # gpr.py:964-1101
+    def _optimize_hyperparameter(self, solve=None):
+        # gpr.py:964-1101.  `solve` replaces the multi-start driver (dist.sharded_fit shards the
+        # restarts over ranks); default: multistart_lbfgsb in this process.
         par_list = ["theta"]
         if self.likelihood == "restricted" or self.estimation_mode == "noisy":
             par_list += ["sigma2"]
@@ -244,9 +245,10 @@ class GaussianProcess(object):
             llf, grad, _ = self.log_likelihood_batch(10.0 ** P, eval_grad=True)
             return -llf, -grad
 
-        param_opt, llf_opt, n_evals, infos = multistart_lbfgsb(
-            batch_fn, np.array(starts), log10bounds, eval_budget, self.wait_iter,
-            mode=self.restart_mode)
+        if solve is None:
+            solve = lambda *a: multistart_lbfgsb(*a, mode=self.restart_mode)  # noqa: E731
+        param_opt, llf_opt, n_evals, infos = solve(batch_fn, np.array(starts), log10bounds, eval_budget,
+                                                   self.wait_iter)
         self.eval_count = n_evals
         self.opt_info_ = infos
         optimal_param = 10.0 ** param_opt
@@ -285,17 +287,17 @@ class GaussianProcess(object):
         return float(out.value)
 
     # ------------------------------------------------------------------------------------
-    def fit(self, X, y):
+    def fit(self, X, y, _solve=None):
         """gpr.py:328-385."""
         self._check_data(X, y)
         self.is_fitted = False
-        self.par, llf = self._optimize_hyperparameter()
+        self.par, llf = self._optimize_hyperparameter(_solve)
         if np.isinf(llf):
             # gpr.py:359-366
             print("Doubling theta upper bound. Increasing nugget...")
             self.thetaU = self.thetaU * 2
             self._nugget = self._nugget * 10
-            self.par, llf = self._optimize_hyperparameter()
+            self.par, llf = self._optimize_hyperparameter(_solve)
         if not self._fitted_on_device():
             raise np.linalg.LinAlgError("GP fit failed: correlation matrix is not positive definite")
         scalar_llf = self.likelihood == "restricted" or self.estimation_mode == "noiseless"

@@ -62,6 +62,14 @@ class _FakeGP:
         return -(P ** 2).sum(1), -2 * P, (P[:, 0] > 0.9).astype(np.int32)
 
 
+def _ms_objective(P):
+    """Batched (f, grad) of a multimodal function of log10-parameters (stand-in for -llf)."""
+    P = np.atleast_2d(P)
+    f = np.sum(P ** 2, axis=1) + np.sum(np.cos(4 * P), axis=1)
+    g = 2 * P - 4 * np.sin(4 * P)
+    return f, g
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -76,7 +84,10 @@ def _worker(rank, world, port, q):
         llf, grad, st = D.sharded_nll(_FakeGP(1), P)
         gp = _FakeGP(rank)
         D.broadcast_fitted_state(gp, src=0)
-        q.put((rank, v, i, llf, grad, st, gp.fitted))
+        # restarts sharded over ranks: 5 starts of a multimodal objective, 3 + 2
+        starts = np.random.default_rng(3).uniform(-2, 2, (5, 2))
+        ms = D.sharded_multistart(_ms_objective, starts, np.array([[-2.0, 2.0]] * 2), 200, 5)
+        q.put((rank, v, i, llf, grad, st, gp.fitted, ms[:3]))
     finally:
         dist.destroy_process_group()
 
@@ -120,7 +131,14 @@ def test_world2_gloo_exchange():
     X = rng.uniform(-1, 1, (1001, 3))
     ref_v, ref_i = _FakeCrit().topk(X, k=4, params=[1.0, 2.0])
     P = rng.uniform(size=(5, 3))
-    for rank, v, i, llf, grad, st, fitted in res:
+    from mipego_b200._mle import multistart_lbfgsb
+    starts = np.random.default_rng(3).uniform(-2, 2, (5, 2))
+    one_p, one_f, one_n, _ = multistart_lbfgsb(_ms_objective, starts, np.array([[-2.0, 2.0]] * 2), 200, 5,
+                                               mode="batched")
+    for r in res:
+        p, f, n_evals = r[7]
+        assert f == one_f and np.array_equal(p, one_p) and n_evals == one_n   # == unsharded run
+    for rank, v, i, llf, grad, st, fitted, _ms in res:
         assert np.array_equal(i, ref_i) and np.array_equal(v, ref_v)      # same as the unsharded run
         assert np.allclose(llf, -(P ** 2).sum(1)) and np.allclose(grad, -2 * P)
         assert np.array_equal(st, (P[:, 0] > 0.9).astype(np.int32))
