@@ -318,7 +318,14 @@ class GaussianProcess(object):
         if not self._fitted_on_device():
             raise np.linalg.LinAlgError("correlation matrix is not positive definite")
         n_theta = self.X.shape[1]
+        names = []
+        if self.likelihood == "restricted" or self.estimation_mode == "noisy":
+            names.append("sigma2")
+        if self.estimation_mode == "noise_estim":
+            names.append("alpha" if self.likelihood == "concentrated" else "noise_var")
         self.par = {"theta": par[:n_theta]}
+        for k, name in enumerate(names):
+            self.par[name] = par[n_theta + k:n_theta + k + 1]
         self.theta_ = self.par["theta"]
         self.log_likelihood_ = llf
         self.noise_var = self._env_noise_var
@@ -330,9 +337,21 @@ class GaussianProcess(object):
         sc = np.zeros(5)
         return h.lib.mgp_get_state(h.h, None, None, None, None, None, None, _cabi.dptr(sc)) == 0
 
-    def update(self, X, y):
-        self.fit(X, y)
-        return self
+    def update(self, X, y, reoptimize=True):
+        """gpr.py:387-390 (`update` = `fit`; its TODO asks for incremental training).
+        reoptimize=False keeps the current hyper-parameters and only rebuilds the factorisation and
+        the posterior operands for the new data (mgp_finalize_fit: 2/3 n^3 flop on the tensor pipe,
+        about 2 ms at n = 4096) -- the cheap refit a BO loop wants between MLE rounds.  A rank-k
+        Cholesky append would save part of that at O(n^2 k); at these sizes the full rebuild is
+        already far below the cost of one objective evaluation, so it is not implemented."""
+        if reoptimize or not self.is_fitted:
+            return self.fit(X, y)
+        par = np.concatenate([np.ravel(v) for v in self.par.values()])
+        if self.estimation_mode == "noise_estim" or self.likelihood == "restricted" or \
+                self.estimation_mode == "noisy":
+            full = getattr(self, "_par_fitted", None)
+            par = full if full is not None and full.size >= par.size else par
+        return self.fit_fixed(X, y, par)
 
     def set_fitted_state(self, X, y, theta, L, gamma, sigma2, beta):
         """Adopt an externally fitted model (mgp_set_state): used by un-pickling and by the

@@ -37,10 +37,12 @@ def make_data(seed, n, d, lb=-5.0, ub=5.0, standardize=True):
     return X, y
 
 
-def ref_model(kind, d, beta, nugget, theta0, thetaL, thetaU, likelihood="concentrated", **kw):
+def ref_model(kind, d, beta, nugget, theta0, thetaL, thetaU, likelihood="concentrated",
+              trend="constant", **kw):
     from mipego.GaussianProcess import GaussianProcess
-    from mipego.GaussianProcess.trend import constant_trend
-    return GaussianProcess(mean=constant_trend(d, beta=beta), corr=kind, theta0=theta0,
+    from mipego.GaussianProcess.trend import constant_trend, linear_trend
+    mean = constant_trend(d, beta=beta) if trend == "constant" else linear_trend(d, beta=beta)
+    return GaussianProcess(mean=mean, corr=kind, theta0=theta0,
                            thetaL=thetaL, thetaU=thetaU, nugget=nugget, optimizer="BFGS",
                            likelihood=likelihood, **kw)
 
@@ -82,10 +84,12 @@ def per_point(fn, Xs, d):
 
 
 def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12,
-                   likelihood="concentrated", noise_estim=False):
+                   likelihood="concentrated", noise_estim=False, trend="constant"):
     """Model state at fixed hyper-parameters + all posterior / acquisition outputs."""
     from mipego import InfillCriteria as IC
     X, y = make_data(seed, n, d)
+    if trend == "linear":       # give the linear basis something to explain
+        y = y + 0.3 * X[:, 1] - 0.2 * X[:, 0]
     rng = np.random.default_rng(seed + 1000)
     theta = (theta_scale / d) * rng.uniform(0.5, 1.5, d) * (4.0 if kind == "matern" else 1.0)
     noisy = bool(nugget)
@@ -96,7 +100,8 @@ def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12,
     else:
         par = np.r_[theta, 0.8] if noisy else theta
     gp = ref_model(kind, d, beta, nugget, theta0=theta, thetaL=1e-5 * np.ones(d),
-                   thetaU=100 * np.ones(d), likelihood=likelihood, noise_estim=noise_estim)
+                   thetaU=100 * np.ones(d), likelihood=likelihood, noise_estim=noise_estim,
+                   trend=trend)
     llf, grad, llf2 = ref_set_par(gp, X, y, par)
     Xs = rng.uniform(-5, 5, (m, d))
     # a few candidates close to / on training points exercise the small-variance guards
@@ -109,11 +114,12 @@ def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12,
         a, b = gp.gradient(x)
         mdx.append(np.ravel(a)); sdx.append(np.ravel(b))
     out = dict(X=X, y=y, par=par, theta=theta, kind=kind, nugget=float(nugget or 0.0),
-               likelihood=likelihood, mode=gp.estimation_mode, estimate_trend=beta is None, beta_in=np.nan if beta is None else float(beta),
+               likelihood=likelihood, mode=gp.estimation_mode, estimate_trend=beta is None,
+               trend=trend, beta_in=np.nan if beta is None else np.asarray(beta, dtype=float),
                llf=llf, llf_env=llf2, llf_grad=grad,
                sigma2=float(np.ravel(gp.sigma2)[0]), noise_var=float(np.ravel(gp.noise_var)[0]),
                L=gp.C, rho=gp.rho, Yt=gp.Yt, gamma=gp.gamma,
-               beta=float(np.ravel(gp.mean.beta)[0]),
+               beta=float(np.ravel(gp.mean.beta)[0]) if trend == "constant" else np.ravel(gp.mean.beta),
                Xs=Xs, mean=mean, mse=mse, mean_dx=np.array(mdx), mse_dx=np.array(sdx))
     if beta is None:
         out.update(Ft=gp.Ft, G=gp.G, Q=gp.Q)
@@ -223,13 +229,33 @@ def variants():
                                likelihood=lik, noise_estim=ne)
 
 
+def linear_trends():
+    """Universal kriging with the first-order polynomial trend (trend.py:90-110), beta estimated
+    (p = d + 1) or given; concentrated (noiseless / noisy) and restricted likelihoods."""
+    k = 0
+    for kind in ("squared_exponential", "matern"):
+        for est in (True, False):
+            for lik, nugget, tag in (("concentrated", 0, "noiseless"), ("concentrated", 1e-6, "noisy"),
+                                     ("restricted", 1e-4, "reml_noisy")):
+                k += 1
+                d = 3 + (k % 2)
+                beta = None if est else list(np.round(np.linspace(0.2, -0.1, d + 1), 3))
+                case_fixed_par("lin_%s_%s_%s" % ("se" if kind[0] == "s" else "m32", "uk" if est else "sk", tag),
+                               seed=400 + k, n=56 + 8 * (k % 3), d=d, kind=kind, beta=beta, nugget=nugget,
+                               m=16, likelihood=lik, trend="linear")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         variants()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "linear":
+        linear_trends()
+        return
     variants()
+    linear_trends()
     k = 0
     for kind in ("squared_exponential", "matern"):
         for beta in (None, 0.3):

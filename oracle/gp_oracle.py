@@ -109,18 +109,49 @@ def corr_grad_theta(kind, theta, X, R0):
 # --------------------------------------------------------------------------------------
 # auxiliary variables and likelihood  (gpr.py:676-697, 798-946)
 # --------------------------------------------------------------------------------------
-def compute_aux_var(R, y, estimate_trend, beta):
-    """L, Ft, Yt, Q, G, rho  (gpr.py:676-697); constant trend only (trend.py:69-88)."""
+def trend_F(trend, X):
+    """Basis functions of the prior mean at X: 'constant' -> 1 (trend.py:69-88),
+    'linear' -> [1, x_1..x_d] (trend.py:90-110).  (m, p)."""
+    X = np.atleast_2d(X)
+    if trend == "constant":
+        return np.ones((X.shape[0], 1))
+    if trend == "linear":
+        return np.c_[np.ones(X.shape[0]), X]
+    raise ValueError(trend)
+
+
+def trend_jacobian(trend, d):
+    """f_dx (p, d), numerator layout: zeros (trend.py:86-88) | [0; I] (trend.py:106-109)."""
+    if trend == "constant":
+        return np.zeros((1, d))
+    if trend == "linear":
+        return np.r_[np.zeros((1, d)), np.eye(d)]
+    raise ValueError(trend)
+
+
+def _beta_vec(beta, p):
+    """BasisExpansionTrend.set_beta (trend.py:27-34): a scalar is repeated p times."""
+    b = np.asarray(beta, dtype=np.float64).ravel()
+    if b.size == 1:
+        b = np.repeat(b, p)
+    if b.size != p:
+        raise ValueError("Shapes of beta and F do not match.")
+    return b.reshape(-1, 1)
+
+
+def compute_aux_var(R, y, estimate_trend, beta, F=None):
+    """L, Ft, Yt, Q, G, rho  (gpr.py:676-697).  F: (n, p) basis matrix (default: constant)."""
     n = R.shape[0]
+    if F is None:
+        F = np.ones((n, 1))
     L = linalg.cholesky(R, lower=True)
     Yt = linalg.solve_triangular(L, y.reshape(-1, 1), lower=True)
     if estimate_trend:
-        F = np.ones((n, 1))
         Ft = linalg.solve_triangular(L, F, lower=True)
         Q, G = linalg.qr(Ft, mode="economic")
         rho = Yt - Q.dot(Q.T).dot(Yt)
     else:
-        mu = np.ones((n, 1)) * float(beta)
+        mu = F.dot(_beta_vec(beta, F.shape[1]))
         rho = Yt - linalg.solve_triangular(L, mu, lower=True)
         Ft, Q, G = None, None, None
     return L, Ft, Yt, Q, G, rho
@@ -128,7 +159,7 @@ def compute_aux_var(R, y, estimate_trend, beta):
 
 def log_likelihood_concentrated(X, y, par, kind="squared_exponential", estimate_trend=True,
                                 beta=0.0, mode="noiseless", noise_var=0.0, eval_grad=False,
-                                env=None):
+                                env=None, trend="constant"):
     """Concentrated log-likelihood and its gradient w.r.t. the raw parameters.
 
     Follows gpr.py:798-946.  mode 'noiseless': par=theta (gpr.py:814-835);
@@ -167,14 +198,14 @@ def log_likelihood_concentrated(X, y, par, kind="squared_exponential", estimate_
         raise ValueError(mode)
 
     try:
-        L, Ft, Yt, Q, G, rho = compute_aux_var(R, y, estimate_trend, beta)
+        L, Ft, Yt, Q, G, rho = compute_aux_var(R, y, estimate_trend, beta, trend_F(trend, X))
     except linalg.LinAlgError:
         return fail
 
     logdet2 = 2.0 * np.log(np.diag(L)).sum()
     rr = float((rho ** 2.0).sum())
     if mode == "noiseless":
-        k = 1 if estimate_trend else 0
+        k = Ft.shape[1] if estimate_trend else 0     # matrix_rank(Q Q^T) = p (gpr.py:829-832)
         sigma2 = rr / (n - k)
         llf = -0.5 * (n * math.log(2.0 * math.pi * sigma2) + logdet2 + n) if sigma2 > 0 \
             else np.inf
@@ -224,7 +255,8 @@ def log_likelihood_concentrated(X, y, par, kind="squared_exponential", estimate_
 
 
 def log_likelihood_restricted(X, y, par, kind="squared_exponential", estimate_trend=True,
-                              beta=0.0, mode="noiseless", noise_var=0.0, eval_grad=False, env=None):
+                              beta=0.0, mode="noiseless", noise_var=0.0, eval_grad=False, env=None,
+                              trend="constant"):
     """Restricted (REML) log-likelihood and gradient, gpr.py:699-796.
 
     par = [theta, sigma2] ('noiseless': noise 0; 'noisy': the given nugget) or
@@ -253,16 +285,17 @@ def log_likelihood_restricted(X, y, par, kind="squared_exponential", estimate_tr
     R0 = correlation_matrix(kind, theta, X)
     v = sigma2 + nv
     R = (sigma2 * R0 + nv * np.eye(n)) / v
+    F = trend_F(trend, X)
     try:
-        L, Ft, Yt, Q, G, rho = compute_aux_var(R, y, estimate_trend, beta)
+        L, Ft, Yt, Q, G, rho = compute_aux_var(R, y, estimate_trend, beta, F)
     except linalg.LinAlgError:
         return (-np.inf, np.zeros((n_par, 1))) if eval_grad else -np.inf
     logdet2 = 2.0 * np.log(np.diag(L)).sum()
     rr = float((rho ** 2.0).sum())
     if estimate_trend:
         p = Ft.shape[1]
-        llf = -0.5 * ((n - p) * math.log(2.0 * math.pi * v) - math.log(float(n)) + logdet2
-                      + math.log(float(np.diag(G).prod()) ** 2) + rr / v)
+        llf = -0.5 * ((n - p) * math.log(2.0 * math.pi * v) - math.log(np.linalg.det(F.T.dot(F)))
+                      + logdet2 + math.log(float(np.diag(G).prod()) ** 2) + rr / v)
     else:
         llf = -0.5 * (n * math.log(2.0 * math.pi * v) - logdet2 + rr / v)
     if llf > 0 or not np.isfinite(llf):       # np.exp(llf) > 1
@@ -291,7 +324,7 @@ def log_likelihood_restricted(X, y, par, kind="squared_exponential", estimate_tr
 
 
 def fit_state(X, y, par, kind="squared_exponential", estimate_trend=True, beta=0.0,
-              mode="noiseless", noise_var=0.0, likelihood="concentrated"):
+              mode="noiseless", noise_var=0.0, likelihood="concentrated", trend="constant"):
     """Fitted-model state for given hyper-parameters: what `fit` harvests after MLE.
 
     gpr.py:1087-1101 (final likelihood call with env), :370-383 (attributes),
@@ -302,7 +335,8 @@ def fit_state(X, y, par, kind="squared_exponential", estimate_trend=True, beta=0
     par = np.asarray(par, dtype=np.float64).ravel()
     env = {}
     llf_fn = log_likelihood_restricted if likelihood == "restricted" else log_likelihood_concentrated
-    llf = llf_fn(X, y, par, kind, estimate_trend, beta, mode, noise_var, eval_grad=False, env=env)
+    llf = llf_fn(X, y, par, kind, estimate_trend, beta, mode, noise_var, eval_grad=False, env=env,
+                 trend=trend)
     if not env:
         raise linalg.LinAlgError("correlation matrix is not positive definite")
     d = X.shape[1]
@@ -312,10 +346,14 @@ def fit_state(X, y, par, kind="squared_exponential", estimate_trend=True, beta=0
               likelihood=likelihood, sigma2=float(env["sigma2"]), noise_var=float(env["noise_var"]),
               L=env["C"], rho=env["rho"], Yt=env["Yt"], Ft=env["Ft"], G=env["G"], Q=env["Q"],
               llf=llf, par=par, d=d)
+    st["trend"] = trend
+    p = trend_F(trend, X[:1]).shape[1]
     if estimate_trend:
-        st["beta"] = float(linalg.solve_triangular(st["G"], st["Q"].T.dot(st["Yt"]))[0, 0])
+        bvec = linalg.solve_triangular(st["G"], st["Q"].T.dot(st["Yt"])).reshape(-1, 1)
     else:
-        st["beta"] = float(beta)
+        bvec = _beta_vec(beta, p)
+    st["beta_vec"] = bvec
+    st["beta"] = float(bvec[0, 0]) if p == 1 else bvec.ravel().copy()
     st["gamma"] = linalg.solve_triangular(st["L"].T, st["rho"], lower=False).reshape(-1, 1)
     return st
 
@@ -340,11 +378,12 @@ def predict(st, Xs, eval_MSE=True, chunk=2048):
     for s in range(0, m, chunk):
         xs = Xs[s:s + chunk]
         r = cross_corr(st["kind"], st["theta"], xs, X)
-        mean[s:s + chunk] = st["beta"] + r.dot(st["gamma"]).ravel()
+        f = trend_F(st.get("trend", "constant"), xs)
+        mean[s:s + chunk] = (f.dot(st["beta_vec"]) + r.dot(st["gamma"])).ravel()
         if eval_MSE:
             rt = linalg.solve_triangular(L, r.T, lower=True)
             if st["estimate_trend"]:
-                u = linalg.solve_triangular(st["G"].T, st["Ft"].T.dot(rt) - 1.0, lower=True)
+                u = linalg.solve_triangular(st["G"].T, st["Ft"].T.dot(rt) - f.T, lower=True)
                 u2 = (u ** 2.0).sum(axis=0)
             else:
                 u2 = 0.0
@@ -384,15 +423,18 @@ def gradient_point(st, x):
     X, L = st["X"], st["L"]
     r = cross_corr(st["kind"], st["theta"], x.reshape(1, -1), X)
     r_dx = corr_dx(st, x).T  # (n, d)
-    y_dx = st["gamma"].T.dot(r_dx)  # beta^T f_dx == 0 for the constant trend (trend.py:86-88)
+    trend = st.get("trend", "constant")
+    f = trend_F(trend, x.reshape(1, -1)).reshape(-1, 1)
+    f_dx = trend_jacobian(trend, x.size)
+    y_dx = st["beta_vec"].T.dot(f_dx) + st["gamma"].T.dot(r_dx)     # gpr.py:539
     rt = linalg.solve_triangular(L, r.T, lower=True)
     rt_dx = linalg.solve_triangular(L, r_dx, lower=True)
     mse_dx = -rt.T.dot(rt_dx)
     if st["estimate_trend"]:
         Ft = st["Ft"]
-        u = Ft.T.dot(rt) - 1.0
-        u_dx = Ft.T.dot(rt_dx)
-        mse_dx = mse_dx + u.T.dot(1.0 / Ft.T.dot(Ft)).dot(u_dx)
+        u = Ft.T.dot(rt) - f
+        u_dx = Ft.T.dot(rt_dx) - f_dx
+        mse_dx = mse_dx + u.T.dot(linalg.inv(Ft.T.dot(Ft))).dot(u_dx)
     mse_dx = 2.0 * st["sigma2"] * mse_dx
     return y_dx.T, mse_dx.T
 
@@ -408,10 +450,12 @@ def gradient(st, Xs, chunk=512):
     X, L, kind = st["X"], st["L"], st["kind"]
     theta = _full_theta(st["theta"], d)
     ok = st["estimate_trend"]
+    trend = st.get("trend", "constant")
+    f_dx = trend_jacobian(trend, d)                                   # (p, d)
     if ok:
         Ft = st["Ft"]
-        a = linalg.solve_triangular(L.T, Ft, lower=False).ravel()
-        ftf = Ft.T.dot(Ft).item()
+        a = linalg.solve_triangular(L.T, Ft, lower=False)             # (n, p) = L^-T Ft
+        Ainv = linalg.inv(Ft.T.dot(Ft))
     mean_dx = np.empty((m, d))
     mse_dx = np.empty((m, d))
     for s in range(0, m, chunk):
@@ -430,11 +474,13 @@ def gradient(st, Xs, chunk=512):
             raise ValueError(kind)
         rt = linalg.solve_triangular(L, r.T, lower=True)  # (n, c)
         w = linalg.solve_triangular(L.T, rt, lower=False)  # (n, c)
-        mean_dx[s:s + chunk] = np.einsum("j,cji->ci", st["gamma"].ravel(), r_dx)
+        mean_dx[s:s + chunk] = np.einsum("j,cji->ci", st["gamma"].ravel(), r_dx) + \
+            st["beta_vec"].T.dot(f_dx)
         g = -np.einsum("jc,cji->ci", w, r_dx)
         if ok:
-            u = Ft.T.dot(rt).ravel() - 1.0
-            g = g + (u / ftf)[:, None] * np.einsum("j,cji->ci", a, r_dx)
+            u = Ft.T.dot(rt) - trend_F(trend, xs).T                   # (p, c)
+            kap = Ainv.dot(u)                                         # (p, c)
+            g = g + np.einsum("jc,cji->ci", a.dot(kap), r_dx) - kap.T.dot(f_dx)
         mse_dx[s:s + chunk] = 2.0 * st["sigma2"] * g
     return mean_dx, mse_dx
 

@@ -8,13 +8,14 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 FIXED = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "fixed_*.npz")))
 VARS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "var_*.npz")))
+LINS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "lin_*.npz")))
 FITS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "fit_*.npz")))
 
 
 def load(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     g = {k: z[k] for k in z.files}
-    for k in ("kind", "likelihood", "mode"):
+    for k in ("kind", "likelihood", "mode", "trend"):
         if k in g:
             g[k] = str(g[k])
     for k in ("estimate_trend",):
@@ -29,7 +30,14 @@ def mode_of(g):
 
 
 def beta_of(g):
-    return 0.0 if g["estimate_trend"] else float(g["beta_in"])
+    if g["estimate_trend"]:
+        return 0.0
+    b = np.asarray(g["beta_in"], dtype=np.float64)
+    return float(b) if b.ndim == 0 else b
+
+
+def trend_of(g):
+    return g.get("trend", "constant")
 
 
 def relerr(a, b, floor=0.0):

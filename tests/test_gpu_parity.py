@@ -512,3 +512,28 @@ def test_bo_shaped_loop():
         X = np.vstack([X, best_x])
         y = np.r_[y, fitness(best_x)]
     assert y.min() <= np.sort(y[:8])[0]
+
+
+def test_update_without_reoptimisation():
+    """update(X, y, reoptimize=False): same hyper-parameters, new data -> the model the oracle builds
+    for those hyper-parameters on the extended data (the refit between MLE rounds of a BO loop)."""
+    mb, O = _mods()
+    rng = np.random.default_rng(8)
+    d = 4
+    X = rng.uniform(-5, 5, (150, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    np.random.seed(8)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="matern", theta0=[0.1] * d,
+                            thetaL=[1e-4] * d, thetaU=[10.0] * d, nugget=1e-5, random_start=2)
+    gp.fit(X[:140], y[:140])
+    par = np.concatenate([np.ravel(v) for v in gp.par.values()])
+    gp.update(X, y, reoptimize=False)
+    assert gp.X.shape[0] == 150 and np.array_equal(np.concatenate([np.ravel(v) for v in gp.par.values()]), par)
+    st = O.fit_state(X, y, par, "matern", True, 0.0, "noisy", 1e-5)
+    Xs = rng.uniform(-5, 5, (500, d))
+    rm, rs = O.predict(st, Xs)
+    mean, mse = gp.predict(Xs, eval_MSE=True)
+    assert np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3)) < 1e-9
+    assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-7
+    gp.update(X, y)        # default: full refit, like the reference
+    assert gp.is_fitted and gp.X.shape[0] == 150

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import gp_oracle as O
-from golden_util import FIXED, FITS, VARS, load, mode_of, beta_of, likelihood_of, relerr
+from golden_util import FIXED, FITS, VARS, LINS, load, mode_of, beta_of, likelihood_of, trend_of, relerr
 
 # Same formulas, possibly different summation order than the reference: tolerances are
 # rounding-level on the well-conditioned (nugget) cases and looser on nugget-0 cases where the
@@ -113,24 +113,27 @@ def test_fit_state_reproduces_reference_fit(name):
 
 
 # ---- estimation-mode / likelihood variants (REML, estimated noise share) ---------------------
-@pytest.mark.parametrize("name", VARS)
+@pytest.mark.parametrize("name", VARS + LINS)
 def test_variant_likelihood_state_posterior(name):
     g = load(name)
     fn = O.log_likelihood_restricted if likelihood_of(g) == "restricted" else O.log_likelihood_concentrated
     llf, grad = fn(g["X"], g["y"], g["par"], g["kind"], g["estimate_trend"], beta_of(g), mode_of(g),
-                   float(g["nugget"]), eval_grad=True)
+                   float(g["nugget"]), eval_grad=True, trend=trend_of(g))
     ref = float(g["llf"])
     if np.isinf(ref):
         assert np.isinf(llf) and llf < 0
     else:
         assert abs(llf - ref) <= 1e-10 * abs(ref)
-    assert relerr(grad.ravel(), g["llf_grad"], floor=1e-6 * np.abs(g["llf_grad"]).max()) < 1e-8
+    if np.abs(g["llf_grad"]).max() == 0.0:       # rejected llf > 0: the concentrated form zeroes it
+        assert np.all(grad == 0.0)
+    else:
+        assert relerr(grad.ravel(), g["llf_grad"], floor=1e-6 * np.abs(g["llf_grad"]).max()) < 1e-8
     st = O.fit_state(g["X"], g["y"], g["par"], g["kind"], g["estimate_trend"], beta_of(g), mode_of(g),
-                     float(g["nugget"]), likelihood=likelihood_of(g))
+                     float(g["nugget"]), likelihood=likelihood_of(g), trend=trend_of(g))
     assert np.allclose(st["L"], g["L"], rtol=0, atol=1e-13)
     assert abs(st["sigma2"] - float(g["sigma2"])) <= 1e-12 * float(g["sigma2"])
     assert abs(st["noise_var"] - float(g["noise_var"])) <= 1e-12 * max(float(g["noise_var"]), 1e-300)
-    assert abs(st["beta"] - float(g["beta"])) <= 1e-9 * max(1.0, abs(float(g["beta"])))
+    assert np.max(np.abs(np.ravel(st["beta"]) - np.ravel(g["beta"]))) <= 1e-9 * max(1.0, np.abs(g["beta"]).max())
     assert np.max(np.abs(st["gamma"] - g["gamma"])) <= 1e-9 * np.abs(g["gamma"]).max()
     mean, mse = O.predict(st, g["Xs"])
     assert relerr(mean, g["mean"], floor=1e-3) < 1e-9
