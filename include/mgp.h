@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MGP_ABI_VERSION 2
+#define MGP_ABI_VERSION 3
 
 /* error codes */
 #define MGP_OK 0
@@ -49,6 +49,9 @@ extern "C" {
 /* trend (prior mean): mipego/GaussianProcess/trend.py:69-88 (constant_trend) */
 #define MGP_TREND_CONST_FIXED 0      /* beta given  -> simple kriging   (gpr.py:693-695) */
 #define MGP_TREND_CONST_ESTIMATED 1  /* beta = None -> ordinary kriging (gpr.py:686-692) */
+/* linear_trend f(x) = [1, x_1..x_d], p = d + 1 basis functions (trend.py:90-110) */
+#define MGP_TREND_LINEAR_FIXED 2      /* beta (p values) given */
+#define MGP_TREND_LINEAR_ESTIMATED 3  /* beta = None -> universal kriging */
 
 /* likelihood / estimation mode: gpr.py:246-251 */
 #define MGP_MODE_NOISELESS 0  /* par = theta             gpr.py:814-835 */
@@ -75,10 +78,11 @@ const char *mgp_last_error(const mgp_t *h);
 
 /* ---- training data: GaussianProcess._check_data, gpr.py:263-288 ------------------------
  * Uploads X (n x d) and y (n).  Returns MGP_EINVAL with "duplicate rows" if two rows of X
- * coincide (the reference raises Exception, gpr.py:275-277).  `beta0` is used only for
- * MGP_TREND_CONST_FIXED. */
+ * coincide (the reference raises Exception, gpr.py:275-277).  `beta`: the given trend
+ * coefficients for the *_FIXED trends (1 value for the constant trend, d + 1 for the linear one),
+ * ignored (may be NULL) otherwise. */
 int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int corr, int trend,
-                  double beta0);
+                  const double *beta);
 
 /* ---- batched marginal likelihood: GaussianProcess.log_likelihood_concentrated,
  * gpr.py:798-946 (with correlation_matrix :658-668, _compute_aux_var :676-697,
@@ -102,15 +106,18 @@ int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double no
 
 /* ---- state exchange (pickling; accepting an externally fitted model).
  * get: any out pointer may be NULL.  out_L: n x n row-major lower triangle (upper = 0);
- * out_theta: d; out_gamma, out_rho, out_Yt, out_Ft: n;
- * out_scalars[5] = {sigma2, beta, G, llf, noise_var}
+ * out_theta: d; out_gamma, out_rho, out_Yt: n; out_Ft: n x p row-major (p = 1 or d + 1);
+ * out_scalars[5] = {sigma2, beta_0, G, llf, noise_var} (G: constant trend only); all p trend
+ * coefficients are returned by mgp_get_trend
  * (Ft and G are meaningful only for MGP_TREND_CONST_ESTIMATED).
  * set: theta (d), L (n x n row-major, lower), gamma (n), sigma2, beta; everything else
  * (L^-1, Ft, G, packed operands) is rebuilt on the device.  Requires mgp_set_train first. */
 int mgp_get_state(mgp_t *h, double *out_theta, double *out_L, double *out_gamma, double *out_rho,
                   double *out_Yt, double *out_Ft, double *out_scalars);
 int mgp_set_state(mgp_t *h, const double *theta, const double *L, const double *gamma,
-                  double sigma2, double beta);
+                  double sigma2, const double *beta /* p values */);
+/* Trend coefficients beta (p values; mean.beta after compute_beta_gamma, gpr.py:670-674). */
+int mgp_get_trend(mgp_t *h, double *out_beta);
 
 /* ---- posterior: GaussianProcess.predict, gpr.py:392-483.  Xs: m x d.  out_mean: m.
  * out_mse: m or NULL.  MSE = |sigma2 (1 - |L^-1 r|^2 + u^2)| (gpr.py:471-474). */

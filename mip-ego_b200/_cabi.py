@@ -12,6 +12,7 @@ CORR = {"squared_exponential": 0, "matern": 1, "absolute_exponential": 2}
 ACQ = {"EI": 0, "PI": 1, "EpsilonPI": 1, "UCB": 2, "MGFI": 3}
 MODE = {"noiseless": 0, "noisy": 1, "noise_estim": 2}
 LIK_RESTRICTED = 16
+TREND = {("constant", False): 0, ("constant", True): 1, ("linear", False): 2, ("linear", True): 3}
 MAX_SETS = 16
 
 c_dp = ctypes.POINTER(ctypes.c_double)
@@ -25,11 +26,12 @@ SIGNATURES = {
     "mgp_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "mgp_destroy": (_i, [_vp]),
     "mgp_last_error": (ctypes.c_char_p, [_vp]),
-    "mgp_set_train": (_i, [_vp, _i, _i, c_dp, c_dp, _i, _i, _d]),
+    "mgp_set_train": (_i, [_vp, _i, _i, c_dp, c_dp, _i, _i, c_dp]),
     "mgp_nll_batch": (_i, [_vp, _i, c_dp, _i, _i, _d, _i, c_dp, c_dp, c_ip]),
     "mgp_finalize_fit": (_i, [_vp, c_dp, _i, _i, _d, c_dp]),
     "mgp_get_state": (_i, [_vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
-    "mgp_set_state": (_i, [_vp, c_dp, c_dp, c_dp, _d, _d]),
+    "mgp_set_state": (_i, [_vp, c_dp, c_dp, c_dp, _d, c_dp]),
+    "mgp_get_trend": (_i, [_vp, c_dp]),
     "mgp_predict": (_i, [_vp, _l, c_dp, c_dp, c_dp]),
     "mgp_gradient": (_i, [_vp, _l, c_dp, c_dp, c_dp]),
     "mgp_acq": (_i, [_vp, _l, c_dp, _i, _i, c_dp, _d, _i, c_dp, c_dp]),
@@ -65,7 +67,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mgp_abi_version() != 2:
+    if lib.mgp_abi_version() != 3:
         raise ImportError("libmgp_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -130,12 +130,13 @@ int mgp_destroy(mgp_t *h) {
   if (!h) return MGP_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf *all[] = {&h->dXc, &h->dy, &h->dcenter, &h->dtheta, &h->dBop, &h->dan, &h->dL, &h->dMinv,
+  DevBuf *all[] = {&h->dtpart, &h->dXc, &h->dy, &h->dcenter, &h->dtheta, &h->dBop, &h->dan, &h->dL, &h->dMinv,
                    &h->dTmp, &h->dLinvDiag, &h->dMp, &h->dRinvP, &h->dgamma, &h->davec, &h->dFt,
                    &h->dYt, &h->drho, &h->dscal, &h->drP, &h->dmeanpart, &h->dftpart, &h->dqpart,
                    &h->dwP, &h->dXs_stage[0], &h->dXs_stage[1], &h->dout_stage[0],
                    &h->dout_stage[1], &h->dtopk_val, &h->dtopk_idx, &h->dtopk_blk, &h->nR, &h->nL, &h->nM, &h->nT,
-                   &h->nLinvDiag, &h->nvec, &h->nscal, &h->npar, &h->ngpart};
+                   &h->nLinvDiag, &h->nvec, &h->nscal, &h->npar, &h->ngpart, &h->nFtm, &h->nBhat, &h->ntws,
+                   &h->dF, &h->dmu, &h->dbetav, &h->dBhat, &h->dCinv, &h->dFtm};
   for (DevBuf *b : all) freebuf(*b);
   for (int i = 0; i < 2; i++) {
     if (h->hpin[i]) cudaFreeHost(h->hpin[i]);
@@ -205,18 +206,27 @@ int64_t mgp_get_counter(const mgp_t *h, const char *name) {
 // training data
 // ---------------------------------------------------------------------------------------------
 int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int corr, int trend,
-                  double beta0) {
+                  const double *beta) {
   CHECK_H(h);
   if (n < 1 || d < 1 || !X || !y) return mgp_fail(h, MGP_EINVAL, "bad training data");
   if (d > MGP_MAX_D) return mgp_fail(h, MGP_EINVAL, "d = %d > %d unsupported", d, MGP_MAX_D);
   if (corr != MGP_CORR_SE && corr != MGP_CORR_MATERN32 && corr != MGP_CORR_ABSEXP)
     return mgp_fail(h, MGP_EINVAL, "correlation type %d not supported by the CUDA path", corr);
-  if (trend != MGP_TREND_CONST_FIXED && trend != MGP_TREND_CONST_ESTIMATED)
+  if (trend < MGP_TREND_CONST_FIXED || trend > MGP_TREND_LINEAR_ESTIMATED)
     return mgp_fail(h, MGP_EINVAL, "trend type %d unknown", trend);
+  const bool linear = trend >= MGP_TREND_LINEAR_FIXED;
+  const bool est = trend == MGP_TREND_CONST_ESTIMATED || trend == MGP_TREND_LINEAR_ESTIMATED;
+  const int p = linear ? d + 1 : 1;
+  if (!est && !beta) return mgp_fail(h, MGP_EINVAL, "a trend with given coefficients needs beta");
+  if (est && n <= p) return mgp_fail(h, MGP_EINVAL, "n = %d samples cannot determine %d trend coefficients", n, p);
   h->fitted = false;
   h->rinv_ready = false;
   h->nll_cap = 0;  // workspaces are re-validated against the new padded size
-  h->n = n; h->d = d; h->corr = corr; h->trend = trend; h->beta0 = beta0;
+  h->n = n; h->d = d; h->corr = corr; h->trend = trend;
+  h->p = p; h->trend_est = est;
+  h->beta_in.assign(p, 0.0);
+  if (!est) h->beta_in.assign(beta, beta + p);
+  h->beta0 = (!est && !linear) ? beta[0] : 0.0;
   h->npad = (int)round_up(n, MGP_TILE);
   h->dpad = (int)round_up(d, 4);
   h->NI = h->npad / MGP_TILE;
@@ -253,6 +263,40 @@ int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int 
     h->n = 0;
     return mgp_fail(h, MGP_EINVAL, "duplicate rows: Multiple input features cannot have the same target value.");
   }
+  // non-constant trends: the basis matrix F (coefficients estimated) or the mean vector F beta
+  if (linear) {
+    MGP_TRY(mgp_ensure(h, h->dbetav, MGP_PMAX * 8));
+    if (est) {
+      MGP_TRY(mgp_ensure(h, h->dF, (size_t)h->npad * MGP_TP * 8));
+      MGP_CUDA(h, launch_trend_basis(P<double>(h->dXc), P<double>(h->dcenter), n, h->npad, d, h->dpad,
+                                     P<double>(h->dF), h->stream));
+      // log det(F^T F) (REML, gpr.py:736) with the same normal-equation kernel, on F itself
+      MGP_TRY(mgp_ensure(h, h->ntws, trend_ws_doubles() * 8));
+      MGP_TRY(mgp_ensure(h, h->dmu, (size_t)h->npad * 8));
+      double *sc = P<double>(h->dscal) + 16;
+      int *stflag = reinterpret_cast<int *>(P<double>(h->dscal) + 8);
+      MGP_CUDA(h, cudaMemsetAsync(stflag, 0, sizeof(int), h->stream));
+      MGP_CUDA(h, launch_trend_solve(P<double>(h->dF), P<double>(h->dy), P<double>(h->dmu), n, h->npad, p,
+                                     P<double>(h->ntws), sc, stflag, 1, h->stream));
+      double ld = 0.0;
+      int bad = 0;
+      MGP_CUDA(h, cudaMemcpyAsync(&ld, sc + NLL_LOGDETA, 8, cudaMemcpyDeviceToHost, h->stream));
+      MGP_CUDA(h, cudaMemcpyAsync(&bad, stflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      MGP_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (bad) { h->n = 0; return mgp_fail(h, MGP_EINVAL, "the trend basis F is rank deficient"); }
+      h->logdetFF = ld;
+      h->launches += 2;
+    } else {
+      MGP_TRY(mgp_ensure(h, h->dmu, (size_t)h->npad * 8));
+      std::vector<double> bp(MGP_PMAX, 0.0);
+      for (int i = 0; i < p; i++) bp[i] = h->beta_in[i];
+      MGP_CUDA(h, cudaMemcpyAsync(h->dbetav.p, bp.data(), MGP_PMAX * 8, cudaMemcpyHostToDevice, h->stream));
+      MGP_CUDA(h, launch_trend_mu(P<double>(h->dXc), P<double>(h->dcenter), n, h->npad, d, h->dpad,
+                                  P<double>(h->dbetav), P<double>(h->dmu), h->stream));
+      MGP_CUDA(h, cudaStreamSynchronize(h->stream));   // bp is a host temporary
+      h->launches++;
+    }
+  }
   return MGP_OK;
 }
 
@@ -271,6 +315,11 @@ static int nll_alloc(mgp_handle *h, int B) {
   MGP_TRY(mgp_ensure(h, h->nvec, (size_t)5 * B * h->npad * 8));
   MGP_TRY(mgp_ensure(h, h->nscal, (size_t)B * nll_scal_doubles() * 8 + (size_t)B * sizeof(int) + 64));
   MGP_TRY(mgp_ensure(h, h->ngpart, (size_t)B * ntiles * (h->dpad + 2) * 8));
+  if (h->p > 1 && h->trend_est) {
+    MGP_TRY(mgp_ensure(h, h->nFtm, (size_t)B * h->npad * MGP_TP * 8));
+    MGP_TRY(mgp_ensure(h, h->nBhat, (size_t)B * h->npad * MGP_TP * 8));
+    MGP_TRY(mgp_ensure(h, h->ntws, (size_t)B * trend_ws_doubles() * 8));
+  }
   h->nll_cap = B;
   return 0;
 }
@@ -320,6 +369,16 @@ static void fill_work(mgp_handle *h, NllWork &w, int b_off, int B, int cap, int 
   w.status = nll_status_ptr(h, cap) + b_off;
   w.out_llf = d_llf; w.out_grad = d_grad;
   w.la = nullptr;
+  w.p = h->p;
+  w.ordinary = h->trend_est;
+  w.mu = (h->p > 1 && !h->trend_est) ? P<double>(h->dmu) : nullptr;
+  if (h->p > 1 && h->trend_est) {
+    w.F = P<double>(h->dF);
+    w.Ftm = P<double>(h->nFtm) + (size_t)b_off * h->npad * MGP_TP;
+    w.Bhat = P<double>(h->nBhat) + (size_t)b_off * h->npad * MGP_TP;
+    w.tws = P<double>(h->ntws) + (size_t)b_off * trend_ws_doubles();
+    w.logdetFF = h->logdetFF;
+  }
 }
 
 // Number of concurrent batch groups: the factorisation of one group has long phases that occupy
@@ -432,6 +491,28 @@ static int adopt_slot0(mgp_handle *h, const double *theta_host, bool take_gamma)
   // a = L^-T Ft  (so that Ft^T L^-1 r = a . r)
   MGP_CUDA(h, launch_trmv(P<double>(h->dMinv), h->npad, 0, P<double>(h->dFt), 0, P<double>(h->davec), 0,
                           h->n, 1, 1, st));
+  if (h->p > 1) {
+    MGP_TRY(mgp_ensure(h, h->dbetav, MGP_PMAX * 8));
+    if (h->trend_est) {
+      const size_t tb = (size_t)h->npad * MGP_TP * 8;
+      MGP_TRY(mgp_ensure(h, h->dBhat, tb));
+      MGP_TRY(mgp_ensure(h, h->dFtm, tb));
+      MGP_TRY(mgp_ensure(h, h->dCinv, (size_t)MGP_PMAX * MGP_PMAX * 8));
+      const double *tw = P<double>(h->ntws);
+      MGP_CUDA(h, cudaMemcpyAsync(h->dBhat.p, h->nBhat.p, tb, cudaMemcpyDeviceToDevice, st));
+      MGP_CUDA(h, cudaMemcpyAsync(h->dFtm.p, h->nFtm.p, tb, cudaMemcpyDeviceToDevice, st));
+      MGP_CUDA(h, cudaMemcpyAsync(h->dCinv.p, tw + TWS_CINV, (size_t)MGP_PMAX * MGP_PMAX * 8, cudaMemcpyDeviceToDevice, st));
+      if (take_gamma) {   // coefficients estimated by this run (not adopted from outside)
+        MGP_CUDA(h, cudaMemcpyAsync(h->dbetav.p, tw + TWS_BETA, MGP_PMAX * 8, cudaMemcpyDeviceToDevice, st));
+        h->hbeta.assign(MGP_PMAX, 0.0);
+        MGP_CUDA(h, cudaMemcpyAsync(h->hbeta.data(), tw + TWS_BETA, MGP_PMAX * 8, cudaMemcpyDeviceToHost, st));
+      }
+    } else {
+      h->hbeta = h->beta_in;
+      h->hbeta.resize(MGP_PMAX, 0.0);
+      MGP_CUDA(h, cudaMemcpyAsync(h->dbetav.p, h->hbeta.data(), MGP_PMAX * 8, cudaMemcpyHostToDevice, st));
+    }
+  }
   std::vector<double> th(h->dpad, 0.0);
   for (int i = 0; i < h->d; i++) th[i] = theta_host[i];
   MGP_CUDA(h, cudaMemcpyAsync(h->dtheta.p, th.data(), th.size() * 8, cudaMemcpyHostToDevice, st));
@@ -456,6 +537,7 @@ int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double no
   MGP_CUDA(h, cudaMemcpyAsync(h->npar.p, par, (size_t)n_par * 8, cudaMemcpyHostToDevice, st));
   NllWork w;
   fill_work(h, w, 0, 1, h->nll_cap, n_par, mode, noise_var, 0, P<double>(h->npar), nullptr, nullptr);
+  w.want_bhat = 1;
   MGP_CUDA(h, nll_pipeline(w, st, &h->launches));
   std::vector<double> sc(nll_scal_doubles());
   int status = 0;
@@ -479,11 +561,21 @@ int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double no
   return MGP_OK;
 }
 
+int mgp_get_trend(mgp_t *h, double *out_beta) {
+  CHECK_H(h);
+  if (!h->fitted) return mgp_fail(h, MGP_ESTATE, "model is not fitted");
+  if (!out_beta) return mgp_fail(h, MGP_EINVAL, "out_beta is NULL");
+  if (h->p == 1) { out_beta[0] = h->beta; return MGP_OK; }
+  MGP_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < h->p; i++) out_beta[i] = h->hbeta[i];
+  return MGP_OK;
+}
+
 int mgp_set_state(mgp_t *h, const double *theta, const double *L, const double *gamma,
-                  double sigma2, double beta) {
+                  double sigma2, const double *beta) {
   CHECK_H(h);
   if (h->n == 0) return mgp_fail(h, MGP_ESTATE, "mgp_set_train must be called first");
-  if (!theta || !L || !gamma) return mgp_fail(h, MGP_EINVAL, "NULL state array");
+  if (!theta || !L || !gamma || !beta) return mgp_fail(h, MGP_EINVAL, "NULL state array");
   MGP_TRY(model_alloc(h));
   if (h->nll_cap < 1) MGP_TRY(nll_alloc(h, 1));
   cudaStream_t st = h->stream;
@@ -502,16 +594,23 @@ int mgp_set_state(mgp_t *h, const double *theta, const double *L, const double *
   NllWork w;
   fill_work(h, w, 0, 1, h->nll_cap, h->d, MGP_MODE_NOISELESS, 0.0, 0, P<double>(h->npar), nullptr, nullptr);
   w.have_L = 1;
+  w.want_bhat = 1;
   MGP_CUDA(h, nll_pipeline(w, st, &h->launches));
   std::vector<double> sc(nll_scal_doubles());
   MGP_CUDA(h, cudaMemcpyAsync(sc.data(), w.scal, sc.size() * 8, cudaMemcpyDeviceToHost, st));
   MGP_CUDA(h, cudaStreamSynchronize(st));
   h->sigma2 = sigma2;
-  h->beta = beta;
+  h->beta = beta[0];
   h->ftf = sc[NLL_FTF];
   h->G = -sqrt(sc[NLL_FTF]);
   h->llf = NAN;
   MGP_TRY(adopt_slot0(h, theta, false));
+  if (h->p > 1) {   // the coefficients travel with the state (they are what the sender fitted)
+    h->hbeta.assign(MGP_PMAX, 0.0);
+    for (int i = 0; i < h->p; i++) h->hbeta[i] = beta[i];
+    MGP_CUDA(h, cudaMemcpyAsync(h->dbetav.p, h->hbeta.data(), MGP_PMAX * 8, cudaMemcpyHostToDevice, st));
+    MGP_CUDA(h, cudaStreamSynchronize(st));
+  }
   h->fitted = true;
   return MGP_OK;
 }
@@ -529,7 +628,13 @@ int mgp_get_state(mgp_t *h, double *out_theta, double *out_L, double *out_gamma,
   if (out_gamma) MGP_CUDA(h, cudaMemcpyAsync(out_gamma, h->dgamma.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   if (out_rho) MGP_CUDA(h, cudaMemcpyAsync(out_rho, h->drho.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   if (out_Yt) MGP_CUDA(h, cudaMemcpyAsync(out_Yt, h->dYt.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  if (out_Ft) MGP_CUDA(h, cudaMemcpyAsync(out_Ft, h->dFt.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (out_Ft) {
+    if (h->p > 1 && h->trend_est)
+      MGP_CUDA(h, cudaMemcpy2DAsync(out_Ft, (size_t)h->p * 8, h->dFtm.p, (size_t)MGP_TP * 8, (size_t)h->p * 8, n,
+                                    cudaMemcpyDeviceToHost, st));
+    else
+      MGP_CUDA(h, cudaMemcpyAsync(out_Ft, h->dFt.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  }
   MGP_CUDA(h, cudaStreamSynchronize(st));
   if (out_scalars) {
     out_scalars[0] = h->sigma2; out_scalars[1] = h->beta; out_scalars[2] = h->G; out_scalars[3] = h->llf;
@@ -567,6 +672,8 @@ static int post_workspace(mgp_handle *h, bool want_dx) {
   MGP_TRY(mgp_ensure(h, h->dftpart, (size_t)h->NI * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dqpart, (size_t)h->NI * chunk * 8));
   if (want_dx) MGP_TRY(mgp_ensure(h, h->dwP, (size_t)h->npad * chunk * 8));
+  if (h->p > 1 && h->trend_est)
+    MGP_TRY(mgp_ensure(h, h->dtpart, (size_t)h->NI * rgen_trend_cols(h->dpad) * chunk * 8));
   return 0;
 }
 
@@ -596,7 +703,11 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
   MGP_TRY(post_workspace(h, q.want_dx));
   if (q.want_dx) MGP_TRY(ensure_rinv(h, st));
   const int NJ8 = h->npad / 8;
-  const bool ordinary = h->trend == MGP_TREND_CONST_ESTIMATED;
+  const bool ordinary = h->trend_est;
+  const bool gen = h->p > 1 && h->trend_est;
+  const int PT = rgen_trend_cols(h->dpad);
+  if (gen && h->corr == MGP_CORR_ABSEXP)
+    return mgp_fail(h, MGP_EINVAL, "an estimated linear trend with the absolute-exponential kernel is not implemented");
   double *chunk_val = nullptr;
   int64_t *blk_idx = nullptr;
   const bool top1 = q.topk == 1 && !q.want_dx;   // per-block arg-max fused into the epilogue
@@ -620,6 +731,8 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     rp.center = P<double>(h->dcenter); rp.theta = P<double>(h->dtheta); rp.Bop = P<double>(h->dBop);
     rp.an = P<double>(h->dan); rp.gamma = P<double>(h->dgamma); rp.avec = P<double>(h->davec);
     rp.Xc = P<double>(h->dXc);
+    rp.Bhat = gen ? P<double>(h->dBhat) : nullptr;
+    rp.tpart = gen ? P<double>(h->dtpart) : nullptr;
     rp.rP = P<double>(h->drP); rp.meanpart = P<double>(h->dmeanpart); rp.ftpart = P<double>(h->dftpart);
     rp.ldp = ldp;
     { KTimer t(h, st, 0); MGP_CUDA(h, launch_rgen(rp, h->corr, h->sm_count, st)); }
@@ -633,6 +746,9 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       ep.qpart = P<double>(h->dqpart); ep.meanpart = P<double>(h->dmeanpart); ep.ftpart = P<double>(h->dftpart);
       ep.NI = h->NI; ep.JS = JS; ep.ld = ldp; ep.mc = mc;
       ep.beta = h->beta; ep.sigma2 = h->sigma2; ep.G = h->G; ep.ordinary = ordinary;
+      ep.p = h->p; ep.PT = PT; ep.d = h->d; ep.trend_est = h->trend_est ? 1 : 0;
+      ep.Xs = q.d_Xs + c0 * h->d; ep.betav = P<double>(h->dbetav); ep.Cinv = P<double>(h->dCinv);
+      ep.tpart = P<double>(h->dtpart);
       ep.out_mean = q.d_mean ? q.d_mean + c0 : nullptr;
       ep.out_mse = q.d_mse ? q.d_mse + c0 : nullptr;
       ep.out_val = nullptr; ep.ld_val = 0;
@@ -656,6 +772,9 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       gp.rP = P<double>(h->drP); gp.wP = P<double>(h->dwP);
       gp.meanpart = P<double>(h->dmeanpart); gp.ftpart = P<double>(h->dftpart); gp.JS = JS;
       gp.beta = h->beta; gp.sigma2 = h->sigma2; gp.G = h->G; gp.ftf = h->ftf; gp.ordinary = ordinary;
+      gp.p = h->p; gp.PT = PT; gp.trend_est = h->trend_est ? 1 : 0;
+      gp.betav = P<double>(h->dbetav); gp.Cinv = P<double>(h->dCinv); gp.tpart = P<double>(h->dtpart);
+      gp.Bhat = P<double>(h->dBhat);
       gp.out_mean = q.d_mean ? q.d_mean + c0 : nullptr;
       gp.out_mse = q.d_mse ? q.d_mse + c0 : nullptr;
       gp.out_mean_dx = q.d_mean_dx ? q.d_mean_dx + c0 * h->d : nullptr;

@@ -569,7 +569,10 @@ static int *sched_words(cudaStream_t st) {
   if (it != table.end()) return it->second;
   int *p = nullptr;
   if (cudaMalloc(&p, 2 * sizeof(int)) != cudaSuccess) return nullptr;
-  cudaMemset(p, 0, 2 * sizeof(int));   // synchronous: visible before any later launch
+  // Zero the words ON THE STREAM that will use them: cudaMemset on device memory is asynchronous
+  // (legacy stream) and is not ordered against work on a non-blocking stream -- recycled memory
+  // would otherwise hand the first kernel a stale tile counter.
+  if (cudaMemsetAsync(p, 0, 2 * sizeof(int), st) != cudaSuccess) { cudaFree(p); return nullptr; }
   table[key] = p;
   return p;
 }

@@ -40,6 +40,17 @@ struct mgp_handle {
   int n = 0, d = 0, npad = 0, dpad = 0, NI = 0;
   int corr = 0, trend = 0;
   double beta0 = 0.0;
+  int p = 1;                    // basis functions of the trend (1 constant, d + 1 linear)
+  bool trend_est = false;       // coefficients estimated (ordinary / universal kriging)
+  std::vector<double> beta_in;  // given coefficients (p), *_FIXED trends
+  std::vector<double> hbeta;    // fitted / adopted coefficients (p)
+  double logdetFF = 0.0;        // log det(F^T F), REML
+  DevBuf dF;       // npad x MGP_TP basis matrix (p > 1, estimated)
+  DevBuf dmu;      // npad: F beta (linear trend with given beta)
+  DevBuf dbetav;   // MGP_PMAX: trend coefficients on the device
+  DevBuf dBhat;    // npad x MGP_TP: L^-T (Ft C^-T)  (p > 1, estimated)
+  DevBuf dCinv;    // MGP_PMAX x MGP_PMAX: C^-1, C = chol(Ft^T Ft)
+  DevBuf dFtm;     // npad x MGP_TP: Ft = L^-1 F (state exchange)
   std::vector<double> hX, hy;   // host copies (state exchange, duplicate check)
   DevBuf dXc;      // npad x dpad, centred, zero padded
   DevBuf dy;       // npad
@@ -63,7 +74,7 @@ struct mgp_handle {
   // ---- posterior workspace ---------------------------------------------------------------
   int64_t chunk = 0;       // candidates per pass (multiple of 128)
   int64_t chunk_opt = 0;   // user override
-  DevBuf drP, dmeanpart, dftpart, dqpart, dwP;
+  DevBuf drP, dmeanpart, dftpart, dqpart, dwP, dtpart;
   DevBuf dXs_stage[2], dout_stage[2];
   DevBuf dtopk_val, dtopk_idx, dtopk_blk;
   void *hpin[2] = {nullptr, nullptr};
@@ -75,6 +86,7 @@ struct mgp_handle {
   cudaStream_t nll_stream[MGP_NLL_STREAMS] = {};  // batch groups
   cudaEvent_t ev_fork = nullptr, ev_join[MGP_NLL_STREAMS] = {};
   DevBuf nR, nL, nM, nT, nLinvDiag, nvec, nscal, npar, ngpart;
+  DevBuf nFtm, nBhat, ntws;   // general-trend workspaces (allocated when p > 1)
 };
 
 int mgp_fail(mgp_handle *h, int code, const char *fmt, ...);

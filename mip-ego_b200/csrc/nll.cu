@@ -22,7 +22,11 @@ constexpr int XP = 132;  // padded row length of the transposed X tile in shared
 
 // scal layout per batch element (doubles)
 enum { SC_SIGMA2 = 0, SC_LLF, SC_FTF, SC_FTY, SC_RR, SC_LOGDET, SC_S, SC_V, SC_BETA, SC_NV, SC_COEFA,
-       SC_THSCALE, SC_N };
+       SC_THSCALE, SC_LOGDETA, SC_N };
+
+// trend workspace layout per batch element
+enum { TW_BETA = 0, TW_AINV = MGP_PMAX, TW_C = MGP_PMAX + MGP_PMAX * MGP_PMAX,
+       TW_CINV = MGP_PMAX + 2 * MGP_PMAX * MGP_PMAX, TW_N = MGP_PMAX + 3 * MGP_PMAX * MGP_PMAX };
 
 // mode = estimation mode | MGP_LIK_RESTRICTED.  Every mode factors
 //   R = c R0 + (1 - c) I,   c = 1 | sigma2 / (sigma2 + noise_var) | alpha      (gpr.py:721-724, 838-839, 861-865)
@@ -106,34 +110,45 @@ __device__ double block_sum(double v, double *red) {
 }
 
 // One CTA per batch element: Ft/Yt inner products, rho, sigma2-hat, log det, llf.
+// p == 1: Ft is the vector L^-1 1 (or L^-1 mu for a given non-constant mean, then beta0 = 1);
+// p > 1: rho, rr, beta and log det(Ft^T Ft) were produced by k_trend_solve (scal slots).
 __global__ void __launch_bounds__(256) k_nll_scalars(const double *L, int npad, int64_t sL, int n,
                                                      const double *Yt, const double *Ft,
                                                      double *rho, int64_t sv, const double *params,
                                                      int n_par, int mode, double noise_var,
-                                                     int ordinary, double beta0, double *scal,
-                                                     int *status, double *out_llf) {
+                                                     int ordinary, double beta0, int p, double logdetFF,
+                                                     double *scal, int *status, double *out_llf) {
   __shared__ double red[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   const double *yt = Yt + b * sv, *ft = Ft + b * sv;
   double *rh = rho + b * sv;
   double a = 0.0, c = 0.0, ld = 0.0;
   for (int j = tid; j < n; j += 256) {
-    a = fma(ft[j], ft[j], a);
-    c = fma(ft[j], yt[j], c);
+    if (p == 1) {
+      a = fma(ft[j], ft[j], a);
+      c = fma(ft[j], yt[j], c);
+    }
     ld += log(L[b * sL + (int64_t)j * (npad + 1)]);
   }
-  const double ftf = block_sum(a, red);
+  double ftf = block_sum(a, red);
   const double fty = block_sum(c, red);
   const double logdet = block_sum(ld, red);
-  // ordinary: rho = Yt - Q Q^T Yt with Q = Ft/|Ft| (gpr.py:691-692); simple: Yt - L^-1 (beta 1)
-  const double coef = ordinary ? fty / ftf : beta0;
   double rr = 0.0;
-  for (int j = tid; j < npad; j += 256) {
-    const double r = j < n ? yt[j] - coef * ft[j] : 0.0;
-    rh[j] = r;
-    rr = fma(r, r, rr);
+  if (p == 1) {
+    // ordinary: rho = Yt - Q Q^T Yt with Q = Ft/|Ft| (gpr.py:691-692); simple: Yt - L^-1 (beta 1)
+    const double coef = ordinary ? fty / ftf : beta0;
+    for (int j = tid; j < npad; j += 256) {
+      const double r = j < n ? yt[j] - coef * ft[j] : 0.0;
+      rh[j] = r;
+      rr = fma(r, r, rr);
+    }
+    rr = block_sum(rr, red);
+  } else {
+    rr = scal[(int64_t)b * SC_N + SC_RR];
+    ftf = exp(scal[(int64_t)b * SC_N + SC_LOGDETA]);   // det(Ft^T Ft) = prod diag(G)^2
   }
-  rr = block_sum(rr, red);
+  const double logdetFtF = p == 1 ? log(ftf) : scal[(int64_t)b * SC_N + SC_LOGDETA];
+  const double logdetF = p == 1 ? log((double)n) : logdetFF;
   if (tid == 0) {
     const ModePar mp = mode_params(mode, params + (int64_t)b * n_par, n_par, noise_var);
     const int est = mode & 15;
@@ -145,13 +160,13 @@ __global__ void __launch_bounds__(256) k_nll_scalars(const double *L, int npad, 
       // carries the reference's minus sign on the log-determinant.
       sigma2 = mp.sigma2; nv = mp.nv; v = sigma2 + nv; s = v;
       if (ordinary) {
-        llf = -0.5 * ((n - 1) * log(two_pi * v) - log((double)n) + 2.0 * logdet + log(ftf) + rr / v);
-        coefa = v / ftf;     // v q q^T with q = L^-T Ft / G  (gpr.py:754-755)
+        llf = -0.5 * ((n - p) * log(two_pi * v) - logdetF + 2.0 * logdet + logdetFtF + rr / v);
+        coefa = p == 1 ? v / ftf : v;   // v q q^T with q = L^-T Q  (gpr.py:754-755); p > 1: Bhat holds L^-T Q
       } else {
         llf = -0.5 * (n * log(two_pi * v) - 2.0 * logdet + rr / v);
       }
     } else if (est == MGP_MODE_NOISELESS) {
-      const int k = ordinary ? 1 : 0;
+      const int k = ordinary ? p : 0;                                   // rank(Q Q^T) = p, gpr.py:829-832
       sigma2 = rr / (double)(n - k);                                    // gpr.py:833
       llf = -0.5 * (n * log(two_pi * sigma2) + 2.0 * logdet + n);       // gpr.py:834-835
       s = sigma2;
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(256) k_nll_scalars(const double *L, int npad, 
     double *sc = scal + (int64_t)b * SC_N;
     sc[SC_SIGMA2] = sigma2; sc[SC_LLF] = llf; sc[SC_FTF] = ftf; sc[SC_FTY] = fty;
     sc[SC_RR] = rr; sc[SC_LOGDET] = logdet; sc[SC_S] = s; sc[SC_V] = v;
-    sc[SC_BETA] = ordinary ? fty / ftf : beta0;   // beta = G^-1 Q^T Yt  (gpr.py:673)
+    if (p == 1) sc[SC_BETA] = ordinary ? fty / ftf : beta0;   // beta = G^-1 Q^T Yt  (gpr.py:673)
     sc[SC_NV] = nv; sc[SC_COEFA] = coefa; sc[SC_THSCALE] = thscale;
     if (out_llf) out_llf[b] = llf;
   }
@@ -187,6 +202,7 @@ __global__ void __launch_bounds__(256) k_nll_grad(const double *Xc, int n, int n
                                                   const double *params, int n_par, int mode,
                                                   const double *Rinv, int64_t sR,
                                                   const double *gamma, const double *avec, int64_t sv,
+                                                  const double *Bhat, int p,
                                                   const double *scal, double *gpart, int ntiles) {
   extern __shared__ double sm[];
   double *xjT = sm;
@@ -223,7 +239,16 @@ __global__ void __launch_bounds__(256) k_nll_grad(const double *Xc, int n, int n
     if (gj >= n || gk >= n || gj < gk) continue;
     const double rinv = Rb[(int64_t)gj * npad + gk];
     double W = gm[gj] * gk_v / s_div - rinv;
-    if (coefa != 0.0) W = fma(av[gj], ak_v, W);
+    if (coefa != 0.0) {
+      if (p == 1) {
+        W = fma(av[gj], ak_v, W);
+      } else {   // v (L^-T Q)(L^-T Q)^T: a p-term dot product per pair
+        const double *bj_ = Bhat + ((int64_t)b * npad + gj) * MGP_TP, *bk_ = Bhat + ((int64_t)b * npad + gk) * MGP_TP;
+        double t = 0.0;
+        for (int q = 0; q < p; q++) t = fma(bj_[q], bk_[q], t);
+        W = fma(coefa, t, W);
+      }
+    }
     if (gj == gk) {
       acc[DP + 1] += W;  // R0_jj = 1: sigma2 / noise-variance derivatives only
       continue;
@@ -298,6 +323,205 @@ __global__ void k_nll_grad_final(const double *gpart, int ntiles, int dp2, int n
   out_grad[(int64_t)b * n_par + i] = g;
 }
 
+// ---- general basis trend -------------------------------------------------------------------------
+__global__ void k_trend_mu(const double *Xc, const double *center, int n, int npad, int d, int dpad,
+                           const double *beta, double *mu) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npad) return;
+  double s = 0.0;
+  if (j < n) {
+    s = beta[0];
+    for (int i = 0; i < d; i++) s = fma(beta[1 + i], Xc[(int64_t)j * dpad + i] + center[i], s);
+  }
+  mu[j] = s;
+}
+__global__ void k_trend_basis(const double *Xc, const double *center, int n, int npad, int d, int dpad,
+                              double *F) {
+  const int j = blockIdx.x, c = threadIdx.x;   // one row per block, MGP_TP threads
+  double v = 0.0;
+  if (j < n) {
+    if (c == 0) v = 1.0;
+    else if (c <= d) v = Xc[(int64_t)j * dpad + c - 1] + center[c - 1];
+  }
+  F[(int64_t)j * MGP_TP + c] = v;
+}
+
+// G = [Ft | y]^T [Ft | y] restricted to what is needed: thread groups of S lanes share one (i, j)
+// pair and split the rows; fixed reduction order (shuffles over the S lanes).
+__device__ void trend_gram(const double *Ft, const double *yv, int n, int p, double *Asm /*[PMAX][PMAX+1]*/,
+                           double *bsm /*[PMAX]*/, int tid, int nthreads) {
+  const int npairs = p * (p + 1) / 2 + p;     // lower pairs of A, then b
+  int S = 32;
+  while (S > 1 && npairs * S > nthreads) S >>= 1;
+  const int groups = nthreads / S;
+  const int g = tid / S, sl = tid % S;
+  for (int pr = g; pr < (npairs + groups - 1) / groups * groups; pr += groups) {
+    int i = 0, j = 0;
+    bool isb = false;
+    if (pr < p * (p + 1) / 2) {
+      while ((i + 1) * (i + 2) / 2 <= pr) i++;
+      j = pr - i * (i + 1) / 2;
+    } else if (pr < npairs) {
+      isb = true;
+      i = pr - p * (p + 1) / 2;
+    }
+    double acc = 0.0;
+    if (pr < npairs) {
+      for (int r = sl; r < n; r += S) {
+        const double a = Ft[(int64_t)r * MGP_TP + i];
+        const double c = isb ? yv[r] : Ft[(int64_t)r * MGP_TP + j];
+        acc = fma(a, c, acc);
+      }
+    }
+    for (int o = S >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (sl == 0 && pr < npairs) {
+      if (isb) bsm[i] = acc;
+      else { Asm[i * (MGP_PMAX + 1) + j] = acc; Asm[j * (MGP_PMAX + 1) + i] = acc; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_trend_solve(const double *Ftm, const double *Yt, double *rho,
+                                                      int n, int npad, int p, double *tws, double *scal,
+                                                      int *status) {
+  extern __shared__ double sm[];
+  constexpr int LD = MGP_PMAX + 1;
+  double *A = sm;                    // [PMAX][LD]  Gram matrix, overwritten by its Cholesky factor C
+  double *Ci = A + MGP_PMAX * LD;    // [PMAX][LD]  C^-1
+  double *bv = Ci + MGP_PMAX * LD;   // [PMAX]
+  double *beta = bv + MGP_PMAX;      // [PMAX]
+  double *red = beta + MGP_PMAX;     // [32]
+  __shared__ int bad;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double *Ft = Ftm + (int64_t)b * npad * MGP_TP;
+  const double *yt = Yt + (int64_t)b * npad;
+  double *rh = rho + (int64_t)b * npad;
+  double *tw = tws + (int64_t)b * TW_N;
+  if (tid == 0) bad = 0;
+  trend_gram(Ft, yt, n, p, A, bv, tid, 1024);
+  __syncthreads();
+  // Cholesky A = C C^T by one warp (column by column), then C^-1 by forward substitution
+  if (warp == 0) {
+    for (int j = 0; j < p; j++) {
+      const double djj = A[j * LD + j];
+      if (!(djj > 0.0) && lane == 0) bad = 1;
+      const double inv = rsqrt(djj);
+      __syncwarp();
+      for (int i = j + lane; i < p; i += 32) A[i * LD + j] = (i == j) ? djj * inv : A[i * LD + j] * inv;
+      __syncwarp();
+      for (int i = j + 1 + lane; i < p; i += 32) {
+        const double lij = A[i * LD + j];
+        for (int k = j + 1; k <= i; k++) A[i * LD + k] = fma(-lij, A[k * LD + j], A[i * LD + k]);
+      }
+      __syncwarp();
+    }
+    // lane c owns column c (+32, +64) of C^-1
+    for (int c = lane; c < p; c += 32) {
+      for (int i = 0; i < p; i++) {
+        double sacc = (i == c) ? 1.0 : 0.0;
+        for (int k = c; k < i; k++) sacc = fma(-A[i * LD + k], Ci[k * LD + c], sacc);
+        Ci[i * LD + c] = i < c ? 0.0 : sacc / A[i * LD + i];
+      }
+    }
+  }
+  __syncthreads();
+  // Ainv = C^-T C^-1 ; beta = Ainv b
+  for (int e = tid; e < p * p; e += 1024) {
+    const int i = e / p, j = e % p;
+    double acc = 0.0;
+    for (int k = max(i, j); k < p; k++) acc = fma(Ci[k * LD + i], Ci[k * LD + j], acc);
+    tw[TW_AINV + i * MGP_PMAX + j] = acc;
+    tw[TW_C + i * MGP_PMAX + j] = j <= i ? A[i * LD + j] : 0.0;
+    tw[TW_CINV + i * MGP_PMAX + j] = j <= i ? Ci[i * LD + j] : 0.0;
+  }
+  __syncthreads();
+  if (tid < p) {
+    double acc = 0.0;
+    for (int j = 0; j < p; j++) acc = fma(tw[TW_AINV + tid * MGP_PMAX + j], bv[j], acc);
+    beta[tid] = acc;
+  }
+  __syncthreads();
+  // rho = Yt - Ft beta, then one refinement step: rho -= Ft Ainv (Ft^T rho)
+  for (int pass = 0; pass < 2; pass++) {
+    for (int r = tid; r < npad; r += 1024) {
+      double v = 0.0;
+      if (r < n) {
+        v = pass == 0 ? yt[r] : rh[r];
+        for (int k = 0; k < p; k++) v = fma(-Ft[(int64_t)r * MGP_TP + k], pass == 0 ? beta[k] : bv[k], v);
+      }
+      rh[r] = v;
+    }
+    __syncthreads();
+    if (pass == 0) {
+      // c = Ft^T rho (into bv), delta = Ainv c (back into bv), beta += delta
+      {
+        int S = 32;
+        while (S > 1 && p * S > 1024) S >>= 1;
+        const int g = tid / S, sl = tid % S;
+        double acc = 0.0;
+        if (g < p)
+          for (int r = sl; r < n; r += S) acc = fma(Ft[(int64_t)r * MGP_TP + g], rh[r], acc);
+        for (int o = S >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sl == 0 && g < p) Ci[g] = acc;      // Ci is free now: reuse row 0 as scratch
+      }
+      __syncthreads();
+      if (tid < p) {
+        double acc = 0.0;
+        for (int j = 0; j < p; j++) acc = fma(tw[TW_AINV + tid * MGP_PMAX + j], Ci[j], acc);
+        bv[tid] = acc;
+        beta[tid] += acc;
+      }
+      __syncthreads();
+    }
+  }
+  double rr = 0.0;
+  for (int r = tid; r < n; r += 1024) rr = fma(rh[r], rh[r], rr);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rr += __shfl_xor_sync(0xffffffffu, rr, o);
+  if (lane == 0) red[warp] = rr;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0, ld = 0.0;
+    for (int w2 = 0; w2 < 32; w2++) t += red[w2];
+    for (int j = 0; j < p; j++) ld += 2.0 * log(A[j * LD + j]);
+    scal[(int64_t)b * SC_N + SC_RR] = t;
+    scal[(int64_t)b * SC_N + SC_LOGDETA] = ld;
+    scal[(int64_t)b * SC_N + SC_BETA] = beta[0];
+    if (bad) atomicCAS(&status[b], 0, npad + 1);   // rank-deficient basis: treated like a failed Cholesky
+  }
+  if (tid < MGP_PMAX) tw[TW_BETA + tid] = tid < p ? beta[tid] : 0.0;
+}
+
+// Qp[r][c] = sum_{k <= c} Ft[r][k] Cinv[c][k]  (Ft C^-T); Cinv recomputed from C per CTA
+__global__ void __launch_bounds__(256) k_trend_q(const double *Ftm, const double *tws, int n, int npad, int p,
+                                                 double *Qp) {
+  extern __shared__ double sm[];
+  constexpr int LD = MGP_PMAX + 1;
+  double *C = sm, *Ci = sm + MGP_PMAX * LD;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const double *tw = tws + (int64_t)b * TW_N;
+  for (int e = tid; e < p * p; e += 256) C[(e / p) * LD + e % p] = tw[TW_C + (e / p) * MGP_PMAX + e % p];
+  __syncthreads();
+  for (int c = tid; c < p; c += 256)
+    for (int i = 0; i < p; i++) {
+      double sacc = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; k++) sacc = fma(-C[i * LD + k], Ci[k * LD + c], sacc);
+      Ci[i * LD + c] = i < c ? 0.0 : sacc / C[i * LD + i];
+    }
+  __syncthreads();
+  const int r0 = blockIdx.x * 64;
+  for (int e = tid; e < 64 * MGP_TP; e += 256) {
+    const int r = r0 + e / MGP_TP, c = e % MGP_TP;
+    if (r >= npad) break;
+    double acc = 0.0;
+    if (r < n && c < p) {
+      const double *fr = Ftm + ((int64_t)b * npad + r) * MGP_TP;
+      for (int k = 0; k <= c; k++) acc = fma(fr[k], Ci[c * LD + k], acc);
+    }
+    Qp[((int64_t)b * npad + r) * MGP_TP + c] = acc;
+  }
+}
+
 __global__ void k_dup_check(const double *Xc, int n, int dpad, int *flag) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
   if (j >= n || j <= k) return;
@@ -310,14 +534,14 @@ template <int CORR>
 cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, const double *Xc, int n,
                           int npad, const double *params, int n_par, int mode, const double *Rinv,
                           int64_t sR, const double *gamma, const double *avec, int64_t sv,
-                          const double *scal, double *gpart, int ntiles) {
+                          const double *Bhat, int p, const double *scal, double *gpart, int ntiles) {
   switch (dpad) {
 #define NG(D)                                                                                   \
   case D:                                                                                       \
     cudaFuncSetAttribute(k_nll_grad<CORR, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                          (int)smem);                                                            \
     k_nll_grad<CORR, D><<<grid, 256, smem, st>>>(Xc, n, npad, params, n_par, mode, Rinv, sR,    \
-                                                  gamma, avec, sv, scal, gpart, ntiles);        \
+                                                  gamma, avec, sv, Bhat, p, scal, gpart, ntiles); \
     break;
     NG(4) NG(8) NG(12) NG(16) NG(20) NG(24) NG(28) NG(32) NG(36) NG(40) NG(44) NG(48) NG(52) NG(56) NG(60) NG(64)
 #undef NG
@@ -335,6 +559,40 @@ cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, con
   } while (0)
 
 size_t nll_scal_doubles() { return SC_N; }
+size_t trend_ws_doubles() { return TW_N; }
+
+cudaError_t launch_trend_mu(const double *Xc, const double *center, int n, int npad, int d, int dpad,
+                            const double *beta, double *mu, cudaStream_t st) {
+  k_trend_mu<<<(npad + 127) / 128, 128, 0, st>>>(Xc, center, n, npad, d, dpad, beta, mu);
+  return cudaGetLastError();
+}
+cudaError_t launch_trend_basis(const double *Xc, const double *center, int n, int npad, int d, int dpad,
+                               double *F, cudaStream_t st) {
+  k_trend_basis<<<npad, MGP_TP, 0, st>>>(Xc, center, n, npad, d, dpad, F);
+  return cudaGetLastError();
+}
+cudaError_t launch_trend_solve(const double *Ftm, const double *Yt, double *rho, int n, int npad, int p,
+                               double *tws, double *scal, int *status, int batch, cudaStream_t st) {
+  const int smem = (2 * MGP_PMAX * (MGP_PMAX + 1) + 2 * MGP_PMAX + 32) * (int)sizeof(double);
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(k_trend_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    done = true;
+  }
+  k_trend_solve<<<batch, 1024, smem, st>>>(Ftm, Yt, rho, n, npad, p, tws, scal, status);
+  return cudaGetLastError();
+}
+cudaError_t launch_trend_q(const double *Ftm, const double *tws, int n, int npad, int p, double *Qp,
+                           int batch, cudaStream_t st) {
+  const int smem = 2 * MGP_PMAX * (MGP_PMAX + 1) * (int)sizeof(double);
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(k_trend_q, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    done = true;
+  }
+  k_trend_q<<<dim3((npad + 63) / 64, batch), 256, smem, st>>>(Ftm, tws, n, npad, p, Qp);
+  return cudaGetLastError();
+}
 int nll_n_par(int mode, int d) { return d + (d - mode_n_theta(mode, d)); }
 
 cudaError_t launch_dup_check(const double *Xc, int n, int dpad, int *flag, cudaStream_t st) {
@@ -374,15 +632,46 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
     NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches, w.la));
   NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches));
   double *Yt = w.Yt, *Ft = w.Ft, *rho = w.rho, *gamma = w.gamma;
+  const bool general = w.p > 1 && w.ordinary;   // p basis functions with estimated coefficients
   NL_TRY(launch_trmv(w.M, npad, sM, w.y, 0, Yt, npad, n, 0, B, st));
-  NL_TRY(launch_trmv(w.M, npad, sM, nullptr, 0, Ft, npad, n, 0, B, st));
+  if (!general) {
+    // Ft = L^-1 1, or L^-1 (F beta) for a given non-constant mean (then rho = Yt - 1 * Ft)
+    NL_TRY(launch_trmv(w.M, npad, sM, w.mu, 0, Ft, npad, n, 0, B, st));
+  } else {
+    // Ft = L^-1 F as a GEMM (gpr.py:690), then the normal equations of the p x p trend problem
+    GemmDesc g = {};
+    g.A = w.M; g.lda = npad; g.ta = 0;
+    g.B = w.F; g.ldb = MGP_TP; g.tb = 1;
+    g.C = w.Ftm; g.ldc = MGP_TP;
+    g.M = npad; g.N = MGP_TP; g.K = npad; g.alpha = 1.0; g.beta = 0.0; g.kmode = 2; g.order = 2;
+    g.n_inner = 1; g.n_outer = B;
+    g.sA_out = sM; g.sB_out = 0; g.sC_out = (int64_t)npad * MGP_TP;
+    NL_TRY(launch_dgemm(g, st));
+    NL_TRY(launch_trend_solve(w.Ftm, Yt, rho, n, npad, w.p, w.tws, w.scal, w.status, B, st));
+    (*launches)++;
+  }
   k_nll_scalars<<<B, 256, 0, st>>>(w.L, npad, sM, n, Yt, Ft, rho, npad, w.params, w.n_par, w.mode,
-                                   w.noise_var, w.ordinary, w.beta0, w.scal, w.status, w.out_llf);
+                                   w.noise_var, w.ordinary, w.mu ? 1.0 : w.beta0, general ? w.p : 1,
+                                   w.logdetFF, w.scal, w.status, w.out_llf);
   NL_TRY(cudaGetLastError());
   NL_TRY(launch_trmv(w.M, npad, sM, rho, npad, gamma, npad, n, 1, B, st));
   (*launches) += 4;
+  const bool need_bhat = general && (w.want_bhat || (w.eval_grad && (w.mode & MGP_LIK_RESTRICTED)));
+  if (need_bhat) {
+    // Bhat = L^-T (Ft C^-T): REML's (L^-T Q)(L^-T Q)^T term and, for the fitted model, Ft^T L^-1 r
+    NL_TRY(launch_trend_q(w.Ftm, w.tws, n, npad, w.p, w.T, B, st));   // T is free until LAUUM
+    GemmDesc g = {};
+    g.A = w.M; g.lda = npad; g.ta = 1;
+    g.B = w.T; g.ldb = MGP_TP; g.tb = 1;
+    g.C = w.Bhat; g.ldc = MGP_TP;
+    g.M = npad; g.N = MGP_TP; g.K = npad; g.alpha = 1.0; g.beta = 0.0; g.kmode = 4; g.order = 1;
+    g.n_inner = 1; g.n_outer = B;
+    g.sA_out = sM; g.sB_out = (int64_t)npad * MGP_TP; g.sC_out = (int64_t)npad * MGP_TP;
+    NL_TRY(launch_dgemm(g, st));
+    (*launches) += 2;
+  }
   if (w.eval_grad) {
-    if ((w.mode & MGP_LIK_RESTRICTED) && w.ordinary) {   // a = L^-T Ft for the q q^T term of REML
+    if ((w.mode & MGP_LIK_RESTRICTED) && w.ordinary && !general) {   // a = L^-T Ft for the q q^T term of REML
       NL_TRY(launch_trmv(w.M, npad, sM, Ft, npad, w.avec, npad, n, 1, B, st));
       (*launches)++;
     }
@@ -392,13 +681,13 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
     dim3 grid(ntiles, B);
     if (w.corr == MGP_CORR_SE)
       NL_TRY(grad_dispatch<0>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
-                              sM, gamma, w.avec, npad, w.scal, w.gpart, ntiles));
+                              sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles));
     else if (w.corr == MGP_CORR_MATERN32)
       NL_TRY(grad_dispatch<1>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
-                              sM, gamma, w.avec, npad, w.scal, w.gpart, ntiles));
+                              sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles));
     else
       NL_TRY(grad_dispatch<2>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
-                              sM, gamma, w.avec, npad, w.scal, w.gpart, ntiles));
+                              sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles));
     k_nll_grad_final<<<B, 128, 0, st>>>(w.gpart, ntiles, w.dpad + 2, w.n_par, w.mode, w.scal,
                                         w.status, w.out_grad);
     NL_TRY(cudaGetLastError());

@@ -17,6 +17,15 @@ struct NllWork {
   double *linv;          // B x NI x 128 x 128
   double *Yt, *Ft, *rho, *gamma;  // each B x npad
   double *avec;          // B x npad: L^-T Ft (restricted likelihood, ordinary kriging)
+  // ---- general basis trend (p > 1 basis functions, e.g. linear_trend: p = d + 1) ----------------
+  int p;                 // number of basis functions (1 = constant trend)
+  const double *F;       // npad x MGP_TP basis matrix (rows >= n and columns >= p zero); p > 1, beta estimated
+  const double *mu;      // npad: F beta for a GIVEN beta (simple kriging with a non-constant mean); nullable
+  double *Ftm;           // B x npad x MGP_TP : L^-1 F
+  double *Bhat;          // B x npad x MGP_TP : L^-T (Ft C^-T), C = chol(Ft^T Ft)  (REML gradient; fitted-state operand)
+  double *tws;           // B x trend_ws_doubles(): beta | Ainv | C | scratch
+  double logdetFF;       // log det(F^T F) of the raw basis (REML, gpr.py:736)
+  int want_bhat;         // build Bhat even without a gradient (mgp_finalize_fit)
   double *scal;          // B x nll_scal_doubles()
   double *gpart;         // B x ntiles x (dpad + 2)
   int *status;           // B
@@ -25,9 +34,27 @@ struct NllWork {
   double *out_grad;      // device, B x n_par (nullable unless eval_grad)
 };
 size_t nll_scal_doubles();
+#define MGP_TP 128          // padded number of basis columns (GEMM tile width)
+#define MGP_PMAX 72         // max basis functions rounded up to 8 (d <= 64 -> p <= 65)
+size_t trend_ws_doubles();  // per batch element: beta[PMAX] | Ainv[PMAX^2] | C[PMAX^2] | Cinv[PMAX^2]
+enum { TWS_BETA = 0, TWS_AINV = MGP_PMAX, TWS_C = MGP_PMAX + MGP_PMAX * MGP_PMAX,
+       TWS_CINV = MGP_PMAX + 2 * MGP_PMAX * MGP_PMAX };
+// mu[j] = beta_0 + sum_i beta_{1+i} x_ji for the linear trend (x = Xc + center), 0 for j >= n
+cudaError_t launch_trend_mu(const double *Xc, const double *center, int n, int npad, int d, int dpad,
+                            const double *beta, double *mu, cudaStream_t st);
+// F[j][0] = 1, F[j][1+i] = x_ji (j < n), zero elsewhere; npad x MGP_TP
+cudaError_t launch_trend_basis(const double *Xc, const double *center, int n, int npad, int d, int dpad,
+                               double *F, cudaStream_t st);
+// A = Ft^T Ft, its Cholesky C, Ainv, beta = Ainv Ft^T Yt, rho = Yt - Ft beta (one refinement step),
+// rr = rho^T rho, log det A.  One CTA per batch element; results in tws and scal (NLL_RR, NLL_LOGDETA).
+cudaError_t launch_trend_solve(const double *Ftm, const double *Yt, double *rho, int n, int npad, int p,
+                               double *tws, double *scal, int *status, int batch, cudaStream_t st);
+// Qp = Ft C^-T (orthonormal columns), npad x MGP_TP
+cudaError_t launch_trend_q(const double *Ftm, const double *tws, int n, int npad, int p, double *Qp,
+                           int batch, cudaStream_t st);
 // scal slots
 enum { NLL_SIGMA2 = 0, NLL_LLF = 1, NLL_FTF = 2, NLL_FTY = 3, NLL_RR = 4, NLL_LOGDET = 5, NLL_S = 6,
-       NLL_V = 7, NLL_BETA = 8, NLL_NV = 9, NLL_COEFA = 10, NLL_THSCALE = 11 };
+       NLL_V = 7, NLL_BETA = 8, NLL_NV = 9, NLL_COEFA = 10, NLL_THSCALE = 11, NLL_LOGDETA = 12 };
 // number of hyper-parameters of a mode for d features (include/mgp.h)
 int nll_n_par(int mode, int d);
 cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches);

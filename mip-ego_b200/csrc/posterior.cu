@@ -40,13 +40,32 @@ __global__ void k_prep_model(const double *Xc, const double *theta, int npad, in
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int rgen_stride(int dpad) { return ((dpad + 11) / 16) * 16 + 4; }
 
-template <int CORR, int KS>
+__host__ __device__ constexpr int trend_tiles(int KS) { return (4 * KS + 1 + 7) / 8; }   // 8-col tiles for p <= 4 KS + 1
+__host__ __device__ constexpr int trend_stride(int P8) { return ((8 * P8 + 15) / 16) * 16 + 2; }  // == 2 (mod 16)
+
+// Bhat^T r on DMMA: the r values a lane holds after K1's distance GEMM (C fragment: candidate
+// lr, training rows 2 lk and 2 lk + 1 of the tile) ARE the A fragments of two MMA k-steps whose
+// k index is mapped to training row 2 lk + s; the B fragment is Bhat[2 lk + s][8 c8 + lr].
+template <int P8>
+__device__ __forceinline__ void trend_mma(double (&tacc)[P8][2], double r0, double r1, const double *sBh,
+                                          int STB, int t8, int lr, int lk) {
+#pragma unroll
+  for (int c8 = 0; c8 < P8; c8++) {
+    const double b0 = sBh[(8 * t8 + 2 * lk) * STB + 8 * c8 + lr];
+    const double b1 = sBh[(8 * t8 + 2 * lk + 1) * STB + 8 * c8 + lr];
+    dmma884(tacc[c8][0], tacc[c8][1], r0, b0);
+    dmma884(tacc[c8][0], tacc[c8][1], r1, b1);
+  }
+}
+
+template <int CORR, int KS, bool LIN>
 __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
   // Persistent: work item = (candidate block cb of 128, training block jb of 128).  The operands
   // of the training block (Bop rows, an, gamma, a) are staged once per item in shared memory.
   constexpr int DPAD = 4 * KS, SB = rgen_stride(DPAD);   // SB % 16 == 4: conflict-free B fragments
   extern __shared__ __align__(16) double sm_rg[];
-  double *sB = sm_rg, *sV = sm_rg + 128 * SB, *sTab = sV + 3 * 128;
+  constexpr int P8 = LIN ? trend_tiles(KS) : 1, STB = trend_stride(P8), PT = 8 * P8;
+  double *sB = sm_rg, *sV = sm_rg + 128 * SB, *sTab = sV + 3 * 128, *sBh = sTab + 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lk = lane & 3;
   const int nItems = p.nCblk * p.JS;
   if (tid < 32) sTab[tid] = c_exp2_tab[tid];
@@ -60,8 +79,19 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
     if (tid < 128) {
       sV[tid] = __ldg(p.an + jb * 128 + tid);
       sV[128 + tid] = __ldg(p.gamma + jb * 128 + tid);
-      sV[256 + tid] = __ldg(p.avec + jb * 128 + tid);
+      sV[256 + tid] = LIN ? 0.0 : __ldg(p.avec + jb * 128 + tid);
     }
+    if (LIN) {
+      for (int idx = tid; idx < 128 * PT; idx += 256) {
+        const int r = idx / PT, c = idx % PT;
+        sBh[r * STB + c] = __ldg(p.Bhat + (int64_t)(jb * 128 + r) * MGP_TP + c);
+      }
+    }
+    double tacc[2][P8][2];
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+      for (int c8 = 0; c8 < P8; c8++) tacc[u][c8][0] = tacc[u][c8][1] = 0.0;
     double xa[2][KS], bn[2];
 #pragma unroll
     for (int u = 0; u < 2; u++) {
@@ -103,8 +133,12 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
         *dst = make_double2(r0, r1);
         macc[u] = fma(g2.x, r0, macc[u]);
         macc[u] = fma(g2.y, r1, macc[u]);
-        facc[u] = fma(a2.x, r0, facc[u]);
-        facc[u] = fma(a2.y, r1, facc[u]);
+        if (LIN) {
+          trend_mma<P8>(tacc[u], r0, r1, sBh, STB, t8, lr, lk);
+        } else {
+          facc[u] = fma(a2.x, r0, facc[u]);
+          facc[u] = fma(a2.y, r1, facc[u]);
+        }
       }
     }
 #pragma unroll
@@ -113,10 +147,19 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
       macc[u] += __shfl_xor_sync(0xffffffffu, macc[u], 2);
       facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 1);
       facc[u] += __shfl_xor_sync(0xffffffffu, facc[u], 2);
+      const int64_t cand = (int64_t)cb * 128 + (2 * warp + u) * 8 + lr;
       if (lk == 0) {
-        const int64_t o = (int64_t)jb * p.ldp + (int64_t)cb * 128 + (2 * warp + u) * 8 + lr;
+        const int64_t o = (int64_t)jb * p.ldp + cand;
         p.meanpart[o] = macc[u];
-        p.ftpart[o] = facc[u];
+        if (!LIN) p.ftpart[o] = facc[u];
+      }
+      if (LIN) {
+#pragma unroll
+        for (int c8 = 0; c8 < P8; c8++) {
+          const int col = 8 * c8 + 2 * lk;
+          p.tpart[((int64_t)jb * PT + col) * p.ldp + cand] = tacc[u][c8][0];
+          p.tpart[((int64_t)jb * PT + col + 1) * p.ldp + cand] = tacc[u][c8][1];
+        }
       }
     }
   }
@@ -460,11 +503,30 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiParams p) {
       md += p.meanpart[(int64_t)y * p.ld + c];
       ft += p.ftpart[(int64_t)y * p.ld + c];
     }
-    mean = p.beta + md;
     double u2 = 0.0;
-    if (p.ordinary) {
-      const double u = (ft - 1.0) / p.G;
-      u2 = u * u;
+    if (p.p == 1) {
+      mean = p.beta + md;
+      if (p.ordinary) {
+        const double u = (ft - 1.0) / p.G;
+        u2 = u * u;
+      }
+    } else {
+      // f(x) = [1, x]; mean = beta . f + r . gamma; u = Bhat^T r - Cinv f  (= G^-T (Ft^T rt - f) up
+      // to the signs of the rows of G, gpr.py:466-467)
+      const double *x = p.Xs + c * p.d;
+      double mt = p.betav[0];
+      for (int i = 0; i < p.d; i++) mt = fma(p.betav[1 + i], x[i], mt);
+      mean = mt + md;
+      if (p.trend_est) {
+        for (int k = 0; k < p.p; k++) {
+          double w = 0.0;
+          for (int y = 0; y < p.JS; y++) w += p.tpart[((int64_t)y * p.PT + k) * p.ld + c];
+          double cf = p.Cinv[k * MGP_PMAX];
+          for (int j = 1; j <= k; j++) cf = fma(p.Cinv[k * MGP_PMAX + j], x[j - 1], cf);
+          const double u = w - cf;
+          u2 = fma(u, u, u2);
+        }
+      }
     }
     mse = fabs(p.sigma2 * (1.0 - q + u2));
     if (p.out_mean) p.out_mean[c] = mean;
@@ -577,13 +639,35 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
   const int64_t c8g = blockIdx.x;            // global 8-candidate group
   const int cb = (int)(c8g >> 4), c8 = (int)(c8g & 15);
   const int64_t c = c8g * 8 + cc;
+  __shared__ double s_u[8][MGP_PMAX];    // per warp: u = Bhat^T r - Cinv f      (p > 1, estimated)
+  __shared__ double s_k[8][MGP_PMAX];    // per warp: kappa = C^-T u = (Ft^T Ft)^-1 (Ft^T rt - f)
   if (c >= p.mc) return;
+  const bool gen = p.p > 1 && p.trend_est;
   double md = 0.0, ft = 0.0;
   for (int y = 0; y < p.JS; y++) {
     md += p.meanpart[(int64_t)y * p.ldp + c];
-    ft += p.ftpart[(int64_t)y * p.ldp + c];
+    if (p.p == 1) ft += p.ftpart[(int64_t)y * p.ldp + c];
   }
-  const double kappa = p.ordinary ? (ft - 1.0) / p.ftf : 0.0;
+  const double kappa = (p.p == 1 && p.ordinary) ? (ft - 1.0) / p.ftf : 0.0;
+  double u2g = 0.0;
+  if (gen) {
+    const double *x = p.Xs + c * p.d;
+    for (int k = lane; k < p.p; k += 32) {
+      double w = 0.0;
+      for (int y = 0; y < p.JS; y++) w += p.tpart[((int64_t)y * p.PT + k) * p.ldp + c];
+      double cf = p.Cinv[k * MGP_PMAX];
+      for (int j = 1; j <= k; j++) cf = fma(p.Cinv[k * MGP_PMAX + j], x[j - 1], cf);
+      s_u[cc][k] = w - cf;
+    }
+    __syncwarp();
+    for (int i = lane; i < p.p; i += 32) {
+      double t = 0.0;
+      for (int k = i; k < p.p; k++) t = fma(p.Cinv[k * MGP_PMAX + i], s_u[cc][k], t);
+      s_k[cc][i] = t;
+    }
+    for (int k = 0; k < p.p; k++) u2g = fma(s_u[cc][k], s_u[cc][k], u2g);
+    __syncwarp();
+  }
   double xs[DP], th[DP], am[DP], as[DP];
 #pragma unroll
   for (int i = 0; i < DP; i++) {
@@ -615,7 +699,14 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
       if (S == 0.0) coincide = 1;
       e = exp(-MGP_SQRT3 * sqrt(S));
     }
-    const double cm = p.gamma[j] * e, cs = (kappa * p.avec[j] - w) * e;
+    double proj = 0.0;    // (Ahat kappa)_j: Bhat_j . u for a general trend, kappa a_j for the constant one
+    if (gen) {
+      const double *bj = p.Bhat + (int64_t)j * MGP_TP;
+      for (int k = 0; k < p.p; k++) proj = fma(bj[k], s_u[cc][k], proj);
+    } else if (p.p == 1) {
+      proj = kappa * p.avec[j];
+    }
+    const double cm = p.gamma[j] * e, cs = (proj - w) * e;
 #pragma unroll
     for (int i = 0; i < DP; i++) {
       am[i] = fma(cm, df[i], am[i]);
@@ -628,11 +719,19 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
     coincide |= __shfl_xor_sync(0xffffffffu, coincide, o);
   }
   const double fac = CORR == 0 ? -2.0 : (CORR == 1 ? -3.0 : -1.0);
-  const double mean = p.beta + md;
+  double mean = p.beta + md;
   double u2 = 0.0;
-  if (p.ordinary) {
-    const double u = (ft - 1.0) / p.G;
-    u2 = u * u;
+  if (p.p == 1) {
+    if (p.ordinary) {
+      const double u = (ft - 1.0) / p.G;
+      u2 = u * u;
+    }
+  } else {
+    const double *x = p.Xs + c * p.d;
+    double mt = p.betav[0];
+    for (int i = 0; i < p.d; i++) mt = fma(p.betav[1 + i], x[i], mt);
+    mean = mt + md;
+    u2 = u2g;
   }
   const double mse = fabs(p.sigma2 * (1.0 - q + u2));
   const double sd = sqrt(mse);
@@ -653,6 +752,12 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
     if ((i & 31) == lane) {
       my_m = coincide ? 0.0 : fac * th[i] * a;
       my_s = coincide ? 0.0 : 2.0 * p.sigma2 * fac * th[i] * b;
+      if (p.p > 1 && i < p.d) {
+        // linear trend: f_dx = [0; I] (trend.py:106-109): beta^T f_dx = beta_{1+i} (gpr.py:539) and
+        // u^T (Ft^T Ft)^-1 (-f_dx) = -kappa_{1+i} (gpr.py:548-551); both survive a zeroed r_dx
+        my_m += p.betav[1 + i];
+        if (gen) my_s -= 2.0 * p.sigma2 * s_k[cc][1 + i];
+      }
     }
     if (i % 32 == 31 || i == DP - 1) {
       const int comp = (i / 32) * 32 + lane;
@@ -702,24 +807,26 @@ cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, i
   return cudaGetLastError();
 }
 
-template <int CORR, int KS>
+template <int CORR, int KS, bool LIN>
 static cudaError_t rgen_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
   static int occ = 0;
-  const int smem = (128 * rgen_stride(4 * KS) + 3 * 128 + 32) * (int)sizeof(double);
+  const int smem = (128 * rgen_stride(4 * KS) + 3 * 128 + 32 +
+                    (LIN ? 128 * trend_stride(trend_tiles(KS)) : 0)) * (int)sizeof(double);
   if (occ == 0) {
-    cudaFuncSetAttribute(k_rgen<CORR, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen<CORR, KS>, 256, smem) != cudaSuccess || occ < 1)
+    cudaFuncSetAttribute(k_rgen<CORR, KS, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen<CORR, KS, LIN>, 256, smem) != cudaSuccess || occ < 1)
       occ = 1;
   }
   const int items = p.nCblk * p.JS;
   const int grid = items < sm_count * occ ? items : sm_count * occ;
-  k_rgen<CORR, KS><<<grid, 256, smem, st>>>(p);
+  k_rgen<CORR, KS, LIN><<<grid, 256, smem, st>>>(p);
   return cudaGetLastError();
 }
+int rgen_trend_cols(int dpad) { return 8 * ((dpad + 1 + 7) / 8); }
 template <int CORR>
 static cudaError_t rgen_dispatch(const RgenParams &p, int sm_count, cudaStream_t st) {
   switch (p.dpad / 4) {
-#define RG(K) case K: return rgen_launch<CORR, K>(p, sm_count, st);
+#define RG(K) case K: return p.Bhat ? rgen_launch<CORR, K, true>(p, sm_count, st) : rgen_launch<CORR, K, false>(p, sm_count, st);
     RG(1) RG(2) RG(3) RG(4) RG(5) RG(6) RG(7) RG(8) RG(9) RG(10) RG(11) RG(12) RG(13) RG(14) RG(15) RG(16)
 #undef RG
     default: return cudaErrorInvalidValue;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "mgp_handle.h"
+#include "nll.cuh"
 
 // Per-fit operand preparation: Bop[j][i] = -2 theta_i xc_ji, an[j] = sum_i theta_i xc_ji^2.
 cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, int dpad,
@@ -15,9 +16,14 @@ struct RgenParams {
   int d, dpad, NJ8, nCblk, JS;   // JS = number of 128-row training blocks (= npad / 128)
   const double *center, *theta, *Bop, *an, *gamma, *avec;
   const double *Xc;   // centred training inputs (npad x dpad): used by the L1 (absolute-exponential) variant
+  // general trend with estimated coefficients (p > 1): Bhat^T r per candidate instead of a . r
+  const double *Bhat; // npad x MGP_TP: L^-T (Ft C^-T); nullptr for the constant trend
+  double *tpart;      // [JS][PT][ldp] partial sums of Bhat^T r (PT = 8 * ceil((4 KS + 1) / 8))
   double *rP, *meanpart, *ftpart;
   int64_t ldp;        // mc rounded up to 128
 };
+// number of trend columns K1 accumulates for a given dpad (multiple of 8, >= d + 1)
+int rgen_trend_cols(int dpad);
 // K1: r tile generator, persistent over (candidate block, training block) items.
 cudaError_t launch_rgen(const RgenParams &p, int corr, int sm_count, cudaStream_t st);
 
@@ -44,6 +50,13 @@ struct EpiParams {
   int kind, n_sets, minimize;
   double plugin;
   double params[MGP_MAX_SETS];
+  // non-constant trend (p > 1): f(x) = [1, x]; mean = beta . f + r . gamma;
+  // estimated coefficients: u = Bhat^T r - Cinv f, MSE uses |u|^2 (gpr.py:465-472)
+  int p, PT, d, trend_est;
+  const double *Xs;       // chunk base of the candidates (raw coordinates, ld d)
+  const double *betav;    // device, p coefficients
+  const double *Cinv;     // device, p x p (row stride MGP_PMAX), lower triangular
+  const double *tpart;    // [JS][PT][ld]
   // top-1 fast path: per-block best (value, global index) per set, [n_sets][ld_blk]; nullable
   double *blk_val;
   int64_t *blk_idx;
@@ -76,6 +89,9 @@ struct GradParams {
   int kind, n_sets, minimize;
   double plugin;
   double params[MGP_MAX_SETS];
+  // non-constant trend (see EpiParams)
+  int p, PT, trend_est;
+  const double *betav, *Cinv, *tpart, *Bhat;
 };
 // K5: gradient contraction + acquisition-with-gradient epilogue.
 cudaError_t launch_grad(const GradParams &p, int corr, cudaStream_t st);

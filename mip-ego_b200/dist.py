@@ -32,22 +32,24 @@ def broadcast_fitted_state(gp, src=0, device=None):
     torch, dist = _dist()
     rank = dist.get_rank()
     n, d = gp.X.shape
+    p = int(getattr(gp.mean, "n_dim", 1) or 1)      # trend coefficients (1 constant, d + 1 linear)
     dev = device if device is not None else "cpu"
     if rank == src:
         pack = [np.asarray(gp._state("theta"), dtype=np.float64).ravel(),
                 np.ascontiguousarray(gp.C, dtype=np.float64).ravel(),
                 np.asarray(gp.gamma, dtype=np.float64).ravel(),
-                np.array([float(np.ravel(gp.sigma2)[0]), float(np.ravel(gp.mean.beta)[0])])]
+                np.r_[float(np.ravel(gp.sigma2)[0]), np.ravel(gp.mean.beta).astype(np.float64)]]
         flat = np.concatenate(pack)
     else:
-        flat = np.empty(d + n * n + n + 2)
+        flat = np.empty(d + n * n + n + 1 + p)
     t = torch.from_numpy(flat).to(dev)
     dist.broadcast(t, src=src)
     if rank != src:
         flat = t.cpu().numpy()
         theta, L = flat[:d], flat[d:d + n * n].reshape(n, n)
-        gamma, sc = flat[d + n * n:d + n * n + n], flat[-2:]
-        gp.set_fitted_state(gp.X, gp.y.ravel(), theta, L, gamma, float(sc[0]), float(sc[1]))
+        gamma, sc = flat[d + n * n:d + n * n + n], flat[d + n * n + n:]
+        gp.set_fitted_state(gp.X, gp.y.ravel(), theta, L, gamma, float(sc[0]),
+                            float(sc[1]) if p == 1 else sc[1:].copy())
     return gp
 
 

@@ -17,7 +17,7 @@ from numpy import log10
 
 from . import _cabi
 from ._mle import multistart_lbfgsb
-from .trend import BasisExpansionTrend, constant_trend
+from .trend import BasisExpansionTrend, constant_trend, linear_trend
 
 MACHINE_EPSILON = np.finfo(np.double).eps
 
@@ -102,8 +102,11 @@ class GaussianProcess(object):
         if callable(self.corr) or self.corr not in self._correlation_types:
             raise NotImplementedError(
                 "corr=%r: the CUDA path implements %s" % (self.corr, self._correlation_types))
-        if not isinstance(self.mean, constant_trend):
-            raise NotImplementedError("only constant_trend is implemented by the CUDA path")
+        if not isinstance(self.mean, (constant_trend, linear_trend)):
+            raise NotImplementedError("constant_trend and linear_trend are implemented by the CUDA path")
+        if isinstance(self.mean, linear_trend) and self.estimate_trend and self.corr == "absolute_exponential":
+            raise NotImplementedError("an estimated linear trend with the absolute-exponential kernel "
+                                      "is not implemented by the CUDA path")
         if self.optimizer not in self._optimizer_types:
             raise ValueError("optimizer should be one of %s" % self._optimizer_types)
 
@@ -111,6 +114,36 @@ class GaussianProcess(object):
         if self._h is None:
             self._h = _cabi.Handle(self.device)
         return self._h
+
+    def _trend_args(self, beta=None):
+        """(trend code, beta array or None) for mgp_set_train."""
+        kind = "linear" if isinstance(self.mean, linear_trend) else "constant"
+        code = _cabi.TREND[(kind, self.estimate_trend)]
+        if self.estimate_trend:
+            return code, None
+        b = self.mean.beta if beta is None else beta
+        b = np.ascontiguousarray(np.ravel(b), dtype=np.float64)
+        if b.size != self.mean.n_dim:
+            raise Exception("Shapes of beta and F do not match.")
+        return code, b
+
+    def _set_train(self, X, y, beta=None):
+        h = self._handle()
+        n, d = X.shape
+        if self.mean.n_feature != d:
+            raise Exception("x does not have the right size!")
+        code, b = self._trend_args(beta)
+        rc = h.lib.mgp_set_train(h.h, n, d, _cabi.dptr(X), _cabi.dptr(y), _cabi.CORR[self.corr], code,
+                                 _cabi.dptr(b))
+        if rc == _cabi.MGP_EINVAL and b"duplicate rows" in h.lib.mgp_last_error(h.h):
+            raise Exception("Multiple input features cannot have the same target value.")
+        h.check(rc)
+
+    def _beta_from_device(self):
+        h = self._handle()
+        b = np.zeros(self.mean.n_dim)
+        h.check(h.lib.mgp_get_trend(h.h, _cabi.dptr(b)))
+        return b.reshape(-1, 1)
 
     def _check_params(self):
         # gpr.py:1103-1149 (the parts that can fail)
@@ -141,17 +174,11 @@ class GaussianProcess(object):
         if self.theta0.size not in (d,):
             raise ValueError("the CUDA path needs one theta per feature (anisotropic): "
                              "len(theta0)=%d, n_features=%d" % (self.theta0.size, d))
-        h = self._handle()
-        beta0 = 0.0 if self.estimate_trend else float(np.ravel(self.mean.beta)[0])
-        rc = h.lib.mgp_set_train(h.h, n, d, _cabi.dptr(X), _cabi.dptr(y), _cabi.CORR[self.corr],
-                                 1 if self.estimate_trend else 0, beta0)
-        if rc == _cabi.MGP_EINVAL and b"duplicate rows" in h.lib.mgp_last_error(h.h):
-            raise Exception("Multiple input features cannot have the same target value.")
-        h.check(rc)
+        self._set_train(X, y)
         self._cache = {}
         self._host_state = None
         if self.estimate_trend:
-            self.F = np.ones((n, 1))
+            self.F = self.mean.F(X)
 
     # ------------------------------------------------------------------------------------
     # likelihood
@@ -282,7 +309,7 @@ class GaussianProcess(object):
         else:
             self._env_noise_var = self._nugget if self.estimation_mode == "noisy" else 0
         if self.estimate_trend:
-            self.mean.beta = np.array([[sc[1]]])
+            self.mean.beta = self._beta_from_device()
         self._par_fitted = par.copy()
         return float(out.value)
 
@@ -361,17 +388,15 @@ class GaussianProcess(object):
         self.X, self.y = X, y.reshape(-1, 1)
         n, d = X.shape
         h = self._handle()
-        beta0 = 0.0 if self.estimate_trend else float(beta)
-        rc = h.lib.mgp_set_train(h.h, n, d, _cabi.dptr(X), _cabi.dptr(y), _cabi.CORR[self.corr],
-                                 1 if self.estimate_trend else 0, beta0)
-        if rc == _cabi.MGP_EINVAL and b"duplicate rows" in h.lib.mgp_last_error(h.h):
-            raise Exception("Multiple input features cannot have the same target value.")
-        h.check(rc)
+        bvec = np.ascontiguousarray(np.ravel(beta), dtype=np.float64)
+        if bvec.size != self.mean.n_dim:
+            raise Exception("Shapes of beta and F do not match.")
+        self._set_train(X, y, beta=bvec)
         theta = _cabi.as_f64(theta).ravel()
         Lc = _cabi.as_f64(L, (n, n))
         g = _cabi.as_f64(gamma).ravel()
         h.check(h.lib.mgp_set_state(h.h, _cabi.dptr(theta), _cabi.dptr(Lc), _cabi.dptr(g),
-                                    float(np.ravel(sigma2)[0]), float(beta)))
+                                    float(np.ravel(sigma2)[0]), _cabi.dptr(bvec)))
         self._cache = {}
         self._host_state = None
         self.theta_ = theta.copy()
@@ -379,8 +404,8 @@ class GaussianProcess(object):
         self.sigma2 = np.array([float(np.ravel(sigma2)[0])]) if self.estimation_mode == "noiseless" \
             else np.float64(np.ravel(sigma2)[0])
         if self.estimate_trend:
-            self.mean.beta = np.array([[float(beta)]])
-            self.F = np.ones((n, 1))
+            self.mean.beta = bvec.reshape(-1, 1).copy()
+            self.F = self.mean.F(X)
         self.is_fitted = True
         return self
 
@@ -391,8 +416,9 @@ class GaussianProcess(object):
         if key not in self._cache:
             h = self._handle()
             n, d = self.X.shape
+            pcols = self.mean.n_dim if self.estimate_trend else 1
             bufs = dict(theta=np.empty(d), L=np.empty((n, n)), gamma=np.empty(n), rho=np.empty(n),
-                        Yt=np.empty(n), Ft=np.empty(n), sc=np.empty(5))
+                        Yt=np.empty(n), Ft=np.empty((n, pcols)), sc=np.empty(5))
             h.check(h.lib.mgp_get_state(h.h, *[_cabi.dptr(bufs[k]) for k in
                                                ("theta", "L", "gamma", "rho", "Yt", "Ft", "sc")]))
             self._cache = bufs
@@ -416,15 +442,33 @@ class GaussianProcess(object):
 
     @property
     def Ft(self):
-        return self._state("Ft").reshape(-1, 1) if self.estimate_trend else None
+        return self._state("Ft").reshape(self.X.shape[0], -1) if self.estimate_trend else None
+
+    def _qr(self):
+        """Q, G of Ft (gpr.py:691) for a p > 1 basis.  The posterior kernels work with the
+        sign-free quantities (Ft^T Ft and its Cholesky factor); G and Q are only materialised
+        for users who read these attributes, with the reference's own LAPACK routine so that the
+        Householder signs agree."""
+        if "QR" not in self._cache:
+            from scipy import linalg
+            self._cache["QR"] = linalg.qr(self.Ft, mode="economic")
+        return self._cache["QR"]
 
     @property
     def G(self):
-        return np.array([[self._state("sc")[2]]]) if self.estimate_trend else None
+        if not self.estimate_trend:
+            return None
+        if self.mean.n_dim == 1:
+            return np.array([[self._state("sc")[2]]])
+        return self._qr()[1]
 
     @property
     def Q(self):
-        return self.Ft / self._state("sc")[2] if self.estimate_trend else None
+        if not self.estimate_trend:
+            return None
+        if self.mean.n_dim == 1:
+            return self.Ft / self._state("sc")[2]
+        return self._qr()[0]
 
     # ------------------------------------------------------------------------------------
     # posterior
@@ -518,7 +562,7 @@ class GaussianProcess(object):
                             rho=np.array(self._state("rho")), Yt=np.array(self._state("Yt")),
                             Ft=np.array(self._state("Ft")), sc=np.array(self._state("sc")),
                             sigma2=float(np.ravel(self.sigma2)[0]),
-                            beta=float(np.ravel(self.mean.beta)[0]))
+                            beta=np.array(np.ravel(self.mean.beta), dtype=np.float64))
         st["_h"] = None
         st["_cache"] = {}
         st["_host_state"] = host

@@ -1,7 +1,7 @@
 """Prior-mean (trend) objects with the reference's interface (mipego/GaussianProcess/trend.py).
 
-Only `constant_trend` is accelerated by the CUDA path (trend.py:69-88); `linear_trend` is
-provided so reference scripts import, but GaussianProcess rejects it.
+`constant_trend` (trend.py:69-88) and `linear_trend` (trend.py:90-110) are evaluated by the CUDA
+path, with given coefficients (simple kriging) or estimated ones (ordinary / universal kriging).
 """
 import numpy as np
 
@@ -58,7 +58,7 @@ class constant_trend(BasisExpansionTrend):
 
 
 class linear_trend(BasisExpansionTrend):
-    """First-order polynomial trend (trend.py:90-110); not supported by the CUDA path yet."""
+    """First-order polynomial trend f(x) = [1, x_1..x_d], p = d + 1 (trend.py:90-110)."""
 
     def __init__(self, n_feature, beta=None):
         super(linear_trend, self).__init__(n_feature)

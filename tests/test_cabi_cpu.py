@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_cabi.SIGNATURES) == syms
-    assert lib.mgp_abi_version() == 2
+    assert lib.mgp_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -132,3 +132,37 @@ def test_c5_shape_runs_and_is_consistent():
     assert np.array_equal(v2[::-1], v) and np.all(v >= 0) and np.all(np.isfinite(v))
     m2, s2_ = gp.predict(Xs, eval_MSE=True)
     assert np.all(s2_ <= s2 * (1 + 1e-9))      # simple kriging: posterior variance <= prior variance
+
+
+def test_batch_groups_on_recycled_memory():
+    """Regression: the tile-scheduler words of a GEMM stream must be zeroed in stream order.  A new
+    handle after a big one has been freed receives recycled (non-zero) device memory; concurrent
+    batch groups (one stream each) must still give bitwise the results of the single-stream run."""
+    import gc
+    import mipego_b200 as mb
+
+    def small(groups):
+        rng = np.random.default_rng(5)
+        n, d = 640, 8
+        X, y, _ = _data(n, d, 5)
+        gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential",
+                                theta0=0.1 * np.ones(d), thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d))
+        gp._check_data(X, y)
+        gp._handle().set_option("nll_groups", groups)
+        P = (0.3 / d) * 10.0 ** rng.uniform(-0.4, 0.4, (5, d))
+        return gp.log_likelihood_batch(P, eval_grad=True)
+
+    ref = small(1)
+    for it in range(4):
+        n, d = 2048, 12
+        X, y, rng = _data(n, d, 31 + it)
+        big = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential",
+                                 theta0=0.02 * np.ones(d), thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d),
+                                 nugget=1e-6)
+        big._check_data(X, y)
+        big.log_likelihood_batch(np.c_[(0.2 / d) * rng.uniform(0.5, 1.5, (8, d)), np.full(8, 0.8)])
+        del big
+        gc.collect()
+        for groups in (0, 1):
+            r = small(groups)
+            assert np.array_equal(r[0], ref[0]) and np.array_equal(r[1], ref[1]) and np.all(r[2] == 0)

@@ -10,7 +10,7 @@ With nugget 0 the reference's own formulas evaluated in two orders differ by 4e-
 import numpy as np
 import pytest
 
-from golden_util import FIXED, FITS, VARS, load, mode_of, beta_of, likelihood_of
+from golden_util import FIXED, FITS, VARS, LINS, load, mode_of, beta_of, likelihood_of, trend_of
 
 pytestmark = pytest.mark.gpu
 
@@ -512,6 +512,104 @@ def test_bo_shaped_loop():
         X = np.vstack([X, best_x])
         y = np.r_[y, fitness(best_x)]
     assert y.min() <= np.sort(y[:8])[0]
+
+
+@pytest.mark.parametrize("name", LINS)
+def test_linear_trend_golden(name):
+    """linear_trend (trend.py:90-110), coefficients estimated (universal kriging, p = d + 1) or
+    given: likelihood + gradient, harvested state, posterior, posterior gradient and EI with its
+    gradient against fixtures produced by the reference."""
+    mb, O = _mods()
+    g = load(name)
+    d = g["X"].shape[1]
+    lik, mode = likelihood_of(g), mode_of(g)
+    est = g["estimate_trend"]
+    beta = None if est else np.asarray(g["beta_in"], dtype=np.float64)
+    nug = float(g["nugget"])
+    gp = mb.GaussianProcess(mean=mb.linear_trend(d, beta=beta), corr=g["kind"], theta0=g["theta"],
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d),
+                            nugget=nug if nug > 0 else 0, likelihood=lik)
+    gp._check_data(g["X"], g["y"])
+    par = g["par"]
+    rng = np.random.default_rng(9)
+    scale = np.ones((3, par.size))
+    scale[:, :d] = rng.uniform(0.7, 1.5, (3, d))
+    P = np.vstack([par, par * scale])
+    llf, grad, status = gp.log_likelihood_batch(P, eval_grad=True)
+    fn = O.log_likelihood_restricted if lik == "restricted" else O.log_likelihood_concentrated
+    for b in range(4):
+        rl, rg = fn(g["X"], g["y"], P[b], g["kind"], est, beta_of(g), mode, nug, eval_grad=True,
+                    trend="linear")
+        if b == 0:
+            assert (np.isinf(rl) and np.isinf(float(g["llf"]))) or abs(rl - float(g["llf"])) <= 1e-9 * abs(rl)
+        if np.isinf(rl):
+            assert np.isinf(llf[b])
+        else:
+            assert abs(llf[b] - rl) <= 1e-9 * abs(rl), (b, llf[b], rl)
+        if np.abs(rg).max() > 0:
+            assert np.max(np.abs(grad[b] - rg.ravel())) <= tol(g, 1e-7, 1e-6) * np.abs(rg).max(), (b, grad[b], rg.ravel())
+    env = {}
+    single = gp.log_likelihood_restricted if lik == "restricted" else gp.log_likelihood_concentrated
+    single(par, env=env)
+    assert np.allclose(env["C"], g["L"], rtol=0, atol=1e-11)
+    assert abs(float(np.ravel(env["sigma2"])[0]) - float(g["sigma2"])) <= 1e-9 * float(g["sigma2"])
+    assert np.max(np.abs(np.ravel(gp.mean.beta) - np.ravel(g["beta"]))) <= tol(g, 1e-8, 1e-6) * max(1.0, np.abs(g["beta"]).max())
+    assert np.max(np.abs(gp.gamma - g["gamma"])) <= tol(g, 1e-8, 1e-6) * np.abs(g["gamma"]).max()
+    assert np.max(np.abs(gp.rho - g["rho"])) <= tol(g, 1e-8, 1e-6) * np.abs(g["rho"]).max()
+    if est:
+        assert gp.Ft.shape == g["Ft"].shape
+        assert np.max(np.abs(gp.Ft - g["Ft"])) <= 1e-9 * np.abs(g["Ft"]).max()
+        assert np.max(np.abs(gp.G - g["G"])) <= 1e-8 * np.abs(g["G"]).max()     # same LAPACK QR signs
+    gp.theta_, gp.is_fitted = par[:d], True
+    mean, mse = gp.predict(g["Xs"], eval_MSE=True)
+    assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-3)) < tol(g, 1e-9, 1e-6)
+    s2 = float(g["sigma2"])
+    assert np.max(np.abs(mse - g["mse"]) / (np.abs(g["mse"]) + 1e-6 * s2)) < tol(g, 1e-7, 1e-5)
+    mdx, sdx = gp.gradient_batch(g["Xs"])
+    assert np.max(np.abs(mdx - g["mean_dx"])) < tol(g, 1e-8, 1e-6) * np.abs(g["mean_dx"]).max()
+    assert np.max(np.abs(sdx - g["mse_dx"])) < tol(g, 1e-7, 1e-5) * np.abs(g["mse_dx"]).max()
+    ei = mb.EI(model=gp, minimize=True, plugin=float(g["plugin_min"]))
+    v, dx = ei(g["Xs"], return_dx=True)
+    easy = g["mse"] > 1e-4 * s2
+    rv, rdx = g["EI_min"], g["EI_min_dx"]
+    assert np.max(np.abs(v[easy] - rv[easy]) / (np.abs(rv[easy]) + 1e-6 * np.abs(rv).max())) < tol(g, 1e-7, 2e-5)
+    assert np.max(np.abs(dx[easy] - rdx[easy])) < tol(g, 1e-7, 2e-5) * np.abs(rdx[easy]).max()
+    # pickle round trip keeps the coefficient vector
+    import pickle
+    g2 = pickle.loads(pickle.dumps(gp))
+    m2, s2_ = g2.predict(g["Xs"], eval_MSE=True)
+    assert np.max(np.abs(m2 - mean)) <= 1e-9 * np.abs(mean).max() and np.max(np.abs(s2_ - mse)) <= 1e-7 * np.abs(mse).max() + 1e-12 * s2
+
+
+def test_linear_trend_fit_and_larger_n():
+    """Universal kriging at n = 700, d = 20 (p = 21: three 8-column trend tiles, several training
+    blocks): a full fit, then the oracle model for the fitted hyper-parameters."""
+    mb, O = _mods()
+    rng = np.random.default_rng(12)
+    n, d = 700, 20
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0]) + 4 * X[:, 2] - 2 * X[:, 7]
+    y = (y - y.mean()) / y.std()
+    np.random.seed(2)
+    gp = mb.GaussianProcess(mean=mb.linear_trend(d, beta=None), corr="squared_exponential",
+                            theta0=[0.01] * d, thetaL=[1e-4] * d, thetaU=[10.0] * d, nugget=1e-6,
+                            random_start=2, eval_budget=60)
+    gp.fit(X, y)
+    par = np.concatenate([np.ravel(v) for v in gp.par.values()])
+    st = O.fit_state(X, y, par, "squared_exponential", True, 0.0, "noisy", 1e-6, trend="linear")
+    assert abs(float(np.ravel(gp.log_likelihood_)[0]) - st["llf"]) <= 1e-8 * abs(st["llf"])
+    assert np.max(np.abs(np.ravel(gp.mean.beta) - np.ravel(st["beta"]))) < 1e-7 * max(1.0, np.abs(st["beta"]).max())
+    Xs = rng.uniform(-5, 5, (3000, d))
+    rm, rs = O.predict(st, Xs)
+    mean, mse = gp.predict(Xs, eval_MSE=True)
+    assert np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3)) < 1e-8
+    assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-6
+    sub = Xs[:300]
+    ei = mb.EI(model=gp, minimize=True, plugin=float(y.min()))
+    v, dx = ei(sub, return_dx=True)
+    rv, rdx = O.acquisition(st, sub, "EI", None, float(y.min()), True, return_dx=True)
+    assert np.max(np.abs(v - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())) < 1e-6
+    assert np.max(np.abs(dx - rdx)) < 1e-6 * np.abs(rdx).max()
 
 
 def test_update_without_reoptimisation():
