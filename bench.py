@@ -58,6 +58,19 @@ def fp64_peak():
         return FP64_PEAK_FALLBACK_TFLOPS, "fallback (earlier DMMA measurement on this pool)"
 
 
+def trmm_traffic(workload, chunk):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_trmm launch from the committed
+    `ncu --set full` capture of this workload (profiles/r01_trmm_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_trmm_traffic.json")) as f:
+            t = json.load(f).get(workload)
+        if t and int(t["chunk"]) == int(chunk):
+            return float(t["bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def synth_model(n, d, kind, seed=10):
     """SURVEY section 8d synthetic training set and hyper-parameters (no fitting here)."""
     rng = np.random.default_rng(seed)
@@ -514,7 +527,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "k_trmm<false> (T = L^-1 r, fused sum of squares)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": trmm_traffic(args.workload, chunk),
                          "peak_source": "FP64 " + peak_src + "; MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_launch": flops_per_launch, "launches_timed": int(trmm_calls),
                          "avg_launch_ms": trmm_ns / max(1, trmm_calls) * 1e-6,

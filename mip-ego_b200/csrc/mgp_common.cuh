@@ -109,7 +109,9 @@ __device__ __forceinline__ double corr_from_S(double S) {
 // polynomial: 11 FP64-pipe instructions instead of ~22 for exp(); measured relative error 2.2e-16
 // against a 200-bit reference (the table entries are correctly rounded).  The K1 kernels are bound
 // by the FP64 pipe, which DFMA shares with DMMA (profiles/r01_fp64_pipe_mix.json), so every
-// instruction saved there is machine time.  `tab` points to the table in SHARED memory.
+// instruction saved there is machine time.  `tab` points to the table in SHARED memory, stored as
+// 32 entries x 16 replicas (entry j, replica lane & 15 at [16 j + (lane & 15)]) so that the
+// data-dependent look-up of a half-warp never hits one bank twice (exp_tab_fill).
 __constant__ double c_exp2_tab[32] = {
     1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577,
     1.1143867425958924, 1.1387886347566916, 1.1637248587775775, 1.189207115002721,
@@ -134,10 +136,14 @@ __device__ __forceinline__ double exp_neg_tab(double S, const double *tab) {
   p = fma(p, t, 0.5);
   p = fma(p, t, 1.0);
   p *= t;
-  const double tj = tab[N & 31];
+  const double tj = tab[((N & 31) << 4) | (threadIdx.x & 15)];   // replica = lane & 15: no bank conflicts
   const double y = fma(tj, p, tj);                         // in [1, 2)
   const double r = __hiloint2double(__double2hiint(y) + ((N >> 5) << 20), __double2loint(y));
   return S > 708.0 ? 0.0 : r;                              // below the normal range: flush
+}
+#define MGP_EXP_TAB_DOUBLES 512
+__device__ __forceinline__ void exp_tab_fill(double *tab, int tid, int nthreads) {
+  for (int i = tid; i < MGP_EXP_TAB_DOUBLES; i += nthreads) tab[i] = c_exp2_tab[i >> 4];
 }
 template <int CORR>
 __device__ __forceinline__ double corr_from_S_tab(double S, const double *tab) {

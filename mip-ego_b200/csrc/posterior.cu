@@ -65,10 +65,10 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
   constexpr int DPAD = 4 * KS, SB = rgen_stride(DPAD);   // SB % 16 == 4: conflict-free B fragments
   extern __shared__ __align__(16) double sm_rg[];
   constexpr int P8 = LIN ? trend_tiles(KS) : 1, STB = trend_stride(P8), PT = 8 * P8;
-  double *sB = sm_rg, *sV = sm_rg + 128 * SB, *sTab = sV + 3 * 128, *sBh = sTab + 32;
+  double *sB = sm_rg, *sV = sm_rg + 128 * SB, *sTab = sV + 3 * 128, *sBh = sTab + MGP_EXP_TAB_DOUBLES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lk = lane & 3;
   const int nItems = p.nCblk * p.JS;
-  if (tid < 32) sTab[tid] = c_exp2_tab[tid];
+  exp_tab_fill(sTab, tid, 256);
   for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
     const int jb = item / p.nCblk, cb = item % p.nCblk;
     __syncthreads();
@@ -112,9 +112,10 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
     }
     __syncthreads();
     double macc[2] = {0.0, 0.0}, facc[2] = {0.0, 0.0};
+    // output tile (cb, j8 = 16 jb + t8, c8 = 2 warp + u): one 64-bit base per item, 32-bit offsets inside
+    double *const dst0 = p.rP + (((int64_t)cb * p.NJ8 + jb * 16) * 16 + 2 * warp) * 64 + lane * 2;
 #pragma unroll 2
     for (int t8 = 0; t8 < 16; t8++) {
-      const int j8 = jb * 16 + t8;
       const int jrow = 8 * t8 + lr, jcol = 8 * t8 + 2 * lk;
       double bf[KS];
 #pragma unroll
@@ -128,9 +129,7 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
 #pragma unroll
         for (int s = 0; s < KS; s++) dmma884(c0, c1, xa[u][s], bf[s]);
         const double r0 = corr_from_S_tab<CORR>(c0, sTab), r1 = corr_from_S_tab<CORR>(c1, sTab);
-        double2 *dst = reinterpret_cast<double2 *>(
-            p.rP + (((int64_t)cb * p.NJ8 + j8) * 16 + (2 * warp + u)) * 64 + lane * 2);
-        *dst = make_double2(r0, r1);
+        *reinterpret_cast<double2 *>(dst0 + (t8 * 16 + u) * 64) = make_double2(r0, r1);
         macc[u] = fma(g2.x, r0, macc[u]);
         macc[u] = fma(g2.y, r1, macc[u]);
         if (LIN) {
@@ -177,8 +176,8 @@ __global__ void __launch_bounds__(256) k_rgen_l1(RgenParams p) {
   double *sC = sX + DPAD * XS;        // [128][CS]    candidate block
   double *sTh = sC + 128 * CS;        // [DPAD]
   double *sV = sTh + DPAD;            // gamma | avec
-  double *sTab = sV + 2 * 128;        // 2^(j/32)
-  if (threadIdx.x < 32) sTab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+  double *sTab = sV + 2 * 128;        // 2^(j/32), 16 replicas
+  exp_tab_fill(sTab, threadIdx.x, 256);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lk = lane & 3;
   const int nItems = p.nCblk * p.JS;
   int last_cb = -1;
@@ -810,7 +809,7 @@ cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, i
 template <int CORR, int KS, bool LIN>
 static cudaError_t rgen_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
   static int occ = 0;
-  const int smem = (128 * rgen_stride(4 * KS) + 3 * 128 + 32 +
+  const int smem = (128 * rgen_stride(4 * KS) + 3 * 128 + MGP_EXP_TAB_DOUBLES +
                     (LIN ? 128 * trend_stride(trend_tiles(KS)) : 0)) * (int)sizeof(double);
   if (occ == 0) {
     cudaFuncSetAttribute(k_rgen<CORR, KS, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -835,7 +834,7 @@ static cudaError_t rgen_dispatch(const RgenParams &p, int sm_count, cudaStream_t
 template <int DPAD>
 static cudaError_t rgen_l1_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
   static int occ = 0;
-  const int smem = (DPAD * 132 + 128 * (DPAD + 1) + DPAD + 2 * 128 + 32) * (int)sizeof(double);
+  const int smem = (DPAD * 132 + 128 * (DPAD + 1) + DPAD + 2 * 128 + MGP_EXP_TAB_DOUBLES) * (int)sizeof(double);
   if (occ == 0) {
     cudaFuncSetAttribute(k_rgen_l1<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen_l1<DPAD>, 256, smem) != cudaSuccess || occ < 1)
