@@ -167,6 +167,10 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
     h->chunk_opt = round_up(value, 128);
     return MGP_OK;
   }
+  if (!strcmp(name, "small_path")) {   // 0 disables the matrix-vector path for <= 8 candidates (tests)
+    h->no_small_path = value == 0;
+    return MGP_OK;
+  }
   if (!strcmp(name, "nll_groups")) {
     if (value < 0 || value > MGP_NLL_STREAMS) return mgp_fail(h, MGP_EINVAL, "nll_groups must be in 0..%d", MGP_NLL_STREAMS);
     h->nll_groups_opt = (int)value;
@@ -684,7 +688,8 @@ static int ensure_rinv(mgp_handle *h, cudaStream_t st) {
   MGP_TRY(mgp_ensure(h, h->dRinvP, mat));
   MGP_CUDA(h, lauum_blocked(P<double>(h->dMinv), P<double>(h->dTmp), h->npad, 0, 1, st, &h->launches));
   MGP_CUDA(h, launch_pack_sym(P<double>(h->dTmp), h->n, h->npad, P<double>(h->dRinvP), st));
-  h->launches++;
+  MGP_CUDA(h, launch_symmetrize(P<double>(h->dTmp), h->npad, st));   // row-major R^-1 for the small-population path
+  h->launches += 2;
   h->rinv_ready = true;
   return 0;
 }
@@ -737,14 +742,22 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     rp.ldp = ldp;
     { KTimer t(h, st, 0); MGP_CUDA(h, launch_rgen(rp, h->corr, h->sm_count, st)); }
     h->launches++;
+    const bool small = mc <= 8 && !h->no_small_path;   // matrix-vector path for tiny populations
     if (!q.want_dx) {
-      TrmmParams tp;
-      tp.Mp = P<double>(h->dMp); tp.rP = P<double>(h->drP); tp.qpart = P<double>(h->dqpart);
-      tp.wP = nullptr; tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 0; tp.ldq = ldp;
-      { KTimer t(h, st, 1); MGP_CUDA(h, launch_trmm(tp, h->sm_count, st)); }
+      if (small) {
+        KTimer t(h, st, 1);
+        MGP_CUDA(h, launch_small_mv(P<double>(h->dMinv), h->npad, h->n, P<double>(h->drP), (int)mc, 0,
+                                    P<double>(h->dqpart), ldp, nullptr, st));
+      } else {
+        TrmmParams tp;
+        tp.Mp = P<double>(h->dMp); tp.rP = P<double>(h->drP); tp.qpart = P<double>(h->dqpart);
+        tp.wP = nullptr; tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 0; tp.ldq = ldp;
+        KTimer t(h, st, 1);
+        MGP_CUDA(h, launch_trmm(tp, h->sm_count, st));
+      }
       EpiParams ep;
       ep.qpart = P<double>(h->dqpart); ep.meanpart = P<double>(h->dmeanpart); ep.ftpart = P<double>(h->dftpart);
-      ep.NI = h->NI; ep.JS = JS; ep.ld = ldp; ep.mc = mc;
+      ep.NI = small ? h->npad / 32 : h->NI; ep.JS = JS; ep.ld = ldp; ep.mc = mc;
       ep.beta = h->beta; ep.sigma2 = h->sigma2; ep.G = h->G; ep.ordinary = ordinary;
       ep.p = h->p; ep.PT = PT; ep.d = h->d; ep.trend_est = h->trend_est ? 1 : 0;
       ep.Xs = q.d_Xs + c0 * h->d; ep.betav = P<double>(h->dbetav); ep.Cinv = P<double>(h->dCinv);
@@ -761,10 +774,17 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       { KTimer t(h, st, 2); MGP_CUDA(h, launch_epilogue(ep, st)); }
       h->launches += 2;
     } else {
-      TrmmParams tp;
-      tp.Mp = P<double>(h->dRinvP); tp.rP = P<double>(h->drP); tp.qpart = nullptr;
-      tp.wP = P<double>(h->dwP); tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 1; tp.ldq = ldp;
-      { KTimer t(h, st, 1); MGP_CUDA(h, launch_trmm(tp, h->sm_count, st)); }
+      if (small) {
+        KTimer t(h, st, 1);
+        MGP_CUDA(h, launch_small_mv(P<double>(h->dTmp), h->npad, h->n, P<double>(h->drP), (int)mc, 1, nullptr, ldp,
+                                    P<double>(h->dwP), st));
+      } else {
+        TrmmParams tp;
+        tp.Mp = P<double>(h->dRinvP); tp.rP = P<double>(h->drP); tp.qpart = nullptr;
+        tp.wP = P<double>(h->dwP); tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 1; tp.ldq = ldp;
+        KTimer t(h, st, 1);
+        MGP_CUDA(h, launch_trmm(tp, h->sm_count, st));
+      }
       GradParams gp;
       gp.Xs = q.d_Xs + c0 * h->d; gp.mc = mc; gp.ldp = ldp; gp.n = h->n; gp.d = h->d; gp.dpad = h->dpad;
       gp.NJ8 = NJ8; gp.Xc = P<double>(h->dXc); gp.center = P<double>(h->dcenter);

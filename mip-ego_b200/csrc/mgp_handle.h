@@ -74,6 +74,7 @@ struct mgp_handle {
   // ---- posterior workspace ---------------------------------------------------------------
   int64_t chunk = 0;       // candidates per pass (multiple of 128)
   int64_t chunk_opt = 0;   // user override
+  bool no_small_path = false;  // option "small_path" = 0
   DevBuf drP, dmeanpart, dftpart, dqpart, dwP, dtpart;
   DevBuf dXs_stage[2], dout_stage[2];
   DevBuf dtopk_val, dtopk_idx, dtopk_blk;

@@ -435,6 +435,97 @@ __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small populations (<= 8 candidates per pass): the call pattern of the reference's own
+// argmax_restart, one point per criterion call (optimizer/utils.py:38-42).  T = L^-1 r (W = R^-1 r)
+// is then a matrix-vector product bound by reading the operand once; the 128-wide MMA tiles of
+// K2c would waste 15/16 of their work on padding and keep only NI SMs busy.  A CTA owns 32 matrix
+// rows (4 per warp), lanes stride over k; all candidates share one pass over the operand.
+//   FULL == false: M = L^-1 (row-major, lower);  qpart[cta][c] = sum over the CTA's rows of T^2
+//   FULL == true : M = R^-1 (row-major, symmetric, both triangles); W written in the packed layout
+// r (and W) use the packed layout of K1 with candidate block 0, tile c8 = 0.
+// ---------------------------------------------------------------------------------------------
+template <bool FULL>
+__global__ void __launch_bounds__(256) k_small_mv(const double *M, int npad, int n, const double *rP, int mc,
+                                                  double *qpart, int64_t ldq, double *wP) {
+  __shared__ double red[8][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.x * 32 + warp * 4;
+  double acc[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc[r][c] = 0.0;
+  const int kmax = FULL ? n : min(n, row0 + 4);
+  for (int k = lane; k < kmax; k += 32) {
+    double rv[8];
+    const double *rk = rP + (int64_t)(k >> 3) * 1024 + (k & 7);
+#pragma unroll
+    for (int c = 0; c < 8; c++) rv[c] = c < mc ? rk[c * 8] : 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int row = row0 + r;
+      const double m = (row < n && (FULL || k <= row)) ? M[(int64_t)row * npad + k] : 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c++) acc[r][c] = fma(m, rv[c], acc[r][c]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      double v = acc[r][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[r][c] = v;
+    }
+  if (FULL) {
+    if (lane < 8) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int row = row0 + r;
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) v = (lane == c) ? acc[r][c] : v;
+        wP[(int64_t)(row >> 3) * 1024 + lane * 8 + (row & 7)] = v;
+      }
+    }
+  } else {
+    if (lane < 8) {
+      double q = 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) v = (lane == c) ? acc[r][c] : v;
+        q = fma(v, v, q);
+      }
+      red[warp][lane] = q;
+    }
+    __syncthreads();
+    if (tid < 8) {
+      double q = 0.0;
+      for (int w = 0; w < 8; w++) q += red[w][tid];   // fixed order
+      qpart[(int64_t)blockIdx.x * ldq + tid] = q;
+    }
+  }
+}
+
+// upper triangle := lower triangle (row-major npad x npad), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(1024) k_symmetrize(double *A, int npad) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  t[ty][tx] = A[(int64_t)(bi * 32 + ty) * npad + bj * 32 + tx];
+  __syncthreads();
+  if (bi == bj) {
+    if (tx > ty) A[(int64_t)(bi * 32 + ty) * npad + bj * 32 + tx] = t[tx][ty];
+  } else {
+    A[(int64_t)(bj * 32 + ty) * npad + bi * 32 + tx] = t[tx][ty];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // acquisition functions (InfillCriteria.py).  Returns the value and the coefficients A, B of
 //   f_dx = A * yhat_dx + B * sd_dx      (yhat already sign-flipped when maximising)
 // ---------------------------------------------------------------------------------------------
@@ -872,6 +963,18 @@ cudaError_t launch_trmm(const TrmmParams &p, int sm_count, cudaStream_t st) {
   const int grid = items < sm_count ? items : sm_count;
   if (p.full) k_trmm<true><<<grid, 384, TRMM_SMEM, st>>>(p);
   else k_trmm<false><<<grid, 384, TRMM_SMEM, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_small_mv(const double *M, int npad, int n, const double *rP, int mc, int full,
+                            double *qpart, int64_t ldq, double *wP, cudaStream_t st) {
+  if (mc < 1 || mc > 8) return cudaErrorInvalidValue;
+  if (full) k_small_mv<true><<<npad / 32, 256, 0, st>>>(M, npad, n, rP, mc, qpart, ldq, wP);
+  else k_small_mv<false><<<npad / 32, 256, 0, st>>>(M, npad, n, rP, mc, qpart, ldq, wP);
+  return cudaGetLastError();
+}
+cudaError_t launch_symmetrize(double *A, int npad, cudaStream_t st) {
+  k_symmetrize<<<dim3(npad / 32, npad / 32), 1024, 0, st>>>(A, npad);
   return cudaGetLastError();
 }
 

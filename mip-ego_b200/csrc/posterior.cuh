@@ -38,6 +38,13 @@ struct TrmmParams {
 // K2c: T = L^-1 r with fused column sums of squares (or W = R^-1 r), persistent grid.
 cudaError_t launch_trmm(const TrmmParams &p, int sm_count, cudaStream_t st);
 
+// Small-population path (mc <= 8): T = L^-1 r or W = R^-1 r as a matrix-vector product over the
+// row-major operand; qpart gets npad / 32 partial sums per candidate (full == 0).
+cudaError_t launch_small_mv(const double *M, int npad, int n, const double *rP, int mc, int full,
+                            double *qpart, int64_t ldq, double *wP, cudaStream_t st);
+// Fill the upper triangle of a row-major symmetric matrix from its lower triangle.
+cudaError_t launch_symmetrize(double *A, int npad, cudaStream_t st);
+
 struct EpiParams {
   const double *qpart, *meanpart, *ftpart;
   int NI, JS;

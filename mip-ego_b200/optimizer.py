@@ -459,6 +459,27 @@ def batch_argmax_restart(obj_funcs, search_space, h=None, g=None, eval_budget=10
     restarts of criterion 0, then criterion 1, ..."""
     objs = [_Objective(f) for f in obj_funcs]
     crits = [o.crit for o in objs]
+    # Inside the drivers every batch goes through the MMA path, whatever its size: the library's
+    # matrix-vector path for <= 8 candidates rounds differently, and a candidate's value must not
+    # depend on how many other restarts happen to be pending ("lock-step" == sequential, bit for bit).
+    handles = []
+    for c in crits:
+        if c is not None:
+            hd = c._handle()
+            if all(hd is not x for x in handles):
+                handles.append(hd)
+    for hd in handles:
+        hd.set_option("small_path", 0)
+    try:
+        return _batch_argmax_restart(objs, crits, search_space, h, g, eval_budget, n_restart, wait_iter,
+                                     optimizer, logger, mode)
+    finally:
+        for hd in handles:
+            hd.set_option("small_path", 1)
+
+
+def _batch_argmax_restart(objs, crits, search_space, h, g, eval_budget, n_restart, wait_iter, optimizer,
+                          logger, mode):
     if all(c is not None for c in crits) and len({id(c._model) for c in crits}) == 1 and \
             len({(type(c), c.minimize, c._plugin_user()) for c in crits}) == 1:
         # same model / class / plugin: one posterior pass evaluates every parameter set

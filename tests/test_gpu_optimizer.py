@@ -36,15 +36,21 @@ def test_lockstep_bfgs_trajectories_equal_reference_loop():
     np.random.seed(11)
     starts = [sp.sampling(1)[0] for _ in range(R)]
     ref = []
+    # the drivers pin the MMA path for every batch size (optimizer.batch_argmax_restart); so does
+    # this reference loop, otherwise the <= 8-candidate matrix-vector path would round differently
+    gp._handle().set_option("small_path", 0)
     for x0 in starts:
         func = lambda x: tuple(map(lambda v: -1.0 * v, crit(x, return_dx=True)))
         xo, fo, info = fmin_l_bfgs_b(func, x0, pgtol=1e-8, factr=1e6, bounds=np.array(sp.bounds), maxfun=100 * d)
         ref.append((-float(fo), xo.flatten().tolist()))
+    gp._handle().set_option("small_path", 1)
     best = max(ref, key=lambda r: r[0])
     np.random.seed(11)
     xopt, fopt = mb.argmax_restart(functools.partial(crit, return_dx=True), sp, eval_budget=100 * d,
                                    n_restart=R, wait_iter=R, optimizer="BFGS")
     assert fopt == best[0] and xopt == best[1]
+    # a single-point call outside the drivers takes the matrix-vector path: same value to rounding
+    assert fopt == pytest.approx(crit(np.array(xopt)), rel=1e-11)
     # the reference's own control flow (shared budget, wait_iter early stop)
     np.random.seed(11)
     xs, fs = mb.argmax_restart(functools.partial(crit, return_dx=True), sp, eval_budget=100 * d,
@@ -67,7 +73,7 @@ def test_parallel_bo_criteria_share_posterior_pass():
     for i, fn in enumerate(fns):
         xo, fo = mb.argmax_restart(fn, sp, eval_budget=300, n_restart=5, optimizer="BFGS")
         assert fo == fs[i] and xo == xs[i]
-        assert fs[i] == pytest.approx(crits[i](np.array(xs[i])), rel=1e-12)
+        assert fs[i] == pytest.approx(crits[i](np.array(xs[i])), rel=1e-10)
 
 
 def test_mies_and_cma_on_cuda_criterion():
@@ -84,12 +90,12 @@ def test_mies_and_cma_on_cuda_criterion():
     np.random.seed(1)
     xo, fo = mb.argmax_restart(functools.partial(crit, return_dx=False), sp, eval_budget=500 * d,
                                n_restart=10, optimizer="MIES")
-    assert np.all(np.abs(xo) <= 5) and fo == pytest.approx(crit(np.array(xo)), rel=1e-12)
+    assert np.all(np.abs(xo) <= 5) and fo == pytest.approx(crit(np.array(xo)), rel=1e-10)
     assert fo >= 0.5 * v.max()
     xb, fb, info = opt.cma_es_argmax(lambda Z: crit(Z), np.array(sp.bounds), lambda_=4096,
                                      max_eval=4096 * 40, seed=3,
                                      topk_fn=lambda Z, k: tuple(a[0] for a in crit.topk(Z, k=k)))
-    assert fb == pytest.approx(crit(xb), rel=1e-12)
+    assert fb == pytest.approx(crit(xb), rel=1e-10)
     assert fb >= 0.9 * v.max(), (fb, v.max(), info)
 
 
