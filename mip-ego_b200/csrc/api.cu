@@ -743,8 +743,11 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     { KTimer t(h, st, 0); MGP_CUDA(h, launch_rgen(rp, h->corr, h->sm_count, st)); }
     h->launches++;
     const bool small = mc <= 8 && !h->no_small_path;   // matrix-vector path for tiny populations
+    const bool mean_only = !q.want_dx && !acq && !q.d_mse;   // predict(eval_MSE=False): K1 alone gives r . gamma
     if (!q.want_dx) {
-      if (small) {
+      if (mean_only) {
+        // no triangular product needed
+      } else if (small) {
         KTimer t(h, st, 1);
         MGP_CUDA(h, launch_small_mv(P<double>(h->dMinv), h->npad, h->n, P<double>(h->drP), (int)mc, 0,
                                     P<double>(h->dqpart), ldp, nullptr, st));
@@ -757,7 +760,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       }
       EpiParams ep;
       ep.qpart = P<double>(h->dqpart); ep.meanpart = P<double>(h->dmeanpart); ep.ftpart = P<double>(h->dftpart);
-      ep.NI = small ? h->npad / 32 : h->NI; ep.JS = JS; ep.ld = ldp; ep.mc = mc;
+      ep.NI = mean_only ? 0 : (small ? h->npad / 32 : h->NI); ep.JS = JS; ep.ld = ldp; ep.mc = mc;
       ep.beta = h->beta; ep.sigma2 = h->sigma2; ep.G = h->G; ep.ordinary = ordinary;
       ep.p = h->p; ep.PT = PT; ep.d = h->d; ep.trend_est = h->trend_est ? 1 : 0;
       ep.Xs = q.d_Xs + c0 * h->d; ep.betav = P<double>(h->dbetav); ep.Cinv = P<double>(h->dCinv);

@@ -166,3 +166,16 @@ def test_batch_groups_on_recycled_memory():
         for groups in (0, 1):
             r = small(groups)
             assert np.array_equal(r[0], ref[0]) and np.array_equal(r[1], ref[1]) and np.all(r[2] == 0)
+
+
+def test_every_entry_point_is_repeatable_on_recycled_memory():
+    """tools/determinism_stress.py: likelihood (all modes / trends), fit, predict, acquisition,
+    gradients, top-k, the <= 8-candidate path -- bitwise identical on fresh handles after large
+    allocations have been freed (stale device memory, different kernel timing)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "determinism_stress.py")
+    spec = importlib.util.spec_from_file_location("determinism_stress", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(reps=2, verbose=True) == 0
