@@ -641,7 +641,7 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
 
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
-                         const LookAhead *la) {
+                         const LookAhead *la, bool clean_upper) {
   // Two-level right-looking blocked Cholesky.  Tiles are 128 wide; PB tiles form a panel.  Inside a
   // panel every tile column is factored (diagonal block, TRSM through the explicit inverse of the
   // diagonal block) and applied to the remaining columns OF THE PANEL only (k = 128); the matrix
@@ -649,8 +649,12 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
   // trailing tile PB times less often than a tile-by-tile right-looking sweep.
   (void)la;
   const int NI = npad / 128, PB = 4;
-  for (int b = 0; b < batch; b++)
-    LA_TRY(cudaMemsetAsync(L + b * sA, 0, sizeof(double) * (size_t)npad * npad, st));
+  // Nothing on the likelihood path reads the tiles above the block diagonal of L (or of L^-1), so
+  // they are only zeroed when the factor is going to be exported (fitted state): for a batch of
+  // likelihood evaluations that saves writing 2 x npad^2 doubles per evaluation.
+  if (clean_upper)
+    for (int b = 0; b < batch; b++)
+      LA_TRY(cudaMemsetAsync(L + b * sA, 0, sizeof(double) * (size_t)npad * npad, st));
   for (int k0 = 0; k0 < NI; k0 += PB) {
     const int k1 = k0 + PB < NI ? k0 + PB : NI;
     for (int kb = k0; kb < k1; kb++) {
@@ -705,10 +709,11 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
 
 cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, int64_t sMat,
                           const double *linv, int64_t sInv, int batch, cudaStream_t st,
-                          int64_t *launches) {
+                          int64_t *launches, bool clean_upper) {
   const int NI = npad / 128;
-  for (int b = 0; b < batch; b++)
-    LA_TRY(cudaMemsetAsync(Minv + b * sMat, 0, sizeof(double) * (size_t)npad * npad, st));
+  if (clean_upper)
+    for (int b = 0; b < batch; b++)
+      LA_TRY(cudaMemsetAsync(Minv + b * sMat, 0, sizeof(double) * (size_t)npad * npad, st));
   k_scatter_diag<<<dim3(NI, batch), 256, 0, st>>>(linv, sInv, Minv, npad, sMat);
   LA_TRY(cudaGetLastError());
   (*launches)++;

@@ -42,11 +42,11 @@ struct LookAhead {      // optional side stream for overlapping the serial diago
 };
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
-                         const LookAhead *la);
+                         const LookAhead *la, bool clean_upper);
 // Minv = L^-1 given L and the diagonal-block inverses; T is scratch (npad x npad per matrix).
 cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, int64_t sMat,
                           const double *linv, int64_t sInv, int batch, cudaStream_t st,
-                          int64_t *launches);
+                          int64_t *launches, bool clean_upper);
 // Rinv(lower tiles) = Minv^T Minv.
 cudaError_t lauum_blocked(const double *Minv, double *Rinv, int npad, int64_t sMat, int batch,
                           cudaStream_t st, int64_t *launches);

@@ -80,20 +80,33 @@ __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int np
   double *Rb = R + b * sR;
   const int c = tid & 127;
   const int gk = bj * 128 + c;
-  for (int r = tid >> 7; r < 128; r += 2) {
-    const int gj = bi * 128 + r;
-    double v;
-    if (gj == gk) v = 1.0;
-    else if (gj >= n || gk >= n) v = 0.0;
-    else {
-      double S = 0.0;
-      for (int i = 0; i < dpad; i++) {
-        const double df = xjT[i * XP + r] - xkT[i * XP + c];
-        S = CORR == 2 ? fma(th[i], fabs(df), S) : fma(th[i] * df, df, S);
+  // a thread owns one column and walks its 64 rows four at a time: per feature one load of the
+  // column's coordinate and two 16-byte broadcast loads of four row coordinates feed four pairs
+  for (int q = 0; q < 16; q++) {
+    const int r = (tid >> 7) * 64 + 4 * q;
+    double S[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < dpad; i++) {
+      const double xk = xkT[i * XP + c], t = th[i];
+      const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
+      const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
+      const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
+      if (CORR == 2) {
+        S[0] = fma(t, fabs(d0), S[0]); S[1] = fma(t, fabs(d1), S[1]);
+        S[2] = fma(t, fabs(d2), S[2]); S[3] = fma(t, fabs(d3), S[3]);
+      } else {
+        S[0] = fma(t * d0, d0, S[0]); S[1] = fma(t * d1, d1, S[1]);
+        S[2] = fma(t * d2, d2, S[2]); S[3] = fma(t * d3, d3, S[3]);
       }
-      v = scale * corr_from_S<CORR>(S);
     }
-    Rb[(int64_t)gj * npad + gk] = v;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int gj = bi * 128 + r + u;
+      double v;
+      if (gj == gk) v = 1.0;
+      else if (gj >= n || gk >= n) v = 0.0;
+      else v = scale * corr_from_S<CORR>(S[u]);
+      Rb[(int64_t)gj * npad + gk] = v;
+    }
   }
 }
 
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(256) k_nll_scalars(const double *L, int npad, 
 //   W_jk = gamma_j gamma_k / s + coefA a_j a_k - Rinv_jk     (a = L^-T Ft; coefA != 0 only for REML)
 // acc[i] += W_jk dR0_jk/dtheta_i (j > k);  acc[DP] += 2 W_jk R0_jk (j > k);  acc[DP+1] += W_jj.
 template <int CORR, int DP>
-__global__ void __launch_bounds__(256) k_nll_grad(const double *Xc, int n, int npad,
+__global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, int npad,
                                                   const double *params, int n_par, int mode,
                                                   const double *Rinv, int64_t sR,
                                                   const double *gamma, const double *avec, int64_t sv,
@@ -234,46 +247,85 @@ __global__ void __launch_bounds__(256) k_nll_grad(const double *Xc, int n, int n
   const int c = tid & 127, gk = bj * 128 + c;
   const double gk_v = gk < n ? gm[gk] : 0.0;
   const double ak_v = (coefa != 0.0 && gk < n) ? coefa * av[gk] : 0.0;
-  for (int r = tid >> 7; r < 128; r += 2) {
-    const int gj = bi * 128 + r;
-    if (gj >= n || gk >= n || gj < gk) continue;
-    const double rinv = Rb[(int64_t)gj * npad + gk];
-    double W = gm[gj] * gk_v / s_div - rinv;
-    if (coefa != 0.0) {
-      if (p == 1) {
-        W = fma(av[gj], ak_v, W);
-      } else {   // v (L^-T Q)(L^-T Q)^T: a p-term dot product per pair
-        const double *bj_ = Bhat + ((int64_t)b * npad + gj) * MGP_TP, *bk_ = Bhat + ((int64_t)b * npad + gk) * MGP_TP;
-        double t = 0.0;
-        for (int q = 0; q < p; q++) t = fma(bj_[q], bk_[q], t);
-        W = fma(coefa, t, W);
+  // four rows per thread and two passes over the features: pass 1 accumulates S for the four
+  // pairs, the pair weights W * fac follow, pass 2 regenerates the squared differences and adds
+  // their weighted sum to the per-feature accumulators (no per-pair array of differences)
+  for (int q = 0; q < 16; q++) {
+    const int r = (tid >> 7) * 64 + 4 * q;
+    if (bi * 128 + r + 3 < gk || bi * 128 + r >= n || gk >= n) continue;   // nothing on or below the diagonal
+    // issue the global loads of the pair weights first: they complete under pass 1
+    double rinv4[4], gj4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int gj = bi * 128 + r + u;
+      const bool on = gj < n && gj >= gk;
+      rinv4[u] = on ? __ldg(Rb + (int64_t)gj * npad + gk) : 0.0;
+      gj4[u] = on ? __ldg(gm + gj) : 0.0;
+    }
+    double S[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+    for (int i = 0; i < DP; i++) {
+      const double xk = xkT[i * XP + c], t = th[i];
+      const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
+      const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
+      const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
+      if (CORR == 2) {
+        S[0] = fma(t, fabs(d0), S[0]); S[1] = fma(t, fabs(d1), S[1]);
+        S[2] = fma(t, fabs(d2), S[2]); S[3] = fma(t, fabs(d3), S[3]);
+      } else {
+        S[0] = fma(t * d0, d0, S[0]); S[1] = fma(t * d1, d1, S[1]);
+        S[2] = fma(t * d2, d2, S[2]); S[3] = fma(t * d3, d3, S[3]);
       }
     }
-    if (gj == gk) {
-      acc[DP + 1] += W;  // R0_jj = 1: sigma2 / noise-variance derivatives only
-      continue;
+    double wf[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int gj = bi * 128 + r + u;
+      wf[u] = 0.0;
+      if (gj >= n || gj < gk) continue;
+      double W = gj4[u] * gk_v / s_div - rinv4[u];
+      if (coefa != 0.0) {
+        if (p == 1) {
+          W = fma(av[gj], ak_v, W);
+        } else {   // v (L^-T Q)(L^-T Q)^T: a p-term dot product per pair
+          const double *bj_ = Bhat + ((int64_t)b * npad + gj) * MGP_TP, *bk_ = Bhat + ((int64_t)b * npad + gk) * MGP_TP;
+          double t = 0.0;
+          for (int k = 0; k < p; k++) t = fma(bj_[k], bk_[k], t);
+          W = fma(coefa, t, W);
+        }
+      }
+      if (gj == gk) {
+        acc[DP + 1] += W;  // R0_jj = 1: sigma2 / noise-variance derivatives only
+        continue;
+      }
+      double R0, fac;
+      if (CORR != 1) {
+        R0 = exp(-S[u]);
+        fac = -R0;  // dR0/dtheta_i = -df_i^2 R0 (gpr.py:634) | -|df_i| R0 (gpr.py:648)
+      } else {
+        const double sq = MGP_SQRT3 * sqrt(S[u]), e = exp(-sq);
+        R0 = (1.0 + sq) * e;
+        fac = -1.5 * e;  // dR0/dtheta_i = -(3/2) df_i^2 e^{-sqrt3 D}   gpr.py:643
+      }
+      wf[u] = W * fac;
+      acc[DP] = fma(2.0 * W, R0, acc[DP]);  // both (j,k) and (k,j)
     }
-    double df2[DP];
-    double S = 0.0;
 #pragma unroll
     for (int i = 0; i < DP; i++) {
-      const double df = xjT[i * XP + r] - xkT[i * XP + c];
-      df2[i] = CORR == 2 ? fabs(df) : df * df;   // abs-exp: dR0/dtheta_i = -|df_i| R0  (gpr.py:648)
-      S = fma(th[i], df2[i], S);
+      const double xk = xkT[i * XP + c];
+      const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
+      const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
+      const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
+      double t;
+      if (CORR == 2) {
+        t = wf[0] * fabs(d0);
+        t = fma(wf[1], fabs(d1), t); t = fma(wf[2], fabs(d2), t); t = fma(wf[3], fabs(d3), t);
+      } else {
+        t = (wf[0] * d0) * d0;
+        t = fma(wf[1] * d1, d1, t); t = fma(wf[2] * d2, d2, t); t = fma(wf[3] * d3, d3, t);
+      }
+      acc[i] += t;
     }
-    double R0, fac;
-    if (CORR != 1) {
-      R0 = exp(-S);
-      fac = -R0;  // dR0/dtheta_i = -df_i^2 R0            gpr.py:634
-    } else {
-      const double sq = MGP_SQRT3 * sqrt(S), e = exp(-sq);
-      R0 = (1.0 + sq) * e;
-      fac = -1.5 * e;  // dR0/dtheta_i = -(3/2) df_i^2 e^{-sqrt3 D}   gpr.py:643
-    }
-    const double wf = W * fac;
-#pragma unroll
-    for (int i = 0; i < DP; i++) acc[i] = fma(wf, df2[i], acc[i]);
-    acc[DP] = fma(2.0 * W, R0, acc[DP]);  // both (j,k) and (k,j)
   }
 #pragma unroll
   for (int i = 0; i <= DP + 1; i++) {
@@ -629,8 +681,10 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
     (*launches)++;
   }
   if (!w.have_L)
-    NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches, w.la));
-  NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches));
+    NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches, w.la,
+                        w.want_bhat != 0));
+  NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches,
+                       w.want_bhat != 0));
   double *Yt = w.Yt, *Ft = w.Ft, *rho = w.rho, *gamma = w.gamma;
   const bool general = w.p > 1 && w.ordinary;   // p basis functions with estimated coefficients
   NL_TRY(launch_trmv(w.M, npad, sM, w.y, 0, Yt, npad, n, 0, B, st));

@@ -25,7 +25,8 @@ struct NllWork {
   double *Bhat;          // B x npad x MGP_TP : L^-T (Ft C^-T), C = chol(Ft^T Ft)  (REML gradient; fitted-state operand)
   double *tws;           // B x trend_ws_doubles(): beta | Ainv | C | scratch
   double logdetFF;       // log det(F^T F) of the raw basis (REML, gpr.py:736)
-  int want_bhat;         // build Bhat even without a gradient (mgp_finalize_fit)
+  int want_bhat;         // fitted-state run (mgp_finalize_fit / mgp_set_state): build Bhat even without a
+                         // gradient and zero the unused upper tiles of L and L^-1 (they get exported)
   double *scal;          // B x nll_scal_doubles()
   double *gpart;         // B x ntiles x (dpad + 2)
   int *status;           // B
