@@ -798,6 +798,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       gp.p = h->p; gp.PT = PT; gp.trend_est = h->trend_est ? 1 : 0;
       gp.betav = P<double>(h->dbetav); gp.Cinv = P<double>(h->dCinv); gp.tpart = P<double>(h->dtpart);
       gp.Bhat = P<double>(h->dBhat);
+      gp.wide = small ? 1 : 0;
       gp.out_mean = q.d_mean ? q.d_mean + c0 : nullptr;
       gp.out_mse = q.d_mse ? q.d_mse + c0 : nullptr;
       gp.out_mean_dx = q.d_mean_dx ? q.d_mean_dx + c0 * h->d : nullptr;

@@ -723,14 +723,17 @@ __global__ void __launch_bounds__(1024) k_topk_merge(const double *vals, const i
 // One warp per candidate; lanes stride over the training points; D = x* - x_j component-wise.
 // A Matern candidate coinciding with a training point zeroes the whole Jacobian (gpr.py:588-615).
 // ---------------------------------------------------------------------------------------------
-template <int CORR, int DP>
+// WIDE == false: one warp per candidate (8 candidates per CTA).  WIDE == true (populations of at
+// most 8, the one-point-per-call pattern): one CTA per candidate, its 8 warps split the training
+// points and combine their partial sums through shared memory in a fixed order.
+template <int CORR, int DP, bool WIDE>
 __global__ void __launch_bounds__(256) k_grad(GradParams p) {
   const int tid = threadIdx.x, lane = tid & 31, cc = tid >> 5;
-  const int64_t c8g = blockIdx.x;            // global 8-candidate group
-  const int cb = (int)(c8g >> 4), c8 = (int)(c8g & 15);
-  const int64_t c = c8g * 8 + cc;
+  const int64_t c = WIDE ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * 8 + cc;
+  const int cb = (int)(c >> 7), c8 = (int)((c >> 3) & 15), crow = (int)(c & 7);
   __shared__ double s_u[8][MGP_PMAX];    // per warp: u = Bhat^T r - Cinv f      (p > 1, estimated)
   __shared__ double s_k[8][MGP_PMAX];    // per warp: kappa = C^-T u = (Ft^T Ft)^-1 (Ft^T rt - f)
+  __shared__ double s_red[WIDE ? 8 : 1][2 * DP + 2];
   if (c >= p.mc) return;
   const bool gen = p.p > 1 && p.trend_est;
   double md = 0.0, ft = 0.0;
@@ -768,9 +771,9 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
   }
   double q = 0.0;
   int coincide = 0;
-  const double *rbase = p.rP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + cc * 8;
-  const double *wbase = p.wP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + cc * 8;
-  for (int j = lane; j < p.n; j += 32) {
+  const double *rbase = p.rP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + crow * 8;
+  const double *wbase = p.wP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + crow * 8;
+  for (int j = WIDE ? tid : lane; j < p.n; j += WIDE ? 256 : 32) {
     const int64_t o = (int64_t)(j >> 3) * 1024 + (j & 7);
     const double r = rbase[o], w = wbase[o];
     q = fma(r, w, q);
@@ -801,6 +804,43 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
     for (int i = 0; i < DP; i++) {
       am[i] = fma(cm, df[i], am[i]);
       as[i] = fma(cs, df[i], as[i]);
+    }
+  }
+  if (WIDE) {
+    // warp sums -> shared memory -> every warp's lane 0 holds the block total (fixed order), the
+    // other lanes hold zero, so that the warp-level reductions below return the totals
+    double cf = (double)coincide;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+      cf += __shfl_xor_sync(0xffffffffu, cf, o);
+    }
+#pragma unroll
+    for (int i = 0; i < DP; i++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        am[i] += __shfl_xor_sync(0xffffffffu, am[i], o);
+        as[i] += __shfl_xor_sync(0xffffffffu, as[i], o);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < DP; i++) { s_red[cc][2 * i] = am[i]; s_red[cc][2 * i + 1] = as[i]; }
+      s_red[cc][2 * DP] = q;
+      s_red[cc][2 * DP + 1] = cf;
+    }
+    __syncthreads();
+    if (cc != 0) return;           // warp 0 finishes the candidate
+    double tq = 0.0, tc = 0.0;
+    for (int w = 0; w < 8; w++) { tq += s_red[w][2 * DP]; tc += s_red[w][2 * DP + 1]; }
+    q = lane == 0 ? tq : 0.0;
+    coincide = tc > 0.0 ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < DP; i++) {
+      double ta = 0.0, tb = 0.0;
+      for (int w = 0; w < 8; w++) { ta += s_red[w][2 * i]; tb += s_red[w][2 * i + 1]; }
+      am[i] = lane == 0 ? ta : 0.0;
+      as[i] = lane == 0 ? tb : 0.0;
     }
   }
 #pragma unroll
@@ -876,9 +916,11 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
 
 template <int CORR>
 static cudaError_t grad_dispatch(const GradParams &p, cudaStream_t st) {
-  const unsigned grid = (unsigned)((p.mc + 7) / 8);
+  const bool wide = p.wide != 0 && p.mc <= 8;
+  const unsigned grid = wide ? (unsigned)p.mc : (unsigned)((p.mc + 7) / 8);
   switch (p.dpad) {
-#define GD(D) case D: k_grad<CORR, D><<<grid, 256, 0, st>>>(p); break;
+#define GD(D) case D: if (wide) k_grad<CORR, D, true><<<grid, 256, 0, st>>>(p); \
+                      else k_grad<CORR, D, false><<<grid, 256, 0, st>>>(p); break;
     GD(4) GD(8) GD(12) GD(16) GD(20) GD(24) GD(28) GD(32) GD(36) GD(40) GD(44) GD(48) GD(52) GD(56) GD(60) GD(64)
 #undef GD
     default: return cudaErrorInvalidValue;

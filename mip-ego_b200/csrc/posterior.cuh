@@ -99,6 +99,7 @@ struct GradParams {
   // non-constant trend (see EpiParams)
   int p, PT, trend_est;
   const double *betav, *Cinv, *tpart, *Bhat;
+  int wide;   // one CTA per candidate (small-population path)
 };
 // K5: gradient contraction + acquisition-with-gradient epilogue.
 cudaError_t launch_grad(const GradParams &p, int corr, cudaStream_t st);
