@@ -7,8 +7,8 @@ Supported configuration: corr in {squared_exponential, mater
 absolute_exponential},
 `constant_trend` mean (beta given = simple kriging, beta=None = ordinary kriging),
 likelihood in {'concentrated', 'restricted'}, estimation modes noiseless (nugget falsy), noisy
-(nugget > 0) and noise_estim, optimizer='BFGS'.  Anything else raises NotImplementedError: there
-is no CPU fallback.
+(nugget > 0) and noise_estim, optimizer in {'BFGS', 'CMA'}.  Anything else raises
+NotImplementedError: there is no CPU fallback.
 """
 import ctypes
 
@@ -39,7 +39,7 @@ def _check_array(X, name="X"):
 
 
 class GaussianProcess(object):
-    _optimizer_types = ["BFGS"]
+    _optimizer_types = ["BFGS", "CMA"]
     _correlation_types = ("squared_exponential", "matern", "absolute_exponential")
     _likelihood_functions = ["concentrated", "restricted"]
 
@@ -272,6 +272,8 @@ class GaussianProcess(object):
             llf, grad, _ = self.log_likelihood_batch(10.0 ** P, eval_grad=True)
             return -llf, -grad
 
+        if solve is None and self.optimizer == "CMA":
+            solve = self._solve_cma
         if solve is None:
             solve = lambda *a: multistart_lbfgsb(*a, mode=self.restart_mode)  # noqa: E731
         param_opt, llf_opt, n_evals, infos = solve(batch_fn, np.array(starts), log10bounds, eval_budget,
@@ -284,6 +286,28 @@ class GaussianProcess(object):
         for k, name in enumerate(par_list[1:]):
             param[name] = optimal_param[n_theta + k:n_theta + k + 1]
         return param, llf
+
+    def _solve_cma(self, batch_fn, starts, log10bounds, eval_budget, wait_iter):
+        """optimizer='CMA' (gpr.py:1066-1085): derivative-free search of the likelihood in the
+        log10 box from the first start point, sigma0 = 0.25 x the box width, `eval_budget`
+        evaluations.  The reference runs a (1+1)-Cholesky-CMA-ES, one likelihood per step; here a
+        (mu/mu_w, lambda)-CMA-ES evaluates its whole population in one batched likelihood launch
+        sequence (lambda = 4 + 3 ln n_par rounded up to a multiple of 8)."""
+        from .optimizer import cma_es_argmax
+        n_par = starts.shape[1]
+        lam = int(8 * np.ceil((4 + 3 * np.log(n_par)) / 8.0))
+
+        def values(P):
+            llf, _, _ = self.log_likelihood_batch(10.0 ** P, eval_grad=False)
+            return np.where(np.isfinite(llf), llf, -1e300)
+        x, f, info = cma_es_argmax(values, log10bounds, lambda_=lam, max_eval=max(lam, eval_budget),
+                                   sigma0=0.25, x0=starts[0],
+                                   seed=np.random.randint(0, 2 ** 31 - 1))
+        f0 = values(starts[:1])[0]
+        if f0 >= f:
+            x, f = starts[0].copy(), f0
+            info["funcalls"] += 1
+        return x, -f, info["funcalls"], [info]
 
     def _finalize(self, par):
         """mgp_finalize_fit: the env-harvesting final likelihood call (gpr.py:1087-1101)."""

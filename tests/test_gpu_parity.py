@@ -671,3 +671,34 @@ def test_small_population_path(kind, n, d):
         rv, rdx = O.acquisition(st, sub, "EI", None, plugin, True, return_dx=True)
         assert np.max(np.abs(v - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())) < 1e-7
         assert np.max(np.abs(dx - rdx)) < 1e-7 * np.abs(rdx).max()
+
+
+def test_fit_with_cma_optimizer():
+    """optimizer='CMA' (gpr.py:1066-1085; test/test_BO.py:133-165): a derivative-free MLE whose
+    populations are evaluated by the batched likelihood; it must reach a likelihood at least as good
+    as the start and produce the oracle's model for the parameters it returns."""
+    mb, O = _mods()
+    rng = np.random.default_rng(21)
+    n, d = 90, 3
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    y = (y - y.mean()) / y.std()
+    np.random.seed(5)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="matern", theta0=[0.05] * d,
+                            thetaL=[1e-4] * d, thetaU=[10.0] * d, nugget=1e-6, optimizer="CMA",
+                            eval_budget=400)
+    gp.fit(X, y)
+    par = np.concatenate([np.ravel(v) for v in gp.par.values()])
+    llf = float(np.ravel(gp.log_likelihood_)[0])
+    rl = O.log_likelihood_concentrated(X, y, par, "matern", True, 0.0, "noisy", 1e-6)
+    assert abs(llf - rl) <= 1e-8 * abs(rl)
+    np.random.seed(5)
+    bf = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="matern", theta0=[0.05] * d,
+                            thetaL=[1e-4] * d, thetaU=[10.0] * d, nugget=1e-6, optimizer="BFGS",
+                            random_start=1).fit(X, y)
+    start = O.log_likelihood_concentrated(X, y, np.r_[[0.05] * d, par[-1]], "matern", True, 0.0, "noisy", 1e-6)
+    assert llf >= start - 1e-9 and gp.eval_count <= 400 + 16
+    assert llf >= float(np.ravel(bf.log_likelihood_)[0]) - 25.0     # same basin or better, loosely
+    with pytest.raises(ValueError):
+        mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), theta0=[0.1] * d, thetaL=[1e-4] * d,
+                           thetaU=[10.0] * d, optimizer="SGD")
