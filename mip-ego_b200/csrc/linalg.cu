@@ -331,6 +331,26 @@ __device__ __forceinline__ void warp_trtri32(const double *D, double *X, double 
 
 // S holds L (lower, 128x128, stride DS), Xd the four 32x32 diagonal inverses.  On return S holds
 // L^-1 (lower part; the strictly upper part is unspecified).
+// 4x4 register patch of a small shared-memory matrix product: acc[u][v] += sum_k A[u][k] B[k][v].
+// A rows are (r0 + u) * lda + k.  BT: B given row-wise as (c0 + v) * ldb + k, else as k * ldb + c0 + v.
+// Eight loads feed sixteen FMAs (the one-output-per-thread loops this replaces needed two per FMA).
+template <bool BT>
+__device__ __forceinline__ void patch4x4(double (&acc)[4][4], const double *A, int lda, const double *B,
+                                         int ldb, int k0, int k1) {
+#pragma unroll 4
+  for (int k = k0; k < k1; k++) {
+    double a[4], bq[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) a[u] = A[u * lda + k];
+#pragma unroll
+    for (int v = 0; v < 4; v++) bq[v] = BT ? B[v * ldb + k] : B[k * ldb + v];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], bq[v], acc[u][v]);
+  }
+}
+
 __device__ void diag_block_inverse(double *S, const double *Xd, int tid) {
   for (int idx = tid; idx < 4 * 32 * 32; idx += DIAG_THREADS) {
     const int s = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
@@ -338,55 +358,49 @@ __device__ void diag_block_inverse(double *S, const double *Xd, int tid) {
   }
   __syncthreads();
   for (int i = 1; i < 4; i++) {
-    // T_ij = sum_{k=j}^{i-1} L_ik X_kj for all j < i, from the untouched L blocks of block row i
-    double t[3][2];
+    // block row i: 32 rows x 32 i columns = 8 x 8 i patches, one per thread
+    const int npc = 8 * i;
+    const bool on = tid < 8 * npc;
+    const int pr = tid / npc, pc = tid - pr * npc;
+    const int r0 = 32 * i + 4 * pr, c0 = 4 * pc, j = c0 >> 5;
+    double acc[4][4];
+    // T_ij = sum_{k=j}^{i-1} L_ik X_kj, from the untouched L blocks of block row i
 #pragma unroll
-    for (int j = 0; j < 3; j++)
+    for (int u = 0; u < 4; u++)
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        t[j][u] = 0.0;
-        if (j < i) {
-          const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
-          double acc = 0.0;
-          for (int m = 32 * j; m < 32 * i; m++)
-            acc = fma(S[(32 * i + r) * DS + m], S[m * DS + 32 * j + c], acc);
-          t[j][u] = acc;
-        }
-      }
+      for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+    if (on) patch4x4<false>(acc, S + r0 * DS, DS, S + c0, DS, 32 * j, 32 * i);
     __syncthreads();
+    if (on) {
 #pragma unroll
-    for (int j = 0; j < 3; j++)
+      for (int u = 0; u < 4; u++)
 #pragma unroll
-      for (int u = 0; u < 2; u++)
-        if (j < i) {
-          const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
-          S[(32 * i + r) * DS + 32 * j + c] = t[j][u];
-        }
+        for (int v = 0; v < 4; v++) S[(r0 + u) * DS + c0 + v] = acc[u][v];
+    }
     __syncthreads();
-    // X_ij = -X_ii T_ij
+    // X_ij = -X_ii T_ij   (X_ii lower triangular: k <= row)
 #pragma unroll
-    for (int j = 0; j < 3; j++)
+    for (int u = 0; u < 4; u++)
 #pragma unroll
-      for (int u = 0; u < 2; u++)
-        if (j < i) {
-          const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
-          double acc = 0.0;
-          for (int q = 0; q <= r; q++)
-            acc = fma(S[(32 * i + r) * DS + 32 * i + q], S[(32 * i + q) * DS + 32 * j + c], acc);
-          t[j][u] = -acc;
-        }
+      for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+    if (on) patch4x4<false>(acc, S + r0 * DS + 32 * i, DS, S + 32 * i * DS + c0, DS, 0, 4 * pr + 4);
     __syncthreads();
+    if (on) {
 #pragma unroll
-    for (int j = 0; j < 3; j++)
+      for (int u = 0; u < 4; u++)
 #pragma unroll
-      for (int u = 0; u < 2; u++)
-        if (j < i) {
-          const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
-          S[(32 * i + r) * DS + 32 * j + c] = t[j][u];
-        }
+        for (int v = 0; v < 4; v++) S[(r0 + u) * DS + c0 + v] = -acc[u][v];
+    }
     __syncthreads();
   }
 }
+
+#ifdef DIAG_PROFILE
+__device__ long long g_diag_clk[16];
+#define DIAG_T(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
+#else
+#define DIAG_T(i)
+#endif
 
 __global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag(double *A, double *Lout, int ld,
                                                               int64_t sA, double *linv,
@@ -396,67 +410,82 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag(double *A, double *
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   const double *Ab = A + b * sA + (int64_t)kb * 128 * ld + kb * 128;
   double *Lb = Lout + b * sA + (int64_t)kb * 128 * ld + kb * 128;
+  DIAG_T(0);
   for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
     S[r * DS + c] = (c <= r) ? Ab[(int64_t)r * ld + c] : 0.0;
   }
   __syncthreads();
+  DIAG_T(1);
   for (int s = 0; s < 4; s++) {
     const int o = 32 * s, nb = 96 - o;   // nb rows below the sub-block
     if (warp == 0) {
       warp_potrf32(S + o * DS + o, col, lane, kb * 128 + o, &status[b]);
       __syncwarp();
+#ifdef DIAG_PROFILE
+      if (s == 0 && lane == 0 && blockIdx.x == 0) g_diag_clk[8] = clock64();
+#endif
       warp_trtri32(S + o * DS + o, Xd + s * 32 * XS, col + 64, lane);
     }
     __syncthreads();
+    if (s == 0) DIAG_T(2);
     if (nb > 0) {
-      // sub-panel P = A[below][o:o+32] D^-T : P[r][c] = sum_{k<=c} A[r][o+k] X[c][k]
+      // sub-panel P = A[below][o:o+32] D^-T : P[r][c] = sum_k A[r][o+k] X[c][k]  (X[c][k] = 0 for k > c)
       const double *X = Xd + s * 32 * XS;
-      double pv[6];
+      {
+        const bool on = tid < (nb / 4) * 8;
+        const int pr = tid >> 3, pc = tid & 7;
+        double acc[4][4];
 #pragma unroll
-      for (int u = 0; u < 6; u++) {
-        const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
-        double acc = 0.0;
-        if (r < nb) {
-          const double *arow = S + (o + 32 + r) * DS + o;
-          for (int k = 0; k <= c; k++) acc = fma(arow[k], X[c * XS + k], acc);
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+        if (on) patch4x4<true>(acc, S + (o + 32 + 4 * pr) * DS + o, DS, X + 4 * pc * XS, XS, 0, 32);
+        __syncthreads();
+        if (on) {
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) S[(o + 32 + 4 * pr + u) * DS + o + 4 * pc + v] = acc[u][v];
         }
-        pv[u] = acc;
+        __syncthreads();
       }
-      __syncthreads();
-#pragma unroll
-      for (int u = 0; u < 6; u++) {
-        const int e = tid + u * DIAG_THREADS, r = e >> 5, c = e & 31;
-        if (r < nb) S[(o + 32 + r) * DS + o + c] = pv[u];
-      }
-      __syncthreads();
       // symmetric update of the remaining rows: A[r][c] -= sum_k P[r][k] P[c][k]  (c <= r)
-      for (int e = tid; e < nb * nb; e += DIAG_THREADS) {
-        const int r = e / nb, c = e - r * nb;
-        if (c > r) continue;
-        const double *pr = S + (o + 32 + r) * DS + o, *pc = S + (o + 32 + c) * DS + o;
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < 32; k += 2) {
-          a0 = fma(pr[k], pc[k], a0);
-          a1 = fma(pr[k + 1], pc[k + 1], a1);
-        }
-        S[(o + 32 + r) * DS + o + 32 + c] -= a0 + a1;
+      const int np = nb / 4;
+      for (int e = tid; e < np * np; e += DIAG_THREADS) {
+        const int pr = e / np, pc = e - pr * np;
+        if (pc > pr) continue;
+        double acc[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+        patch4x4<true>(acc, S + (o + 32 + 4 * pr) * DS + o, DS, S + (o + 32 + 4 * pc) * DS + o, DS, 0, 32);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int v = 0; v < 4; v++)
+            if (4 * pc + v <= 4 * pr + u) S[(o + 32 + 4 * pr + u) * DS + o + 32 + 4 * pc + v] -= acc[u][v];
       }
       __syncthreads();
+      if (s == 0) DIAG_T(3);
     }
   }
+  DIAG_T(4);
   for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
     Lb[(int64_t)r * ld + c] = (c <= r) ? S[r * DS + c] : 0.0;
   }
   __syncthreads();
+  DIAG_T(5);
   diag_block_inverse(S, Xd, tid);
+  DIAG_T(6);
   double *Ib = linv + b * sInv + (int64_t)kb * 128 * 128;
   for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
     Ib[idx] = (c <= r) ? S[r * DS + c] : 0.0;
   }
+  DIAG_T(7);
 }
 
 __global__ void __launch_bounds__(DIAG_THREADS) k_trtri_diag(const double *L, int ld, int64_t sL,

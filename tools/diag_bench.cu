@@ -1,0 +1,58 @@
+// Times the 128x128 diagonal-block Cholesky + inverse kernel (the serial critical path of the blocked
+// factorisation) on a batch of SPD blocks and checks L L^T = A, L^-1 L = I.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../mip-ego_b200/csrc -I../include -o diag_bench diag_bench.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#define DIAG_PROFILE
+#include "../mip-ego_b200/csrc/linalg.cu"
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+int main() {
+  const int batch = 8, n = 128;
+  std::vector<double> A((size_t)batch * n * n);
+  srand(1);
+  for (int b = 0; b < batch; b++) {
+    std::vector<double> G(n * n);
+    for (auto &g : G) g = rand() / (double)RAND_MAX - 0.5;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        double s = i == j ? 1.0 : 0.0;
+        for (int k = 0; k < n; k++) s += 0.05 * G[i * n + k] * G[j * n + k];
+        A[((size_t)b * n + i) * n + j] = s;
+      }
+  }
+  double *dA, *dL, *dI; int *dst;
+  CK(cudaMalloc(&dA, A.size() * 8)); CK(cudaMalloc(&dL, A.size() * 8)); CK(cudaMalloc(&dI, A.size() * 8));
+  CK(cudaMalloc(&dst, batch * sizeof(int))); CK(cudaMemset(dst, 0, batch * sizeof(int)));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice));
+  cudaStream_t st; CK(cudaStreamCreate(&st));
+  for (int i = 0; i < 5; i++) CK(launch_potrf_diag(dA, dL, n, (int64_t)n * n, dI, (int64_t)n * n, 0, dst, batch, st));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int reps = 200;
+  CK(cudaEventRecord(e0, st));
+  for (int i = 0; i < reps; i++) CK(launch_potrf_diag(dA, dL, n, (int64_t)n * n, dI, (int64_t)n * n, 0, dst, batch, st));
+  CK(cudaEventRecord(e1, st)); CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  std::vector<double> L(A.size()), I(A.size());
+  CK(cudaMemcpy(L.data(), dL, L.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(I.data(), dI, I.size() * 8, cudaMemcpyDeviceToHost));
+  double e_chol = 0, e_inv = 0;
+  for (int b = 0; b < batch; b++)
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j <= i; j++) {
+        double s = 0, t = 0;
+        for (int k = 0; k <= j; k++) s += L[((size_t)b * n + i) * n + k] * L[((size_t)b * n + j) * n + k];
+        for (int k = j; k <= i; k++) t += I[((size_t)b * n + i) * n + k] * L[((size_t)b * n + k) * n + j];
+        e_chol = fmax(e_chol, fabs(s - A[((size_t)b * n + i) * n + j]));
+        e_inv = fmax(e_inv, fabs(t - (i == j ? 1.0 : 0.0)));
+      }
+  long long clk[16];
+  CK(cudaMemcpyFromSymbol(clk, g_diag_clk, sizeof(clk)));
+  printf("cycles: load %lld | potrf32 %lld trtri32 %lld | panel+update(s=0) %lld | steps1-3 %lld | storeL %lld | inverse %lld | storeInv %lld | total %lld\n",
+         clk[1] - clk[0], clk[8] - clk[1], clk[2] - clk[8], clk[3] - clk[2], clk[4] - clk[3], clk[5] - clk[4], clk[6] - clk[5], clk[7] - clk[6], clk[7] - clk[0]);
+  printf("{\"potrf_diag_us\": %.2f, \"batch\": %d, \"max_err_LLt\": %.3e, \"max_err_LinvL\": %.3e}\n", ms * 1e3 / reps, batch, e_chol, e_inv);
+  return 0;
+}
