@@ -303,7 +303,7 @@ def run_nll(args, rank, world, local):
 
     out = None
     # an explicit (non-legacy) stream: the legacy default stream implicitly synchronises with other
-    # blocking streams and defeats the library's look-ahead side stream
+    # blocking streams and would serialise the library's concurrent batch-group streams
     work = torch.cuda.Stream(device=dev)
     sampler = ClockSampler(local)
     sampler.start()

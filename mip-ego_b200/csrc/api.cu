@@ -100,14 +100,9 @@ int mgp_create(int device, mgp_t **out_h) {
     return MGP_ECUDA;
   }
   h->sm_count = prop.multiProcessorCount;
-  // the look-ahead stream runs the short serial diagonal factorisations: highest priority, so its
-  // CTAs are placed as soon as an SM frees up under a concurrent trailing update
-  int prio_lo = 0, prio_hi = 0;
-  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return MGP_ECUDA;
   }
@@ -120,7 +115,6 @@ int mgp_create(int device, mgp_t **out_h) {
     cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_la[i], cudaEventDisableTiming);
   }
   *out_h = h;
   return MGP_OK;
@@ -131,7 +125,7 @@ int mgp_destroy(mgp_t *h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   DevBuf *all[] = {&h->dtpart, &h->dXc, &h->dy, &h->dcenter, &h->dtheta, &h->dBop, &h->dan, &h->dL, &h->dMinv,
-                   &h->dTmp, &h->dLinvDiag, &h->dMp, &h->dRinvP, &h->dgamma, &h->davec, &h->dFt,
+                   &h->dTmp, &h->dMp, &h->dRinvP, &h->dgamma, &h->davec, &h->dFt,
                    &h->dYt, &h->drho, &h->dscal, &h->drP, &h->dmeanpart, &h->dftpart, &h->dqpart,
                    &h->dwP, &h->dXs_stage[0], &h->dXs_stage[1], &h->dout_stage[0],
                    &h->dout_stage[1], &h->dtopk_val, &h->dtopk_idx, &h->dtopk_blk, &h->nR, &h->nL, &h->nM, &h->nT,
@@ -139,11 +133,9 @@ int mgp_destroy(mgp_t *h) {
                    &h->dF, &h->dmu, &h->dbetav, &h->dBhat, &h->dCinv, &h->dFtm};
   for (DevBuf *b : all) freebuf(*b);
   for (int i = 0; i < 2; i++) {
-    if (h->hpin[i]) cudaFreeHost(h->hpin[i]);
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
-    if (h->ev_la[i]) cudaEventDestroy(h->ev_la[i]);
   }
   for (int i = 0; i < MGP_NLL_STREAMS; i++) {
     if (h->nll_stream[i]) cudaStreamDestroy(h->nll_stream[i]);
@@ -153,7 +145,6 @@ int mgp_destroy(mgp_t *h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->out_stream) cudaStreamDestroy(h->out_stream);
-  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   delete h;
   return MGP_OK;
 }
@@ -372,7 +363,6 @@ static void fill_work(mgp_handle *h, NllWork &w, int b_off, int B, int cap, int 
   w.gpart = P<double>(h->ngpart) + (size_t)b_off * ntiles * (h->dpad + 2);
   w.status = nll_status_ptr(h, cap) + b_off;
   w.out_llf = d_llf; w.out_grad = d_grad;
-  w.la = nullptr;
   w.p = h->p;
   w.ordinary = h->trend_est;
   w.mu = (h->p > 1 && !h->trend_est) ? P<double>(h->dmu) : nullptr;

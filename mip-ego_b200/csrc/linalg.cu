@@ -670,13 +670,12 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
 
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
-                         const LookAhead *la, bool clean_upper) {
+                         bool clean_upper) {
   // Two-level right-looking blocked Cholesky.  Tiles are 128 wide; PB tiles form a panel.  Inside a
   // panel every tile column is factored (diagonal block, TRSM through the explicit inverse of the
   // diagonal block) and applied to the remaining columns OF THE PANEL only (k = 128); the matrix
   // right of the panel then receives one update with k = PB*128, which reads and writes every
   // trailing tile PB times less often than a tile-by-tile right-looking sweep.
-  (void)la;
   const int NI = npad / 128, PB = 4;
   // Nothing on the likelihood path reads the tiles above the block diagonal of L (or of L^-1), so
   // they are only zeroed when the factor is going to be exported (fitted state): for a batch of

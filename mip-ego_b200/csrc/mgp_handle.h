@@ -32,9 +32,6 @@ struct mgp_handle {
   double kernel_ms[4] = {0, 0, 0, 0};   // rgen, trmm, epilogue/grad, topk
   int64_t kernel_calls[4] = {0, 0, 0, 0};
   int sm_count = 148;
-  cudaStream_t side_stream = nullptr;  // look-ahead stream of the blocked Cholesky
-  cudaEvent_t ev_la[2] = {nullptr, nullptr};
-  LookAhead la = {nullptr, nullptr, nullptr};
 
   // ---- training data -------------------------------------------------------------------
   int n = 0, d = 0, npad = 0, dpad = 0, NI = 0;
@@ -65,7 +62,6 @@ struct mgp_handle {
   DevBuf dL;       // npad x npad row-major lower Cholesky factor
   DevBuf dMinv;    // npad x npad row-major L^-1
   DevBuf dTmp;     // npad x npad scratch
-  DevBuf dLinvDiag;  // NI x 128 x 128 inverses of the diagonal blocks of L
   DevBuf dMp;      // packed lower-triangular L^-1 (posterior A operand)
   DevBuf dRinvP;   // packed full R^-1 (gradient path), built lazily
   bool rinv_ready = false;
@@ -78,8 +74,6 @@ struct mgp_handle {
   DevBuf drP, dmeanpart, dftpart, dqpart, dwP, dtpart;
   DevBuf dXs_stage[2], dout_stage[2];
   DevBuf dtopk_val, dtopk_idx, dtopk_blk;
-  void *hpin[2] = {nullptr, nullptr};
-  size_t hpin_bytes = 0;
   // ---- likelihood workspace --------------------------------------------------------------
   int nll_cap = 0;  // batch capacity of the buffers below
   int nll_groups_opt = 0;  // 0 = default

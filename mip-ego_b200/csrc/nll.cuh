@@ -30,7 +30,6 @@ struct NllWork {
   double *scal;          // B x nll_scal_doubles()
   double *gpart;         // B x ntiles x (dpad + 2)
   int *status;           // B
-  const struct LookAhead *la;  // optional (linalg.cuh)
   double *out_llf;       // device, B (nullable)
   double *out_grad;      // device, B x n_par (nullable unless eval_grad)
 };
