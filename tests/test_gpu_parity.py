@@ -708,3 +708,46 @@ def test_fit_with_cma_optimizer():
     with pytest.raises(ValueError):
         mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), theta0=[0.1] * d, thetaL=[1e-4] * d,
                            thetaU=[10.0] * d, optimizer="SGD")
+
+
+def test_edge_shapes_and_values():
+    """d = 1 and d = 64 (the supported maximum; 65 is rejected), n = 3 / 128 / 129, candidates on
+    training points, far outside the data, non-finite, top-k with k > m and with ties."""
+    mb, O = _mods()
+    rng = np.random.default_rng(17)
+    for n, d in ((3, 1), (128, 1), (129, 2), (200, 64)):
+        X = rng.uniform(-5, 5, (n, d))
+        y = np.sin(X[:, 0]) + 0.1 * (X ** 2).sum(1) / d
+        theta = np.full(d, 0.3 / d)
+        par = np.r_[theta, 0.7]
+        gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="matern", theta0=theta,
+                                thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=1e-6)
+        gp.fit_fixed(X, y, par)
+        st = O.fit_state(X, y, par, "matern", True, 0.0, "noisy", 1e-6)
+        Xs = np.vstack([rng.uniform(-5, 5, (40, d)), X[:2], X[:1] + 1e3, -1e6 * np.ones((1, d))])
+        mean, mse = gp.predict(Xs, eval_MSE=True)
+        rm, rs = O.predict(st, Xs)
+        assert np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3)) < 1e-9, (n, d)
+        assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-7, (n, d)
+        assert np.all(np.isfinite(mean)) and np.all(np.isfinite(mse))
+        ei = mb.EI(model=gp, minimize=True)
+        v, dx = ei(Xs, return_dx=True)
+        rv, rdx = O.acquisition(st, Xs, "EI", None, None, True, return_dx=True)
+        far = np.arange(len(Xs)) >= 42
+        assert np.max(np.abs(v - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max() + 1e-300)) < 1e-6, (n, d)
+        assert np.all(np.isfinite(dx))
+        assert np.max(np.abs(dx[~far] - rdx[~far])) < 1e-5 * (np.abs(rdx[~far]).max() + 1e-300), (n, d)
+        # top-k: k larger than the population, and exact ties resolved towards the smaller index
+        tv, ti = ei.topk(Xs[:5], k=9)
+        assert tv.shape == (1, 5) and sorted(ti[0].tolist()) == [0, 1, 2, 3, 4]
+        dup = np.vstack([Xs[:3], Xs[:3]])
+        tv, ti = ei.topk(dup, k=6)
+        vd = ei(dup)
+        order = np.lexsort((np.arange(6), -vd))
+        assert np.array_equal(ti[0], order)
+        with pytest.raises(ValueError):
+            gp.predict(np.full((2, d), np.nan))
+    with pytest.raises(Exception):
+        X = rng.uniform(-1, 1, (80, 65))
+        mb.GaussianProcess(mean=mb.constant_trend(65, beta=None), theta0=[0.1] * 65, thetaL=[1e-3] * 65,
+                           thetaU=[10.0] * 65).fit_fixed(X, X.sum(1), np.full(65, 0.1))
