@@ -5,8 +5,10 @@ scipy's `fmin_l_bfgs_b` is the reference's own optimiser (gpr.py:1039) and is ke
   * `sequential` mode reproduces the reference loop exactly -- one restart after the other,
     shared evaluation budget, `wait_iter` early stop (gpr.py:1030-1064) -- each objective call
     being a batch-of-1 `mgp_nll_batch`;
-  * `batched` mode runs every restart's L-BFGS-B in its own thread and gathers the pending
-    objective calls of all live restarts into ONE `mgp_nll_batch` call per step ("lock-step").
+  * `batched` mode advances every restart's L-BFGS-B together and gathers the pending objective
+    calls of all live restarts into ONE `mgp_nll_batch` call per step ("lock-step"): scipy's
+    compiled `setulb` routine driven as state machines (_lockstep.py), or, if that private symbol
+    is unavailable, one thread per restart around the public `fmin_l_bfgs_b`.
     Each trajectory is bit-for-bit what scipy would produce alone given the same (f, g), but all
     restarts run to their own convergence (the reference may stop early on budget/wait_iter),
     so the result is at least as good as the reference's.
@@ -97,6 +99,19 @@ def multistart_lbfgsb(batch_fn, starts, log10bounds, eval_budget, wait_iter, mod
             if budget <= 0 or wait >= wait_iter:
                 break
         return best_p, best_f, n_evals[0], infos
+
+    from . import _lockstep
+    if _lockstep.available():
+        # thread-free engine: scipy's own setulb driven as R state machines (bit-identical to
+        # fmin_l_bfgs_b, verified at first use), one batched likelihood call per step
+        out, _ = _lockstep.run(batch_fn, starts, log10bounds, eval_budget)
+        best = None
+        for wid in range(R):
+            p, f, info = out[wid]
+            n_evals[0] += info["funcalls"]
+            if best is None or f <= best[1]:
+                best = (p, f)
+        return best[0], best[1], n_evals[0], [o[2] for o in out]
 
     ls = _LockStep(batch_fn, R)
     out = [None] * R

@@ -4,10 +4,11 @@ Drop-in for `mipego.optimizer.utils.argmax_restart` (optimizer/utils.py:8-87) wi
 signature and return value, plus the batched front-ends SURVEY section 8f ranks next (N1, N2):
 
   * `argmax_restart(..., optimizer='BFGS')` -- the reference runs its `n_restart` L-BFGS-B restarts
-    one after the other, one candidate per criterion call (optimizer/utils.py:25-52).  Here every
-    restart runs scipy's unmodified `fmin_l_bfgs_b` in its own thread and the pending
-    (value, gradient) requests of all live restarts are served by ONE batched criterion call per
-    step ("lock-step").  A candidate's result does not depend on what else is in the batch, so
+    one after the other, one candidate per criterion call (optimizer/utils.py:25-52).  Here all
+    restarts advance together -- scipy's own compiled L-BFGS-B routine driven as state machines
+    (_lockstep.py; verified bit-identical to `fmin_l_bfgs_b` at first use, with a thread-per-restart
+    fallback) -- and the pending (value, gradient) requests of all live restarts are served by ONE
+    batched criterion call per step ("lock-step").  A candidate's result does not depend on what else is in the batch, so
     each trajectory is bit-for-bit what the sequential loop would produce from the same start.
   * `argmax_restart(..., optimizer='MIES')` -- a vectorised restatement of the continuous-variable
     operators of the reference's MIES (optimizer/mies.py:160-175 recombination, :210-237
@@ -214,6 +215,27 @@ def _lbfgsb_restarts(objs, starts, bounds, eval_budget, wait_iter, mode, logger=
                 f[idx], g[idx] = fv, gv
         return -f, -g
 
+    from . import _lockstep
+    if _lockstep.available():
+        flat = starts.reshape(n_work, d)
+        out, _ = _lockstep.run(batch_fn, flat, bounds, eval_budget, factr=1e6, pgtol=1e-8, with_keys=True)
+    else:
+        out = _threaded_restarts(batch_fn, starts, bounds, eval_budget, n_work, R)
+    for p in range(n_prob):
+        best = None
+        for it in range(R):
+            x_, f_, info = out[p * R + it]
+            if logger is not None and info["warnflag"] != 0:
+                logger.debug("L-BFGS-B terminated abnormally with the state: %s" % info)
+            f_ = -float(f_)
+            if best is None or f_ > best[1]:
+                best = (x_.flatten().tolist(), f_)
+        results.append(best)
+    return results
+
+
+def _threaded_restarts(batch_fn, starts, bounds, eval_budget, n_work, R):
+    """Fallback lock-step driver: one thread per restart around the public fmin_l_bfgs_b."""
     ls = _KeyedLockStep(batch_fn, n_work)
     out = [None] * n_work
 
@@ -234,17 +256,7 @@ def _lbfgsb_restarts(objs, starts, bounds, eval_budget, wait_iter, mode, logger=
     for o in out:
         if isinstance(o, BaseException):
             raise o
-    for p in range(n_prob):
-        best = None
-        for it in range(R):
-            x_, f_, info = out[p * R + it]
-            if logger is not None and info["warnflag"] != 0:
-                logger.debug("L-BFGS-B terminated abnormally with the state: %s" % info)
-            f_ = -float(f_)
-            if best is None or f_ > best[1]:
-                best = (x_.flatten().tolist(), f_)
-        results.append(best)
-    return results
+    return out
 
 
 class _KeyedLockStep(_LockStep):

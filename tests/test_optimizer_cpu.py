@@ -150,3 +150,40 @@ def test_cma_es_population_generator():
     xb3, fb3, _ = opt.cma_es_argmax(lambda X: X[:, 0] + X[:, 1], np.array([[-5.0, 5.0]] * 2), lambda_=64,
                                     max_eval=64 * 60, seed=3)
     assert fb3 > 9.9
+
+
+def test_lockstep_engine_matches_scipy_and_threads():
+    """_lockstep.Trajectory drives scipy's compiled L-BFGS-B routine as a state machine: it must
+    reproduce fmin_l_bfgs_b bit for bit (incl. evaluation / iteration counts and the stop reason,
+    also when maxfun cuts a run short), and the thread-per-restart fallback must agree with it."""
+    from mipego_b200 import _lockstep, _mle
+    assert _lockstep.available()
+    d = 7
+    rng = np.random.default_rng(4)
+    b = np.array([[-2.0, 3.0]] * d)
+
+    def fg(x):
+        x = np.asarray(x)
+        return float(np.sum((x - 1.0) ** 4) - np.sum(np.cos(3 * x))), 4 * (x - 1.0) ** 3 + 3 * np.sin(3 * x)
+
+    def batch(P):
+        return np.sum((P - 1.0) ** 4, axis=1) - np.sum(np.cos(3 * P), axis=1), 4 * (P - 1.0) ** 3 + 3 * np.sin(3 * P)
+    starts = rng.uniform(-2, 3, (9, d))
+    for maxfun, factr, pgtol in ((500, 1e7, 1e-5), (7, 1e6, 1e-8)):
+        res, nb = _lockstep.run(batch, starts, b, maxfun, factr=factr, pgtol=pgtol)
+        assert nb <= maxfun + 25
+        for k in range(len(starts)):
+            xr, fr, dr = fmin_l_bfgs_b(fg, starts[k], bounds=b, maxfun=maxfun, factr=factr, pgtol=pgtol)
+            xm, fm, dm = res[k]
+            assert np.array_equal(xr, xm) and fr == fm
+            assert (dr["funcalls"], dr["nit"], dr["warnflag"], dr["task"]) == \
+                (dm["funcalls"], dm["nit"], dm["warnflag"], dm["task"])
+    # engine vs thread fallback through the MLE driver
+    p1, f1, n1, _ = _mle.multistart_lbfgsb(batch, starts, b, 300, 5, mode="batched")
+    saved = _lockstep._checked
+    try:
+        _lockstep._checked = False
+        p2, f2, n2, _ = _mle.multistart_lbfgsb(batch, starts, b, 300, 5, mode="batched")
+    finally:
+        _lockstep._checked = saved
+    assert np.array_equal(p1, p2) and f1 == f2 and n1 == n2
