@@ -610,18 +610,16 @@ static int g_gemm_cta_cap = 0;   // 0 = one CTA per SM
 void set_dgemm_cta_cap(int cap) { g_gemm_cta_cap = cap; }
 
 cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
-  static bool attr_done = false;
-  static int sm_count = 0;
-  if (!attr_done) {
+  static bool attr_done[MGP_MAX_DEVICES] = {};
+  if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_dgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    attr_done = true;
   }
+  int dev = 0, sm_count = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   int *sched = sched_words(st);
   if (!sched) return cudaErrorMemoryAllocation;
@@ -640,11 +638,10 @@ static const int kDiagSmem = kDiagSmemDbl * sizeof(double);
 
 cudaError_t launch_potrf_diag(double *A, double *Lout, int ld, int64_t sA, double *linv,
                               int64_t sInv, int kb, int *status, int batch, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[MGP_MAX_DEVICES] = {};
+  if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     cudaFuncSetAttribute(k_trtri_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
-    attr_done = true;
   }
   k_potrf_diag<<<batch, DIAG_THREADS, kDiagSmem, st>>>(A, Lout, ld, sA, linv, sInv, kb, status);
   return cudaGetLastError();
@@ -652,11 +649,10 @@ cudaError_t launch_potrf_diag(double *A, double *Lout, int ld, int64_t sA, doubl
 
 cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv, int64_t sInv,
                               int NI, int batch, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[MGP_MAX_DEVICES] = {};
+  if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     cudaFuncSetAttribute(k_trtri_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
-    attr_done = true;
   }
   k_trtri_diag<<<dim3(NI, batch), DIAG_THREADS, kDiagSmem, st>>>(L, ld, sL, linv, sInv);
   return cudaGetLastError();

@@ -153,4 +153,16 @@ __device__ __forceinline__ double corr_from_S_tab(double S, const double *tab) {
   return (1.0 + s) * exp_neg_tab(s, tab);
 }
 
+// Function attributes (dynamic shared-memory opt-in) are per device: `first_use_on_device(flags)`
+// is true once per (call site, current device).
+#define MGP_MAX_DEVICES 64
+static inline bool first_use_on_device(bool (&flags)[MGP_MAX_DEVICES]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = dev < 0 ? 0 : (dev >= MGP_MAX_DEVICES ? MGP_MAX_DEVICES - 1 : dev);
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

@@ -626,22 +626,16 @@ cudaError_t launch_trend_basis(const double *Xc, const double *center, int n, in
 cudaError_t launch_trend_solve(const double *Ftm, const double *Yt, double *rho, int n, int npad, int p,
                                double *tws, double *scal, int *status, int batch, cudaStream_t st) {
   const int smem = (2 * MGP_PMAX * (MGP_PMAX + 1) + 2 * MGP_PMAX + 32) * (int)sizeof(double);
-  static bool done = false;
-  if (!done) {
-    cudaFuncSetAttribute(k_trend_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    done = true;
-  }
+  static bool done[MGP_MAX_DEVICES] = {};
+  if (first_use_on_device(done)) cudaFuncSetAttribute(k_trend_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   k_trend_solve<<<batch, 1024, smem, st>>>(Ftm, Yt, rho, n, npad, p, tws, scal, status);
   return cudaGetLastError();
 }
 cudaError_t launch_trend_q(const double *Ftm, const double *tws, int n, int npad, int p, double *Qp,
                            int batch, cudaStream_t st) {
   const int smem = 2 * MGP_PMAX * (MGP_PMAX + 1) * (int)sizeof(double);
-  static bool done = false;
-  if (!done) {
-    cudaFuncSetAttribute(k_trend_q, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    done = true;
-  }
+  static bool done[MGP_MAX_DEVICES] = {};
+  if (first_use_on_device(done)) cudaFuncSetAttribute(k_trend_q, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   k_trend_q<<<dim3((npad + 63) / 64, batch), 256, smem, st>>>(Ftm, tws, n, npad, p, Qp);
   return cudaGetLastError();
 }

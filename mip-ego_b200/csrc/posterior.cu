@@ -942,9 +942,10 @@ cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, i
 template <int CORR, int KS, bool LIN>
 static cudaError_t rgen_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
   static int occ = 0;
+  static bool attr_done[MGP_MAX_DEVICES] = {};
   const int smem = (128 * rgen_stride(4 * KS) + 3 * 128 + MGP_EXP_TAB_DOUBLES +
                     (LIN ? 128 * trend_stride(trend_tiles(KS)) : 0)) * (int)sizeof(double);
-  if (occ == 0) {
+  if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_rgen<CORR, KS, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen<CORR, KS, LIN>, 256, smem) != cudaSuccess || occ < 1)
       occ = 1;
@@ -967,8 +968,9 @@ static cudaError_t rgen_dispatch(const RgenParams &p, int sm_count, cudaStream_t
 template <int DPAD>
 static cudaError_t rgen_l1_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
   static int occ = 0;
+  static bool attr_done[MGP_MAX_DEVICES] = {};
   const int smem = (DPAD * 132 + 128 * (DPAD + 1) + DPAD + 2 * 128 + MGP_EXP_TAB_DOUBLES) * (int)sizeof(double);
-  if (occ == 0) {
+  if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_rgen_l1<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen_l1<DPAD>, 256, smem) != cudaSuccess || occ < 1)
       occ = 1;
@@ -994,11 +996,10 @@ cudaError_t launch_rgen(const RgenParams &p, int corr, int sm_count, cudaStream_
 }
 
 cudaError_t launch_trmm(const TrmmParams &p, int sm_count, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[MGP_MAX_DEVICES] = {};
+  if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_trmm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRMM_SMEM);
     cudaFuncSetAttribute(k_trmm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRMM_SMEM);
-    attr_done = true;
   }
   const int items = p.NI * p.nCblk;
   if (items <= 0) return cudaSuccess;
