@@ -1,3 +1,5 @@
+# Round-1 evidence capture (run on a B200 box through gpurun): launch lists + `ncu --set full` of the top kernels.
+# Exports CSV/text summaries only (the .ncu-rep files exceed the 64 MiB gpurun_out limit); copy what is kept into profiles/.
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_c2.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2_r01.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_c2.log 2>&1
 cap() { # name, kernel regex, skip, count, bench args...
