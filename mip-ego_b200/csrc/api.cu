@@ -749,6 +749,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
         TrmmParams tp;
         tp.Mp = P<double>(h->dMp); tp.rP = P<double>(h->drP); tp.qpart = P<double>(h->dqpart);
         tp.wP = nullptr; tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 0; tp.ldq = ldp;
+        tp.last_tiles = (h->n - (h->NI - 1) * MGP_TILE + 7) / 8;
         KTimer t(h, st, 1);
         MGP_CUDA(h, launch_trmm(tp, h->sm_count, st));
       }
@@ -779,6 +780,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
         TrmmParams tp;
         tp.Mp = P<double>(h->dRinvP); tp.rP = P<double>(h->drP); tp.qpart = nullptr;
         tp.wP = P<double>(h->dwP); tp.NI = h->NI; tp.nCblk = nCblk; tp.NJ8 = NJ8; tp.full = 1; tp.ldq = ldp;
+        tp.last_tiles = 16;
         KTimer t(h, st, 1);
         MGP_CUDA(h, launch_trmm(tp, h->sm_count, st));
       }

@@ -261,7 +261,7 @@ constexpr int TRMM_SMEM = 2 * TS * STAGE_DBL * 8 + 2 * TS * 8 + 2 * 128 * 8;
 // i8 = 2 rt + wr) times 4 column tiles.  RT0 is a template parameter so that skipping the zero
 // tiles of the diagonal block is a real (warp-uniform) branch: predicated-off DMMAs would still
 // pay their static issue stalls.
-template <int RT0>
+template <int RT0, int RT1 = 8>
 __device__ __forceinline__ void slab_mma(double (&acc)[8][4][2], const double *as_slab,
                                          const double *bs_slab, int wr, int wc, int lane) {
   double2 b[4], a[8];
@@ -269,16 +269,33 @@ __device__ __forceinline__ void slab_mma(double (&acc)[8][4][2], const double *a
   for (int ct = 0; ct < 4; ct++)
     b[ct] = *reinterpret_cast<const double2 *>(bs_slab + (wc * 4 + ct) * 64 + lane * 2);
 #pragma unroll
-  for (int rt = RT0; rt < 8; rt++)
+  for (int rt = RT0; rt < RT1; rt++)
     a[rt] = *reinterpret_cast<const double2 *>(as_slab + (2 * rt + wr) * 64 + lane * 2);
 #pragma unroll
-  for (int rt = RT0; rt < 8; rt++)
+  for (int rt = RT0; rt < RT1; rt++)
 #pragma unroll
     for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt].x, b[ct].x);
 #pragma unroll
-  for (int rt = RT0; rt < 8; rt++)
+  for (int rt = RT0; rt < RT1; rt++)
 #pragma unroll
     for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt].y, b[ct].y);
+}
+
+// Last row block of a matrix whose size is not a multiple of 128: the row tiles that hold only
+// padding (zero rows of the packed operand) are skipped -- again by a warp-uniform branch.
+__device__ __forceinline__ void slab_mma_upto(int rt1, double (&acc)[8][4][2], const double *a_s,
+                                              const double *b_s, int wr, int wc, int lane) {
+  switch (rt1) {
+    case 1: slab_mma<0, 1>(acc, a_s, b_s, wr, wc, lane); break;
+    case 2: slab_mma<0, 2>(acc, a_s, b_s, wr, wc, lane); break;
+    case 3: slab_mma<0, 3>(acc, a_s, b_s, wr, wc, lane); break;
+    case 4: slab_mma<0, 4>(acc, a_s, b_s, wr, wc, lane); break;
+    case 5: slab_mma<0, 5>(acc, a_s, b_s, wr, wc, lane); break;
+    case 6: slab_mma<0, 6>(acc, a_s, b_s, wr, wc, lane); break;
+    case 7: slab_mma<0, 7>(acc, a_s, b_s, wr, wc, lane); break;
+    case 8: slab_mma<0, 8>(acc, a_s, b_s, wr, wc, lane); break;
+    default: break;
+  }
 }
 
 __device__ __forceinline__ void consumer_sync() {  // named barrier 1: the 8 consumer warps only
@@ -367,8 +384,15 @@ __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
       const double *as = As + stage * STAGE_DBL, *bs = Bs + stage * STAGE_DBL;
       const int dl = FULL ? -1 : kc - 4 * I;  // >= 0 inside the diagonal 128x128 block
       if (dl < 0) {
+        // valid 8-row tiles of this warp in the row block (interleaved: tile i8 = 2 rt + wr)
+        const int rt1 = (!FULL && I == p.NI - 1) ? min(8, max(0, (p.last_tiles - wr + 1) >> 1)) : 8;
+        if (rt1 == 8) {
 #pragma unroll
-        for (int js = 0; js < 4; js++) slab_mma<0>(acc, as + js * 1024, bs + js * 1024, wr, wc, lane);
+          for (int js = 0; js < 4; js++) slab_mma<0>(acc, as + js * 1024, bs + js * 1024, wr, wc, lane);
+        } else {
+#pragma unroll 1
+          for (int js = 0; js < 4; js++) slab_mma_upto(rt1, acc, as + js * 1024, bs + js * 1024, wr, wc, lane);
+        }
       } else {
         // diagonal block: tiles above the diagonal (i8 < jl) are zero.  Row tiles are interleaved
         // between the two row-warps (i8 = 2 rt + wr), so both warps of every SM sub-partition

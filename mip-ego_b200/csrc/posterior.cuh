@@ -34,6 +34,7 @@ struct TrmmParams {
   double *wP;         // packed W = R^-1 r, same layout as rP        (full == 1)
   int NI, nCblk, NJ8, full;
   int64_t ldq;
+  int last_tiles;     // 8-row tiles of the last row block that contain training rows (1..16)
 };
 // K2c: T = L^-1 r with fused column sums of squares (or W = R^-1 r), persistent grid.
 cudaError_t launch_trmm(const TrmmParams &p, int sm_count, cudaStream_t st);
