@@ -52,7 +52,14 @@ def test_c3_chunk_and_order_invariance(c3_model):
     for s in range(len(ts)):
         order = np.lexsort((np.arange(m), -V0[s]))[:16]
         assert np.array_equal(ti[s], order) and np.array_equal(tv[s], V0[s][order])
+    # k = 1 takes the fused per-block arg-max of the epilogue: several passes (chunk 4096) and one
+    h.set_option("chunk", 4096)
+    t1v, t1i = crit.topk(Xs, k=1, params=ts)
     h.set_option("chunk", 0)
+    t1v0, t1i0 = crit.topk(Xs, k=1, params=ts)
+    for s in range(len(ts)):
+        best = np.lexsort((np.arange(m), -V0[s]))[0]
+        assert t1i[s, 0] == best and t1i0[s, 0] == best and t1v[s, 0] == V0[s][best] == t1v0[s, 0]
     # "shards": evaluating two halves separately gives the same numbers as one call
     Va = crit.evaluate(Xs[:m // 2 + 17], params=ts)
     Vb = crit.evaluate(Xs[m // 2 + 17:], params=ts)
