@@ -397,8 +397,10 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
   if (B < 1 || !d_params || !d_out_llf || (eval_grad && !d_out_grad))
     return mgp_fail(h, MGP_EINVAL, "bad arguments to mgp_nll_batch");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int cap = std::min(B, nll_max_batch(h));
-  if (cap > h->nll_cap) MGP_TRY(nll_alloc(h, cap));
+  if (B > h->nll_cap) {   // grow the workspace (cudaMemGetInfo is slow: only asked when growing)
+    const int cap = std::min(B, nll_max_batch(h));
+    if (cap > h->nll_cap) MGP_TRY(nll_alloc(h, cap));
+  }
   const int use = h->nll_cap;
   for (int b0 = 0; b0 < B; b0 += use) {
     const int nb = std::min(use, B - b0);

@@ -589,9 +589,12 @@ cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, con
                           const double *Bhat, int p, const double *scal, double *gpart, int ntiles) {
   switch (dpad) {
 #define NG(D)                                                                                   \
-  case D:                                                                                       \
-    cudaFuncSetAttribute(k_nll_grad<CORR, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                         (int)smem);                                                            \
+  case D: {                                                                                     \
+    static bool attr[MGP_MAX_DEVICES] = {};                                                     \
+    if (first_use_on_device(attr))                                                              \
+      cudaFuncSetAttribute(k_nll_grad<CORR, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                           (int)smem);                                                          \
+  }                                                                                             \
     k_nll_grad<CORR, D><<<grid, 256, smem, st>>>(Xc, n, npad, params, n_par, mode, Rinv, sR,    \
                                                   gamma, avec, sv, Bhat, p, scal, gpart, ntiles); \
     break;
@@ -656,16 +659,23 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
   } else {
     const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad) * sizeof(double);
     dim3 grid(NI, NI, B);
-    if (w.corr == MGP_CORR_SE) {
+    static size_t smem_set[MGP_MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = dev < 0 || dev >= MGP_MAX_DEVICES ? 0 : dev;
+    if (smem > smem_set[dev]) {   // the opt-in only ever needs to grow
       cudaFuncSetAttribute(k_build_R<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_build_R<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_build_R<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      smem_set[dev] = smem;
+    }
+    if (w.corr == MGP_CORR_SE) {
       k_build_R<0><<<grid, 256, smem, st>>>(w.Xc, n, npad, w.dpad, w.params, w.n_par, w.mode,
                                             w.noise_var, w.R, sM);
     } else if (w.corr == MGP_CORR_MATERN32) {
-      cudaFuncSetAttribute(k_build_R<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       k_build_R<1><<<grid, 256, smem, st>>>(w.Xc, n, npad, w.dpad, w.params, w.n_par, w.mode,
                                             w.noise_var, w.R, sM);
     } else if (w.corr == MGP_CORR_ABSEXP) {
-      cudaFuncSetAttribute(k_build_R<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       k_build_R<2><<<grid, 256, smem, st>>>(w.Xc, n, npad, w.dpad, w.params, w.n_par, w.mode,
                                             w.noise_var, w.R, sM);
     } else {
