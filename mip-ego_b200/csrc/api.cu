@@ -107,7 +107,15 @@ int mgp_create(int device, mgp_t **out_h) {
     return MGP_ECUDA;
   }
   for (int i = 0; i < MGP_NLL_STREAMS; i++) {
-    cudaStreamCreateWithFlags(&h->nll_stream[i], cudaStreamNonBlocking);
+    // Descending priorities: when batch groups run concurrently the block scheduler then always
+    // prefers the pending CTAs of the group that is furthest ahead, so its short kernels (diagonal
+    // blocks, panel solves) are not queued behind the wide GEMMs of the other groups
+    // (n = 4096, 8 groups: 21.9 -> 21.3 ms per 8 evaluations).
+    int pr_lo = 0, pr_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);   // pr_hi is the numerically smallest (greatest priority)
+    const int pr = pr_hi + i > pr_lo ? pr_lo : pr_hi + i;
+    if (cudaStreamCreateWithPriority(&h->nll_stream[i], cudaStreamNonBlocking, pr) != cudaSuccess)
+      cudaStreamCreateWithFlags(&h->nll_stream[i], cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);

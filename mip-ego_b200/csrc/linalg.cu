@@ -52,6 +52,57 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDesc &g, int id, int 
   return t;
 }
 
+// One 16-k pipeline stage of the 128 x 128 tile for one consumer warp, restricted to the row tiles
+// [RT0, RT1) and column tiles [0, CT1) of the warp's 8 x 4 grid of 8 x 8 accumulator tiles.  The
+// bounds are template parameters so that the zero part of a triangular operand's diagonal block is
+// skipped by warp-uniform branches over straight-line code: predicated-off DMMAs would still pay
+// their issue slots (profiles/r01_trmm_c2_v4_source_summary.txt).
+template <bool TA, bool TB, int RT0, int RT1, int CT1>
+__device__ __forceinline__ void mma_stage(double (&acc)[8][4][2], const double *as, const double *bs,
+                                          int wr, int wc, int lr, int lk) {
+#pragma unroll
+  for (int p = 0; p < 2; p++) {
+    double2 a[8], b[4];   // TA/TB == 0: [tile] = (step 0, step 1);  == 1: [2 s + group] = (even, odd)
+    if (!TA) {
+#pragma unroll
+      for (int rt = RT0; rt < RT1; rt++)
+        a[rt] = *reinterpret_cast<const double2 *>(as + (wr * 64 + rt * 8 + lr) * LDK + 8 * p + 2 * lk);
+    } else {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+        for (int rp = RT0 / 2; rp < (RT1 + 1) / 2; rp++)
+          a[4 * s2 + rp] = *reinterpret_cast<const double2 *>(
+              as + (8 * p + 2 * lk + s2) * LDM + wr * 64 + 16 * rp + 2 * lr);
+    }
+    if (!TB) {
+#pragma unroll
+      for (int ct = 0; ct < CT1; ct++)
+        b[ct] = *reinterpret_cast<const double2 *>(bs + (wc * 32 + ct * 8 + lr) * LDK + 8 * p + 2 * lk);
+    } else {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+        for (int cp = 0; cp < (CT1 + 1) / 2; cp++)
+          b[2 * s2 + cp] = *reinterpret_cast<const double2 *>(
+              bs + (8 * p + 2 * lk + s2) * LDM + wc * 32 + 16 * cp + 2 * lr);
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+      for (int rt = RT0; rt < RT1; rt++) {
+        const double av = TA ? ((rt & 1) ? a[4 * s2 + (rt >> 1)].y : a[4 * s2 + (rt >> 1)].x)
+                             : (s2 ? a[rt].y : a[rt].x);
+#pragma unroll
+        for (int ct = 0; ct < CT1; ct++) {
+          const double bv = TB ? ((ct & 1) ? b[2 * s2 + (ct >> 1)].y : b[2 * s2 + (ct >> 1)].x)
+                               : (s2 ? b[ct].y : b[ct].x);
+          dmma884(acc[rt][ct][0], acc[rt][ct][1], av, bv);
+        }
+      }
+  }
+}
+
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(GemmDesc g, int *sched_g) {
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -170,7 +221,10 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
 
   // ---- consumers --------------------------------------------------------------------------------
   asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
-  const int wr = warp >> 2, wc = warp & 3, lr = lane >> 2, lk = lane & 3;
+  // warp -> (row half wr, column quarter wc): the two warps of an SM sub-partition (warp & 3) take
+  // mirrored column quarters, so that skipping by column (below) leaves every sub-partition the
+  // same amount of work
+  const int wr = warp >> 2, wc = wr ? 3 - (warp & 3) : (warp & 3), lr = lane >> 2, lk = lane & 3;
   int64_t x = 0;
   for (int q = 0;; q++) {
     const int id = next_tile(q);
@@ -180,6 +234,9 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
     const int i0 = t.rowblk * 128, j0 = t.colblk * 128;
     int klo, nk;
     k_range(t, klo, nk);
+    const bool tri_lo = (g.kmode & 2) && (t.rowblk + 1) * 128 <= g.K && nk >= 8;
+    const bool tri_hi = (g.kmode & 4) && klo == t.rowblk * 128 && nk >= 8;
+    const bool tri_b = (g.kmode & 1) && klo == t.colblk * 128 && nk >= 8;
     double acc[8][4][2];
 #pragma unroll
     for (int r = 0; r < 8; r++)
@@ -190,46 +247,38 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
       const int stage = (int)(x % NST);
       mbar_wait(&full[stage], (uint32_t)((x / NST) & 1));
       const double *as = As + stage * OP_DBL, *bs = Bs + stage * OP_DBL;
-#pragma unroll
-      for (int p = 0; p < 2; p++) {
-        double2 a[8], b[4];   // TA/TB == 0: [tile] = (step 0, step 1);  == 1: [2 s + group] = (even, odd)
-        if (!TA) {
-#pragma unroll
-          for (int rt = 0; rt < 8; rt++)
-            a[rt] = *reinterpret_cast<const double2 *>(as + (wr * 64 + rt * 8 + lr) * LDK + 8 * p + 2 * lk);
-        } else {
-#pragma unroll
-          for (int s2 = 0; s2 < 2; s2++)
-#pragma unroll
-            for (int rp = 0; rp < 4; rp++)
-              a[4 * s2 + rp] = *reinterpret_cast<const double2 *>(
-                  as + (8 * p + 2 * lk + s2) * LDM + wr * 64 + 16 * rp + 2 * lr);
+      // Diagonal block of a triangular operand: 16-k stage s of that block touches only
+      //   A lower triangular, k <= row (kmode 2, last block):   rows >= 16 s        -> row tiles >= rt0
+      //   A^T of a lower triangle, k >= row (kmode 4, first):   rows <  16 (s + 1)  -> row tiles <  rt1
+      //   B^T of a lower triangle, k >= col (kmode 1, first):   cols <  16 (s + 1)  -> col tiles <  ct1
+      // (the skipped products are exact zeros: the diagonal tiles of L and L^-1 are stored with a
+      // zero upper triangle).  One rule per stage; the column rule relies on the mirrored wc mapping.
+      int rt0 = 0, rt1 = 8, ct1 = 4;
+      if (!TA && tri_lo && kt >= nk - 8) rt0 = min(8, max(0, 2 * (kt - (nk - 8)) - 8 * wr));
+      else if (TA && tri_hi && kt < 8) rt1 = 2 * min(4, max(0, kt - 4 * wr + 1));
+      else if (TB && tri_b && kt < 8) ct1 = 2 * min(2, max(0, kt - 2 * wc + 1));
+      if (rt0 == 0 && rt1 == 8 && ct1 == 4) {
+        mma_stage<TA, TB, 0, 8, 4>(acc, as, bs, wr, wc, lr, lk);
+      } else if (!TA && rt0 > 0) {
+        switch (rt0) {
+          case 1: mma_stage<TA, TB, 1, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 2: mma_stage<TA, TB, 2, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 3: mma_stage<TA, TB, 3, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 4: mma_stage<TA, TB, 4, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 5: mma_stage<TA, TB, 5, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 6: mma_stage<TA, TB, 6, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 7: mma_stage<TA, TB, 7, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          default: break;
         }
-        if (!TB) {
-#pragma unroll
-          for (int ct = 0; ct < 4; ct++)
-            b[ct] = *reinterpret_cast<const double2 *>(bs + (wc * 32 + ct * 8 + lr) * LDK + 8 * p + 2 * lk);
-        } else {
-#pragma unroll
-          for (int s2 = 0; s2 < 2; s2++)
-#pragma unroll
-            for (int cp = 0; cp < 2; cp++)
-              b[2 * s2 + cp] = *reinterpret_cast<const double2 *>(
-                  bs + (8 * p + 2 * lk + s2) * LDM + wc * 32 + 16 * cp + 2 * lr);
+      } else if (TA && rt1 < 8) {
+        switch (rt1) {
+          case 2: mma_stage<TA, TB, 0, 2, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 4: mma_stage<TA, TB, 0, 4, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 6: mma_stage<TA, TB, 0, 6, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          default: break;
         }
-#pragma unroll
-        for (int s2 = 0; s2 < 2; s2++)
-#pragma unroll
-          for (int rt = 0; rt < 8; rt++) {
-            const double av = TA ? ((rt & 1) ? a[4 * s2 + (rt >> 1)].y : a[4 * s2 + (rt >> 1)].x)
-                                 : (s2 ? a[rt].y : a[rt].x);
-#pragma unroll
-            for (int ct = 0; ct < 4; ct++) {
-              const double bv = TB ? ((ct & 1) ? b[2 * s2 + (ct >> 1)].y : b[2 * s2 + (ct >> 1)].x)
-                                   : (s2 ? b[ct].y : b[ct].x);
-              dmma884(acc[rt][ct][0], acc[rt][ct][1], av, bv);
-            }
-          }
+      } else if (TB && ct1 < 4) {
+        if (ct1 == 2) mma_stage<TA, TB, 0, 8, 2>(acc, as, bs, wr, wc, lr, lk);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
