@@ -256,7 +256,7 @@ def cpu_nll_rate(n, d, reps):
 
 def run_nll(args, rank, world, local):
     """BASELINE configs[3]: GP hyper-parameter MLE n=4096 d=20, 64 restarts -> 8 NLL+grad per GPU."""
-    n, d, B = args.nll_n, 20, 8
+    n, d, B = args.nll_n, 20, args.nll_batch
     desc = "GP NLL+grad n=%d d=%d, %d theta-vectors per GPU per step (BASELINE configs[3]: 64 over 8 GPUs)" % (n, d, B)
     if args.impl == "reference":
         if rank != 0:
@@ -384,6 +384,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["nll"])
     ap.add_argument("--nll-n", type=int, default=4096)
+    ap.add_argument("--nll-batch", type=int, default=8, help="theta-vectors per GPU per step (configs[3]: 8)")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--nll-groups", type=int, default=0)
     ap.add_argument("--gemm-cta-cap", type=int, default=0)

@@ -451,18 +451,102 @@ __device__ long long g_diag_clk[16];
 #define DIAG_T(i)
 #endif
 
+// Barrier of the 15 warps that work beside the factoring warp (named barrier 1).
+__device__ __forceinline__ void bar_side() { asm volatile("bar.sync 1, 480;\n" ::: "memory"); }
+
+// Block row i >= 1 of the inverse, in place: rows < i of S already hold the inverse (diagonal
+// sub-blocks included), row i still holds L (already saved by the caller).  ALL: executed by the
+// whole CTA (__syncthreads) or by warps 1..15 only (bar_side).
+// (A DMMA version of these small products was measured SLOWER: 8 x 8 x 4 fragments read from a
+// row stride of 129 doubles hit 4-way bank conflicts and a dependent DMMA chain costs ~150 cycles
+// per step; tools/diag_bench.cu, 63 us against 56 us for the whole kernel.)
+template <bool ALL>
+__device__ __forceinline__ void inverse_block_row(double *S, const double *Xd, int i, int tid) {
+  auto sync = [] { if (ALL) __syncthreads(); else bar_side(); };
+  constexpr int NT = ALL ? DIAG_THREADS : DIAG_THREADS - 32;
+  const int t = ALL ? tid : tid - 32;
+  // block row i: 32 rows x 32 i columns = 8 x 8 i patches of 4 x 4, one per thread.  Lanes run over
+  // the row patches: the column-patch reads then are broadcasts and the row reads (rows four apart,
+  // stride 129) at most 2-way conflicts; the other order made the threads of a warp read addresses
+  // 32 bytes apart (8-way conflicts).
+  const int npc = 8 * i;
+  const bool on = t < 8 * npc;
+  const int pr = t & 7, pc = t >> 3;
+  const int r0 = 32 * i + 4 * pr, c0 = 4 * pc, j = c0 >> 5;
+  double acc[4][4];
+  // T_ij = sum_{k=j}^{i-1} L_ik X_kj
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+#pragma unroll
+    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+  if (on) patch4x4<false>(acc, S + r0 * DS, DS, S + c0, DS, 32 * j, 32 * i);
+  sync();
+  if (on) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int v = 0; v < 4; v++) S[(r0 + u) * DS + c0 + v] = acc[u][v];
+  }
+  for (int idx = t; idx < 32 * 32; idx += NT) {   // X_ii replaces L_ii
+    const int r = idx >> 5, c = idx & 31;
+    S[(32 * i + r) * DS + 32 * i + c] = Xd[i * 32 * XS + r * XS + c];
+  }
+  sync();
+  // X_ij = -X_ii T_ij   (X_ii lower triangular: k <= row)
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+#pragma unroll
+    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+  if (on) patch4x4<false>(acc, S + r0 * DS + 32 * i, DS, S + 32 * i * DS + c0, DS, 0, 4 * pr + 4);
+  sync();
+  if (on) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int v = 0; v < 4; v++) S[(r0 + u) * DS + c0 + v] = -acc[u][v];
+  }
+  sync();
+}
+
+// Rows [32 i, 32 i + 32) of the 128-wide lower-triangular block in S -> global (zeros above the
+// diagonal), 16-byte stores.  NT threads, thread index t.
+__device__ __forceinline__ void store_block_row(const double *S, double *G, int ldg, int i, int t, int NT) {
+  for (int idx = t; idx < 32 * 64; idx += NT) {
+    const int r = 32 * i + (idx >> 6), c = 2 * (idx & 63);
+    double2 v;
+    v.x = (c <= r) ? S[r * DS + c] : 0.0;
+    v.y = (c + 1 <= r) ? S[r * DS + c + 1] : 0.0;
+    *reinterpret_cast<double2 *>(G + (int64_t)r * ldg + c) = v;
+  }
+}
+
 __global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag(double *A, double *Lout, int ld,
                                                               int64_t sA, double *linv,
                                                               int64_t sInv, int kb, int *status) {
+  // While warp 0 factors and inverts the 32x32 diagonal sub-block s (the serial part), warps 1..15
+  // save block row s-1 of L, turn it into block row s-1 of the inverse and save that too; only the
+  // last block row is left for the end.
   extern __shared__ __align__(16) double S[];
   double *Xd = S + 128 * DS, *col = Xd + 4 * 32 * XS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   const double *Ab = A + b * sA + (int64_t)kb * 128 * ld + kb * 128;
   double *Lb = Lout + b * sA + (int64_t)kb * 128 * ld + kb * 128;
+  double *Ib = linv + b * sInv + (int64_t)kb * 128 * 128;
   DIAG_T(0);
-  for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
-    const int r = idx >> 7, c = idx & 127;
-    S[r * DS + c] = (c <= r) ? Ab[(int64_t)r * ld + c] : 0.0;
+  {
+    // lower triangle only, 16-byte loads, all of a thread's loads in flight together
+    double2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int idx = tid + DIAG_THREADS * q, r = idx >> 6, c = 2 * (idx & 63);
+      v[q] = (c <= r) ? *reinterpret_cast<const double2 *>(Ab + (int64_t)r * ld + c) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int idx = tid + DIAG_THREADS * q, r = idx >> 6, c = 2 * (idx & 63);
+      S[r * DS + c] = v[q].x;
+      S[r * DS + c + 1] = (c + 1 <= r) ? v[q].y : 0.0;
+    }
   }
   __syncthreads();
   DIAG_T(1);
@@ -475,6 +559,18 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag(double *A, double *
       if (s == 0 && lane == 0 && blockIdx.x == 0) g_diag_clk[8] = clock64();
 #endif
       warp_trtri32(S + o * DS + o, Xd + s * 32 * XS, col + 64, lane);
+    } else if (s > 0) {
+      const int t = tid - 32, i = s - 1;
+      store_block_row(S, Lb, ld, i, t, DIAG_THREADS - 32);
+      bar_side();
+      if (i == 0) {
+        for (int idx = t; idx < 32 * 32; idx += DIAG_THREADS - 32)
+          S[(idx >> 5) * DS + (idx & 31)] = Xd[(idx >> 5) * XS + (idx & 31)];
+        bar_side();
+      } else {
+        inverse_block_row<false>(S, Xd, i, tid);
+      }
+      store_block_row(S, Ib, 128, i, t, DIAG_THREADS - 32);
     }
     __syncthreads();
     if (s == 0) DIAG_T(2);
@@ -499,41 +595,51 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag(double *A, double *
         }
         __syncthreads();
       }
-      // symmetric update of the remaining rows: A[r][c] -= sum_k P[r][k] P[c][k]  (c <= r)
+      if (s == 0) DIAG_T(9);
+      // symmetric update of the remaining rows: A[r][c] -= sum_k P[r][k] P[c][k]  (c <= r).
+      // A patch owns the INTERLEAVED rows pr + u np and columns pc + v np (np = nb / 4): the
+      // threads of a warp then read consecutive rows of P (row stride 129: conflict-free) instead
+      // of rows four apart (6-way bank conflicts), and (u, v) is needed iff v < u, or v == u and
+      // pc <= pr -- ten products per k instead of sixteen.
       const int np = nb / 4;
+      const double *P = S + (o + 32) * DS + o;
       for (int e = tid; e < np * np; e += DIAG_THREADS) {
         const int pr = e / np, pc = e - pr * np;
-        if (pc > pr) continue;
         double acc[4][4];
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
           for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
-        patch4x4<true>(acc, S + (o + 32 + 4 * pr) * DS + o, DS, S + (o + 32 + 4 * pc) * DS + o, DS, 0, 32);
+#pragma unroll 4
+        for (int k = 0; k < 32; k++) {
+          double a[4], bq[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) a[u] = P[(pr + u * np) * DS + k];
+#pragma unroll
+          for (int v = 0; v < 4; v++) bq[v] = P[(pc + v * np) * DS + k];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v <= u; v++) acc[u][v] = fma(a[u], bq[v], acc[u][v]);
+        }
+        double *Cp = S + (o + 32) * DS + o + 32;
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
-          for (int v = 0; v < 4; v++)
-            if (4 * pc + v <= 4 * pr + u) S[(o + 32 + 4 * pr + u) * DS + o + 32 + 4 * pc + v] -= acc[u][v];
+          for (int v = 0; v <= u; v++)
+            if (v < u || pc <= pr) Cp[(pr + u * np) * DS + pc + v * np] -= acc[u][v];
       }
       __syncthreads();
       if (s == 0) DIAG_T(3);
     }
   }
   DIAG_T(4);
-  for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
-    const int r = idx >> 7, c = idx & 127;
-    Lb[(int64_t)r * ld + c] = (c <= r) ? S[r * DS + c] : 0.0;
-  }
+  store_block_row(S, Lb, ld, 3, tid, DIAG_THREADS);
   __syncthreads();
   DIAG_T(5);
-  diag_block_inverse(S, Xd, tid);
+  inverse_block_row<true>(S, Xd, 3, tid);
   DIAG_T(6);
-  double *Ib = linv + b * sInv + (int64_t)kb * 128 * 128;
-  for (int idx = tid; idx < 128 * 128; idx += DIAG_THREADS) {
-    const int r = idx >> 7, c = idx & 127;
-    Ib[idx] = (c <= r) ? S[r * DS + c] : 0.0;
-  }
+  store_block_row(S, Ib, 128, 3, tid, DIAG_THREADS);
   DIAG_T(7);
 }
 
@@ -558,12 +664,16 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_trtri_diag(const double *L, in
   }
 }
 
-__global__ void k_scatter_diag(const double *linv, int64_t sInv, double *M, int ld, int64_t sM) {
+__global__ void __launch_bounds__(1024) k_scatter_diag(const double *linv, int64_t sInv, double *M, int ld,
+                                                       int64_t sM) {
   const int kb = blockIdx.x, b = blockIdx.y;
-  const double *src = linv + b * sInv + (int64_t)kb * 128 * 128;
+  const double2 *src = reinterpret_cast<const double2 *>(linv + b * sInv + (int64_t)kb * 128 * 128);
   double *dst = M + b * sM + (int64_t)kb * 128 * ld + kb * 128;
-  for (int idx = threadIdx.x; idx < 128 * 128; idx += blockDim.x)
-    dst[(int64_t)(idx >> 7) * ld + (idx & 127)] = src[idx];
+#pragma unroll
+  for (int q = 0; q < 8; q++) {   // 8192 double2 per tile, 8 independent copies in flight per thread
+    const int idx = threadIdx.x + 1024 * q;
+    *reinterpret_cast<double2 *>(dst + (int64_t)(idx >> 6) * ld + 2 * (idx & 63)) = src[idx];
+  }
 }
 
 // ---- triangular mat-vec -------------------------------------------------------------------
@@ -787,7 +897,7 @@ cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, in
   if (clean_upper)
     for (int b = 0; b < batch; b++)
       LA_TRY(cudaMemsetAsync(Minv + b * sMat, 0, sizeof(double) * (size_t)npad * npad, st));
-  k_scatter_diag<<<dim3(NI, batch), 256, 0, st>>>(linv, sInv, Minv, npad, sMat);
+  k_scatter_diag<<<dim3(NI, batch), 1024, 0, st>>>(linv, sInv, Minv, npad, sMat);
   LA_TRY(cudaGetLastError());
   (*launches)++;
   for (int sb = 1; sb < NI; sb *= 2) {

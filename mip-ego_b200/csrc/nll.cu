@@ -55,26 +55,48 @@ __host__ __device__ inline int mode_n_theta(int mode, int n_par) {
   return n_par - extra;
 }
 
+// Feature scaling of the staged coordinates: with x' = c_i x the weighted distance needs one
+// subtraction and one FMA per feature and pair instead of three FP64 instructions,
+//   SE / Matern:  c_i = sqrt(theta_i),  sum_i theta_i (x_i - y_i)^2 = sum_i (x'_i - y'_i)^2
+//   abs-exp:      c_i = theta_i,        sum_i theta_i |x_i - y_i|   = sum_i |x'_i - y'_i|
+// (the likelihood kernels are bound by the FP64 pipe, which they share with the DMMAs of the other
+// batch groups).  A theta_i of exactly zero cannot be folded into the coordinates -- the gradient
+// with respect to it would be lost -- so such a vector takes the unscaled loop (CTA-uniform branch).
+template <int CORR>
+__device__ __forceinline__ double feature_scale(double theta) { return CORR == 2 ? theta : sqrt(theta); }
+
 // R tile builder: lower tiles (bi >= bj); padded indices give the identity.
 template <int CORR>
 __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int npad, int dpad,
                                                  const double *params, int n_par, int mode,
                                                  double noise_var, double *R, int64_t sR) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   double *xjT = sm;               // [dpad][XP]  rows of tile bi
   double *xkT = sm + dpad * XP;   // [dpad][XP]  rows of tile bj
-  double *th = xkT + dpad * XP;   // [dpad]
+  double *th = xkT + dpad * XP;   // [dpad]      theta, then the feature scales
+  double *tab = th + dpad;        // exp table (mgp_common.cuh)
+  __shared__ int s_anyzero;
   const int bj = blockIdx.x, bi = blockIdx.y, b = blockIdx.z;
   if (bj > bi) return;
   const int tid = threadIdx.x;
   const double *par = params + (int64_t)b * n_par;
   const int d = mode_n_theta(mode, n_par);
+  if (tid == 0) s_anyzero = 0;
+  exp_tab_fill(tab, tid, 256);
+  __syncthreads();
+  for (int i = tid; i < dpad; i += 256) {
+    const double t = i < d ? par[i] : 0.0;
+    th[i] = t;
+    if (i < d && !(t > 0.0)) s_anyzero = 1;
+  }
+  __syncthreads();
+  const bool scaled = s_anyzero == 0;
   for (int idx = tid; idx < 128 * dpad; idx += 256) {
     const int r = idx / dpad, i = idx % dpad;
-    xjT[i * XP + r] = Xc[(int64_t)(bi * 128 + r) * dpad + i];
-    xkT[i * XP + r] = Xc[(int64_t)(bj * 128 + r) * dpad + i];
+    const double c = scaled ? feature_scale<CORR>(th[i]) : 1.0;
+    xjT[i * XP + r] = c * Xc[(int64_t)(bi * 128 + r) * dpad + i];
+    xkT[i * XP + r] = c * Xc[(int64_t)(bj * 128 + r) * dpad + i];
   }
-  for (int i = tid; i < dpad; i += 256) th[i] = i < d ? par[i] : 0.0;
   __syncthreads();
   const double scale = mode_params(mode, par, n_par, noise_var).c;
   double *Rb = R + b * sR;
@@ -85,17 +107,33 @@ __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int np
   for (int q = 0; q < 16; q++) {
     const int r = (tid >> 7) * 64 + 4 * q;
     double S[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = 0; i < dpad; i++) {
-      const double xk = xkT[i * XP + c], t = th[i];
-      const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
-      const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
-      const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
-      if (CORR == 2) {
-        S[0] = fma(t, fabs(d0), S[0]); S[1] = fma(t, fabs(d1), S[1]);
-        S[2] = fma(t, fabs(d2), S[2]); S[3] = fma(t, fabs(d3), S[3]);
-      } else {
-        S[0] = fma(t * d0, d0, S[0]); S[1] = fma(t * d1, d1, S[1]);
-        S[2] = fma(t * d2, d2, S[2]); S[3] = fma(t * d3, d3, S[3]);
+    if (scaled) {
+#pragma unroll 4
+      for (int i = 0; i < dpad; i++) {
+        const double xk = xkT[i * XP + c];
+        const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
+        const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
+        const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
+        if (CORR == 2) {
+          S[0] += fabs(d0); S[1] += fabs(d1); S[2] += fabs(d2); S[3] += fabs(d3);
+        } else {
+          S[0] = fma(d0, d0, S[0]); S[1] = fma(d1, d1, S[1]);
+          S[2] = fma(d2, d2, S[2]); S[3] = fma(d3, d3, S[3]);
+        }
+      }
+    } else {
+      for (int i = 0; i < dpad; i++) {
+        const double xk = xkT[i * XP + c], t = th[i];
+        const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
+        const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
+        const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
+        if (CORR == 2) {
+          S[0] = fma(t, fabs(d0), S[0]); S[1] = fma(t, fabs(d1), S[1]);
+          S[2] = fma(t, fabs(d2), S[2]); S[3] = fma(t, fabs(d3), S[3]);
+        } else {
+          S[0] = fma(t * d0, d0, S[0]); S[1] = fma(t * d1, d1, S[1]);
+          S[2] = fma(t * d2, d2, S[2]); S[3] = fma(t * d3, d3, S[3]);
+        }
       }
     }
 #pragma unroll
@@ -104,7 +142,7 @@ __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int np
       double v;
       if (gj == gk) v = 1.0;
       else if (gj >= n || gk >= n) v = 0.0;
-      else v = scale * corr_from_S<CORR>(S[u]);
+      else v = scale * corr_from_S_tab<CORR>(S[u], tab);
       Rb[(int64_t)gj * npad + gk] = v;
     }
   }
@@ -217,11 +255,13 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
                                                   const double *gamma, const double *avec, int64_t sv,
                                                   const double *Bhat, int p,
                                                   const double *scal, double *gpart, int ntiles) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   double *xjT = sm;
   double *xkT = sm + DP * XP;
   double *th = xkT + DP * XP;
   double *red = th + DP;  // [8][DP+2]
+  double *tab = red + 8 * (DP + 2);   // exp table (mgp_common.cuh)
+  __shared__ int s_anyzero;
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // tile index -> (bi, bj), bi >= bj
   int t = blockIdx.x, bi = 0;
@@ -229,12 +269,24 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
   const int bj = t - bi * (bi + 1) / 2;
   const double *par = params + (int64_t)b * n_par;
   const int d = mode_n_theta(mode, n_par);
+  if (tid == 0) s_anyzero = 0;
+  exp_tab_fill(tab, tid, 256);
+  __syncthreads();
+  for (int i = tid; i < DP; i += 256) {
+    const double tv = i < d ? par[i] : 0.0;
+    th[i] = tv;
+    if (i < d && !(tv > 0.0)) s_anyzero = 1;
+  }
+  __syncthreads();
+  // coordinates scaled per feature (see feature_scale): the accumulators then hold theta_i times
+  // the wanted sums, undone when the tile partials are written
+  const bool scaled = s_anyzero == 0;
   for (int idx = tid; idx < 128 * DP; idx += 256) {
     const int r = idx / DP, i = idx % DP;
-    xjT[i * XP + r] = Xc[(int64_t)(bi * 128 + r) * DP + i];
-    xkT[i * XP + r] = Xc[(int64_t)(bj * 128 + r) * DP + i];
+    const double c = scaled ? feature_scale<CORR>(th[i]) : 1.0;
+    xjT[i * XP + r] = c * Xc[(int64_t)(bi * 128 + r) * DP + i];
+    xkT[i * XP + r] = c * Xc[(int64_t)(bj * 128 + r) * DP + i];
   }
-  for (int i = tid; i < DP; i += 256) th[i] = i < d ? par[i] : 0.0;
   __syncthreads();
   const double s_div = scal[(int64_t)b * SC_N + SC_S];
   const double coefa = scal[(int64_t)b * SC_N + SC_COEFA];
@@ -263,18 +315,34 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
       gj4[u] = on ? __ldg(gm + gj) : 0.0;
     }
     double S[4] = {0.0, 0.0, 0.0, 0.0};
+    if (scaled) {
 #pragma unroll 4
-    for (int i = 0; i < DP; i++) {
-      const double xk = xkT[i * XP + c], t = th[i];
-      const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
-      const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
-      const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
-      if (CORR == 2) {
-        S[0] = fma(t, fabs(d0), S[0]); S[1] = fma(t, fabs(d1), S[1]);
-        S[2] = fma(t, fabs(d2), S[2]); S[3] = fma(t, fabs(d3), S[3]);
-      } else {
-        S[0] = fma(t * d0, d0, S[0]); S[1] = fma(t * d1, d1, S[1]);
-        S[2] = fma(t * d2, d2, S[2]); S[3] = fma(t * d3, d3, S[3]);
+      for (int i = 0; i < DP; i++) {
+        const double xk = xkT[i * XP + c];
+        const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
+        const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
+        const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
+        if (CORR == 2) {
+          S[0] += fabs(d0); S[1] += fabs(d1); S[2] += fabs(d2); S[3] += fabs(d3);
+        } else {
+          S[0] = fma(d0, d0, S[0]); S[1] = fma(d1, d1, S[1]);
+          S[2] = fma(d2, d2, S[2]); S[3] = fma(d3, d3, S[3]);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < DP; i++) {
+        const double xk = xkT[i * XP + c], tv = th[i];
+        const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
+        const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
+        const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
+        if (CORR == 2) {
+          S[0] = fma(tv, fabs(d0), S[0]); S[1] = fma(tv, fabs(d1), S[1]);
+          S[2] = fma(tv, fabs(d2), S[2]); S[3] = fma(tv, fabs(d3), S[3]);
+        } else {
+          S[0] = fma(tv * d0, d0, S[0]); S[1] = fma(tv * d1, d1, S[1]);
+          S[2] = fma(tv * d2, d2, S[2]); S[3] = fma(tv * d3, d3, S[3]);
+        }
       }
     }
     double wf[4];
@@ -289,9 +357,9 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
           W = fma(av[gj], ak_v, W);
         } else {   // v (L^-T Q)(L^-T Q)^T: a p-term dot product per pair
           const double *bj_ = Bhat + ((int64_t)b * npad + gj) * MGP_TP, *bk_ = Bhat + ((int64_t)b * npad + gk) * MGP_TP;
-          double t = 0.0;
-          for (int k = 0; k < p; k++) t = fma(bj_[k], bk_[k], t);
-          W = fma(coefa, t, W);
+          double tq = 0.0;
+          for (int k = 0; k < p; k++) tq = fma(bj_[k], bk_[k], tq);
+          W = fma(coefa, tq, W);
         }
       }
       if (gj == gk) {
@@ -300,10 +368,10 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
       }
       double R0, fac;
       if (CORR != 1) {
-        R0 = exp(-S[u]);
+        R0 = exp_neg_tab(S[u], tab);
         fac = -R0;  // dR0/dtheta_i = -df_i^2 R0 (gpr.py:634) | -|df_i| R0 (gpr.py:648)
       } else {
-        const double sq = MGP_SQRT3 * sqrt(S[u]), e = exp(-sq);
+        const double sq = MGP_SQRT3 * sqrt(S[u]), e = exp_neg_tab(sq, tab);
         R0 = (1.0 + sq) * e;
         fac = -1.5 * e;  // dR0/dtheta_i = -(3/2) df_i^2 e^{-sqrt3 D}   gpr.py:643
       }
@@ -316,15 +384,15 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
       const double2 a = *reinterpret_cast<const double2 *>(xjT + i * XP + r);
       const double2 bq = *reinterpret_cast<const double2 *>(xjT + i * XP + r + 2);
       const double d0 = a.x - xk, d1 = a.y - xk, d2 = bq.x - xk, d3 = bq.y - xk;
-      double t;
+      double tq;
       if (CORR == 2) {
-        t = wf[0] * fabs(d0);
-        t = fma(wf[1], fabs(d1), t); t = fma(wf[2], fabs(d2), t); t = fma(wf[3], fabs(d3), t);
+        tq = wf[0] * fabs(d0);
+        tq = fma(wf[1], fabs(d1), tq); tq = fma(wf[2], fabs(d2), tq); tq = fma(wf[3], fabs(d3), tq);
       } else {
-        t = (wf[0] * d0) * d0;
-        t = fma(wf[1] * d1, d1, t); t = fma(wf[2] * d2, d2, t); t = fma(wf[3] * d3, d3, t);
+        tq = (wf[0] * d0) * d0;
+        tq = fma(wf[1] * d1, d1, tq); tq = fma(wf[2] * d2, d2, tq); tq = fma(wf[3] * d3, d3, tq);
       }
-      acc[i] += t;
+      acc[i] += tq;
     }
   }
 #pragma unroll
@@ -338,6 +406,9 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
   for (int i = tid; i <= DP + 1; i += 256) {
     double v = 0.0;
     for (int w = 0; w < 8; w++) v += red[w * (DP + 2) + i];
+    // scaled coordinates: the feature sums carry a factor theta_i (squared differences of
+    // sqrt(theta_i) x, or absolute differences of theta_i x)
+    if (scaled && i < DP) v = i < d ? v / th[i] : 0.0;
     gpart[((int64_t)b * ntiles + t) * (DP + 2) + i] = v;
   }
 }
@@ -347,32 +418,39 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
 //   concentrated noisy  sigma2 : (0.5 / v) sum_all W R0                    (gpr.py:938-944)
 //   concentrated noise_estim alpha : sum_{j>k} W R0 = -1/2 (sum Rinv o (R0 - I) - ...)   (gpr.py:927-930)
 //   restricted sigma2 : (0.5 / v) sum_all W R0;  noise_var : (0.5 / v) sum_j W_jj        (gpr.py:762-783)
-__global__ void k_nll_grad_final(const double *gpart, int ntiles, int dp2, int n_par, int mode,
-                                 const double *scal, const int *status, double *out_grad) {
-  const int b = blockIdx.x, i = threadIdx.x;
-  if (i >= n_par) return;
+__global__ void __launch_bounds__(1024) k_nll_grad_final(const double *gpart, int ntiles, int dp2, int n_par,
+                                                         int mode, const double *scal, const int *status,
+                                                         double *out_grad) {
+  // one warp per parameter: lane l sums the tiles l, l + 32, ... in order, the 32 partial sums are
+  // combined by a fixed shuffle tree -- the result does not depend on scheduling
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d = mode_n_theta(mode, n_par);
   const bool restricted = (mode & MGP_LIK_RESTRICTED) != 0;
   const int est = mode & 15;
-  double g = 0.0;
-  if (status[b] == 0 || (restricted && status[b] == -1)) {
-    auto col = [&](int src) {
-      double t = 0.0;
-      for (int q = 0; q < ntiles; q++) t += gpart[((int64_t)b * ntiles + q) * dp2 + src];
-      return t;
-    };
-    const double v = scal[(int64_t)b * SC_N + SC_V];
-    if (i < d) {
-      g = col(i) * scal[(int64_t)b * SC_N + SC_THSCALE];
-    } else if (!restricted && est == MGP_MODE_NOISE_ESTIM) {
-      g = 0.5 * col(dp2 - 2);
-    } else if (i == d) {
-      g = (col(dp2 - 2) + col(dp2 - 1)) * 0.5 / v;
-    } else {
-      g = col(dp2 - 1) * 0.5 / v;
+  const bool live = status[b] == 0 || (restricted && status[b] == -1);
+  auto col = [&](int src) {
+    double t = 0.0;
+    for (int q = lane; q < ntiles; q += 32) t += gpart[((int64_t)b * ntiles + q) * dp2 + src];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+  };
+  for (int i = warp; i < n_par; i += 32) {
+    double g = 0.0;
+    if (live) {
+      const double v = scal[(int64_t)b * SC_N + SC_V];
+      if (i < d) {
+        g = col(i) * scal[(int64_t)b * SC_N + SC_THSCALE];
+      } else if (!restricted && est == MGP_MODE_NOISE_ESTIM) {
+        g = 0.5 * col(dp2 - 2);
+      } else if (i == d) {
+        g = (col(dp2 - 2) + col(dp2 - 1)) * 0.5 / v;
+      } else {
+        g = col(dp2 - 1) * 0.5 / v;
+      }
     }
+    if (lane == 0) out_grad[(int64_t)b * n_par + i] = g;
   }
-  out_grad[(int64_t)b * n_par + i] = g;
 }
 
 // ---- general basis trend -------------------------------------------------------------------------
@@ -657,7 +735,7 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
     NL_TRY(launch_trtri_diag(w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, NI, B, st));
     (*launches)++;
   } else {
-    const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad) * sizeof(double);
+    const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + MGP_EXP_TAB_DOUBLES) * sizeof(double);
     dim3 grid(NI, NI, B);
     static size_t smem_set[MGP_MAX_DEVICES] = {};
     int dev = 0;
@@ -735,7 +813,7 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
     }
     NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, st, launches));
     const int ntiles = NI * (NI + 1) / 2;
-    const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + 8 * (w.dpad + 2)) * sizeof(double);
+    const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + 8 * (w.dpad + 2) + MGP_EXP_TAB_DOUBLES) * sizeof(double);
     dim3 grid(ntiles, B);
     if (w.corr == MGP_CORR_SE)
       NL_TRY(grad_dispatch<0>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
@@ -746,7 +824,7 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
     else
       NL_TRY(grad_dispatch<2>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
                               sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles));
-    k_nll_grad_final<<<B, 128, 0, st>>>(w.gpart, ntiles, w.dpad + 2, w.n_par, w.mode, w.scal,
+    k_nll_grad_final<<<B, 1024, 0, st>>>(w.gpart, ntiles, w.dpad + 2, w.n_par, w.mode, w.scal,
                                         w.status, w.out_grad);
     NL_TRY(cudaGetLastError());
     (*launches) += 2;

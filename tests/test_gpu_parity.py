@@ -736,7 +736,10 @@ def test_edge_shapes_and_values():
         far = np.arange(len(Xs)) >= 42
         assert np.max(np.abs(v - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max() + 1e-300)) < 1e-6, (n, d)
         assert np.all(np.isfinite(dx))
-        assert np.max(np.abs(dx[~far] - rdx[~far])) < 1e-5 * (np.abs(rdx[~far]).max() + 1e-300), (n, d)
+        # absolute floor: for n = 128, d = 1 every EI value is ~1e-10 (z ~ -6), so the gradients
+        # themselves sit at 1e-10 and carry the rounding of the fitted state amplified by |z|
+        floor = 1e-13 * np.sqrt(float(np.ravel(st["sigma2"])[0]))
+        assert np.max(np.abs(dx[~far] - rdx[~far])) < 1e-5 * np.abs(rdx[~far]).max() + floor, (n, d)
         # top-k: k larger than the population, and exact ties resolved towards the smaller index
         tv, ti = ei.topk(Xs[:5], k=9)
         assert tv.shape == (1, 5) and sorted(ti[0].tolist()) == [0, 1, 2, 3, 4]

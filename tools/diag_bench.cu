@@ -51,8 +51,8 @@ int main() {
       }
   long long clk[16];
   CK(cudaMemcpyFromSymbol(clk, g_diag_clk, sizeof(clk)));
-  printf("cycles: load %lld | potrf32 %lld trtri32 %lld | panel+update(s=0) %lld | steps1-3 %lld | storeL %lld | inverse %lld | storeInv %lld | total %lld\n",
-         clk[1] - clk[0], clk[8] - clk[1], clk[2] - clk[8], clk[3] - clk[2], clk[4] - clk[3], clk[5] - clk[4], clk[6] - clk[5], clk[7] - clk[6], clk[7] - clk[0]);
+  printf("cycles: load %lld | potrf32 %lld trtri32 %lld | panel(s=0) %lld update(s=0) %lld | steps1-3 %lld | storeL %lld | inverse %lld | storeInv %lld | total %lld\n",
+         clk[1] - clk[0], clk[8] - clk[1], clk[2] - clk[8], clk[9] - clk[2], clk[3] - clk[9], clk[4] - clk[3], clk[5] - clk[4], clk[6] - clk[5], clk[7] - clk[6], clk[7] - clk[0]);
   printf("{\"potrf_diag_us\": %.2f, \"batch\": %d, \"max_err_LLt\": %.3e, \"max_err_LinvL\": %.3e}\n", ms * 1e3 / reps, batch, e_chol, e_inv);
   return 0;
 }
