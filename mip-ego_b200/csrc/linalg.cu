@@ -59,21 +59,21 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDesc &g, int id, int 
 // their issue slots (profiles/r01_trmm_c2_v4_source_summary.txt).
 template <bool TA, bool TB, int RT0, int RT1, int CT1>
 __device__ __forceinline__ void mma_stage(double (&acc)[8][4][2], const double *as, const double *bs,
-                                          int wr, int wc, int lr, int lk) {
+                                          int rbase, int wc, int lr, int lk) {
 #pragma unroll
   for (int p = 0; p < 2; p++) {
     double2 a[8], b[4];   // TA/TB == 0: [tile] = (step 0, step 1);  == 1: [2 s + group] = (even, odd)
     if (!TA) {
 #pragma unroll
       for (int rt = RT0; rt < RT1; rt++)
-        a[rt] = *reinterpret_cast<const double2 *>(as + (wr * 64 + rt * 8 + lr) * LDK + 8 * p + 2 * lk);
+        a[rt] = *reinterpret_cast<const double2 *>(as + (rbase + rt * 8 + lr) * LDK + 8 * p + 2 * lk);
     } else {
 #pragma unroll
       for (int s2 = 0; s2 < 2; s2++)
 #pragma unroll
         for (int rp = RT0 / 2; rp < (RT1 + 1) / 2; rp++)
           a[4 * s2 + rp] = *reinterpret_cast<const double2 *>(
-              as + (8 * p + 2 * lk + s2) * LDM + wr * 64 + 16 * rp + 2 * lr);
+              as + (8 * p + 2 * lk + s2) * LDM + rbase + 16 * rp + 2 * lr);
     }
     if (!TB) {
 #pragma unroll
@@ -103,8 +103,13 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][4][2], const double *
   }
 }
 
-template <bool TA, bool TB>
+// MT: rows of the output tile.  MT = 64 (k-contiguous A, full k range only) halves the tile so that
+// launches with fewer 128-row tiles than half the SMs -- the panel solves and panel updates on the
+// serial chain of the blocked Cholesky -- spread over twice as many SMs.
+template <bool TA, bool TB, int MT = 128>
 __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(GemmDesc g, int *sched_g) {
+  static_assert(MT == 128 || (MT == 64 && !TA), "half tiles: k-contiguous A only");
+  constexpr int RTN = MT / 16;   // 8-row accumulator tiles per consumer warp
   extern __shared__ __align__(128) unsigned char smraw[];
   double *As = reinterpret_cast<double *>(smraw);
   double *Bs = As + NST * OP_DBL;
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
   int *slot_id = reinterpret_cast<int *>(sempty + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = g.N / 128, ty = g.M / 128, nz = g.n_inner * g.n_outer;
+  const int tx = g.N / 128, ty = g.M / MT, nz = g.n_inner * g.n_outer;
   const int total = tx * ty * nz;
   constexpr int NWARPS = (GEMM_CONSUMERS + GEMM_PRODUCERS) / 32;
 
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
         if (id >= total) { id = -1; break; }
         if (!g.lower_only) break;
         const TileCoord t = decode_tile(g, id, tx, ty, nz);
-        if (t.colblk <= t.rowblk) break;
+        if (t.colblk * 128 < (t.rowblk + 1) * MT) break;
       }
       slot_id[slot] = id;
       mbar_arrive(&sfull[slot]);
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
       if (id < 0) break;
       const TileCoord t = decode_tile(g, id, tx, ty, nz);
       const int inner = t.z % g.n_inner, outer = t.z / g.n_inner;
-      const int i0 = t.rowblk * 128, j0 = t.colblk * 128;
+      const int i0 = t.rowblk * MT, j0 = t.colblk * 128;
       int klo, nk;
       k_range(t, klo, nk);
       const double *A = g.A + inner * g.sA_in + outer * g.sA_out;
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
           const int c = ptid + GEMM_PRODUCERS * u;
           if (!TA) {
             const int row = c >> 3, kc = c & 7;
-            cp_async16(as + row * LDK + kc * 2, A + (int64_t)(i0 + row) * g.lda + k0 + kc * 2);
+            if (u < MT / 16) cp_async16(as + row * LDK + kc * 2, A + (int64_t)(i0 + row) * g.lda + k0 + kc * 2);
           } else {
             const int kr = c >> 6, mc = c & 63;
             cp_async16(as + kr * LDM + mc * 2, A + (int64_t)(k0 + kr) * g.lda + i0 + mc * 2);
@@ -231,9 +236,10 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
     if (id < 0) break;
     const TileCoord t = decode_tile(g, id, tx, ty, nz);
     const int inner = t.z % g.n_inner, outer = t.z / g.n_inner;
-    const int i0 = t.rowblk * 128, j0 = t.colblk * 128;
+    const int i0 = t.rowblk * MT, j0 = t.colblk * 128;
     int klo, nk;
     k_range(t, klo, nk);
+    const int rbase = wr * (MT / 2);
     const bool tri_lo = (g.kmode & 2) && (t.rowblk + 1) * 128 <= g.K && nk >= 8;
     const bool tri_hi = (g.kmode & 4) && klo == t.rowblk * 128 && nk >= 8;
     const bool tri_b = (g.kmode & 1) && klo == t.colblk * 128 && nk >= 8;
@@ -257,28 +263,28 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
       if (!TA && tri_lo && kt >= nk - 8) rt0 = min(8, max(0, 2 * (kt - (nk - 8)) - 8 * wr));
       else if (TA && tri_hi && kt < 8) rt1 = 2 * min(4, max(0, kt - 4 * wr + 1));
       else if (TB && tri_b && kt < 8) ct1 = 2 * min(2, max(0, kt - 2 * wc + 1));
-      if (rt0 == 0 && rt1 == 8 && ct1 == 4) {
-        mma_stage<TA, TB, 0, 8, 4>(acc, as, bs, wr, wc, lr, lk);
+      if (MT != 128 || (rt0 == 0 && rt1 == 8 && ct1 == 4)) {
+        mma_stage<TA, TB, 0, RTN, 4>(acc, as, bs, rbase, wc, lr, lk);
       } else if (!TA && rt0 > 0) {
         switch (rt0) {
-          case 1: mma_stage<TA, TB, 1, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
-          case 2: mma_stage<TA, TB, 2, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
-          case 3: mma_stage<TA, TB, 3, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
-          case 4: mma_stage<TA, TB, 4, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
-          case 5: mma_stage<TA, TB, 5, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
-          case 6: mma_stage<TA, TB, 6, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
-          case 7: mma_stage<TA, TB, 7, 8, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 1: mma_stage<TA, TB, 1, 8, 4>(acc, as, bs, rbase, wc, lr, lk); break;
+          case 2: mma_stage<TA, TB, 2, 8, 4>(acc, as, bs, rbase, wc, lr, lk); break;
+          case 3: mma_stage<TA, TB, 3, 8, 4>(acc, as, bs, rbase, wc, lr, lk); break;
+          case 4: mma_stage<TA, TB, 4, 8, 4>(acc, as, bs, rbase, wc, lr, lk); break;
+          case 5: mma_stage<TA, TB, 5, 8, 4>(acc, as, bs, rbase, wc, lr, lk); break;
+          case 6: mma_stage<TA, TB, 6, 8, 4>(acc, as, bs, rbase, wc, lr, lk); break;
+          case 7: mma_stage<TA, TB, 7, 8, 4>(acc, as, bs, rbase, wc, lr, lk); break;
           default: break;
         }
       } else if (TA && rt1 < 8) {
         switch (rt1) {
-          case 2: mma_stage<TA, TB, 0, 2, 4>(acc, as, bs, wr, wc, lr, lk); break;
-          case 4: mma_stage<TA, TB, 0, 4, 4>(acc, as, bs, wr, wc, lr, lk); break;
-          case 6: mma_stage<TA, TB, 0, 6, 4>(acc, as, bs, wr, wc, lr, lk); break;
+          case 2: mma_stage<TA, TB, 0, 2, 4>(acc, as, bs, rbase, wc, lr, lk); break;
+          case 4: mma_stage<TA, TB, 0, 4, 4>(acc, as, bs, rbase, wc, lr, lk); break;
+          case 6: mma_stage<TA, TB, 0, 6, 4>(acc, as, bs, rbase, wc, lr, lk); break;
           default: break;
         }
       } else if (TB && ct1 < 4) {
-        if (ct1 == 2) mma_stage<TA, TB, 0, 8, 2>(acc, as, bs, wr, wc, lr, lk);
+        if (ct1 == 2) mma_stage<TA, TB, 0, 8, 2>(acc, as, bs, rbase, wc, lr, lk);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
@@ -287,8 +293,8 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
     // ---- epilogue: C = alpha * acc + beta * C -------------------------------------------------
     double *C = g.C + inner * g.sC_in + outer * g.sC_out;
 #pragma unroll
-    for (int rt = 0; rt < 8; rt++) {
-      const int row = i0 + wr * 64 + (TA ? 16 * (rt >> 1) + 2 * lr + (rt & 1) : rt * 8 + lr);
+    for (int rt = 0; rt < RTN; rt++) {
+      const int row = i0 + rbase + (TA ? 16 * (rt >> 1) + 2 * lr + (rt & 1) : rt * 8 + lr);
       double *crow = C + (int64_t)row * g.ldc + j0 + wc * 32;
       if (!TB) {
 #pragma unroll
@@ -772,6 +778,7 @@ cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   static bool attr_done[MGP_MAX_DEVICES] = {};
   if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_dgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(k_dgemm<false, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
@@ -782,11 +789,15 @@ cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   int *sched = sched_words(st);
   if (!sched) return cudaErrorMemoryAllocation;
-  const int total = (g.N / 128) * (g.M / 128) * g.n_inner * g.n_outer;
-  int grid = total < sm_count ? total : sm_count;
-  if (g_gemm_cta_cap > 0 && grid > g_gemm_cta_cap) grid = g_gemm_cta_cap;
+  int total = (g.N / 128) * (g.M / 128) * g.n_inner * g.n_outer;
+  int limit = sm_count;
+  if (g_gemm_cta_cap > 0 && limit > g_gemm_cta_cap) limit = g_gemm_cta_cap;
+  const bool half = !g.ta && !g.tb && g.kmode == 0 && 2 * total <= limit;   // see k_dgemm: MT = 64
+  if (half) total *= 2;
+  const int grid = total < limit ? total : limit;
   const int threads = GEMM_CONSUMERS + GEMM_PRODUCERS;
-  if (!g.ta && !g.tb) k_dgemm<false, false><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  if (half) k_dgemm<false, false, 64><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  else if (!g.ta && !g.tb) k_dgemm<false, false><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else if (!g.ta && g.tb) k_dgemm<false, true><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else if (g.ta && !g.tb) k_dgemm<true, false><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else k_dgemm<true, true><<<grid, threads, GEMM_SMEM, st>>>(g, sched);

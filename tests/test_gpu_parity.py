@@ -379,6 +379,37 @@ def test_likelihood_oracle_larger_n(kind, mode, n, d):
             assert np.max(np.abs(grad[b] - rg)) < 1e-6 * np.abs(rg).max() + 1e-7, (b, grad[b], rg)
 
 
+@pytest.mark.parametrize("kind", ["squared_exponential", "matern", "absolute_exponential"])
+def test_likelihood_with_zero_theta(kind):
+    """A theta_i of exactly 0 cannot be folded into the staged coordinates (the R build and the
+    gradient kernel scale them by sqrt(theta_i) or theta_i): such vectors take the unscaled loops.
+    Both branches in one batch, llf and the FULL gradient (including d/d theta_i at theta_i = 0)
+    against the oracle."""
+    mb, O = _mods()
+    rng = np.random.default_rng(23)
+    n, d = 300, 5
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    y = (y - y.mean()) / y.std()
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr=kind, theta0=0.1 * np.ones(d),
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=1e-6)
+    gp._check_data(X, y)
+    scale = 0.3 / d
+    P = scale * 10.0 ** rng.uniform(-0.3, 0.3, (4, d))
+    P[1, 2] = 0.0
+    P[3, 0] = 0.0
+    P[3, 4] = 0.0
+    P = np.c_[P, rng.uniform(0.5, 1.0, 4)]
+    llf, grad, status = gp.log_likelihood_batch(P, eval_grad=True)
+    assert np.all(status == 0)
+    for b in range(4):
+        rl, rg = O.log_likelihood_concentrated(X, y, P[b], kind, True, 0.0, "noisy", 1e-6, eval_grad=True)
+        rl = float(np.ravel(rl)[0])
+        rg = np.ravel(rg)
+        assert abs(llf[b] - rl) < 1e-8 * abs(rl) + 1e-7, (b, llf[b], rl)
+        assert np.max(np.abs(grad[b] - rg)) < 1e-6 * np.abs(rg).max() + 1e-7, (b, grad[b], rg)
+
+
 def test_ragged_and_tiny_inputs():
     mb, O = _mods()
     st = synth_model(O, 130, 3, "squared_exponential", seed=3)
