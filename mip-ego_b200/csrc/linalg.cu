@@ -463,9 +463,11 @@ __device__ __forceinline__ void bar_side() { asm volatile("bar.sync 1, 480;\n" :
 // Block row i >= 1 of the inverse, in place: rows < i of S already hold the inverse (diagonal
 // sub-blocks included), row i still holds L (already saved by the caller).  ALL: executed by the
 // whole CTA (__syncthreads) or by warps 1..15 only (bar_side).
-// (A DMMA version of these small products was measured SLOWER: 8 x 8 x 4 fragments read from a
-// row stride of 129 doubles hit 4-way bank conflicts and a dependent DMMA chain costs ~150 cycles
-// per step; tools/diag_bench.cu, 63 us against 56 us for the whole kernel.)
+// (A DMMA version of these small products was measured SLOWER, 63 us against 56 us for the whole
+// kernel (tools/diag_bench.cu): 8 x 8 x 4 fragments read with LDS.64 from a row stride of 129
+// doubles hit 4-way bank conflicts, i.e. 16 shared-memory cycles per DMMA for the whole SM against
+// an issue interval of 16.7 cycles per DMMA and sub-partition (tools/fp64_lat.cu) -- the four
+// sub-partitions then wait on shared memory.  It needs a tile stride of 4 (mod 16) doubles.)
 template <bool ALL>
 __device__ __forceinline__ void inverse_block_row(double *S, const double *Xd, int i, int tid) {
   auto sync = [] { if (ALL) __syncthreads(); else bar_side(); };
