@@ -336,19 +336,32 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
 //   P = A D^-T and the symmetric update of the remaining rows.
 // The inverse of the whole block follows from the four 32x32 inverses by block rows:
 //   X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj).
-constexpr int DS = 129;   // smem row stride of the 128x128 block
-constexpr int XS = 33;    // row stride of a 32x32 inverse
+// Row strides of 4 (mod 16) doubles: the 8x8x4 DMMA fragments of the small products (lane (lr, lk)
+// reads element [lr][lk] or [lk][lr]) then fall on 16 distinct bank pairs per half-warp.  Per-lane
+// row accesses (lane = row) would be 8-way conflicted at this stride; the one place that needs
+// them, the register factorisation of a 32x32 sub-block, goes through a stride-33 scratch copy.
+constexpr int DS = 132;   // smem row stride of the 128x128 block
+constexpr int XS = 36;    // row stride of a 32x32 inverse
+constexpr int PS = 33;    // row stride of the factorisation scratch (inside one XS-strided slot)
 constexpr int DIAG_THREADS = 512;
 constexpr int kDiagSmemDbl = 128 * DS + 4 * 32 * XS + 64 + 4 * 32;
 
-__device__ __forceinline__ void warp_potrf32(double *D, double *col, int lane, int pivot0,
+__device__ __forceinline__ void warp_potrf32(double *D, double *scr, double *col, int lane, int pivot0,
                                              int *status) {
   // Straight-line code (fully unrolled, no branches): the critical path per pivot is
   // shuffle -> rsqrt -> multiply -> smem broadcast -> one FMA; the remaining updates of the step
-  // overlap the next pivot's latency.  `col` is double-buffered (2 x 32 doubles).
+  // overlap the next pivot's latency.  `col` is double-buffered (2 x 32 doubles).  The sub-block
+  // travels through `scr` (32 x PS): row-wise copies with lane = column, register loads with lane = row.
   double a[32];
+  // all loads first, then all stores: D and scr may alias as far as the compiler knows, and a
+  // load-store-load chain would serialise on shared-memory latency
 #pragma unroll
-  for (int k = 0; k < 32; k++) a[k] = D[lane * DS + k];
+  for (int r = 0; r < 32; r++) a[r] = D[r * DS + lane];
+#pragma unroll
+  for (int r = 0; r < 32; r++) scr[r * PS + lane] = a[r];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 32; k++) a[k] = scr[lane * PS + k];
   int bad = 0;
 #pragma unroll
   for (int j = 0; j < 32; j++) {
@@ -365,7 +378,13 @@ __device__ __forceinline__ void warp_potrf32(double *D, double *col, int lane, i
   }
   if (bad && lane == 0) atomicCAS(status, 0, bad);
 #pragma unroll
-  for (int k = 0; k < 32; k++) D[lane * DS + k] = (k <= lane) ? a[k] : 0.0;
+  for (int k = 0; k < 32; k++) scr[lane * PS + k] = (k <= lane) ? a[k] : 0.0;
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 32; r++) a[r] = scr[r * PS + lane];
+#pragma unroll
+  for (int r = 0; r < 32; r++) D[r * DS + lane] = a[r];
+  __syncwarp();
 }
 
 // X = D^-1 for a 32x32 lower-triangular D (stride DS); lane owns column `lane` of X.
@@ -462,56 +481,71 @@ __device__ __forceinline__ void bar_side() { asm volatile("bar.sync 1, 480;\n" :
 
 // Block row i >= 1 of the inverse, in place: rows < i of S already hold the inverse (diagonal
 // sub-blocks included), row i still holds L (already saved by the caller).  ALL: executed by the
-// whole CTA (__syncthreads) or by warps 1..15 only (bar_side).
-// (A DMMA version of these small products was measured SLOWER, 63 us against 56 us for the whole
-// kernel (tools/diag_bench.cu): 8 x 8 x 4 fragments read with LDS.64 from a row stride of 129
-// doubles hit 4-way bank conflicts, i.e. 16 shared-memory cycles per DMMA for the whole SM against
-// an issue interval of 16.7 cycles per DMMA and sub-partition (tools/fp64_lat.cu) -- the four
-// sub-partitions then wait on shared memory.  It needs a tile stride of 4 (mod 16) doubles.)
+// whole CTA (16 warps, __syncthreads) or by warps 1..15 only (bar_side).  The 32 x 32 i block row
+// is cut into 8 x 8 DMMA tiles, dealt round-robin to the warps; the small products run on the
+// tensor pipe because 4 x 4 register patches fed by scalar shared-memory loads are bound by
+// shared-memory bandwidth (8 loads per 16 FMAs; one fragment pair feeds 256).  With the row stride
+// DS = 4 (mod 16) every fragment load is conflict-free (at stride 129 they were 4-way conflicted
+// and this version was slower than the patches: 63 against 56 us for the whole kernel).
 template <bool ALL>
 __device__ __forceinline__ void inverse_block_row(double *S, const double *Xd, int i, int tid) {
   auto sync = [] { if (ALL) __syncthreads(); else bar_side(); };
-  constexpr int NT = ALL ? DIAG_THREADS : DIAG_THREADS - 32;
-  const int t = ALL ? tid : tid - 32;
-  // block row i: 32 rows x 32 i columns = 8 x 8 i patches of 4 x 4, one per thread.  Lanes run over
-  // the row patches: the column-patch reads then are broadcasts and the row reads (rows four apart,
-  // stride 129) at most 2-way conflicts; the other order made the threads of a warp read addresses
-  // 32 bytes apart (8-way conflicts).
-  const int npc = 8 * i;
-  const bool on = t < 8 * npc;
-  const int pr = t & 7, pc = t >> 3;
-  const int r0 = 32 * i + 4 * pr, c0 = 4 * pc, j = c0 >> 5;
-  double acc[4][4];
-  // T_ij = sum_{k=j}^{i-1} L_ik X_kj
+  constexpr int NW = ALL ? DIAG_THREADS / 32 : DIAG_THREADS / 32 - 1;
+  constexpr int NT = NW * 32;
+  const int t = ALL ? tid : tid - 32, w = t >> 5, lane = t & 31, lr = lane >> 2, lk = lane & 3;
+  const int ntile = 16 * i;             // 4 tile rows x 4 i tile columns
+  constexpr int MAXT = 4;               // ceil(48 / 15)
+  double acc[MAXT][2];
+  // T_ij = sum_{k=j}^{i-1} L_ik X_kj : tile (tr, tc), k from 32 (tc / 4) to 32 i
 #pragma unroll
-  for (int u = 0; u < 4; u++)
-#pragma unroll
-    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
-  if (on) patch4x4<false>(acc, S + r0 * DS, DS, S + c0, DS, 32 * j, 32 * i);
+  for (int x = 0; x < MAXT; x++) {
+    acc[x][0] = acc[x][1] = 0.0;
+    const int tl = w + NW * x;
+    if (tl < ntile) {
+      const int tr = tl & 3, tc = tl >> 2;
+      const double *ap = S + (32 * i + 8 * tr + lr) * DS + lk;
+      const double *bp = S + lk * DS + 8 * tc + lr;
+      for (int k = 32 * (tc >> 2); k < 32 * i; k += 4) dmma884(acc[x][0], acc[x][1], ap[k], bp[k * DS]);
+    }
+  }
   sync();
-  if (on) {
 #pragma unroll
-    for (int u = 0; u < 4; u++)
-#pragma unroll
-      for (int v = 0; v < 4; v++) S[(r0 + u) * DS + c0 + v] = acc[u][v];
+  for (int x = 0; x < MAXT; x++) {
+    const int tl = w + NW * x;
+    if (tl < ntile) {
+      const int tr = tl & 3, tc = tl >> 2;
+      double *cp = S + (32 * i + 8 * tr + lr) * DS + 8 * tc + 2 * lk;
+      cp[0] = acc[x][0];
+      cp[1] = acc[x][1];
+    }
   }
   for (int idx = t; idx < 32 * 32; idx += NT) {   // X_ii replaces L_ii
     const int r = idx >> 5, c = idx & 31;
     S[(32 * i + r) * DS + 32 * i + c] = Xd[i * 32 * XS + r * XS + c];
   }
   sync();
-  // X_ij = -X_ii T_ij   (X_ii lower triangular: k <= row)
+  // X_ij = -X_ii T_ij   (X_ii lower triangular: k < 8 (tr + 1))
 #pragma unroll
-  for (int u = 0; u < 4; u++)
-#pragma unroll
-    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
-  if (on) patch4x4<false>(acc, S + r0 * DS + 32 * i, DS, S + 32 * i * DS + c0, DS, 0, 4 * pr + 4);
+  for (int x = 0; x < MAXT; x++) {
+    acc[x][0] = acc[x][1] = 0.0;
+    const int tl = w + NW * x;
+    if (tl < ntile) {
+      const int tr = tl & 3, tc = tl >> 2;
+      const double *ap = S + (32 * i + 8 * tr + lr) * DS + 32 * i + lk;
+      const double *bp = S + (32 * i + lk) * DS + 8 * tc + lr;
+      for (int k = 0; k < 8 * (tr + 1); k += 4) dmma884(acc[x][0], acc[x][1], ap[k], bp[k * DS]);
+    }
+  }
   sync();
-  if (on) {
 #pragma unroll
-    for (int u = 0; u < 4; u++)
-#pragma unroll
-      for (int v = 0; v < 4; v++) S[(r0 + u) * DS + c0 + v] = -acc[u][v];
+  for (int x = 0; x < MAXT; x++) {
+    const int tl = w + NW * x;
+    if (tl < ntile) {
+      const int tr = tl & 3, tc = tl >> 2;
+      double *cp = S + (32 * i + 8 * tr + lr) * DS + 8 * tc + 2 * lk;
+      cp[0] = -acc[x][0];
+      cp[1] = -acc[x][1];
+    }
   }
   sync();
 }
@@ -561,7 +595,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag(double *A, double *
   for (int s = 0; s < 4; s++) {
     const int o = 32 * s, nb = 96 - o;   // nb rows below the sub-block
     if (warp == 0) {
-      warp_potrf32(S + o * DS + o, col, lane, kb * 128 + o, &status[b]);
+      warp_potrf32(S + o * DS + o, Xd + s * 32 * XS, col, lane, kb * 128 + o, &status[b]);
       __syncwarp();
 #ifdef DIAG_PROFILE
       if (s == 0 && lane == 0 && blockIdx.x == 0) g_diag_clk[8] = clock64();
@@ -583,59 +617,61 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag(double *A, double *
     __syncthreads();
     if (s == 0) DIAG_T(2);
     if (nb > 0) {
-      // sub-panel P = A[below][o:o+32] D^-T : P[r][c] = sum_k A[r][o+k] X[c][k]  (X[c][k] = 0 for k > c)
+      // sub-panel P = A[below][o:o+32] D^-T : P[r][c] = sum_k A[r][o+k] X[c][k]  (X[c][k] = 0 for k > c).
+      // Warp w owns the 8-row strip w (4 DMMA tiles): it reads and overwrites only its own rows.
       const double *X = Xd + s * 32 * XS;
-      {
-        const bool on = tid < (nb / 4) * 8;
-        const int pr = tid >> 3, pc = tid & 7;
-        double acc[4][4];
+      const int lr = lane >> 2, lk = lane & 3;
+      if (warp < nb / 8) {
+        double *row = S + (o + 32 + 8 * warp + lr) * DS + o;
+        double acc[4][2];
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int tc = 0; tc < 4; tc++) acc[tc][0] = acc[tc][1] = 0.0;
 #pragma unroll
-          for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
-        if (on) patch4x4<true>(acc, S + (o + 32 + 4 * pr) * DS + o, DS, X + 4 * pc * XS, XS, 0, 32);
-        __syncthreads();
-        if (on) {
+        for (int k = 0; k < 32; k += 4) {
+          const double a = row[k + lk];
 #pragma unroll
-          for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int v = 0; v < 4; v++) S[(o + 32 + 4 * pr + u) * DS + o + 4 * pc + v] = acc[u][v];
+          for (int tc = 0; tc < 4; tc++)
+            if (k < 8 * (tc + 1)) dmma884(acc[tc][0], acc[tc][1], a, X[(8 * tc + lr) * XS + k + lk]);
         }
-        __syncthreads();
+        __syncwarp();
+#pragma unroll
+        for (int tc = 0; tc < 4; tc++) {
+          row[8 * tc + 2 * lk] = acc[tc][0];
+          row[8 * tc + 2 * lk + 1] = acc[tc][1];
+        }
       }
+      __syncthreads();
       if (s == 0) DIAG_T(9);
-      // symmetric update of the remaining rows: A[r][c] -= sum_k P[r][k] P[c][k]  (c <= r).
-      // A patch owns the INTERLEAVED rows pr + u np and columns pc + v np (np = nb / 4): the
-      // threads of a warp then read consecutive rows of P (row stride 129: conflict-free) instead
-      // of rows four apart (6-way bank conflicts), and (u, v) is needed iff v < u, or v == u and
-      // pc <= pr -- ten products per k instead of sixteen.
-      const int np = nb / 4;
-      const double *P = S + (o + 32) * DS + o;
-      for (int e = tid; e < np * np; e += DIAG_THREADS) {
-        const int pr = e / np, pc = e - pr * np;
-        double acc[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-          for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < 32; k++) {
-          double a[4], bq[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) a[u] = P[(pr + u * np) * DS + k];
-#pragma unroll
-          for (int v = 0; v < 4; v++) bq[v] = P[(pc + v * np) * DS + k];
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int v = 0; v <= u; v++) acc[u][v] = fma(a[u], bq[v], acc[u][v]);
-        }
+      // symmetric update of the remaining rows: A[r][c] -= sum_k P[r][k] P[c][k]  (c <= r): the lower
+      // 8 x 8 tiles of the (nb / 8)^2 tile grid, dealt round-robin to the 16 warps (at most 5 each)
+      {
+        const int np8 = nb / 8, ntile = np8 * (np8 + 1) / 2;
+        const double *P = S + (o + 32) * DS + o;
         double *Cp = S + (o + 32) * DS + o + 32;
+        double acc[5][2];
+        int trv[5], tcv[5];
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int x = 0; x < 5; x++) {
+          acc[x][0] = acc[x][1] = 0.0;
+          const int tl = warp + 16 * x;
+          int tr = 0;
+          while ((tr + 1) * (tr + 2) / 2 <= tl) tr++;
+          trv[x] = tr;
+          tcv[x] = tl - tr * (tr + 1) / 2;
+        }
 #pragma unroll
-          for (int v = 0; v <= u; v++)
-            if (v < u || pc <= pr) Cp[(pr + u * np) * DS + pc + v * np] -= acc[u][v];
+        for (int k = 0; k < 32; k += 4)
+#pragma unroll
+          for (int x = 0; x < 5; x++)
+            if (warp + 16 * x < ntile)
+              dmma884(acc[x][0], acc[x][1], P[(8 * trv[x] + lr) * DS + k + lk], P[(8 * tcv[x] + lr) * DS + k + lk]);
+#pragma unroll
+        for (int x = 0; x < 5; x++)
+          if (warp + 16 * x < ntile) {
+            const int r = 8 * trv[x] + lr, c = 8 * tcv[x] + 2 * lk;
+            if (c <= r) Cp[r * DS + c] -= acc[x][0];
+            if (c + 1 <= r) Cp[r * DS + c + 1] -= acc[x][1];
+          }
       }
       __syncthreads();
       if (s == 0) DIAG_T(3);
