@@ -387,11 +387,12 @@ static void fill_work(mgp_handle *h, NllWork &w, int b_off, int B, int cap, int 
 // only a few SMs (diagonal blocks, panel solves); running the groups on separate streams lets the
 // wide kernels of one group fill the machine while another group is in such a phase.
 static int nll_groups(const mgp_handle *h, int nb) {
-  // default: more groups for larger matrices -- below ~2000 rows the host cannot launch the small
-  // kernels of many groups fast enough and a single stream is quicker (measured: n = 512: 9.0k
-  // evaluations/s with 1 group, 3.3k with 8; n = 4096: 300 with 1, 359 with 8)
+  // default: more groups for larger matrices -- for small matrices batching the short kernels of all
+  // evaluations into one launch beats overlapping them (measured, 8 evaluations per call, evaluations/s
+  // with 1 / 2 / 4 / 8 groups: n = 768: 8205 / 8001 / 7468 / 5990; n = 1024: 6172 / 6145 / 5774 / 4962;
+  // n = 1536: 3310 / 3328 / 3292 / 3109; n = 2048: 1899 / 1993 / 2042 / 1953; n = 3072: 755 / 788 / 813 / 825)
   int g = h->nll_groups_opt > 0 ? h->nll_groups_opt
-          : (h->npad <= 768 ? 1 : (h->npad <= 1536 ? 2 : (h->npad <= 3072 ? 4 : MGP_NLL_STREAMS)));
+          : (h->npad <= 768 ? 1 : (h->npad <= 1536 ? 2 : (h->npad <= 2560 ? 4 : MGP_NLL_STREAMS)));
   if (g > MGP_NLL_STREAMS) g = MGP_NLL_STREAMS;
   if (g > nb) g = nb;
   return g < 1 ? 1 : g;
