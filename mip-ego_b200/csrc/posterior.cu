@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) k_rgen_l1(RgenParams p) {
   double *sC = sX + DPAD * XS;        // [128][CS]    candidate block
   double *sTh = sC + 128 * CS;        // [DPAD]
   double *sV = sTh + DPAD;            // gamma | avec
-  double *sTab = sV + 2 * 128;        // 2^(j/32), 16 replicas
+  double *sTab = sV + 2 * 128;        // 2^(j/64), 16 replicas
   exp_tab_fill(sTab, threadIdx.x, 256);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lr = lane >> 2, lk = lane & 3;
   const int nItems = p.nCblk * p.JS;
