@@ -1,10 +1,11 @@
-# Round-1 (third session) evidence refresh after the likelihood-path changes: final bench lines, the
-# NLL launch list (one batch group = serialised) and `ncu --set full` of the changed GEMM / diag kernels.
-set -x
+# Round-1 (third session) final evidence: bench lines, launch lists of the C2 and likelihood workloads
+# (likelihood with one batch group = serialised), `ncu --set full` of the kernels changed in this session.
+# Exports CSV/text summaries only (the .ncu-rep files exceed the 64 MiB gpurun_out limit); copy what is kept into profiles/.
 for w in c1 c2 c3 c5; do python bench.py --workload $w --steps 6 --warmup 3 > gpurun_out/s3_${w}.json 2> gpurun_out/s3_${w}.err; done
 python bench.py --workload nll --steps 8 --warmup 3 > gpurun_out/s3_nll.json 2> gpurun_out/s3_nll.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/s3_ref_c2.json 2> gpurun_out/s3_ref.err
-python bench.py --workload nll --steps 1 --warmup 3 --no-cpu-baseline --nll-groups 1 > gpurun_out/plain_nll_s3.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2_s3.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_c2_s3.log 2>&1
+python tools/agg_launches.py gpurun_out/launches_c2_s3.csv > gpurun_out/launches_c2_s3_summary.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 130 --csv --log-file gpurun_out/launches_nll_s3.csv python bench.py --workload nll --steps 1 --warmup 0 --no-cpu-baseline --nll-groups 1 > gpurun_out/ncu_nll_s3.log 2>&1
 python tools/agg_launches.py gpurun_out/launches_nll_s3.csv > gpurun_out/launches_nll_s3_summary.txt
 cap() { # name, kernel regex, skip, count, bench args...
@@ -12,13 +13,18 @@ cap() { # name, kernel regex, skip, count, bench args...
   ncu --set full --clock-control none --import-source on -k regex:$rx --launch-skip $sk --launch-count $cn -o /tmp/$name -f python bench.py "$@" > gpurun_out/ncu_$name.log 2>&1
   ncu -i /tmp/$name.ncu-rep --page raw --csv > gpurun_out/${name}_raw.csv 2>/dev/null
   ncu -i /tmp/$name.ncu-rep --page details > gpurun_out/${name}_details.txt 2>/dev/null
+  python tools/ncu_summary.py gpurun_out/${name}_raw.csv > gpurun_out/${name}_summary.txt
   rm -f /tmp/$name.ncu-rep
 }
-# k_dgemm launches of one evaluation batch (G = 1): 66 x <0,0>, then 10 x <0,1> (trtri), then <1,1> (M^T M)
-cap dgemm_lauum_s3 'k_dgemm<1' 0 1 --workload nll --steps 1 --warmup 0 --no-cpu-baseline --nll-groups 1
-cap dgemm_trtri_s3 'k_dgemm<0, 1' 9 1 --workload nll --steps 1 --warmup 0 --no-cpu-baseline --nll-groups 1
+cap rgen_c2_s3 k_rgen 12 1 --steps 2 --warmup 3 --no-cpu-baseline
+cap trmm_c2_s3 k_trmm 12 1 --steps 2 --warmup 3 --no-cpu-baseline
+# k_dgemm launches of one evaluation batch (G = 1): #7 = first k = 512 trailing update, #70/#71 = top-level TRTRI, #72 = M^T M
+cap dgemm_tri_s3 k_dgemm 70 3 --workload nll --steps 1 --warmup 0 --no-cpu-baseline --nll-groups 1
+cap dgemm_upd_s3 k_dgemm 7 1 --workload nll --steps 1 --warmup 0 --no-cpu-baseline --nll-groups 1
 cap potrf_diag_s3 k_potrf_diag 3 1 --workload nll --steps 1 --warmup 0 --no-cpu-baseline --nll-groups 1
 cap buildR_s3 k_build_R 0 1 --workload nll --steps 1 --warmup 0 --no-cpu-baseline --nll-groups 1
 cap nllgrad_s3 k_nll_grad 0 1 --workload nll --steps 1 --warmup 0 --no-cpu-baseline --nll-groups 1
-for f in dgemm_lauum_s3 dgemm_trtri_s3 potrf_diag_s3 buildR_s3 nllgrad_s3; do python tools/ncu_summary.py gpurun_out/${f}_raw.csv > gpurun_out/${f}_summary.txt; done
-ls -la gpurun_out | tail -30; du -sh gpurun_out
+timeout 60 tools/diag_bench > gpurun_out/diag_bench_s3.txt 2>&1
+tools/fp64_lat > gpurun_out/fp64_lat_s3.json 2>&1
+tools/exp_check > gpurun_out/exp_check_s3.json 2>&1
+du -sh gpurun_out
