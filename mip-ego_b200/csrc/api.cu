@@ -897,9 +897,15 @@ static int host_run(mgp_handle *h, int64_t m, const double *Xs, PostReq q, const
     q.d_topv = reinterpret_cast<double *>(q.d_topi + (size_t)ns * q.topk);
   }
   cudaStream_t st = h->stream, cs = h->copy_stream, os = h->out_stream;
+  // Ramp: the H2D of the first unit is the one copy no kernel can hide, so large populations start
+  // with an eighth of a unit, then half a unit (its copy fits under the first unit's kernels), then
+  // full units -- the exposed copy shrinks from 12 MB to 1.5 MB at C2 (10^6 candidates, d = 10).
+  const int64_t ramp0 = round_up(std::max<int64_t>(unit / 8, (int64_t)h->sm_count * 128), 128);
+  const bool ramp = m >= 3 * unit && ramp0 * 4 <= unit;
   int it = 0;
-  for (int64_t s0 = 0; s0 < m; s0 += unit, it++) {
-    const int64_t ms = std::min(unit, m - s0);
+  for (int64_t s0 = 0, ms = 0; s0 < m; s0 += ms, it++) {
+    const int64_t want = !ramp ? unit : (it == 0 ? ramp0 : (it == 1 ? round_up(unit / 2, 128) : unit));
+    ms = std::min(want, m - s0);
     const int buf = it & 1;
     if (it >= 2) MGP_CUDA(h, cudaStreamWaitEvent(cs, h->ev_done[buf], 0));   // input buffer free
     MGP_CUDA(h, cudaMemcpyAsync(h->dXs_stage[buf].p, Xs + s0 * d, (size_t)ms * d * 8, cudaMemcpyHostToDevice, cs));
