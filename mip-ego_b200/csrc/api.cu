@@ -418,18 +418,33 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
     // (diagonal blocks, panel solves) then start without waiting for a machine-wide GEMM to drain
     if (G > 1 && h->gemm_cap_opt == 0) set_dgemm_cta_cap(h->sm_count * 3 / 4);
     if (G > 1) MGP_CUDA(h, cudaEventRecord(h->ev_fork, st));
+    NllWork works[MGP_NLL_STREAMS];
+    int gsize[MGP_NLL_STREAMS], gfirst[MGP_NLL_STREAMS];
+    int nph = 0;
     for (int g = 0; g < G; g++) {
       const int g0 = (int)((int64_t)nb * g / G), g1 = (int)((int64_t)nb * (g + 1) / G);
+      gfirst[g] = g0; gsize[g] = g1 - g0;
       if (g1 == g0) continue;
-      cudaStream_t gs = G > 1 ? h->nll_stream[g] : st;
-      if (G > 1) MGP_CUDA(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
-      NllWork w;
-      fill_work(h, w, g0, g1 - g0, use, n_par, mode, noise_var, eval_grad,
+      if (G > 1) MGP_CUDA(h, cudaStreamWaitEvent(h->nll_stream[g], h->ev_fork, 0));
+      fill_work(h, works[g], g0, g1 - g0, use, n_par, mode, noise_var, eval_grad,
                 d_params + (size_t)(b0 + g0) * n_par, d_out_llf + b0 + g0,
                 eval_grad ? d_out_grad + (size_t)(b0 + g0) * n_par : nullptr);
-      MGP_CUDA(h, nll_pipeline(w, gs, &h->launches));
+      nph = nll_num_phases(works[g]);
+    }
+    // phase by phase, group by group: every group has its first kernels queued at once (issuing
+    // the ~100 launches of one group after the other delayed the last of 8 groups by milliseconds,
+    // which a caller that synchronises after every batch -- the L-BFGS-B driver -- pays in full)
+    for (int ph = 0; ph < nph; ph++)
+      for (int g = 0; g < G; g++) {
+        if (gsize[g] == 0) continue;
+        MGP_CUDA(h, nll_pipeline(works[g], G > 1 ? h->nll_stream[g] : st, &h->launches, G > 1 ? ph : -1));
+        if (G == 1) ph = nph;   // a single group runs the whole pipeline in one call
+      }
+    for (int g = 0; g < G; g++) {
+      if (gsize[g] == 0) continue;
+      cudaStream_t gs = G > 1 ? h->nll_stream[g] : st;
       if (d_out_status)
-        MGP_CUDA(h, cudaMemcpyAsync(d_out_status + b0 + g0, w.status, sizeof(int) * (g1 - g0),
+        MGP_CUDA(h, cudaMemcpyAsync(d_out_status + b0 + gfirst[g], works[g].status, sizeof(int) * gsize[g],
                                     cudaMemcpyDeviceToDevice, gs));
       if (G > 1) {
         MGP_CUDA(h, cudaEventRecord(h->ev_join[g], gs));

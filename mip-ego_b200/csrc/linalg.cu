@@ -872,9 +872,11 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
     if (e__ != cudaSuccess) return e__; \
   } while (0)
 
+int chol_panels(int npad) { return (npad / 128 + 3) / 4; }
+
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
-                         bool clean_upper) {
+                         bool clean_upper, int panel_lo, int panel_hi) {
   // Two-level right-looking blocked Cholesky.  Tiles are 128 wide; PB tiles form a panel.  Inside a
   // panel every tile column is factored (diagonal block, TRSM through the explicit inverse of the
   // diagonal block) and applied to the remaining columns OF THE PANEL only (k = 128); the matrix
@@ -884,10 +886,12 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
   // Nothing on the likelihood path reads the tiles above the block diagonal of L (or of L^-1), so
   // they are only zeroed when the factor is going to be exported (fitted state): for a batch of
   // likelihood evaluations that saves writing 2 x npad^2 doubles per evaluation.
-  if (clean_upper)
+  // panels [panel_lo, panel_hi) of PB tile columns each (callers that interleave the launches of
+  // several batch groups walk the panels one at a time); the whole factorisation is [0, chol_panels)
+  if (clean_upper && panel_lo == 0)
     for (int b = 0; b < batch; b++)
       LA_TRY(cudaMemsetAsync(L + b * sA, 0, sizeof(double) * (size_t)npad * npad, st));
-  for (int k0 = 0; k0 < NI; k0 += PB) {
+  for (int k0 = panel_lo * PB; k0 < NI && k0 < panel_hi * PB; k0 += PB) {
     const int k1 = k0 + PB < NI ? k0 + PB : NI;
     for (int kb = k0; kb < k1; kb++) {
       LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, kb, status, batch, st));

@@ -36,9 +36,11 @@ cudaError_t launch_potrf_diag(double *A, double *Lout, int ld, int64_t sA, doubl
 cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv, int64_t sInv,
                               int NI, int batch, cudaStream_t st);
 // Full blocked Cholesky A -> L (lower, row-major npad x npad, A is destroyed) + diag inverses.
+// Only the panels [panel_lo, panel_hi) of 4 tile columns are processed (all: 0 .. chol_panels(npad)).
+int chol_panels(int npad);
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
-                         bool clean_upper);
+                         bool clean_upper, int panel_lo, int panel_hi);
 // Minv = L^-1 given L and the diagonal-block inverses; T is scratch (npad x npad per matrix).
 cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, int64_t sMat,
                           const double *linv, int64_t sInv, int batch, cudaStream_t st,

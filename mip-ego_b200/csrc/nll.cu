@@ -727,9 +727,18 @@ cudaError_t launch_dup_check(const double *Xc, int n, int dpad, int *flag, cudaS
   return cudaGetLastError();
 }
 
-cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
+int nll_num_phases(const NllWork &w) { return w.have_L ? 2 : chol_panels(w.npad) + 2; }
+
+// phase < 0: the whole pipeline.  Otherwise phase 0 builds R (or inverts the diagonal blocks of a
+// given L), phases 1 .. P factor one Cholesky panel each and the last phase does the rest; a caller
+// with several batch groups on concurrent streams issues phase by phase, group by group, so that
+// every group has work queued within microseconds instead of after the ~100 launches of each
+// preceding group (mgp_nll_batch_dev).
+cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, int phase) {
   const int npad = w.npad, n = w.n, B = w.B, NI = npad / 128;
   const int64_t sM = (int64_t)npad * npad;
+  const int last = nll_num_phases(w) - 1;
+  if (phase <= 0) {
   NL_TRY(cudaMemsetAsync(w.status, 0, sizeof(int) * B, st));
   if (w.have_L) {
     NL_TRY(launch_trtri_diag(w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, NI, B, st));
@@ -762,9 +771,15 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches) {
     NL_TRY(cudaGetLastError());
     (*launches)++;
   }
-  if (!w.have_L)
-    NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches,
-                        w.want_bhat != 0));
+  }
+  if (!w.have_L) {
+    const int P = chol_panels(npad);
+    const int lo = phase < 0 ? 0 : phase - 1, hi = phase < 0 ? P : phase;
+    if (phase < 0 || (phase >= 1 && phase <= P))
+      NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches,
+                          w.want_bhat != 0, lo, hi));
+  }
+  if (phase >= 0 && phase != last) return cudaSuccess;
   NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches,
                        w.want_bhat != 0));
   double *Yt = w.Yt, *Ft = w.Ft, *rho = w.rho, *gamma = w.gamma;

@@ -57,6 +57,9 @@ enum { NLL_SIGMA2 = 0, NLL_LLF = 1, NLL_FTF = 2, NLL_FTY = 3, NLL_RR = 4, NLL_LO
        NLL_V = 7, NLL_BETA = 8, NLL_NV = 9, NLL_COEFA = 10, NLL_THSCALE = 11, NLL_LOGDETA = 12 };
 // number of hyper-parameters of a mode for d features (include/mgp.h)
 int nll_n_par(int mode, int d);
-cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches);
+// phase < 0 runs everything; otherwise one of nll_num_phases(w) phases (R build | one Cholesky panel
+// each | the rest), so that a caller can interleave the launches of several batch groups.
+int nll_num_phases(const NllWork &w);
+cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, int phase = -1);
 // flag[0] |= 1 if two of the n rows of Xc (npad x dpad) coincide (gpr.py:274-277).
 cudaError_t launch_dup_check(const double *Xc, int n, int dpad, int *flag, cudaStream_t st);
