@@ -120,6 +120,42 @@ def test_c4_likelihood_gradient_vs_differences():
     assert np.array_equal(llf1, llf[:3]) and np.array_equal(grad1, grad[:3])
 
 
+def test_host_api_ramped_staging_units():
+    """Host-pointer calls on populations of at least three compute chunks start with 1/8 and 1/2 of a
+    chunk so that only a small first H2D copy is exposed (api.cu, host_run): same numbers, bit for
+    bit, as the un-ramped schedule of a smaller chunk size; top-1 across the ragged units too."""
+    import mipego_b200 as mb
+    rng = np.random.default_rng(77)
+    n, d = 60, 3
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1)
+    y = (y - y.mean()) / y.std()
+    theta = np.full(d, 0.05)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential", theta0=theta,
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=1e-6)
+    gp.fit_fixed(X, y, np.r_[theta, 0.9])
+    h = gp._handle()
+    h.set_option("chunk", 0)
+    ei = mb.EI(model=gp, minimize=True)
+    ei.evaluate(X[:4])                                     # sizes the workspace: default chunk
+    chunk = h.counter("chunk")
+    assert chunk >= 4 * 148 * 128
+    m = 3 * int(chunk) + 12345                             # ramp active, ragged last unit
+    Xs = rng.uniform(-5, 5, (m, d))
+    v_ramp = ei.evaluate(Xs)
+    mean_r, mse_r = gp.predict(Xs, eval_MSE=True)
+    tv_r, ti_r = ei.topk(Xs, k=1)
+    h.set_option("chunk", 32768)                           # below four ramp units: plain schedule
+    v_plain = ei.evaluate(Xs)
+    mean_p, mse_p = gp.predict(Xs, eval_MSE=True)
+    tv_p, ti_p = ei.topk(Xs, k=1)
+    h.set_option("chunk", 0)
+    assert np.array_equal(v_ramp, v_plain)
+    assert np.array_equal(mean_r, mean_p) and np.array_equal(mse_r, mse_p)
+    best = np.lexsort((np.arange(m), -np.ravel(v_plain)))[0]
+    assert ti_r[0, 0] == best == ti_p[0, 0] and tv_r[0, 0] == tv_p[0, 0] == np.ravel(v_plain)[best]
+
+
 def test_c5_shape_runs_and_is_consistent():
     """BASELINE configs[4] shape: n=8192, d=40, Matern-3/2, simple kriging, nugget 0."""
     import mipego_b200 as mb
