@@ -57,7 +57,22 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDesc &g, int id, int 
 // bounds are template parameters so that the zero part of a triangular operand's diagonal block is
 // skipped by warp-uniform branches over straight-line code: predicated-off DMMAs would still pay
 // their issue slots (profiles/r01_trmm_c2_v4_source_summary.txt).
-template <bool TA, bool TB, int RT0, int RT1, int CT1>
+// STAIR: diagonal output tile of a symmetric product (only the part on or below the diagonal is
+// wanted): per row tile rt only the column tiles below ct_hi are computed,
+//   1 / 2: k-contiguous operands, 8-granular:  ct <= rt + D,      D = 8 wr - 4 wc =  0 / -4
+//   3 / 4: k-major operands, 16-granular:      ct/2 <= rt/2 + D', D' = 4 wr - 2 wc = 0 / -2
+// (the warps with larger D compute everything, those with smaller D nothing: k_dgemm decides).
+template <int STAIR>
+__host__ __device__ constexpr int stair_ct_hi(int rt, int CT1) {
+  int hi = CT1;
+  if (STAIR == 1) hi = rt + 1;
+  if (STAIR == 2) hi = rt - 3;
+  if (STAIR == 3) hi = 2 * ((rt >> 1) + 1);
+  if (STAIR == 4) hi = 2 * ((rt >> 1) - 1);
+  return hi < 0 ? 0 : (hi > CT1 ? CT1 : hi);
+}
+
+template <bool TA, bool TB, int RT0, int RT1, int CT1, int STAIR = 0>
 __device__ __forceinline__ void mma_stage(double (&acc)[8][4][2], const double *as, const double *bs,
                                           int rbase, int wc, int lr, int lk) {
 #pragma unroll
@@ -95,6 +110,7 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][4][2], const double *
                              : (s2 ? a[rt].y : a[rt].x);
 #pragma unroll
         for (int ct = 0; ct < CT1; ct++) {
+          if (ct >= stair_ct_hi<STAIR>(rt, CT1)) continue;   // compile-time after unrolling
           const double bv = TB ? ((ct & 1) ? b[2 * s2 + (ct >> 1)].y : b[2 * s2 + (ct >> 1)].x)
                                : (s2 ? b[ct].y : b[ct].x);
           dmma884(acc[rt][ct][0], acc[rt][ct][1], av, bv);
@@ -243,6 +259,13 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
     const bool tri_lo = (g.kmode & 2) && (t.rowblk + 1) * 128 <= g.K && nk >= 8;
     const bool tri_hi = (g.kmode & 4) && klo == t.rowblk * 128 && nk >= 8;
     const bool tri_b = (g.kmode & 1) && klo == t.colblk * 128 && nk >= 8;
+    // diagonal output tile of a symmetric product: 0 = compute everything, 1..4 = stair (mma_stage),
+    // 5 = this warp's part lies entirely above the diagonal
+    int stair = 0;
+    if (MT == 128 && TA == TB && g.lower_only && t.rowblk == t.colblk) {
+      const int D = TA ? 4 * wr - 2 * wc : 8 * wr - 4 * wc, unit = TA ? 2 : 4;
+      stair = D >= unit ? 0 : (D == 0 ? (TA ? 3 : 1) : (D == -unit ? (TA ? 4 : 2) : 5));
+    }
     double acc[8][4][2];
 #pragma unroll
     for (int r = 0; r < 8; r++)
@@ -263,7 +286,15 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
       if (!TA && tri_lo && kt >= nk - 8) rt0 = min(8, max(0, 2 * (kt - (nk - 8)) - 8 * wr));
       else if (TA && tri_hi && kt < 8) rt1 = 2 * min(4, max(0, kt - 4 * wr + 1));
       else if (TB && tri_b && kt < 8) ct1 = 2 * min(2, max(0, kt - 2 * wc + 1));
-      if (MT != 128 || (rt0 == 0 && rt1 == 8 && ct1 == 4)) {
+      if (MT == 128 && TA == TB && stair != 0 && rt0 == 0 && rt1 == 8 && ct1 == 4) {
+        if (TA) {
+          if (stair == 3) mma_stage<TA, TB, 0, 8, 4, 3>(acc, as, bs, rbase, wc, lr, lk);
+          else if (stair == 4) mma_stage<TA, TB, 4, 8, 4, 4>(acc, as, bs, rbase, wc, lr, lk);
+        } else {
+          if (stair == 1) mma_stage<TA, TB, 0, 8, 4, 1>(acc, as, bs, rbase, wc, lr, lk);
+          else if (stair == 2) mma_stage<TA, TB, 4, 8, 4, 2>(acc, as, bs, rbase, wc, lr, lk);
+        }
+      } else if (MT != 128 || (rt0 == 0 && rt1 == 8 && ct1 == 4)) {
         mma_stage<TA, TB, 0, RTN, 4>(acc, as, bs, rbase, wc, lr, lk);
       } else if (!TA && rt0 > 0) {
         switch (rt0) {
@@ -779,7 +810,9 @@ __global__ void __launch_bounds__(1024) k_pack_sym(const double *Rinv, int n, in
   const int w = threadIdx.x, i8 = w >> 6, ri = (w >> 3) & 7, kj = w & 7;
   const int row = 128 * I + 8 * i8 + ri, col = 8 * j8 + kj;
   const int64_t slab = (int64_t)I * NJ8 + j8;
-  const bool lower = (col >> 7) <= I;
+  // only the part on or below the diagonal is valid (diagonal tiles included: the GEMM that forms
+  // R^-1 skips what lies above it)
+  const bool lower = col <= row;
   double v = lower ? Rinv[(int64_t)row * npad + col] : Rinv[(int64_t)col * npad + row];
   if (row >= n || col >= n) v = 0.0;
   Rp[slab * 1024 + w] = v;
