@@ -346,7 +346,8 @@ def test_oracle_parity_medium(kind, n, d):
 
 @pytest.mark.parametrize("kind,mode,n,d", [("squared_exponential", "noisy", 1100, 20),
                                            ("matern", "noiseless", 1300, 7),
-                                           ("squared_exponential", "noiseless", 640, 8)])
+                                           ("squared_exponential", "noiseless", 640, 8),
+                                           ("matern", "noisy", 300, 64)])
 def test_likelihood_oracle_larger_n(kind, mode, n, d):
     """Batched llf + gradient against the oracle at sizes that exercise several Cholesky panels
     (npad/128 = 9, 11, 5: full and partial panels), the recursive triangular inverse with a ragged

@@ -1,0 +1,1 @@
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "larger_n" 2>&1 | tail -5
