@@ -245,6 +245,28 @@ def linear_trends():
                                m=16, likelihood=lik, trend="linear")
 
 
+def zero_theta():
+    """Likelihood + gradient with some theta_i exactly 0 (the CUDA kernels fold sqrt(theta_i) into the
+    staged coordinates and take a separate, unscaled path for such vectors; the reference has no
+    special case: gpr.py:798-946 with kernel.py:147-317)."""
+    out = {}
+    for tag, kind in (("se", "squared_exponential"), ("m32", "matern"), ("absexp", "absolute_exponential")):
+        d, n = 5, 72
+        X, y = make_data(140 + len(tag), n, d)
+        rng = np.random.default_rng(1400 + len(tag))
+        theta = (0.3 / d) * 10.0 ** rng.uniform(-0.3, 0.3, d)
+        theta[2] = 0.0
+        if tag == "m32":
+            theta[0] = 0.0
+        par = np.r_[theta, 0.8]
+        gp = ref_model(kind, d, None, 1e-6, theta0=np.full(d, 0.1), thetaL=1e-5 * np.ones(d),
+                       thetaU=100 * np.ones(d))
+        llf, grad, _ = ref_set_par(gp, X, y, par)
+        out.update({tag + "_X": X, tag + "_y": y, tag + "_par": par, tag + "_llf": llf, tag + "_grad": grad})
+    np.savez_compressed(os.path.join(OUT, "zero_theta.npz"), **out)
+    print("zero_theta", {k: float(v) for k, v in out.items() if k.endswith("_llf")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     load_reference()
@@ -254,8 +276,12 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "linear":
         linear_trends()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "zero_theta":
+        zero_theta()
+        return
     variants()
     linear_trends()
+    zero_theta()
     k = 0
     for kind in ("squared_exponential", "matern"):
         for beta in (None, 0.3):

@@ -145,3 +145,19 @@ def test_variant_likelihood_state_posterior(name):
     rv = g["EI_min"]
     easy = g["mse"] > 1e-6 * float(g["sigma2"])
     assert np.max(np.abs(val[easy] - rv[easy]) / (np.abs(rv[easy]) + 1e-6 * np.abs(rv).max())) < 1e-6
+
+
+@pytest.mark.parametrize("tag,kind", [("se", "squared_exponential"), ("m32", "matern"),
+                                      ("absexp", "absolute_exponential")])
+def test_likelihood_with_zero_theta(tag, kind):
+    """theta_i = 0 for some features (reference output frozen by gen_golden.py zero_theta): the
+    oracle is what the GPU test of the same name compares the unscaled kernel path with."""
+    import os
+    from golden_util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "zero_theta.npz"))
+    X, y, par = z[tag + "_X"], z[tag + "_y"], z[tag + "_par"]
+    assert np.any(par[:-1] == 0.0)
+    llf, grad = O.log_likelihood_concentrated(X, y, par, kind, True, 0.0, "noisy", 1e-6, eval_grad=True)
+    ref_llf, ref_grad = float(z[tag + "_llf"]), z[tag + "_grad"]
+    assert abs(float(np.ravel(llf)[0]) - ref_llf) <= 1e-10 * abs(ref_llf)
+    assert relerr(np.ravel(grad), ref_grad, floor=1e-6 * np.abs(ref_grad).max()) < 1e-8
