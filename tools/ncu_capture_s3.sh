@@ -1,5 +1,7 @@
 # Round-1 (third session) final evidence: bench lines, launch lists of the C2 and likelihood workloads
 # (likelihood with one batch group = serialised), `ncu --set full` of the kernels changed in this session.
+# Build the micro-benchmarks first (in the build container; the binaries travel with the snapshot):
+#   cd tools && for t in diag_bench fp64_lat exp_check; do nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../mip-ego_b200/csrc -I../include -o $t $t.cu; done
 # Exports CSV/text summaries only (the .ncu-rep files exceed the 64 MiB gpurun_out limit); copy what is kept into profiles/.
 for w in c1 c2 c3 c5; do python bench.py --workload $w --steps 6 --warmup 3 > gpurun_out/s3_${w}.json 2> gpurun_out/s3_${w}.err; done
 python bench.py --workload nll --steps 8 --warmup 3 > gpurun_out/s3_nll.json 2> gpurun_out/s3_nll.err
