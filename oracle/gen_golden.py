@@ -267,6 +267,20 @@ def zero_theta():
     print("zero_theta", {k: float(v) for k, v in out.items() if k.endswith("_llf")})
 
 
+def multi_restart_fits():
+    """Reference fits with several L-BFGS-B restarts (gpr.py:1030-1064: sequential restarts, shared
+    budget, wait_iter early stop).  Modes whose analytic gradient is exact (noisy; given trend --
+    SURVEY Q6), so that the end point of a restart is a property of the likelihood surface and not
+    of rounding in the line search: the fixture pins "multi-restart fit reaches at least the
+    reference's likelihood" (SURVEY H5)."""
+    case_fit("mfit_se_ok_noisy_rs4", seed=21, n=60, d=3, kind="squared_exponential", beta=None,
+             nugget=1e-6, random_start=4)
+    case_fit("mfit_m32_ok_noisy_rs5", seed=22, n=72, d=4, kind="matern", beta=None, nugget=1e-4,
+             random_start=5)
+    case_fit("mfit_se_sk_noiseless_rs4", seed=23, n=56, d=3, kind="squared_exponential", beta=0.0,
+             nugget=0, random_start=4)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     load_reference()
@@ -279,9 +293,13 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "zero_theta":
         zero_theta()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "multi_restart":
+        multi_restart_fits()
+        return
     variants()
     linear_trends()
     zero_theta()
+    multi_restart_fits()
     k = 0
     for kind in ("squared_exponential", "matern"):
         for beta in (None, 0.3):

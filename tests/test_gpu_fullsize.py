@@ -1,7 +1,11 @@
-"""BASELINE.json full-size configurations checked through size-independent properties (the oracle
-needs minutes at these sizes): bitwise invariance to chunking and to the order of candidates,
-interpolation at the training points, top-k == sort of the full evaluation, the likelihood
-gradient against central differences of the likelihood itself, shard-count independence."""
+"""BASELINE.json full-size configurations (C3 n=4096 d=20, C4 likelihood n=4096, C5 n=8192 d=40):
+  * against the CPU oracle on sampled candidates / single parameter vectors at the north_star
+    tolerances (1e-9 mean and likelihood, 1e-7 MSE / acquisition / gradients) -- about two minutes
+    of oracle time on the host cores in total;
+  * through size-independent properties: bitwise invariance to chunking and to the order of
+    candidates, interpolation at the training points, top-k == sort of the full evaluation, the
+    likelihood gradient against central differences of the likelihood itself, shard-count
+    independence."""
 import numpy as np
 import pytest
 
@@ -26,6 +30,92 @@ def c3_model():
                             thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=1e-6)
     gp.fit_fixed(X, y, np.r_[theta, 0.9])
     return mb, gp, X, y, theta
+
+
+def test_c3_against_oracle(c3_model):
+    """BASELINE configs[2] model against the oracle: 512 sampled candidates, MGFI for the 8
+    t-values of ParallelBO (one posterior pass), EI with its gradient, mean / MSE."""
+    from oracle import gp_oracle as O
+    mb, gp, X, y, theta = c3_model
+    d = X.shape[1]
+    st = O.fit_state(X, y, np.r_[theta, 0.9], "squared_exponential", True, 0.0, "noisy", 1e-6)
+    assert abs(float(np.ravel(gp.log_likelihood_)[0]) - st["llf"]) <= 1e-9 * abs(st["llf"])
+    Xs = np.random.default_rng(21).uniform(-5, 5, (512, d))
+    plugin = float(y.min())
+    mean, mse = gp.predict(Xs, eval_MSE=True)
+    rm, rs = O.predict(st, Xs)
+    e_mean = np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3))
+    e_mse = np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"]))
+    ts = np.exp(np.log(2) + 0.5 * np.random.default_rng(22).standard_normal(8))
+    crit = mb.MGFI(model=gp, minimize=True, plugin=plugin, t=float(ts[0]))
+    V = crit.evaluate(Xs, params=ts)
+    e_mgfi = 0.0
+    for s, t in enumerate(ts):
+        rv = O.acquisition(st, Xs, "MGFI", float(t), plugin, True)
+        e_mgfi = max(e_mgfi, np.max(np.abs(V[s] - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())))
+    ei = mb.EI(model=gp, minimize=True, plugin=plugin)
+    v, dx = ei(Xs[:64], return_dx=True)
+    rv, rdx = O.acquisition(st, Xs[:64], "EI", None, plugin, True, return_dx=True)
+    e_ei = np.max(np.abs(v - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max()))
+    e_dx = np.max(np.abs(dx - rdx)) / np.abs(rdx).max()
+    print("C3 vs oracle: mean %.2e mse %.2e MGFI x8 %.2e EI %.2e EI_dx %.2e" % (e_mean, e_mse, e_mgfi, e_ei, e_dx))
+    assert e_mean < 1e-9 and e_mse < 1e-7 and e_mgfi < 1e-7 and e_ei < 1e-7 and e_dx < 1e-7
+
+
+@pytest.mark.parametrize("mode", ["noisy", "noiseless"])
+def test_c4_likelihood_against_oracle(mode):
+    """BASELINE configs[3]: one n=4096, d=20 likelihood + gradient per estimation mode against
+    `log_likelihood_concentrated(eval_grad=True)` of the oracle (gpr.py:798-946)."""
+    import mipego_b200 as mb
+    from oracle import gp_oracle as O
+    n, d = 4096, 20
+    X, y, rng = _data(n, d, 30)
+    theta = (0.12 / d) * rng.uniform(0.5, 1.5, d)
+    if mode == "noisy":
+        par, nugget = np.r_[theta, 0.8], 1e-6
+    else:
+        par, nugget = 6.0 * theta, 0.0      # at the C3 theta the noiseless llf is > 0, which the reference rejects
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential", theta0=theta,
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=nugget)
+    gp._check_data(X, y)
+    llf, grad, status = gp.log_likelihood_batch(par.reshape(1, -1), eval_grad=True)
+    rl, rg = O.log_likelihood_concentrated(X, y, par, "squared_exponential", True, 0.0, mode, nugget, eval_grad=True)
+    e_llf = abs(llf[0] - rl) / abs(rl)
+    e_grad = np.max(np.abs(grad[0] - rg.ravel())) / np.abs(rg).max()
+    print("C4 %s vs oracle: llf %.12g (oracle %.12g) rel %.2e, grad rel %.2e" % (mode, llf[0], rl, e_llf, e_grad))
+    assert status[0] == 0 and np.isfinite(rl)
+    assert e_llf < 1e-9 and e_grad < 1e-7
+
+
+def test_c5_against_oracle():
+    """BASELINE configs[4] shape: n=8192, d=40, Matern-3/2, simple kriging, nugget 0; 200 sampled
+    candidates: mean, MSE, EI and the EI gradient on 16 of them."""
+    import mipego_b200 as mb
+    from oracle import gp_oracle as O
+    n, d = 8192, 40
+    X, y, rng = _data(n, d, 40)
+    theta = (0.12 / d) * rng.uniform(0.5, 1.5, d) * 4.0
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=0.0), corr="matern", theta0=theta,
+                            thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d))
+    gp.fit_fixed(X, y, theta)
+    st = O.fit_state(X, y, theta, "matern", False, 0.0, "noiseless", 0.0)
+    assert abs(float(np.ravel(gp.log_likelihood_)[0]) - st["llf"]) <= 1e-9 * abs(st["llf"])
+    assert abs(float(np.ravel(gp.sigma2)[0]) - st["sigma2"]) <= 1e-9 * st["sigma2"]
+    Xs = rng.uniform(-5, 5, (200, d))
+    plugin = float(y.min())
+    mean, mse = gp.predict(Xs, eval_MSE=True)
+    rm, rs = O.predict(st, Xs)
+    e_mean = np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3))
+    e_mse = np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"]))
+    ei = mb.EI(model=gp, minimize=True, plugin=plugin)
+    v = ei(Xs)
+    rv = O.acquisition(st, Xs, "EI", None, plugin, True)
+    e_ei = np.max(np.abs(v - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max()))
+    v16, dx = ei(Xs[:16], return_dx=True)
+    _, rdx = O.acquisition(st, Xs[:16], "EI", None, plugin, True, return_dx=True)
+    e_dx = np.max(np.abs(dx - rdx)) / (np.abs(rdx).max() + 1e-300)
+    print("C5 vs oracle: mean %.2e mse %.2e EI %.2e EI_dx %.2e" % (e_mean, e_mse, e_ei, e_dx))
+    assert e_mean < 1e-9 and e_mse < 1e-7 and e_ei < 1e-7 and e_dx < 1e-7
 
 
 def test_c3_chunk_and_order_invariance(c3_model):

@@ -10,7 +10,7 @@ With nugget 0 the reference's own formulas evaluated in two orders differ by 4e-
 import numpy as np
 import pytest
 
-from golden_util import FIXED, FITS, VARS, LINS, load, mode_of, beta_of, likelihood_of, trend_of
+from golden_util import FIXED, FITS, MFITS, VARS, LINS, load, mode_of, beta_of, likelihood_of, trend_of
 
 pytestmark = pytest.mark.gpu
 
@@ -273,17 +273,95 @@ def test_not_positive_definite_and_positive_llf_status():
 
 
 def test_c1_example_config():
-    """BASELINE config 1 (n=50, d=2, EI) against the reference's own per-point outputs."""
+    """BASELINE config 1 (n=50, d=2, EI) against the reference's own per-point outputs.  The
+    reference's fit ends at theta = (0.5, 0.5), cond(L) = 20: a well-conditioned model although
+    nugget = 0, so the north_star gates apply unrelaxed (1e-9 mean, 1e-7 MSE / EI / EI gradient)."""
     mb, O = _mods()
     g = load("c1_example")
     gp = mb.GaussianProcess(mean=mb.constant_trend(2, beta=None), corr="squared_exponential",
                             theta0=g["theta_"], thetaL=[1e-9] * 2, thetaU=[100] * 2, nugget=0)
     gp.set_fitted_state(g["X"], g["y"], g["theta_"], g["L"], g["gamma"], float(g["sigma2"]), float(g["beta"]))
     mean, mse = gp.predict(g["Xs"], eval_MSE=True)
-    assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-2)) < 1e-5
+    s2 = float(g["sigma2"])
+    e_mean = np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-2))
+    e_mse = np.max(np.abs(mse - g["mse"]) / (np.abs(g["mse"]) + 1e-6 * s2))
     ei = mb.EI(model=gp, minimize=True)
-    v = ei(g["Xs"])
-    assert np.max(np.abs(v - g["EI"])) < 1e-4 * np.abs(g["EI"]).max()
+    v, dx = ei(g["Xs"], return_dx=True)
+    e_ei = np.max(np.abs(v - g["EI"])) / np.abs(g["EI"]).max()
+    e_dx = np.max(np.abs(dx - g["EI_dx"].reshape(dx.shape))) / np.abs(g["EI_dx"]).max()
+    print("C1 rel err: mean %.2e mse %.2e EI %.2e EI_dx %.2e" % (e_mean, e_mse, e_ei, e_dx))
+    assert e_mean < 1e-9 and e_mse < 1e-7 and e_ei < 1e-7 and e_dx < 1e-7
+    # the same model built by the library itself from (X, y, theta): its own Cholesky
+    gp2 = mb.GaussianProcess(mean=mb.constant_trend(2, beta=None), corr="squared_exponential",
+                             theta0=g["theta_"], thetaL=[1e-9] * 2, thetaU=[100] * 2, nugget=0)
+    gp2.fit_fixed(g["X"], g["y"], g["theta_"])
+    mean2, mse2 = gp2.predict(g["Xs"], eval_MSE=True)
+    assert np.max(np.abs(mean2 - g["mean"]) / (np.abs(g["mean"]) + 1e-2)) < 1e-9
+    assert np.max(np.abs(mse2 - g["mse"]) / (np.abs(g["mse"]) + 1e-6 * s2)) < 1e-7
+    assert abs(float(np.ravel(gp2.log_likelihood_)[0]) - float(g["llf"])) <= 1e-9 * abs(float(g["llf"]))
+
+
+def _stress_problem(kind, scale, n=200, d=4, seed=50, radius=0.05):
+    """SURVEY H1 / section 8d stress set: 25 % of the training points within `radius` of one
+    centre (what a BO trajectory does around its incumbent), nugget 0."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-5, 5, (n, d))
+    c = rng.uniform(-3, 3, d)
+    k = n // 4
+    v = rng.standard_normal((k, d))
+    v /= np.linalg.norm(v, axis=1)[:, None]
+    X[:k] = c + radius * rng.uniform(0, 1, (k, 1)) ** (1.0 / d) * v
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    y = (y - y.mean()) / y.std()
+    theta = (0.12 / d) * rng.uniform(0.5, 1.5, d) * scale
+    Xs = np.r_[rng.uniform(-5, 5, (200, d)), c + 0.2 * rng.standard_normal((100, d))]
+    return X, y, theta, Xs
+
+
+@pytest.mark.parametrize("kind,scale", [("squared_exponential", 30.0), ("squared_exponential", 100.0),
+                                        ("matern", 1.0)])
+def test_stress_set_against_extended_precision_truth(kind, scale):
+    """Ill-conditioned models (cond(R) up to 2e15) cannot be gated at 1e-9 against the float64
+    reference: the reference itself is 1e-3 .. 1e-11 away from the exact posterior there (its
+    Cholesky loses cond(R) * eps).  Judged instead against an extended-precision evaluation of
+    the same formulas (oracle/gp_truth.py, numpy longdouble): the CUDA path -- its own
+    factorisation, explicit L^-1, distance GEMM -- must be no farther from the truth than a small
+    multiple of the reference's own distance (both are O(cond * eps) with different constants)."""
+    mb, O = _mods()
+    from oracle import gp_truth as T
+    X, y, theta, Xs = _stress_problem(kind, scale)
+    d = X.shape[1]
+    st = O.fit_state(X, y, theta, kind, True, 0.0, "noiseless", 0.0)        # the reference's float64 path
+    ft = T.fit_truth(X, y, theta, kind)
+    tm, ts = (np.asarray(a, dtype=np.float64) for a in T.predict(ft, Xs))
+    s2 = float(ft["sigma2"])
+    rm, rs = O.predict(st, Xs)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr=kind, theta0=theta,
+                            thetaL=1e-6 * np.ones(d), thetaU=100 * np.ones(d), nugget=0)
+    gp.fit_fixed(X, y, theta)
+    gm, gs = gp.predict(Xs, eval_MSE=True)
+
+    def dist(m, s):
+        return (np.max(np.abs(m - tm) / (np.abs(tm) + 1e-3)), np.max(np.abs(s - ts) / (np.abs(ts) + 1e-6 * s2)))
+    ref_e, gpu_e = dist(rm, rs), dist(gm, gs)
+    e_s2 = (abs(st["sigma2"] - s2) / s2, abs(float(np.ravel(gp.sigma2)[0]) - s2) / s2)
+    print("stress %s x%g: cond(L) %.1e | distance to truth  reference: mean %.2e mse %.2e sigma2 %.2e | "
+          "CUDA: mean %.2e mse %.2e sigma2 %.2e" % (kind, scale, np.linalg.cond(st["L"]), ref_e[0], ref_e[1],
+                                                    e_s2[0], gpu_e[0], gpu_e[1], e_s2[1]))
+    K = 20.0    # O(cond * eps) on both sides, constants differ (blocked vs. unblocked Cholesky, L^-1 vs. substitution)
+    assert gpu_e[0] <= K * ref_e[0] + 1e-11 and gpu_e[1] <= K * ref_e[1] + 1e-9
+    assert e_s2[1] <= K * e_s2[0] + 1e-12
+    # the same state handed over (mgp_set_state): only the posterior arithmetic differs now, and the
+    # truth is evaluated from that float64 state taken as exact
+    gp2 = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr=kind, theta0=theta,
+                             thetaL=1e-6 * np.ones(d), thetaU=100 * np.ones(d), nugget=0)
+    gp2.set_fitted_state(X, y, theta, st["L"], st["gamma"], st["sigma2"], st["beta"])
+    t2 = T.state_truth(X, theta, st["L"], st["gamma"], st["sigma2"], st["beta"], kind)
+    tm, ts = (np.asarray(a, dtype=np.float64) for a in T.predict(t2, Xs))
+    s2 = float(st["sigma2"])
+    ref_e, gpu_e = dist(rm, rs), dist(*gp2.predict(Xs, eval_MSE=True))
+    print("   same state: reference mean %.2e mse %.2e | CUDA mean %.2e mse %.2e" % (ref_e + gpu_e))
+    assert gpu_e[0] <= K * ref_e[0] + 1e-11 and gpu_e[1] <= K * ref_e[1] + 1e-9
 
 
 def synth_model(O, n, d, kind, seed, nugget=1e-6, estimate_trend=True):
@@ -452,13 +530,10 @@ def test_duplicate_rows_and_errors():
 
 @pytest.mark.parametrize("name", FITS)
 def test_fit_against_reference_fit(name):
-    """End-to-end fit(): same start, same optimiser (scipy L-BFGS-B, sequential restarts).
-    The reference's analytic gradient is inexact in noiseless + estimated-trend mode,
-    so L-BFGS-B line searches end on rounding-level differences: the end points agree in
-    likelihood to about a percent (same number of iterations and evaluations, theta within ~1 %),
-    not bit for bit -- any change of summation order inside the factorisation moves them.
-    What is pinned exactly is function-level parity: same theta -> same llf to 1e-9, at the
-    reference's optimum (below) and at the end point this fit reached (oracle call below)."""
+    """End-to-end fit(): same start, same optimiser (scipy L-BFGS-B, sequential restarts), against
+    a fit() of the unmodified reference.  A rounding-level perturbation of (llf, grad) moves the
+    end point of L-BFGS-B by about 1e-11 in likelihood on these problems (measured with the oracle),
+    so the fitted likelihood is gated at 1e-6 relative and theta at 1e-3."""
     mb, O = _mods()
     g = load(name)
     d = g["X"].shape[1]
@@ -470,19 +545,49 @@ def test_fit_against_reference_fit(name):
                             random_start=int(g["random_start"]), restart_mode="sequential")
     gp.fit(g["X"], g["y"])
     llf = float(np.ravel(gp.log_likelihood_)[0])
-    assert llf >= float(g["llf"]) - 2e-2 * abs(float(g["llf"]))
+    print("fit %s: llf %.12g (reference %.12g), %d evaluations (reference %d)" %
+          (name, llf, float(g["llf"]), gp.eval_count, int(g["eval_count"])))
+    assert llf >= float(g["llf"]) - 1e-6 * abs(float(g["llf"]))
     par_end = np.concatenate([np.ravel(v) for v in gp.par.values()])
     l_or = O.log_likelihood_concentrated(g["X"], g["y"], par_end, g["kind"], g["estimate_trend"], beta_of(g),
                                          mode_of(g), nug)
-    assert abs(llf - l_or) <= 1e-7 * abs(l_or)
+    assert abs(llf - l_or) <= 1e-9 * abs(l_or)
     # at the reference's own optimum the CUDA likelihood agrees to 1e-9
     l_ref, _, st_ref = gp.log_likelihood_batch(g["par"], eval_grad=False)
-    assert st_ref[0] <= 0
-    if st_ref[0] == 0:
-        assert abs(l_ref[0] - float(g["llf"])) <= 1e-9 * abs(float(g["llf"]))
-    if abs(llf - float(g["llf"])) <= 1e-7 * abs(float(g["llf"])):
-        assert np.allclose(gp.theta_, g["theta_"], rtol=1e-4)
-        mean, mse = gp.predict(g["Xs"], eval_MSE=True)
+    assert st_ref[0] == 0
+    assert abs(l_ref[0] - float(g["llf"])) <= 1e-9 * abs(float(g["llf"]))
+    assert np.allclose(gp.theta_, g["theta_"], rtol=1e-3)
+    mean, mse = gp.predict(g["Xs"], eval_MSE=True)
+    assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-2)) < 1e-4
+
+
+@pytest.mark.parametrize("restart_mode", ["sequential", "batched"])
+@pytest.mark.parametrize("name", MFITS)
+def test_multi_restart_fit_reaches_reference_likelihood(name, restart_mode):
+    """Multi-restart fit() against multi-restart fit() of the unmodified reference
+    (oracle/gen_golden.py multi_restart_fits: random_start = 4..5, same numpy seed, hence the same
+    restart points, gpr.py:1035-1036).  SURVEY H5: lock-step batching keeps every trajectory but
+    not the "which restarts ran" sequence, so the contract is final llf >= reference - 1e-6 |ref|
+    in both restart modes."""
+    mb, O = _mods()
+    g = load(name)
+    d = g["X"].shape[1]
+    beta = None if g["estimate_trend"] else float(g["beta_in"])
+    nug = float(g["nugget"])
+    np.random.seed(int(g["seed"]))
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=beta), corr=g["kind"], theta0=g["theta0"],
+                            thetaL=g["thetaL"], thetaU=g["thetaU"], nugget=nug if nug > 0 else 0,
+                            random_start=int(g["random_start"]), restart_mode=restart_mode)
+    gp.fit(g["X"], g["y"])
+    llf = float(np.ravel(gp.log_likelihood_)[0])
+    print("multi-restart fit %s [%s]: llf %.12g (reference %.12g), %d evaluations (reference %d)" %
+          (name, restart_mode, llf, float(g["llf"]), gp.eval_count, int(g["eval_count"])))
+    assert llf >= float(g["llf"]) - 1e-6 * abs(float(g["llf"]))
+    if restart_mode == "sequential":     # the reference's own loop: same restarts, same end point
+        assert np.allclose(gp.theta_, g["theta_"], rtol=1e-3)
+        assert gp.eval_count == int(g["eval_count"])
+    mean, mse = gp.predict(g["Xs"], eval_MSE=True)
+    if abs(llf - float(g["llf"])) <= 1e-6 * abs(float(g["llf"])):
         assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-2)) < 1e-4
 
 
