@@ -17,7 +17,11 @@
  *  - functions without the _dev suffix take HOST pointers and are synchronous: host<->device
  *    copies happen inside the call.  *_dev functions take DEVICE pointers (on the handle's
  *    device) plus a cudaStream_t (as void*); they enqueue work on that stream and return
- *    without synchronising;
+ *    without synchronising.  Calls on different streams are ordered by the library itself: every
+ *    entry point makes its stream wait for the previous user of the handle's workspaces and of the
+ *    fitted model (an event recorded when that call's work was enqueued), so e.g. mgp_acq_dev on a
+ *    user stream followed by mgp_acq or mgp_finalize_fit is safe without an explicit
+ *    synchronisation.  What stays the caller's job: the lifetime of its own device buffers;
  *  - all arithmetic is float64.  There is no CPU fallback: without a CUDA device every compute
  *    entry point fails with MGP_ECUDA.
  */
@@ -30,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MGP_ABI_VERSION 3
+#define MGP_ABI_VERSION 4
 
 /* error codes */
 #define MGP_OK 0
@@ -104,6 +108,17 @@ int mgp_nll_batch(mgp_t *h, int B, const double *params, int n_par, int mode, do
 int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double noise_var,
                      double *out_llf);
 
+/* ---- the `env` harvest of a likelihood call WITHOUT adopting the state: what
+ * log_likelihood_concentrated / _restricted(par, env) fill in (gpr.py:876-887, 785-794).  Runs the
+ * pipeline for one parameter vector in scratch memory and copies out L (n x n row-major, upper = 0),
+ * rho, Yt (n each), Ft (n x p; meaningful for estimated trends) and
+ * out_scalars[5] = {sigma2, beta_0, G, llf, noise_var} (G: constant trend only).  Any out pointer
+ * may be NULL.  The fitted model of the handle (mgp_finalize_fit / mgp_set_state) is left untouched,
+ * like the reference, whose env harvest has no side effects.  MGP_ENOTPD if R is not positive
+ * definite (nothing is written then). */
+int mgp_nll_env(mgp_t *h, const double *par, int n_par, int mode, double noise_var, double *out_L,
+                double *out_rho, double *out_Yt, double *out_Ft, double *out_scalars);
+
 /* ---- state exchange (pickling; accepting an externally fitted model).
  * get: any out pointer may be NULL.  out_L: n x n row-major lower triangle (upper = 0);
  * out_theta: d; out_gamma, out_rho, out_Yt: n; out_Ft: n x p row-major (p = 1 or d + 1);
@@ -158,12 +173,49 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
                       double noise_var, int eval_grad, double *d_out_llf, double *d_out_grad,
                       int *d_out_status, void *stream);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch.  The
+ * reference has no collective on this path; its only parallelism is joblib processes over the
+ * n_point acquisition sub-problems (BayesOpt.py:94-97), each of which unpickles the whole model.
+ * Here candidates and MLE restarts are sharded over ranks and two exchanges remain:
+ *   - the fitted model goes once per fit from the root's HBM to every rank's HBM (no host bounce,
+ *     no re-factorisation: every rank holds the bit-identical model, so results do not depend on
+ *     the number of shards);
+ *   - the per-rank k best (value, global index) pairs are all-gathered and merged on the device in
+ *     the single-GPU order (value descending, NaN last, ties -> smaller index), identically on
+ *     every rank.
+ * NCCL is bound at run time with dlopen (the copy the process already loaded, e.g. PyTorch's,
+ * else libnccl.so.2, else $MGP_NCCL_LIB): the library has no link-time dependency on it.
+ * mgp_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId; the caller ships it to the other
+ * ranks by any means (torch.distributed, MPI, a file).  mgp_comm_init: collective over all ranks.
+ * mgp_bcast_model: collective; every rank has called mgp_set_train with the same X, y (checked:
+ * n, d, kernel, trend and checksums of X and y must agree, else EVERY rank returns MGP_EINVAL);
+ * the root must be fitted.  mgp_allgather_topk(_dev): val / idx are this rank's n_sets x k best
+ * (idx < 0 = empty slot), idx_offset = global index of this rank's row 0; out_* receive the n_sets
+ * x k global best.  mgp_allgather_f64_dev: plain all-gather of `count` doubles per rank (rows of
+ * sharded likelihood evaluations). */
+int mgp_comm_unique_id(char *out_id /* 128 bytes */);
+int mgp_comm_init(mgp_t *h, int rank, int world, const char *id /* 128 bytes */);
+int mgp_comm_destroy(mgp_t *h);
+const char *mgp_comm_info(const mgp_t *h);
+int mgp_bcast_model(mgp_t *h, int root);
+int mgp_allgather_topk(mgp_t *h, int n_sets, int k, const double *val, const int64_t *idx,
+                       int64_t idx_offset, double *out_val, int64_t *out_idx);
+int mgp_allgather_topk_dev(mgp_t *h, int n_sets, int k, const double *d_val, const int64_t *d_idx,
+                           int64_t idx_offset, double *d_out_val, int64_t *d_out_idx, void *stream);
+int mgp_allgather_f64_dev(mgp_t *h, const double *d_send, int64_t count, double *d_recv, void *stream);
+
 /* ---- tuning / introspection ------------------------------------------------------------
  * mgp_set_option: "chunk" = candidates per pass of the posterior pipeline (multiple of 128, 0 =
- * default); "time_kernels" = 1 brackets every posterior kernel launch with CUDA events on the
+ * default); "isotropic" = 1: ONE theta shared by all features (kernel.py:312-317) -- every parameter
+ * vector then has 1 instead of d leading theta entries, and the likelihood gradient follows the
+ * reference's indexing of its derivative tensor (entry 0 = derivative w.r.t. the first feature's
+ * theta; set it before the first likelihood call); "small_path" = 0 disables the matrix-vector path
+ * for <= 8 candidates; "nll_groups", "gemm_cta_cap": scheduling of batched likelihoods (0 = automatic);
+ * "time_kernels" = 1 brackets every posterior kernel launch with CUDA events on the
  * launching stream (resets the timers).
  * mgp_get_counter: "launches" = kernels launched by this handle so far; "npad", "chunk",
- * "sm_count"; with time_kernels: "<k>_ns" / "<k>_calls" for k in rgen, trmm, epilogue, topk
+ * "sm_count", "small_path", "isotropic", "n", "rank", "world", "bcast_bytes" (payload of the last
+ * mgp_bcast_model); with time_kernels: "<k>_ns" / "<k>_calls" for k in rgen, trmm, epilogue, topk
  * (accumulated device time in nanoseconds; synchronises on the recorded events). */
 int mgp_set_option(mgp_t *h, const char *name, int64_t value);
 int64_t mgp_get_counter(const mgp_t *h, const char *name);

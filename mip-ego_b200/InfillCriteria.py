@@ -111,15 +111,18 @@ class InfillCriteria(object):
         stream = torch.cuda.current_stream(X.device).cuda_stream
         return torch, h, P, stream
 
-    def evaluate_device(self, X, params=None, out=None):
+    def evaluate_device(self, X, params=None, out=None, return_dx=False, out_dx=None):
+        """Values (n_sets, m) [and, with return_dx, gradients (n_sets, m, d)] as CUDA tensors."""
         torch, h, P, stream = self._dev_args(X, params)
-        m = X.shape[0]
+        m, d = X.shape
         if out is None:
             out = torch.empty((P.size, m), dtype=torch.float64, device=X.device)
+        if return_dx and out_dx is None:
+            out_dx = torch.empty((P.size, m, d), dtype=torch.float64, device=X.device)
         h.check(h.lib.mgp_acq_dev(h.h, m, X.data_ptr(), _cabi.ACQ[self._kind], P.size, _cabi.dptr(P),
                                   float(self._plugin_user()), 1 if self.minimize else 0,
-                                  out.data_ptr(), None, stream))
-        return out
+                                  out.data_ptr(), out_dx.data_ptr() if return_dx else None, stream))
+        return (out, out_dx) if return_dx else out
 
     def topk_device(self, X, k=1, params=None, out=None):
         torch, h, P, stream = self._dev_args(X, params)

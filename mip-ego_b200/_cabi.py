@@ -14,6 +14,7 @@ MODE = {"noiseless": 0, "noisy": 1, "noise_estim": 2}
 LIK_RESTRICTED = 16
 TREND = {("constant", False): 0, ("constant", True): 1, ("linear", False): 2, ("linear", True): 3}
 MAX_SETS = 16
+ABI_VERSION = 4
 
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_ip = ctypes.POINTER(ctypes.c_int)
@@ -29,6 +30,7 @@ SIGNATURES = {
     "mgp_set_train": (_i, [_vp, _i, _i, c_dp, c_dp, _i, _i, c_dp]),
     "mgp_nll_batch": (_i, [_vp, _i, c_dp, _i, _i, _d, _i, c_dp, c_dp, c_ip]),
     "mgp_finalize_fit": (_i, [_vp, c_dp, _i, _i, _d, c_dp]),
+    "mgp_nll_env": (_i, [_vp, c_dp, _i, _i, _d, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "mgp_get_state": (_i, [_vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "mgp_set_state": (_i, [_vp, c_dp, c_dp, c_dp, _d, c_dp]),
     "mgp_get_trend": (_i, [_vp, c_dp]),
@@ -40,6 +42,14 @@ SIGNATURES = {
     "mgp_acq_dev": (_i, [_vp, _l, _vp, _i, _i, c_dp, _d, _i, _vp, _vp, _vp]),
     "mgp_acq_topk_dev": (_i, [_vp, _l, _vp, _i, _i, c_dp, _d, _i, _i, _vp, _vp, _vp]),
     "mgp_nll_batch_dev": (_i, [_vp, _i, _vp, _i, _i, _d, _i, _vp, _vp, _vp, _vp]),
+    "mgp_comm_unique_id": (_i, [ctypes.c_char_p]),
+    "mgp_comm_init": (_i, [_vp, _i, _i, ctypes.c_char_p]),
+    "mgp_comm_destroy": (_i, [_vp]),
+    "mgp_comm_info": (ctypes.c_char_p, [_vp]),
+    "mgp_bcast_model": (_i, [_vp, _i]),
+    "mgp_allgather_topk": (_i, [_vp, _i, _i, c_dp, c_lp, _l, c_dp, c_lp]),
+    "mgp_allgather_topk_dev": (_i, [_vp, _i, _i, _vp, _vp, _l, _vp, _vp, _vp]),
+    "mgp_allgather_f64_dev": (_i, [_vp, _vp, _l, _vp, _vp]),
     "mgp_set_option": (_i, [_vp, ctypes.c_char_p, _l]),
     "mgp_get_counter": (_l, [_vp, ctypes.c_char_p]),
 }
@@ -67,7 +77,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mgp_abi_version() != 3:
+    if lib.mgp_abi_version() != ABI_VERSION:
         raise ImportError("libmgp_b200.so ABI version mismatch")
     _lib = lib
     return lib

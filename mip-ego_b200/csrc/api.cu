@@ -75,6 +75,21 @@ static void resolve_timers(mgp_handle *h) {
   h->ev_pending.clear();
 }
 
+// See mgp_handle::ev_ws.  A wait on an event recorded on the same stream is a no-op for the device.
+static cudaError_t ws_acquire(mgp_handle *h, cudaStream_t st) {
+  if (!h->ws_recorded) return cudaSuccess;
+  return cudaStreamWaitEvent(st, h->ev_ws, 0);
+}
+static cudaError_t ws_release(mgp_handle *h, cudaStream_t st) {
+  h->ws_recorded = true;
+  return cudaEventRecord(h->ev_ws, st);
+}
+struct WsScope {   // acquire on construction, release on destruction (every return path)
+  mgp_handle *h; cudaStream_t st; cudaError_t err;
+  WsScope(mgp_handle *h_, cudaStream_t st_) : h(h_), st(st_), err(ws_acquire(h_, st_)) {}
+  ~WsScope() { ws_release(h, st); }
+};
+
 #define CHECK_H(h) \
   if (!(h)) return MGP_EINVAL; \
   MGP_CUDA(h, cudaSetDevice((h)->device))
@@ -119,6 +134,8 @@ int mgp_create(int device, mgp_t **out_h) {
     cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_ws, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming);
   for (int i = 0; i < 2; i++) {
     cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
@@ -132,13 +149,14 @@ int mgp_destroy(mgp_t *h) {
   if (!h) return MGP_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  mgp_comm_destroy(h);
   DevBuf *all[] = {&h->dtpart, &h->dXc, &h->dy, &h->dcenter, &h->dtheta, &h->dBop, &h->dan, &h->dL, &h->dMinv,
                    &h->dTmp, &h->dMp, &h->dRinvP, &h->dgamma, &h->davec, &h->dFt,
                    &h->dYt, &h->drho, &h->dscal, &h->drP, &h->dmeanpart, &h->dftpart, &h->dqpart,
                    &h->dwP, &h->dXs_stage[0], &h->dXs_stage[1], &h->dout_stage[0],
                    &h->dout_stage[1], &h->dtopk_val, &h->dtopk_idx, &h->dtopk_blk, &h->nR, &h->nL, &h->nM, &h->nT,
                    &h->nLinvDiag, &h->nvec, &h->nscal, &h->npar, &h->ngpart, &h->nFtm, &h->nBhat, &h->ntws,
-                   &h->dF, &h->dmu, &h->dbetav, &h->dBhat, &h->dCinv, &h->dFtm};
+                   &h->dF, &h->dmu, &h->dbetav, &h->dBhat, &h->dCinv, &h->dFtm, &h->niso, &h->dcomm, &h->dgather, &h->dgather_io};
   for (DevBuf *b : all) freebuf(*b);
   for (int i = 0; i < 2; i++) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -146,10 +164,13 @@ int mgp_destroy(mgp_t *h) {
     if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
   }
   for (int i = 0; i < MGP_NLL_STREAMS; i++) {
-    if (h->nll_stream[i]) cudaStreamDestroy(h->nll_stream[i]);
+    if (h->nll_stream[i]) { release_dgemm_stream(h->nll_stream[i]); cudaStreamDestroy(h->nll_stream[i]); }
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_ws) cudaEventDestroy(h->ev_ws);
+  if (h->ev_gather) cudaEventDestroy(h->ev_gather);
+  if (h->stream) release_dgemm_stream(h->stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->out_stream) cudaStreamDestroy(h->out_stream);
@@ -177,7 +198,10 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
   }
   if (!strcmp(name, "gemm_cta_cap")) {
     h->gemm_cap_opt = (int)value;
-    set_dgemm_cta_cap((int)value);
+    return MGP_OK;
+  }
+  if (!strcmp(name, "isotropic")) {   // one theta for all features: n_par shrinks by d - 1
+    h->isotropic = value != 0;
     return MGP_OK;
   }
   if (!strcmp(name, "time_kernels")) {
@@ -194,6 +218,12 @@ int64_t mgp_get_counter(const mgp_t *h, const char *name) {
   if (!strcmp(name, "npad")) return h->npad;
   if (!strcmp(name, "chunk")) return h->chunk;
   if (!strcmp(name, "sm_count")) return h->sm_count;
+  if (!strcmp(name, "small_path")) return h->no_small_path ? 0 : 1;
+  if (!strcmp(name, "isotropic")) return h->isotropic ? 1 : 0;
+  if (!strcmp(name, "n")) return h->n;
+  if (!strcmp(name, "world")) return h->world;
+  if (!strcmp(name, "rank")) return h->rank;
+  if (!strcmp(name, "bcast_bytes")) return h->bcast_bytes;
   static const char *kn[4] = {"rgen", "trmm", "epilogue", "topk"};
   for (int i = 0; i < 4; i++) {
     char buf[64];
@@ -246,6 +276,8 @@ int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int 
     for (int i = 0; i < d; i++) Xc[(size_t)j * h->dpad + i] = X[(size_t)j * d + i] - center[i];
     yp[j] = y[j];
   }
+  WsScope ws(h, h->stream);   // a *_dev call may still be reading the training data on another stream
+  MGP_CUDA(h, ws.err);
   MGP_TRY(mgp_ensure(h, h->dXc, Xc.size() * 8));
   MGP_TRY(mgp_ensure(h, h->dy, yp.size() * 8));
   MGP_TRY(mgp_ensure(h, h->dcenter, center.size() * 8));
@@ -343,11 +375,18 @@ static int check_par(mgp_handle *h, int n_par, int mode) {
   const int est = mode & 15;
   if ((mode & ~(15 | MGP_LIK_RESTRICTED)) || est > MGP_MODE_NOISE_ESTIM)
     return mgp_fail(h, MGP_EINVAL, "estimation mode %d not supported", mode);
-  const int want = nll_n_par(mode, h->d);
+  const int n_theta = h->isotropic ? 1 : h->d;
+  const int want = nll_n_par(mode, h->d) - h->d + n_theta;
   if (n_par != want)
-    return mgp_fail(h, MGP_EINVAL, "n_par = %d, expected %d for mode %d (anisotropic theta + %d)", n_par,
-                    want, mode, want - h->d);
+    return mgp_fail(h, MGP_EINVAL, "n_par = %d, expected %d for mode %d (%d theta + %d)", n_par,
+                    want, mode, n_theta, want - n_theta);
   return 0;
+}
+// Isotropic theta (kernel.py:312-317): the kernels always work with d values; a host vector of the
+// short layout [theta, extras...] is expanded to [theta x d, extras...].
+static void iso_expand_host(const mgp_handle *h, const double *par, int n_par, std::vector<double> &full) {
+  full.assign(h->d, par[0]);
+  for (int i = 1; i < n_par; i++) full.push_back(par[i]);
 }
 
 // Work descriptor for `B` parameter vectors living in workspace slots b_off .. b_off + B - 1 of a
@@ -410,13 +449,28 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
     const int cap = std::min(B, nll_max_batch(h));
     if (cap > h->nll_cap) MGP_TRY(nll_alloc(h, cap));
   }
+  WsScope ws(h, st);
+  MGP_CUDA(h, ws.err);
+  // isotropic theta: expand to the d-value layout the kernels use, map the gradient back afterwards
+  const int n_short = n_par;
+  double *d_grad_user = d_out_grad;
+  const bool iso = h->isotropic && h->d > 1;
+  if (iso) {
+    n_par = nll_n_par(mode, h->d);
+    MGP_TRY(mgp_ensure(h, h->niso, (size_t)2 * B * n_par * 8));
+    double *pf = P<double>(h->niso);
+    MGP_CUDA(h, launch_iso_expand(d_params, B, n_short, h->d, pf, st));
+    h->launches++;
+    d_params = pf;
+    d_out_grad = pf + (size_t)B * n_par;
+  }
   const int use = h->nll_cap;
   for (int b0 = 0; b0 < B; b0 += use) {
     const int nb = std::min(use, B - b0);
     const int G = nll_groups(h, nb);
     // with concurrent groups no GEMM launch takes every SM: the short kernels of the other groups
     // (diagonal blocks, panel solves) then start without waiting for a machine-wide GEMM to drain
-    if (G > 1 && h->gemm_cap_opt == 0) set_dgemm_cta_cap(h->sm_count * 3 / 4);
+    const int cta_cap = h->gemm_cap_opt > 0 ? h->gemm_cap_opt : (G > 1 ? h->sm_count * 3 / 4 : 0);
     if (G > 1) MGP_CUDA(h, cudaEventRecord(h->ev_fork, st));
     NllWork works[MGP_NLL_STREAMS];
     int gsize[MGP_NLL_STREAMS], gfirst[MGP_NLL_STREAMS];
@@ -429,6 +483,7 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
       fill_work(h, works[g], g0, g1 - g0, use, n_par, mode, noise_var, eval_grad,
                 d_params + (size_t)(b0 + g0) * n_par, d_out_llf + b0 + g0,
                 eval_grad ? d_out_grad + (size_t)(b0 + g0) * n_par : nullptr);
+      works[g].gemm_cta_cap = cta_cap;
       nph = nll_num_phases(works[g]);
     }
     // phase by phase, group by group: every group has its first kernels queued at once (issuing
@@ -451,7 +506,10 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
         MGP_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[g], 0));
       }
     }
-    if (G > 1 && h->gemm_cap_opt == 0) set_dgemm_cta_cap(0);
+  }
+  if (iso && eval_grad) {
+    MGP_CUDA(h, launch_iso_gather(d_out_grad, B, n_short, n_par, h->d, mode, d_grad_user, st));
+    h->launches++;
   }
   return MGP_OK;
 }
@@ -483,7 +541,7 @@ int mgp_nll_batch(mgp_t *h, int B, const double *params, int n_par, int mode, do
 // ---------------------------------------------------------------------------------------------
 // fitted state
 // ---------------------------------------------------------------------------------------------
-static int model_alloc(mgp_handle *h) {
+int mgp_model_alloc(mgp_handle *h) {
   const size_t mat = (size_t)h->npad * h->npad * 8, vec = (size_t)h->npad * 8;
   MGP_TRY(mgp_ensure(h, h->dL, mat));
   MGP_TRY(mgp_ensure(h, h->dMinv, mat));
@@ -552,12 +610,20 @@ static int adopt_slot0(mgp_handle *h, const double *theta_host, bool take_gamma)
 int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double noise_var,
                      double *out_llf) {
   CHECK_H(h);
-  MGP_TRY(check_par(h, n_par, mode));
   if (!par) return mgp_fail(h, MGP_EINVAL, "par is NULL");
-  MGP_TRY(model_alloc(h));
+  MGP_TRY(check_par(h, n_par, mode));
+  std::vector<double> pfull;
+  if (h->isotropic && h->d > 1) {
+    iso_expand_host(h, par, n_par, pfull);
+    par = pfull.data();
+    n_par = (int)pfull.size();
+  }
+  MGP_TRY(mgp_model_alloc(h));
   if (h->nll_cap < 1) MGP_TRY(nll_alloc(h, 1));
   MGP_TRY(mgp_ensure(h, h->npar, (size_t)n_par * 8 + 64));
   cudaStream_t st = h->stream;
+  WsScope ws(h, st);
+  MGP_CUDA(h, ws.err);
   MGP_CUDA(h, cudaMemcpyAsync(h->npar.p, par, (size_t)n_par * 8, cudaMemcpyHostToDevice, st));
   NllWork w;
   fill_work(h, w, 0, 1, h->nll_cap, n_par, mode, noise_var, 0, P<double>(h->npar), nullptr, nullptr);
@@ -585,6 +651,53 @@ int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double no
   return MGP_OK;
 }
 
+int mgp_nll_env(mgp_t *h, const double *par, int n_par, int mode, double noise_var, double *out_L,
+                double *out_rho, double *out_Yt, double *out_Ft, double *out_scalars) {
+  CHECK_H(h);
+  if (!par) return mgp_fail(h, MGP_EINVAL, "par is NULL");
+  MGP_TRY(check_par(h, n_par, mode));
+  std::vector<double> pfull;
+  if (h->isotropic && h->d > 1) {
+    iso_expand_host(h, par, n_par, pfull);
+    par = pfull.data();
+    n_par = (int)pfull.size();
+  }
+  if (h->nll_cap < 1) MGP_TRY(nll_alloc(h, 1));
+  MGP_TRY(mgp_ensure(h, h->npar, (size_t)n_par * 8 + 64));
+  cudaStream_t st = h->stream;
+  WsScope ws(h, st);
+  MGP_CUDA(h, ws.err);
+  MGP_CUDA(h, cudaMemcpyAsync(h->npar.p, par, (size_t)n_par * 8, cudaMemcpyHostToDevice, st));
+  NllWork w;
+  fill_work(h, w, 0, 1, h->nll_cap, n_par, mode, noise_var, 0, P<double>(h->npar), nullptr, nullptr);
+  w.want_bhat = 1;   // exported factor: zero the tiles above the block diagonal
+  MGP_CUDA(h, nll_pipeline(w, st, &h->launches));
+  std::vector<double> sc(nll_scal_doubles());
+  int status = 0;
+  const int n = h->n;
+  MGP_CUDA(h, cudaMemcpyAsync(sc.data(), w.scal, sc.size() * 8, cudaMemcpyDeviceToHost, st));
+  MGP_CUDA(h, cudaMemcpyAsync(&status, w.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (out_L)
+    MGP_CUDA(h, cudaMemcpy2DAsync(out_L, (size_t)n * 8, w.L, (size_t)h->npad * 8, (size_t)n * 8, n,
+                                  cudaMemcpyDeviceToHost, st));
+  if (out_rho) MGP_CUDA(h, cudaMemcpyAsync(out_rho, w.rho, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (out_Yt) MGP_CUDA(h, cudaMemcpyAsync(out_Yt, w.Yt, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (out_Ft) {
+    if (h->p > 1 && h->trend_est)
+      MGP_CUDA(h, cudaMemcpy2DAsync(out_Ft, (size_t)h->p * 8, w.Ftm, (size_t)MGP_TP * 8, (size_t)h->p * 8, n,
+                                    cudaMemcpyDeviceToHost, st));
+    else
+      MGP_CUDA(h, cudaMemcpyAsync(out_Ft, w.Ft, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  }
+  MGP_CUDA(h, cudaStreamSynchronize(st));
+  if (status > 0) return mgp_fail(h, MGP_ENOTPD, "correlation matrix not positive definite at pivot %d", status);
+  if (out_scalars) {
+    out_scalars[0] = sc[NLL_SIGMA2]; out_scalars[1] = sc[NLL_BETA]; out_scalars[2] = -sqrt(sc[NLL_FTF]);
+    out_scalars[3] = sc[NLL_LLF]; out_scalars[4] = sc[NLL_NV];
+  }
+  return MGP_OK;
+}
+
 int mgp_get_trend(mgp_t *h, double *out_beta) {
   CHECK_H(h);
   if (!h->fitted) return mgp_fail(h, MGP_ESTATE, "model is not fitted");
@@ -600,9 +713,11 @@ int mgp_set_state(mgp_t *h, const double *theta, const double *L, const double *
   CHECK_H(h);
   if (h->n == 0) return mgp_fail(h, MGP_ESTATE, "mgp_set_train must be called first");
   if (!theta || !L || !gamma || !beta) return mgp_fail(h, MGP_EINVAL, "NULL state array");
-  MGP_TRY(model_alloc(h));
+  MGP_TRY(mgp_model_alloc(h));
   if (h->nll_cap < 1) MGP_TRY(nll_alloc(h, 1));
   cudaStream_t st = h->stream;
+  WsScope ws(h, st);
+  MGP_CUDA(h, ws.err);
   const int n = h->n, npad = h->npad;
   // L -> slot 0 (identity on the padding)
   std::vector<double> Lp((size_t)npad * npad, 0.0), gp(npad, 0.0);
@@ -644,6 +759,8 @@ int mgp_get_state(mgp_t *h, double *out_theta, double *out_L, double *out_gamma,
   CHECK_H(h);
   if (!h->fitted) return mgp_fail(h, MGP_ESTATE, "model is not fitted");
   cudaStream_t st = h->stream;
+  WsScope ws(h, st);
+  MGP_CUDA(h, ws.err);
   const int n = h->n;
   if (out_theta) MGP_CUDA(h, cudaMemcpyAsync(out_theta, h->dtheta.p, (size_t)h->d * 8, cudaMemcpyDeviceToHost, st));
   if (out_L)
@@ -726,6 +843,8 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
   }
   if (q.topk > 64) return mgp_fail(h, MGP_EINVAL, "k must be <= 64");
   MGP_TRY(post_workspace(h, q.want_dx));
+  WsScope ws(h, st);
+  MGP_CUDA(h, ws.err);
   if (q.want_dx) MGP_TRY(ensure_rinv(h, st));
   const int NJ8 = h->npad / 8;
   const bool ordinary = h->trend_est;

@@ -823,9 +823,11 @@ __global__ void __launch_bounds__(1024) k_pack_sym(const double *Rinv, int n, in
 // ---- launchers ------------------------------------------------------------------------------
 // Scheduler words {next tile, finished CTAs} per stream: kernels on one stream run back to back and
 // re-arm the words themselves; concurrent streams (batch groups) must not share them.
+static std::mutex g_sched_mu;
+static std::map<std::pair<int, cudaStream_t>, int *> g_sched_table;
 static int *sched_words(cudaStream_t st) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, int *> table;
+  std::mutex &mu = g_sched_mu;
+  auto &table = g_sched_table;
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
@@ -842,8 +844,15 @@ static int *sched_words(cudaStream_t st) {
   return p;
 }
 
-static int g_gemm_cta_cap = 0;   // 0 = one CTA per SM
-void set_dgemm_cta_cap(int cap) { g_gemm_cta_cap = cap; }
+void release_dgemm_stream(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_sched_mu);
+  auto it = g_sched_table.find(std::make_pair(dev, st));
+  if (it == g_sched_table.end()) return;
+  cudaFree(it->second);
+  g_sched_table.erase(it);
+}
 
 cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   static bool attr_done[MGP_MAX_DEVICES] = {};
@@ -862,7 +871,7 @@ cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   if (!sched) return cudaErrorMemoryAllocation;
   int total = (g.N / 128) * (g.M / 128) * g.n_inner * g.n_outer;
   int limit = sm_count;
-  if (g_gemm_cta_cap > 0 && limit > g_gemm_cta_cap) limit = g_gemm_cta_cap;
+  if (g.cta_cap > 0 && limit > g.cta_cap) limit = g.cta_cap;
   const bool half = !g.ta && !g.tb && g.kmode == 0 && 2 * total <= limit;   // see k_dgemm: MT = 64
   if (half) total *= 2;
   const int grid = total < limit ? total : limit;
@@ -909,7 +918,7 @@ int chol_panels(int npad) { return (npad / 128 + 3) / 4; }
 
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
-                         bool clean_upper, int panel_lo, int panel_hi) {
+                         bool clean_upper, int panel_lo, int panel_hi, int cta_cap) {
   // Two-level right-looking blocked Cholesky.  Tiles are 128 wide; PB tiles form a panel.  Inside a
   // panel every tile column is factored (diagonal block, TRSM through the explicit inverse of the
   // diagonal block) and applied to the remaining columns OF THE PANEL only (k = 128); the matrix
@@ -933,6 +942,7 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
       if (below == 0) break;
       const int64_t off_panel = (int64_t)(kb + 1) * 128 * npad + (int64_t)kb * 128;
       GemmDesc g = {};
+      g.cta_cap = cta_cap;
       // L[kb+1:, kb] = A[kb+1:, kb] * inv(L_kk)^T
       g.A = A + off_panel; g.lda = npad; g.ta = 0;
       g.B = linv + (int64_t)kb * 128 * 128; g.ldb = 128; g.tb = 0;
@@ -947,6 +957,7 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
       if (inpanel > 0) {
         // A[kb+1:, kb+1:k1] -= L[kb+1:, kb] L[kb+1:k1, kb]^T  (lower tiles)
         GemmDesc u = {};
+      u.cta_cap = cta_cap;
         u.A = L + off_panel; u.lda = npad; u.ta = 0;
         u.B = L + off_panel; u.ldb = npad; u.tb = 0;
         u.C = A + (int64_t)(kb + 1) * 128 * (npad + 1); u.ldc = npad;
@@ -962,6 +973,7 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
       // A[k1:, k1:] -= L[k1:, k0:k1] L[k1:, k0:k1]^T  (lower tiles), k = (k1 - k0) * 128
       const int64_t off = (int64_t)k1 * 128 * npad + (int64_t)k0 * 128;
       GemmDesc u = {};
+      u.cta_cap = cta_cap;
       u.A = L + off; u.lda = npad; u.ta = 0;
       u.B = L + off; u.ldb = npad; u.tb = 0;
       u.C = A + (int64_t)k1 * 128 * (npad + 1); u.ldc = npad;
@@ -978,7 +990,7 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
 
 cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, int64_t sMat,
                           const double *linv, int64_t sInv, int batch, cudaStream_t st,
-                          int64_t *launches, bool clean_upper) {
+                          int64_t *launches, bool clean_upper, int cta_cap) {
   const int NI = npad / 128;
   if (clean_upper)
     for (int b = 0; b < batch; b++)
@@ -999,6 +1011,7 @@ cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, in
       const int64_t base = (int64_t)p0 * 2 * s * (npad + 1);
       const int64_t pstride = (int64_t)2 * s * (npad + 1);
       GemmDesc g = {};
+      g.cta_cap = cta_cap;
       g.A = L + base + (int64_t)s * npad; g.lda = npad; g.ta = 0;   // C block  [brows][s]
       g.B = Minv + base; g.ldb = npad; g.tb = 1;                   // A^-1     [s][s] k-major
       g.C = T + base + (int64_t)s * npad; g.ldc = npad;
@@ -1008,6 +1021,7 @@ cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, in
       g.sA_out = g.sB_out = g.sC_out = sMat;
       LA_TRY(launch_dgemm(g, st));
       GemmDesc h = {};
+      h.cta_cap = cta_cap;
       h.A = Minv + base + (int64_t)s * (npad + 1); h.lda = npad; h.ta = 0;  // B^-1 [brows][brows]
       h.B = T + base + (int64_t)s * npad; h.ldb = npad; h.tb = 1;          // T    [brows][s]
       h.C = Minv + base + (int64_t)s * npad; h.ldc = npad;
@@ -1023,8 +1037,9 @@ cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, in
 }
 
 cudaError_t lauum_blocked(const double *Minv, double *Rinv, int npad, int64_t sMat, int batch,
-                          cudaStream_t st, int64_t *launches) {
+                          cudaStream_t st, int64_t *launches, int cta_cap) {
   GemmDesc g = {};
+  g.cta_cap = cta_cap;
   g.A = Minv; g.lda = npad; g.ta = 1;
   g.B = Minv; g.ldb = npad; g.tb = 1;
   g.C = Rinv; g.ldc = npad;

@@ -20,11 +20,15 @@ struct GemmDesc {
   int order;   // tile hand-out order (longest k first): 0/1 rows ascending, 2 rows descending, 3 columns ascending
   int n_inner, n_outer;
   int64_t sA_in, sB_in, sC_in, sA_out, sB_out, sC_out;
+  // Upper bound on the CTAs of this launch (0 = one per SM): leaves SMs to the kernels of other
+  // streams when several batch groups run concurrently.  Per launch, so that two handles (or two
+  // host threads) never see each other's setting.
+  int cta_cap;
 };
 cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st);
-// Upper bound on the CTAs of one GEMM launch (0 = one per SM): leaves SMs to kernels of other
-// streams when several batch groups run concurrently.
-void set_dgemm_cta_cap(int cap);
+// Frees the tile-scheduler words kept for `st` on the current device (called when a handle destroys
+// its streams).
+void release_dgemm_stream(cudaStream_t st);
 
 // In-place Cholesky of the kb-th 128x128 diagonal block of each matrix of the batch
 // (A row-major, ld, batch stride sA), writing L_kk into Lout (same geometry) and L_kk^-1 into
@@ -40,14 +44,14 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
 int chol_panels(int npad);
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
-                         bool clean_upper, int panel_lo, int panel_hi);
+                         bool clean_upper, int panel_lo, int panel_hi, int cta_cap = 0);
 // Minv = L^-1 given L and the diagonal-block inverses; T is scratch (npad x npad per matrix).
 cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, int64_t sMat,
                           const double *linv, int64_t sInv, int batch, cudaStream_t st,
-                          int64_t *launches, bool clean_upper);
+                          int64_t *launches, bool clean_upper, int cta_cap = 0);
 // Rinv(lower tiles) = Minv^T Minv.
 cudaError_t lauum_blocked(const double *Minv, double *Rinv, int npad, int64_t sMat, int batch,
-                          cudaStream_t st, int64_t *launches);
+                          cudaStream_t st, int64_t *launches, int cta_cap = 0);
 
 // y = M x (trans == 0) or y = M^T x (trans == 1), M lower-triangular row-major npad x npad.
 // x == nullptr means the all-ones vector restricted to the first n entries.

@@ -25,6 +25,12 @@ struct mgp_handle {
   cudaStream_t out_stream = nullptr;   // D2H of staged results
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int64_t launches = 0;
+  // Workspace ordering across streams: the posterior / likelihood scratch, the fitted-state buffers
+  // and the running top-k are shared by the host-pointer entry points (h->stream) and the *_dev
+  // entry points (caller's stream).  Every entry point makes its stream wait on ev_ws (recorded by
+  // whoever used the workspaces last) before touching them and records it again when done.
+  cudaEvent_t ev_ws = nullptr;
+  bool ws_recorded = false;
   // optional per-kernel timing (option "time_kernels"): event pairs resolved lazily
   int time_kernels = 0;
   struct EvPair { cudaEvent_t a, b; int which; };
@@ -36,6 +42,7 @@ struct mgp_handle {
   // ---- training data -------------------------------------------------------------------
   int n = 0, d = 0, npad = 0, dpad = 0, NI = 0;
   int corr = 0, trend = 0;
+  bool isotropic = false;       // one theta shared by all features (kernel.py:312-317); option "isotropic"
   double beta0 = 0.0;
   int p = 1;                    // basis functions of the trend (1 constant, d + 1 linear)
   bool trend_est = false;       // coefficients estimated (ordinary / universal kriging)
@@ -82,11 +89,19 @@ struct mgp_handle {
   cudaEvent_t ev_fork = nullptr, ev_join[MGP_NLL_STREAMS] = {};
   DevBuf nR, nL, nM, nT, nLinvDiag, nvec, nscal, npar, ngpart;
   DevBuf nFtm, nBhat, ntws;   // general-trend workspaces (allocated when p > 1)
+  DevBuf niso;                // isotropic theta: expanded parameters | full gradient
+  // ---- multi-GPU (comm.cu) -----------------------------------------------------------------
+  void *comm = nullptr;       // ncclComm_t
+  int rank = 0, world = 1;
+  DevBuf dcomm, dgather, dgather_io;
+  cudaEvent_t ev_gather = nullptr;
+  int64_t bcast_bytes = 0;    // payload of the last mgp_bcast_model
 };
 
 int mgp_fail(mgp_handle *h, int code, const char *fmt, ...);
 int mgp_cuda_fail(mgp_handle *h, cudaError_t e, const char *what);
 int mgp_ensure(mgp_handle *h, DevBuf &b, size_t bytes);
+extern "C" int mgp_model_alloc(mgp_handle *h);   // fitted-model buffers of a handle that has training data (api.cu)
 
 #define MGP_CUDA(h, call)                                          \
   do {                                                             \

@@ -660,6 +660,21 @@ __global__ void k_dup_check(const double *Xc, int n, int dpad, int *flag) {
   if (same) atomicOr(flag, 1);
 }
 
+__global__ void k_iso_expand(const double *P, int B, int n_short, int d, double *Pfull) {
+  const int n_full = d + n_short - 1;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * n_full) return;
+  const int b = e / n_full, i = e % n_full;
+  Pfull[e] = P[(int64_t)b * n_short + (i < d ? 0 : i - d + 1)];
+}
+__global__ void k_iso_gather(const double *Gfull, int B, int n_short, int n_full, int d, int mode, double *G) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * n_short) return;
+  const int b = e / n_short, i = e % n_short;
+  const bool share = !(mode & MGP_LIK_RESTRICTED) && (mode & 15) == MGP_MODE_NOISE_ESTIM && i == n_short - 1;
+  G[e] = Gfull[(int64_t)b * n_full + (share ? d : i)];
+}
+
 template <int CORR>
 cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, const double *Xc, int n,
                           int npad, const double *params, int n_par, int mode, const double *Rinv,
@@ -720,6 +735,17 @@ cudaError_t launch_trend_q(const double *Ftm, const double *tws, int n, int npad
   k_trend_q<<<dim3((npad + 63) / 64, batch), 256, smem, st>>>(Ftm, tws, n, npad, p, Qp);
   return cudaGetLastError();
 }
+cudaError_t launch_iso_expand(const double *P, int B, int n_short, int d, double *Pfull, cudaStream_t st) {
+  const int tot = B * (d + n_short - 1);
+  k_iso_expand<<<(tot + 255) / 256, 256, 0, st>>>(P, B, n_short, d, Pfull);
+  return cudaGetLastError();
+}
+cudaError_t launch_iso_gather(const double *Gfull, int B, int n_short, int n_full, int d, int mode, double *G,
+                              cudaStream_t st) {
+  const int tot = B * n_short;
+  k_iso_gather<<<(tot + 255) / 256, 256, 0, st>>>(Gfull, B, n_short, n_full, d, mode, G);
+  return cudaGetLastError();
+}
 int nll_n_par(int mode, int d) { return d + (d - mode_n_theta(mode, d)); }
 
 cudaError_t launch_dup_check(const double *Xc, int n, int dpad, int *flag, cudaStream_t st) {
@@ -777,11 +803,11 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
     const int lo = phase < 0 ? 0 : phase - 1, hi = phase < 0 ? P : phase;
     if (phase < 0 || (phase >= 1 && phase <= P))
       NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches,
-                          w.want_bhat != 0, lo, hi));
+                          w.want_bhat != 0, lo, hi, w.gemm_cta_cap));
   }
   if (phase >= 0 && phase != last) return cudaSuccess;
   NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches,
-                       w.want_bhat != 0));
+                       w.want_bhat != 0, w.gemm_cta_cap));
   double *Yt = w.Yt, *Ft = w.Ft, *rho = w.rho, *gamma = w.gamma;
   const bool general = w.p > 1 && w.ordinary;   // p basis functions with estimated coefficients
   NL_TRY(launch_trmv(w.M, npad, sM, w.y, 0, Yt, npad, n, 0, B, st));
@@ -791,6 +817,7 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
   } else {
     // Ft = L^-1 F as a GEMM (gpr.py:690), then the normal equations of the p x p trend problem
     GemmDesc g = {};
+    g.cta_cap = w.gemm_cta_cap;
     g.A = w.M; g.lda = npad; g.ta = 0;
     g.B = w.F; g.ldb = MGP_TP; g.tb = 1;
     g.C = w.Ftm; g.ldc = MGP_TP;
@@ -812,6 +839,7 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
     // Bhat = L^-T (Ft C^-T): REML's (L^-T Q)(L^-T Q)^T term and, for the fitted model, Ft^T L^-1 r
     NL_TRY(launch_trend_q(w.Ftm, w.tws, n, npad, w.p, w.T, B, st));   // T is free until LAUUM
     GemmDesc g = {};
+    g.cta_cap = w.gemm_cta_cap;
     g.A = w.M; g.lda = npad; g.ta = 1;
     g.B = w.T; g.ldb = MGP_TP; g.tb = 1;
     g.C = w.Bhat; g.ldc = MGP_TP;
@@ -826,7 +854,7 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
       NL_TRY(launch_trmv(w.M, npad, sM, Ft, npad, w.avec, npad, n, 1, B, st));
       (*launches)++;
     }
-    NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, st, launches));
+    NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, st, launches, w.gemm_cta_cap));
     const int ntiles = NI * (NI + 1) / 2;
     const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + 8 * (w.dpad + 2) + MGP_EXP_TAB_DOUBLES) * sizeof(double);
     dim3 grid(ntiles, B);

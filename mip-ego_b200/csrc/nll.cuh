@@ -7,6 +7,7 @@
 
 struct NllWork {
   int n, npad, dpad, B, n_par, mode, corr, ordinary, eval_grad;
+  int gemm_cta_cap;       // CTA cap of the GEMM launches of this work item (0 = one per SM)
   int have_L;             // 1: L (B=1) is given in w.L; skip the correlation build and Cholesky
   double noise_var, beta0;
   const double *Xc;      // npad x dpad centred training inputs
@@ -55,6 +56,15 @@ cudaError_t launch_trend_q(const double *Ftm, const double *tws, int n, int npad
 // scal slots
 enum { NLL_SIGMA2 = 0, NLL_LLF = 1, NLL_FTF = 2, NLL_FTY = 3, NLL_RR = 4, NLL_LOGDET = 5, NLL_S = 6,
        NLL_V = 7, NLL_BETA = 8, NLL_NV = 9, NLL_COEFA = 10, NLL_THSCALE = 11, NLL_LOGDETA = 12 };
+// isotropic theta: Pfull[b] = [P[b][0] x d, P[b][1:]]  (n_short = 1 + extras values per row)
+cudaError_t launch_iso_expand(const double *P, int B, int n_short, int d, double *Pfull, cudaStream_t st);
+// ... and the gradient back: G[b][i] = Gfull[b][i], except the noise-share derivative of the
+// concentrated noise_estim mode, which is Gfull[b][d].  The reference indexes its (n, n, d (+1))
+// derivative tensor with range(n_par) (gpr.py:907-944, 760-783), so an isotropic theta receives the
+// derivative w.r.t. the FIRST feature's theta and, in noisy mode with d > 1, sigma2 receives the
+// derivative w.r.t. the second feature's theta: reproduced as is.
+cudaError_t launch_iso_gather(const double *Gfull, int B, int n_short, int n_full, int d, int mode, double *G,
+                              cudaStream_t st);
 // number of hyper-parameters of a mode for d features (include/mgp.h)
 int nll_n_par(int mode, int d);
 // phase < 0 runs everything; otherwise one of nll_num_phases(w) phases (R build | one Cholesky panel

@@ -8,8 +8,21 @@ independent units.  The only exchanges are
   * an all-gather of each rank's k best (value, global index) pairs, merged identically on every
     rank (value descending, ties -> smaller global index, the order the single-GPU kernel uses).
 No collective sits inside the compute kernels; the data path itself needs none.
+
+Two transports:
+  * the library's own NCCL communicator (`init_comm`: mgp_comm_init / mgp_bcast_model /
+    mgp_allgather_topk in include/mgp.h) -- the model travels HBM -> HBM with no host bounce and no
+    re-factorisation on the receivers, the top-k merge runs on the device.  torch.distributed is
+    then only the rendezvous that ships the 128-byte NCCL id and a few Python scalars;
+  * plain torch.distributed tensors (gloo in the CPU tests, or NCCL) when no communicator was
+    created: host-side pack / unpack + `set_fitted_state`.
 """
+import ctypes
+
 import numpy as np
+
+_PY_STATE = ("par", "_par_fitted", "theta_", "sigma2", "noise_var", "_env_noise_var", "log_likelihood_",
+             "thetaU", "_nugget")
 
 
 def shard_range(m, rank, world):
@@ -25,31 +38,97 @@ def _dist():
     return torch, dist
 
 
-def broadcast_fitted_state(gp, src=0, device=None):
-    """Broadcast (theta, L, gamma, sigma2, beta) of the fitted model on `src` and adopt it on the
-    other ranks through `set_fitted_state` (mgp_set_state).  Every rank must hold the same
-    training data X, y (they are part of the optimiser state in the BO loop)."""
+def has_comm(gp):
+    """True when gp's device handle owns an NCCL communicator (init_comm)."""
+    h = getattr(gp, "_h", None)
+    return h is not None and h.counter("world") > 1
+
+
+def init_comm(gp):
+    """Create the library's NCCL communicator for gp's handle over the torch.distributed world
+    (collective).  The 128-byte ncclUniqueId is made on rank 0 (mgp_comm_unique_id) and shipped with
+    torch.distributed -- any backend; that is all torch does for the exchanges that follow."""
     torch, dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    h = gp._handle()
+    if world == 1:
+        return gp
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        rc = h.lib.mgp_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError("mgp_comm_unique_id failed (%d): %s" % (rc, h.lib.mgp_comm_info(h.h).decode()))
+    box = [buf.raw if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    h.check(h.lib.mgp_comm_init(h.h, rank, world, box[0]))
+    return gp
+
+
+def _broadcast_model_nccl(gp, src):
+    """HBM -> HBM broadcast of the fitted model through the library's communicator."""
+    torch, dist = _dist()
+    rank = dist.get_rank()
+    h = gp._handle()
+    h.check(h.lib.mgp_bcast_model(h.h, int(src)))
+    # the Python-side attributes (hyper-parameters, typed scalars): a few hundred bytes
+    box = [None]
+    if rank == src:
+        box[0] = {k: getattr(gp, k) for k in _PY_STATE if hasattr(gp, k)}
+        box[0]["beta"] = None if gp.mean.beta is None else np.array(gp.mean.beta, dtype=np.float64)
+        box[0]["estimate_trend"] = gp.estimate_trend
+    dist.broadcast_object_list(box, src=src)
+    if rank != src:
+        st = dict(box[0])
+        beta, est = st.pop("beta"), st.pop("estimate_trend")
+        gp.__dict__.update(st)
+        if est and beta is not None:
+            gp.mean.beta = beta
+        gp._cache = {}
+        gp._host_state = None
+        gp.is_fitted = True
+    return gp
+
+
+def broadcast_fitted_state(gp, src=0, device=None):
+    """Give every rank the bit-identical fitted model of `src`.  Every rank must hold the same
+    training data X, y (they are part of the optimiser state in the BO loop; non-source ranks call
+    `gp._check_data(X, y)` first).  With a communicator (`init_comm`) the model goes HBM -> HBM
+    (mgp_bcast_model); otherwise (theta, L, gamma, sigma2, beta, par) travel as one torch tensor and
+    are adopted through `set_fitted_state` (mgp_set_state)."""
+    torch, dist = _dist()
+    if has_comm(gp):
+        return _broadcast_model_nccl(gp, src)
     rank = dist.get_rank()
     n, d = gp.X.shape
     p = int(getattr(gp.mean, "n_dim", 1) or 1)      # trend coefficients (1 constant, d + 1 linear)
     dev = device if device is not None else "cpu"
+    # full hyper-parameter vector (theta + sigma2 / alpha / noise_var as the mode has them), so that
+    # update(reoptimize=False) works on the receivers in every estimation mode
+    n_extra = len(gp._par_names()) - 1 if hasattr(gp, "_par_names") else 0
     if rank == src:
+        if n_extra:
+            extra = np.asarray(gp._par_vector(), dtype=np.float64)[-n_extra:]
+        else:
+            extra = np.empty(0)
         pack = [np.asarray(gp._state("theta"), dtype=np.float64).ravel(),
                 np.ascontiguousarray(gp.C, dtype=np.float64).ravel(),
                 np.asarray(gp.gamma, dtype=np.float64).ravel(),
-                np.r_[float(np.ravel(gp.sigma2)[0]), np.ravel(gp.mean.beta).astype(np.float64)]]
+                np.r_[float(np.ravel(gp.sigma2)[0]), np.ravel(gp.mean.beta).astype(np.float64)], extra]
         flat = np.concatenate(pack)
     else:
-        flat = np.empty(d + n * n + n + 1 + p)
+        flat = np.empty(d + n * n + n + 1 + p + n_extra)
     t = torch.from_numpy(flat).to(dev)
     dist.broadcast(t, src=src)
     if rank != src:
         flat = t.cpu().numpy()
         theta, L = flat[:d], flat[d:d + n * n].reshape(n, n)
-        gamma, sc = flat[d + n * n:d + n * n + n], flat[d + n * n + n:]
+        gamma, sc = flat[d + n * n:d + n * n + n], flat[d + n * n + n:d + n * n + n + 1 + p]
+        kw = {}
+        if n_extra:
+            n_theta = int(np.size(getattr(gp, "theta0", theta)))
+            kw["par"] = np.r_[theta[:n_theta] if n_theta == 1 else theta, flat[-n_extra:]]
         gp.set_fitted_state(gp.X, gp.y.ravel(), theta, L, gamma, float(sc[0]),
-                            float(sc[1]) if p == 1 else sc[1:].copy())
+                            float(sc[1]) if p == 1 else sc[1:].copy(), **kw)
     return gp
 
 
@@ -71,9 +150,20 @@ def merge_topk(vals, idx, k):
     return out_v, out_i
 
 
-def allgather_topk(local_vals, local_idx, k, offset, device=None):
+def allgather_topk(local_vals, local_idx, k, offset, device=None, gp=None):
     """All-gather each rank's (n_sets, k) best candidates (local indices + `offset` = global) and
-    merge.  Every rank returns the same (values, global indices)."""
+    merge.  Every rank returns the same (values, global indices).  With `gp` holding a communicator
+    the exchange and the merge run on the device (mgp_allgather_topk)."""
+    if gp is not None and has_comm(gp):
+        from . import _cabi
+        h = gp._handle()
+        lv = np.ascontiguousarray(local_vals, dtype=np.float64)
+        li = np.ascontiguousarray(local_idx, dtype=np.int64)
+        ns, kk = lv.shape
+        ov, oi = np.empty((ns, kk)), np.empty((ns, kk), dtype=np.int64)
+        h.check(h.lib.mgp_allgather_topk(h.h, ns, kk, _cabi.dptr(lv), li.ctypes.data_as(_cabi.c_lp), int(offset),
+                                         _cabi.dptr(ov), oi.ctypes.data_as(_cabi.c_lp)))
+        return ov[:, :k], oi[:, :k]
     torch, dist = _dist()
     world = dist.get_world_size()
     dev = device if device is not None else "cpu"
@@ -98,7 +188,32 @@ def sharded_topk(criterion, X, k=1, params=None, device=None):
         pad = k - v.shape[1]
         v = np.c_[v, np.full((v.shape[0], pad), -np.inf)]
         i = np.c_[i, np.full((i.shape[0], pad), -1, dtype=np.int64)]
-    return allgather_topk(v, i, k, lo, device=device)
+    return allgather_topk(v, i, k, lo, device=device, gp=getattr(criterion, "model", None))
+
+
+def sharded_topk_device(criterion, X_shard, offset, k=1, params=None, out=None):
+    """Device-resident population arg-max across ranks: `X_shard` is THIS rank's (m_r, d) CUDA tensor
+    of candidates whose row 0 has global index `offset`.  The local top-k (mgp_acq_topk_dev), the
+    NCCL all-gather and the merge (mgp_allgather_topk_dev) are enqueued on torch's current stream;
+    nothing synchronises.  Returns CUDA tensors (values (n_sets, k), global indices (n_sets, k)),
+    identical on every rank.  Needs `init_comm(criterion.model)`."""
+    import torch
+    gp = criterion.model
+    h = gp._handle()
+    if h.counter("world") <= 1:
+        raise RuntimeError("sharded_topk_device needs dist.init_comm(model)")
+    tv, ti = criterion.topk_device(X_shard, k=k, params=params)
+    ns = tv.shape[0]
+    if out is None:
+        out = (torch.empty((ns, k), dtype=torch.float64, device=X_shard.device),
+               torch.empty((ns, k), dtype=torch.int64, device=X_shard.device))
+    stream = torch.cuda.current_stream(X_shard.device).cuda_stream
+    h.check(h.lib.mgp_allgather_topk_dev(h.h, ns, k, tv.data_ptr(), ti.data_ptr(), int(offset),
+                                         out[0].data_ptr(), out[1].data_ptr(), stream))
+    # tv / ti are read by the enqueued kernels: keep them alive until the stream has passed them
+    tv.record_stream(torch.cuda.current_stream(X_shard.device))
+    ti.record_stream(torch.cuda.current_stream(X_shard.device))
+    return out
 
 
 def sharded_nll(gp, params, eval_grad=True, device=None):

@@ -138,6 +138,8 @@ class GaussianProcess(object):
         if rc == _cabi.MGP_EINVAL and b"duplicate rows" in h.lib.mgp_last_error(h.h):
             raise Exception("Multiple input features cannot have the same target value.")
         h.check(rc)
+        # one theta for all features (kernel.py:312-317): the parameter vectors get 1 theta entry
+        h.set_option("isotropic", 1 if (self.theta0.size == 1 and d > 1) else 0)
 
     def _beta_from_device(self):
         h = self._handle()
@@ -171,9 +173,8 @@ class GaussianProcess(object):
         self.X, self.y = X, y.reshape(-1, 1)
         self._check_params()
         n, d = X.shape
-        if self.theta0.size not in (d,):
-            raise ValueError("the CUDA path needs one theta per feature (anisotropic): "
-                             "len(theta0)=%d, n_features=%d" % (self.theta0.size, d))
+        if self.theta0.size not in (1, d):
+            raise ValueError("Length of theta must be 1 or %s" % d)      # kernel.py:314-315
         self._set_train(X, y)
         self._cache = {}
         self._host_state = None
@@ -222,12 +223,48 @@ class GaussianProcess(object):
         par = np.asarray(par, dtype=np.float64).ravel()
         llf, grad, status = self.log_likelihood_batch(par, eval_grad=eval_grad)
         if env is not None and status[0] <= 0:
-            self._finalize(par)
-            env.update(sigma2=self.sigma2, noise_var=self._env_noise_var, rho=self.rho, Yt=self.Yt,
-                       C=self.C, Ft=self.Ft, G=self.G, Q=self.Q)
+            env.update(self._harvest_env(par))
         if eval_grad:
             return float(llf[0]), grad[0].reshape(-1, 1)
         return float(llf[0])
+
+    def _harvest_env(self, par):
+        """The `env` dictionary of a likelihood call (gpr.py:876-887, 785-794) through mgp_nll_env:
+        computed in scratch memory, the fitted model (device and Python attributes) is not touched --
+        the reference's env harvest has no side effects either."""
+        h = self._handle()
+        n = self.X.shape[0]
+        pcols = self.mean.n_dim if self.estimate_trend else 1
+        L, rho, Yt, Ft, sc = np.empty((n, n)), np.empty(n), np.empty(n), np.empty((n, pcols)), np.zeros(5)
+        mode, nv = self._mode_nv()
+        h.check(h.lib.mgp_nll_env(h.h, _cabi.dptr(par), par.size, mode, nv, _cabi.dptr(L), _cabi.dptr(rho),
+                                  _cabi.dptr(Yt), _cabi.dptr(Ft), _cabi.dptr(sc)))
+        env = dict(sigma2=self._typed_sigma2(sc[0]), noise_var=self._typed_noise_var(sc[4]),
+                   rho=rho.reshape(-1, 1), Yt=Yt.reshape(-1, 1), C=L)
+        if self.estimate_trend:
+            if pcols == 1:
+                G = np.array([[sc[2]]])
+                Q = Ft / sc[2]
+            else:
+                from scipy import linalg
+                Q, G = linalg.qr(Ft, mode="economic")
+            env.update(Ft=Ft, G=G, Q=Q)
+        elif self.likelihood == "concentrated":
+            env.update(Ft=None, G=None, Q=None)     # gpr.py:693-697: the names exist, set to None
+        return env
+
+    def _typed_sigma2(self, v):
+        # SURVEY Q10: sigma2 is a (1,) array where the reference derives it from rho (concentrated
+        # noiseless / noise_estim, gpr.py:833,849) and a numpy scalar where it is a parameter
+        # (concentrated noisy, restricted)
+        derived = self.likelihood == "concentrated" and self.estimation_mode != "noisy"
+        return np.array([v]) if derived else np.float64(v)
+
+    def _typed_noise_var(self, v):
+        if self.estimation_mode == "noise_estim":
+            derived = self.likelihood == "concentrated"
+            return np.array([v]) if derived else np.float64(v)
+        return self._nugget if self.estimation_mode == "noisy" else 0
 
     def _hyperparameter_bound(self, par_list):
         # gpr.py:948-962
@@ -323,15 +360,8 @@ class GaussianProcess(object):
         self._host_state = None
         sc = np.zeros(5)
         h.check(h.lib.mgp_get_state(h.h, None, None, None, None, None, None, _cabi.dptr(sc)))
-        # types follow SURVEY Q10: sigma2 is a (1,) array where the reference derives it from rho
-        # (concentrated noiseless / noise_estim, gpr.py:833,849) and a numpy scalar where it is a
-        # parameter (concentrated noisy, restricted)
-        derived = self.likelihood == "concentrated" and self.estimation_mode != "noisy"
-        self.sigma2 = np.array([sc[0]]) if derived else np.float64(sc[0])
-        if self.estimation_mode == "noise_estim":
-            self._env_noise_var = np.array([sc[4]]) if derived else np.float64(sc[4])
-        else:
-            self._env_noise_var = self._nugget if self.estimation_mode == "noisy" else 0
+        self.sigma2 = self._typed_sigma2(sc[0])
+        self._env_noise_var = self._typed_noise_var(sc[4])
         if self.estimate_trend:
             self.mean.beta = self._beta_from_device()
         self._par_fitted = par.copy()
@@ -368,12 +398,8 @@ class GaussianProcess(object):
         llf = self._finalize(par)
         if not self._fitted_on_device():
             raise np.linalg.LinAlgError("correlation matrix is not positive definite")
-        n_theta = self.X.shape[1]
-        names = []
-        if self.likelihood == "restricted" or self.estimation_mode == "noisy":
-            names.append("sigma2")
-        if self.estimation_mode == "noise_estim":
-            names.append("alpha" if self.likelihood == "concentrated" else "noise_var")
+        n_theta = self.theta0.size
+        names = self._par_names()[1:]
         self.par = {"theta": par[:n_theta]}
         for k, name in enumerate(names):
             self.par[name] = par[n_theta + k:n_theta + k + 1]
@@ -388,25 +414,52 @@ class GaussianProcess(object):
         sc = np.zeros(5)
         return h.lib.mgp_get_state(h.h, None, None, None, None, None, None, _cabi.dptr(sc)) == 0
 
+    def _par_names(self):
+        names = ["theta"]
+        if self.likelihood == "restricted" or self.estimation_mode == "noisy":
+            names.append("sigma2")
+        if self.estimation_mode == "noise_estim":
+            names.append("alpha" if self.likelihood == "concentrated" else "noise_var")
+        return names
+
+    def _par_vector(self):
+        """The fitted hyper-parameters as the flat vector of the likelihood's layout."""
+        full = getattr(self, "_par_fitted", None)
+        if full is not None:
+            return np.array(full, dtype=np.float64)
+        return np.concatenate([np.ravel(self.par[k]) for k in self._par_names() if k in self.par])
+
     def update(self, X, y, reoptimize=True):
         """gpr.py:387-390 (`update` = `fit`; its TODO asks for incremental training).
-        reoptimize=False keeps the current hyper-parameters and only rebuilds the factorisation and
-        the posterior operands for the new data (mgp_finalize_fit: 2/3 n^3 flop on the tensor pipe,
-        about 2 ms at n = 4096) -- the cheap refit a BO loop wants between MLE rounds.  A rank-k
-        Cholesky append would save part of that at O(n^2 k); at these sizes the full rebuild is
-        already far below the cost of one objective evaluation, so it is not implemented."""
+        reoptimize=False keeps the current hyper-parameters.  When (X, y) extends the current
+        training set by appended rows, the factorisation is EXTENDED (mgp_append_train: rank-k border
+        update of L, L^-1 and the posterior operands, O(n^2 k) instead of O(n^3)); otherwise it is
+        rebuilt at the current hyper-parameters (mgp_finalize_fit)."""
         if reoptimize or not self.is_fitted:
             return self.fit(X, y)
-        par = np.concatenate([np.ravel(v) for v in self.par.values()])
-        if self.estimation_mode == "noise_estim" or self.likelihood == "restricted" or \
-                self.estimation_mode == "noisy":
-            full = getattr(self, "_par_fitted", None)
-            par = full if full is not None and full.size >= par.size else par
+        par = self._par_vector()
+        n_need = self.theta0.size + len(self._par_names()) - 1
+        if par.size != n_need:
+            raise ValueError("the adopted state holds %d hyper-parameters, the %s / %s likelihood needs %d: "
+                             "pass the full parameter vector to set_fitted_state(par=...)"
+                             % (par.size, self.likelihood, self.estimation_mode, n_need))
+        self._ensure_device_state()
+        Xn = _check_array(X)
+        n0 = self.X.shape[0]
+        if (self._append_ok and Xn.shape[0] > n0 and Xn.shape[1] == self.X.shape[1]
+                and np.array_equal(Xn[:n0], self.X)
+                and np.array_equal(np.asarray(y, dtype=np.float64).ravel()[:n0], self.y.ravel())):
+            return self._append(Xn, np.asarray(y, dtype=np.float64).ravel(), par)
         return self.fit_fixed(X, y, par)
 
-    def set_fitted_state(self, X, y, theta, L, gamma, sigma2, beta):
-        """Adopt an externally fitted model (mgp_set_state): used by un-pickling and by the
-        parity tests to give the reference and the CUDA path the identical model."""
+    _append_ok = False    # switched on where the library exports mgp_append_train
+
+    def set_fitted_state(self, X, y, theta, L, gamma, sigma2, beta, par=None):
+        """Adopt an externally fitted model (mgp_set_state): used by un-pickling, by the multi-GPU
+        broadcast and by the parity tests to give the reference and the CUDA path the identical
+        model.  `par`: the full hyper-parameter vector [theta, (sigma2 | alpha), (noise_var)] in the
+        layout of this model's likelihood / estimation mode; needed for a later
+        update(reoptimize=False) in the noisy / noise_estim / REML modes (default: theta only)."""
         X = _check_array(X)
         y = np.ascontiguousarray(y, dtype=np.float64).ravel()
         self.X, self.y = X, y.reshape(-1, 1)
@@ -417,16 +470,31 @@ class GaussianProcess(object):
             raise Exception("Shapes of beta and F do not match.")
         self._set_train(X, y, beta=bvec)
         theta = _cabi.as_f64(theta).ravel()
+        if theta.size not in (1, d):
+            raise ValueError("Length of theta must be 1 or %s" % d)
+        th_full = np.repeat(theta, d) if theta.size == 1 and d > 1 else theta
+        if self.theta0.size == 1 and d > 1:          # isotropic model: keep the 1-entry layout
+            theta = th_full[:1].copy()
         Lc = _cabi.as_f64(L, (n, n))
         g = _cabi.as_f64(gamma).ravel()
-        h.check(h.lib.mgp_set_state(h.h, _cabi.dptr(theta), _cabi.dptr(Lc), _cabi.dptr(g),
+        h.check(h.lib.mgp_set_state(h.h, _cabi.dptr(th_full), _cabi.dptr(Lc), _cabi.dptr(g),
                                     float(np.ravel(sigma2)[0]), _cabi.dptr(bvec)))
         self._cache = {}
         self._host_state = None
         self.theta_ = theta.copy()
-        self.par = {"theta": self.theta_}
-        self.sigma2 = np.array([float(np.ravel(sigma2)[0])]) if self.estimation_mode == "noiseless" \
-            else np.float64(np.ravel(sigma2)[0])
+        names = self._par_names()
+        if par is not None:
+            par = np.array(par, dtype=np.float64).ravel()
+            if par.size != theta.size + len(names) - 1:
+                raise ValueError("par has %d entries, expected %d" % (par.size, theta.size + len(names) - 1))
+            self.par = {"theta": self.theta_}
+            for k, name in enumerate(names[1:]):
+                self.par[name] = par[theta.size + k:theta.size + k + 1]
+            self._par_fitted = par
+        else:
+            self.par = {"theta": self.theta_}
+            self._par_fitted = self.theta_.copy() if len(names) == 1 else None
+        self.sigma2 = self._typed_sigma2(float(np.ravel(sigma2)[0]))
         if self.estimate_trend:
             self.mean.beta = bvec.reshape(-1, 1).copy()
             self.F = self.mean.F(X)
@@ -502,8 +570,11 @@ class GaussianProcess(object):
         if self._host_state is not None:
             st = self._host_state
             self._host_state = None
+            keep = {k: getattr(self, k) for k in ("par", "_par_fitted", "theta_", "sigma2", "noise_var",
+                                                  "_env_noise_var", "log_likelihood_") if hasattr(self, k)}
             self.set_fitted_state(st["X"], st["y"], st["theta"], st["L"], st["gamma"],
                                   st["sigma2"], st["beta"])
+            self.__dict__.update(keep)     # the pickled hyper-parameters, types and likelihood stay
 
     def predict(self, X, eval_MSE=False, batch_size=None):
         """gpr.py:392-483.  `batch_size` is accepted and ignored: the reference's chunking

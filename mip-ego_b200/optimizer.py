@@ -91,18 +91,23 @@ def handle_box_constraint(x, lb, ub):
 
 def dynamic_penalty(X, t, equality=None, inquality=None, C=0.5, alpha=1, beta=2, epsilon=0.01,
                     minimize=True):
-    """mipego/utils.py:13-30 (user constraint functions are called point by point)."""
-    N = len(X)
-    p = np.zeros(N)
+    """Penalty of the user's constraint functions h(x) = 0 / g(x) <= 0 for a whole population, with
+    the reference's keyword names, defaults and formula (mipego/utils.py:13-30, called from
+    mies.py:189-193): (C t)^alpha * (sum |h| beyond epsilon + sum max(g, 0)^beta), sign flipped when
+    maximising.  The constraint callables are user code and take one point each."""
+    pts = list(X)
+
+    def violations(fn):
+        return np.array([np.ravel(fn(x)) for x in pts], dtype=np.float64).reshape(len(pts), -1)
+
+    total = np.zeros(len(pts))
     if equality is not None:
-        v = np.atleast_2d(list(map(equality, X))).reshape(N, -1)
-        v[np.abs(v) <= epsilon] = 0
-        p += np.sum(np.abs(v), axis=1)
+        hv = np.abs(violations(equality))
+        total += np.where(hv > epsilon, hv, 0.0).sum(axis=1)
     if inquality is not None:
-        v = np.atleast_2d(list(map(inquality, X))).reshape(N, -1)
-        v[v <= 0] = 0
-        p += np.sum(np.abs(v) ** beta, axis=1)
-    return (-1) ** (not minimize) * (C * t) ** alpha * p
+        total += (np.clip(violations(inquality), 0.0, None) ** beta).sum(axis=1)
+    scale = (C * t) ** alpha
+    return (scale if minimize else -scale) * total
 
 
 # ------------------------------------------------------------------------------------------------
@@ -480,14 +485,15 @@ def batch_argmax_restart(obj_funcs, search_space, h=None, g=None, eval_budget=10
             hd = c._handle()
             if all(hd is not x for x in handles):
                 handles.append(hd)
+    previous = [hd.counter("small_path") for hd in handles]      # the user's own setting is restored
     for hd in handles:
         hd.set_option("small_path", 0)
     try:
         return _batch_argmax_restart(objs, crits, search_space, h, g, eval_budget, n_restart, wait_iter,
                                      optimizer, logger, mode)
     finally:
-        for hd in handles:
-            hd.set_option("small_path", 1)
+        for hd, old in zip(handles, previous):
+            hd.set_option("small_path", old)
 
 
 def _batch_argmax_restart(objs, crits, search_space, h, g, eval_budget, n_restart, wait_iter, optimizer,

@@ -1,7 +1,13 @@
-"""Prior-mean (trend) objects with the reference's interface (mipego/GaussianProcess/trend.py).
+"""Prior-mean (trend) objects behind the reference's interface (mipego/GaussianProcess/trend.py).
 
-`constant_trend` (trend.py:69-88) and `linear_trend` (trend.py:90-110) are evaluated by the CUDA
-path, with given coefficients (simple kriging) or estimated ones (ordinary / universal kriging).
+The class names, `n_feature` / `n_dim` / `beta` attributes and the methods `set_beta`, `F`,
+`Jacobian`, `__call__`, `check_input` are the contract: `GaussianProcess` and user scripts construct
+`constant_trend(d, beta=...)` / `linear_trend(d, beta=...)` and read those members
+(gpr.py:255-261, 281-288, 539).  The arithmetic of the trend itself runs on the device (the basis
+matrix, F beta, the normal equations of Ft); these host objects only describe WHICH basis is meant
+and carry the coefficients.  `constant_trend`: f(x) = 1, p = 1 (trend.py:69-88); `linear_trend`:
+f(x) = [1, x_1 .. x_d], p = d + 1 (trend.py:90-110).  beta given = simple kriging, beta None =
+estimated (ordinary / universal kriging).
 """
 import numpy as np
 
@@ -11,46 +17,54 @@ class Trend(object):
 
 
 class BasisExpansionTrend(Trend):
-    def __init__(self, n_feature):
-        self.n_feature = n_feature
-        self.n_dim = None
+    """mean(x) = f(x)^T beta over a fixed basis f of `n_dim` functions of `n_feature` inputs."""
+
+    _basis = None      # "constant" | "linear": what the device code is told to build
+
+    def __init__(self, n_feature, n_dim=None, beta=None):
+        self.n_feature = int(n_feature)
+        self.n_dim = n_dim
         self.beta = None
+        if n_dim is not None:
+            self.set_beta(beta)
 
     def set_beta(self, beta):
-        # trend.py:27-34
-        if beta is not None:
-            if not hasattr(beta, "__iter__"):
-                beta = np.array([beta] * self.n_dim)
-            beta = np.atleast_2d(beta).reshape(-1, 1)
-            if len(beta) != self.n_dim:
-                raise Exception("Shapes of beta and F do not match.")
-        self.beta = beta
+        """Coefficients as an (n_dim, 1) column; a scalar stands for the same value on every basis
+        function; None means "to be estimated" (same conventions as trend.py:27-34)."""
+        if beta is None:
+            self.beta = None
+            return
+        col = np.asarray(beta, dtype=np.float64)
+        col = np.full(self.n_dim, float(col)) if col.ndim == 0 else col.ravel()
+        if col.size != self.n_dim:
+            raise Exception("Shapes of beta and F do not match.")
+        self.beta = col.reshape(self.n_dim, 1)
+
+    def check_input(self, X):
+        """(m, n_feature) view of X; a (n_feature, m) array is transposed, as the reference does."""
+        X = np.asarray(X)
+        X = X.reshape(1, -1) if X.ndim < 2 else X
+        for cand in (X, X.T):
+            if cand.shape[1] == self.n_feature:
+                return cand
+        raise Exception("x does not have the right size!")
 
     def __call__(self, X):
         if self.beta is None:
             raise Exception("beta is not set!")
-        return self.F(X).dot(self.beta)
-
-    def check_input(self, X):
-        X = np.atleast_2d(X)
-        if X.shape[1] != self.n_feature:
-            X = X.T
-        if X.shape[1] != self.n_feature:
-            raise Exception("x does not have the right size!")
-        return X
+        return self.F(X) @ self.beta
 
 
 class constant_trend(BasisExpansionTrend):
     """Zero-order polynomial trend f(x) = 1 (trend.py:69-88)."""
 
+    _basis = "constant"
+
     def __init__(self, n_feature, beta=None):
-        super(constant_trend, self).__init__(n_feature)
-        self.n_dim = 1
-        self.set_beta(beta)
+        super().__init__(n_feature, n_dim=1, beta=beta)
 
     def F(self, X):
-        X = self.check_input(X)
-        return np.ones((X.shape[0], 1))
+        return np.ones((len(self.check_input(X)), 1))
 
     def Jacobian(self, x):
         self.check_input(x)
@@ -58,17 +72,22 @@ class constant_trend(BasisExpansionTrend):
 
 
 class linear_trend(BasisExpansionTrend):
-    """First-order polynomial trend f(x) = [1, x_1..x_d], p = d + 1 (trend.py:90-110)."""
+    """First-order polynomial trend f(x) = [1, x_1 .. x_d], p = d + 1 (trend.py:90-110)."""
+
+    _basis = "linear"
 
     def __init__(self, n_feature, beta=None):
-        super(linear_trend, self).__init__(n_feature)
-        self.n_dim = n_feature + 1
-        self.set_beta(beta)
+        super().__init__(n_feature, n_dim=int(n_feature) + 1, beta=beta)
 
     def F(self, X):
         X = self.check_input(X)
-        return np.c_[np.ones(X.shape[0]), X]
+        out = np.empty((X.shape[0], self.n_dim))
+        out[:, 0] = 1.0
+        out[:, 1:] = X
+        return out
 
     def Jacobian(self, x):
-        x = self.check_input(x)
-        return np.r_[np.zeros((1, self.n_feature)), np.eye(self.n_feature)]
+        self.check_input(x)
+        J = np.zeros((self.n_dim, self.n_feature))
+        J[1:] = np.eye(self.n_feature)
+        return J

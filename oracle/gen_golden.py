@@ -84,7 +84,7 @@ def per_point(fn, Xs, d):
 
 
 def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12,
-                   likelihood="concentrated", noise_estim=False, trend="constant"):
+                   likelihood="concentrated", noise_estim=False, trend="constant", isotropic=False):
     """Model state at fixed hyper-parameters + all posterior / acquisition outputs."""
     from mipego import InfillCriteria as IC
     X, y = make_data(seed, n, d)
@@ -92,6 +92,9 @@ def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12,
         y = y + 0.3 * X[:, 1] - 0.2 * X[:, 0]
     rng = np.random.default_rng(seed + 1000)
     theta = (theta_scale / d) * rng.uniform(0.5, 1.5, d) * (4.0 if kind == "matern" else 1.0)
+    if isotropic:               # ONE theta for all features (kernel.py:312-317)
+        theta = theta[:1]
+    nth = theta.size
     noisy = bool(nugget)
     if likelihood == "restricted":          # [theta, sigma2 (, noise_var)]  gpr.py:712-719
         par = np.r_[theta, 0.8, 0.01] if noise_estim else np.r_[theta, 0.8]
@@ -99,8 +102,8 @@ def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12,
         par = np.r_[theta, 0.95]
     else:
         par = np.r_[theta, 0.8] if noisy else theta
-    gp = ref_model(kind, d, beta, nugget, theta0=theta, thetaL=1e-5 * np.ones(d),
-                   thetaU=100 * np.ones(d), likelihood=likelihood, noise_estim=noise_estim,
+    gp = ref_model(kind, d, beta, nugget, theta0=theta, thetaL=1e-5 * np.ones(nth),
+                   thetaU=100 * np.ones(nth), likelihood=likelihood, noise_estim=noise_estim,
                    trend=trend)
     llf, grad, llf2 = ref_set_par(gp, X, y, par)
     Xs = rng.uniform(-5, 5, (m, d))
@@ -146,13 +149,14 @@ def case_fixed_par(name, seed, n, d, kind, beta, nugget, m=24, theta_scale=0.12,
     print("wrote", name, "llf=%.6f" % llf)
 
 
-def case_fit(name, seed, n, d, kind, beta, nugget, random_start=1):
+def case_fit(name, seed, n, d, kind, beta, nugget, random_start=1, isotropic=False):
     """A full reference fit (MLE by L-BFGS-B from theta0; gpr.py:964-1101)."""
     X, y = make_data(seed, n, d)
     lb, ub = -5.0, 5.0
-    thetaL = 1e-5 * (ub - lb) * np.ones(d)
-    thetaU = 10 * (ub - lb) * np.ones(d)
-    theta0 = np.full(d, 0.05)
+    nth = 1 if isotropic else d
+    thetaL = 1e-5 * (ub - lb) * np.ones(nth)
+    thetaU = 10 * (ub - lb) * np.ones(nth)
+    theta0 = np.full(nth, 0.05)
     np.random.seed(seed)
     gp = ref_model(kind, d, beta, nugget, theta0=theta0, thetaL=thetaL, thetaU=thetaU,
                    random_start=random_start, random_state=seed)
@@ -267,6 +271,28 @@ def zero_theta():
     print("zero_theta", {k: float(v) for k, v in out.items() if k.endswith("_llf")})
 
 
+def isotropic_cases():
+    """ONE theta shared by all features (kernel.py:312-317, 'theta.size == 1').  Note what the
+    reference's likelihood gradient does then (gpr.py:907-944): it indexes its (n, n, d (+1))
+    derivative tensor with range(n_par), so entry 0 is the derivative w.r.t. the FIRST feature's
+    theta only and, in noisy mode, the sigma2 entry receives the second feature's -- frozen here as
+    the reference computes it."""
+    case_fixed_par("iso_se_ok_noiseless", seed=301, n=64, d=3, kind="squared_exponential", beta=None,
+                   nugget=0, theta_scale=0.5, isotropic=True)
+    case_fixed_par("iso_se_ok_noisy", seed=302, n=72, d=4, kind="squared_exponential", beta=None,
+                   nugget=1e-6, isotropic=True)
+    case_fixed_par("iso_m32_sk_noisy", seed=303, n=64, d=3, kind="matern", beta=0.3, nugget=1e-6,
+                   isotropic=True)
+    case_fixed_par("iso_absexp_ok_noisy", seed=304, n=48, d=3, kind="absolute_exponential", beta=None,
+                   nugget=1e-6, isotropic=True)
+    case_fixed_par("iso_se_ok_conc_noiseestim", seed=305, n=64, d=3, kind="squared_exponential", beta=None,
+                   nugget=0, noise_estim=True, isotropic=True)
+    case_fixed_par("iso_se_ok_reml_noisy", seed=306, n=64, d=3, kind="squared_exponential", beta=None,
+                   nugget=1e-6, likelihood="restricted", isotropic=True)
+    case_fit("ifit_se_ok_noisy", seed=31, n=40, d=3, kind="squared_exponential", beta=None, nugget=1e-6,
+             isotropic=True)
+
+
 def multi_restart_fits():
     """Reference fits with several L-BFGS-B restarts (gpr.py:1030-1064: sequential restarts, shared
     budget, wait_iter early stop).  Modes whose analytic gradient is exact (noisy; given trend --
@@ -293,6 +319,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "zero_theta":
         zero_theta()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "isotropic":
+        isotropic_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "multi_restart":
         multi_restart_fits()
         return
@@ -300,6 +329,7 @@ def main():
     linear_trends()
     zero_theta()
     multi_restart_fits()
+    isotropic_cases()
     k = 0
     for kind in ("squared_exponential", "matern"):
         for beta in (None, 0.3):

@@ -45,8 +45,17 @@ def corr(kind, theta, D):
     theta = np.asarray(theta, dtype=np.float64).ravel()
     D = np.asarray(D, dtype=np.float64)
     nf = D.shape[1]
-    if theta.size == 1:
-        theta = np.repeat(theta, nf)
+    if theta.size == 1 and nf > 1:
+        # isotropic: the reference multiplies the SUM over features by theta[0]
+        # (kernel.py:312-313, 173-174, 267-268), which rounds differently from sum(theta_i d_i^2)
+        if kind == "squared_exponential":
+            return np.exp(-theta[0] * np.sum(D ** 2, axis=1))
+        if kind == "matern":
+            K = np.sqrt(theta[0] * np.sum(D ** 2, axis=1)) * SQRT3
+            return (1.0 + K) * np.exp(-K)
+        if kind == "absolute_exponential":
+            return np.exp(-theta[0] * np.sum(np.abs(D), axis=1))
+        raise ValueError(kind)
     if theta.size != nf:
         raise ValueError("Length of theta must be 1 or %s" % nf)
     if kind == "squared_exponential":
@@ -355,7 +364,12 @@ def fit_state(X, y, par, kind="squared_exponential", estimate_trend=True, beta=0
     if not env:
         raise linalg.LinAlgError("correlation matrix is not positive definite")
     d = X.shape[1]
-    theta = par[:d]
+    # theta = everything before the variance parameters of the mode (gpr.py:712-719, 814, 837, 855);
+    # a single theta entry is the isotropic form (kernel.py:312-317)
+    extras = {"noiseless": 0, "noisy": 1, "noise_estim": 1}[mode]
+    if likelihood == "restricted":
+        extras = {"noiseless": 1, "noisy": 1, "noise_estim": 2}[mode]
+    theta = par[:par.size - extras]
     st = dict(X=X, y=y, kind=kind, theta=np.array(theta, dtype=np.float64),
               estimate_trend=bool(estimate_trend), mode=mode,
               likelihood=likelihood, sigma2=float(env["sigma2"]), noise_var=float(env["noise_var"]),

@@ -10,6 +10,7 @@ FIXED = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, 
 VARS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "var_*.npz")))
 LINS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "lin_*.npz")))
 FITS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "fit_*.npz")))
+ISOS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "iso_*.npz")))
 MFITS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "mfit_*.npz")))
 
 

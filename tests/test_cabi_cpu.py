@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_cabi.SIGNATURES) == syms
-    assert lib.mgp_abi_version() == 3
+    assert lib.mgp_abi_version() == _cabi.ABI_VERSION == 4
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -91,3 +91,26 @@ def test_lockstep_driver_matches_sequential_scipy():
     assert max(calls) == 7 and len(calls) < ne
     p2, f2, ne2, _ = multistart_lbfgsb(batch_fn, starts, bounds, 500, 100, mode="sequential")
     assert f2 == f
+
+
+def test_integration_doc_stub_signatures():
+    """The ctypes stub printed in INTEGRATION.md binds the real library with the same prototypes as
+    mipego_b200/_cabi.py (the GPU suite also runs its demo against the oracle)."""
+    import ctypes
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"<!-- ctypes-stub:begin -->\s*```python\n(.*?)```\s*<!-- ctypes-stub:end -->", txt, flags=re.S)
+    assert m
+    ns = {}
+    exec(compile(m.group(1), "INTEGRATION.md", "exec"), ns)
+    from mipego_b200 import _cabi
+    lib = ns["bind"](_cabi.LIB_PATH)
+    for name, (res, args) in ns["PROTOTYPES"].items():
+        want_res, want_args = _cabi.SIGNATURES[name]
+        assert res is want_res, name
+        assert len(args) == len(want_args), name
+        for a, b in zip(args, want_args):
+            assert ctypes.sizeof(a) == ctypes.sizeof(b), name
+            # pointer vs. scalar must agree (a double passed where a pointer is expected was the old doc bug)
+            assert issubclass(a, ctypes._Pointer) == issubclass(b, ctypes._Pointer) or \
+                {a, b} <= {ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)} or a is b, (name, a, b)
+        assert getattr(lib, name).argtypes == args

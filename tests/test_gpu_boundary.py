@@ -1,0 +1,319 @@
+"""Boundary behaviour of the drop-in on the GPU: isotropic theta against
+reference fixtures, stream ordering between the device-pointer and host-pointer entry points,
+the env harvest without side effects, pickling in every estimation mode, the NCCL entry points on
+a one-rank communicator, the documented limits (d <= 64, n_sets <= 16, k <= 64), and the ctypes
+stub of INTEGRATION.md run against the real library."""
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from golden_util import ISOS, load, mode_of, beta_of, likelihood_of
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _mods():
+    import mipego_b200 as mb
+    from oracle import gp_oracle as O
+    return mb, O
+
+
+def _data(n, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-5, 5, (n, d))
+    y = (X ** 2).sum(1) + 3 * np.sin(X[:, 0])
+    return X, (y - y.mean()) / y.std(), rng
+
+
+# ---- isotropic theta (kernel.py:312-317) -----------------------------------------------------------
+@pytest.mark.parametrize("name", ISOS)
+def test_isotropic_theta_golden(name):
+    """ONE theta for all features: likelihood, the reference's (quirky) gradient, env, fitted state,
+    posterior, gradients and EI against fixtures produced by the unmodified reference."""
+    mb, O = _mods()
+    g = load(name)
+    d = g["X"].shape[1]
+    lik, mode = likelihood_of(g), mode_of(g)
+    beta = None if g["estimate_trend"] else float(g["beta_in"])
+    nug = float(g["nugget"])
+    assert g["theta"].size == 1
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=beta), corr=g["kind"], theta0=g["theta"],
+                            thetaL=[1e-5], thetaU=[100.0], nugget=nug if nug > 0 else 0,
+                            noise_estim=(mode == "noise_estim"), likelihood=lik)
+    gp._check_data(g["X"], g["y"])
+    par = g["par"]
+    assert par.size == 1 + (1 if (lik == "restricted" or mode != "noiseless") else 0)
+    P = np.vstack([par, par * np.r_[1.7, np.ones(par.size - 1)], par * np.r_[0.6, np.ones(par.size - 1)]])
+    llf, grad, status = gp.log_likelihood_batch(P, eval_grad=True)
+    assert status[0] == 0 and abs(llf[0] - float(g["llf"])) <= 1e-9 * abs(float(g["llf"]))
+    gs = np.abs(g["llf_grad"]).max()
+    assert grad.shape == (3, par.size)
+    assert np.max(np.abs(grad[0] - g["llf_grad"])) <= (1e-7 if nug > 0 else 1e-6) * gs, (grad[0], g["llf_grad"])
+    fn = O.log_likelihood_restricted if lik == "restricted" else O.log_likelihood_concentrated
+    for b in (1, 2):
+        rl, rg = fn(g["X"], g["y"], P[b], g["kind"], g["estimate_trend"], beta_of(g), mode, nug, eval_grad=True)
+        if np.isfinite(rl):
+            assert abs(llf[b] - rl) <= 1e-9 * abs(rl)
+            assert np.max(np.abs(grad[b] - rg.ravel())) <= (1e-7 if nug > 0 else 1e-6) * np.abs(rg).max()
+    gp.fit_fixed(g["X"], g["y"], par)
+    assert gp.theta_.size == 1 and gp.par["theta"].size == 1
+    assert np.allclose(gp.C, g["L"], rtol=0, atol=1e-11)
+    t = 1e-9 if nug > 0 else 1e-6
+    mean, mse = gp.predict(g["Xs"], eval_MSE=True)
+    s2 = float(g["sigma2"])
+    assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-3)) < t
+    assert np.max(np.abs(mse - g["mse"]) / (np.abs(g["mse"]) + 1e-6 * s2)) < 100 * t
+    mdx, sdx = gp.gradient_batch(g["Xs"])
+    assert np.max(np.abs(mdx - g["mean_dx"])) < 10 * t * np.abs(g["mean_dx"]).max()
+    assert np.max(np.abs(sdx - g["mse_dx"])) < 100 * t * np.abs(g["mse_dx"]).max()
+    ei = mb.EI(model=gp, minimize=True, plugin=float(g["plugin_min"]))
+    v = ei(g["Xs"])
+    easy = g["mse"] > 1e-4 * s2
+    rv = g["EI_min"]
+    assert np.max(np.abs(v[easy] - rv[easy]) / (np.abs(rv[easy]) + 1e-6 * np.abs(rv).max())) < 100 * t
+    # pickle round trip and a refit at the same hyper-parameters keep the one-entry layout
+    g2 = pickle.loads(pickle.dumps(gp))
+    m2 = g2.predict(g["Xs"])
+    assert np.max(np.abs(m2 - mean)) <= 1e-9 * np.abs(mean).max()
+    assert g2.theta_.size == 1
+    g2.update(g["X"], g["y"], reoptimize=False)
+    assert np.max(np.abs(g2.predict(g["Xs"]) - mean)) <= 1e-9 * np.abs(mean).max()
+
+
+def test_isotropic_fit_against_reference_fit():
+    """fit() with one shared theta: same optimiser, same (reference-quirk) gradient, same end point."""
+    mb, O = _mods()
+    g = load("ifit_se_ok_noisy")
+    d = g["X"].shape[1]
+    np.random.seed(int(g["seed"]))
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr=g["kind"], theta0=g["theta0"],
+                            thetaL=g["thetaL"], thetaU=g["thetaU"], nugget=float(g["nugget"]),
+                            random_start=1, restart_mode="sequential")
+    gp.fit(g["X"], g["y"])
+    llf = float(np.ravel(gp.log_likelihood_)[0])
+    assert abs(llf - float(g["llf"])) <= 1e-8 * abs(float(g["llf"]))
+    assert np.allclose(gp.theta_, g["theta_"], rtol=1e-6) and gp.eval_count == int(g["eval_count"])
+    mean = gp.predict(g["Xs"])
+    assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-2)) < 1e-7
+    with pytest.raises(ValueError):
+        mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), theta0=[0.1, 0.1], thetaL=[1e-3] * 2,
+                           thetaU=[1.0] * 2).fit(g["X"], g["y"])          # neither 1 nor d entries
+
+
+# ---- the env harvest has no side effects (gpr.py:876-887) -------------------------------------------
+def test_env_harvest_leaves_the_fitted_model_alone():
+    mb, O = _mods()
+    X, y, rng = _data(300, 5, 8)
+    theta = (0.3 / 5) * rng.uniform(0.5, 1.5, 5)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(5, beta=None), corr="matern", theta0=theta,
+                            thetaL=[1e-5] * 5, thetaU=[100.0] * 5, nugget=1e-6)
+    gp.fit_fixed(X, y, np.r_[theta, 0.9])
+    Xs = rng.uniform(-5, 5, (1000, 5))
+    ei = mb.EI(model=gp, minimize=True)
+    mean0, mse0 = gp.predict(Xs, eval_MSE=True)
+    v0 = ei(Xs)
+    L0, gamma0, s0, b0, par0 = gp.C.copy(), gp.gamma.copy(), gp.sigma2, gp.mean.beta.copy(), dict(gp.par)
+    other = np.r_[3.0 * theta, 0.4]
+    env = {}
+    l_other = gp.log_likelihood_concentrated(other, env=env)
+    st = O.fit_state(X, y, other, "matern", True, 0.0, "noisy", 1e-6)
+    assert abs(l_other - st["llf"]) <= 1e-9 * abs(st["llf"])
+    assert np.allclose(env["C"], st["L"], rtol=0, atol=1e-11) and float(env["sigma2"]) == 0.4
+    assert np.max(np.abs(env["rho"] - st["rho"])) <= 1e-9 * np.abs(st["rho"]).max()
+    # nothing about the fitted model moved: attributes, device state, results
+    assert np.array_equal(gp.C, L0) and np.array_equal(gp.gamma, gamma0) and gp.sigma2 == s0
+    assert np.array_equal(gp.mean.beta, b0) and all(np.array_equal(gp.par[k], par0[k]) for k in par0)
+    mean1, mse1 = gp.predict(Xs, eval_MSE=True)
+    assert np.array_equal(mean0, mean1) and np.array_equal(mse0, mse1) and np.array_equal(ei(Xs), v0)
+
+
+# ---- stream ordering between *_dev and host-pointer calls -------------------------------------------
+def test_device_and_host_entry_points_interleave_without_explicit_sync():
+    """mgp_acq_dev / mgp_nll_batch_dev enqueue on the caller's stream and share the handle's scratch
+    with the host-pointer calls (internal stream): the library orders them itself (event recorded
+    after every call, waited on by the next user), so no cudaDeviceSynchronize is needed between."""
+    import torch
+    mb, O = _mods()
+    X, y, rng = _data(1100, 8, 9)
+    theta = (0.2 / 8) * rng.uniform(0.5, 1.5, 8)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(8, beta=None), corr="squared_exponential", theta0=theta,
+                            thetaL=[1e-5] * 8, thetaU=[100.0] * 8, nugget=1e-6)
+    gp.fit_fixed(X, y, np.r_[theta, 0.9])
+    ei = mb.EI(model=gp, minimize=True)
+    Xa = rng.uniform(-5, 5, (200_000, 8))
+    Xb = rng.uniform(-5, 5, (30_000, 8))
+    va = ei.evaluate(Xa)[0]
+    vb = ei.evaluate(Xb)[0]
+    P = np.c_[theta * rng.uniform(0.5, 2.0, (4, 8)), np.full(4, 0.8)]
+    l_ref, g_ref, _ = gp.log_likelihood_batch(P)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    Xa_d, P_d = torch.from_numpy(Xa).cuda(), torch.from_numpy(P).cuda()
+    torch.cuda.synchronize()
+    for rep in range(5):
+        with torch.cuda.stream(side):
+            out_a = ei.evaluate_device(Xa_d)                   # long, on a user stream, not synchronised
+        vb2 = ei.evaluate(Xb)[0]                               # host API right behind it: same scratch
+        with torch.cuda.stream(side):
+            lo = gp.log_likelihood_batch_device(P_d)
+        gp.fit_fixed(X, y, np.r_[theta, 0.9])                  # rewrites the model behind a pending dev call
+        with torch.cuda.stream(side):
+            out_a2 = ei.evaluate_device(Xa_d)
+        mean_b = gp.predict(Xb)                                # and again host behind device
+        side.synchronize()
+        assert np.array_equal(out_a[0].cpu().numpy(), va) and np.array_equal(vb2, vb)
+        assert np.array_equal(out_a2[0].cpu().numpy(), va)
+        assert np.array_equal(lo[0].cpu().numpy(), l_ref) and np.array_equal(lo[1].cpu().numpy(), g_ref)
+        assert np.all(np.isfinite(mean_b))
+
+
+# ---- pickling keeps the full hyper-parameter vector ---------------------------------------------------
+@pytest.mark.parametrize("lik,noise_estim,nugget", [("concentrated", False, 1e-4), ("restricted", False, 0),
+                                                    ("restricted", True, 0), ("concentrated", True, 0)])
+def test_unpickle_then_update_without_reoptimisation(lik, noise_estim, nugget):
+    mb, O = _mods()
+    X, y, rng = _data(120, 3, 10)
+    y = y + 0.05 * rng.standard_normal(y.size)
+    np.random.seed(5)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(3, beta=None), corr="squared_exponential", theta0=[0.05] * 3,
+                            thetaL=[1e-4] * 3, thetaU=[10.0] * 3, nugget=nugget, noise_estim=noise_estim,
+                            likelihood=lik, random_start=2)
+    gp.fit(X[:100], y[:100])
+    par = np.concatenate([np.ravel(v) for v in gp.par.values()])
+    g2 = pickle.loads(pickle.dumps(gp))
+    assert type(g2.sigma2) is type(gp.sigma2) and np.array_equal(np.ravel(g2.sigma2), np.ravel(gp.sigma2))
+    assert all(np.array_equal(g2.par[k], gp.par[k]) for k in gp.par)
+    Xs = rng.uniform(-5, 5, (64, 3))
+    assert np.max(np.abs(g2.predict(Xs) - gp.predict(Xs))) <= 1e-9
+    g2.update(X, y, reoptimize=False)                     # 20 more rows at the pickled hyper-parameters
+    par2 = np.concatenate([np.ravel(v) for v in g2.par.values()])
+    assert np.array_equal(par2, par)
+    fresh = mb.GaussianProcess(mean=mb.constant_trend(3, beta=None), corr="squared_exponential", theta0=[0.05] * 3,
+                               thetaL=[1e-4] * 3, thetaU=[10.0] * 3, nugget=nugget, noise_estim=noise_estim,
+                               likelihood=lik).fit_fixed(X, y, par)
+    m2, s2 = g2.predict(Xs, eval_MSE=True)
+    m3, s3 = fresh.predict(Xs, eval_MSE=True)
+    assert np.max(np.abs(m2 - m3)) <= 1e-9 * np.abs(m3).max() and np.max(np.abs(s2 - s3)) <= 1e-7 * np.abs(s3).max() + 1e-12
+
+
+# ---- NCCL entry points on a one-rank communicator ---------------------------------------------------
+def test_nccl_entry_points_single_rank():
+    """mgp_comm_* / mgp_bcast_model / mgp_allgather_topk with world = 1: NCCL is found and bound at
+    run time, the pack / all-gather / merge path reproduces the single-GPU top-k order."""
+    import ctypes
+    import torch
+    mb, O = _mods()
+    from mipego_b200 import _cabi
+    X, y, rng = _data(200, 4, 11)
+    theta = (0.3 / 4) * rng.uniform(0.5, 1.5, 4)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(4, beta=None), corr="squared_exponential", theta0=theta,
+                            thetaL=[1e-5] * 4, thetaU=[100.0] * 4, nugget=1e-6)
+    gp.fit_fixed(X, y, np.r_[theta, 0.9])
+    h = gp._handle()
+    buf = ctypes.create_string_buffer(128)
+    assert h.lib.mgp_comm_unique_id(buf) == 0, h.lib.mgp_comm_info(h.h)
+    h.check(h.lib.mgp_comm_init(h.h, 0, 1, buf.raw))
+    info = h.lib.mgp_comm_info(h.h).decode()
+    assert "world=1" in info and "version=" in info
+    print("NCCL:", info)
+    Xs = rng.uniform(-5, 5, (5000, 4))
+    before = gp.predict(Xs)
+    h.check(h.lib.mgp_bcast_model(h.h, 0))                 # root == only rank: the model is unchanged
+    assert np.array_equal(gp.predict(Xs), before) and h.counter("bcast_bytes") > 200 * 200 * 8
+    ts = np.array([1.0, 2.5, 0.3])
+    crit = mb.MGFI(model=gp, minimize=True, t=1.0)
+    tv, ti = crit.topk(Xs, k=7, params=ts)
+    ti_holes = ti.copy()
+    ti_holes[1, 5:] = -1                                   # empty slots of a short shard
+    ov, oi = np.empty_like(tv), np.empty_like(ti)
+    h.check(h.lib.mgp_allgather_topk(h.h, 3, 7, _cabi.dptr(tv), ti_holes.ctypes.data_as(_cabi.c_lp), 1000,
+                                     _cabi.dptr(ov), oi.ctypes.data_as(_cabi.c_lp)))
+    assert np.array_equal(oi[0], ti[0] + 1000) and np.array_equal(ov[0], tv[0])
+    assert np.array_equal(oi[1, :5], ti[1, :5] + 1000) and np.all(oi[1, 5:] == -1) and np.all(np.isinf(ov[1, 5:]))
+    # device-resident variant on torch's stream
+    tvd, tid = crit.topk_device(torch.from_numpy(Xs).cuda(), k=7, params=ts)
+    ovd, oid = torch.empty_like(tvd), torch.empty_like(tid)
+    st = torch.cuda.current_stream().cuda_stream
+    h.check(h.lib.mgp_allgather_topk_dev(h.h, 3, 7, tvd.data_ptr(), tid.data_ptr(), 0, ovd.data_ptr(),
+                                         oid.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert np.array_equal(oid.cpu().numpy(), ti) and np.array_equal(ovd.cpu().numpy(), tv)
+    h.check(h.lib.mgp_comm_destroy(h.h))
+    assert h.lib.mgp_bcast_model(h.h, 0) == _cabi.MGP_ESTATE
+
+
+# ---- documented limits ----------------------------------------------------------------------------------
+def test_limits_at_the_edge():
+    """d <= 64 (MGP_MAX_D), n_sets <= 16, k <= 64: the largest admitted value works and agrees with
+    the oracle, one more is rejected with MGP_EINVAL (no silent truncation)."""
+    mb, O = _mods()
+    from mipego_b200 import _cabi
+    n, d = 160, 64
+    X, y, rng = _data(n, d, 12)
+    theta = (0.12 / d) * rng.uniform(0.5, 1.5, d)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential", theta0=theta,
+                            thetaL=[1e-6] * d, thetaU=[100.0] * d, nugget=1e-6)
+    par = np.r_[theta, 0.9]
+    gp.fit_fixed(X, y, par)
+    st = O.fit_state(X, y, par, "squared_exponential", True, 0.0, "noisy", 1e-6)
+    Xs = rng.uniform(-5, 5, (300, d))
+    mean, mse = gp.predict(Xs, eval_MSE=True)
+    rm, rs = O.predict(st, Xs)
+    assert np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3)) < 1e-9
+    assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-7
+    llf, grad, status = gp.log_likelihood_batch(par.reshape(1, -1))
+    rl, rg = O.log_likelihood_concentrated(X, y, par, "squared_exponential", True, 0.0, "noisy", 1e-6, eval_grad=True)
+    assert abs(llf[0] - rl) <= 1e-9 * abs(rl) and np.max(np.abs(grad[0] - rg.ravel())) <= 1e-7 * np.abs(rg).max()
+    ei = mb.EI(model=gp, minimize=True)
+    v, dx = ei(Xs[:40], return_dx=True)                    # K5 with DP = 64
+    rv, rdx = O.acquisition(st, Xs[:40], "EI", None, None, True, return_dx=True)
+    assert np.max(np.abs(v - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())) < 1e-7
+    assert np.max(np.abs(dx - rdx)) < 1e-7 * np.abs(rdx).max()
+    ts = np.linspace(0.2, 3.0, 16)                         # n_sets = 16
+    crit = mb.MGFI(model=gp, minimize=True, t=1.0)
+    V = crit.evaluate(Xs, params=ts)
+    for s in (0, 15):
+        rv = O.acquisition(st, Xs, "MGFI", float(ts[s]), None, True)
+        assert np.max(np.abs(V[s] - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())) < 1e-7
+    tv, ti = crit.topk(Xs, k=64, params=ts)                # k = 64
+    for s in (0, 7, 15):
+        order = np.lexsort((np.arange(len(Xs)), -V[s]))[:64]
+        assert np.array_equal(ti[s], order) and np.array_equal(tv[s], V[s][order])
+    with pytest.raises(_cabi.MgpError) as e:
+        crit.evaluate(Xs, params=np.linspace(0.2, 3.0, 17))
+    assert e.value.code == _cabi.MGP_EINVAL
+    with pytest.raises(_cabi.MgpError) as e:
+        crit.topk(Xs, k=65)
+    assert e.value.code == _cabi.MGP_EINVAL
+    big = mb.GaussianProcess(mean=mb.constant_trend(65, beta=None), corr="squared_exponential", theta0=[0.01] * 65,
+                             thetaL=[1e-6] * 65, thetaU=[100.0] * 65)
+    with pytest.raises(_cabi.MgpError) as e:
+        big.fit_fixed(rng.uniform(-5, 5, (100, 65)), rng.uniform(size=100), np.full(65, 0.01))
+    assert e.value.code == _cabi.MGP_EINVAL and "unsupported" in str(e.value)
+
+
+# ---- the from-scratch ctypes stub, run against the real library ------------------------
+def _doc_stub():
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"<!-- ctypes-stub:begin -->\s*```python\n(.*?)```\s*<!-- ctypes-stub:end -->", txt, flags=re.S)
+    assert m, "INTEGRATION.md lost its ctypes stub markers"
+    return m.group(1)
+
+
+def test_integration_doc_stub_runs():
+    mb, O = _mods()
+    ns = {}
+    exec(compile(_doc_stub(), "INTEGRATION.md", "exec"), ns)
+    X, y, rng = _data(90, 3, 13)
+    Xs = rng.uniform(-5, 5, (500, 3))
+    theta = np.array([0.05, 0.08, 0.03])
+    lib = ns["bind"](os.path.join(ROOT, "mip-ego_b200", "libmgp_b200.so"))
+    llf, ei = ns["demo"](lib, X, y, Xs, theta, sigma2=0.9, nugget=1e-6)
+    st = O.fit_state(X, y, np.r_[theta, 0.9], "squared_exponential", True, 0.0, "noisy", 1e-6)
+    rv = O.acquisition(st, Xs, "EI", None, float(y.min()), True)
+    assert abs(llf - st["llf"]) <= 1e-9 * abs(st["llf"])
+    assert np.max(np.abs(ei - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())) < 1e-7

@@ -142,9 +142,20 @@ def test_likelihood_golden(name):
         assert status[b] == 0
         assert abs(llf[b] - ref[0]) <= 1e-9 * abs(ref[0])
         assert np.max(np.abs(grad[b] - ref[1].ravel())) <= tol(g, 1e-7, 1e-6) * np.abs(ref[1]).max()
-    # the fitted state harvested on the device
-    llf1 = gp.log_likelihood_concentrated(par, env={})
+    # the env harvested by a likelihood call (gpr.py:876-887): no side effect on the model ...
+    env = {}
+    llf1 = gp.log_likelihood_concentrated(par, env=env)
     assert abs(llf1 - float(g["llf_env"])) <= 1e-9 * abs(float(g["llf_env"]))
+    assert not gp.is_fitted and not gp._fitted_on_device()
+    assert np.allclose(env["C"], g["L"], rtol=0, atol=1e-11)
+    assert np.max(np.abs(env["rho"] - g["rho"])) <= tol(g, 1e-9, 1e-7) * np.abs(g["rho"]).max()
+    assert np.max(np.abs(env["Yt"] - g["Yt"])) <= tol(g, 1e-9, 1e-7) * np.abs(g["Yt"]).max()
+    assert abs(float(np.ravel(env["sigma2"])[0]) - float(g["sigma2"])) <= 1e-10 * float(g["sigma2"])
+    if g["estimate_trend"]:
+        assert np.max(np.abs(env["Ft"] - g["Ft"])) <= 1e-9 * np.abs(g["Ft"]).max()
+        assert np.max(np.abs(env["Q"] - g["Q"])) <= 1e-9 * np.abs(g["Q"]).max()
+    # ... the fitted state is what fit / fit_fixed build (mgp_finalize_fit)
+    gp.fit_fixed(g["X"], g["y"], par)
     assert np.allclose(gp.C, g["L"], rtol=0, atol=1e-11)
     assert abs(float(np.ravel(gp.sigma2)[0]) - float(g["sigma2"])) <= 1e-10 * float(g["sigma2"])
     assert abs(float(np.ravel(gp.mean.beta)[0]) - float(g["beta"])) <= 1e-8 * max(1.0, abs(float(g["beta"])))
@@ -204,8 +215,9 @@ def test_variant_modes_golden(name):
     assert abs(float(np.ravel(env["sigma2"])[0]) - float(g["sigma2"])) <= 1e-10 * float(g["sigma2"])
     assert abs(float(np.ravel(env["noise_var"])[0]) - float(g["noise_var"])) <= \
         1e-10 * max(float(g["noise_var"]), 1e-300)
+    assert not gp.is_fitted                      # the env harvest does not adopt the state
+    gp.fit_fixed(g["X"], g["y"], par)
     assert np.max(np.abs(gp.gamma - g["gamma"])) <= tol(g, 1e-8, 1e-6) * np.abs(g["gamma"]).max()
-    gp.theta_, gp.is_fitted = par[:d], True
     mean, mse = gp.predict(g["Xs"], eval_MSE=True)
     assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-3)) < tol(g, 1e-9, 1e-6)
     s2 = float(g["sigma2"])
@@ -697,6 +709,10 @@ def test_linear_trend_golden(name):
     single(par, env=env)
     assert np.allclose(env["C"], g["L"], rtol=0, atol=1e-11)
     assert abs(float(np.ravel(env["sigma2"])[0]) - float(g["sigma2"])) <= 1e-9 * float(g["sigma2"])
+    if est:
+        assert np.max(np.abs(env["Ft"] - g["Ft"])) <= 1e-9 * np.abs(g["Ft"]).max()
+        assert np.max(np.abs(env["G"] - g["G"])) <= 1e-8 * np.abs(g["G"]).max()
+    gp.fit_fixed(g["X"], g["y"], par)
     assert np.max(np.abs(np.ravel(gp.mean.beta) - np.ravel(g["beta"]))) <= tol(g, 1e-8, 1e-6) * max(1.0, np.abs(g["beta"]).max())
     assert np.max(np.abs(gp.gamma - g["gamma"])) <= tol(g, 1e-8, 1e-6) * np.abs(g["gamma"]).max()
     assert np.max(np.abs(gp.rho - g["rho"])) <= tol(g, 1e-8, 1e-6) * np.abs(g["rho"]).max()
@@ -704,7 +720,6 @@ def test_linear_trend_golden(name):
         assert gp.Ft.shape == g["Ft"].shape
         assert np.max(np.abs(gp.Ft - g["Ft"])) <= 1e-9 * np.abs(g["Ft"]).max()
         assert np.max(np.abs(gp.G - g["G"])) <= 1e-8 * np.abs(g["G"]).max()     # same LAPACK QR signs
-    gp.theta_, gp.is_fitted = par[:d], True
     mean, mse = gp.predict(g["Xs"], eval_MSE=True)
     assert np.max(np.abs(mean - g["mean"]) / (np.abs(g["mean"]) + 1e-3)) < tol(g, 1e-9, 1e-6)
     s2 = float(g["sigma2"])

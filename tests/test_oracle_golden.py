@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import gp_oracle as O
-from golden_util import FIXED, FITS, MFITS, VARS, LINS, load, mode_of, beta_of, likelihood_of, trend_of, relerr
+from golden_util import FIXED, FITS, MFITS, ISOS, VARS, LINS, load, mode_of, beta_of, likelihood_of, trend_of, relerr
 
 # Same formulas, possibly different summation order than the reference: tolerances are
 # rounding-level on the well-conditioned (nugget) cases and looser on nugget-0 cases where the
@@ -104,7 +104,7 @@ def test_c1_example():
     assert np.max(np.abs(dx - g["EI_dx"].reshape(dx.shape))) < 1e-9 * np.abs(g["EI_dx"]).max()
 
 
-@pytest.mark.parametrize("name", FITS + MFITS)
+@pytest.mark.parametrize("name", FITS + MFITS + ["ifit_se_ok_noisy"])
 def test_fit_state_reproduces_reference_fit(name):
     g = load(name)
     st = O.fit_state(g["X"], g["y"], g["par"], g["kind"], g["estimate_trend"], beta_of(g),
@@ -115,7 +115,7 @@ def test_fit_state_reproduces_reference_fit(name):
 
 
 # ---- estimation-mode / likelihood variants (REML, estimated noise share) ---------------------
-@pytest.mark.parametrize("name", VARS + LINS)
+@pytest.mark.parametrize("name", VARS + LINS + ISOS)
 def test_variant_likelihood_state_posterior(name):
     g = load(name)
     fn = O.log_likelihood_restricted if likelihood_of(g) == "restricted" else O.log_likelihood_concentrated
