@@ -108,6 +108,17 @@ int mgp_nll_batch(mgp_t *h, int B, const double *params, int n_par, int mode, do
 int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double noise_var,
                      double *out_llf);
 
+/* ---- incremental training: GaussianProcess.update (gpr.py:387-390, "TODO: implement incremental
+ * training") for k rows APPENDED to the training set, at the hyper-parameters of the last
+ * mgp_finalize_fit.  L, L^-1 and the packed posterior operands are extended by a rank-k border
+ * update in O(n^2 k) (three GEMMs against the kept leading block + a k x k factorisation) instead of
+ * the 2/3 n^3 rebuild; rho, sigma2, beta, gamma and the likelihood are recomputed for the new y.
+ * X_add: k x d, y_add: k.  Returns MGP_ESTATE when the incremental path does not apply (model
+ * adopted with mgp_set_state, non-constant trend, fewer than 512 kept rows or more than a quarter of
+ * them appended): the caller then rebuilds with mgp_set_train + mgp_finalize_fit.  MGP_EINVAL
+ * "duplicate rows" / MGP_ENOTPD leave the previous model intact. */
+int mgp_append_train(mgp_t *h, int k, const double *X_add, const double *y_add, double *out_llf);
+
 /* ---- the `env` harvest of a likelihood call WITHOUT adopting the state: what
  * log_likelihood_concentrated / _restricted(par, env) fill in (gpr.py:876-887, 785-794).  Runs the
  * pipeline for one parameter vector in scratch memory and copies out L (n x n row-major, upper = 0),

@@ -30,6 +30,7 @@ SIGNATURES = {
     "mgp_set_train": (_i, [_vp, _i, _i, c_dp, c_dp, _i, _i, c_dp]),
     "mgp_nll_batch": (_i, [_vp, _i, c_dp, _i, _i, _d, _i, c_dp, c_dp, c_ip]),
     "mgp_finalize_fit": (_i, [_vp, c_dp, _i, _i, _d, c_dp]),
+    "mgp_append_train": (_i, [_vp, _i, c_dp, c_dp, c_dp]),
     "mgp_nll_env": (_i, [_vp, c_dp, _i, _i, _d, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "mgp_get_state": (_i, [_vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "mgp_set_state": (_i, [_vp, c_dp, c_dp, c_dp, _d, c_dp]),

@@ -221,6 +221,7 @@ int64_t mgp_get_counter(const mgp_t *h, const char *name) {
   if (!strcmp(name, "small_path")) return h->no_small_path ? 0 : 1;
   if (!strcmp(name, "isotropic")) return h->isotropic ? 1 : 0;
   if (!strcmp(name, "n")) return h->n;
+  if (!strcmp(name, "appends")) return h->appends;
   if (!strcmp(name, "world")) return h->world;
   if (!strcmp(name, "rank")) return h->rank;
   if (!strcmp(name, "bcast_bytes")) return h->bcast_bytes;
@@ -278,6 +279,8 @@ int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int 
   }
   WsScope ws(h, h->stream);   // a *_dev call may still be reading the training data on another stream
   MGP_CUDA(h, ws.err);
+  h->hcenter = center;
+  h->hpar.clear();
   MGP_TRY(mgp_ensure(h, h->dXc, Xc.size() * 8));
   MGP_TRY(mgp_ensure(h, h->dy, yp.size() * 8));
   MGP_TRY(mgp_ensure(h, h->dcenter, center.size() * 8));
@@ -646,7 +649,155 @@ int mgp_finalize_fit(mgp_t *h, const double *par, int n_par, int mode, double no
   h->G = -sqrt(sc[NLL_FTF]);  // LAPACK's Householder QR of the positive-leading column Ft
   h->beta = sc[NLL_BETA];
   MGP_TRY(adopt_slot0(h, par, true));
+  h->hpar.assign(par, par + n_par);
+  h->par_noise_var = noise_var;
   h->fitted = true;
+  if (out_llf) *out_llf = h->llf;
+  return MGP_OK;
+}
+
+// Rank-k extension of the fitted model by k appended training rows at the CURRENT hyper-parameters
+// (the incremental training gpr.py:387-390 asks for).  With nb = the last multiple of 128 <= n, the
+// leading nb x nb blocks L11, M11 = L11^-1 stay; the T = (npad' - nb) / 128 trailing tile rows are
+// recomputed:  L21 = R21 M11^T,  S = R22 - L21 L21^T,  L22 = chol(S),  M22 = L22^-1,
+// M21 = -M22 (L21 M11)  -- three GEMMs of T*128 x nb x nb, i.e. O(n^2 k) instead of the 2/3 n^3 of a
+// rebuild -- then the O(n^2) tail of the likelihood pipeline (Yt, Ft, rho, sigma2, beta, gamma, llf)
+// and the packing of the posterior operands.
+int mgp_append_train(mgp_t *h, int k, const double *X_add, const double *y_add, double *out_llf) {
+  CHECK_H(h);
+  if (!h->fitted) return mgp_fail(h, MGP_ESTATE, "model is not fitted");
+  if (k < 1 || !X_add || !y_add) return mgp_fail(h, MGP_EINVAL, "bad rows to append");
+  if (h->hpar.empty()) return mgp_fail(h, MGP_ESTATE, "append: the model was adopted with mgp_set_state, its hyper-parameters are unknown");
+  if (h->p > 1) return mgp_fail(h, MGP_ESTATE, "append: only the constant trend is extended incrementally");
+  const int n0 = h->n, npad0 = h->npad, d = h->d, dpad = h->dpad;
+  const int n1 = n0 + k, npad1 = (int)round_up(n1, MGP_TILE), NI1 = npad1 / MGP_TILE;
+  const int nb = (n0 / MGP_TILE) * MGP_TILE;   // rows [0, nb) are complete tiles and keep their factor
+  const int tail = npad1 - nb;                 // recomputed rows (a multiple of 128)
+  if (nb < 512 || tail * 4 > nb)
+    return mgp_fail(h, MGP_ESTATE, "append: the leading block (%d rows) is too small for %d new rows -- refit instead", nb, k);
+  cudaStream_t st = h->stream;
+  WsScope ws(h, st);
+  MGP_CUDA(h, ws.err);
+  // ---- new training buffers (old centring kept: differences are translation invariant) -----------
+  DevBuf nXc, nY;
+  MGP_TRY(mgp_ensure(h, nXc, (size_t)npad1 * dpad * 8));
+  MGP_TRY(mgp_ensure(h, nY, (size_t)npad1 * 8));
+  auto drop_new = [&]() { freebuf(nXc); freebuf(nY); };
+  std::vector<double> Xa((size_t)k * dpad, 0.0);
+  for (int j = 0; j < k; j++)
+    for (int i = 0; i < d; i++) Xa[(size_t)j * dpad + i] = X_add[(size_t)j * d + i] - h->hcenter[i];
+  cudaError_t e = cudaMemsetAsync(nXc.p, 0, (size_t)npad1 * dpad * 8, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(nY.p, 0, (size_t)npad1 * 8, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nXc.p, h->dXc.p, (size_t)n0 * dpad * 8, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(P<double>(nXc) + (size_t)n0 * dpad, Xa.data(), Xa.size() * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nY.p, h->dy.p, (size_t)n0 * 8, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(P<double>(nY) + n0, y_add, (size_t)k * 8, cudaMemcpyHostToDevice, st);
+  int *flag = P<int>(h->dscal);
+  if (e == cudaSuccess) e = cudaMemsetAsync(flag, 0, 2 * sizeof(int), st);
+  if (e == cudaSuccess) e = launch_dup_check(P<double>(nXc), n1, dpad, flag, st);
+  int hflag = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { drop_new(); return mgp_cuda_fail(h, e, "append: staging the new rows"); }
+  h->launches++;
+  if (hflag) { drop_new(); return mgp_fail(h, MGP_EINVAL, "duplicate rows: Multiple input features cannot have the same target value."); }
+  // ---- switch the handle to the new geometry (restored if the extension fails) ---------------------
+  std::swap(h->dXc, nXc); std::swap(h->dy, nY);
+  h->n = n1; h->npad = npad1; h->NI = NI1;
+  auto restore = [&]() {
+    std::swap(h->dXc, nXc); std::swap(h->dy, nY);
+    h->n = n0; h->npad = npad0; h->NI = npad0 / MGP_TILE;
+    h->nll_cap = 0;
+    drop_new();
+  };
+  if (npad1 != npad0) h->nll_cap = 0;
+  int rc = h->nll_cap < 1 ? nll_alloc(h, 1) : 0;
+  if (rc == 0) rc = mgp_ensure(h, h->npar, h->hpar.size() * 8 + 64);
+  if (rc != 0) { restore(); return rc; }
+  const int n_par = (int)h->hpar.size();
+  NllWork w;
+  fill_work(h, w, 0, 1, h->nll_cap, n_par, h->mode, h->par_noise_var, 0, P<double>(h->npar), nullptr, nullptr);
+  w.have_L = 1; w.have_M = 1; w.want_bhat = 1;
+  const size_t ld = (size_t)npad1;
+  int *chol_status = flag + 1;
+#define AP_CUDA(call)                                                       \
+  do {                                                                      \
+    cudaError_t e__ = (call);                                               \
+    if (e__ != cudaSuccess) { cudaStreamSynchronize(st); restore(); return mgp_cuda_fail(h, e__, #call); } \
+  } while (0)
+  AP_CUDA(cudaMemcpyAsync(h->npar.p, h->hpar.data(), (size_t)n_par * 8, cudaMemcpyHostToDevice, st));
+  // old factor and inverse into the workspace slot at the new leading dimension
+  if (npad1 == npad0) {
+    AP_CUDA(cudaMemcpyAsync(w.L, h->dL.p, ld * ld * 8, cudaMemcpyDeviceToDevice, st));
+    AP_CUDA(cudaMemcpyAsync(w.M, h->dMinv.p, ld * ld * 8, cudaMemcpyDeviceToDevice, st));
+  } else {
+    AP_CUDA(cudaMemsetAsync(w.L, 0, ld * ld * 8, st));
+    AP_CUDA(cudaMemsetAsync(w.M, 0, ld * ld * 8, st));
+    AP_CUDA(cudaMemcpy2DAsync(w.L, ld * 8, h->dL.p, (size_t)npad0 * 8, (size_t)nb * 8, nb, cudaMemcpyDeviceToDevice, st));
+    AP_CUDA(cudaMemcpy2DAsync(w.M, ld * 8, h->dMinv.p, (size_t)npad0 * 8, (size_t)nb * 8, nb, cudaMemcpyDeviceToDevice, st));
+  }
+  // R, tile rows >= nb / 128 (lower block triangle)
+  AP_CUDA(launch_build_R(w, nb / MGP_TILE, st));
+  double *Rt = w.R + (size_t)nb * ld, *Lt = w.L + (size_t)nb * ld, *Mt = w.M + (size_t)nb * ld;
+  double *Tt = w.T + (size_t)nb * ld;                       // tail rows of the scratch matrix: L21 M11
+  double *Sc = w.T, *L22 = Sc + (size_t)tail * tail, *M22 = L22 + (size_t)tail * tail, *Ts = M22 + (size_t)tail * tail;
+  {  // L21 = R21 M11^T   (M11 stored [N][K]: B(k, j) = M11[j][k]; its zero half is multiplied too)
+    GemmDesc g = {};
+    g.A = Rt; g.lda = (int)ld; g.ta = 0; g.B = w.M; g.ldb = (int)ld; g.tb = 0; g.C = Lt; g.ldc = (int)ld;
+    g.M = tail; g.N = nb; g.K = nb; g.alpha = 1.0; g.beta = 0.0; g.n_inner = 1; g.n_outer = 1;
+    AP_CUDA(launch_dgemm(g, st));
+  }
+  {  // S = R22 - L21 L21^T  (lower tiles), in place in R
+    GemmDesc g = {};
+    g.A = Lt; g.lda = (int)ld; g.ta = 0; g.B = Lt; g.ldb = (int)ld; g.tb = 0; g.C = Rt + nb; g.ldc = (int)ld;
+    g.M = tail; g.N = tail; g.K = nb; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1; g.n_inner = 1; g.n_outer = 1;
+    AP_CUDA(launch_dgemm(g, st));
+  }
+  // L22 = chol(S), M22 = L22^-1 on a compact tail x tail copy
+  AP_CUDA(cudaMemcpy2DAsync(Sc, (size_t)tail * 8, Rt + nb, ld * 8, (size_t)tail * 8, tail, cudaMemcpyDeviceToDevice, st));
+  AP_CUDA(cudaMemsetAsync(chol_status, 0, sizeof(int), st));
+  AP_CUDA(chol_blocked(Sc, L22, tail, 0, w.linv, 0, chol_status, 1, st, &h->launches, true, 0, chol_panels(tail)));
+  AP_CUDA(trtri_blocked(L22, M22, Ts, tail, 0, w.linv, 0, 1, st, &h->launches, true));
+  AP_CUDA(cudaMemcpy2DAsync(Lt + nb, ld * 8, L22, (size_t)tail * 8, (size_t)tail * 8, tail, cudaMemcpyDeviceToDevice, st));
+  AP_CUDA(cudaMemcpy2DAsync(Mt + nb, ld * 8, M22, (size_t)tail * 8, (size_t)tail * 8, tail, cudaMemcpyDeviceToDevice, st));
+  {  // Tt = L21 M11   (M11 stored [K][N], lower triangular: k starts at the column block)
+    GemmDesc g = {};
+    g.A = Lt; g.lda = (int)ld; g.ta = 0; g.B = w.M; g.ldb = (int)ld; g.tb = 1; g.C = Tt; g.ldc = (int)ld;
+    g.M = tail; g.N = nb; g.K = nb; g.alpha = 1.0; g.beta = 0.0; g.kmode = 1; g.order = 3; g.n_inner = 1; g.n_outer = 1;
+    AP_CUDA(launch_dgemm(g, st));
+  }
+  {  // M21 = -M22 Tt   (M22 lower triangular: k ends with the row block)
+    GemmDesc g = {};
+    g.A = Mt + nb; g.lda = (int)ld; g.ta = 0; g.B = Tt; g.ldb = (int)ld; g.tb = 1; g.C = Mt; g.ldc = (int)ld;
+    g.M = tail; g.N = nb; g.K = tail; g.alpha = -1.0; g.beta = 0.0; g.kmode = 2; g.order = 2; g.n_inner = 1; g.n_outer = 1;
+    AP_CUDA(launch_dgemm(g, st));
+  }
+  h->launches += 5;
+  AP_CUDA(nll_pipeline(w, st, &h->launches));
+  std::vector<double> sc(nll_scal_doubles());
+  int status = 0, cstatus = 0;
+  AP_CUDA(cudaMemcpyAsync(sc.data(), w.scal, sc.size() * 8, cudaMemcpyDeviceToHost, st));
+  AP_CUDA(cudaMemcpyAsync(&status, w.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  AP_CUDA(cudaMemcpyAsync(&cstatus, chol_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  AP_CUDA(cudaStreamSynchronize(st));
+#undef AP_CUDA
+  if (cstatus > 0 || status > 0) {
+    restore();
+    return mgp_fail(h, MGP_ENOTPD, "append: extended correlation matrix not positive definite at pivot %d",
+                    cstatus > 0 ? nb + cstatus : status);
+  }
+  h->hX.insert(h->hX.end(), X_add, X_add + (size_t)k * d);
+  h->hy.insert(h->hy.end(), y_add, y_add + k);
+  drop_new();                        // the old training buffers
+  h->noise_var = sc[NLL_NV];
+  h->sigma2 = sc[NLL_SIGMA2];
+  h->llf = sc[NLL_LLF];
+  h->ftf = sc[NLL_FTF];
+  h->G = -sqrt(sc[NLL_FTF]);
+  h->beta = sc[NLL_BETA];
+  MGP_TRY(mgp_model_alloc(h));
+  MGP_TRY(adopt_slot0(h, h->hpar.data(), true));
+  h->appends++;
   if (out_llf) *out_llf = h->llf;
   return MGP_OK;
 }
@@ -743,6 +894,7 @@ int mgp_set_state(mgp_t *h, const double *theta, const double *L, const double *
   h->ftf = sc[NLL_FTF];
   h->G = -sqrt(sc[NLL_FTF]);
   h->llf = NAN;
+  h->hpar.clear();
   MGP_TRY(adopt_slot0(h, theta, false));
   if (h->p > 1) {   // the coefficients travel with the state (they are what the sender fitted)
     h->hbeta.assign(MGP_PMAX, 0.0);

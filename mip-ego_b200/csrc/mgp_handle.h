@@ -25,6 +25,7 @@ struct mgp_handle {
   cudaStream_t out_stream = nullptr;   // D2H of staged results
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int64_t launches = 0;
+  int64_t appends = 0;          // successful mgp_append_train calls
   // Workspace ordering across streams: the posterior / likelihood scratch, the fitted-state buffers
   // and the running top-k are shared by the host-pointer entry points (h->stream) and the *_dev
   // entry points (caller's stream).  Every entry point makes its stream wait on ev_ws (recorded by
@@ -63,6 +64,11 @@ struct mgp_handle {
   bool fitted = false;
   int mode = 0;
   double sigma2 = 0, beta = 0, G = 0, ftf = 0, llf = 0, noise_var = 0;
+  // hyper-parameters of the fitted model in the kernels' layout (d theta values + extras), kept by
+  // mgp_finalize_fit for mgp_append_train; empty after mgp_set_state (adopted from outside)
+  std::vector<double> hpar;
+  double par_noise_var = 0.0;
+  std::vector<double> hcenter;   // centring offsets of dXc
   DevBuf dtheta;   // dpad
   DevBuf dBop;     // npad x dpad : -2 theta_i xc_ji
   DevBuf dan;      // npad        : sum_i theta_i xc_ji^2

@@ -69,14 +69,14 @@ __device__ __forceinline__ double feature_scale(double theta) { return CORR == 2
 template <int CORR>
 __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int npad, int dpad,
                                                  const double *params, int n_par, int mode,
-                                                 double noise_var, double *R, int64_t sR) {
+                                                 double noise_var, double *R, int64_t sR, int bi0) {
   extern __shared__ __align__(16) double sm[];
   double *xjT = sm;               // [dpad][XP]  rows of tile bi
   double *xkT = sm + dpad * XP;   // [dpad][XP]  rows of tile bj
   double *th = xkT + dpad * XP;   // [dpad]      theta, then the feature scales
   double *tab = th + dpad;        // exp table (mgp_common.cuh)
   __shared__ int s_anyzero;
-  const int bj = blockIdx.x, bi = blockIdx.y, b = blockIdx.z;
+  const int bj = blockIdx.x, bi = blockIdx.y + bi0, b = blockIdx.z;
   if (bj > bi) return;
   const int tid = threadIdx.x;
   const double *par = params + (int64_t)b * n_par;
@@ -753,6 +753,33 @@ cudaError_t launch_dup_check(const double *Xc, int n, int dpad, int *flag, cudaS
   return cudaGetLastError();
 }
 
+cudaError_t launch_build_R(const NllWork &w, int bi0, cudaStream_t st) {
+  const int NI = w.npad / 128;
+  const int64_t sM = (int64_t)w.npad * w.npad;
+  if (bi0 < 0 || bi0 >= NI) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + MGP_EXP_TAB_DOUBLES) * sizeof(double);
+  dim3 grid(NI, NI - bi0, w.B);
+  static size_t smem_set[MGP_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = dev < 0 || dev >= MGP_MAX_DEVICES ? 0 : dev;
+  if (smem > smem_set[dev]) {   // the opt-in only ever needs to grow
+    cudaFuncSetAttribute(k_build_R<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_build_R<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_build_R<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set[dev] = smem;
+  }
+  if (w.corr == MGP_CORR_SE)
+    k_build_R<0><<<grid, 256, smem, st>>>(w.Xc, w.n, w.npad, w.dpad, w.params, w.n_par, w.mode, w.noise_var, w.R, sM, bi0);
+  else if (w.corr == MGP_CORR_MATERN32)
+    k_build_R<1><<<grid, 256, smem, st>>>(w.Xc, w.n, w.npad, w.dpad, w.params, w.n_par, w.mode, w.noise_var, w.R, sM, bi0);
+  else if (w.corr == MGP_CORR_ABSEXP)
+    k_build_R<2><<<grid, 256, smem, st>>>(w.Xc, w.n, w.npad, w.dpad, w.params, w.n_par, w.mode, w.noise_var, w.R, sM, bi0);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 int nll_num_phases(const NllWork &w) { return w.have_L ? 2 : chol_panels(w.npad) + 2; }
 
 // phase < 0: the whole pipeline.  Otherwise phase 0 builds R (or inverts the diagonal blocks of a
@@ -766,35 +793,13 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
   const int last = nll_num_phases(w) - 1;
   if (phase <= 0) {
   NL_TRY(cudaMemsetAsync(w.status, 0, sizeof(int) * B, st));
-  if (w.have_L) {
+  if (w.have_L && w.have_M) {
+    // factor and inverse both given (rank-k append): nothing to prepare
+  } else if (w.have_L) {
     NL_TRY(launch_trtri_diag(w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, NI, B, st));
     (*launches)++;
   } else {
-    const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + MGP_EXP_TAB_DOUBLES) * sizeof(double);
-    dim3 grid(NI, NI, B);
-    static size_t smem_set[MGP_MAX_DEVICES] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev = dev < 0 || dev >= MGP_MAX_DEVICES ? 0 : dev;
-    if (smem > smem_set[dev]) {   // the opt-in only ever needs to grow
-      cudaFuncSetAttribute(k_build_R<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_build_R<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_build_R<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      smem_set[dev] = smem;
-    }
-    if (w.corr == MGP_CORR_SE) {
-      k_build_R<0><<<grid, 256, smem, st>>>(w.Xc, n, npad, w.dpad, w.params, w.n_par, w.mode,
-                                            w.noise_var, w.R, sM);
-    } else if (w.corr == MGP_CORR_MATERN32) {
-      k_build_R<1><<<grid, 256, smem, st>>>(w.Xc, n, npad, w.dpad, w.params, w.n_par, w.mode,
-                                            w.noise_var, w.R, sM);
-    } else if (w.corr == MGP_CORR_ABSEXP) {
-      k_build_R<2><<<grid, 256, smem, st>>>(w.Xc, n, npad, w.dpad, w.params, w.n_par, w.mode,
-                                            w.noise_var, w.R, sM);
-    } else {
-      return cudaErrorInvalidValue;
-    }
-    NL_TRY(cudaGetLastError());
+    NL_TRY(launch_build_R(w, 0, st));
     (*launches)++;
   }
   }
@@ -806,8 +811,9 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
                           w.want_bhat != 0, lo, hi, w.gemm_cta_cap));
   }
   if (phase >= 0 && phase != last) return cudaSuccess;
-  NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches,
-                       w.want_bhat != 0, w.gemm_cta_cap));
+  if (!(w.have_L && w.have_M))
+    NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches,
+                         w.want_bhat != 0, w.gemm_cta_cap));
   double *Yt = w.Yt, *Ft = w.Ft, *rho = w.rho, *gamma = w.gamma;
   const bool general = w.p > 1 && w.ordinary;   // p basis functions with estimated coefficients
   NL_TRY(launch_trmv(w.M, npad, sM, w.y, 0, Yt, npad, n, 0, B, st));

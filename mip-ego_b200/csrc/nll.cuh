@@ -8,6 +8,7 @@
 struct NllWork {
   int n, npad, dpad, B, n_par, mode, corr, ordinary, eval_grad;
   int gemm_cta_cap;       // CTA cap of the GEMM launches of this work item (0 = one per SM)
+  int have_M;             // 1 (with have_L): L^-1 is given in w.M as well; skip the triangular inversion
   int have_L;             // 1: L (B=1) is given in w.L; skip the correlation build and Cholesky
   double noise_var, beta0;
   const double *Xc;      // npad x dpad centred training inputs
@@ -65,6 +66,8 @@ cudaError_t launch_iso_expand(const double *P, int B, int n_short, int d, double
 // derivative w.r.t. the second feature's theta: reproduced as is.
 cudaError_t launch_iso_gather(const double *Gfull, int B, int n_short, int n_full, int d, int mode, double *G,
                               cudaStream_t st);
+// Builds the tile rows >= bi0 (128 rows each) of the lower block triangle of R into w.R.
+cudaError_t launch_build_R(const NllWork &w, int bi0, cudaStream_t st);
 // number of hyper-parameters of a mode for d features (include/mgp.h)
 int nll_n_par(int mode, int d);
 // phase < 0 runs everything; otherwise one of nll_num_phases(w) phases (R build | one Cholesky panel

@@ -452,7 +452,40 @@ class GaussianProcess(object):
             return self._append(Xn, np.asarray(y, dtype=np.float64).ravel(), par)
         return self.fit_fixed(X, y, par)
 
-    _append_ok = False    # switched on where the library exports mgp_append_train
+    _append_ok = True     # update(reoptimize=False) extends the factorisation for appended rows
+
+    def _append(self, X, y, par):
+        """Rank-k extension through mgp_append_train (O(n^2 k)); falls back to the rebuild at the
+        same hyper-parameters where the library declines (MGP_ESTATE: small models, large batches of
+        new rows, non-constant trends, models adopted from outside)."""
+        h = self._handle()
+        n0 = self.X.shape[0]
+        Xa = np.ascontiguousarray(X[n0:], dtype=np.float64)
+        ya = np.ascontiguousarray(y[n0:], dtype=np.float64)
+        if not np.isfinite(ya).all():
+            raise ValueError("Input y contains NaN or infinity.")
+        out = ctypes.c_double(0.0)
+        rc = h.lib.mgp_append_train(h.h, Xa.shape[0], _cabi.dptr(Xa), _cabi.dptr(ya), ctypes.byref(out))
+        if rc == _cabi.MGP_ESTATE or rc == _cabi.MGP_ENOTPD:
+            return self.fit_fixed(X, y, par)
+        if rc == _cabi.MGP_EINVAL and b"duplicate rows" in h.lib.mgp_last_error(h.h):
+            raise Exception("Multiple input features cannot have the same target value.")
+        h.check(rc)
+        self.X, self.y = X, y.reshape(-1, 1)
+        self._cache = {}
+        self._host_state = None
+        sc = np.zeros(5)
+        h.check(h.lib.mgp_get_state(h.h, None, None, None, None, None, None, _cabi.dptr(sc)))
+        self.sigma2 = self._typed_sigma2(sc[0])
+        self._env_noise_var = self._typed_noise_var(sc[4])
+        self.noise_var = self._env_noise_var
+        if self.estimate_trend:
+            self.mean.beta = self._beta_from_device()
+            self.F = self.mean.F(X)
+        llf = float(out.value)
+        scalar_llf = self.likelihood == "restricted" or self.estimation_mode == "noiseless"
+        self.log_likelihood_ = llf if scalar_llf else np.array([llf])
+        return self
 
     def set_fitted_state(self, X, y, theta, L, gamma, sigma2, beta, par=None):
         """Adopt an externally fitted model (mgp_set_state): used by un-pickling, by the multi-GPU
