@@ -20,7 +20,22 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("MIPEGO_REFERENCE_ROOT", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    """$MIPEGO_REFERENCE_ROOT, else /root/reference (the build container), else the temporary copy
+    tools/ship_reference_run.sh places under baseline/_ref/ for ONE run on the GPU box (git-ignored,
+    removed afterwards -- reference sources are never part of this repository)."""
+    cands = [os.environ.get("MIPEGO_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(_ROOT, "baseline", "_ref", "reference")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "mipego")):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available():
