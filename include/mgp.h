@@ -222,10 +222,13 @@ int mgp_allgather_f64_dev(mgp_t *h, const double *d_send, int64_t count, double 
  * reference's indexing of its derivative tensor (entry 0 = derivative w.r.t. the first feature's
  * theta; set it before the first likelihood call); "small_path" = 0 disables the matrix-vector path
  * for <= 8 candidates; "nll_groups", "gemm_cta_cap": scheduling of batched likelihoods (0 = automatic);
+ * "nll_graphs" = 0 issues every batched likelihood launch by launch (default 1: the launch sequence of
+ * a batch shape is captured in a CUDA graph at its second use and replayed with one cudaGraphLaunch;
+ * not used on the legacy default stream);
  * "time_kernels" = 1 brackets every posterior kernel launch with CUDA events on the
  * launching stream (resets the timers).
  * mgp_get_counter: "launches" = kernels launched by this handle so far; "npad", "chunk",
- * "sm_count", "small_path", "isotropic", "n", "rank", "world", "bcast_bytes" (payload of the last
+ * "sm_count", "small_path", "isotropic", "n", "appends", "graph_replays", "nll_graphs" (captured shapes), "rank", "world", "bcast_bytes" (payload of the last
  * mgp_bcast_model); with time_kernels: "<k>_ns" / "<k>_calls" for k in rgen, trmm, epilogue, topk
  * (accumulated device time in nanoseconds; synchronises on the recorded events). */
 int mgp_set_option(mgp_t *h, const char *name, int64_t value);

@@ -96,6 +96,8 @@ struct WsScope {   // acquire on construction, release on destruction (every ret
 
 extern "C" {
 
+static void nll_graphs_clear(mgp_handle *h);
+
 int mgp_abi_version(void) { return MGP_ABI_VERSION; }
 
 int mgp_create(int device, mgp_t **out_h) {
@@ -150,13 +152,14 @@ int mgp_destroy(mgp_t *h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   mgp_comm_destroy(h);
+  nll_graphs_clear(h);
   DevBuf *all[] = {&h->dtpart, &h->dXc, &h->dy, &h->dcenter, &h->dtheta, &h->dBop, &h->dan, &h->dL, &h->dMinv,
                    &h->dTmp, &h->dMp, &h->dRinvP, &h->dgamma, &h->davec, &h->dFt,
                    &h->dYt, &h->drho, &h->dscal, &h->drP, &h->dmeanpart, &h->dftpart, &h->dqpart,
                    &h->dwP, &h->dXs_stage[0], &h->dXs_stage[1], &h->dout_stage[0],
                    &h->dout_stage[1], &h->dtopk_val, &h->dtopk_idx, &h->dtopk_blk, &h->nR, &h->nL, &h->nM, &h->nT,
                    &h->nLinvDiag, &h->nvec, &h->nscal, &h->npar, &h->ngpart, &h->nFtm, &h->nBhat, &h->ntws,
-                   &h->dF, &h->dmu, &h->dbetav, &h->dBhat, &h->dCinv, &h->dFtm, &h->niso, &h->dcomm, &h->dgather, &h->dgather_io};
+                   &h->dF, &h->dmu, &h->dbetav, &h->dBhat, &h->dCinv, &h->dFtm, &h->niso, &h->dcomm, &h->dgather, &h->dgather_io, &h->ngio};
   for (DevBuf *b : all) freebuf(*b);
   for (int i = 0; i < 2; i++) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -194,10 +197,17 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
   if (!strcmp(name, "nll_groups")) {
     if (value < 0 || value > MGP_NLL_STREAMS) return mgp_fail(h, MGP_EINVAL, "nll_groups must be in 0..%d", MGP_NLL_STREAMS);
     h->nll_groups_opt = (int)value;
+    nll_graphs_clear(h);
     return MGP_OK;
   }
   if (!strcmp(name, "gemm_cta_cap")) {
     h->gemm_cap_opt = (int)value;
+    nll_graphs_clear(h);
+    return MGP_OK;
+  }
+  if (!strcmp(name, "nll_graphs")) {   // 0: every batched likelihood is issued launch by launch
+    h->graphs_opt = value != 0;
+    if (!h->graphs_opt) nll_graphs_clear(h);
     return MGP_OK;
   }
   if (!strcmp(name, "isotropic")) {   // one theta for all features: n_par shrinks by d - 1
@@ -222,6 +232,8 @@ int64_t mgp_get_counter(const mgp_t *h, const char *name) {
   if (!strcmp(name, "isotropic")) return h->isotropic ? 1 : 0;
   if (!strcmp(name, "n")) return h->n;
   if (!strcmp(name, "appends")) return h->appends;
+  if (!strcmp(name, "graph_replays")) return h->graph_replays;
+  if (!strcmp(name, "nll_graphs")) return (int64_t)h->nll_graphs.size();
   if (!strcmp(name, "world")) return h->world;
   if (!strcmp(name, "rank")) return h->rank;
   if (!strcmp(name, "bcast_bytes")) return h->bcast_bytes;
@@ -281,6 +293,7 @@ int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int 
   MGP_CUDA(h, ws.err);
   h->hcenter = center;
   h->hpar.clear();
+  nll_graphs_clear(h);
   MGP_TRY(mgp_ensure(h, h->dXc, Xc.size() * 8));
   MGP_TRY(mgp_ensure(h, h->dy, yp.size() * 8));
   MGP_TRY(mgp_ensure(h, h->dcenter, center.size() * 8));
@@ -440,27 +453,18 @@ static int nll_groups(const mgp_handle *h, int nb) {
   return g < 1 ? 1 : g;
 }
 
-int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mode,
-                      double noise_var, int eval_grad, double *d_out_llf, double *d_out_grad,
-                      int *d_out_status, void *stream) {
-  CHECK_H(h);
-  MGP_TRY(check_par(h, n_par, mode));
-  if (B < 1 || !d_params || !d_out_llf || (eval_grad && !d_out_grad))
-    return mgp_fail(h, MGP_EINVAL, "bad arguments to mgp_nll_batch");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (B > h->nll_cap) {   // grow the workspace (cudaMemGetInfo is slow: only asked when growing)
-    const int cap = std::min(B, nll_max_batch(h));
-    if (cap > h->nll_cap) MGP_TRY(nll_alloc(h, cap));
-  }
-  WsScope ws(h, st);
-  MGP_CUDA(h, ws.err);
+// Issues the launches of one batched likelihood on `st` (and, for several batch groups, on the
+// handle's group streams forked from / joined into `st`).  No workspace ordering, no allocation of
+// the main workspace: the caller has done both.  Capturable in a CUDA graph once every lazily
+// created resource exists (function attributes, scheduler words: after one eager pass).
+static int nll_issue(mgp_handle *h, int B, const double *d_params, int n_par, int mode, double noise_var,
+                     int eval_grad, double *d_out_llf, double *d_out_grad, int *d_out_status, cudaStream_t st) {
   // isotropic theta: expand to the d-value layout the kernels use, map the gradient back afterwards
   const int n_short = n_par;
   double *d_grad_user = d_out_grad;
   const bool iso = h->isotropic && h->d > 1;
   if (iso) {
     n_par = nll_n_par(mode, h->d);
-    MGP_TRY(mgp_ensure(h, h->niso, (size_t)2 * B * n_par * 8));
     double *pf = P<double>(h->niso);
     MGP_CUDA(h, launch_iso_expand(d_params, B, n_short, h->d, pf, st));
     h->launches++;
@@ -517,6 +521,118 @@ int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mo
   return MGP_OK;
 }
 
+static void nll_graphs_clear(mgp_handle *h) {
+  for (auto &g : h->nll_graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->nll_graphs.clear();
+}
+
+// Staging area of the graph path: [params B x n_par | llf B | grad B x n_par | status B ints].
+static int nll_staging(mgp_handle *h, int B, int n_par, double **par, double **llf, double **grad, int **status) {
+  const size_t need = ((size_t)2 * B * n_par + B) * 8 + (size_t)B * sizeof(int) + 256;
+  if (h->ngio.bytes < need) {
+    // a larger staging area invalidates the graphs that point into the old one
+    nll_graphs_clear(h);
+    MGP_TRY(mgp_ensure(h, h->ngio, std::max(need, (size_t)1 << 16)));
+  }
+  *par = P<double>(h->ngio);
+  *grad = *par + (size_t)B * n_par;
+  *llf = *grad + (size_t)B * n_par;
+  *status = reinterpret_cast<int *>(*llf + B);
+  return 0;
+}
+
+int mgp_nll_batch_dev(mgp_t *h, int B, const double *d_params, int n_par, int mode,
+                      double noise_var, int eval_grad, double *d_out_llf, double *d_out_grad,
+                      int *d_out_status, void *stream) {
+  CHECK_H(h);
+  MGP_TRY(check_par(h, n_par, mode));
+  if (B < 1 || !d_params || !d_out_llf || (eval_grad && !d_out_grad))
+    return mgp_fail(h, MGP_EINVAL, "bad arguments to mgp_nll_batch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (B > h->nll_cap) {   // grow the workspace (cudaMemGetInfo is slow: only asked when growing)
+    const int cap = std::min(B, nll_max_batch(h));
+    if (cap > h->nll_cap) {
+      nll_graphs_clear(h);      // the workspace moves
+      MGP_TRY(nll_alloc(h, cap));
+    }
+  }
+  if (h->isotropic && h->d > 1) {
+    const size_t need = (size_t)2 * B * nll_n_par(mode, h->d) * 8;
+    if (h->niso.bytes < need) {
+      nll_graphs_clear(h);      // graphs of smaller batches point into the old buffer
+      MGP_TRY(mgp_ensure(h, h->niso, need));
+    }
+  }
+  WsScope ws(h, st);
+  MGP_CUDA(h, ws.err);
+  // ---- CUDA-graph path: shapes that fit the workspace in one pass, on a capturable stream -----------
+  const bool graphable = h->graphs_opt && !h->time_kernels && B <= h->nll_cap && st != nullptr &&
+                         st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (!graphable)
+    return nll_issue(h, B, d_params, n_par, mode, noise_var, eval_grad, d_out_llf, d_out_grad, d_out_status, st);
+  const int G = nll_groups(h, B);
+  mgp_handle::NllGraph key = {B, n_par, mode, eval_grad, h->n, h->npad, G, h->gemm_cap_opt, h->isotropic ? 1 : 0,
+                              noise_var, nullptr, 0, 0};
+  mgp_handle::NllGraph *rec = nullptr;
+  for (auto &g : h->nll_graphs)
+    if (g.B == key.B && g.n_par == key.n_par && g.mode == key.mode && g.eval_grad == key.eval_grad && g.n == key.n &&
+        g.npad == key.npad && g.groups == key.groups && g.cap == key.cap && g.iso == key.iso &&
+        g.noise_var == key.noise_var) { rec = &g; break; }
+  if (!rec) {
+    // first sight of this shape: eager pass (creates function attributes, scheduler words, ...)
+    if (h->nll_graphs.size() >= 16) nll_graphs_clear(h);
+    h->nll_graphs.push_back(key);
+    return nll_issue(h, B, d_params, n_par, mode, noise_var, eval_grad, d_out_llf, d_out_grad, d_out_status, st);
+  }
+  double *sp, *sl, *sg;
+  int *ss;
+  {
+    const size_t before = h->nll_graphs.size();
+    MGP_TRY(nll_staging(h, B, n_par, &sp, &sl, &sg, &ss));
+    if (h->nll_graphs.size() != before) {      // staging grew: every record is gone, start over for this shape
+      h->nll_graphs.push_back(key);
+      rec = &h->nll_graphs.back();
+    }
+  }
+  const bool direct = d_params == sp;          // the host-pointer entry point stages into ngio itself
+  if (!direct)
+    MGP_CUDA(h, cudaMemcpyAsync(sp, d_params, (size_t)B * n_par * 8, cudaMemcpyDeviceToDevice, st));
+  if (!rec->exec) {
+    const int64_t l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    MGP_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = nll_issue(h, B, sp, n_par, mode, noise_var, eval_grad, sl, sg, ss, st);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != 0 || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      h->graphs_opt = 0;         // not capturable here: stay on the eager path
+      h->launches = l0;
+      if (!direct) {
+        MGP_TRY(nll_issue(h, B, d_params, n_par, mode, noise_var, eval_grad, d_out_llf, d_out_grad, d_out_status, st));
+        return MGP_OK;
+      }
+      return nll_issue(h, B, sp, n_par, mode, noise_var, eval_grad, sl, sg, ss, st);
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&rec->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { rec->exec = nullptr; h->graphs_opt = 0; return mgp_cuda_fail(h, ie, "cudaGraphInstantiate"); }
+    rec->launches = h->launches - l0;
+    h->launches = l0;
+  }
+  MGP_CUDA(h, cudaGraphLaunch(rec->exec, st));
+  rec->uses++;
+  h->graph_replays++;
+  h->launches += rec->launches;
+  if (!direct) {
+    MGP_CUDA(h, cudaMemcpyAsync(d_out_llf, sl, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+    if (eval_grad) MGP_CUDA(h, cudaMemcpyAsync(d_out_grad, sg, (size_t)B * n_par * 8, cudaMemcpyDeviceToDevice, st));
+    if (d_out_status) MGP_CUDA(h, cudaMemcpyAsync(d_out_status, ss, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
+  return MGP_OK;
+}
+
 int mgp_nll_batch(mgp_t *h, int B, const double *params, int n_par, int mode, double noise_var,
                   int eval_grad, double *out_llf, double *out_grad, int *out_status) {
   CHECK_H(h);
@@ -524,12 +640,15 @@ int mgp_nll_batch(mgp_t *h, int B, const double *params, int n_par, int mode, do
   if (B < 1 || !params || !out_llf || (eval_grad && !out_grad))
     return mgp_fail(h, MGP_EINVAL, "bad arguments to mgp_nll_batch");
   const size_t pb = (size_t)B * n_par * 8;
-  MGP_TRY(mgp_ensure(h, h->npar, 2 * pb + (size_t)B * 8 + (size_t)B * sizeof(int) + 256));
-  double *d_par = P<double>(h->npar);
-  double *d_grad = d_par + (size_t)B * n_par;
-  double *d_llf = d_grad + (size_t)B * n_par;
-  int *d_status = reinterpret_cast<int *>(d_llf + B);
-  MGP_CUDA(h, cudaMemcpyAsync(d_par, params, pb, cudaMemcpyHostToDevice, h->stream));
+  // parameters and results go through the staging area the likelihood graphs are wired to
+  double *d_par, *d_llf, *d_grad;
+  int *d_status;
+  MGP_TRY(nll_staging(h, B, n_par, &d_par, &d_llf, &d_grad, &d_status));
+  {
+    WsScope ws(h, h->stream);     // a graph replay on another stream may still be reading the staging area
+    MGP_CUDA(h, ws.err);
+    MGP_CUDA(h, cudaMemcpyAsync(d_par, params, pb, cudaMemcpyHostToDevice, h->stream));
+  }
   MGP_TRY(mgp_nll_batch_dev(h, B, d_par, n_par, mode, noise_var, eval_grad, d_llf, d_grad, d_status,
                             h->stream));
   MGP_CUDA(h, cudaMemcpyAsync(out_llf, d_llf, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));

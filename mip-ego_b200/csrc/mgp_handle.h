@@ -96,6 +96,21 @@ struct mgp_handle {
   DevBuf nR, nL, nM, nT, nLinvDiag, nvec, nscal, npar, ngpart;
   DevBuf nFtm, nBhat, ntws;   // general-trend workspaces (allocated when p > 1)
   DevBuf niso;                // isotropic theta: expanded parameters | full gradient
+  // CUDA graphs of the batched likelihood (one per shape): the ~100 launches of a batch on up to 8
+  // streams are captured once and replayed with ONE cudaGraphLaunch.  The graph reads its parameters
+  // from / writes its results to the handle's own staging area (ngio), so it does not depend on the
+  // caller's pointers.
+  struct NllGraph {
+    int B, n_par, mode, eval_grad, n, npad, groups, cap, iso;
+    double noise_var;
+    cudaGraphExec_t exec;      // nullptr: shape seen once (eager run), captured at the next call
+    int64_t launches;          // kernels in the graph
+    int64_t uses;
+  };
+  std::vector<NllGraph> nll_graphs;
+  int graphs_opt = 1;         // option "nll_graphs": 0 disables capture
+  int64_t graph_replays = 0;
+  DevBuf ngio;                // staging: params | llf | grad | status
   // ---- multi-GPU (comm.cu) -----------------------------------------------------------------
   void *comm = nullptr;       // ncclComm_t
   int rank = 0, world = 1;

@@ -747,49 +747,98 @@ __global__ void __launch_bounds__(1024) k_topk_merge(const double *vals, const i
 // One warp per candidate; lanes stride over the training points; D = x* - x_j component-wise.
 // A Matern candidate coinciding with a training point zeroes the whole Jacobian (gpr.py:588-615).
 // ---------------------------------------------------------------------------------------------
-// WIDE == false: one warp per candidate (8 candidates per CTA).  WIDE == true (populations of at
-// most 8, the one-point-per-call pattern): one CTA per candidate, its 8 warps split the training
-// points and combine their partial sums through shared memory in a fixed order.
-template <int CORR, int DP, bool WIDE>
-__global__ void __launch_bounds__(256) k_grad(GradParams p) {
-  const int tid = threadIdx.x, lane = tid & 31, cc = tid >> 5;
-  const int64_t c = WIDE ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * 8 + cc;
-  const int cb = (int)(c >> 7), c8 = (int)((c >> 3) & 15), crow = (int)(c & 7);
-  __shared__ double s_u[8][MGP_PMAX];    // per warp: u = Bhat^T r - Cinv f      (p > 1, estimated)
-  __shared__ double s_k[8][MGP_PMAX];    // per warp: kappa = C^-T u = (Ft^T Ft)^-1 (Ft^T rt - f)
-  __shared__ double s_red[WIDE ? 8 : 1][2 * DP + 2];
-  if (c >= p.mc) return;
+// Work decomposition.  A thread owns ONE candidate (its accumulators never leave registers and
+// nothing is reduced across lanes at the end) and a SLICE of DPS <= 16 features; LPC = 1, 2 or 4
+// adjacent lanes share a candidate when dpad > 16, so that 3 x DPS doubles of state fit the register
+// file for every d <= 64 (the previous warp-per-candidate kernel kept 5 x DP doubles per lane and
+// spilled 0.5 - 6 KB per thread for DP >= 24).  The training rows stream through shared memory in
+// tiles of 32 rows, pre-scaled by c_i = sqrt(theta_i) (theta_i for the absolute-exponential kernel),
+// and are read as broadcasts; r and W = R^-1 r come straight from their packed tiles, 16-byte loads
+// that are contiguous across the CTA.  Only the Matern distance (and the trend projection of a
+// general basis) needs the other slices: one or two shuffles per row.
+// WIDE (populations of at most 8, the one-point-per-call pattern): one CTA per candidate, its
+// 128 / LPC row groups split the rows of a tile and combine their sums through shared memory in a
+// fixed order.
+constexpr int GR_THREADS = 128;
+template <int DPS, int LPC, bool WIDE>
+struct GradCfg {
+  static constexpr int JT = WIDE ? 128 : 32;                  // training rows per shared-memory tile
+  static constexpr int DPW = DPS * LPC;                       // padded feature width
+  static constexpr int KS = DPS + 1;                          // trend coefficients per slice
+  static constexpr int KW = KS * LPC;
+  static constexpr int NG = WIDE ? GR_THREADS / LPC : 1;      // row groups
+  static constexpr int NCAND = WIDE ? 1 : GR_THREADS / LPC;   // candidates per CTA
+  static constexpr int RED = 2 * DPS + 2;                     // per thread: am | as | q | coincide
+  static int smem_doubles(bool gen) {
+    return JT * DPW + 2 * JT + (gen ? JT * KW + 2 * NCAND * KW : 0) + (WIDE ? GR_THREADS * RED : 0);
+  }
+};
+
+template <int CORR, int DPS, int LPC, bool WIDE>
+__global__ void __launch_bounds__(GR_THREADS) k_grad(GradParams p) {
+  using C = GradCfg<DPS, LPC, WIDE>;
+  extern __shared__ __align__(16) double gsm[];
   const bool gen = p.p > 1 && p.trend_est;
+  double *sX = gsm;                                 // [JT][DPW] scaled training coordinates
+  double *sG = sX + C::JT * C::DPW;                 // [JT] gamma
+  double *sA = sG + C::JT;                          // [JT] a = L^-T Ft (constant trend)
+  double *sB = sA + C::JT;                          // [JT][KW] Bhat rows           (general trend)
+  double *sU = sB + (gen ? C::JT * C::KW : 0);      // [NCAND][KW] u = Bhat^T r - Cinv f
+  double *sK = sU + (gen ? C::NCAND * C::KW : 0);   // [NCAND][KW] kappa = C^-T u
+  double *sR = sK + (gen ? C::NCAND * C::KW : 0);   // [THREADS][RED] row-group partial sums (WIDE)
+  const int tid = threadIdx.x, s = tid % LPC, grp = tid / LPC;
+  const int cl = WIDE ? 0 : grp, g = WIDE ? grp : 0;
+  const int64_t c = WIDE ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * C::NCAND + cl;
+  const bool valid = c < p.mc;
+  const int64_t cv = valid ? c : 0;                 // invalid threads shadow candidate 0, write nothing
+  const int cb = (int)(cv >> 7), c8 = (int)((cv >> 3) & 15), crow = (int)(cv & 7);
+
   double md = 0.0, ft = 0.0;
   for (int y = 0; y < p.JS; y++) {
-    md += p.meanpart[(int64_t)y * p.ldp + c];
-    if (p.p == 1) ft += p.ftpart[(int64_t)y * p.ldp + c];
+    md += p.meanpart[(int64_t)y * p.ldp + cv];
+    if (p.p == 1) ft += p.ftpart[(int64_t)y * p.ldp + cv];
   }
   const double kappa = (p.p == 1 && p.ordinary) ? (ft - 1.0) / p.ftf : 0.0;
+  // lanes that share this candidate (adjacent): the only ones a shuffle may name, since in WIDE mode
+  // the row groups of a warp can leave the row loop at different times
+  const unsigned gmask = LPC == 1 ? 0u : (((1u << LPC) - 1u) << ((tid & 31) & ~(LPC - 1)));
+  // ---- general trend: u, kappa, |u|^2 per candidate (gpr.py:465-472, 548-551) ------------------
   double u2g = 0.0;
   if (gen) {
-    const double *x = p.Xs + c * p.d;
-    for (int k = lane; k < p.p; k += 32) {
-      double w = 0.0;
-      for (int y = 0; y < p.JS; y++) w += p.tpart[((int64_t)y * p.PT + k) * p.ldp + c];
-      double cf = p.Cinv[k * MGP_PMAX];
-      for (int j = 1; j <= k; j++) cf = fma(p.Cinv[k * MGP_PMAX + j], x[j - 1], cf);
-      s_u[cc][k] = w - cf;
-    }
-    __syncwarp();
-    for (int i = lane; i < p.p; i += 32) {
-      double t = 0.0;
-      for (int k = i; k < p.p; k++) t = fma(p.Cinv[k * MGP_PMAX + i], s_u[cc][k], t);
-      s_k[cc][i] = t;
-    }
-    for (int k = 0; k < p.p; k++) u2g = fma(s_u[cc][k], s_u[cc][k], u2g);
-    __syncwarp();
-  }
-  double xs[DP], th[DP], am[DP], as[DP];
+    const double *x = p.Xs + cv * p.d;
 #pragma unroll
-  for (int i = 0; i < DP; i++) {
-    xs[i] = i < p.d ? p.Xs[c * p.d + i] - p.center[i] : 0.0;
-    th[i] = p.theta[i];
+    for (int kk = 0; kk < C::KS; kk++) {
+      const int k = s * C::KS + kk;
+      double u = 0.0;
+      if (k < p.p) {
+        double w = 0.0;
+        for (int y = 0; y < p.JS; y++) w += p.tpart[((int64_t)y * p.PT + k) * p.ldp + cv];
+        double cf = p.Cinv[k * MGP_PMAX];
+        for (int j = 1; j <= k; j++) cf = fma(p.Cinv[k * MGP_PMAX + j], x[j - 1], cf);
+        u = w - cf;
+      }
+      if (!WIDE || g == 0) sU[cl * C::KW + k] = u;
+    }
+    __syncthreads();
+    for (int k = 0; k < p.p; k++) u2g = fma(sU[cl * C::KW + k], sU[cl * C::KW + k], u2g);
+    if (!WIDE || g == 0) {
+#pragma unroll
+      for (int kk = 0; kk < C::KS; kk++) {
+        const int i = s * C::KS + kk;
+        double t = 0.0;
+        for (int k = i; k < p.p; k++) t = fma(p.Cinv[k * MGP_PMAX + i], sU[cl * C::KW + k], t);
+        sK[cl * C::KW + i] = t;
+      }
+    }
+  }
+  // ---- this thread's slice of the (scaled, centred) candidate --------------------------------
+  double xs[DPS], am[DPS], as[DPS];
+#pragma unroll
+  for (int i = 0; i < DPS; i++) {
+    const int f = s * DPS + i;
+    const double th = f < p.dpad ? p.theta[f] : 0.0;
+    const double cf = CORR == 2 ? th : sqrt(th);
+    xs[i] = f < p.d ? cf * (p.Xs[cv * p.d + f] - p.center[f]) : 0.0;
     am[i] = 0.0;
     as[i] = 0.0;
   }
@@ -797,81 +846,104 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
   int coincide = 0;
   const double *rbase = p.rP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + crow * 8;
   const double *wbase = p.wP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + crow * 8;
-  for (int j = WIDE ? tid : lane; j < p.n; j += WIDE ? 256 : 32) {
-    const int64_t o = (int64_t)(j >> 3) * 1024 + (j & 7);
-    const double r = rbase[o], w = wbase[o];
-    q = fma(r, w, q);
-    const double *xj = p.Xc + (int64_t)j * DP;
-    double df[DP];
-    double S = 0.0;
+
+  for (int j0 = 0; j0 < p.n; j0 += C::JT) {
+    __syncthreads();                                // previous tile consumed
+    for (int idx = tid; idx < C::JT * C::DPW; idx += GR_THREADS) {
+      const int jj = idx / C::DPW, f = idx % C::DPW, j = j0 + jj;
+      double v = 0.0;
+      if (j < p.n && f < p.dpad) {
+        const double th = p.theta[f];
+        v = (CORR == 2 ? th : sqrt(th)) * p.Xc[(int64_t)j * p.dpad + f];
+      }
+      sX[idx] = v;
+    }
+    if (tid < C::JT) {
+      const int j = j0 + tid;
+      sG[tid] = j < p.n ? p.gamma[j] : 0.0;
+      sA[tid] = (j < p.n && p.p == 1) ? p.avec[j] : 0.0;
+    }
+    if (gen)
+      for (int idx = tid; idx < C::JT * C::KW; idx += GR_THREADS) {
+        const int jj = idx / C::KW, k = idx % C::KW, j = j0 + jj;
+        sB[idx] = (j < p.n && k < p.p) ? p.Bhat[(int64_t)j * MGP_TP + k] : 0.0;
+      }
+    __syncthreads();
+    const int jend = min(C::JT, p.n - j0);
+    for (int jj = g; jj < jend; jj += C::NG) {
+      const int j = j0 + jj;
+      const int64_t o = (int64_t)(j >> 3) * 1024 + (j & 7);
+      const double r = rbase[o], w = wbase[o];
+      q = fma(r, w, q);
+      const double *xj = sX + jj * C::DPW + s * DPS;
+      double e = r;
+      double df[DPS];
+      double S = 0.0;
 #pragma unroll
-    for (int i = 0; i < DP; i++) {
-      df[i] = xs[i] - xj[i];
-      if (CORR == 1) S = fma(th[i] * df[i], df[i], S);
-      // absolute exponential: r_dx = -theta_i sign(D_i) r  (gpr.py:606-607; numpy sign(0) = 0)
-      if (CORR == 2) df[i] = df[i] > 0.0 ? 1.0 : (df[i] < 0.0 ? -1.0 : 0.0);
-    }
-    double e = r;
-    if (CORR == 1) {
-      if (S == 0.0) coincide = 1;
-      e = exp(-MGP_SQRT3 * sqrt(S));
-    }
-    double proj = 0.0;    // (Ahat kappa)_j: Bhat_j . u for a general trend, kappa a_j for the constant one
-    if (gen) {
-      const double *bj = p.Bhat + (int64_t)j * MGP_TP;
-      for (int k = 0; k < p.p; k++) proj = fma(bj[k], s_u[cc][k], proj);
-    } else if (p.p == 1) {
-      proj = kappa * p.avec[j];
-    }
-    const double cm = p.gamma[j] * e, cs = (proj - w) * e;
+      for (int i = 0; i < DPS; i += 2) {
+        const double2 x2 = *reinterpret_cast<const double2 *>(xj + i);
+        df[i] = xs[i] - x2.x;
+        df[i + 1] = xs[i + 1] - x2.y;
+        if (CORR == 1) { S = fma(df[i], df[i], S); S = fma(df[i + 1], df[i + 1], S); }
+        if (CORR == 2) {
+          // absolute exponential: r_dx = -theta_i sign(D_i) r  (gpr.py:606-607; numpy sign(0) = 0)
+          df[i] = df[i] > 0.0 ? 1.0 : (df[i] < 0.0 ? -1.0 : 0.0);
+          df[i + 1] = df[i + 1] > 0.0 ? 1.0 : (df[i + 1] < 0.0 ? -1.0 : 0.0);
+        }
+      }
+      double proj = 0.0;    // (Ahat kappa)_j: Bhat_j . u for a general trend, kappa a_j for the constant one
+      if (gen) {
+        const double *bj = sB + jj * C::KW + s * C::KS, *uj = sU + cl * C::KW + s * C::KS;
 #pragma unroll
-    for (int i = 0; i < DP; i++) {
-      am[i] = fma(cm, df[i], am[i]);
-      as[i] = fma(cs, df[i], as[i]);
+        for (int kk = 0; kk < C::KS; kk++) proj = fma(bj[kk], uj[kk], proj);
+      } else if (p.p == 1) {
+        proj = kappa * sA[jj];
+      }
+      if (LPC > 1) {        // the other slices of this candidate sit in the adjacent lanes
+#pragma unroll
+        for (int o2 = 1; o2 < LPC; o2 <<= 1) {
+          if (CORR == 1) S += __shfl_xor_sync(gmask, S, o2);
+          if (gen) proj += __shfl_xor_sync(gmask, proj, o2);
+        }
+      }
+      if (CORR == 1) {
+        if (S == 0.0) coincide = 1;
+        e = exp(-MGP_SQRT3 * sqrt(S));
+      }
+      const double cm = sG[jj] * e, cs = (proj - w) * e;
+#pragma unroll
+      for (int i = 0; i < DPS; i++) {
+        am[i] = fma(cm, df[i], am[i]);
+        as[i] = fma(cs, df[i], as[i]);
+      }
     }
   }
   if (WIDE) {
-    // warp sums -> shared memory -> every warp's lane 0 holds the block total (fixed order), the
-    // other lanes hold zero, so that the warp-level reductions below return the totals
-    double cf = (double)coincide;
+    // row-group sums -> shared memory; thread v then adds ONE of the LPC x RED quantities over the
+    // row groups in a fixed order (parallel over the quantities, 128 / LPC terms each), row group 0
+    // picks the totals up
+    double *mine = sR + tid * C::RED;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-      cf += __shfl_xor_sync(0xffffffffu, cf, o);
-    }
-#pragma unroll
-    for (int i = 0; i < DP; i++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        am[i] += __shfl_xor_sync(0xffffffffu, am[i], o);
-        as[i] += __shfl_xor_sync(0xffffffffu, as[i], o);
-      }
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < DP; i++) { s_red[cc][2 * i] = am[i]; s_red[cc][2 * i + 1] = as[i]; }
-      s_red[cc][2 * DP] = q;
-      s_red[cc][2 * DP + 1] = cf;
+    for (int i = 0; i < DPS; i++) { mine[2 * i] = am[i]; mine[2 * i + 1] = as[i]; }
+    mine[2 * DPS] = q;
+    mine[2 * DPS + 1] = (double)coincide;
+    __syncthreads();
+    double *tot = sX;                               // the row tiles are consumed: reuse their space
+    for (int v = tid; v < LPC * C::RED; v += GR_THREADS) {
+      const int s2 = v / C::RED, idx = v % C::RED;
+      double t = 0.0;
+      for (int gg = 0; gg < C::NG; gg++) t += sR[(gg * LPC + s2) * C::RED + idx];
+      tot[v] = t;
     }
     __syncthreads();
-    if (cc != 0) return;           // warp 0 finishes the candidate
-    double tq = 0.0, tc = 0.0;
-    for (int w = 0; w < 8; w++) { tq += s_red[w][2 * DP]; tc += s_red[w][2 * DP + 1]; }
-    q = lane == 0 ? tq : 0.0;
-    coincide = tc > 0.0 ? 1 : 0;
+    if (g != 0) return;
+    const double *o = tot + s * C::RED;
 #pragma unroll
-    for (int i = 0; i < DP; i++) {
-      double ta = 0.0, tb = 0.0;
-      for (int w = 0; w < 8; w++) { ta += s_red[w][2 * i]; tb += s_red[w][2 * i + 1]; }
-      am[i] = lane == 0 ? ta : 0.0;
-      as[i] = lane == 0 ? tb : 0.0;
-    }
+    for (int i = 0; i < DPS; i++) { am[i] = o[2 * i]; as[i] = o[2 * i + 1]; }
+    q = o[2 * DPS];
+    coincide = o[2 * DPS + 1] > 0.0 ? 1 : 0;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-    coincide |= __shfl_xor_sync(0xffffffffu, coincide, o);
-  }
+  if (!valid) return;
   const double fac = CORR == 0 ? -2.0 : (CORR == 1 ? -3.0 : -1.0);
   double mean = p.beta + md;
   double u2 = 0.0;
@@ -889,67 +961,82 @@ __global__ void __launch_bounds__(256) k_grad(GradParams p) {
   }
   const double mse = fabs(p.sigma2 * (1.0 - q + u2));
   const double sd = sqrt(mse);
-  if (lane == 0) {
+  if (s == 0) {
     if (p.out_mean) p.out_mean[c] = mean;
     if (p.out_mse) p.out_mse[c] = mse;
   }
-  // lane i ends up owning component i (static indices keep am/as in registers)
-  double my_m = 0.0, my_s = 0.0;
+  const double yhat = p.minimize ? mean : -mean;
+  const double plug = p.minimize ? p.plugin : -p.plugin;
+  // a Matern candidate on a training point zeroes the whole Jacobian (gpr.py:588-615)
+  double gm[DPS], gs[DPS];
 #pragma unroll
-  for (int i = 0; i < DP; i++) {
-    double a = am[i], b = as[i];
+  for (int i = 0; i < DPS; i++) {
+    const int f = s * DPS + i;
+    const double th = f < p.dpad ? p.theta[f] : 0.0;
+    const double cf = CORR == 2 ? th : sqrt(th);
+    gm[i] = coincide ? 0.0 : fac * cf * am[i];
+    gs[i] = coincide ? 0.0 : 2.0 * p.sigma2 * fac * cf * as[i];
+    if (p.p > 1 && f < p.d) {
+      // linear trend: f_dx = [0; I] (trend.py:106-109): beta^T f_dx = beta_{1+i} (gpr.py:539) and
+      // u^T (Ft^T Ft)^-1 (-f_dx) = -kappa_{1+i} (gpr.py:548-551); both survive a zeroed r_dx
+      gm[i] += p.betav[1 + f];
+      if (gen) gs[i] -= 2.0 * p.sigma2 * sK[cl * C::KW + 1 + f];
+    }
+    if (f < p.d) {
+      if (p.out_mean_dx) p.out_mean_dx[c * p.d + f] = gm[i];
+      if (p.out_mse_dx) p.out_mse_dx[c * p.d + f] = gs[i];
+    }
+  }
+  for (int st = 0; st < p.n_sets; st++) {
+    const Acq a2 = acq_eval(p.kind, p.params[st], plug, yhat, sd, p.sigma2);
+    if (p.out_dx) {
+      const bool dead = a2.A == 0.0 && a2.B == 0.0;     // guarded points: zero gradient
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    if ((i & 31) == lane) {
-      my_m = coincide ? 0.0 : fac * th[i] * a;
-      my_s = coincide ? 0.0 : 2.0 * p.sigma2 * fac * th[i] * b;
-      if (p.p > 1 && i < p.d) {
-        // linear trend: f_dx = [0; I] (trend.py:106-109): beta^T f_dx = beta_{1+i} (gpr.py:539) and
-        // u^T (Ft^T Ft)^-1 (-f_dx) = -kappa_{1+i} (gpr.py:548-551); both survive a zeroed r_dx
-        my_m += p.betav[1 + i];
-        if (gen) my_s -= 2.0 * p.sigma2 * s_k[cc][1 + i];
-      }
-    }
-    if (i % 32 == 31 || i == DP - 1) {
-      const int comp = (i / 32) * 32 + lane;
-      if (comp < p.d && comp <= i) {
-        if (p.out_mean_dx) p.out_mean_dx[c * p.d + comp] = my_m;
-        if (p.out_mse_dx) p.out_mse_dx[c * p.d + comp] = my_s;
-        if (p.n_sets > 0) {
-          const double yhat = p.minimize ? mean : -mean;
-          const double ydx = p.minimize ? my_m : -my_m;
-          const double plug = p.minimize ? p.plugin : -p.plugin;
-          const double sd_dx = my_s / (2.0 * sd);
-          for (int s = 0; s < p.n_sets; s++) {
-            const Acq a2 = acq_eval(p.kind, p.params[s], plug, yhat, sd, p.sigma2);
-            if (p.out_dx) {
-              double g = a2.A * ydx + a2.B * sd_dx;
-              if (a2.A == 0.0 && a2.B == 0.0) g = 0.0;  // guarded (dead) points: zero gradient
-              p.out_dx[((int64_t)s * p.ld_val + c) * p.d + comp] = g;
-            }
-            if (p.out_val && comp == 0) p.out_val[(int64_t)s * p.ld_val + c] = a2.val;
-          }
+      for (int i = 0; i < DPS; i++) {
+        const int f = s * DPS + i;
+        if (f < p.d) {
+          const double ydx = p.minimize ? gm[i] : -gm[i];
+          const double sd_dx = gs[i] / (2.0 * sd);
+          p.out_dx[((int64_t)st * p.ld_val + c) * p.d + f] = dead ? 0.0 : a2.A * ydx + a2.B * sd_dx;
         }
       }
     }
+    if (p.out_val && s == 0) p.out_val[(int64_t)st * p.ld_val + c] = a2.val;
   }
+}
+
+template <int CORR, int DPS, int LPC, bool WIDE>
+static cudaError_t grad_launch(const GradParams &p, cudaStream_t st) {
+  using C = GradCfg<DPS, LPC, WIDE>;
+  const bool gen = p.p > 1 && p.trend_est;
+  const int smem = C::smem_doubles(gen) * (int)sizeof(double);
+  static int smem_set[MGP_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = dev < 0 || dev >= MGP_MAX_DEVICES ? 0 : dev;
+  if (smem > smem_set[dev]) {
+    cudaFuncSetAttribute(k_grad<CORR, DPS, LPC, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    smem_set[dev] = smem;
+  }
+  const unsigned grid = WIDE ? (unsigned)p.mc : (unsigned)((p.mc + C::NCAND - 1) / C::NCAND);
+  k_grad<CORR, DPS, LPC, WIDE><<<grid, GR_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
 }
 
 template <int CORR>
 static cudaError_t grad_dispatch(const GradParams &p, cudaStream_t st) {
   const bool wide = p.wide != 0 && p.mc <= 8;
-  const unsigned grid = wide ? (unsigned)p.mc : (unsigned)((p.mc + 7) / 8);
-  switch (p.dpad) {
-#define GD(D) case D: if (wide) k_grad<CORR, D, true><<<grid, 256, 0, st>>>(p); \
-                      else k_grad<CORR, D, false><<<grid, 256, 0, st>>>(p); break;
-    GD(4) GD(8) GD(12) GD(16) GD(20) GD(24) GD(28) GD(32) GD(36) GD(40) GD(44) GD(48) GD(52) GD(56) GD(60) GD(64)
+#define GD(S, L) return wide ? grad_launch<CORR, S, L, true>(p, st) : grad_launch<CORR, S, L, false>(p, st)
+  if (p.dpad <= 4) GD(4, 1);
+  if (p.dpad <= 8) GD(8, 1);
+  if (p.dpad <= 12) GD(12, 1);
+  if (p.dpad <= 16) GD(16, 1);
+  if (p.dpad <= 24) GD(12, 2);
+  if (p.dpad <= 32) GD(16, 2);
+  if (p.dpad <= 48) GD(12, 4);
+  if (p.dpad <= 64) GD(16, 4);
 #undef GD
-    default: return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace

@@ -171,6 +171,77 @@ def test_device_and_host_entry_points_interleave_without_explicit_sync():
         assert np.all(np.isfinite(mean_b))
 
 
+# ---- CUDA graphs of the batched likelihood ---------------------------------------------------------------
+def test_likelihood_graphs_are_bitwise_the_eager_path():
+    """A batch shape is captured in a CUDA graph at its second use and replayed afterwards (host
+    and device entry points, one and several batch groups): every value is bitwise what the
+    launch-by-launch path gives; new training data, a different batch size or appended rows
+    never reuse a stale graph."""
+    import torch
+    mb, O = _mods()
+    d = 6
+    X, y, rng = _data(1400, d, 21)
+    theta = (0.4 / d) * rng.uniform(0.5, 1.5, d)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential", theta0=theta,
+                            thetaL=[1e-5] * d, thetaU=[100.0] * d, nugget=1e-6)
+    gp._check_data(X[:1300], y[:1300])
+    h = gp._handle()
+
+    def draw(B):
+        return np.c_[theta * rng.uniform(0.6, 1.6, (B, d)), rng.uniform(0.5, 1.0, B)]
+    for B in (6, 3):
+        h.set_option("nll_graphs", 0)
+        Ps = [draw(B) for _ in range(4)]
+        eager = [gp.log_likelihood_batch(P) for P in Ps]
+        h.set_option("nll_graphs", 1)
+        r0 = h.counter("graph_replays")
+        for rep in range(2):
+            for P, e in zip(Ps, eager):
+                llf, grad, status = gp.log_likelihood_batch(P)
+                assert np.array_equal(llf, e[0]) and np.array_equal(grad, e[1]) and np.array_equal(status, e[2])
+        assert h.counter("graph_replays") - r0 == 7           # first call eager, the rest replayed
+        l_ng = gp.log_likelihood_batch(Ps[0], eval_grad=False)[0]     # another shape (no gradient)
+        assert np.array_equal(l_ng, eager[0][0])
+    # device entry point on a user stream: the caller's tensors change, the graph does not
+    side = torch.cuda.Stream()
+    Pd = [torch.from_numpy(P).cuda() for P in Ps]
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        outs = [gp.log_likelihood_batch_device(P) for P in Pd for _ in range(2)]
+    side.synchronize()
+    for k, o in enumerate(outs):
+        e = eager[k // 2]
+        assert np.array_equal(o[0].cpu().numpy(), e[0]) and np.array_equal(o[1].cpu().numpy(), e[1])
+    # a failing element inside a replayed batch still reports its status (noiseless model: theta -> 0
+    # makes R singular, gpr.py:820-826)
+    nl = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="squared_exponential", theta0=theta,
+                            thetaL=[1e-12] * d, thetaU=[100.0] * d)
+    nl._check_data(X[:300], y[:300])
+    bad = np.vstack([20 * theta, np.full(d, 1e-12), 30 * theta])
+    outs = [nl.log_likelihood_batch(bad) for _ in range(3)]
+    assert nl._handle().counter("graph_replays") == 2
+    for llf, grad, status in outs:
+        assert status[1] > 0 and np.isinf(llf[1]) and np.all(grad[1] == 0) and status[0] == 0 and status[2] == 0
+        assert np.array_equal(llf, outs[0][0]) and np.array_equal(grad, outs[0][1])
+    # new data: same shapes, fresh graphs
+    gp._check_data(X, y)
+    ref = O.log_likelihood_concentrated(X, y, Ps[0][0], "squared_exponential", True, 0.0, "noisy", 1e-6)
+    for _ in range(3):
+        llf = gp.log_likelihood_batch(Ps[0])[0]
+        assert abs(llf[0] - ref) <= 1e-9 * abs(ref)
+    # many groups (n = 4096 uses 8 streams): eager == replay
+    Xb, yb, rb = _data(2700, d, 22)
+    big = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="matern", theta0=theta, thetaL=[1e-5] * d,
+                             thetaU=[100.0] * d, nugget=1e-6)
+    big._check_data(Xb, yb)
+    P = np.c_[4 * theta * rb.uniform(0.6, 1.6, (8, d)), rb.uniform(0.5, 1.0, 8)]
+    first = big.log_likelihood_batch(P)
+    for _ in range(3):
+        again = big.log_likelihood_batch(P)
+        assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])
+    assert big._handle().counter("graph_replays") == 3          # four calls: eager, capture + replay, replay, replay
+
+
 # ---- pickling keeps the full hyper-parameter vector ---------------------------------------------------
 @pytest.mark.parametrize("lik,noise_estim,nugget", [("concentrated", False, 1e-4), ("restricted", False, 0),
                                                     ("restricted", True, 0), ("concentrated", True, 0)])
