@@ -153,7 +153,7 @@ int mgp_destroy(mgp_t *h) {
   cudaDeviceSynchronize();
   mgp_comm_destroy(h);
   nll_graphs_clear(h);
-  DevBuf *all[] = {&h->dtpart, &h->dXc, &h->dy, &h->dcenter, &h->dtheta, &h->dBop, &h->dan, &h->dL, &h->dMinv,
+  DevBuf *all[] = {&h->dtpart, &h->dXc, &h->dy, &h->dcenter, &h->dtheta, &h->dBop, &h->dan, &h->dXsc, &h->dL, &h->dMinv,
                    &h->dTmp, &h->dMp, &h->dRinvP, &h->dgamma, &h->davec, &h->dFt,
                    &h->dYt, &h->drho, &h->dscal, &h->drP, &h->dmeanpart, &h->dftpart, &h->dqpart,
                    &h->dwP, &h->dXs_stage[0], &h->dXs_stage[1], &h->dout_stage[0],
@@ -671,6 +671,7 @@ int mgp_model_alloc(mgp_handle *h) {
   MGP_TRY(mgp_ensure(h, h->dtheta, (size_t)h->dpad * 8));
   MGP_TRY(mgp_ensure(h, h->dBop, (size_t)h->npad * h->dpad * 8));
   MGP_TRY(mgp_ensure(h, h->dan, vec));
+  MGP_TRY(mgp_ensure(h, h->dXsc, (size_t)h->npad * grad_row_stride(h->dpad) * 8));
   MGP_TRY(mgp_ensure(h, h->dgamma, vec));
   MGP_TRY(mgp_ensure(h, h->davec, vec));
   MGP_TRY(mgp_ensure(h, h->dFt, vec));
@@ -721,7 +722,7 @@ static int adopt_slot0(mgp_handle *h, const double *theta_host, bool take_gamma)
   for (int i = 0; i < h->d; i++) th[i] = theta_host[i];
   MGP_CUDA(h, cudaMemcpyAsync(h->dtheta.p, th.data(), th.size() * 8, cudaMemcpyHostToDevice, st));
   MGP_CUDA(h, launch_prep_model(P<double>(h->dXc), P<double>(h->dtheta), h->npad, h->dpad,
-                                P<double>(h->dBop), P<double>(h->dan), st));
+                                P<double>(h->dBop), P<double>(h->dan), P<double>(h->dXsc), h->corr, st));
   MGP_CUDA(h, launch_pack_tri(P<double>(h->dMinv), h->n, h->npad, P<double>(h->dMp), st));
   h->launches += 3;
   MGP_CUDA(h, cudaStreamSynchronize(st));  // th is a host temporary
@@ -1202,7 +1203,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       }
       GradParams gp;
       gp.Xs = q.d_Xs + c0 * h->d; gp.mc = mc; gp.ldp = ldp; gp.n = h->n; gp.d = h->d; gp.dpad = h->dpad;
-      gp.NJ8 = NJ8; gp.Xc = P<double>(h->dXc); gp.center = P<double>(h->dcenter);
+      gp.NJ8 = NJ8; gp.Xc = P<double>(h->dXc); gp.center = P<double>(h->dcenter); gp.Xsc = P<double>(h->dXsc);
       gp.theta = P<double>(h->dtheta); gp.gamma = P<double>(h->dgamma); gp.avec = P<double>(h->davec);
       gp.rP = P<double>(h->drP); gp.wP = P<double>(h->dwP);
       gp.meanpart = P<double>(h->dmeanpart); gp.ftpart = P<double>(h->dftpart); gp.JS = JS;

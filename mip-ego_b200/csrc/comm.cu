@@ -207,7 +207,7 @@ int mgp_bcast_model(mgp_t *h, int root) {
   struct Item { DevBuf *b; size_t count; };
   std::vector<Item> items = {{&h->dtheta, (size_t)h->dpad}, {&h->dL, mat}, {&h->dMinv, mat},
                              {&h->dMp, (size_t)8 * h->NI * (h->NI + 1) * 1024}, {&h->dBop, vec * h->dpad},
-                             {&h->dan, vec}, {&h->dgamma, vec}, {&h->davec, vec}, {&h->dFt, vec}, {&h->dYt, vec},
+                             {&h->dan, vec}, {&h->dXsc, vec * grad_row_stride(h->dpad)}, {&h->dgamma, vec}, {&h->davec, vec}, {&h->dFt, vec}, {&h->dYt, vec},
                              {&h->drho, vec}};
   if (h->p > 1) {
     MGP_TRY(mgp_ensure(h, h->dbetav, MGP_PMAX * 8));

@@ -72,6 +72,7 @@ struct mgp_handle {
   DevBuf dtheta;   // dpad
   DevBuf dBop;     // npad x dpad : -2 theta_i xc_ji
   DevBuf dan;      // npad        : sum_i theta_i xc_ji^2
+  DevBuf dXsc;     // npad x grad_row_stride(dpad): sqrt(theta_i) xc_ji (gradient kernel)
   DevBuf dL;       // npad x npad row-major lower Cholesky factor
   DevBuf dMinv;    // npad x npad row-major L^-1
   DevBuf dTmp;     // npad x npad scratch

@@ -19,8 +19,10 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // per-fit operand preparation
 // ---------------------------------------------------------------------------------------------
+// Xsc: the training coordinates scaled by c_i = sqrt(theta_i) (theta_i for the absolute-exponential
+// kernel), row stride xstride >= dpad, zero padded: the operand of the gradient kernel K5.
 __global__ void k_prep_model(const double *Xc, const double *theta, int npad, int dpad, double *Bop,
-                             double *an) {
+                             double *an, double *Xsc, int xstride, int corr) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= npad) return;
   double s = 0.0;
@@ -28,7 +30,9 @@ __global__ void k_prep_model(const double *Xc, const double *theta, int npad, in
     const double x = Xc[(int64_t)j * dpad + i], t = theta[i];
     Bop[(int64_t)j * dpad + i] = -2.0 * t * x;
     s = fma(t * x, x, s);
+    Xsc[(int64_t)j * xstride + i] = (corr == MGP_CORR_ABSEXP ? t : sqrt(t)) * x;
   }
+  for (int i = dpad; i < xstride; i++) Xsc[(int64_t)j * xstride + i] = 0.0;
   an[j] = s;
 }
 
@@ -747,48 +751,51 @@ __global__ void __launch_bounds__(1024) k_topk_merge(const double *vals, const i
 // One warp per candidate; lanes stride over the training points; D = x* - x_j component-wise.
 // A Matern candidate coinciding with a training point zeroes the whole Jacobian (gpr.py:588-615).
 // ---------------------------------------------------------------------------------------------
-// Work decomposition.  A thread owns ONE candidate (its accumulators never leave registers and
-// nothing is reduced across lanes at the end) and a SLICE of DPS <= 16 features; LPC = 1, 2 or 4
-// adjacent lanes share a candidate when dpad > 16, so that 3 x DPS doubles of state fit the register
-// file for every d <= 64 (the previous warp-per-candidate kernel kept 5 x DP doubles per lane and
-// spilled 0.5 - 6 KB per thread for DP >= 24).  The training rows stream through shared memory in
-// tiles of 32 rows, pre-scaled by c_i = sqrt(theta_i) (theta_i for the absolute-exponential kernel),
-// and are read as broadcasts; r and W = R^-1 r come straight from their packed tiles, 16-byte loads
-// that are contiguous across the CTA.  Only the Matern distance (and the trend projection of a
-// general basis) needs the other slices: one or two shuffles per row.
-// WIDE (populations of at most 8, the one-point-per-call pattern): one CTA per candidate, its
-// 128 / LPC row groups split the rows of a tile and combine their sums through shared memory in a
-// fixed order.
+// Work decomposition.  A thread owns ONE candidate (its accumulators never leave registers) and a
+// SLICE of DPS <= 16 features; LPC = 1, 2 or 4 adjacent lanes share a candidate when dpad > 16, so
+// that 3 x DPS doubles of state fit the register file for every d <= 64 (the previous
+// warp-per-candidate kernel kept 5 x DP doubles per lane and spilled 0.5 - 6 KB per thread for
+// DP >= 24).  The training rows stream through shared memory in tiles, pre-scaled by
+// c_i = sqrt(theta_i) (theta_i for the absolute-exponential kernel), and are read as broadcasts;
+// r and W = R^-1 r come straight from their packed tiles.  Only the Matern distance (and the trend
+// projection of a general basis) needs the other slices: one or two shuffles per row.
+// NG row groups per candidate split the rows of a tile and combine their sums through shared memory
+// in a fixed order: NG = 1 for large populations (128 / LPC candidates per CTA, nothing to combine),
+// NG = 8 for a few thousand candidates, NG = 128 / LPC (one CTA per candidate) below that and for the
+// one-point-per-call pattern -- enough CTAs to fill the machine at every population size.
 constexpr int GR_THREADS = 128;
-template <int DPS, int LPC, bool WIDE>
+template <int DPS, int LPC, int NGSEL>     // NGSEL: 0 -> NG = 1, 1 -> NG = 8, 2 -> NG = 128 / LPC
 struct GradCfg {
-  static constexpr int JT = WIDE ? 128 : 32;                  // training rows per shared-memory tile
+  static constexpr int NG = NGSEL == 0 ? 1 : (NGSEL == 1 ? 8 : GR_THREADS / LPC);   // row groups
+  static constexpr int NCAND = GR_THREADS / (LPC * NG);       // candidates per CTA
+  static constexpr int JT = 32;                               // training rows per shared-memory tile (NG == 1)
   static constexpr int DPW = DPS * LPC;                       // padded feature width
   static constexpr int KS = DPS + 1;                          // trend coefficients per slice
   static constexpr int KW = KS * LPC;
-  static constexpr int NG = WIDE ? GR_THREADS / LPC : 1;      // row groups
-  static constexpr int NCAND = WIDE ? 1 : GR_THREADS / LPC;   // candidates per CTA
   static constexpr int RED = 2 * DPS + 2;                     // per thread: am | as | q | coincide
   static int smem_doubles(bool gen) {
-    return JT * DPW + 2 * JT + (gen ? JT * KW + 2 * NCAND * KW : 0) + (WIDE ? GR_THREADS * RED : 0);
+    const int tile = NG == 1 ? JT * DPW + 2 * JT + (gen ? JT * KW : 0) : NCAND * LPC * RED;   // NG > 1: the totals
+    return tile + (gen ? 2 * NCAND * KW : 0) + (NG > 1 ? GR_THREADS * RED : 0);
   }
 };
 
-template <int CORR, int DPS, int LPC, bool WIDE>
-__global__ void __launch_bounds__(GR_THREADS) k_grad(GradParams p) {
-  using C = GradCfg<DPS, LPC, WIDE>;
+template <int CORR, int DPS, int LPC, int NGSEL>
+__global__ void __launch_bounds__(GR_THREADS, 2) k_grad(GradParams p) {
+  using C = GradCfg<DPS, LPC, NGSEL>;
+  constexpr bool WIDE = C::NG > 1;
   extern __shared__ __align__(16) double gsm[];
   const bool gen = p.p > 1 && p.trend_est;
-  double *sX = gsm;                                 // [JT][DPW] scaled training coordinates
-  double *sG = sX + C::JT * C::DPW;                 // [JT] gamma
-  double *sA = sG + C::JT;                          // [JT] a = L^-T Ft (constant trend)
-  double *sB = sA + C::JT;                          // [JT][KW] Bhat rows           (general trend)
-  double *sU = sB + (gen ? C::JT * C::KW : 0);      // [NCAND][KW] u = Bhat^T r - Cinv f
+  constexpr int TILE = C::NG == 1 ? C::JT * C::DPW + 2 * C::JT : C::NCAND * LPC * C::RED;
+  double *sX = gsm;                                 // NG == 1: [JT][DPW] scaled rows; NG > 1: the totals
+  double *sG = sX + C::JT * C::DPW;                 // [JT] gamma                   (NG == 1)
+  double *sA = sG + C::JT;                          // [JT] a = L^-T Ft             (NG == 1)
+  double *sB = gsm + TILE;                          // [JT][KW] Bhat rows           (NG == 1, general trend)
+  double *sU = sB + ((gen && C::NG == 1) ? C::JT * C::KW : 0);   // [NCAND][KW] u = Bhat^T r - Cinv f
   double *sK = sU + (gen ? C::NCAND * C::KW : 0);   // [NCAND][KW] kappa = C^-T u
   double *sR = sK + (gen ? C::NCAND * C::KW : 0);   // [THREADS][RED] row-group partial sums (WIDE)
   const int tid = threadIdx.x, s = tid % LPC, grp = tid / LPC;
-  const int cl = WIDE ? 0 : grp, g = WIDE ? grp : 0;
-  const int64_t c = WIDE ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * C::NCAND + cl;
+  const int g = grp % C::NG, cl = grp / C::NG;     // row group, candidate within the CTA
+  const int64_t c = (int64_t)blockIdx.x * C::NCAND + cl;
   const bool valid = c < p.mc;
   const int64_t cv = valid ? c : 0;                 // invalid threads shadow candidate 0, write nothing
   const int cb = (int)(cv >> 7), c8 = (int)((cv >> 3) & 15), crow = (int)(cv & 7);
@@ -847,81 +854,100 @@ __global__ void __launch_bounds__(GR_THREADS) k_grad(GradParams p) {
   const double *rbase = p.rP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + crow * 8;
   const double *wbase = p.wP + ((int64_t)cb * p.NJ8 * 16 + c8) * 64 + crow * 8;
 
-  for (int j0 = 0; j0 < p.n; j0 += C::JT) {
-    __syncthreads();                                // previous tile consumed
-    for (int idx = tid; idx < C::JT * C::DPW; idx += GR_THREADS) {
-      const int jj = idx / C::DPW, f = idx % C::DPW, j = j0 + jj;
-      double v = 0.0;
-      if (j < p.n && f < p.dpad) {
-        const double th = p.theta[f];
-        v = (CORR == 2 ? th : sqrt(th)) * p.Xc[(int64_t)j * p.dpad + f];
+  // one training row: r, w = its entries of r and R^-1 r; xj = this slice of the scaled row;
+  // gam, aj = gamma_j, a_j; bj = this slice of Bhat_j (general trend)
+  auto row = [&](double r, double w, const double *xj, double gam, double aj, const double *bj) {
+    q = fma(r, w, q);
+    double e = r;
+    double df[DPS];
+    double S = 0.0;
+#pragma unroll
+    for (int i = 0; i < DPS; i += 2) {
+      const double2 x2 = *reinterpret_cast<const double2 *>(xj + i);
+      df[i] = xs[i] - x2.x;
+      df[i + 1] = xs[i + 1] - x2.y;
+      if (CORR == 1) { S = fma(df[i], df[i], S); S = fma(df[i + 1], df[i + 1], S); }
+      if (CORR == 2) {
+        // absolute exponential: r_dx = -theta_i sign(D_i) r  (gpr.py:606-607; numpy sign(0) = 0)
+        df[i] = df[i] > 0.0 ? 1.0 : (df[i] < 0.0 ? -1.0 : 0.0);
+        df[i + 1] = df[i + 1] > 0.0 ? 1.0 : (df[i + 1] < 0.0 ? -1.0 : 0.0);
       }
-      sX[idx] = v;
     }
-    if (tid < C::JT) {
-      const int j = j0 + tid;
-      sG[tid] = j < p.n ? p.gamma[j] : 0.0;
-      sA[tid] = (j < p.n && p.p == 1) ? p.avec[j] : 0.0;
+    double proj = 0.0;    // (Ahat kappa)_j: Bhat_j . u for a general trend, kappa a_j for the constant one
+    if (gen) {
+      const double *uj = sU + cl * C::KW + s * C::KS;
+#pragma unroll
+      for (int kk = 0; kk < C::KS; kk++) proj = fma(bj[kk], uj[kk], proj);
+    } else if (p.p == 1) {
+      proj = kappa * aj;
     }
-    if (gen)
-      for (int idx = tid; idx < C::JT * C::KW; idx += GR_THREADS) {
-        const int jj = idx / C::KW, k = idx % C::KW, j = j0 + jj;
-        sB[idx] = (j < p.n && k < p.p) ? p.Bhat[(int64_t)j * MGP_TP + k] : 0.0;
-      }
-    __syncthreads();
-    const int jend = min(C::JT, p.n - j0);
-    for (int jj = g; jj < jend; jj += C::NG) {
-      const int j = j0 + jj;
-      const int64_t o = (int64_t)(j >> 3) * 1024 + (j & 7);
-      const double r = rbase[o], w = wbase[o];
-      q = fma(r, w, q);
-      const double *xj = sX + jj * C::DPW + s * DPS;
-      double e = r;
-      double df[DPS];
-      double S = 0.0;
+    if (LPC > 1) {        // the other slices of this candidate sit in the adjacent lanes
 #pragma unroll
-      for (int i = 0; i < DPS; i += 2) {
-        const double2 x2 = *reinterpret_cast<const double2 *>(xj + i);
-        df[i] = xs[i] - x2.x;
-        df[i + 1] = xs[i + 1] - x2.y;
-        if (CORR == 1) { S = fma(df[i], df[i], S); S = fma(df[i + 1], df[i + 1], S); }
-        if (CORR == 2) {
-          // absolute exponential: r_dx = -theta_i sign(D_i) r  (gpr.py:606-607; numpy sign(0) = 0)
-          df[i] = df[i] > 0.0 ? 1.0 : (df[i] < 0.0 ? -1.0 : 0.0);
-          df[i + 1] = df[i + 1] > 0.0 ? 1.0 : (df[i + 1] < 0.0 ? -1.0 : 0.0);
+      for (int o2 = 1; o2 < LPC; o2 <<= 1) {
+        if (CORR == 1) S += __shfl_xor_sync(gmask, S, o2);
+        if (gen) proj += __shfl_xor_sync(gmask, proj, o2);
+      }
+    }
+    if (CORR == 1) {
+      if (S == 0.0) coincide = 1;
+      e = exp(-MGP_SQRT3 * sqrt(S));
+    }
+    const double cm = gam * e, cs = (proj - w) * e;
+#pragma unroll
+    for (int i = 0; i < DPS; i++) {
+      am[i] = fma(cm, df[i], am[i]);
+      as[i] = fma(cs, df[i], as[i]);
+    }
+  };
+  if (C::NG == 1) {
+    // large populations: the rows pass through shared memory in tiles and are read as broadcasts
+    for (int j0 = 0; j0 < p.n; j0 += C::JT) {
+      __syncthreads();                                // previous tile consumed
+      const int jend = min(C::JT, p.n - j0);
+      {
+        const double2 *src = reinterpret_cast<const double2 *>(p.Xsc + (int64_t)j0 * C::DPW);
+        double2 *dst = reinterpret_cast<double2 *>(sX);
+        for (int idx = tid; idx < jend * C::DPW / 2; idx += GR_THREADS) dst[idx] = src[idx];
+      }
+      if (tid < jend) {
+        sG[tid] = p.gamma[j0 + tid];
+        sA[tid] = p.p == 1 ? p.avec[j0 + tid] : 0.0;
+      }
+      if (gen)
+        for (int idx = tid; idx < jend * C::KW; idx += GR_THREADS) {
+          const int jj = idx / C::KW, k = idx % C::KW;
+          sB[idx] = p.Bhat[(int64_t)(j0 + jj) * MGP_TP + k];
         }
+      __syncthreads();
+      for (int jj = 0; jj < jend; jj++) {
+        const int j = j0 + jj;
+        const int64_t o = (int64_t)(j >> 3) * 1024 + (j & 7);
+        row(rbase[o], wbase[o], sX + jj * C::DPW + s * DPS, sG[jj], sA[jj], sB + jj * C::KW + s * C::KS);
       }
-      double proj = 0.0;    // (Ahat kappa)_j: Bhat_j . u for a general trend, kappa a_j for the constant one
-      if (gen) {
-        const double *bj = sB + jj * C::KW + s * C::KS, *uj = sU + cl * C::KW + s * C::KS;
-#pragma unroll
-        for (int kk = 0; kk < C::KS; kk++) proj = fma(bj[kk], uj[kk], proj);
-      } else if (p.p == 1) {
-        proj = kappa * sA[jj];
-      }
-      if (LPC > 1) {        // the other slices of this candidate sit in the adjacent lanes
-#pragma unroll
-        for (int o2 = 1; o2 < LPC; o2 <<= 1) {
-          if (CORR == 1) S += __shfl_xor_sync(gmask, S, o2);
-          if (gen) proj += __shfl_xor_sync(gmask, proj, o2);
-        }
-      }
-      if (CORR == 1) {
-        if (S == 0.0) coincide = 1;
-        e = exp(-MGP_SQRT3 * sqrt(S));
-      }
-      const double cm = sG[jj] * e, cs = (proj - w) * e;
-#pragma unroll
-      for (int i = 0; i < DPS; i++) {
-        am[i] = fma(cm, df[i], am[i]);
-        as[i] = fma(cs, df[i], as[i]);
-      }
+    }
+  } else {
+    // few candidates: NG row groups per candidate read their rows straight from global memory (the
+    // model is L2 resident), two rows in flight per thread; no tile, no barrier in the loop
+    const double *xb = p.Xsc + s * DPS, *bb = p.Bhat + s * C::KS;
+    int j = g;
+    for (; j + C::NG < p.n; j += 2 * C::NG) {
+      const int j1 = j + C::NG;
+      const int64_t o0 = (int64_t)(j >> 3) * 1024 + (j & 7), o1 = (int64_t)(j1 >> 3) * 1024 + (j1 & 7);
+      const double r0 = rbase[o0], w0 = wbase[o0], r1 = rbase[o1], w1 = wbase[o1];
+      const double g0 = p.gamma[j], g1 = p.gamma[j1];
+      const double a0 = p.p == 1 ? p.avec[j] : 0.0, a1 = p.p == 1 ? p.avec[j1] : 0.0;
+      row(r0, w0, xb + (int64_t)j * C::DPW, g0, a0, bb + (int64_t)j * MGP_TP);
+      row(r1, w1, xb + (int64_t)j1 * C::DPW, g1, a1, bb + (int64_t)j1 * MGP_TP);
+    }
+    if (j < p.n) {
+      const int64_t o0 = (int64_t)(j >> 3) * 1024 + (j & 7);
+      row(rbase[o0], wbase[o0], xb + (int64_t)j * C::DPW, p.gamma[j], p.p == 1 ? p.avec[j] : 0.0,
+          bb + (int64_t)j * MGP_TP);
     }
   }
   if (WIDE) {
-    // row-group sums -> shared memory; thread v then adds ONE of the LPC x RED quantities over the
-    // row groups in a fixed order (parallel over the quantities, 128 / LPC terms each), row group 0
-    // picks the totals up
+    // row-group sums -> shared memory; thread v then adds ONE of the NCAND x LPC x RED quantities over
+    // the NG row groups in a fixed order (parallel over the quantities), row group 0 picks the totals up
     double *mine = sR + tid * C::RED;
 #pragma unroll
     for (int i = 0; i < DPS; i++) { mine[2 * i] = am[i]; mine[2 * i + 1] = as[i]; }
@@ -929,15 +955,16 @@ __global__ void __launch_bounds__(GR_THREADS) k_grad(GradParams p) {
     mine[2 * DPS + 1] = (double)coincide;
     __syncthreads();
     double *tot = sX;                               // the row tiles are consumed: reuse their space
-    for (int v = tid; v < LPC * C::RED; v += GR_THREADS) {
-      const int s2 = v / C::RED, idx = v % C::RED;
+    for (int v = tid; v < C::NCAND * LPC * C::RED; v += GR_THREADS) {
+      const int cs2 = v / C::RED, idx = v % C::RED;   // cs2 = candidate * LPC + slice
+      const int c2 = cs2 / LPC, s2 = cs2 % LPC;
       double t = 0.0;
-      for (int gg = 0; gg < C::NG; gg++) t += sR[(gg * LPC + s2) * C::RED + idx];
+      for (int gg = 0; gg < C::NG; gg++) t += sR[((c2 * C::NG + gg) * LPC + s2) * C::RED + idx];
       tot[v] = t;
     }
     __syncthreads();
     if (g != 0) return;
-    const double *o = tot + s * C::RED;
+    const double *o = tot + (cl * LPC + s) * C::RED;
 #pragma unroll
     for (int i = 0; i < DPS; i++) { am[i] = o[2 * i]; as[i] = o[2 * i + 1]; }
     q = o[2 * DPS];
@@ -1005,9 +1032,9 @@ __global__ void __launch_bounds__(GR_THREADS) k_grad(GradParams p) {
   }
 }
 
-template <int CORR, int DPS, int LPC, bool WIDE>
+template <int CORR, int DPS, int LPC, int NGSEL>
 static cudaError_t grad_launch(const GradParams &p, cudaStream_t st) {
-  using C = GradCfg<DPS, LPC, WIDE>;
+  using C = GradCfg<DPS, LPC, NGSEL>;
   const bool gen = p.p > 1 && p.trend_est;
   const int smem = C::smem_doubles(gen) * (int)sizeof(double);
   static int smem_set[MGP_MAX_DEVICES] = {};
@@ -1015,18 +1042,27 @@ static cudaError_t grad_launch(const GradParams &p, cudaStream_t st) {
   cudaGetDevice(&dev);
   dev = dev < 0 || dev >= MGP_MAX_DEVICES ? 0 : dev;
   if (smem > smem_set[dev]) {
-    cudaFuncSetAttribute(k_grad<CORR, DPS, LPC, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_grad<CORR, DPS, LPC, NGSEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     smem_set[dev] = smem;
   }
-  const unsigned grid = WIDE ? (unsigned)p.mc : (unsigned)((p.mc + C::NCAND - 1) / C::NCAND);
-  k_grad<CORR, DPS, LPC, WIDE><<<grid, GR_THREADS, smem, st>>>(p);
+  const unsigned grid = (unsigned)((p.mc + C::NCAND - 1) / C::NCAND);
+  k_grad<CORR, DPS, LPC, NGSEL><<<grid, GR_THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
 
 template <int CORR>
 static cudaError_t grad_dispatch(const GradParams &p, cudaStream_t st) {
-  const bool wide = p.wide != 0 && p.mc <= 8;
-#define GD(S, L) return wide ? grad_launch<CORR, S, L, true>(p, st) : grad_launch<CORR, S, L, false>(p, st)
+  // enough CTAs for the machine at every population size (148 SMs, 2+ CTAs each).  The row-group
+  // count fixes the order of the sums: values and gradients are bitwise independent of the
+  // population size WITHIN each class (with LPC lanes per candidate: fewer than 4736 / LPC, fewer
+  // than 37 888 / LPC, or more candidates per pass) -- the lock-step optimisers, whose batch shrinks
+  // as trajectories finish, stay inside the first one.
+#define GD(S, L)                                                                        \
+  {                                                                                     \
+    const int64_t w = p.mc * (L);                                                       \
+    return w < 4736 ? grad_launch<CORR, S, L, 2>(p, st)                                 \
+                    : (w < 37888 ? grad_launch<CORR, S, L, 1>(p, st) : grad_launch<CORR, S, L, 0>(p, st)); \
+  }
   if (p.dpad <= 4) GD(4, 1);
   if (p.dpad <= 8) GD(8, 1);
   if (p.dpad <= 12) GD(12, 1);
@@ -1044,9 +1080,12 @@ static cudaError_t grad_dispatch(const GradParams &p, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+int grad_row_stride(int dpad) {   // DPS x LPC of the K5 instantiation that serves this dpad (grad_dispatch)
+  return dpad <= 16 ? dpad : (dpad <= 24 ? 24 : (dpad <= 32 ? 32 : (dpad <= 48 ? 48 : 64)));
+}
 cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, int dpad,
-                              double *Bop, double *an, cudaStream_t st) {
-  k_prep_model<<<(npad + 127) / 128, 128, 0, st>>>(Xc, theta, npad, dpad, Bop, an);
+                              double *Bop, double *an, double *Xsc, int corr, cudaStream_t st) {
+  k_prep_model<<<(npad + 127) / 128, 128, 0, st>>>(Xc, theta, npad, dpad, Bop, an, Xsc, grad_row_stride(dpad), corr);
   return cudaGetLastError();
 }
 

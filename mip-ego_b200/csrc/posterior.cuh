@@ -7,8 +7,11 @@
 #include "nll.cuh"
 
 // Per-fit operand preparation: Bop[j][i] = -2 theta_i xc_ji, an[j] = sum_i theta_i xc_ji^2.
+// Xsc[j][i] = c_i xc_ji with c_i = sqrt(theta_i) (theta_i for the absolute-exponential kernel), row
+// stride grad_row_stride(dpad), zero padded: the training operand of the gradient kernel K5.
+int grad_row_stride(int dpad);
 cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, int dpad,
-                              double *Bop, double *an, cudaStream_t st);
+                              double *Bop, double *an, double *Xsc, int corr, cudaStream_t st);
 
 struct RgenParams {
   const double *Xs;   // chunk base: candidate rows, row-major with leading dimension d
@@ -85,6 +88,7 @@ struct GradParams {
   int64_t mc, ldp;
   int n, d, dpad, NJ8;
   const double *Xc, *center, *theta, *gamma, *avec;
+  const double *Xsc;   // scaled training coordinates, row stride grad_row_stride(dpad)
   const double *rP, *wP;
   const double *meanpart, *ftpart;
   int JS;
