@@ -741,8 +741,12 @@ def main():
             t0 = time.time()
             extra["c3"] = bench_posterior(ctx, args, "c3", 2, 3, cpu=cpu_x)
             extra["nll"] = bench_nll(ctx, args, 4096, 64, 3, 3, strong=True, cpu=cpu_x)
+            # BO-loop sizes: 8 theta-vectors per GPU per step (a lock-step MLE with few restarts: bound by the
+            # serial chain of the factorisation) and 64 (run_sequential.py uses random_start = 10 d)
             extra["nll_n2048"] = bench_nll(ctx, args, 2048, 8, 10, 3, strong=False, cpu=False)
+            extra["nll_n2048_b64"] = bench_nll(ctx, args, 2048, 64, 5, 3, strong=False, cpu=False)
             extra["nll_n1024"] = bench_nll(ctx, args, 1024, 8, 20, 3, strong=False, cpu=False)
+            extra["nll_n1024_b64"] = bench_nll(ctx, args, 1024, 64, 10, 3, strong=False, cpu=False)
             extra["c5"] = bench_posterior(ctx, args, "c5", 3, 3, cpu=cpu_x)
             extra["c2dx"] = bench_posterior(ctx, args, "c2dx", 5, 3, cpu=cpu_x)
             extra["fit"] = bench_fit(ctx)
