@@ -97,7 +97,7 @@ __global__ void k_topk_pack(const double *val, const int64_t *idx, int cnt, int6
   send[cnt + e] = empty ? INT64_MAX : i + offset;
 }
 
-const int HDR = 32;   // doubles in the model header
+const int HDR = 128;  // doubles in the model header: 32 scalars + up to 96 hyper-parameters
 
 }  // namespace
 
@@ -175,6 +175,11 @@ int mgp_bcast_model(mgp_t *h, int root) {
                      h->sigma2, h->beta, h->G, h->ftf, h->llf, h->noise_var, h->logdetFF, (double)(h->isotropic ? 1 : 0),
                      (double)(h->fitted ? 1 : 0)};
     memcpy(hdr, vals, sizeof(vals));
+    // the hyper-parameters of the fit travel too: a receiver can then extend the model
+    // incrementally (mgp_append_train) exactly like the root
+    hdr[16] = (double)h->hpar.size();
+    hdr[17] = h->par_noise_var;
+    for (size_t i = 0; i < h->hpar.size() && 32 + i < (size_t)HDR; i++) hdr[32 + i] = h->hpar[i];
   }
   MGP_TRY(mgp_ensure(h, h->dcomm, (size_t)(HDR + 2 * h->world + 8) * 8));
   double *dh = P<double>(h->dcomm);
@@ -202,6 +207,9 @@ int mgp_bcast_model(mgp_t *h, int root) {
     MGP_TRY(mgp_model_alloc(h));
     h->mode = (int)hdr[6]; h->sigma2 = hdr[7]; h->beta = hdr[8]; h->G = hdr[9]; h->ftf = hdr[10]; h->llf = hdr[11];
     h->noise_var = hdr[12]; h->logdetFF = hdr[13]; h->isotropic = hdr[14] != 0.0;
+    const int np = (int)hdr[16];
+    h->hpar.assign(hdr + 32, hdr + 32 + (np > 0 && np <= HDR - 32 ? np : 0));
+    h->par_noise_var = hdr[17];
   }
   const size_t mat = (size_t)h->npad * h->npad, vec = (size_t)h->npad;
   struct Item { DevBuf *b; size_t count; };
