@@ -533,7 +533,8 @@ def bench_posterior(ctx, args, name, steps, warmup, cpu=True):
                          "kernel": "k_trmm<true> (W = R^-1 r)" if dx else "k_trmm<false> (T = L^-1 r, fused sum of squares)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
-                         "traffic": None if dx else trmm_traffic(name, chunk),
+                         "traffic": trmm_traffic(name, chunk),
+                         "algorithmic_bytes_8d": 8.0 * (d + wl["sets"]) * per_launch_c,
                          "peak_source": "FP64 " + peak_src + "; MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_launch": flops_per_launch, "launches_timed": int(trmm_calls),
                          "avg_launch_ms": trmm_ns / max(1, trmm_calls) * 1e-6,
