@@ -1122,8 +1122,6 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
   const bool ordinary = h->trend_est;
   const bool gen = h->p > 1 && h->trend_est;
   const int PT = rgen_trend_cols(h->dpad);
-  if (gen && h->corr == MGP_CORR_ABSEXP)
-    return mgp_fail(h, MGP_EINVAL, "an estimated linear trend with the absolute-exponential kernel is not implemented");
   double *chunk_val = nullptr;
   int64_t *blk_idx = nullptr;
   const bool top1 = q.topk == 1 && !q.want_dx;   // per-block arg-max fused into the epilogue

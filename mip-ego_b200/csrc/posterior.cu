@@ -1115,6 +1115,37 @@ static cudaError_t rgen_dispatch(const RgenParams &p, int sm_count, cudaStream_t
     default: return cudaErrorInvalidValue;
   }
 }
+// Bhat^T r for the absolute-exponential kernel with an estimated non-constant trend: K1' (k_rgen_l1)
+// has no DMMA distance GEMM whose C fragments could feed the trend product, so the projection is a
+// separate pass over the packed r it wrote: tpart[jb][k][c] = sum_{j in block jb} Bhat[j][k] r[c][j].
+// One CTA per (candidate block, training block); thread = (candidate, half of the trend columns).
+__global__ void __launch_bounds__(256) k_trend_proj(RgenParams p, int PT) {
+  extern __shared__ __align__(16) double sBh[];          // [128][PT] rows of Bhat of this training block
+  const int cb = blockIdx.x, jb = blockIdx.y, tid = threadIdx.x;
+  for (int idx = tid; idx < 128 * PT; idx += 256) {
+    const int j = idx / PT, k = idx % PT;
+    sBh[idx] = p.Bhat[(int64_t)(jb * 128 + j) * MGP_TP + k];
+  }
+  __syncthreads();
+  const int cl = tid & 127, half = tid >> 7;
+  const int c8 = cl >> 3, crow = cl & 7;
+  const int k0 = half * (PT / 2), k1 = k0 + PT / 2;
+  const double *rb = p.rP + (((int64_t)cb * p.NJ8 + jb * 16) * 16 + c8) * 64 + crow * 8;
+  for (int kk = k0; kk < k1; kk += 4) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int j = 0; j < 128; j++) {
+      const double r = rb[(int64_t)(j >> 3) * 1024 + (j & 7)];
+      const double *b = sBh + j * PT + kk;
+      a0 = fma(b[0], r, a0); a1 = fma(b[1], r, a1); a2 = fma(b[2], r, a2); a3 = fma(b[3], r, a3);
+    }
+    const int64_t c = (int64_t)cb * 128 + cl;
+    p.tpart[((int64_t)jb * PT + kk) * p.ldp + c] = a0;
+    p.tpart[((int64_t)jb * PT + kk + 1) * p.ldp + c] = a1;
+    p.tpart[((int64_t)jb * PT + kk + 2) * p.ldp + c] = a2;
+    p.tpart[((int64_t)jb * PT + kk + 3) * p.ldp + c] = a3;
+  }
+}
+
 template <int DPAD>
 static cudaError_t rgen_l1_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
   static int occ = 0;
@@ -1141,7 +1172,22 @@ static cudaError_t rgen_l1_dispatch(const RgenParams &p, int sm_count, cudaStrea
 cudaError_t launch_rgen(const RgenParams &p, int corr, int sm_count, cudaStream_t st) {
   if (corr == MGP_CORR_SE) return rgen_dispatch<0>(p, sm_count, st);
   if (corr == MGP_CORR_MATERN32) return rgen_dispatch<1>(p, sm_count, st);
-  if (corr == MGP_CORR_ABSEXP) return rgen_l1_dispatch(p, sm_count, st);
+  if (corr == MGP_CORR_ABSEXP) {
+    cudaError_t e = rgen_l1_dispatch(p, sm_count, st);
+    if (e != cudaSuccess || !p.Bhat) return e;
+    const int PT = rgen_trend_cols(p.dpad);            // multiple of 8
+    const int smem = 128 * PT * (int)sizeof(double);
+    static int smem_set[MGP_MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = dev < 0 || dev >= MGP_MAX_DEVICES ? 0 : dev;
+    if (smem > smem_set[dev]) {
+      cudaFuncSetAttribute(k_trend_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      smem_set[dev] = smem;
+    }
+    k_trend_proj<<<dim3(p.nCblk, p.JS), 256, smem, st>>>(p, PT);
+    return cudaGetLastError();
+  }
   return cudaErrorInvalidValue;
 }
 

@@ -104,9 +104,6 @@ class GaussianProcess(object):
                 "corr=%r: the CUDA path implements %s" % (self.corr, self._correlation_types))
         if not isinstance(self.mean, (constant_trend, linear_trend)):
             raise NotImplementedError("constant_trend and linear_trend are implemented by the CUDA path")
-        if isinstance(self.mean, linear_trend) and self.estimate_trend and self.corr == "absolute_exponential":
-            raise NotImplementedError("an estimated linear trend with the absolute-exponential kernel "
-                                      "is not implemented by the CUDA path")
         if self.optimizer not in self._optimizer_types:
             raise ValueError("optimizer should be one of %s" % self._optimizer_types)
 

@@ -247,6 +247,17 @@ def linear_trends():
                 case_fixed_par("lin_%s_%s_%s" % ("se" if kind[0] == "s" else "m32", "uk" if est else "sk", tag),
                                seed=400 + k, n=56 + 8 * (k % 3), d=d, kind=kind, beta=beta, nugget=nugget,
                                m=16, likelihood=lik, trend="linear")
+    linear_trends_absexp()
+
+
+def linear_trends_absexp():
+    """The linear trend with the absolute-exponential kernel (estimated and given coefficients)."""
+    case_fixed_par("lin_absexp_uk_noisy", seed=431, n=64, d=3, kind="absolute_exponential", beta=None,
+                   nugget=1e-6, m=16, trend="linear")
+    case_fixed_par("lin_absexp_uk_reml_noisy", seed=432, n=56, d=4, kind="absolute_exponential", beta=None,
+                   nugget=1e-4, m=16, likelihood="restricted", trend="linear")
+    case_fixed_par("lin_absexp_sk_noiseless", seed=433, n=56, d=3, kind="absolute_exponential",
+                   beta=[0.2, 0.1, 0.0, -0.1], nugget=0, m=16, trend="linear")
 
 
 def zero_theta():
@@ -318,6 +329,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "zero_theta":
         zero_theta()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "linear_absexp":
+        linear_trends_absexp()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "isotropic":
         isotropic_cases()
