@@ -3,6 +3,7 @@
 // fails with MGP_ECUDA.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -12,6 +13,7 @@
 #include "mgp_common.cuh"
 #include "mgp_handle.h"
 #include "nll.cuh"
+#include "ozaki.cuh"
 #include "posterior.cuh"
 
 int mgp_fail(mgp_handle *h, int code, const char *fmt, ...) {
@@ -117,6 +119,10 @@ int mgp_create(int device, mgp_t **out_h) {
     return MGP_ECUDA;
   }
   h->sm_count = prop.multiProcessorCount;
+  {   // MGP_TRMM_I8=1: every handle starts with the INT8 (Ozaki-scheme) K2c switched on (option "trmm_i8")
+    const char *e = getenv("MGP_TRMM_I8");
+    h->trmm_i8_opt = (e && *e && *e != '0') ? 1 : 0;
+  }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -159,7 +165,7 @@ int mgp_destroy(mgp_t *h) {
                    &h->dwP, &h->dXs_stage[0], &h->dXs_stage[1], &h->dout_stage[0],
                    &h->dout_stage[1], &h->dtopk_val, &h->dtopk_idx, &h->dtopk_blk, &h->nR, &h->nL, &h->nM, &h->nT,
                    &h->nLinvDiag, &h->nvec, &h->nscal, &h->npar, &h->ngpart, &h->nFtm, &h->nBhat, &h->ntws,
-                   &h->dF, &h->dmu, &h->dbetav, &h->dBhat, &h->dCinv, &h->dFtm, &h->niso, &h->dcomm, &h->dgather, &h->dgather_io, &h->ngio};
+                   &h->dF, &h->dmu, &h->dbetav, &h->dBhat, &h->dCinv, &h->dFtm, &h->niso, &h->dcomm, &h->dgather, &h->dgather_io, &h->ngio, &h->dMI8, &h->dMscale, &h->dRI8};
   for (DevBuf *b : all) freebuf(*b);
   for (int i = 0; i < 2; i++) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -205,6 +211,10 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
     nll_graphs_clear(h);
     return MGP_OK;
   }
+  if (!strcmp(name, "trmm_i8")) {   // 1: K2c on the INT8 tensor pipe (Ozaki split, 7 x 7-bit slices); 0: FP64 DMMA
+    h->trmm_i8_opt = value != 0;
+    return MGP_OK;
+  }
   if (!strcmp(name, "nll_graphs")) {   // 0: every batched likelihood is issued launch by launch
     h->graphs_opt = value != 0;
     if (!h->graphs_opt) nll_graphs_clear(h);
@@ -232,6 +242,7 @@ int64_t mgp_get_counter(const mgp_t *h, const char *name) {
   if (!strcmp(name, "isotropic")) return h->isotropic ? 1 : 0;
   if (!strcmp(name, "n")) return h->n;
   if (!strcmp(name, "appends")) return h->appends;
+  if (!strcmp(name, "trmm_i8")) return h->trmm_i8_opt;
   if (!strcmp(name, "graph_replays")) return h->graph_replays;
   if (!strcmp(name, "nll_graphs")) return (int64_t)h->nll_graphs.size();
   if (!strcmp(name, "world")) return h->world;
@@ -267,6 +278,7 @@ int mgp_set_train(mgp_t *h, int n, int d, const double *X, const double *y, int 
   if (est && n <= p) return mgp_fail(h, MGP_EINVAL, "n = %d samples cannot determine %d trend coefficients", n, p);
   h->fitted = false;
   h->rinv_ready = false;
+  h->i8_ready = false;
   h->nll_cap = 0;  // workspaces are re-validated against the new padded size
   h->n = n; h->d = d; h->corr = corr; h->trend = trend;
   h->p = p; h->trend_est = est;
@@ -727,6 +739,7 @@ static int adopt_slot0(mgp_handle *h, const double *theta_host, bool take_gamma)
   h->launches += 3;
   MGP_CUDA(h, cudaStreamSynchronize(st));  // th is a host temporary
   h->rinv_ready = false;
+  h->i8_ready = false;
   return 0;
 }
 
@@ -1083,7 +1096,8 @@ static int post_workspace(mgp_handle *h, bool want_dx) {
   MGP_TRY(mgp_ensure(h, h->drP, (size_t)h->npad * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dmeanpart, (size_t)h->NI * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dftpart, (size_t)h->NI * chunk * 8));
-  MGP_TRY(mgp_ensure(h, h->dqpart, (size_t)h->NI * chunk * 8));
+  MGP_TRY(mgp_ensure(h, h->dqpart, (size_t)(h->trmm_i8_opt ? 2 : 1) * h->NI * chunk * 8));
+  if (h->trmm_i8_opt) MGP_TRY(mgp_ensure(h, h->dRI8, ozaki_r_bytes(h->npad, chunk)));
   if (want_dx) MGP_TRY(mgp_ensure(h, h->dwP, (size_t)h->npad * chunk * 8));
   if (h->p > 1 && h->trend_est)
     MGP_TRY(mgp_ensure(h, h->dtpart, (size_t)h->NI * rgen_trend_cols(h->dpad) * chunk * 8));
@@ -1103,6 +1117,17 @@ static int ensure_rinv(mgp_handle *h, cudaStream_t st) {
   return 0;
 }
 
+// INT8 slices of L^-1 for the Ozaki-scheme K2c (built once per fitted model, on first use)
+static int ensure_i8(mgp_handle *h, cudaStream_t st) {
+  if (h->i8_ready) return 0;
+  MGP_TRY(mgp_ensure(h, h->dMI8, ozaki_M_bytes(h->npad)));
+  MGP_TRY(mgp_ensure(h, h->dMscale, (size_t)h->npad * 8));
+  MGP_CUDA(h, launch_ozaki_pack_M(P<double>(h->dMinv), h->n, h->npad, P<double>(h->dMscale), P<int8_t>(h->dMI8), st));
+  h->launches += 2;
+  h->i8_ready = true;
+  return 0;
+}
+
 static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
   if (!h->fitted) return mgp_fail(h, MGP_ESTATE, "model is not fitted");
   if (q.m < 0) return mgp_fail(h, MGP_EINVAL, "m < 0");
@@ -1118,6 +1143,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
   WsScope ws(h, st);
   MGP_CUDA(h, ws.err);
   if (q.want_dx) MGP_TRY(ensure_rinv(h, st));
+  if (h->trmm_i8_opt && !q.want_dx) MGP_TRY(ensure_i8(h, st));
   const int NJ8 = h->npad / 8;
   const bool ordinary = h->trend_est;
   const bool gen = h->p > 1 && h->trend_est;
@@ -1153,6 +1179,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     h->launches++;
     const bool small = mc <= 8 && !h->no_small_path;   // matrix-vector path for tiny populations
     const bool mean_only = !q.want_dx && !acq && !q.d_mse;   // predict(eval_MSE=False): K1 alone gives r . gamma
+    const bool use_i8 = h->trmm_i8_opt && !q.want_dx && !small && !mean_only;
     if (!q.want_dx) {
       if (mean_only) {
         // no triangular product needed
@@ -1160,6 +1187,16 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
         KTimer t(h, st, 1);
         MGP_CUDA(h, launch_small_mv(P<double>(h->dMinv), h->npad, h->n, P<double>(h->drP), (int)mc, 0,
                                     P<double>(h->dqpart), ldp, nullptr, st));
+      } else if (use_i8) {
+        // K2c on the INT8 tensor pipe: slice r, then the tcgen05 product (timed together as "trmm")
+        KTimer t(h, st, 1);
+        MGP_CUDA(h, launch_ozaki_slice_r(P<double>(h->drP), h->npad, nCblk, P<uint8_t>(h->dRI8), st));
+        OzakiParams op;
+        op.RI8 = P<uint8_t>(h->dRI8); op.MI8 = P<int8_t>(h->dMI8); op.scale = P<double>(h->dMscale);
+        op.qpart = P<double>(h->dqpart); op.ldq = ldp; op.NI2 = h->npad / 64; op.nCblk = nCblk; op.nks = h->npad / 64;
+        op.cgroup = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)h->npad * 896));
+        MGP_CUDA(h, launch_trmm_i8(op, h->sm_count, st));
+        h->launches++;
       } else {
         TrmmParams tp;
         tp.Mp = P<double>(h->dMp); tp.rP = P<double>(h->drP); tp.qpart = P<double>(h->dqpart);
@@ -1170,7 +1207,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       }
       EpiParams ep;
       ep.qpart = P<double>(h->dqpart); ep.meanpart = P<double>(h->dmeanpart); ep.ftpart = P<double>(h->dftpart);
-      ep.NI = mean_only ? 0 : (small ? h->npad / 32 : h->NI); ep.JS = JS; ep.ld = ldp; ep.mc = mc;
+      ep.NI = mean_only ? 0 : (small ? h->npad / 32 : (use_i8 ? 2 * h->NI : h->NI)); ep.JS = JS; ep.ld = ldp; ep.mc = mc;
       ep.beta = h->beta; ep.sigma2 = h->sigma2; ep.G = h->G; ep.ordinary = ordinary;
       ep.p = h->p; ep.PT = PT; ep.d = h->d; ep.trend_est = h->trend_est ? 1 : 0;
       ep.Xs = q.d_Xs + c0 * h->d; ep.betav = P<double>(h->dbetav); ep.Cinv = P<double>(h->dCinv);

@@ -78,6 +78,11 @@ struct mgp_handle {
   DevBuf dTmp;     // npad x npad scratch
   DevBuf dMp;      // packed lower-triangular L^-1 (posterior A operand)
   DevBuf dRinvP;   // packed full R^-1 (gradient path), built lazily
+  // INT8 (Ozaki-scheme) variant of K2c, option "trmm_i8": slices of L^-1 (built lazily per fit), row
+  // scales, slices of the current chunk's r
+  DevBuf dMI8, dMscale, dRI8;
+  bool i8_ready = false;
+  int trmm_i8_opt = 0;
   bool rinv_ready = false;
   DevBuf dgamma, davec, dFt, dYt, drho;  // npad each
   DevBuf dscal;    // small device scalar area

@@ -1,0 +1,327 @@
+// K2c-i8: T = L^-1 r with fused column sums of squares on the INT8 tensor pipe (tcgen05 / TMEM),
+// an Ozaki-scheme evaluation of the FP64 product (opt-in: option "trmm_i8").
+//
+// Why: the exact-FP64 triangular product is n^2 flop per candidate on the DMMA pipe (37 TFLOP/s
+// measured), which bounds C3 / C5 at the 96-97 % of that roofline K2c already reaches.  The INT8
+// pipe of the same SM is ~120 x wider.  Both operands are split into S = 7 slices of 7 bits,
+//   L^-1[i][j] = 2^ea_i sum_p a_p[i][j] 2^-7(p+1)   (balanced digits |a_p| <= 64, per-row exponent)
+//   r[c][j]    =        sum_q b_q[c][j] 2^-7(q+1)   (unsigned digits 0..128; 0 < r <= 1 needs no exponent)
+// every slice product a_p . b_q is an EXACT int32 GEMM (|sum| <= 4096 * 64 * 128 * 7 < 2^31), the
+// S (S + 1) / 2 = 28 products with p + q <= 6 are accumulated by level s = p + q in seven TMEM
+// accumulators, and the epilogue recombines them in FP64:  T = 2^ea_i sum_s 2^-7(s+2) G_s.
+// What is dropped (p + q >= 7) is below 7 * 2^-49 of the row scale: T agrees with the DMMA path to
+// about 1e-14 of max|L^-1 row| -- the parity tests run on it unchanged.
+//
+// Kernel shape (one persistent CTA per SM, warp-specialised, 1-CTA MMA):
+//   item = (64-row block I2 of L^-1, 128-candidate block cb);  D[c][i] in TMEM: lane = candidate,
+//   column = level * 64 + row  (7 * 64 = 448 of the 512 columns);
+//   warp 0 lane 0: producer -- per K = 64 stage ONE bulk copy of the 7 candidate slices (56 KB) and
+//                  one of the 7 L^-1 slices (28 KB); both operands are pre-packed in global memory in
+//                  the shared-memory image the UMMA descriptors expect (no-swizzle K-major core
+//                  matrices), so no tensor map is needed; 2-stage mbarrier ring;
+//   warp 1 lane 0: issues the 2 x 28 tcgen05.mma.kind::i8 (M = 128, N = 64, K = 32) per stage and
+//                  commits them to the ring / to the accumulator-full barrier;
+//   warps 2-5:     epilogue -- tcgen05.ld level by level (64 columns per thread = one candidate's
+//                  64 rows), FP64 recombination, square, sum: qpart[I2][c].
+// Measured mainloop rate on B200 (tools/ozaki/umma_i8_rate.cu): 3195 cycles per stage against the
+// 8192 a DMMA tile needs at its peak: 2.56 x the FP64 tensor roofline.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mgp_common.cuh"
+#include "ozaki.cuh"
+
+namespace {
+
+constexpr int OZ_S = 7;                    // slices per operand
+constexpr int OZ_M = 128;                  // candidates per tile (MMA M, TMEM lanes)
+constexpr int OZ_N = 64;                   // L^-1 rows per tile (MMA N)
+constexpr int OZ_BK = 64;                  // training columns per stage
+constexpr int OZ_A_SLICE = OZ_M * OZ_BK;   // 8 KB
+constexpr int OZ_B_SLICE = OZ_N * OZ_BK;   // 4 KB
+constexpr int OZ_A_STAGE = OZ_S * OZ_A_SLICE;
+constexpr int OZ_B_STAGE = OZ_S * OZ_B_SLICE;
+constexpr int OZ_STAGE = OZ_A_STAGE + OZ_B_STAGE;   // 84 KB
+constexpr int OZ_NST = 2;
+constexpr int OZ_SMEM = OZ_NST * OZ_STAGE + 1024;
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: a core matrix is 8 rows x 16 bytes (128 contiguous bytes); LBO = distance of
+// the two 16-byte K chunks of one K = 32 MMA, SBO = distance of consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t addr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]),
+        "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]),
+        "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]),
+        "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- per-fit: row scales of L^-1 and its int8 slices ------------------------------------------
+// scale[i] = 2^ea_i with |L^-1[i][j]| / scale[i] < 1/2 for all j (1 for an all-zero / padding row)
+__global__ void __launch_bounds__(256) k_oz_rowscale(const double *Minv, int n, int npad, double *scale) {
+  __shared__ double red[8];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  double m = 0.0;
+  if (i < n)
+    for (int j = tid; j <= i; j += 256) m = fmax(m, fabs(Minv[(int64_t)i * npad + j]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; w++) m = fmax(m, red[w]);
+    int e = 0;
+    if (m > 0.0) frexp(m, &e);            // m = f 2^e, f in [0.5, 1)
+    scale[i] = m > 0.0 ? ldexp(1.0, e + 1) : 1.0;
+  }
+}
+
+// L^-1 slices in the B-operand image: for the 64-row block I2 and the K = 64 stage ks <= I2 the 7
+// slices are contiguous (7 x 4 KB); inside a slice byte (kk / 16) * 1024 + (i / 8) * 128 + (i % 8) * 16 + kk % 16.
+// Stage index of (I2, ks): I2 (I2 + 1) / 2 + ks.  One CTA per stage; thread = (row i, 16-column chunk).
+__global__ void __launch_bounds__(256) k_oz_pack_M(const double *Minv, const double *scale, int n, int npad, int8_t *MI8) {
+  const int I2 = blockIdx.y, ks = blockIdx.x;
+  if (ks > I2) return;
+  const int tid = threadIdx.x, il = tid >> 2, kq = tid & 3;
+  const int i = I2 * OZ_N + il, j0 = ks * OZ_BK + kq * 16;
+  int8_t *dst = MI8 + ((int64_t)I2 * (I2 + 1) / 2 + ks) * OZ_B_STAGE + kq * 1024 + (il >> 3) * 128 + (il & 7) * 16;
+  const double inv = 1.0 / scale[i];            // a power of two: the scaling is exact
+  double x[16];
+#pragma unroll
+  for (int t = 0; t < 16; t++) {
+    const int j = j0 + t;
+    x[t] = (i < n && j < n && j <= i) ? Minv[(int64_t)i * npad + j] * inv : 0.0;      // |x| < 1/2, exact scaling
+  }
+#pragma unroll
+  for (int p = 0; p < OZ_S; p++) {
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+      const double y = x[t] * 128.0;                 // exact
+      const double dg = rint(y);                     // |dg| <= 64
+      x[t] = y - dg;                                 // exact, |x| <= 1/2
+      w[t >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)dg) << (8 * (t & 3));
+    }
+    *reinterpret_cast<uint4 *>(dst + p * OZ_B_SLICE) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ---- per chunk: r slices (A operand) from the packed FP64 r that K1 wrote -------------------------
+// Stage (cb, ks): 7 slices x 8 KB contiguous; inside a slice byte (kk / 16) * 2048 + (c / 8) * 128 + (c % 8) * 16 + kk % 16.
+// Unsigned digits: r in (0, 1]; d = floor(128 x) in 0..128, x <- 128 x - d (exact).
+__global__ void __launch_bounds__(256) k_oz_slice_r(const double *rP, int NJ8, int nks, uint8_t *RI8) {
+  const int ks = blockIdx.x, cb = blockIdx.y, tid = threadIdx.x;
+  uint8_t *stage = RI8 + ((int64_t)cb * nks + ks) * OZ_A_STAGE;
+#pragma unroll
+  for (int rep = 0; rep < 2; rep++) {
+    const int w = tid + 256 * rep, c = w >> 2, kq = w & 3;           // candidate, 16-column chunk
+    const int j8 = ks * 8 + kq * 2;                                  // two 8-row groups of the packed r
+    const double *src = rP + (((int64_t)cb * NJ8 + j8) * 16 + (c >> 3)) * 64 + (c & 7) * 8;
+    double x[16];
+#pragma unroll
+    for (int t = 0; t < 8; t += 2) {
+      const double2 a = *reinterpret_cast<const double2 *>(src + t);
+      const double2 b = *reinterpret_cast<const double2 *>(src + 1024 + t);
+      x[t] = a.x; x[t + 1] = a.y; x[8 + t] = b.x; x[8 + t + 1] = b.y;
+    }
+    uint8_t *dst = stage + kq * 2048 + (c >> 3) * 128 + (c & 7) * 16;
+#pragma unroll
+    for (int p = 0; p < OZ_S; p++) {
+      uint32_t wd[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int t = 0; t < 16; t++) {
+        const double y = x[t] * 128.0;
+        const double dg = floor(y);
+        x[t] = y - dg;
+        wd[t >> 2] |= ((uint32_t)(int)dg & 0xffu) << (8 * (t & 3));
+      }
+      *reinterpret_cast<uint4 *>(dst + p * OZ_A_SLICE) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+  }
+}
+
+// ---- the product -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
+  extern __shared__ __align__(1024) uint8_t osm[];
+  __shared__ uint64_t full[OZ_NST], empty[OZ_NST], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NI2 = p.NI2, nItems = NI2 * p.nCblk;
+  if (tid == 0) {
+    for (int s = 0; s < OZ_NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(OZ_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_base;
+  // items: candidate blocks in groups of CG (their r slices stay L2 resident while every row block
+  // passes over them), row blocks in decreasing cost inside a group
+  const int CG = p.cgroup;
+  auto decode = [&](int item, int &I2, int &cb) {
+    const int per = CG * NI2;
+    const int grp = item / per, rem = item - grp * per;
+    const int gsz = min(CG, p.nCblk - grp * CG);
+    I2 = NI2 - 1 - rem / gsz;
+    cb = grp * CG + rem % gsz;
+  };
+  // the item list is ragged when nCblk is not a multiple of CG: enumerate by groups
+  const int nGroups = (p.nCblk + CG - 1) / CG;
+  (void)nGroups;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int64_t x = 0;
+      for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        int I2, cb;
+        decode(item, I2, cb);
+        if (cb >= p.nCblk || I2 < 0) continue;
+        for (int ks = 0; ks <= I2; ks++, x++) {
+          const int st = (int)(x % OZ_NST);
+          if (x >= OZ_NST) mbar_wait(&empty[st], (uint32_t)(((x / OZ_NST) - 1) & 1));
+          mbar_expect_tx(&full[st], OZ_STAGE);
+          bulk_g2s(osm + st * OZ_STAGE, p.RI8 + ((int64_t)cb * p.nks + ks) * OZ_A_STAGE, OZ_A_STAGE, &full[st]);
+          bulk_g2s(osm + st * OZ_STAGE + OZ_A_STAGE, p.MI8 + ((int64_t)I2 * (I2 + 1) / 2 + ks) * OZ_B_STAGE, OZ_B_STAGE,
+                   &full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = S32, A = UINT8 (r digits), B = INT8 (L^-1 digits), both K-major, N = 64, M = 128
+      const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
+      int64_t x = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        int I2, cb;
+        decode(item, I2, cb);
+        if (cb >= p.nCblk || I2 < 0) continue;
+        if (it > 0) mbar_wait(&acc_empty, (uint32_t)((it - 1) & 1));      // the epilogue has drained TMEM
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        for (int ks = 0; ks <= I2; ks++, x++) {
+          const int st = (int)(x % OZ_NST);
+          mbar_wait(&full[st], (uint32_t)((x / OZ_NST) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint32_t a0 = smem_u32(osm + st * OZ_STAGE), b0 = a0 + OZ_A_STAGE;
+#pragma unroll
+          for (int k = 0; k < OZ_BK / 32; k++)
+#pragma unroll
+            for (int pa = 0; pa < OZ_S; pa++)       // slice of r (A operand)
+#pragma unroll
+              for (int pb = 0; pb < OZ_S; pb++) {   // slice of L^-1 (B operand)
+                if (pa + pb >= OZ_S) continue;
+                const uint64_t da = umma_desc(a0 + pa * OZ_A_SLICE + k * 2 * (OZ_M * 16), OZ_M * 16, 128);
+                const uint64_t db = umma_desc(b0 + pb * OZ_B_SLICE + k * 2 * (OZ_N * 16), OZ_N * 16, 128);
+                // the first product of a level in an item overwrites its accumulator: with pa outermost
+                // that is (pa = 0, pb = level) of the first K step
+                const uint32_t accumulate = (ks == 0 && k == 0 && pa == 0) ? 0u : 1u;
+                umma_i8(tmem + (uint32_t)((pa + pb) * OZ_N), da, db, idesc, accumulate);
+              }
+          umma_commit(&empty[st]);                  // frees the stage when these MMAs have read it
+        }
+        umma_commit(&acc_full);                     // all levels of this item are complete
+        it++;
+      }
+    }
+  } else {
+    // epilogue warps 2..5: TMEM lane quarter = warp % 4
+    const int quarter = warp & 3, cl = quarter * 32 + lane;           // candidate within the block
+    int it = 0;
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+      int I2, cb;
+      decode(item, I2, cb);
+      if (cb >= p.nCblk || I2 < 0) continue;
+      mbar_wait(&acc_full, (uint32_t)(it & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      double t[OZ_N];
+#pragma unroll
+      for (int i = 0; i < OZ_N; i++) t[i] = 0.0;
+      // smallest level first; level weight 2^-7(s+2)
+#pragma unroll 1
+      for (int s = OZ_S - 1; s >= 0; s--) {
+        uint32_t v[64];
+        tmem_ld64(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * OZ_N), v);
+        const double wgt = __longlong_as_double((int64_t)(1023 - 7 * (s + 2)) << 52);
+#pragma unroll
+        for (int i = 0; i < OZ_N; i++) t[i] = fma((double)(int32_t)v[i], wgt, t[i]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      mbar_arrive(&acc_empty);                      // TMEM may be overwritten
+      double q = 0.0;
+      const double *sc = p.scale + I2 * OZ_N;
+#pragma unroll
+      for (int i = 0; i < OZ_N; i++) {
+        const double T = t[i] * sc[i];
+        q = fma(T, T, q);
+      }
+      p.qpart[(int64_t)I2 * p.ldq + (int64_t)cb * OZ_M + cl] = q;
+      it++;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(OZ_TMEM_COLS));
+}
+
+}  // namespace
+
+size_t ozaki_M_bytes(int npad) {
+  const int64_t NI2 = npad / OZ_N;
+  return (size_t)(NI2 * (NI2 + 1) / 2) * OZ_B_STAGE;
+}
+size_t ozaki_r_bytes(int npad, int64_t chunk) { return (size_t)(chunk / OZ_M) * (npad / OZ_BK) * OZ_A_STAGE; }
+
+cudaError_t launch_ozaki_pack_M(const double *Minv, int n, int npad, double *scale, int8_t *MI8, cudaStream_t st) {
+  k_oz_rowscale<<<npad, 256, 0, st>>>(Minv, n, npad, scale);
+  const int NI2 = npad / OZ_N;
+  k_oz_pack_M<<<dim3(NI2, NI2), 256, 0, st>>>(Minv, scale, n, npad, MI8);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ozaki_slice_r(const double *rP, int npad, int nCblk, uint8_t *RI8, cudaStream_t st) {
+  const int nks = npad / OZ_BK;
+  k_oz_slice_r<<<dim3(nks, nCblk), 256, 0, st>>>(rP, npad / 8, nks, RI8);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trmm_i8(const OzakiParams &p, int sm_count, cudaStream_t st) {
+  static bool attr_done[MGP_MAX_DEVICES] = {};
+  if (first_use_on_device(attr_done))
+    cudaFuncSetAttribute(k_trmm_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+  const int items = p.NI2 * p.nCblk;
+  if (items <= 0) return cudaSuccess;
+  const int grid = items < sm_count ? items : sm_count;
+  k_trmm_i8<<<grid, OZ_THREADS, OZ_SMEM, st>>>(p);
+  return cudaGetLastError();
+}
