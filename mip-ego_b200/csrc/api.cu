@@ -121,7 +121,7 @@ int mgp_create(int device, mgp_t **out_h) {
   h->sm_count = prop.multiProcessorCount;
   {   // MGP_TRMM_I8=1: every handle starts with the INT8 (Ozaki-scheme) K2c switched on (option "trmm_i8")
     const char *e = getenv("MGP_TRMM_I8");
-    h->trmm_i8_opt = (e && *e && *e != '0') ? 1 : 0;
+    h->trmm_i8_opt = (e && *e && *e != '0') ? (*e == '7' ? 7 : 8) : 0;
   }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -211,8 +211,10 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
     nll_graphs_clear(h);
     return MGP_OK;
   }
-  if (!strcmp(name, "trmm_i8")) {   // 1: K2c on the INT8 tensor pipe (Ozaki split, 7 x 7-bit slices); 0: FP64 DMMA
-    h->trmm_i8_opt = value != 0;
+  if (!strcmp(name, "trmm_i8")) {   // K2c on the INT8 tensor pipe (Ozaki split): 0 off (FP64 DMMA), 1 or 8: 8 slices, 7: 7 slices
+    const int v = value == 0 ? 0 : (value == 7 ? 7 : 8);
+    if (v != h->trmm_i8_opt) h->i8_ready = false;      // the packed slices depend on the slice count
+    h->trmm_i8_opt = v;
     return MGP_OK;
   }
   if (!strcmp(name, "nll_graphs")) {   // 0: every batched likelihood is issued launch by launch
@@ -1097,7 +1099,7 @@ static int post_workspace(mgp_handle *h, bool want_dx) {
   MGP_TRY(mgp_ensure(h, h->dmeanpart, (size_t)h->NI * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dftpart, (size_t)h->NI * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dqpart, (size_t)(h->trmm_i8_opt ? 2 : 1) * h->NI * chunk * 8));
-  if (h->trmm_i8_opt) MGP_TRY(mgp_ensure(h, h->dRI8, ozaki_r_bytes(h->npad, chunk)));
+  if (h->trmm_i8_opt) MGP_TRY(mgp_ensure(h, h->dRI8, ozaki_r_bytes(h->npad, chunk, h->trmm_i8_opt)));
   if (want_dx) MGP_TRY(mgp_ensure(h, h->dwP, (size_t)h->npad * chunk * 8));
   if (h->p > 1 && h->trend_est)
     MGP_TRY(mgp_ensure(h, h->dtpart, (size_t)h->NI * rgen_trend_cols(h->dpad) * chunk * 8));
@@ -1120,9 +1122,10 @@ static int ensure_rinv(mgp_handle *h, cudaStream_t st) {
 // INT8 slices of L^-1 for the Ozaki-scheme K2c (built once per fitted model, on first use)
 static int ensure_i8(mgp_handle *h, cudaStream_t st) {
   if (h->i8_ready) return 0;
-  MGP_TRY(mgp_ensure(h, h->dMI8, ozaki_M_bytes(h->npad)));
+  MGP_TRY(mgp_ensure(h, h->dMI8, ozaki_M_bytes(h->npad, h->trmm_i8_opt)));
   MGP_TRY(mgp_ensure(h, h->dMscale, (size_t)h->npad * 8));
-  MGP_CUDA(h, launch_ozaki_pack_M(P<double>(h->dMinv), h->n, h->npad, P<double>(h->dMscale), P<int8_t>(h->dMI8), st));
+  MGP_CUDA(h, launch_ozaki_pack_M(P<double>(h->dMinv), h->n, h->npad, P<double>(h->dMscale), P<int8_t>(h->dMI8),
+                                  h->trmm_i8_opt, st));
   h->launches += 2;
   h->i8_ready = true;
   return 0;
@@ -1190,12 +1193,12 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       } else if (use_i8) {
         // K2c on the INT8 tensor pipe: slice r, then the tcgen05 product (timed together as "trmm")
         KTimer t(h, st, 1);
-        MGP_CUDA(h, launch_ozaki_slice_r(P<double>(h->drP), h->npad, nCblk, P<uint8_t>(h->dRI8), st));
+        MGP_CUDA(h, launch_ozaki_slice_r(P<double>(h->drP), h->npad, nCblk, P<uint8_t>(h->dRI8), h->trmm_i8_opt, st));
         OzakiParams op;
         op.RI8 = P<uint8_t>(h->dRI8); op.MI8 = P<int8_t>(h->dMI8); op.scale = P<double>(h->dMscale);
         op.qpart = P<double>(h->dqpart); op.ldq = ldp; op.NI2 = h->npad / 64; op.nCblk = nCblk; op.nks = h->npad / 64;
-        op.cgroup = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)h->npad * 896));
-        MGP_CUDA(h, launch_trmm_i8(op, h->sm_count, st));
+        op.cgroup = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)h->npad * 128 * h->trmm_i8_opt));
+        MGP_CUDA(h, launch_trmm_i8(op, h->trmm_i8_opt, h->sm_count, st));
         h->launches++;
       } else {
         TrmmParams tp;

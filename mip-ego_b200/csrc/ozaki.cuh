@@ -6,8 +6,8 @@
 #include <stdint.h>
 
 struct OzakiParams {
-  const uint8_t *RI8;   // r slices of the current chunk: [cand block][K stage][7 slices][8 KB]
-  const int8_t *MI8;    // L^-1 slices: [64-row block I2][K stage <= I2][7 slices][4 KB]
+  const uint8_t *RI8;   // r slices of the current chunk: [cand block][K stage][S slices][8 KB]
+  const int8_t *MI8;    // L^-1 slices: [64-row block I2][K stage <= I2][S slices][4 KB]
   const double *scale;  // npad row scales 2^ea_i of L^-1
   double *qpart;        // [NI2][ldq] partial sums of squares per 64-row block
   int64_t ldq;
@@ -16,10 +16,11 @@ struct OzakiParams {
   int nks;              // K stages per candidate block (npad / 64)
   int cgroup;           // candidate blocks per L2-resident group
 };
-size_t ozaki_M_bytes(int npad);
-size_t ozaki_r_bytes(int npad, int64_t chunk);
+// S: slices per operand, 8 (default; 56 bits) or 7 (49 bits, faster)
+size_t ozaki_M_bytes(int npad, int S);
+size_t ozaki_r_bytes(int npad, int64_t chunk, int S);
 // per fit: row scales + int8 slices of the row-major L^-1 (npad x npad, lower)
-cudaError_t launch_ozaki_pack_M(const double *Minv, int n, int npad, double *scale, int8_t *MI8, cudaStream_t st);
+cudaError_t launch_ozaki_pack_M(const double *Minv, int n, int npad, double *scale, int8_t *MI8, int S, cudaStream_t st);
 // per chunk: int8 slices of the packed FP64 r that K1 wrote
-cudaError_t launch_ozaki_slice_r(const double *rP, int npad, int nCblk, uint8_t *RI8, cudaStream_t st);
-cudaError_t launch_trmm_i8(const OzakiParams &p, int sm_count, cudaStream_t st);
+cudaError_t launch_ozaki_slice_r(const double *rP, int npad, int nCblk, uint8_t *RI8, int S, cudaStream_t st);
+cudaError_t launch_trmm_i8(const OzakiParams &p, int S, int sm_count, cudaStream_t st);

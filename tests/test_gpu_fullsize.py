@@ -60,6 +60,20 @@ def test_c3_against_oracle(c3_model):
     e_dx = np.max(np.abs(dx - rdx)) / np.abs(rdx).max()
     print("C3 vs oracle: mean %.2e mse %.2e MGFI x8 %.2e EI %.2e EI_dx %.2e" % (e_mean, e_mse, e_mgfi, e_ei, e_dx))
     assert e_mean < 1e-9 and e_mse < 1e-7 and e_mgfi < 1e-7 and e_ei < 1e-7 and e_dx < 1e-7
+    # the same sample through K2c on the INT8 tensor pipe (Ozaki split, tcgen05): same gates
+    h = gp._handle()
+    for slices in (8, 7):
+        h.set_option("trmm_i8", slices)
+        mse8 = gp.predict(Xs, eval_MSE=True)[1]
+        V8 = crit.evaluate(Xs, params=ts)
+        e8 = np.max(np.abs(mse8 - rs) / (np.abs(rs) + 1e-6 * st["sigma2"]))
+        g8 = 0.0
+        for s, t in enumerate(ts):
+            rv = O.acquisition(st, Xs, "MGFI", float(t), plugin, True)
+            g8 = max(g8, np.max(np.abs(V8[s] - rv) / (np.abs(rv) + 1e-6 * np.abs(rv).max())))
+        print("C3 vs oracle, INT8 K2c with %d slices: mse %.2e MGFI x8 %.2e" % (slices, e8, g8))
+        assert e8 < (1e-7 if slices == 8 else 1e-6) and g8 < (1e-7 if slices == 8 else 1e-6)
+    h.set_option("trmm_i8", 0)
 
 
 @pytest.mark.parametrize("mode", ["noisy", "noiseless"])
