@@ -27,6 +27,9 @@ roofline, e2e, cpu_baseline, clocks) for the other named shapes of the metric --
              the N ranks (strong scaling), plus 8 evaluations per GPU at n=1024 and n=2048 (the
              sizes a BO loop lives at);
   extra.c5   n=8192, d=40 Matern, simple kriging, 2^18 candidates per GPU;
+  extra.c3_i8, extra.c5_i8  the same two shapes with K2c on the INT8 tensor pipe (option trmm_i8: Ozaki
+             split into 8 slices, tcgen05.mma kind::i8, TMEM accumulators) -- same parity gates, reported
+             against the FP64 DMMA roofline (frac > 1) and the INT8 one;
   extra.c2dx EI with its gradient (return_dx) at the C2 shape;
   extra.fit  wall time of GaussianProcess.fit (n=500, d=10, 10 lock-step restarts).
 N > 1 (torchrun): the model is fitted on rank 0 and broadcast through the library's own NCCL
@@ -60,6 +63,13 @@ WORKLOADS = {
     "c3": dict(n=4096, d=20, m=10_000_000, kind="squared_exponential", crit="MGFI", sets=8, nugget=1e-6, beta=None,
                strong=True,
                desc="ParallelBO MGFI n_point=8 d=20 n=4096, 10^7 candidates split over the GPUs (BASELINE configs[2])"),
+    "c3_i8": dict(n=4096, d=20, m=10_000_000, kind="squared_exponential", crit="MGFI", sets=8, nugget=1e-6, beta=None,
+                  strong=True, i8=8,
+                  desc="ParallelBO MGFI n_point=8 d=20 n=4096, 10^7 candidates split over the GPUs (BASELINE configs[2]); "
+                       "K2c on the INT8 tensor pipe (Ozaki split, 8 slices, tcgen05 + TMEM)"),
+    "c5_i8": dict(n=8192, d=40, m=262_144, kind="matern", crit="EI", sets=1, nugget=0.0, beta=0.0, i8=8,
+                  desc="BBOB-shaped surrogate d=40 n=8192 Matern-3/2 simple kriging, 2^18 candidates per GPU "
+                       "(BASELINE configs[4]); K2c on the INT8 tensor pipe (Ozaki split, 8 slices, tcgen05 + TMEM)"),
     "c5": dict(n=8192, d=40, m=262_144, kind="matern", crit="EI", sets=1, nugget=0.0, beta=0.0,
                desc="BBOB-shaped surrogate d=40 n=8192 Matern-3/2 simple kriging, EI over CMA-ES-sized "
                     "populations, 2^18 candidates per GPU (BASELINE configs[4])"),
@@ -400,6 +410,9 @@ def bench_posterior(ctx, args, name, steps, warmup, cpu=True):
     h = gp._handle()
     if args.chunk:
         h.set_option("chunk", args.chunk)
+    i8 = int(wl.get("i8", 0))
+    if i8:
+        h.set_option("trmm_i8", i8)
     plugin = float(y.min())
     ts = set_times(wl["sets"])
     crit = mb.EI(model=gp, minimize=True, plugin=plugin) if wl["crit"] == "EI" else \
@@ -544,6 +557,19 @@ def bench_posterior(ctx, args, name, steps, warmup, cpu=True):
                          "whole_step_frac_of_peak": value / ctx.world * flops_per_candidate(n, d, dx) / (peak * 1e12)},
             "clocks": sampler.summary(),
         }
+        if i8:
+            # the same n^2 FP64-equivalent flops per candidate, evaluated as 36 (8 slices) or 34 (7) exact int8
+            # slice products: reported against BOTH rooflines (frac > 1 = beyond the FP64 DMMA peak)
+            pairs = 36 if i8 == 8 else 34
+            # per candidate and slice product: n^2 / 2 multiply-adds over the triangle = n^2 int8 ops
+            int8_ops = pairs * float(n) * n * (value / ctx.world)             # per GPU per second
+            line["roofline"]["kernel"] = ("k_oz_slice_r + k_trmm_i8<%d> (T = L^-1 r as %d exact int8 slice products, "
+                                          "tcgen05.mma kind::i8, TMEM accumulators, FP64 recombination)" % (i8, pairs))
+            line["roofline"]["int8"] = {"achieved": int8_ops / 1e12, "peak": 4500.0, "unit": "TOP/s",
+                                        "frac": int8_ops / 4.5e15,
+                                        "peak_source": "nominal dense INT8 of B200 (no measured INT8 entry in MEASURED_PEAKS.json)",
+                                        "note": "ops = 2 x multiply-adds over the lower triangle (n^2 / 2 per slice product and candidate)"}
+            line["roofline"]["note"] = "frac is FP64-equivalent n^2 flop per candidate over the measured DMMA peak"
         if bc:
             line["broadcast"] = bc
         if cpu:
@@ -749,6 +775,9 @@ def main():
             extra["nll_n1024"] = bench_nll(ctx, args, 1024, 8, 20, 3, strong=False, cpu=False)
             extra["nll_n1024_b64"] = bench_nll(ctx, args, 1024, 64, 10, 3, strong=False, cpu=False)
             extra["c5"] = bench_posterior(ctx, args, "c5", 3, 3, cpu=cpu_x)
+            # the two trmm-bound shapes again with K2c on the INT8 tensor pipe (opt-in path, same parity gates)
+            extra["c3_i8"] = bench_posterior(ctx, args, "c3_i8", 2, 3, cpu=cpu_x)
+            extra["c5_i8"] = bench_posterior(ctx, args, "c5_i8", 3, 3, cpu=False)
             extra["c2dx"] = bench_posterior(ctx, args, "c2dx", 5, 3, cpu=cpu_x)
             extra["fit"] = bench_fit(ctx)
             if ctx.rank == 0:
