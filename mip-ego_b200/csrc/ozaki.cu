@@ -19,7 +19,11 @@
 //                  one of the 7 L^-1 slices (28 KB); both operands are pre-packed in global memory in
 //                  the shared-memory image the UMMA descriptors expect (no-swizzle K-major core
 //                  matrices), so no tensor map is needed; 2-stage mbarrier ring;
-//   warp 1 lane 0: issues the 2 x 34 tcgen05.mma.kind::i8 (M = 128, N = 64, K = 32) per stage and
+//   warp 1 lane 0: issues the tcgen05.mma.kind::i8 (M = 128, K = 32) of a stage: the slices of L^-1 are
+//                  stacked along N in the shared-memory image, so ONE MMA with N = 256 multiplies a slice
+//                  of r with four slices of L^-1 and accumulates into four consecutive levels (2 x 12
+//                  MMAs per stage instead of 2 x 36 of N = 64: a third of the A-operand reads, which is
+//                  what bounded the N = 64 version at 57 cycles per MMA against 32 at the INT8 peak);
 //                  commits them to the ring / to the accumulator-full barrier;
 //   warps 2-5:     epilogue -- tcgen05.ld level by level (64 columns per thread = one candidate's
 //                  64 rows), FP64 recombination, square, sum: qpart[I2][c].
@@ -106,8 +110,10 @@ __global__ void __launch_bounds__(256) k_oz_rowscale(const double *Minv, int n, 
   }
 }
 
-// L^-1 slices in the B-operand image: for the 64-row block I2 and the K = 64 stage ks <= I2 the 7
-// slices are contiguous (7 x 4 KB); inside a slice byte (kk / 16) * 1024 + (i / 8) * 128 + (i % 8) * 16 + kk % 16.
+// L^-1 slices in the B-operand image: for the 64-row block I2 and the K = 64 stage ks <= I2 the S
+// slices are STACKED ALONG N inside every 16-byte K chunk: byte (kk / 16) * S * 1024 + p * 1024 +
+// (i / 8) * 128 + (i % 8) * 16 + kk % 16, so that one MMA with N = 64 cnt multiplies a slice of r with
+// cnt consecutive slices of L^-1 and lands in cnt consecutive level accumulators.
 // Stage index of (I2, ks): I2 (I2 + 1) / 2 + ks.  One CTA per stage; thread = (row i, 16-column chunk).
 template <int OZ_S>
 __global__ void __launch_bounds__(256) k_oz_pack_M(const double *Minv, const double *scale, int n, int npad, int8_t *MI8) {
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(256) k_oz_pack_M(const double *Minv, const dou
   if (ks > I2) return;
   const int tid = threadIdx.x, il = tid >> 2, kq = tid & 3;
   const int i = I2 * OZ_N + il, j0 = ks * OZ_BK + kq * 16;
-  int8_t *dst = MI8 + ((int64_t)I2 * (I2 + 1) / 2 + ks) * Oz<OZ_S>::B_STAGE + kq * 1024 + (il >> 3) * 128 + (il & 7) * 16;
+  int8_t *dst = MI8 + ((int64_t)I2 * (I2 + 1) / 2 + ks) * Oz<OZ_S>::B_STAGE + kq * (OZ_S * 1024) + (il >> 3) * 128 + (il & 7) * 16;
   const double inv = 1.0 / scale[i];            // a power of two: the scaling is exact
   double x[16];
 #pragma unroll
@@ -133,7 +139,7 @@ __global__ void __launch_bounds__(256) k_oz_pack_M(const double *Minv, const dou
       x[t] = y - dg;                                 // exact, |x| <= 1/2
       w[t >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)dg) << (8 * (t & 3));
     }
-    *reinterpret_cast<uint4 *>(dst + p * OZ_B_SLICE) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4 *>(dst + p * 1024) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -228,8 +234,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D = S32, A = UINT8 (r digits), B = INT8 (L^-1 digits), both K-major, N = 64, M = 128
-      const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
+      // instruction descriptor: D = S32, A = UINT8 (r digits), B = INT8 (L^-1 digits), both K-major, M = 128;
+      // N = 64 x (number of stacked L^-1 slices, at most 4)
+      const uint32_t idesc0 = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(OZ_M >> 4) << 24);
       int64_t x = 0;
       int it = 0;
       for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
@@ -244,19 +251,28 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint32_t a0 = smem_u32(osm + st * OZ_STAGE), b0 = a0 + OZ_A_STAGE;
 #pragma unroll
-          for (int k = 0; k < OZ_BK / 32; k++)
+          for (int k = 0; k < OZ_BK / 32; k++) {
+            const bool first = ks == 0 && k == 0;   // the first product of a level in an item overwrites its accumulator
 #pragma unroll
-            for (int pa = 0; pa < OZ_S; pa++)       // slice of r (A operand)
+            for (int pa = 0; pa < OZ_S; pa++) {     // slice of r (A operand) against the slices pb = 0 .. nsl - 1 of L^-1
+              const int nsl = OZ_S < OZ_LV - pa ? OZ_S : OZ_LV - pa;
+              const uint64_t da = umma_desc(a0 + pa * OZ_A_SLICE + k * 2 * (OZ_M * 16), OZ_M * 16, 128);
+              auto mma = [&](int q, int cnt, uint32_t accumulate) {
+                const uint64_t db = umma_desc(b0 + k * 2 * (OZ_S * 1024) + q * 1024, OZ_S * 1024, 128);
+                umma_i8(tmem + (uint32_t)((pa + q) * OZ_N), da, db, idesc0 | ((uint32_t)((cnt * OZ_N) >> 3) << 17), accumulate);
+              };
 #pragma unroll
-              for (int pb = 0; pb < OZ_S; pb++) {   // slice of L^-1 (B operand)
-                if (pa + pb >= OZ_LV) continue;
-                const uint64_t da = umma_desc(a0 + pa * OZ_A_SLICE + k * 2 * (OZ_M * 16), OZ_M * 16, 128);
-                const uint64_t db = umma_desc(b0 + pb * OZ_B_SLICE + k * 2 * (OZ_N * 16), OZ_N * 16, 128);
-                // the first product of a level in an item overwrites its accumulator: with pa outermost
-                // that is (pa = 0, pb = level) of the first K step (with 7 slices level 7 starts at (1, 6))
-                const uint32_t accumulate = (ks == 0 && k == 0 && (pa == 0 || (pa + pb == OZ_LV - 1 && pb == OZ_S - 1 && pa == OZ_LV - OZ_S))) ? 0u : 1u;
-                umma_i8(tmem + (uint32_t)((pa + pb) * OZ_N), da, db, idesc, accumulate);
+              for (int q = 0; q < nsl; q += 4) {
+                const int cnt = nsl - q < 4 ? nsl - q : 4;
+                if (pa == 0) mma(q, cnt, first ? 0u : 1u);
+                else if (OZ_S < OZ_LV && pa == OZ_LV - OZ_S && q + cnt == nsl && first) {
+                  // 7 slices: level 7 is first touched here (pa = 1, pb = 6) while levels 1..6 already hold pa = 0
+                  if (cnt > 1) mma(q, cnt - 1, 1u);
+                  mma(nsl - 1, 1, 0u);
+                } else mma(q, cnt, 1u);
               }
+            }
+          }
           umma_commit(&empty[st]);                  // frees the stage when these MMAs have read it
         }
         umma_commit(&acc_full);                     // all levels of this item are complete

@@ -27,7 +27,7 @@ __device__ __forceinline__ void umma_i8(uint32_t d, uint64_t da, uint64_t db, ui
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
-template <int NROW, int S, int NST>
+template <int NROW, int S, int NST, bool STACK = false>
 __global__ void __launch_bounds__(128) k_rate(const int8_t *buf, size_t buf_bytes, int nstage, long long *clk) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int A_BYTES = S * M * BK, B_BYTES = S * NROW * BK, ST_BYTES = A_BYTES + B_BYTES;
@@ -67,6 +67,23 @@ __global__ void __launch_bounds__(128) k_rate(const int8_t *buf, size_t buf_byte
       mbar_wait(&full[st], (uint32_t)((s / NST) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;");
       const uint32_t a0 = smem_u32(smem + st * ST_BYTES), b0 = a0 + A_BYTES;
+      if (STACK) {
+        // slices of the row operand stacked along N: one MMA covers the levels p .. p + cnt - 1
+        // (B image: 16-byte K chunk -> S slices x NROW rows contiguous, LBO = S * NROW * 16)
+        for (int k = 0; k < BK / 32; k++)
+          for (int p = 0; p < S; p++) {
+            int q = 0;
+            while (q < S - p) {
+              int cnt = S - p - q;
+              if (cnt * NROW > 256) cnt = 256 / NROW;
+              const uint32_t id2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((cnt * NROW) >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+              const uint64_t da = umma_desc(a0 + p * (M * BK) + k * 2 * (M * 16), M * 16, 128);
+              const uint64_t db = umma_desc(b0 + k * 2 * (S * NROW * 16) + q * (NROW * 16), S * NROW * 16, 128);
+              umma_i8(tmem + (uint32_t)((p + q) * NROW), da, db, id2, (s | k | p) ? 1u : 0u);
+              q += cnt;
+            }
+          }
+      } else
       for (int k = 0; k < BK / 32; k++)
         for (int p = 0; p < S; p++)
           for (int q = 0; p + q < S; q++) {
@@ -86,17 +103,17 @@ __global__ void __launch_bounds__(128) k_rate(const int8_t *buf, size_t buf_byte
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-template <int NROW, int S, int NST>
+template <int NROW, int S, int NST, bool STACK = false>
 static void run(int8_t *buf, size_t bytes, int grid) {
   const int nstage = 2000;
   constexpr int ST_BYTES = S * (M + NROW) * BK;
   const int smem = NST * ST_BYTES + 1024;
   long long *dclk; CK(cudaMalloc(&dclk, sizeof(long long) * grid));
-  CK(cudaFuncSetAttribute(k_rate<NROW, S, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_rate<NROW, S, NST, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  k_rate<NROW, S, NST><<<grid, 128, smem>>>(buf, bytes, 100, dclk); CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+  k_rate<NROW, S, NST, STACK><<<grid, 128, smem>>>(buf, bytes, 100, dclk); CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  k_rate<NROW, S, NST><<<grid, 128, smem>>>(buf, bytes, nstage, dclk); CK(cudaGetLastError());
+  k_rate<NROW, S, NST, STACK><<<grid, 128, smem>>>(buf, bytes, nstage, dclk); CK(cudaGetLastError());
   CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
   long long h[148]; CK(cudaMemcpy(h, dclk, sizeof(long long) * (grid < 148 ? grid : 148), cudaMemcpyDeviceToHost));
@@ -104,9 +121,9 @@ static void run(int8_t *buf, size_t bytes, int grid) {
   const double clk_stage = (double)h[0] / nstage;
   const double dmma_clk = 128.0 * NROW * 64 / 64.0;
   const double mac_rate = npair * 2 * 128.0 * NROW * 32 / clk_stage;     // int8 MACs per clk per SM
-  printf("{\"rows\": %d, \"slices\": %d, \"stages\": %d, \"grid\": %d, \"buf_MB\": %.0f, \"ms\": %.3f, \"clk_per_stage\": %.0f, "
+  printf("{\"stacked\": %d, \"rows\": %d, \"slices\": %d, \"stages\": %d, \"grid\": %d, \"buf_MB\": %.0f, \"ms\": %.3f, \"clk_per_stage\": %.0f, "
          "\"int8_mac_per_clk_per_sm\": %.0f, \"dmma_clk_same_work\": %.0f, \"speedup_vs_dmma_peak\": %.2f, \"l2_TBps\": %.2f}\n",
-         NROW, S, NST, grid, bytes / 1048576.0, ms, clk_stage, mac_rate, dmma_clk, dmma_clk / clk_stage,
+         (int)STACK, NROW, S, NST, grid, bytes / 1048576.0, ms, clk_stage, mac_rate, dmma_clk, dmma_clk / clk_stage,
          (double)grid * nstage * ST_BYTES / (ms * 1e-3) / 1e12);
   cudaFree(dclk);
 }
@@ -120,5 +137,9 @@ int main() {
   run<64, 8, 2>(buf, big, 148);
   run<128, 4, 2>(buf, big, 148);      // 4 levels x 128 rows (first pass of a two-pass scheme)
   run<32, 7, 3>(buf, big, 148);
+  run<64, 8, 2, true>(buf, small, 1);
+  run<64, 8, 2, true>(buf, big, 148);
+  run<64, 7, 2, true>(buf, big, 148);
+  run<64, 8, 1, true>(buf, big, 148);
   return 0;
 }
