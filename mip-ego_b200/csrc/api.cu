@@ -217,6 +217,10 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
     h->trmm_i8_opt = v;
     return MGP_OK;
   }
+  if (!strcmp(name, "trmm_i8_pair")) {   // K2c-i8 as two-CTA clusters sharing the candidate slices by multicast
+    h->trmm_i8_pair = value != 0;
+    return MGP_OK;
+  }
   if (!strcmp(name, "nll_graphs")) {   // 0: every batched likelihood is issued launch by launch
     h->graphs_opt = value != 0;
     if (!h->graphs_opt) nll_graphs_clear(h);
@@ -245,6 +249,7 @@ int64_t mgp_get_counter(const mgp_t *h, const char *name) {
   if (!strcmp(name, "n")) return h->n;
   if (!strcmp(name, "appends")) return h->appends;
   if (!strcmp(name, "trmm_i8")) return h->trmm_i8_opt;
+  if (!strcmp(name, "trmm_i8_pair")) return h->trmm_i8_pair;
   if (!strcmp(name, "graph_replays")) return h->graph_replays;
   if (!strcmp(name, "nll_graphs")) return (int64_t)h->nll_graphs.size();
   if (!strcmp(name, "world")) return h->world;
@@ -1197,7 +1202,8 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
         OzakiParams op;
         op.RI8 = P<uint8_t>(h->dRI8); op.MI8 = P<int8_t>(h->dMI8); op.scale = P<double>(h->dMscale);
         op.qpart = P<double>(h->dqpart); op.ldq = ldp; op.NI2 = h->npad / 64; op.nCblk = nCblk; op.nks = h->npad / 64;
-        op.cgroup = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)h->npad * 128 * h->trmm_i8_opt));
+        op.cgroup = (int)std::max<int64_t>(1, ((int64_t)32 << 20) / ((int64_t)h->npad * 128 * h->trmm_i8_opt));
+        op.pair = h->trmm_i8_pair;
         MGP_CUDA(h, launch_trmm_i8(op, h->trmm_i8_opt, h->sm_count, st));
         h->launches++;
       } else {

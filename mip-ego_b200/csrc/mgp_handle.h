@@ -83,6 +83,7 @@ struct mgp_handle {
   DevBuf dMI8, dMscale, dRI8;
   bool i8_ready = false;
   int trmm_i8_opt = 0;
+  int trmm_i8_pair = 0;        // K2c-i8 as clusters of two CTAs with multicast candidate slices (no gain measured: off)
   bool rinv_ready = false;
   DevBuf dgamma, davec, dFt, dYt, drho;  // npad each
   DevBuf dscal;    // small device scalar area

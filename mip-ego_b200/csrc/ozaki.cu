@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) k_oz_pack_M(const double *Minv, const dou
 
 // ---- per chunk: r slices (A operand) from the packed FP64 r that K1 wrote -------------------------
 // Stage (cb, ks): 7 slices x 8 KB contiguous; inside a slice byte (kk / 16) * 2048 + (c / 8) * 128 + (c % 8) * 16 + kk % 16.
-// Unsigned digits: r in (0, 1]; d = floor(128 x) in 0..128, x <- 128 x - d (exact).
+// Unsigned digits of the fixed-point value rint(r 2^7S), r in (0, 1]: 0..127, the leading one 0..128.
 template <int OZ_S>
 __global__ void __launch_bounds__(256) k_oz_slice_r(const double *rP, int NJ8, int nks, uint8_t *RI8) {
   const int ks = blockIdx.x, cb = blockIdx.y, tid = threadIdx.x;
@@ -163,15 +163,24 @@ __global__ void __launch_bounds__(256) k_oz_slice_r(const double *rP, int NJ8, i
       x[t] = a.x; x[t + 1] = a.y; x[8 + t] = b.x; x[8 + t + 1] = b.y;
     }
     uint8_t *dst = stage + kq * 2048 + (c >> 3) * 128 + (c & 7) * 16;
+    // v = rint(r 2^7S) once (one multiply by a power of two + one conversion on the FP64 pipe), the
+    // digits by shifts on the integer pipe: digit p = bits [7 (S-1-p), 7 (S-p)) of v, the leading digit
+    // keeps the overflow (r = 1 -> 128).  The same fixed-point value as S - 1 floors and a final rint.
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+      const long long v = __double2ll_rn(x[t] * (double)(1ll << (7 * OZ_S)));
+      lo[t] = (uint32_t)v; hi[t] = (uint32_t)((unsigned long long)v >> 32);
+    }
 #pragma unroll
     for (int p = 0; p < OZ_S; p++) {
+      const int sh = 7 * (OZ_S - 1 - p);
       uint32_t wd[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int t = 0; t < 16; t++) {
-        const double y = x[t] * 128.0;
-        const double dg = p == OZ_S - 1 ? rint(y) : floor(y);     // the last digit is rounded: error +-2^-50, unbiased
-        x[t] = y - dg;
-        wd[t >> 2] |= ((uint32_t)(int)dg & 0xffu) << (8 * (t & 3));
+        uint32_t dg = sh >= 32 ? (hi[t] >> (sh - 32)) : __funnelshift_r(lo[t], hi[t], sh);
+        if (p > 0) dg &= 127u;
+        wd[t >> 2] |= (dg & 0xffu) << (8 * (t & 3));
       }
       *reinterpret_cast<uint4 *>(dst + p * OZ_A_SLICE) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
     }
@@ -179,16 +188,43 @@ __global__ void __launch_bounds__(256) k_oz_slice_r(const double *rP, int NJ8, i
 }
 
 // ---- the product -----------------------------------------------------------------------------------
-template <int OZ_S>
+// PAIR: launched as clusters of two CTAs that work on the SAME candidate block and on the row blocks
+// 2j (rank 0) and 2j + 1 (rank 1).  The candidate slices of a stage (the larger operand, S x 8 KB) are
+// then fetched from L2 once per pair: each CTA loads one half and multicasts it into both shared
+// memories (cp.async.bulk ... .multicast::cluster; the completion bytes are signalled on the same
+// barrier offset in both CTAs), which cuts the L2 -> SM traffic of a stage from 96 to 64 KB per CTA --
+// Measured on B200 (C3 / C5 shapes): no gain -- 4.25e6 against 4.32e6 cand/s, the product is bound by
+// the 1000 W power cap (SM clock 1.6 GHz under load), not by L2 bandwidth -- so the pair variant is
+// an option (OzakiParams::pair, handle option "trmm_i8_pair"), off by default, kept under test.
+// A stage buffer is rewritten by both producers, so its "empty" barrier counts the MMA commits of
+// both CTAs (tcgen05.commit ... .multicast::cluster).  Both CTAs walk 2j + 2 stages; in the last one
+// rank 0 has no L^-1 tile (above the diagonal) and only passes the candidate half on.
+__device__ __forceinline__ void bulk_g2s_mc(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::
+          "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int OZ_S, bool PAIR>
 __global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
   constexpr int OZ_A_STAGE = Oz<OZ_S>::A_STAGE, OZ_B_STAGE = Oz<OZ_S>::B_STAGE, OZ_STAGE = Oz<OZ_S>::STAGE;
   extern __shared__ __align__(1024) uint8_t osm[];
   __shared__ uint64_t full[OZ_NST], empty[OZ_NST], acc_full, acc_empty;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int NI2 = p.NI2, nItems = NI2 * p.nCblk;
+  const int rank = PAIR ? (int)(blockIdx.x & 1) : 0;               // cluster dims (2, 1, 1): rank = blockIdx.x % 2
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nWorkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int NR = PAIR ? p.NI2 / 2 : p.NI2;                           // row units (pairs of 64-row blocks, or blocks)
+  const int nItems = NR * p.nCblk;
   if (tid == 0) {
-    for (int s = 0; s < OZ_NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < OZ_NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], PAIR ? 2 : 1); }
     mbar_init(&acc_full, 1);
     mbar_init(&acc_empty, 128);
     mbar_fence_init();
@@ -199,36 +235,45 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers exist before anything is multicast into them
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tmem_base;
-  // items: candidate blocks in groups of CG (their r slices stay L2 resident while every row block
-  // passes over them), row blocks in decreasing cost inside a group
+  // items: candidate blocks in groups of CG (their r slices stay L2 resident while every row unit
+  // passes over them), row units in decreasing cost inside a group.  The list is ragged when nCblk is
+  // not a multiple of CG: entries of the last group beyond its size decode to a negative row unit.
   const int CG = p.cgroup;
-  auto decode = [&](int item, int &I2, int &cb) {
-    const int per = CG * NI2;
+  auto decode = [&](int item, int &I2, int &cb, int &nst) {
+    const int per = CG * NR;
     const int grp = item / per, rem = item - grp * per;
     const int gsz = min(CG, p.nCblk - grp * CG);
-    I2 = NI2 - 1 - rem / gsz;
+    const int ru = NR - 1 - rem / gsz;
     cb = grp * CG + rem % gsz;
+    I2 = PAIR ? 2 * ru + rank : ru;
+    nst = PAIR ? 2 * ru + 2 : ru + 1;          // stages the worker walks (rank 0 of a pair idles in the last one)
+    return ru >= 0 && cb < p.nCblk;
   };
-  // the item list is ragged when nCblk is not a multiple of CG: enumerate by groups
-  const int nGroups = (p.nCblk + CG - 1) / CG;
-  (void)nGroups;
 
   if (warp == 0) {
     if (lane == 0) {
       int64_t x = 0;
-      for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
-        int I2, cb;
-        decode(item, I2, cb);
-        if (cb >= p.nCblk || I2 < 0) continue;
-        for (int ks = 0; ks <= I2; ks++, x++) {
+      for (int item = worker; item < nItems; item += nWorkers) {
+        int I2, cb, nst;
+        if (!decode(item, I2, cb, nst)) continue;
+        for (int ks = 0; ks < nst; ks++, x++) {
           const int st = (int)(x % OZ_NST);
           if (x >= OZ_NST) mbar_wait(&empty[st], (uint32_t)(((x / OZ_NST) - 1) & 1));
-          mbar_expect_tx(&full[st], OZ_STAGE);
-          bulk_g2s(osm + st * OZ_STAGE, p.RI8 + ((int64_t)cb * p.nks + ks) * OZ_A_STAGE, OZ_A_STAGE, &full[st]);
-          bulk_g2s(osm + st * OZ_STAGE + OZ_A_STAGE, p.MI8 + ((int64_t)I2 * (I2 + 1) / 2 + ks) * OZ_B_STAGE, OZ_B_STAGE,
-                   &full[st]);
+          const bool hasB = ks <= I2;
+          mbar_expect_tx(&full[st], OZ_A_STAGE + (hasB ? OZ_B_STAGE : 0));
+          const uint8_t *asrc = p.RI8 + ((int64_t)cb * p.nks + ks) * OZ_A_STAGE;
+          if (PAIR) {
+            constexpr int HALF = OZ_A_STAGE / 2;
+            bulk_g2s_mc(osm + st * OZ_STAGE + rank * HALF, asrc + rank * HALF, HALF, &full[st], (uint16_t)3);
+          } else {
+            bulk_g2s(osm + st * OZ_STAGE, asrc, OZ_A_STAGE, &full[st]);
+          }
+          if (hasB)
+            bulk_g2s(osm + st * OZ_STAGE + OZ_A_STAGE, p.MI8 + ((int64_t)I2 * (I2 + 1) / 2 + ks) * OZ_B_STAGE, OZ_B_STAGE,
+                     &full[st]);
         }
       }
     }
@@ -239,41 +284,44 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
       const uint32_t idesc0 = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(OZ_M >> 4) << 24);
       int64_t x = 0;
       int it = 0;
-      for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
-        int I2, cb;
-        decode(item, I2, cb);
-        if (cb >= p.nCblk || I2 < 0) continue;
+      for (int item = worker; item < nItems; item += nWorkers) {
+        int I2, cb, nst;
+        if (!decode(item, I2, cb, nst)) continue;
         if (it > 0) mbar_wait(&acc_empty, (uint32_t)((it - 1) & 1));      // the epilogue has drained TMEM
         asm volatile("tcgen05.fence::after_thread_sync;");
-        for (int ks = 0; ks <= I2; ks++, x++) {
+        for (int ks = 0; ks < nst; ks++, x++) {
           const int st = (int)(x % OZ_NST);
           mbar_wait(&full[st], (uint32_t)((x / OZ_NST) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint32_t a0 = smem_u32(osm + st * OZ_STAGE), b0 = a0 + OZ_A_STAGE;
+          if (ks <= I2) {
 #pragma unroll
-          for (int k = 0; k < OZ_BK / 32; k++) {
-            const bool first = ks == 0 && k == 0;   // the first product of a level in an item overwrites its accumulator
+            for (int k = 0; k < OZ_BK / 32; k++) {
+              const bool first = ks == 0 && k == 0;   // the first product of a level in an item overwrites its accumulator
 #pragma unroll
-            for (int pa = 0; pa < OZ_S; pa++) {     // slice of r (A operand) against the slices pb = 0 .. nsl - 1 of L^-1
-              const int nsl = OZ_S < OZ_LV - pa ? OZ_S : OZ_LV - pa;
-              const uint64_t da = umma_desc(a0 + pa * OZ_A_SLICE + k * 2 * (OZ_M * 16), OZ_M * 16, 128);
-              auto mma = [&](int q, int cnt, uint32_t accumulate) {
-                const uint64_t db = umma_desc(b0 + k * 2 * (OZ_S * 1024) + q * 1024, OZ_S * 1024, 128);
-                umma_i8(tmem + (uint32_t)((pa + q) * OZ_N), da, db, idesc0 | ((uint32_t)((cnt * OZ_N) >> 3) << 17), accumulate);
-              };
+              for (int pa = 0; pa < OZ_S; pa++) {     // slice of r (A operand) against the slices pb = 0 .. nsl - 1 of L^-1
+                const int nsl = OZ_S < OZ_LV - pa ? OZ_S : OZ_LV - pa;
+                const uint64_t da = umma_desc(a0 + pa * OZ_A_SLICE + k * 2 * (OZ_M * 16), OZ_M * 16, 128);
+                auto mma = [&](int q, int cnt, uint32_t accumulate) {
+                  const uint64_t db = umma_desc(b0 + k * 2 * (OZ_S * 1024) + q * 1024, OZ_S * 1024, 128);
+                  umma_i8(tmem + (uint32_t)((pa + q) * OZ_N), da, db, idesc0 | ((uint32_t)((cnt * OZ_N) >> 3) << 17), accumulate);
+                };
 #pragma unroll
-              for (int q = 0; q < nsl; q += 4) {
-                const int cnt = nsl - q < 4 ? nsl - q : 4;
-                if (pa == 0) mma(q, cnt, first ? 0u : 1u);
-                else if (OZ_S < OZ_LV && pa == OZ_LV - OZ_S && q + cnt == nsl && first) {
-                  // 7 slices: level 7 is first touched here (pa = 1, pb = 6) while levels 1..6 already hold pa = 0
-                  if (cnt > 1) mma(q, cnt - 1, 1u);
-                  mma(nsl - 1, 1, 0u);
-                } else mma(q, cnt, 1u);
+                for (int q = 0; q < nsl; q += 4) {
+                  const int cnt = nsl - q < 4 ? nsl - q : 4;
+                  if (pa == 0) mma(q, cnt, first ? 0u : 1u);
+                  else if (OZ_S < OZ_LV && pa == OZ_LV - OZ_S && q + cnt == nsl && first) {
+                    // 7 slices: level 7 is first touched here (pa = 1, pb = 6) while levels 1..6 already hold pa = 0
+                    if (cnt > 1) mma(q, cnt - 1, 1u);
+                    mma(nsl - 1, 1, 0u);
+                  } else mma(q, cnt, 1u);
+                }
               }
             }
           }
-          umma_commit(&empty[st]);                  // frees the stage when these MMAs have read it
+          // frees the stage when these MMAs have read it (in a pair: in both CTAs, whose producers both write it)
+          if (PAIR) umma_commit_mc(&empty[st], (uint16_t)3);
+          else umma_commit(&empty[st]);
         }
         umma_commit(&acc_full);                     // all levels of this item are complete
         it++;
@@ -283,10 +331,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
     // epilogue warps 2..5: TMEM lane quarter = warp % 4
     const int quarter = warp & 3, cl = quarter * 32 + lane;           // candidate within the block
     int it = 0;
-    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
-      int I2, cb;
-      decode(item, I2, cb);
-      if (cb >= p.nCblk || I2 < 0) continue;
+    for (int item = worker; item < nItems; item += nWorkers) {
+      int I2, cb, nst;
+      if (!decode(item, I2, cb, nst)) continue;
       mbar_wait(&acc_full, (uint32_t)(it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;");
       double t[OZ_N];
@@ -316,6 +363,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(OZ_TMEM_COLS));
 }
 
@@ -345,16 +393,39 @@ cudaError_t launch_ozaki_slice_r(const double *rP, int npad, int nCblk, uint8_t 
   return cudaGetLastError();
 }
 
-cudaError_t launch_trmm_i8(const OzakiParams &p, int S, int sm_count, cudaStream_t st) {
+template <int S>
+static cudaError_t trmm_i8_launch(const OzakiParams &p, int sm_count, cudaStream_t st) {
   static bool attr_done[MGP_MAX_DEVICES] = {};
+  static int max_clusters[MGP_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = Oz<S>::SMEM; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
   if (first_use_on_device(attr_done)) {
-    cudaFuncSetAttribute(k_trmm_i8<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz<7>::SMEM);
-    cudaFuncSetAttribute(k_trmm_i8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz<8>::SMEM);
+    cudaFuncSetAttribute(k_trmm_i8<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz<S>::SMEM);
+    cudaFuncSetAttribute(k_trmm_i8<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz<S>::SMEM);
+    // co-resident pairs (one CTA per SM; a GPC with an odd number of free SMs leaves one unused)
+    cfg.gridDim = dim3(2 * (sm_count / 2));
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, k_trmm_i8<S, true>, &cfg) != cudaSuccess) { nc = 0; cudaGetLastError(); }
+    if (dev >= 0 && dev < MGP_MAX_DEVICES) max_clusters[dev] = nc;
+  }
+  const int nc = (dev >= 0 && dev < MGP_MAX_DEVICES) ? max_clusters[dev] : 0;
+  const int pair_items = (p.NI2 / 2) * p.nCblk;
+  // pairs need an even number of row blocks (npad is a multiple of 128: always) and most of the machine
+  if (p.pair && nc >= sm_count * 3 / 8 && p.NI2 % 2 == 0 && pair_items > 0) {
+    cfg.gridDim = dim3(2 * (pair_items < nc ? pair_items : nc));
+    return cudaLaunchKernelEx(&cfg, k_trmm_i8<S, true>, p);
   }
   const int items = p.NI2 * p.nCblk;
   if (items <= 0) return cudaSuccess;
-  const int grid = items < sm_count ? items : sm_count;
-  if (oz_slices(S) == 7) k_trmm_i8<7><<<grid, OZ_THREADS, Oz<7>::SMEM, st>>>(p);
-  else k_trmm_i8<8><<<grid, OZ_THREADS, Oz<8>::SMEM, st>>>(p);
+  k_trmm_i8<S, false><<<items < sm_count ? items : sm_count, OZ_THREADS, Oz<S>::SMEM, st>>>(p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_trmm_i8(const OzakiParams &p, int S, int sm_count, cudaStream_t st) {
+  return oz_slices(S) == 7 ? trmm_i8_launch<7>(p, sm_count, st) : trmm_i8_launch<8>(p, sm_count, st);
 }

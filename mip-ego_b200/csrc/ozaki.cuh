@@ -15,6 +15,7 @@ struct OzakiParams {
   int nCblk;            // candidate blocks of 128
   int nks;              // K stages per candidate block (npad / 64)
   int cgroup;           // candidate blocks per L2-resident group
+  int pair;             // 1: clusters of two CTAs share (multicast) the candidate slices of a stage
 };
 // S: slices per operand, 8 (default; 56 bits) or 7 (49 bits, faster)
 size_t ozaki_M_bytes(int npad, int S);

@@ -56,6 +56,12 @@ def test_i8_posterior_against_oracle(slices, n, d, kind, ordinary):
           (slices, n, kind[:6], e_mean, e_mse, np.max(np.abs(mse_f - rs) / (np.abs(rs) + 1e-6 * s2)), e_vs_dmma))
     assert np.array_equal(mean, mean_f)                          # the mean comes from K1, untouched
     assert e_mean < 1e-9 and e_mse < tol
+    # two-CTA clusters sharing the candidate slices by multicast: the same exact integer sums, recombined
+    # in the same order -> bitwise the single-CTA kernel
+    h.set_option("trmm_i8_pair", 1)
+    mean_p, mse_p = gp.predict(Xs, eval_MSE=True)
+    h.set_option("trmm_i8_pair", 0)
+    assert np.array_equal(mse_p, mse) and np.array_equal(mean_p, mean)
     plugin = float(y.min())
     for crit, name, par in ((mb.EI(model=gp, minimize=True, plugin=plugin), "EI", None),
                             (mb.MGFI(model=gp, minimize=True, plugin=plugin, t=2.0), "MGFI", 2.0),
