@@ -187,3 +187,63 @@ def test_lockstep_engine_matches_scipy_and_threads():
     finally:
         _lockstep._checked = saved
     assert np.array_equal(p1, p2) and f1 == f2 and n1 == n2
+
+
+@pytest.mark.parametrize("name", ["mies_min", "mies_max"])
+def test_vectorised_mies_replays_the_reference_generation_by_generation(name, monkeypatch):
+    """Parity pin of `mies_argmax` against the unmodified reference MIES (optimizer/mies.py:21-316).
+    oracle/gen_golden_mies.py ran the reference with SCRIPTED random draws and froze every generation's
+    offspring; here the same numbers are handed to the vectorised implementation in the array shapes it
+    draws ((runs, lambda) parents, (runs, lambda, d) recombination mask / step-size factors / mutation)
+    and every generation must produce the same offspring (x after reflection into the box), hence the
+    same comma selection, incumbent, evaluation count and stop reason."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    lb, ub, centre = g["lb"], g["ub"], g["centre"]
+    d, mu, lam, G = len(lb), int(g["mu"]), int(g["lam"]), int(g["generations"])
+    minimize = bool(g["minimize"])
+    sgn = 1.0 if minimize else -1.0
+    state = {"gen": 0, "ints": 0, "normals": 0}
+
+    def rand(*shape):              # initial parents: (runs, mu, d) uniforms that reproduce the reference's sample
+        assert shape == (1, mu, d)
+        return ((g["pop0"] - lb) / (ub - lb)).reshape(1, mu, d)
+
+    def randint(lo, hi, shape):
+        assert (lo, hi, shape) == (0, mu, (1, lam))
+        k = state["ints"] % 2
+        state["ints"] += 1
+        return (g["P1"] if k == 0 else g["P2"])[state["gen"]].reshape(1, lam)
+
+    def randn(*shape):
+        k = state["normals"] % 4
+        state["normals"] += 1
+        gen = state["gen"]
+        if k == 3:
+            state["gen"] += 1
+        src = (g["Ztake"], g["Ztau"], g["Ztaup"], g["Zmut"])[k][gen]
+        want = (1, lam, 1) if k == 1 else (1, lam, d)
+        assert shape == want
+        return src.reshape(want)
+
+    monkeypatch.setattr(opt, "rand", rand)
+    monkeypatch.setattr(opt, "randint", randint)
+    monkeypatch.setattr(opt, "randn", randn)
+    seen = []
+
+    def values(X):
+        X = np.asarray(X, dtype=np.float64)
+        seen.append(X.copy())
+        return sgn * np.sum((X - centre) ** 2 * np.arange(1, d + 1), axis=1)
+
+    xopt, fopt, evals, reasons = opt.mies_argmax(values, np.c_[lb, ub], n_restart=1, max_eval=int(g["max_eval"]),
+                                                 mu_=mu, lambda_=lam, minimize=minimize)
+    assert np.allclose(seen[0], g["pop0"], rtol=0, atol=1e-14) and np.allclose(values(g["pop0"]), g["fit0"], rtol=1e-13)
+    seen.pop()
+    assert len(seen) == G + 1
+    for k in range(G):
+        assert np.allclose(seen[k + 1], g["offspring"][k][:, :d], rtol=0, atol=1e-11), "generation %d" % k
+    assert np.allclose(xopt[0], g["xopt"], rtol=0, atol=1e-11)
+    assert abs(fopt[0] - float(g["fopt"])) <= 1e-10 * max(1.0, abs(float(g["fopt"])))
+    assert int(evals[0]) == int(g["funcalls"])
+    assert sorted(k for k, v in reasons[0].items() if v) == [str(r) for r in g["reasons"]]
