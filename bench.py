@@ -27,11 +27,14 @@ roofline, e2e, cpu_baseline, clocks) for the other named shapes of the metric --
              the N ranks (strong scaling), plus 8 evaluations per GPU at n=1024 and n=2048 (the
              sizes a BO loop lives at);
   extra.c5   n=8192, d=40 Matern, simple kriging, 2^18 candidates per GPU;
-  extra.c3_i8, extra.c5_i8  the same two shapes with K2c on the INT8 tensor pipe (option trmm_i8: Ozaki
+  extra.c3_i8, extra.c5_i8, extra.c2_i8  the same shapes with K2c on the INT8 tensor pipe (option trmm_i8: Ozaki
              split into 8 slices, tcgen05.mma kind::i8, TMEM accumulators) -- same parity gates, reported
              against the FP64 DMMA roofline (frac > 1) and the INT8 one;
   extra.c2dx EI with its gradient (return_dx) at the C2 shape;
-  extra.fit  wall time of GaussianProcess.fit (n=500, d=10, 10 lock-step restarts).
+  extra.fit  wall time of GaussianProcess.fit (n=500, d=10, 10 lock-step restarts), with the reference's
+             sequential restart loop on the oracle port as its CPU baseline (BASELINE.md B4);
+  extra.per_point  single-point criterion(x) / criterion(x, return_dx=True) calls per second, the call
+             pattern of the reference's own optimisers, GPU drop-in and oracle port.
 N > 1 (torchrun): the model is fitted on rank 0 and broadcast through the library's own NCCL
 communicator (mgp_bcast_model); candidates / restarts are sharded; per-rank top-1 pairs are
 all-gathered and merged on the device every step (mgp_allgather_topk_dev).
@@ -58,6 +61,9 @@ WORKLOADS = {
                desc="GP fit n=50 d=2, EI over 10^4 candidates (BASELINE configs[0], the reference's CPU-runnable case)"),
     "c2": dict(n=500, d=10, m=1_000_000, kind="squared_exponential", crit="EI", sets=1, nugget=1e-6, beta=None,
                desc="GP predict+EI d=10 n=500 over 10^6 synthetic candidates per GPU (BASELINE configs[1])"),
+    "c2_i8": dict(n=500, d=10, m=1_000_000, kind="squared_exponential", crit="EI", sets=1, nugget=1e-6, beta=None, i8=8,
+                  desc="GP predict+EI d=10 n=500 over 10^6 synthetic candidates per GPU (BASELINE configs[1]); "
+                       "K2c on the INT8 tensor pipe (Ozaki split, 8 slices, tcgen05 + TMEM)"),
     "c2dx": dict(n=500, d=10, m=262_144, kind="squared_exponential", crit="EI", sets=1, nugget=1e-6, beta=None, dx=True,
                  desc="GP predict+EI with gradient (return_dx) d=10 n=500 over 2^18 candidates per GPU (BASELINE configs[1] shape)"),
     "c3": dict(n=4096, d=20, m=10_000_000, kind="squared_exponential", crit="MGFI", sets=8, nugget=1e-6, beta=None,
@@ -691,7 +697,7 @@ def bench_nll(ctx, args, n, B_total, steps, warmup, strong, cpu=True, groups=0, 
     return line
 
 
-def bench_fit(ctx):
+def bench_fit(ctx, cpu=False):
     """Wall time of GaussianProcess.fit in the reference's loop shape (base.py:516: one fit per BO
     iteration): n=500, d=10, Matern, 10 lock-step L-BFGS-B restarts (gpr.py:964-1101).  Rank 0 only."""
     mb = ctx.mb
@@ -721,6 +727,111 @@ def bench_fit(ctx):
                "config": {"n": n, "d": d, "kernel": "matern", "restarts": R, "likelihood_evaluations": int(evals),
                           "restart_mode": "batched (lock-step L-BFGS-B, one batched likelihood call per step)"},
                "ms_per_evaluation": 1e3 * min(ts) / max(1, evals), "runs_ms": [1e3 * t for t in ts]}
+        if cpu:
+            out["cpu_baseline"] = cpu_fit_leg(mb, ctx.local, X, y, d, R)
+    ctx.barrier()
+    return out
+
+
+def cpu_fit_leg(mb, device, X, y, d, R, budget_s=20.0):
+    """the reference's fit() loop on the host cores -- sequential L-BFGS-B restarts with a
+    shared evaluation budget and the wait_iter early stop (gpr.py:1030-1064), every objective call ONE
+    likelihood + gradient evaluation of the oracle port -- bounded to `budget_s` seconds of CPU work
+    (a full run is 200 n_par = 2200 evaluations at most).  The restart points, bounds and parametrisation
+    are the ones GaussianProcess.fit draws (injected through its `_solve` hook)."""
+    from oracle import gp_oracle as O
+    from scipy.optimize import fmin_l_bfgs_b
+    use_all_host_threads()
+    stat = {"evals": 0, "restarts": 0, "timeout": False, "t": 0.0}
+
+    class _Timeout(Exception):
+        pass
+
+    def solve(batch_fn, starts, log10bounds, eval_budget, wait_iter):
+        t0 = time.perf_counter()
+
+        def func(p):
+            if time.perf_counter() - t0 > budget_s:
+                raise _Timeout()
+            stat["evals"] += 1
+            llf, g = O.log_likelihood_concentrated(X, y, 10.0 ** np.asarray(p), "matern", True, 0.0, "noisy", 1e-6,
+                                                   eval_grad=True)
+            return -float(llf), -np.asarray(g, dtype=np.float64).ravel()
+        best_p, best_f, wait, budget = np.array(starts[0]), np.inf, 0, eval_budget
+        try:
+            for it in range(len(starts)):
+                p_, f_, info = fmin_l_bfgs_b(func, starts[it], bounds=log10bounds, maxfun=budget)
+                stat["restarts"] += 1
+                if it == 0 or f_ <= best_f:
+                    best_p, best_f, wait = p_, f_, 0
+                else:
+                    wait += 1
+                budget -= info["funcalls"]
+                if budget <= 0 or wait >= wait_iter:
+                    break
+        except _Timeout:
+            stat["timeout"] = True
+        stat["t"] = time.perf_counter() - t0
+        return best_p, best_f, stat["evals"], []
+
+    np.random.seed(1)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="matern", theta0=[0.05] * d,
+                            thetaL=[1e-4] * d, thetaU=[10.0] * d, nugget=1e-6, random_start=R, device=device)
+    gp.fit(X, y, _solve=solve)
+    return {"value": 1e3 * stat["t"], "unit": "ms", "cores": blas_threads(), "kind": "port",
+            "evaluations": stat["evals"], "restarts_completed": stat["restarts"], "stopped_by_time_bound": stat["timeout"],
+            "ms_per_evaluation": 1e3 * stat["t"] / max(1, stat["evals"]),
+            "sample": "the reference's sequential restart loop (gpr.py:1030-1064) on the oracle PORT of the likelihood, "
+                      "same data / bounds / restart points, bounded to %.0f s (BASELINE.md B4)" % budget_s}
+
+
+def bench_per_point(ctx, cpu):
+    """the acquisition exactly as the reference's optimisers call it -- ONE point per call
+    (optimizer/utils.py:38-42) -- over 10^3 seeded candidates at the C2 model: criterion(x) and
+    criterion(x, return_dx=True) through the drop-in classes on the GPU, and the same calls through the
+    oracle port on the host cores.  Rank 0 only."""
+    out = None
+    if ctx.rank == 0:
+        mb = ctx.mb
+        wl = WORKLOADS["c2"]
+        n, d, kind = wl["n"], wl["d"], wl["kind"]
+        X, y, theta = synth_model(n, d, kind)
+        gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=wl["beta"]), corr=kind, theta0=theta,
+                                thetaL=1e-5 * np.ones(d), thetaU=100 * np.ones(d), nugget=wl["nugget"], device=ctx.local)
+        gp.fit_fixed(X, y, model_par(wl, theta))
+        ei = mb.EI(model=gp, minimize=True, plugin=float(y.min()))
+        Xs = np.random.default_rng(11).uniform(-5, 5, (1000, d))
+        for x in Xs[:50]:
+            ei(x)
+            ei(x, return_dx=True)
+        t0 = time.perf_counter()
+        for x in Xs:
+            ei(x)
+        t1 = time.perf_counter()
+        for x in Xs:
+            ei(x, return_dx=True)
+        t2 = time.perf_counter()
+        out = {"metric": "per-point acquisition calls/sec (the reference optimisers' call pattern)", "unit": "calls/s",
+               "value": 1000 / (t1 - t0), "value_with_dx": 1000 / (t2 - t1), "higher_is_better": True,
+               "us_per_call": 1e3 * (t1 - t0), "us_per_call_with_dx": 1e3 * (t2 - t1),
+               "config": {"n": n, "d": d, "kernel": kind, "criterion": "EI", "points": 1000}}
+        if cpu:
+            from oracle import gp_oracle as O
+            use_all_host_threads()
+            st = oracle_state(wl, X, y, theta)
+            plugin = float(y.min())
+            m = 300
+            t0 = time.perf_counter()
+            for x in Xs[:m]:
+                O.acquisition(st, x[None, :], "EI", None, plugin, True)
+            t1 = time.perf_counter()
+            for x in Xs[:m]:
+                O.acquisition(st, x[None, :], "EI", None, plugin, True, return_dx=True)
+            t2 = time.perf_counter()
+            out["cpu_baseline"] = {"value": m / (t1 - t0), "value_with_dx": m / (t2 - t1), "unit": "calls/s",
+                                   "cores": blas_threads(), "kind": "port",
+                                   "sample": "%d single-point EI calls (and %d with return_dx) through the oracle PORT "
+                                             "of gpr.py:392-617 + InfillCriteria.py:113-148 (BASELINE.md B1)" % (m, m)}
     ctx.barrier()
     return out
 
@@ -778,8 +889,10 @@ def main():
             # the two trmm-bound shapes again with K2c on the INT8 tensor pipe (opt-in path, same parity gates)
             extra["c3_i8"] = bench_posterior(ctx, args, "c3_i8", 2, 3, cpu=cpu_x)
             extra["c5_i8"] = bench_posterior(ctx, args, "c5_i8", 3, 3, cpu=False)
+            extra["c2_i8"] = bench_posterior(ctx, args, "c2_i8", 10, 3, cpu=False)
             extra["c2dx"] = bench_posterior(ctx, args, "c2dx", 5, 3, cpu=cpu_x)
-            extra["fit"] = bench_fit(ctx)
+            extra["fit"] = bench_fit(ctx, cpu=cpu_x)
+            extra["per_point"] = bench_per_point(ctx, cpu_x)
             if ctx.rank == 0:
                 extra["seconds"] = time.time() - t0
                 line["extra"] = extra
