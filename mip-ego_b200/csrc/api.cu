@@ -217,6 +217,10 @@ int mgp_set_option(mgp_t *h, const char *name, int64_t value) {
     h->trmm_i8_opt = v;
     return MGP_OK;
   }
+  if (!strcmp(name, "trmm_i8_fuse")) {   // 1 (default): K1 emits the int8 slices of r itself where it can; 0: separate slicing pass
+    h->trmm_i8_fuse = value != 0;
+    return MGP_OK;
+  }
   if (!strcmp(name, "trmm_i8_pair")) {   // K2c-i8 as two-CTA clusters sharing the candidate slices by multicast
     h->trmm_i8_pair = value != 0;
     return MGP_OK;
@@ -250,6 +254,7 @@ int64_t mgp_get_counter(const mgp_t *h, const char *name) {
   if (!strcmp(name, "appends")) return h->appends;
   if (!strcmp(name, "trmm_i8")) return h->trmm_i8_opt;
   if (!strcmp(name, "trmm_i8_pair")) return h->trmm_i8_pair;
+  if (!strcmp(name, "trmm_i8_fuse")) return h->trmm_i8_fuse;
   if (!strcmp(name, "graph_replays")) return h->graph_replays;
   if (!strcmp(name, "nll_graphs")) return (int64_t)h->nll_graphs.size();
   if (!strcmp(name, "world")) return h->world;
@@ -1103,7 +1108,7 @@ static int post_workspace(mgp_handle *h, bool want_dx) {
   MGP_TRY(mgp_ensure(h, h->drP, (size_t)h->npad * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dmeanpart, (size_t)h->NI * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dftpart, (size_t)h->NI * chunk * 8));
-  MGP_TRY(mgp_ensure(h, h->dqpart, (size_t)(h->trmm_i8_opt ? 2 : 1) * h->NI * chunk * 8));
+  MGP_TRY(mgp_ensure(h, h->dqpart, (size_t)(h->trmm_i8_opt ? 4 : 1) * h->NI * chunk * 8));
   if (h->trmm_i8_opt) MGP_TRY(mgp_ensure(h, h->dRI8, ozaki_r_bytes(h->npad, chunk, h->trmm_i8_opt)));
   if (want_dx) MGP_TRY(mgp_ensure(h, h->dwP, (size_t)h->npad * chunk * 8));
   if (h->p > 1 && h->trend_est)
@@ -1173,7 +1178,13 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     const int64_t ldp = round_up(mc, 128);
     const int nCblk = (int)(ldp / 128);
     const int JS = h->NI;
+    const bool small = mc <= 8 && !h->no_small_path;   // matrix-vector path for tiny populations
+    const bool mean_only = !q.want_dx && !acq && !q.d_mse;   // predict(eval_MSE=False): K1 alone gives r . gamma
+    const bool use_i8 = h->trmm_i8_opt && !q.want_dx && !small && !mean_only;
+    // K1 writes the int8 slices itself where it can (no FP64 r, no separate slicing pass)
+    const bool k1_slices = use_i8 && h->trmm_i8_fuse && rgen_can_slice(h->corr, h->dpad, gen, h->trmm_i8_opt);
     RgenParams rp;
+    rp.RI8 = k1_slices ? P<uint8_t>(h->dRI8) : nullptr; rp.nks = h->npad / 64;
     rp.Xs = q.d_Xs + c0 * h->d; rp.mc = mc; rp.d = h->d; rp.dpad = h->dpad; rp.NJ8 = NJ8;
     rp.nCblk = nCblk; rp.JS = JS;
     rp.center = P<double>(h->dcenter); rp.theta = P<double>(h->dtheta); rp.Bop = P<double>(h->dBop);
@@ -1185,9 +1196,6 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     rp.ldp = ldp;
     { KTimer t(h, st, 0); MGP_CUDA(h, launch_rgen(rp, h->corr, h->sm_count, st)); }
     h->launches++;
-    const bool small = mc <= 8 && !h->no_small_path;   // matrix-vector path for tiny populations
-    const bool mean_only = !q.want_dx && !acq && !q.d_mse;   // predict(eval_MSE=False): K1 alone gives r . gamma
-    const bool use_i8 = h->trmm_i8_opt && !q.want_dx && !small && !mean_only;
     if (!q.want_dx) {
       if (mean_only) {
         // no triangular product needed
@@ -1196,9 +1204,12 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
         MGP_CUDA(h, launch_small_mv(P<double>(h->dMinv), h->npad, h->n, P<double>(h->drP), (int)mc, 0,
                                     P<double>(h->dqpart), ldp, nullptr, st));
       } else if (use_i8) {
-        // K2c on the INT8 tensor pipe: slice r, then the tcgen05 product (timed together as "trmm")
+        // K2c on the INT8 tensor pipe: slice r (unless K1 already did), then the tcgen05 product (timed together as "trmm")
         KTimer t(h, st, 1);
-        MGP_CUDA(h, launch_ozaki_slice_r(P<double>(h->drP), h->npad, nCblk, P<uint8_t>(h->dRI8), h->trmm_i8_opt, st));
+        if (!k1_slices) {
+          MGP_CUDA(h, launch_ozaki_slice_r(P<double>(h->drP), h->npad, nCblk, P<uint8_t>(h->dRI8), h->trmm_i8_opt, st));
+          h->launches++;
+        }
         OzakiParams op;
         op.RI8 = P<uint8_t>(h->dRI8); op.MI8 = P<int8_t>(h->dMI8); op.scale = P<double>(h->dMscale);
         op.qpart = P<double>(h->dqpart); op.ldq = ldp; op.NI2 = h->npad / 64; op.nCblk = nCblk; op.nks = h->npad / 64;
@@ -1216,7 +1227,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       }
       EpiParams ep;
       ep.qpart = P<double>(h->dqpart); ep.meanpart = P<double>(h->dmeanpart); ep.ftpart = P<double>(h->dftpart);
-      ep.NI = mean_only ? 0 : (small ? h->npad / 32 : (use_i8 ? 2 * h->NI : h->NI)); ep.JS = JS; ep.ld = ldp; ep.mc = mc;
+      ep.NI = mean_only ? 0 : (small ? h->npad / 32 : (use_i8 ? 4 * h->NI : h->NI)); ep.JS = JS; ep.ld = ldp; ep.mc = mc;
       ep.beta = h->beta; ep.sigma2 = h->sigma2; ep.G = h->G; ep.ordinary = ordinary;
       ep.p = h->p; ep.PT = PT; ep.d = h->d; ep.trend_est = h->trend_est ? 1 : 0;
       ep.Xs = q.d_Xs + c0 * h->d; ep.betav = P<double>(h->dbetav); ep.Cinv = P<double>(h->dCinv);

@@ -11,6 +11,8 @@
 // epilogue recombines them in FP64:  T = 2^ea_i sum_s 2^-7(s+2) G_s.  What is dropped (p + q >= 8)
 // is below 2^-56 of the row scale per term; the slices themselves carry 2^-50 (both operands rounded
 // in their last digit).  The whole GPU parity suite passes with this path switched on.
+// The slices of r come from K1 itself where it can produce them (k_rgen<..., I8> in posterior.cu: 8
+// slices, SE / Matern, constant trend, d <= 40: no FP64 r in HBM at all), else from k_oz_slice_r below.
 //
 // Kernel shape (one persistent CTA per SM, warp-specialised, 1-CTA MMA):
 //   item = (64-row block I2 of L^-1, 128-candidate block cb);  D[c][i] in TMEM: lane = candidate,
@@ -25,8 +27,9 @@
 //                  MMAs per stage instead of 2 x 36 of N = 64: a third of the A-operand reads, which is
 //                  what bounded the N = 64 version at 57 cycles per MMA against 32 at the INT8 peak);
 //                  commits them to the ring / to the accumulator-full barrier;
-//   warps 2-5:     epilogue -- tcgen05.ld level by level (64 columns per thread = one candidate's
-//                  64 rows), FP64 recombination, square, sum: qpart[I2][c].
+//   warps 2-9:     epilogue -- a thread owns one candidate and 32 of the 64 rows: tcgen05.ld of the eight
+//                  level sums, exact 64-bit integer recombination of levels 0..3 and 4..7, two FP64
+//                  operations per row, square, sum: qpart[2 I2 + half][c].
 // Measured mainloop rate on B200 (tools/ozaki/umma_i8_rate.cu): 3195 cycles per stage against the
 // 8192 a DMMA tile needs at its peak: 2.56 x the FP64 tensor roofline.
 #include <cuda_runtime.h>
@@ -44,7 +47,7 @@ constexpr int OZ_BK = 64;                  // training columns per stage
 constexpr int OZ_A_SLICE = OZ_M * OZ_BK;   // 8 KB
 constexpr int OZ_B_SLICE = OZ_N * OZ_BK;   // 4 KB
 constexpr int OZ_NST = 2;
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_THREADS = 320;              // producer warp, MMA warp, 8 epilogue warps
 constexpr int OZ_TMEM_COLS = 512;
 // S = slices per operand: 8 (56 bits, 36 slice products per K step: the default, as accurate as the
 // DMMA path) or 7 (49 bits, 34 products: 12 % faster, about 10 x the rounding of the DMMA path)
@@ -74,20 +77,13 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld64(uint32_t addr, uint32_t (&v)[64]) {
+// 16 consecutive columns of this warp's 32 lanes; the caller issues several and waits once
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
-      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]),
-        "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]),
-        "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]),
-        "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(addr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // ---- per-fit: row scales of L^-1 and its int8 slices ------------------------------------------
@@ -226,7 +222,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
   if (tid == 0) {
     for (int s = 0; s < OZ_NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], PAIR ? 2 : 1); }
     mbar_init(&acc_full, 1);
-    mbar_init(&acc_empty, 128);
+    mbar_init(&acc_empty, 256);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -328,36 +324,47 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_trmm_i8(OzakiParams p) {
       }
     }
   } else {
-    // epilogue warps 2..5: TMEM lane quarter = warp % 4
-    const int quarter = warp & 3, cl = quarter * 32 + lane;           // candidate within the block
+    // epilogue warps 2..9: TMEM lane quarter = warp % 4 (the hardware's rule), column half = (warp - 2) / 4:
+    // a thread owns one candidate and 32 of the 64 rows.  The eight level sums of a row are combined
+    // EXACTLY in two 64-bit integers first (levels 0..3 and 4..7: |G_s| < 2^30, so |hi|, |lo| < 2^52 and
+    // their conversion to FP64 is exact): 2 conversions and 2 FP64 operations per row instead of 8 + 8,
+    // in chunks of 16 rows (8 x 16 TMEM words in registers); TMEM is released as soon as the last chunk
+    // has been read.  The two halves write separate partial sums (K3 adds them in a fixed order).
+    const int quarter = warp & 3, half = (warp - 2) >> 2, cl = quarter * 32 + lane;   // cl: candidate within the block
+    const double w_hi = __longlong_as_double((int64_t)(1023 - 35) << 52);           // 2^-7(3+2): weight of level 3
+    const double w_lo = __longlong_as_double((int64_t)(1023 - 63) << 52);           // 2^-7(7+2): weight of level 7
     int it = 0;
     for (int item = worker; item < nItems; item += nWorkers) {
       int I2, cb, nst;
       if (!decode(item, I2, cb, nst)) continue;
       mbar_wait(&acc_full, (uint32_t)(it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;");
-      double t[OZ_N];
-#pragma unroll
-      for (int i = 0; i < OZ_N; i++) t[i] = 0.0;
-      // smallest level first; level weight 2^-7(s+2)
-#pragma unroll 1
-      for (int s = OZ_LV - 1; s >= 0; s--) {
-        uint32_t v[64];
-        tmem_ld64(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * OZ_N), v);
-        const double wgt = __longlong_as_double((int64_t)(1023 - 7 * (s + 2)) << 52);
-#pragma unroll
-        for (int i = 0; i < OZ_N; i++) t[i] = fma((double)(int32_t)v[i], wgt, t[i]);
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;");
-      mbar_arrive(&acc_empty);                      // TMEM may be overwritten
+      const double *sc = p.scale + I2 * OZ_N + half * 32;
       double q = 0.0;
-      const double *sc = p.scale + I2 * OZ_N;
 #pragma unroll
-      for (int i = 0; i < OZ_N; i++) {
-        const double T = t[i] * sc[i];
-        q = fma(T, T, q);
+      for (int c = 0; c < 2; c++) {
+        uint32_t v[OZ_LV][16];
+#pragma unroll
+        for (int s = 0; s < OZ_LV; s++)
+          tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * OZ_N + half * 32 + c * 16), v[s]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;");
+          mbar_arrive(&acc_empty);                    // TMEM may be overwritten
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          int64_t hi = (int32_t)v[0][i], lo = (int32_t)v[4][i];
+#pragma unroll
+          for (int s = 1; s < 4; s++) {
+            hi = hi * 128 + (int32_t)v[s][i];
+            lo = lo * 128 + (int32_t)v[4 + s][i];
+          }
+          const double T = fma((double)hi, w_hi, (double)lo * w_lo) * sc[c * 16 + i];
+          q = fma(T, T, q);
+        }
       }
-      p.qpart[(int64_t)I2 * p.ldq + (int64_t)cb * OZ_M + cl] = q;
+      p.qpart[(int64_t)(2 * I2 + half) * p.ldq + (int64_t)cb * OZ_M + cl] = q;
       it++;
     }
   }

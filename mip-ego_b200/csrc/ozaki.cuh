@@ -9,7 +9,7 @@ struct OzakiParams {
   const uint8_t *RI8;   // r slices of the current chunk: [cand block][K stage][S slices][8 KB]
   const int8_t *MI8;    // L^-1 slices: [64-row block I2][K stage <= I2][S slices][4 KB]
   const double *scale;  // npad row scales 2^ea_i of L^-1
-  double *qpart;        // [NI2][ldq] partial sums of squares per 64-row block
+  double *qpart;        // [2 NI2][ldq] partial sums of squares per 32-row half block
   int64_t ldq;
   int NI2;              // npad / 64
   int nCblk;            // candidate blocks of 128

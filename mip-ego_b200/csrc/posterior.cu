@@ -62,7 +62,26 @@ __device__ __forceinline__ void trend_mma(double (&tacc)[P8][2], double r0, doub
   }
 }
 
-template <int CORR, int KS, bool LIN>
+// I8: instead of the packed FP64 r the kernel writes the eight 7-bit slices of r in the shared-memory
+// image of K2c-i8's A operand (ozaki.cu; stage = 64 training rows, slice = 8 KB, byte
+// (kk / 16) * 2048 + (c / 8) * 128 + (c % 8) * 16 + kk % 16): the lanes of a quad hold 2 x 2 adjacent
+// training rows of one candidate for an even / odd pair of 8-row groups, i.e. the 16 bytes of one
+// core-matrix row between them; two shuffles and a byte permute per slice give every lane one 32-bit
+// word of it, and a warp stores one full 128-byte core matrix per slice.  Saves the FP64 round trip
+// of r through HBM and the separate slicing pass (k_oz_slice_r).
+__device__ __forceinline__ void oz_fixed56(double r, uint32_t &lo, uint32_t &hi) {
+  const long long v = __double2ll_rn(r * 72057594037927936.0);   // rint(r 2^56), r in [0, 1]
+  lo = (uint32_t)v;
+  hi = (uint32_t)((unsigned long long)v >> 32);
+}
+template <int P>
+__device__ __forceinline__ uint32_t oz_digit56(uint32_t lo, uint32_t hi) {   // digit P of 8: bits [7 (7 - P), 7 (8 - P))
+  constexpr int sh = 7 * (7 - P);
+  if (P == 0) return hi >> (sh - 32);                                        // keeps the overflow (r = 1 -> 128)
+  return (sh >= 32 ? (hi >> (sh - 32)) : (sh == 0 ? lo : __funnelshift_r(lo, hi, sh))) & 127u;
+}
+
+template <int CORR, int KS, bool LIN, bool I8 = false>
 __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
   // Persistent: work item = (candidate block cb of 128, training block jb of 128).  The operands
   // of the training block (Bop rows, an, gamma, a) are staged once per item in shared memory.
@@ -117,30 +136,60 @@ __global__ void __launch_bounds__(256) k_rgen(RgenParams p) {
     __syncthreads();
     double macc[2] = {0.0, 0.0}, facc[2] = {0.0, 0.0};
     // output tile (cb, j8 = 16 jb + t8, c8 = 2 warp + u): one 64-bit base per item, 32-bit offsets inside
-    double *const dst0 = p.rP + (((int64_t)cb * p.NJ8 + jb * 16) * 16 + 2 * warp) * 64 + lane * 2;
-#pragma unroll 2
-    for (int t8 = 0; t8 < 16; t8++) {
-      const int jrow = 8 * t8 + lr, jcol = 8 * t8 + 2 * lk;
-      double bf[KS];
+    double *const dst0 = I8 ? nullptr : p.rP + (((int64_t)cb * p.NJ8 + jb * 16) * 16 + 2 * warp) * 64 + lane * 2;
+    // I8: stage (cb, ks = 2 jb + tp / 4); inside a slice: (tp % 4) * 2048 + (2 warp + u) * 128 + lr * 16 + 4 lk
+    uint8_t *const i8dst = I8 ? p.RI8 + ((int64_t)cb * p.nks + 2 * jb) * 65536 + warp * 256 + lr * 16 + lk * 4 : nullptr;
+#pragma unroll 1
+    for (int tp = 0; tp < 8; tp++) {
+      uint32_t flo[2][2][2], fhi[2][2][2];      // [e][u][value]: rint(r 2^56)
 #pragma unroll
-      for (int s = 0; s < KS; s++) bf[s] = sB[jrow * SB + 4 * s + lk];
-      const double2 an2 = *reinterpret_cast<const double2 *>(sV + jcol);
-      const double2 g2 = *reinterpret_cast<const double2 *>(sV + 128 + jcol);
-      const double2 a2 = *reinterpret_cast<const double2 *>(sV + 256 + jcol);
+      for (int e = 0; e < 2; e++) {
+        const int t8 = 2 * tp + e;
+        const int jrow = 8 * t8 + lr, jcol = 8 * t8 + 2 * lk;
+        double bf[KS];
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        double c0 = bn[u] + an2.x, c1 = bn[u] + an2.y;
+        for (int s = 0; s < KS; s++) bf[s] = sB[jrow * SB + 4 * s + lk];
+        const double2 an2 = *reinterpret_cast<const double2 *>(sV + jcol);
+        const double2 g2 = *reinterpret_cast<const double2 *>(sV + 128 + jcol);
+        const double2 a2 = *reinterpret_cast<const double2 *>(sV + 256 + jcol);
 #pragma unroll
-        for (int s = 0; s < KS; s++) dmma884(c0, c1, xa[u][s], bf[s]);
-        const double r0 = corr_from_S_tab<CORR>(c0, sTab), r1 = corr_from_S_tab<CORR>(c1, sTab);
-        *reinterpret_cast<double2 *>(dst0 + (t8 * 16 + u) * 64) = make_double2(r0, r1);
-        macc[u] = fma(g2.x, r0, macc[u]);
-        macc[u] = fma(g2.y, r1, macc[u]);
-        if (LIN) {
-          trend_mma<P8>(tacc[u], r0, r1, sBh, STB, t8, lr, lk);
-        } else {
-          facc[u] = fma(a2.x, r0, facc[u]);
-          facc[u] = fma(a2.y, r1, facc[u]);
+        for (int u = 0; u < 2; u++) {
+          double c0 = bn[u] + an2.x, c1 = bn[u] + an2.y;
+#pragma unroll
+          for (int s = 0; s < KS; s++) dmma884(c0, c1, xa[u][s], bf[s]);
+          const double r0 = corr_from_S_tab<CORR>(c0, sTab), r1 = corr_from_S_tab<CORR>(c1, sTab);
+          if (I8) {
+            oz_fixed56(r0, flo[e][u][0], fhi[e][u][0]);
+            oz_fixed56(r1, flo[e][u][1], fhi[e][u][1]);
+          } else {
+            *reinterpret_cast<double2 *>(dst0 + (t8 * 16 + u) * 64) = make_double2(r0, r1);
+          }
+          macc[u] = fma(g2.x, r0, macc[u]);
+          macc[u] = fma(g2.y, r1, macc[u]);
+          if (LIN) {
+            trend_mma<P8>(tacc[u], r0, r1, sBh, STB, t8, lr, lk);
+          } else {
+            facc[u] = fma(a2.x, r0, facc[u]);
+            facc[u] = fma(a2.y, r1, facc[u]);
+          }
+        }
+      }
+      if (I8) {
+        // word j of a core-matrix row = training rows 4 j .. 4 j + 3 of the 16: e = j / 2, source lanes lk' = 2 (j % 2), + 1
+        const int srcA = (lane & ~3) | ((lk & 1) << 1);
+        const uint32_t sel = (lk & 2) ? 0x7632u : 0x5410u;
+        uint8_t *const d0 = i8dst + (int64_t)(tp >> 2) * 65536 + (tp & 3) * 2048;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+#define OZ_EMIT(P)                                                                                               \
+          {                                                                                                        \
+            const uint32_t w = oz_digit56<P>(flo[0][u][0], fhi[0][u][0]) | (oz_digit56<P>(flo[0][u][1], fhi[0][u][1]) << 8) | \
+                               (oz_digit56<P>(flo[1][u][0], fhi[1][u][0]) << 16) | (oz_digit56<P>(flo[1][u][1], fhi[1][u][1]) << 24); \
+            const uint32_t xa_ = __shfl_sync(0xffffffffu, w, srcA), xb_ = __shfl_sync(0xffffffffu, w, srcA + 1);     \
+            *reinterpret_cast<uint32_t *>(d0 + P * 8192 + u * 128) = __byte_perm(xa_, xb_, sel);                     \
+          }
+          OZ_EMIT(0) OZ_EMIT(1) OZ_EMIT(2) OZ_EMIT(3) OZ_EMIT(4) OZ_EMIT(5) OZ_EMIT(6) OZ_EMIT(7)
+#undef OZ_EMIT
         }
       }
     }
@@ -1089,29 +1138,35 @@ cudaError_t launch_prep_model(const double *Xc, const double *theta, int npad, i
   return cudaGetLastError();
 }
 
-template <int CORR, int KS, bool LIN>
+template <int CORR, int KS, bool LIN, bool I8 = false>
 static cudaError_t rgen_launch(const RgenParams &p, int sm_count, cudaStream_t st) {
   static int occ = 0;
   static bool attr_done[MGP_MAX_DEVICES] = {};
   const int smem = (128 * rgen_stride(4 * KS) + 3 * 128 + MGP_EXP_TAB_DOUBLES +
                     (LIN ? 128 * trend_stride(trend_tiles(KS)) : 0)) * (int)sizeof(double);
   if (first_use_on_device(attr_done)) {
-    cudaFuncSetAttribute(k_rgen<CORR, KS, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen<CORR, KS, LIN>, 256, smem) != cudaSuccess || occ < 1)
+    cudaFuncSetAttribute(k_rgen<CORR, KS, LIN, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rgen<CORR, KS, LIN, I8>, 256, smem) != cudaSuccess || occ < 1)
       occ = 1;
   }
   const int items = p.nCblk * p.JS;
   const int grid = items < sm_count * occ ? items : sm_count * occ;
-  k_rgen<CORR, KS, LIN><<<grid, 256, smem, st>>>(p);
+  k_rgen<CORR, KS, LIN, I8><<<grid, 256, smem, st>>>(p);
   return cudaGetLastError();
+}
+// K1 can emit the int8 slices of K2c-i8 itself (8 slices, SE / Matern, constant trend, d <= 40)
+bool rgen_can_slice(int corr, int dpad, bool general_trend, int slices) {
+  return slices == 8 && !general_trend && dpad <= 40 && (corr == MGP_CORR_SE || corr == MGP_CORR_MATERN32);
 }
 int rgen_trend_cols(int dpad) { return 8 * ((dpad + 1 + 7) / 8); }
 template <int CORR>
 static cudaError_t rgen_dispatch(const RgenParams &p, int sm_count, cudaStream_t st) {
   switch (p.dpad / 4) {
 #define RG(K) case K: return p.Bhat ? rgen_launch<CORR, K, true>(p, sm_count, st) : rgen_launch<CORR, K, false>(p, sm_count, st);
-    RG(1) RG(2) RG(3) RG(4) RG(5) RG(6) RG(7) RG(8) RG(9) RG(10) RG(11) RG(12) RG(13) RG(14) RG(15) RG(16)
+#define RGI(K) case K: return p.Bhat ? rgen_launch<CORR, K, true>(p, sm_count, st) : (p.RI8 ? rgen_launch<CORR, K, false, true>(p, sm_count, st) : rgen_launch<CORR, K, false>(p, sm_count, st));
+    RGI(1) RGI(2) RGI(3) RGI(4) RGI(5) RGI(6) RGI(7) RGI(8) RGI(9) RGI(10) RG(11) RG(12) RG(13) RG(14) RG(15) RG(16)
 #undef RG
+#undef RGI
     default: return cudaErrorInvalidValue;
   }
 }

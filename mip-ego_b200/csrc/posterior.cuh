@@ -24,7 +24,11 @@ struct RgenParams {
   double *tpart;      // [JS][PT][ldp] partial sums of Bhat^T r (PT = 8 * ceil((4 KS + 1) / 8))
   double *rP, *meanpart, *ftpart;
   int64_t ldp;        // mc rounded up to 128
+  // K2c-i8: when set (and rgen_can_slice), K1 writes the eight int8 slices of r here INSTEAD of rP
+  uint8_t *RI8;
+  int nks;            // K = 64 stages per candidate block (npad / 64)
 };
+bool rgen_can_slice(int corr, int dpad, bool general_trend, int slices);
 // number of trend columns K1 accumulates for a given dpad (multiple of 8, >= d + 1)
 int rgen_trend_cols(int dpad);
 // K1: r tile generator, persistent over (candidate block, training block) items.

@@ -62,6 +62,13 @@ def test_i8_posterior_against_oracle(slices, n, d, kind, ordinary):
     mean_p, mse_p = gp.predict(Xs, eval_MSE=True)
     h.set_option("trmm_i8_pair", 0)
     assert np.array_equal(mse_p, mse) and np.array_equal(mean_p, mean)
+    # K1 emitting the slices itself (default where it can: 8 slices, SE / Matern, constant trend) against the
+    # separate slicing pass over the FP64 r: the same fixed-point digits, hence bitwise the same result
+    assert h.counter("trmm_i8_fuse") == 1
+    h.set_option("trmm_i8_fuse", 0)
+    mean_s, mse_s = gp.predict(Xs, eval_MSE=True)
+    h.set_option("trmm_i8_fuse", 1)
+    assert np.array_equal(mse_s, mse) and np.array_equal(mean_s, mean)
     plugin = float(y.min())
     for crit, name, par in ((mb.EI(model=gp, minimize=True, plugin=plugin), "EI", None),
                             (mb.MGFI(model=gp, minimize=True, plugin=plugin, t=2.0), "MGFI", 2.0),
