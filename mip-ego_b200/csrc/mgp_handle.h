@@ -83,6 +83,9 @@ struct mgp_handle {
   DevBuf dMI8, dMscale, dRI8;
   bool i8_ready = false;
   int trmm_i8_opt = 0;
+  // small host-pointer calls: pinned page mapped into the device address space (candidates in, results out)
+  void *hpin = nullptr, *hpin_dev = nullptr;
+  int zero_copy_opt = 1;
   int trmm_i8_fuse = 1;        // K1 writes the int8 slices of r directly (SE / Matern, constant trend, 8 slices, d <= 40)
   int trmm_i8_pair = 0;        // K2c-i8 as clusters of two CTAs with multicast candidate slices (no gain measured: off)
   bool rinv_ready = false;

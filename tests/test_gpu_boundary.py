@@ -171,6 +171,48 @@ def test_device_and_host_entry_points_interleave_without_explicit_sync():
         assert np.all(np.isfinite(mean_b))
 
 
+# ---- small host-pointer calls through the mapped pinned page ---------------------------------------------
+@pytest.mark.parametrize("kind,ordinary", [("squared_exponential", True), ("matern", False)])
+def test_small_calls_zero_copy_equals_copy_engine_path(kind, ordinary):
+    """Calls with <= 4 KB of candidates (the reference optimisers' one-point-per-call pattern,
+    optimizer/utils.py:38-42) read their input from, and write their results to, a pinned page mapped into
+    the device address space -- no copy engine, no events, one synchronisation.  Every output kind must be
+    bitwise what the three-stream staging path returns, at every m up to the limit and one beyond it."""
+    mb, O = _mods()
+    d = 6
+    X, y, rng = _data(700, d, 21)
+    theta = (0.2 / d) * rng.uniform(0.5, 1.5, d)
+    gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None if ordinary else 0.1), corr=kind, theta0=theta,
+                            thetaL=[1e-5] * d, thetaU=[100.0] * d, nugget=1e-6)
+    gp.fit_fixed(X, y, np.r_[theta, 0.9])
+    h = gp._handle()
+    ei = mb.EI(model=gp, minimize=True)
+    mg = mb.MGFI(model=gp, minimize=True, t=1.0)
+    ts = [0.5, 1.0, 2.0]
+
+    def everything(Z):
+        out = list(gp.predict(np.atleast_2d(Z), eval_MSE=True)) + list(gp.gradient_batch(np.atleast_2d(Z)))
+        out += list(ei(Z, return_dx=True)) + [ei(Z)] + [mg.evaluate(np.atleast_2d(Z), params=ts)]
+        return [np.asarray(a) for a in out]
+
+    assert h.counter("zero_copy") == 1
+    for m in (1, 2, 8, 9, 33, 85, 86):            # 85 x 6 x 8 B = 4080 B: the last size on the page
+        Z = rng.uniform(-5, 5, (m, d)) if m > 1 else rng.uniform(-5, 5, d)
+        a = everything(Z)
+        h.set_option("zero_copy", 0)
+        b = everything(Z)
+        h.set_option("zero_copy", 1)
+        for u, v in zip(a, b):
+            assert u.shape == v.shape and np.array_equal(u, v), m
+    # against the oracle once, through the page
+    st = O.fit_state(X, y, np.r_[theta, 0.9], kind, ordinary, 0.1, "noisy", 1e-6)
+    Z = rng.uniform(-5, 5, (5, d))
+    rm, rs = O.predict(st, Z)
+    mean, mse = gp.predict(Z, eval_MSE=True)
+    assert np.max(np.abs(mean - rm) / (np.abs(rm) + 1e-3)) < 1e-9
+    assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-7
+
+
 # ---- CUDA graphs of the batched likelihood ---------------------------------------------------------------
 def test_likelihood_graphs_are_bitwise_the_eager_path():
     """A batch shape is captured in a CUDA graph at its second use and replayed afterwards (host
