@@ -33,7 +33,9 @@ def _model(mb, O, n, d, kind, ordinary, seed):
 @pytest.mark.parametrize("slices", [8, 7])
 @pytest.mark.parametrize("n,d,kind,ordinary", [(500, 10, "squared_exponential", True), (1100, 7, "matern", True),
                                                (333, 3, "matern", False), (1999, 12, "squared_exponential", False),
-                                               (64, 2, "squared_exponential", True), (129, 5, "absolute_exponential", True)])
+                                               (64, 2, "squared_exponential", True), (129, 5, "absolute_exponential", True),
+                                               # d = 40: the widest K1 that emits the slices itself; d = 44: separate slicing pass
+                                               (300, 40, "matern", False), (300, 44, "squared_exponential", True)])
 def test_i8_posterior_against_oracle(slices, n, d, kind, ordinary):
     mb, O = _mods()
     gp, st, X, y, rng = _model(mb, O, n, d, kind, ordinary, 1000 + n)

@@ -12,6 +12,9 @@ WANT = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "sm_
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "sm__cycles_elapsed.max"]
+# every tensor-pipe / TMEM / clock metric the capture holds (names differ between pipes: take them by pattern)
+PATTERNS = ("sm__pipe_tensor", "sm__inst_executed_pipe_tensor", "sm__inst_executed_pipe_uniform", "tmem", "sm__cycles_active.avg",
+            "gpc__cycles_elapsed.avg.per_second", "sm__throughput.avg", "gpu__dram_throughput", "lts__throughput")
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 for r in rows[2:]:
@@ -20,3 +23,6 @@ for r in rows[2:]:
         if w in hdr:
             i = hdr.index(w)
             print("  %-88s %s %s" % (w, r[i], units[i]))
+    for i, name in enumerate(hdr):
+        if name not in WANT and any(pt in name for pt in PATTERNS):
+            print("  %-88s %s %s" % (name, r[i], units[i]))
