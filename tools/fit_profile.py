@@ -1,6 +1,8 @@
+"""Where the time of GaussianProcess.fit goes (n = 500, d = 10, 10 lock-step restarts): wall time, the share spent
+inside mgp_nll_batch, and a cProfile listing.  Output committed as profiles/r02_fit_profile.txt."""
 import os, sys, time, cProfile, pstats
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mipego_b200 as mb
 n, d, R = 500, 10, 10
 rng = np.random.default_rng(0); X = rng.uniform(-5, 5, (n, d)); y = (X**2).sum(1)+3*np.sin(X[:,0]); y=(y-y.mean())/y.std()

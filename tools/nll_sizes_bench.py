@@ -1,6 +1,8 @@
+"""Likelihood + gradient at n = 512 ... 4096 with 8 and 64 parameter vectors per call: device time (CUDA events on the
+launching stream) and host time of the call, eager launches and CUDA-graph replay.  Output: profiles/r02_nll_sizes.txt."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, mipego_b200 as mb
 d = 20
 for n in (512, 1024, 2048, 4096):
