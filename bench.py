@@ -569,8 +569,11 @@ def bench_posterior(ctx, args, name, steps, warmup, cpu=True):
             pairs = 36 if i8 == 8 else 34
             # per candidate and slice product: n^2 / 2 multiply-adds over the triangle = n^2 int8 ops
             int8_ops = pairs * float(n) * n * (value / ctx.world)             # per GPU per second
-            line["roofline"]["kernel"] = ("k_oz_slice_r + k_trmm_i8<%d> (T = L^-1 r as %d exact int8 slice products, "
-                                          "tcgen05.mma kind::i8, TMEM accumulators, FP64 recombination)" % (i8, pairs))
+            fused = bool(h.counter("trmm_i8_fuse")) and i8 == 8 and kind != "absolute_exponential" and d <= 40
+            line["roofline"]["kernel"] = ("%sk_trmm_i8<%d> (T = L^-1 r as %d exact int8 slice products, tcgen05.mma kind::i8, "
+                                          "TMEM accumulators, FP64 recombination%s)"
+                                          % ("" if fused else "k_oz_slice_r + ", i8, pairs,
+                                             "; the int8 slices of r are written by K1 itself" if fused else ""))
             line["roofline"]["int8"] = {"achieved": int8_ops / 1e12, "peak": 4500.0, "unit": "TOP/s",
                                         "frac": int8_ops / 4.5e15,
                                         "peak_source": "nominal dense INT8 of B200 (no measured INT8 entry in MEASURED_PEAKS.json)",
