@@ -1114,7 +1114,7 @@ static int post_workspace(mgp_handle *h, bool want_dx) {
   MGP_TRY(mgp_ensure(h, h->drP, (size_t)h->npad * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dmeanpart, (size_t)h->NI * chunk * 8));
   MGP_TRY(mgp_ensure(h, h->dftpart, (size_t)h->NI * chunk * 8));
-  MGP_TRY(mgp_ensure(h, h->dqpart, (size_t)(h->trmm_i8_opt ? 4 : 1) * h->NI * chunk * 8));
+  MGP_TRY(mgp_ensure(h, h->dqpart, (size_t)(h->trmm_i8_opt ? 4 : 2) * h->NI * chunk * 8));
   if (h->trmm_i8_opt) MGP_TRY(mgp_ensure(h, h->dRI8, ozaki_r_bytes(h->npad, chunk, h->trmm_i8_opt)));
   if (want_dx) MGP_TRY(mgp_ensure(h, h->dwP, (size_t)h->npad * chunk * 8));
   if (h->p > 1 && h->trend_est)
@@ -1186,7 +1186,8 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
     const int JS = h->NI;
     const bool small = mc <= 8 && !h->no_small_path;   // matrix-vector path for tiny populations
     const bool mean_only = !q.want_dx && !acq && !q.d_mse;   // predict(eval_MSE=False): K1 alone gives r . gamma
-    const bool use_i8 = h->trmm_i8_opt && !q.want_dx && !small && !mean_only;
+    // (npad <= 16384: a level sum of up to 8 slice products stays below 8 x 16384 x 64 x 128 = 2^30 in int32)
+    const bool use_i8 = h->trmm_i8_opt && !q.want_dx && !small && !mean_only && h->npad <= 16384;
     // K1 writes the int8 slices itself where it can (no FP64 r, no separate slicing pass)
     const bool k1_slices = use_i8 && h->trmm_i8_fuse && rgen_can_slice(h->corr, h->dpad, gen, h->trmm_i8_opt);
     RgenParams rp;
@@ -1233,7 +1234,7 @@ static int posterior_run(mgp_handle *h, const PostReq &q, cudaStream_t st) {
       }
       EpiParams ep;
       ep.qpart = P<double>(h->dqpart); ep.meanpart = P<double>(h->dmeanpart); ep.ftpart = P<double>(h->dftpart);
-      ep.NI = mean_only ? 0 : (small ? h->npad / 32 : (use_i8 ? 4 * h->NI : h->NI)); ep.JS = JS; ep.ld = ldp; ep.mc = mc;
+      ep.NI = mean_only ? 0 : (small ? h->npad / 32 : (use_i8 ? 4 * h->NI : 2 * h->NI)); ep.JS = JS; ep.ld = ldp; ep.mc = mc;
       ep.beta = h->beta; ep.sigma2 = h->sigma2; ep.G = h->G; ep.ordinary = ordinary;
       ep.p = h->p; ep.PT = PT; ep.d = h->d; ep.trend_est = h->trend_est ? 1 : 0;
       ep.Xs = q.d_Xs + c0 * h->d; ep.betav = P<double>(h->dbetav); ep.Cinv = P<double>(h->dCinv);

@@ -351,10 +351,6 @@ __device__ __forceinline__ void slab_mma_upto(int rt1, double (&acc)[8][4][2], c
   }
 }
 
-__device__ __forceinline__ void consumer_sync() {  // named barrier 1: the 8 consumer warps only
-  asm volatile("bar.sync 1, 256;\n" ::: "memory");
-}
-
 template <bool FULL>
 __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
   // Warp-specialised: warpgroups 0-1 (warps 0-7) are MMA consumers, warpgroup 2 is the producer.
@@ -366,7 +362,6 @@ __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
   double *Bs = As + TS * STAGE_DBL;
   uint64_t *full = reinterpret_cast<uint64_t *>(Bs + TS * STAGE_DBL);
   uint64_t *empty = full + TS;
-  double *red = reinterpret_cast<double *>(empty + TS);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nItems = p.NI * p.nCblk;
@@ -485,16 +480,16 @@ __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
           s += __shfl_xor_sync(0xffffffffu, s, 16);
           qs[ct][e] = s;
         }
+      // Every warp writes the sums of ITS 64 rows (row parity wr) straight from registers: partial row
+      // 2 I + wr of qpart, added in a fixed order by K3.  No barrier between the consumer warps at the end
+      // of an item: a warp that is done moves on to the next item's stages while the other warp of its SM
+      // sub-partition is still issuing DMMAs (the two consumer barriers per item of the earlier version,
+      // which summed the two parities through shared memory, left the tensor pipe idle 8 % of the time).
       if (lr == 0) {
+        double *qrow = p.qpart + (int64_t)(2 * I + wr) * p.ldq + (int64_t)cb * 128 + wc * 32 + 2 * lk;
 #pragma unroll
-        for (int ct = 0; ct < 4; ct++) {
-          red[wr * 128 + wc * 32 + ct * 8 + 2 * lk] = qs[ct][0];
-          red[wr * 128 + wc * 32 + ct * 8 + 2 * lk + 1] = qs[ct][1];
-        }
+        for (int ct = 0; ct < 4; ct++) *reinterpret_cast<double2 *>(qrow + ct * 8) = make_double2(qs[ct][0], qs[ct][1]);
       }
-      consumer_sync();
-      if (tid < 128) p.qpart[(int64_t)I * p.ldq + (int64_t)cb * 128 + tid] = red[tid] + red[128 + tid];
-      consumer_sync();
     } else {
       // W[j][c] for j in row block I: thread holds rows 8(2rt+wr)+lr, cols 8(wc*4+ct)+2lk+{0,1}.
       // rP-style layout wants, per (j8, c8) tile, element (cc, jj) at cc*8 + jj.

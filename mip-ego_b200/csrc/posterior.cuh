@@ -37,7 +37,7 @@ cudaError_t launch_rgen(const RgenParams &p, int corr, int sm_count, cudaStream_
 struct TrmmParams {
   const double *Mp;   // packed operand (triangular L^-1 or full R^-1)
   const double *rP;   // packed r
-  double *qpart;      // [NI][ldq] partial sums of squares          (full == 0)
+  double *qpart;      // [2 NI][ldq] partial sums of squares: row 2 I + (row parity of the warp)   (full == 0)
   double *wP;         // packed W = R^-1 r, same layout as rP        (full == 1)
   int NI, nCblk, NJ8, full;
   int64_t ldq;

@@ -45,6 +45,7 @@ def test_i8_posterior_against_oracle(slices, n, d, kind, ordinary):
     Xs[:40] = X[:40] + 1e-4 * rng.standard_normal((40, d))       # next to training points: 1 - |T|^2 cancels
     Xs[40:44] = X[:4]                                            # on training points
     rm, rs = O.predict(st, Xs)
+    h.set_option("trmm_i8", 0)                                   # (a process started with MGP_TRMM_I8=1 has it on)
     mean_f, mse_f = gp.predict(Xs, eval_MSE=True)                # FP64 DMMA path
     h.set_option("trmm_i8", slices)
     assert h.counter("trmm_i8") == slices
