@@ -351,6 +351,21 @@ __device__ __forceinline__ void slab_mma_upto(int rt1, double (&acc)[8][4][2], c
   }
 }
 
+// Item order: candidate blocks in groups of G = gridDim.x, inside a group the row blocks in decreasing
+// cost, candidate block innermost.  Dealt round-robin, CTA w of a full group therefore walks ALL row
+// blocks of ONE candidate block (g G + w) one after the other and finds its r tile, which it read from
+// HBM for the longest row block, in L2 for the others: at C2 the DRAM reads of a launch fall from
+// (1 + 2 + 3 + 4) / 4 = 2.5 x the r chunk to about 1 x, and every CTA still gets one item per cost class
+// (the order "all candidate blocks of row block NI - 1, then NI - 2, ..." it replaces was equally balanced
+// but re-read every r tile NI times from HBM).  The last group may be ragged.
+__device__ __forceinline__ void trmm_item(int item, int NI, int nCblk, int G, int &I, int &cb) {
+  const int per = G * NI;
+  const int grp = item / per, rem = item - grp * per;
+  const int gsz = min(G, nCblk - grp * G);
+  I = NI - 1 - rem / gsz;
+  cb = grp * G + rem % gsz;
+}
+
 template <bool FULL>
 __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
   // Warp-specialised: warpgroups 0-1 (warps 0-7) are MMA consumers, warpgroup 2 is the producer.
@@ -381,7 +396,8 @@ __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
     if (warp == 8 && lane == 0) {
       int64_t x = 0;
       for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
-        const int I = p.NI - 1 - item / p.nCblk, cb = item % p.nCblk;
+        int I, cb;
+        trmm_item(item, p.NI, p.nCblk, (int)gridDim.x, I, cb);
         const int nkc = FULL ? p.NJ8 / 4 : 4 * (I + 1);
         for (int kc = 0; kc < nkc; kc++, x++) {
           const int stage = (int)(x % TS);
@@ -418,7 +434,8 @@ __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
   const int wr = warp >> 2, wc = warp & 3, lr = lane >> 2, lk = lane & 3;
   int64_t x = 0;
   for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
-    const int I = p.NI - 1 - item / p.nCblk, cb = item % p.nCblk;
+    int I, cb;
+    trmm_item(item, p.NI, p.nCblk, (int)gridDim.x, I, cb);
     const int nkc = FULL ? p.NJ8 / 4 : 4 * (I + 1);
     double acc[8][4][2];
 #pragma unroll
