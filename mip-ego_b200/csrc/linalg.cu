@@ -509,6 +509,8 @@ __device__ long long g_diag_clk[16];
 
 // Barrier of the 15 warps that work beside the factoring warp (named barrier 1).
 __device__ __forceinline__ void bar_side() { asm volatile("bar.sync 1, 480;\n" ::: "memory"); }
+template <int NW>
+__device__ __forceinline__ void bar_side_n() { asm volatile("bar.sync 1, %0;\n" ::"n"(NW * 32) : "memory"); }
 
 // Block row i >= 1 of the inverse, in place: rows < i of S already hold the inverse (diagonal
 // sub-blocks included), row i still holds L (already saved by the caller).  ALL: executed by the
@@ -518,10 +520,10 @@ __device__ __forceinline__ void bar_side() { asm volatile("bar.sync 1, 480;\n" :
 // shared-memory bandwidth (8 loads per 16 FMAs; one fragment pair feeds 256).  With the row stride
 // DS = 4 (mod 16) every fragment load is conflict-free (at stride 129 they were 4-way conflicted
 // and this version was slower than the patches: 63 against 56 us for the whole kernel).
-template <bool ALL>
+template <bool ALL, int NSIDE = DIAG_THREADS / 32 - 1>
 __device__ __forceinline__ void inverse_block_row(double *S, const double *Xd, int i, int tid) {
-  auto sync = [] { if (ALL) __syncthreads(); else bar_side(); };
-  constexpr int NW = ALL ? DIAG_THREADS / 32 : DIAG_THREADS / 32 - 1;
+  auto sync = [] { if (ALL) __syncthreads(); else bar_side_n<NSIDE>(); };
+  constexpr int NW = ALL ? DIAG_THREADS / 32 : NSIDE;
   constexpr int NT = NW * 32;
   const int t = ALL ? tid : tid - 32, w = t >> 5, lane = t & 31, lr = lane >> 2, lk = lane & 3;
   const int ntile = 16 * i;             // 4 tile rows x 4 i tile columns
@@ -718,6 +720,287 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag(double *A, double *
   DIAG_T(7);
 }
 
+// ---- version 2 of the diagonal-block kernel ---------------------------------------------------
+// Same result, shorter serial chain.  What version 1 keeps on warp 0's critical path per 32-wide
+// sub-column -- the inverse of the sub-block (needed for the sub-panel P = A D^-T), the sub-panel and
+// the whole symmetric update -- is taken off it:
+//   * warp 0 publishes every column of L_ss (column-major copy `Lc`, double-buffered over s) and
+//     1 / l_jj, four columns at a time (release store of a counter); warps 13..15 solve the rows below
+//     by forward SUBSTITUTION, one row per lane with the row in registers, consuming the columns as
+//     they appear: the sub-panel is complete a few hundred cycles after the sub-block.  No inverse on
+//     the path; the inverse of the sub-block is computed by a side warp (the same substitution applied
+//     to the unit vectors) while the next sub-block is being factored;
+//   * of the symmetric update only the ten 8x8 tiles of the NEXT diagonal sub-block are applied before
+//     warp 0 starts factoring it; the rest of the update, the stores and the block row of the inverse
+//     run on warps 1..12 meanwhile;
+//   * inside the factorisation of a sub-block the pivot chain is  1/sqrt -> l -> (a - l^2) -> shuffle:
+//     the next pivot comes from the pivot lane's own registers, the two columns right of the pivot are
+//     updated from shuffled values, and the shared-memory round trip of the rest of the column update
+//     is deferred by one step so that it runs under the next pivot's 1/sqrt;
+//   * 1/sqrt(d) is MUFU.RSQ64H (rsqrt.approx.f64, ~2^-21) with one third-order correction, error
+//     O(e^3), instead of the library routine.
+constexpr int LCS = 34;      // column stride of Lc (even: the broadcast reads of a column are 16-byte loads)
+constexpr int NSIDE2 = 12;   // warps 1..12: side work; warps 13..15: sub-panel rows
+constexpr int kDiag2SmemDbl = 128 * DS + 4 * 32 * XS + 2 * 32 * LCS + 2 * 32 + 2;
+
+__device__ __forceinline__ double rsqrt_pos(double d) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y0) : "d"(d));
+  const double t = d * y0;
+  const double e = fma(-t, y0, 1.0);          // 1 - d y0^2
+  const double p = fma(0.375, e, 0.5);
+  const double q = y0 * e;
+  return fma(q, p, y0);                       // y0 (1 + e/2 + 3 e^2 / 8)
+}
+
+__device__ __forceinline__ void st_release_cta(int *p, int v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;\n" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta(const int *p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+
+// a[k] -= p * col[k] for k in [K0, 32): col is 16-byte aligned, broadcast reads as double2
+template <int K0>
+__device__ __forceinline__ void axpy_from(double (&a)[32], double p, const double *col) {
+  constexpr int KE = K0 & ~1;
+#pragma unroll
+  for (int k = KE; k < 32; k += 2) {
+    const double2 c = *reinterpret_cast<const double2 *>(col + k);
+    if (k >= K0) a[k] = fma(-p, c.x, a[k]);
+    a[k + 1] = fma(-p, c.y, a[k + 1]);
+  }
+}
+
+template <int J>
+__device__ __forceinline__ void potrf32_step(double (&a)[32], double &d, double &lprev, int &bad, double *Lc,
+                                             double *rinv, int *ready, int ready0, int lane, int pivot0) {
+  // deferred part of column J - 1 (published before the previous step's __syncwarp): independent of
+  // the pivot chain below, the scheduler runs it under the latency of the reciprocal square root
+  if constexpr (J >= 1) axpy_from<J + 2>(a, lprev, Lc + (J - 1) * LCS);
+  bad = (bad == 0 && !(d > 0.0)) ? pivot0 + J + 1 : bad;
+  const double inv = rsqrt_pos(d);
+  const double l = (lane == J) ? d * inv : a[J] * inv;
+  a[J] = l;
+  Lc[J * LCS + lane] = (lane >= J) ? l : 0.0;
+  if (lane == J) rinv[J] = inv;
+  if constexpr (J < 31) {
+    // the next pivot from the pivot lane's own registers
+    const double dn = fma(-l, l, a[J + 1]);
+    d = __shfl_sync(0xffffffffu, dn, J + 1);
+    // the two columns the next step needs in full, from the owning lanes' registers
+    const double l1 = __shfl_sync(0xffffffffu, l, J + 1);
+    a[J + 1] = fma(-l, l1, a[J + 1]);
+  }
+  if constexpr (J < 30) {
+    const double l2 = __shfl_sync(0xffffffffu, l, J + 2);
+    a[J + 2] = fma(-l, l2, a[J + 2]);
+  }
+  lprev = l;
+  __syncwarp();
+  if constexpr ((J & 3) == 3) {
+    if (lane == 0) st_release_cta(ready, ready0 + J + 1);   // columns .. J are visible to the solving warps
+  }
+  if constexpr (J < 31) potrf32_step<J + 1>(a, d, lprev, bad, Lc, rinv, ready, ready0, lane, pivot0);
+}
+
+// Factor the 32x32 sub-block D (stride DS, read only) : Lc[j * LCS + i] = L[i][j] (zeros above the
+// diagonal), rinv[j] = 1 / L[j][j].  scr: 32 x PS scratch.  *ready counts the published columns
+// (ready0 + 4, + 8, ... + 32).
+__device__ __forceinline__ void warp_potrf32_v2(const double *D, double *scr, double *Lc, double *rinv,
+                                                int *ready, int ready0, int lane, int pivot0, int *status) {
+  double a[32];
+#pragma unroll
+  for (int r = 0; r < 32; r++) a[r] = D[r * DS + lane];
+#pragma unroll
+  for (int r = 0; r < 32; r++) scr[r * PS + lane] = a[r];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 32; k++) a[k] = scr[lane * PS + k];
+  int bad = 0;
+  double d = __shfl_sync(0xffffffffu, a[0], 0), lprev = 0.0;
+  potrf32_step<0>(a, d, lprev, bad, Lc, rinv, ready, ready0, lane, pivot0);
+  if (bad && lane == 0) atomicCAS(status, 0, bad);
+}
+
+// Column-oriented forward substitution with L_ss: a <- the solution x of  x L_ss^T = a  (a row of the
+// sub-panel), equally of  L_ss x = a  (a column of the inverse when a is a unit vector).
+// WAIT: the columns are consumed while warp 0 is still producing them (four at a time).
+template <int J, bool WAIT>
+__device__ __forceinline__ void solve32_step(double (&a)[32], const double *Lc, const double *rinv,
+                                             const int *ready, int ready0) {
+  if constexpr (WAIT && (J & 3) == 0) {
+    while (ld_acquire_cta(ready) < ready0 + J + 4) { }
+  }
+  const double p = a[J] * rinv[J];
+  a[J] = p;
+  axpy_from<J + 1>(a, p, Lc + J * LCS);
+  if constexpr (J < 31) solve32_step<J + 1, WAIT>(a, Lc, rinv, ready, ready0);
+}
+// One row of the sub-panel P = A L_ss^-T, in place (row = 32 doubles at `row`, 16-byte aligned).
+__device__ __forceinline__ void lane_solve32(double *row, const double *Lc, const double *rinv,
+                                             const int *ready, int ready0) {
+  double a[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) {
+    const double2 v = *reinterpret_cast<const double2 *>(row + k);
+    a[k] = v.x; a[k + 1] = v.y;
+  }
+  solve32_step<0, true>(a, Lc, rinv, ready, ready0);
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) *reinterpret_cast<double2 *>(row + k) = make_double2(a[k], a[k + 1]);
+}
+// X = L_ss^-1: column `lane` of X solves L x = e_lane.
+__device__ __forceinline__ void warp_trtri32_lc(const double *Lc, const double *rinv, double *X, int lane) {
+  double a[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) a[k] = (k == lane) ? 1.0 : 0.0;
+  solve32_step<0, false>(a, Lc, rinv, nullptr, 0);
+#pragma unroll
+  for (int i = 0; i < 32; i++) X[i * XS + lane] = (lane <= i) ? a[i] : 0.0;
+}
+
+// C[tr][tc] -= P[tr] P[tc]^T for one 8x8 tile of the rows below sub-block s (o = 32 s): P = rows
+// o+32.. of column block s, C = the same rows of the columns right of it.  Two accumulator chains.
+__device__ __forceinline__ void upd_tile(double *S, int o, int tr, int tc, int lane) {
+  const int lr = lane >> 2, lk = lane & 3;
+  const double *P = S + (o + 32) * DS + o;
+  const double *ap = P + (8 * tr + lr) * DS + lk, *bp = P + (8 * tc + lr) * DS + lk;
+  double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    dmma884(e0, e1, ap[k], bp[k]);
+    dmma884(f0, f1, ap[k + 4], bp[k + 4]);
+  }
+  double2 *cp = reinterpret_cast<double2 *>(S + (o + 32 + 8 * tr + lr) * DS + o + 32 + 8 * tc + 2 * lk);
+  double2 c = *cp;
+  c.x -= e0 + f0;
+  c.y -= e1 + f1;
+  *cp = c;
+}
+
+// Named barriers of version 2: 1 = the NSIDE2 side warps among themselves (bar_side_n), 2 = side warps
+// (arrive) -> solving warps (sync): the rows below the next sub-block have received step i's update,
+// 3 = warps 1..15 in the tail.
+__device__ __forceinline__ void bar2_arrive() { asm volatile("bar.arrive 2, %0;\n" ::"n"((NSIDE2 + 3) * 32) : "memory"); }
+__device__ __forceinline__ void bar2_sync() { asm volatile("bar.sync 2, %0;\n" ::"n"((NSIDE2 + 3) * 32) : "memory"); }
+__device__ __forceinline__ void bar3_sync() { asm volatile("bar.sync 3, 480;\n" ::: "memory"); }
+
+// What warps 1..12 do while warp 0 factors sub-block i + 1: the rest of step i's symmetric update
+// (first the tile columns of block column i + 1, which the solving warps are waiting for), L block row
+// i -> global, X_ii (warp 1), block row i of the inverse in place, -> global.
+__device__ __forceinline__ void diag2_side(double *S, double *Xd, const double *lc, const double *ri,
+                                           double *Lb, int ld, double *Ib, int i, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, t = tid - 32, o = 32 * i;
+  const int np8 = (96 - o) / 8, m = np8 - 4, nLR = 4 * m;
+  constexpr int NT = NSIDE2 * 32;
+  // rows 4.. of tile columns 0..3 (block column i + 1 below its diagonal sub-block)
+  for (int q = warp - 1; q < nLR; q += NSIDE2) upd_tile(S, o, 4 + (q >> 2), q & 3, lane);
+  bar2_arrive();
+  if (warp == 1) {
+    warp_trtri32_lc(lc, ri, Xd + i * 32 * XS, lane);
+  } else if (m > 0) {
+    // the lower tiles of the (np8 - 4)^2 grid right of block column i + 1
+    const int ntile = m * (m + 1) / 2;
+    for (int u = warp - 2; u < ntile; u += NSIDE2 - 1) {
+      int a = 0;
+      while ((a + 1) * (a + 2) / 2 <= u) a++;
+      upd_tile(S, o, 4 + a, 4 + u - a * (a + 1) / 2, lane);
+    }
+  }
+  store_block_row(S, Lb, ld, i, t, NT);
+  bar_side_n<NSIDE2>();
+  if (i == 0) {
+    for (int idx = t; idx < 32 * 32; idx += NT)
+      S[(idx >> 5) * DS + (idx & 31)] = Xd[(idx >> 5) * XS + (idx & 31)];
+    bar_side_n<NSIDE2>();
+  } else {
+    inverse_block_row<false, NSIDE2>(S, Xd, i, tid);
+  }
+  store_block_row(S, Ib, 128, i, t, NT);
+}
+
+__global__ void __launch_bounds__(DIAG_THREADS) k_potrf_diag2(double *A, double *Lout, int ld,
+                                                               int64_t sA, double *linv,
+                                                               int64_t sInv, int kb, int *status) {
+  extern __shared__ __align__(16) double S[];
+  double *Xd = S + 128 * DS, *Lc = Xd + 4 * 32 * XS, *rinv = Lc + 2 * 32 * LCS;
+  int *ready = reinterpret_cast<int *>(rinv + 2 * 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+  const double *Ab = A + b * sA + (int64_t)kb * 128 * ld + kb * 128;
+  double *Lb = Lout + b * sA + (int64_t)kb * 128 * ld + kb * 128;
+  double *Ib = linv + b * sInv + (int64_t)kb * 128 * 128;
+  DIAG_T(0);
+  if (tid == 0) *ready = 0;
+  {
+    double2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int idx = tid + DIAG_THREADS * q, r = idx >> 6, c = 2 * (idx & 63);
+      v[q] = (c <= r) ? *reinterpret_cast<const double2 *>(Ab + (int64_t)r * ld + c) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int idx = tid + DIAG_THREADS * q, r = idx >> 6, c = 2 * (idx & 63);
+      S[r * DS + c] = v[q].x;
+      S[r * DS + c + 1] = (c + 1 <= r) ? v[q].y : 0.0;
+    }
+  }
+  __syncthreads();
+  DIAG_T(1);
+  for (int s = 0; s < 4; s++) {
+    const int o = 32 * s, nb = 96 - o;
+    double *lc = Lc + (s & 1) * 32 * LCS, *ri = rinv + (s & 1) * 32;
+    if (warp == 0) {
+      warp_potrf32_v2(S + o * DS + o, Xd + s * 32 * XS, lc, ri, ready, 32 * s, lane, kb * 128 + o, &status[b]);
+    } else if (warp <= NSIDE2) {
+      if (s > 0)
+        diag2_side(S, Xd, Lc + ((s - 1) & 1) * 32 * LCS, rinv + ((s - 1) & 1) * 32, Lb, ld, Ib, s - 1, tid);
+    } else {
+      // rows below sub-block s: final once step s - 1's update of block column s is in (barrier 2)
+      if (s > 0) bar2_sync();
+      if (warp - (NSIDE2 + 1) < nb / 32)
+        lane_solve32(S + (o + 32 + 32 * (warp - (NSIDE2 + 1)) + lane) * DS + o, lc, ri, ready, 32 * s);
+    }
+    __syncthreads();   // L_ss published, sub-panel in place, the side work of step s - 1 complete
+    if (s == 0) DIAG_T(8);
+    if (s == 3) break;
+    if (warp >= 1 && warp <= 10) {
+      // the ten lower tiles of the next diagonal sub-block
+      const int u = warp - 1;
+      int a = 0;
+      while ((a + 1) * (a + 2) / 2 <= u) a++;
+      upd_tile(S, o, a, u - a * (a + 1) / 2, lane);
+    } else if (warp > 10) {
+      // L_ss row-major into S for the stores and the inverse (nothing reads the part above the diagonal)
+      for (int idx = tid - 11 * 32; idx < 32 * 32; idx += 5 * 32)
+        S[(o + (idx >> 5)) * DS + o + (idx & 31)] = lc[(idx & 31) * LCS + (idx >> 5)];
+    }
+    __syncthreads();   // next diagonal sub-block up to date
+    if (s == 0) DIAG_T(2);
+  }
+  DIAG_T(4);
+  {
+    const double *lc = Lc + 32 * LCS, *ri = rinv + 32;
+    if (warp == 0) {
+      warp_trtri32_lc(lc, ri, Xd + 3 * 32 * XS, lane);
+    } else {
+      for (int idx = tid - 32; idx < 32 * 32; idx += DIAG_THREADS - 32)
+        S[(96 + (idx >> 5)) * DS + 96 + (idx & 31)] = lc[(idx & 31) * LCS + (idx >> 5)];
+      bar3_sync();
+      store_block_row(S, Lb, ld, 3, tid - 32, DIAG_THREADS - 32);
+    }
+  }
+  __syncthreads();
+  DIAG_T(5);
+  inverse_block_row<true>(S, Xd, 3, tid);
+  DIAG_T(6);
+  store_block_row(S, Ib, 128, 3, tid, DIAG_THREADS);
+  DIAG_T(7);
+}
+
 __global__ void __launch_bounds__(DIAG_THREADS) k_trtri_diag(const double *L, int ld, int64_t sL,
                                                               double *linv, int64_t sInv) {
   extern __shared__ __align__(16) double S[];
@@ -740,8 +1023,8 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_trtri_diag(const double *L, in
 }
 
 __global__ void __launch_bounds__(1024) k_scatter_diag(const double *linv, int64_t sInv, double *M, int ld,
-                                                       int64_t sM) {
-  const int kb = blockIdx.x, b = blockIdx.y;
+                                                       int64_t sM, int kb0) {
+  const int kb = blockIdx.x + kb0, b = blockIdx.y;
   const double2 *src = reinterpret_cast<const double2 *>(linv + b * sInv + (int64_t)kb * 128 * 128);
   double *dst = M + b * sM + (int64_t)kb * 128 * ld + kb * 128;
 #pragma unroll
@@ -885,15 +1168,23 @@ cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
 }
 
 static const int kDiagSmem = kDiagSmemDbl * sizeof(double);
+static const int kDiag2Smem = kDiag2SmemDbl * sizeof(double);
+// MGP_DIAG_V1=1 selects the first version of the diagonal-block kernel (kept for A/B measurements)
+static int diag_version() {
+  static const int v = [] { const char *e = getenv("MGP_DIAG_V1"); return (e && e[0] == '1') ? 1 : 2; }();
+  return v;
+}
 
 cudaError_t launch_potrf_diag(double *A, double *Lout, int ld, int64_t sA, double *linv,
                               int64_t sInv, int kb, int *status, int batch, cudaStream_t st) {
   static bool attr_done[MGP_MAX_DEVICES] = {};
   if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    cudaFuncSetAttribute(k_potrf_diag2, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiag2Smem);
     cudaFuncSetAttribute(k_trtri_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
   }
-  k_potrf_diag<<<batch, DIAG_THREADS, kDiagSmem, st>>>(A, Lout, ld, sA, linv, sInv, kb, status);
+  if (diag_version() == 1) k_potrf_diag<<<batch, DIAG_THREADS, kDiagSmem, st>>>(A, Lout, ld, sA, linv, sInv, kb, status);
+  else k_potrf_diag2<<<batch, DIAG_THREADS, kDiag2Smem, st>>>(A, Lout, ld, sA, linv, sInv, kb, status);
   return cudaGetLastError();
 }
 
@@ -902,6 +1193,7 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
   static bool attr_done[MGP_MAX_DEVICES] = {};
   if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    cudaFuncSetAttribute(k_potrf_diag2, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiag2Smem);
     cudaFuncSetAttribute(k_trtri_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
   }
   k_trtri_diag<<<dim3(NI, batch), DIAG_THREADS, kDiagSmem, st>>>(L, ld, sL, linv, sInv);
@@ -916,9 +1208,55 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
 
 int chol_panels(int npad) { return (npad / 128 + 3) / 4; }
 
+// Block row kb of L^-1 on the side stream, as soon as diagonal block kb is factored and inverted
+// (everything it needs -- L[kb, 0:kb], the rows above of L^-1, inv(L_kk) -- is final then):
+//   X[kb, 0:kb] = -inv(L_kk) (L[kb, 0:kb] X[0:kb, 0:kb])
+// The two products overlap the panel solve / update / next diagonal block of the factorisation on
+// `st`; after the last block row `st` waits for the side stream.
+static cudaError_t rowinv_block_row(const RowInv &ri, const double *L, int npad, int64_t sMat,
+                                    const double *linv, int64_t sInv, int kb, int batch, cudaStream_t st,
+                                    int64_t *launches, int cta_cap) {
+  const int NI = npad / 128;
+  LA_TRY(cudaEventRecord(ri.ev_fork, st));
+  LA_TRY(cudaStreamWaitEvent(ri.side, ri.ev_fork, 0));
+  if (kb == 0 && ri.clean_upper)
+    for (int b = 0; b < batch; b++)
+      LA_TRY(cudaMemsetAsync(ri.Minv + b * sMat, 0, sizeof(double) * (size_t)npad * npad, ri.side));
+  k_scatter_diag<<<dim3(1, batch), 1024, 0, ri.side>>>(linv, sInv, ri.Minv, npad, sMat, kb);
+  LA_TRY(cudaGetLastError());
+  (*launches)++;
+  if (kb > 0) {
+    const int64_t row = (int64_t)kb * 128 * npad;
+    GemmDesc g = {};
+    g.cta_cap = cta_cap;
+    g.A = L + row; g.lda = npad; g.ta = 0;                 // L[kb, 0:kb]       [128][128 kb]
+    g.B = ri.Minv; g.ldb = npad; g.tb = 1;                 // X[0:kb, 0:kb]     k-major, lower triangular
+    g.C = ri.T + row; g.ldc = npad;
+    g.M = 128; g.N = kb * 128; g.K = kb * 128; g.alpha = 1.0; g.beta = 0.0; g.kmode = 1; g.order = 3;
+    g.n_inner = 1; g.n_outer = batch;
+    g.sA_out = g.sB_out = g.sC_out = sMat;
+    LA_TRY(launch_dgemm(g, ri.side));
+    GemmDesc h = {};
+    h.cta_cap = cta_cap;
+    h.A = linv + (int64_t)kb * 128 * 128; h.lda = 128; h.ta = 0;   // inv(L_kk), lower triangular
+    h.B = ri.T + row; h.ldb = npad; h.tb = 1;
+    h.C = ri.Minv + row; h.ldc = npad;
+    h.M = 128; h.N = kb * 128; h.K = 128; h.alpha = -1.0; h.beta = 0.0; h.kmode = 2; h.order = 2;
+    h.n_inner = 1; h.n_outer = batch;
+    h.sA_out = sInv; h.sB_out = h.sC_out = sMat;
+    LA_TRY(launch_dgemm(h, ri.side));
+    (*launches) += 2;
+  }
+  if (kb == NI - 1) {
+    LA_TRY(cudaEventRecord(ri.ev_join, ri.side));
+    LA_TRY(cudaStreamWaitEvent(st, ri.ev_join, 0));
+  }
+  return cudaSuccess;
+}
+
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
-                         bool clean_upper, int panel_lo, int panel_hi, int cta_cap) {
+                         bool clean_upper, int panel_lo, int panel_hi, int cta_cap, const RowInv *ri) {
   // Two-level right-looking blocked Cholesky.  Tiles are 128 wide; PB tiles form a panel.  Inside a
   // panel every tile column is factored (diagonal block, TRSM through the explicit inverse of the
   // diagonal block) and applied to the remaining columns OF THE PANEL only (k = 128); the matrix
@@ -938,6 +1276,7 @@ cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *lin
     for (int kb = k0; kb < k1; kb++) {
       LA_TRY(launch_potrf_diag(A, L, npad, sA, linv, sInv, kb, status, batch, st));
       (*launches)++;
+      if (ri) LA_TRY(rowinv_block_row(*ri, L, npad, sA, linv, sInv, kb, batch, st, launches, cta_cap));
       const int below = NI - 1 - kb;
       if (below == 0) break;
       const int64_t off_panel = (int64_t)(kb + 1) * 128 * npad + (int64_t)kb * 128;
@@ -995,7 +1334,7 @@ cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, in
   if (clean_upper)
     for (int b = 0; b < batch; b++)
       LA_TRY(cudaMemsetAsync(Minv + b * sMat, 0, sizeof(double) * (size_t)npad * npad, st));
-  k_scatter_diag<<<dim3(NI, batch), 1024, 0, st>>>(linv, sInv, Minv, npad, sMat);
+  k_scatter_diag<<<dim3(NI, batch), 1024, 0, st>>>(linv, sInv, Minv, npad, sMat, 0);
   LA_TRY(cudaGetLastError());
   (*launches)++;
   for (int sb = 1; sb < NI; sb *= 2) {

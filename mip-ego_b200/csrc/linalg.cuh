@@ -42,9 +42,19 @@ cudaError_t launch_trtri_diag(const double *L, int ld, int64_t sL, double *linv,
 // Full blocked Cholesky A -> L (lower, row-major npad x npad, A is destroyed) + diag inverses.
 // Only the panels [panel_lo, panel_hi) of 4 tile columns are processed (all: 0 .. chol_panels(npad)).
 int chol_panels(int npad);
+// Optional companion of the factorisation: L^-1 block row by block row on a second stream while the
+// factorisation proceeds (instead of trtri_blocked afterwards).  For few, small matrices the likelihood
+// is bound by the serial chain of short launches; this takes the triangular inversion off that chain.
+struct RowInv {
+  double *Minv, *T;       // L^-1 (output) and scratch, same geometry as L
+  cudaStream_t side;      // stream of the inversion's launches
+  cudaEvent_t ev_fork, ev_join;
+  bool clean_upper;       // zero Minv first (exported factors)
+};
 cudaError_t chol_blocked(double *A, double *L, int npad, int64_t sA, double *linv, int64_t sInv,
                          int *status, int batch, cudaStream_t st, int64_t *launches,
-                         bool clean_upper, int panel_lo, int panel_hi, int cta_cap = 0);
+                         bool clean_upper, int panel_lo, int panel_hi, int cta_cap = 0,
+                         const RowInv *ri = nullptr);
 // Minv = L^-1 given L and the diagonal-block inverses; T is scratch (npad x npad per matrix).
 cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, int64_t sMat,
                           const double *linv, int64_t sInv, int batch, cudaStream_t st,

@@ -104,6 +104,10 @@ struct mgp_handle {
   int gemm_cap_opt = 0;    // user override of the per-launch CTA cap (0 = automatic)
   cudaStream_t nll_stream[MGP_NLL_STREAMS] = {};  // batch groups
   cudaEvent_t ev_fork = nullptr, ev_join[MGP_NLL_STREAMS] = {};
+  // second stream per batch group: L^-1 block row by block row while the factorisation runs (RowInv)
+  cudaStream_t nll_side[MGP_NLL_STREAMS] = {};
+  cudaEvent_t ev_sfork[MGP_NLL_STREAMS] = {}, ev_sjoin[MGP_NLL_STREAMS] = {};
+  int rowinv_opt = -1;     // option "trtri_rowwise": -1 automatic (few small matrices), 0 never, 1 always
   DevBuf nR, nL, nM, nT, nLinvDiag, nvec, nscal, npar, ngpart;
   DevBuf nFtm, nBhat, ntws;   // general-trend workspaces (allocated when p > 1)
   DevBuf niso;                // isotropic theta: expanded parameters | full gradient

@@ -806,12 +806,13 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
   if (!w.have_L) {
     const int P = chol_panels(npad);
     const int lo = phase < 0 ? 0 : phase - 1, hi = phase < 0 ? P : phase;
+    RowInv ri = {w.M, w.T, w.side, w.ev_side_fork, w.ev_side_join, w.want_bhat != 0};
     if (phase < 0 || (phase >= 1 && phase <= P))
       NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches,
-                          w.want_bhat != 0, lo, hi, w.gemm_cta_cap));
+                          w.want_bhat != 0, lo, hi, w.gemm_cta_cap, w.side ? &ri : nullptr));
   }
   if (phase >= 0 && phase != last) return cudaSuccess;
-  if (!(w.have_L && w.have_M))
+  if (!(w.have_L && w.have_M) && !(w.side && !w.have_L))
     NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches,
                          w.want_bhat != 0, w.gemm_cta_cap));
   double *Yt = w.Yt, *Ft = w.Ft, *rho = w.rho, *gamma = w.gamma;

@@ -213,6 +213,38 @@ def test_small_calls_zero_copy_equals_copy_engine_path(kind, ordinary):
     assert np.max(np.abs(mse - rs) / (np.abs(rs) + 1e-6 * st["sigma2"])) < 1e-7
 
 
+# ---- triangular inversion beside the factorisation -----------------------------------------------------------
+def test_rowwise_inversion_matches_the_recursive_one():
+    """Option trtri_rowwise: L^-1 block row by block row on a second stream while the Cholesky runs.  Same
+    likelihood, gradient and status as the recursive inversion after the factorisation (different summation
+    order: gated at 1e-10 / 1e-9), eager and replayed from a CUDA graph, one and two batch groups."""
+    mb, O = _mods()
+    d = 5
+    for n, B in ((130, 3), (600, 4), (1100, 5)):
+        X, y, rng = _data(n, d, 40 + n)
+        theta = (0.5 / d) * rng.uniform(0.5, 1.5, d)
+        gp = mb.GaussianProcess(mean=mb.constant_trend(d, beta=None), corr="matern", theta0=theta,
+                                thetaL=[1e-5] * d, thetaU=[100.0] * d, nugget=1e-6)
+        gp._check_data(X, y)
+        h = gp._handle()
+        P = np.c_[theta * rng.uniform(0.6, 1.6, (B, d)), rng.uniform(0.5, 1.0, B)]
+        P[-1, :d] = 1e-9        # nearly singular correlation matrix: the failure status must agree as well
+        out = {}
+        for opt in (0, 1):
+            h.set_option("trtri_rowwise", opt)
+            res = [gp.log_likelihood_batch(P) for _ in range(3)]      # eager, then two graph replays
+            for r in res[1:]:
+                assert np.array_equal(r[0], res[0][0]) and np.array_equal(r[1], res[0][1])
+            out[opt] = res[0]
+        assert np.array_equal(out[0][2], out[1][2])
+        ok = out[0][2] == 0
+        assert ok[:-1].all()
+        assert np.max(np.abs(out[0][0][ok] - out[1][0][ok]) / np.abs(out[0][0][ok])) < 1e-10
+        g0, g1 = out[0][1][ok], out[1][1][ok]
+        assert np.max(np.abs(g0 - g1)) / np.max(np.abs(g0)) < 1e-9
+        h.set_option("trtri_rowwise", -1)
+
+
 # ---- CUDA graphs of the batched likelihood ---------------------------------------------------------------
 def test_likelihood_graphs_are_bitwise_the_eager_path():
     """A batch shape is captured in a CUDA graph at its second use and replayed afterwards (host
