@@ -544,11 +544,10 @@ static int nll_issue(mgp_handle *h, int B, const double *d_params, int n_par, in
       // n = 1024: 1.151 / 1.183 at 8, 3.794 / 3.690 at 64 -- profiles/r02_nll_chain.txt)
       const bool rowwise = h->NI >= 2 && (h->rowinv_opt == 1 ||
                                           (h->rowinv_opt < 0 && (h->NI <= 4 || (h->NI <= 8 && g1 - g0 >= 32))));
-      if (rowwise) {
-        works[g].side = h->nll_side[g];
-        works[g].ev_side_fork = h->ev_sfork[g];
-        works[g].ev_side_join = h->ev_sjoin[g];
-      }
+      works[g].side = h->nll_side[g];
+      works[g].ev_side_fork = h->ev_sfork[g];
+      works[g].ev_side_join = h->ev_sjoin[g];
+      works[g].rowwise = rowwise ? 1 : 0;
       nph = nll_num_phases(works[g]);
     }
     // phase by phase, group by group: every group has its first kernels queued at once (issuing

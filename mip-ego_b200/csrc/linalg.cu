@@ -124,7 +124,7 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][4][2], const double *
 // serial chain of the blocked Cholesky -- spread over twice as many SMs.
 template <bool TA, bool TB, int MT = 128>
 __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(GemmDesc g, int *sched_g) {
-  static_assert(MT == 128 || (MT == 64 && !TA), "half tiles: k-contiguous A only");
+  static_assert(MT == 128 || ((MT == 64 || MT == 32) && !TA), "half / quarter tiles: k-contiguous A only");
   constexpr int RTN = MT / 16;   // 8-row accumulator tiles per consumer warp
   extern __shared__ __align__(128) unsigned char smraw[];
   double *As = reinterpret_cast<double *>(smraw);
@@ -1053,6 +1053,28 @@ __global__ void __launch_bounds__(256) k_trmv_n(const double *M, int npad, int64
   if (lane == 0) y[b * sy + row] = acc;
 }
 
+// Two products with one pass over M: y1 = M x1, y2 = M x2 (Yt and Ft of the likelihood share L^-1).
+__global__ void __launch_bounds__(256) k_trmv_n2(const double *M, int npad, int64_t sM,
+                                                 const double *x1, const double *x2, double *y1, double *y2,
+                                                 int64_t sy, int n) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  const double *Mr = M + b * sM + (int64_t)row * npad;
+  double a1 = 0.0, a2 = 0.0;
+  for (int k = lane; k <= row; k += 32) {
+    const double m = Mr[k];
+    a1 = fma(m, x1[k], a1);
+    a2 = fma(m, x2 ? x2[k] : (k < n ? 1.0 : 0.0), a2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (lane == 0) { y1[b * sy + row] = a1; y2[b * sy + row] = a2; }
+}
+
 // y[col] = sum_{k >= col} M[k][col] x[k]: a block owns 32 columns, its 32 warps stride over the
 // rows (coalesced 256-byte row segments), partial sums are combined in a fixed order.
 __global__ void __launch_bounds__(1024) k_trmv_t(const double *M, int npad, int64_t sM,
@@ -1137,11 +1159,18 @@ void release_dgemm_stream(cudaStream_t st) {
   g_sched_table.erase(it);
 }
 
+// MGP_GEMM_QUARTER=0 switches the 32-row tiles off (A/B measurements)
+static bool quarter_tiles() {
+  static const bool on = [] { const char *e = getenv("MGP_GEMM_QUARTER"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   static bool attr_done[MGP_MAX_DEVICES] = {};
   if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(k_dgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<false, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(k_dgemm<false, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
@@ -1155,11 +1184,17 @@ cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   int total = (g.N / 128) * (g.M / 128) * g.n_inner * g.n_outer;
   int limit = sm_count;
   if (g.cta_cap > 0 && limit > g.cta_cap) limit = g.cta_cap;
-  const bool half = !g.ta && !g.tb && g.kmode == 0 && 2 * total <= limit;   // see k_dgemm: MT = 64
+  // see k_dgemm: MT = 64, or MT = 32 when even the half tiles leave half of the SMs idle (few small
+  // matrices: a 128 x 128 x 128 tile is 17 us on one SM, and these launches sit on the serial chain)
+  const bool plain = !g.ta && !g.tb && g.kmode == 0;
+  const bool quarter = plain && quarter_tiles() && 4 * total <= limit;
+  const bool half = plain && !quarter && 2 * total <= limit;
   if (half) total *= 2;
+  if (quarter) total *= 4;
   const int grid = total < limit ? total : limit;
   const int threads = GEMM_CONSUMERS + GEMM_PRODUCERS;
-  if (half) k_dgemm<false, false, 64><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  if (quarter) k_dgemm<false, false, 32><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  else if (half) k_dgemm<false, false, 64><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else if (!g.ta && !g.tb) k_dgemm<false, false><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else if (!g.ta && g.tb) k_dgemm<false, true><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else if (g.ta && !g.tb) k_dgemm<true, false><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
@@ -1393,6 +1428,12 @@ cudaError_t launch_trmv(const double *M, int npad, int64_t sM, const double *x, 
                         double *y, int64_t sy, int n, int trans, int batch, cudaStream_t st) {
   if (!trans) k_trmv_n<<<dim3(npad / 8, batch), 256, 0, st>>>(M, npad, sM, x, sx, y, sy, n);
   else k_trmv_t<<<dim3(npad / 32, batch), 1024, 0, st>>>(M, npad, sM, x, sx, y, sy, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trmv2(const double *M, int npad, int64_t sM, const double *x1, const double *x2,
+                         double *y1, double *y2, int64_t sy, int n, int batch, cudaStream_t st) {
+  k_trmv_n2<<<dim3(npad / 8, batch), 256, 0, st>>>(M, npad, sM, x1, x2, y1, y2, sy, n);
   return cudaGetLastError();
 }
 

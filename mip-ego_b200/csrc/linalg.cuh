@@ -68,6 +68,10 @@ cudaError_t lauum_blocked(const double *Minv, double *Rinv, int npad, int64_t sM
 cudaError_t launch_trmv(const double *M, int npad, int64_t sM, const double *x, int64_t sx,
                         double *y, int64_t sy, int n, int trans, int batch, cudaStream_t st);
 
+// y1 = M x1 and y2 = M x2 in one pass over M (x vectors shared by the batch; x2 == nullptr: ones).
+cudaError_t launch_trmv2(const double *M, int npad, int64_t sM, const double *x1, const double *x2,
+                         double *y1, double *y2, int64_t sy, int n, int batch, cudaStream_t st);
+
 // Pack row-major L^-1 into the slab layout of the posterior kernel (lower block triangle).
 cudaError_t launch_pack_tri(const double *Minv, int n, int npad, double *Mp, cudaStream_t st);
 // Pack a symmetric matrix given by its lower tiles into the full slab layout (all blocks).

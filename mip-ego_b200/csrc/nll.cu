@@ -809,19 +809,27 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
     RowInv ri = {w.M, w.T, w.side, w.ev_side_fork, w.ev_side_join, w.want_bhat != 0};
     if (phase < 0 || (phase >= 1 && phase <= P))
       NL_TRY(chol_blocked(w.R, w.L, npad, sM, w.linv, (int64_t)NI * 128 * 128, w.status, B, st, launches,
-                          w.want_bhat != 0, lo, hi, w.gemm_cta_cap, w.side ? &ri : nullptr));
+                          w.want_bhat != 0, lo, hi, w.gemm_cta_cap, w.rowwise ? &ri : nullptr));
   }
   if (phase >= 0 && phase != last) return cudaSuccess;
-  if (!(w.have_L && w.have_M) && !(w.side && !w.have_L))
+  if (!(w.have_L && w.have_M) && !(w.rowwise && !w.have_L))
     NL_TRY(trtri_blocked(w.L, w.M, w.T, npad, sM, w.linv, (int64_t)NI * 128 * 128, B, st, launches,
                          w.want_bhat != 0, w.gemm_cta_cap));
   double *Yt = w.Yt, *Ft = w.Ft, *rho = w.rho, *gamma = w.gamma;
   const bool general = w.p > 1 && w.ordinary;   // p basis functions with estimated coefficients
-  NL_TRY(launch_trmv(w.M, npad, sM, w.y, 0, Yt, npad, n, 0, B, st));
+  // M^T M (needed by the gradient only) depends on nothing below: beside the vector chain on the side stream
+  const bool side_lauum = w.side && w.eval_grad && !general;
+  if (side_lauum) {
+    NL_TRY(cudaEventRecord(w.ev_side_fork, st));
+    NL_TRY(cudaStreamWaitEvent(w.side, w.ev_side_fork, 0));
+    NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, w.side, launches, w.gemm_cta_cap));
+    NL_TRY(cudaEventRecord(w.ev_side_join, w.side));
+  }
   if (!general) {
-    // Ft = L^-1 1, or L^-1 (F beta) for a given non-constant mean (then rho = Yt - 1 * Ft)
-    NL_TRY(launch_trmv(w.M, npad, sM, w.mu, 0, Ft, npad, n, 0, B, st));
+    // Yt = L^-1 y and Ft = L^-1 1, or L^-1 (F beta) for a given non-constant mean (then rho = Yt - 1 * Ft)
+    NL_TRY(launch_trmv2(w.M, npad, sM, w.y, w.mu, Yt, Ft, npad, n, B, st));
   } else {
+    NL_TRY(launch_trmv(w.M, npad, sM, w.y, 0, Yt, npad, n, 0, B, st));
     // Ft = L^-1 F as a GEMM (gpr.py:690), then the normal equations of the p x p trend problem
     GemmDesc g = {};
     g.cta_cap = w.gemm_cta_cap;
@@ -840,7 +848,7 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
                                    w.logdetFF, w.scal, w.status, w.out_llf);
   NL_TRY(cudaGetLastError());
   NL_TRY(launch_trmv(w.M, npad, sM, rho, npad, gamma, npad, n, 1, B, st));
-  (*launches) += 4;
+  (*launches) += general ? 4 : 3;
   const bool need_bhat = general && (w.want_bhat || (w.eval_grad && (w.mode & MGP_LIK_RESTRICTED)));
   if (need_bhat) {
     // Bhat = L^-T (Ft C^-T): REML's (L^-T Q)(L^-T Q)^T term and, for the fitted model, Ft^T L^-1 r
@@ -861,7 +869,8 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
       NL_TRY(launch_trmv(w.M, npad, sM, Ft, npad, w.avec, npad, n, 1, B, st));
       (*launches)++;
     }
-    NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, st, launches, w.gemm_cta_cap));
+    if (side_lauum) NL_TRY(cudaStreamWaitEvent(st, w.ev_side_join, 0));
+    else NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, st, launches, w.gemm_cta_cap));
     const int ntiles = NI * (NI + 1) / 2;
     const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + 8 * (w.dpad + 2) + MGP_EXP_TAB_DOUBLES) * sizeof(double);
     dim3 grid(ntiles, B);

@@ -8,10 +8,12 @@
 struct NllWork {
   int n, npad, dpad, B, n_par, mode, corr, ordinary, eval_grad;
   int gemm_cta_cap;       // CTA cap of the GEMM launches of this work item (0 = one per SM)
-  // L^-1 block row by block row on `side` while the Cholesky runs (linalg.cuh: RowInv); side == nullptr:
-  // recursive inversion after the factorisation
+  // second stream of this work item (nullable) with a fork / join event pair: M^T M beside the vector
+  // chain, and -- rowwise = 1 -- L^-1 block row by block row while the Cholesky runs (linalg.cuh: RowInv)
+  // instead of the recursive inversion after the factorisation
   cudaStream_t side;
   cudaEvent_t ev_side_fork, ev_side_join;
+  int rowwise;
   int have_M;             // 1 (with have_L): L^-1 is given in w.M as well; skip the triangular inversion
   int have_L;             // 1: L (B=1) is given in w.L; skip the correlation build and Cholesky
   double noise_var, beta0;
