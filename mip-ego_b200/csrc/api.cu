@@ -412,7 +412,7 @@ static int nll_alloc(mgp_handle *h, int B) {
   MGP_TRY(mgp_ensure(h, h->nLinvDiag, (size_t)B * h->NI * 128 * 128 * 8));
   MGP_TRY(mgp_ensure(h, h->nvec, (size_t)5 * B * h->npad * 8));
   MGP_TRY(mgp_ensure(h, h->nscal, (size_t)B * nll_scal_doubles() * 8 + (size_t)B * sizeof(int) + 64));
-  MGP_TRY(mgp_ensure(h, h->ngpart, (size_t)B * ntiles * (h->dpad + 2) * 8));
+  MGP_TRY(mgp_ensure(h, h->ngpart, (size_t)B * ntiles * 4 * (h->dpad + 2) * 8));   // four parts per tile (k_nll_grad)
   if (h->p > 1 && h->trend_est) {
     MGP_TRY(mgp_ensure(h, h->nFtm, (size_t)B * h->npad * MGP_TP * 8));
     MGP_TRY(mgp_ensure(h, h->nBhat, (size_t)B * h->npad * MGP_TP * 8));
@@ -470,7 +470,7 @@ static void fill_work(mgp_handle *h, NllWork &w, int b_off, int B, int cap, int 
   double *v = P<double>(h->nvec) + (size_t)b_off * h->npad;
   w.Yt = v; w.Ft = v + sec; w.rho = v + 2 * sec; w.gamma = v + 3 * sec; w.avec = v + 4 * sec;
   w.scal = P<double>(h->nscal) + (size_t)b_off * nll_scal_doubles();
-  w.gpart = P<double>(h->ngpart) + (size_t)b_off * ntiles * (h->dpad + 2);
+  w.gpart = P<double>(h->ngpart) + (size_t)b_off * ntiles * 4 * (h->dpad + 2);
   w.status = nll_status_ptr(h, cap) + b_off;
   w.out_llf = d_llf; w.out_grad = d_grad;
   w.p = h->p;
@@ -540,10 +540,13 @@ static int nll_issue(mgp_handle *h, int B, const double *d_params, int n_par, in
       works[g].gemm_cta_cap = cta_cap;
       // small matrices: the step is bound by the serial chain of short launches, so the triangular
       // inversion runs block row by block row on a second stream beside the factorisation
-      // (measured, B200, ms per call after / beside: n = 500: 0.496 / 0.468 at 4 vectors, 0.953 / 0.950 at 64;
-      // n = 1024: 1.151 / 1.183 at 8, 3.794 / 3.690 at 64 -- profiles/r02_nll_chain.txt)
+      // (measured on B200 with the 32-row tiles of the inversion's products, ms per call after / beside --
+      // profiles/r02_nll_chain.txt: n = 500: 0.350 / 0.315 at 4 vectors, 0.933 / 0.931 at 64; n = 1024: 0.700 / 0.601
+      // at 1, 0.990 / 0.876 at 8, 3.79 / 3.66 at 64; n = 2048: 1.60 / 1.46 at 1, 2.12 / 2.01 at 4, 3.33 / 3.32 at 8,
+      // 21.64 / 21.68 at 64)
       const bool rowwise = h->NI >= 2 && (h->rowinv_opt == 1 ||
-                                          (h->rowinv_opt < 0 && (h->NI <= 4 || (h->NI <= 8 && g1 - g0 >= 32))));
+                                          (h->rowinv_opt < 0 && h->NI <= 16));   // by size only: a row of the batch
+      // gives the same bits whatever the batch size
       works[g].side = h->nll_side[g];
       works[g].ev_side_fork = h->ev_sfork[g];
       works[g].ev_side_join = h->ev_sjoin[g];

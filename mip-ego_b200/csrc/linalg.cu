@@ -1171,6 +1171,8 @@ cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
     cudaFuncSetAttribute(k_dgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<false, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<false, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(k_dgemm<false, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(k_dgemm<false, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     cudaFuncSetAttribute(k_dgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
@@ -1187,13 +1189,20 @@ cudaError_t launch_dgemm(const GemmDesc &g, cudaStream_t st) {
   // see k_dgemm: MT = 64, or MT = 32 when even the half tiles leave half of the SMs idle (few small
   // matrices: a 128 x 128 x 128 tile is 17 us on one SM, and these launches sit on the serial chain)
   const bool plain = !g.ta && !g.tb && g.kmode == 0;
-  const bool quarter = plain && quarter_tiles() && 4 * total <= limit;
-  const bool half = plain && !quarter && 2 * total <= limit;
+  // ... and the two products of the triangular inversion, L_C X_A (k-major triangular B: the k range depends
+  // on the column block only) and -X_B T with a single 128-wide k block: 128-row tiles with k up to 128 kb
+  // are what the last block rows of the inversion wait for (n = 500, 8 matrices: 52 + 18 us -> see
+  // profiles/r02_nll500_launches_summary.txt); the small tiles take no triangular shortcuts (exact zeros)
+  const bool tri_small = !g.ta && g.tb && !g.lower_only && (g.kmode == 1 || (g.kmode == 2 && g.K <= 128));
+  const bool quarter = (plain || tri_small) && quarter_tiles() && 4 * total <= limit;
+  const bool half = (plain || tri_small) && !quarter && 2 * total <= limit;
   if (half) total *= 2;
   if (quarter) total *= 4;
   const int grid = total < limit ? total : limit;
   const int threads = GEMM_CONSUMERS + GEMM_PRODUCERS;
-  if (quarter) k_dgemm<false, false, 32><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  if (quarter && g.tb) k_dgemm<false, true, 32><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  else if (half && g.tb) k_dgemm<false, true, 64><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
+  else if (quarter) k_dgemm<false, false, 32><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else if (half) k_dgemm<false, false, 64><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else if (!g.ta && !g.tb) k_dgemm<false, false><<<grid, threads, GEMM_SMEM, st>>>(g, sched);
   else if (!g.ta && g.tb) k_dgemm<false, true><<<grid, threads, GEMM_SMEM, st>>>(g, sched);

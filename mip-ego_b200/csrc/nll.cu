@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
                                                   const double *Rinv, int64_t sR,
                                                   const double *gamma, const double *avec, int64_t sv,
                                                   const double *Bhat, int p,
-                                                  const double *scal, double *gpart, int ntiles) {
+                                                  const double *scal, double *gpart, int ntiles, int nsplit) {
   extern __shared__ __align__(16) double sm[];
   double *xjT = sm;
   double *xkT = sm + DP * XP;
@@ -263,8 +263,13 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
   double *tab = red + 8 * (DP + 2);   // exp table (mgp_common.cuh)
   __shared__ int s_anyzero;
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // tile index -> (bi, bj), bi >= bj
-  int t = blockIdx.x, bi = 0;
+  // tile index -> (bi, bj), bi >= bj.  The 16 row groups of a tile are summed in FOUR parts, each with its
+  // own row of partial sums, and nsplit = 1, 2 or 4 CTAs share a tile (4 / nsplit parts each): with few
+  // small matrices one CTA per tile leaves half of the SMs idle and the kernel sits on the serial chain
+  // of the fit (n = 500, 8 matrices: 80 CTAs, 47 us).  The partial sums and their order do not depend on
+  // nsplit, so a row of the batch gives bitwise the same gradient whatever the batch size.
+  const int part0 = (blockIdx.x % nsplit) * (4 / nsplit);
+  int t = blockIdx.x / nsplit, bi = 0;
   while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
   const int bj = t - bi * (bi + 1) / 2;
   const double *par = params + (int64_t)b * n_par;
@@ -294,15 +299,16 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
   const double *gm = gamma + b * sv;
   const double *av = avec + b * sv;
   double acc[DP + 2];
-#pragma unroll
-  for (int i = 0; i <= DP + 1; i++) acc[i] = 0.0;
   const int c = tid & 127, gk = bj * 128 + c;
   const double gk_v = gk < n ? gm[gk] : 0.0;
   const double ak_v = (coefa != 0.0 && gk < n) ? coefa * av[gk] : 0.0;
   // four rows per thread and two passes over the features: pass 1 accumulates S for the four
   // pairs, the pair weights W * fac follow, pass 2 regenerates the squared differences and adds
   // their weighted sum to the per-feature accumulators (no per-pair array of differences)
-  for (int q = 0; q < 16; q++) {
+  for (int part = part0; part < part0 + 4 / nsplit; part++) {
+#pragma unroll
+  for (int i = 0; i <= DP + 1; i++) acc[i] = 0.0;
+  for (int q = 4 * part; q < 4 * part + 4; q++) {
     const int r = (tid >> 7) * 64 + 4 * q;
     if (bi * 128 + r + 3 < gk || bi * 128 + r >= n || gk >= n) continue;   // nothing on or below the diagonal
     // issue the global loads of the pair weights first: they complete under pass 1
@@ -409,7 +415,9 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
     // scaled coordinates: the feature sums carry a factor theta_i (squared differences of
     // sqrt(theta_i) x, or absolute differences of theta_i x)
     if (scaled && i < DP) v = i < d ? v / th[i] : 0.0;
-    gpart[((int64_t)b * ntiles + t) * (DP + 2) + i] = v;
+    gpart[((int64_t)b * ntiles * 4 + 4 * t + part) * (DP + 2) + i] = v;
+  }
+  __syncthreads();   // red is reused by the next part
   }
 }
 
@@ -679,7 +687,7 @@ template <int CORR>
 cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, const double *Xc, int n,
                           int npad, const double *params, int n_par, int mode, const double *Rinv,
                           int64_t sR, const double *gamma, const double *avec, int64_t sv,
-                          const double *Bhat, int p, const double *scal, double *gpart, int ntiles) {
+                          const double *Bhat, int p, const double *scal, double *gpart, int ntiles, int nsplit) {
   switch (dpad) {
 #define NG(D)                                                                                   \
   case D: {                                                                                     \
@@ -689,7 +697,7 @@ cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, con
                            (int)smem);                                                          \
   }                                                                                             \
     k_nll_grad<CORR, D><<<grid, 256, smem, st>>>(Xc, n, npad, params, n_par, mode, Rinv, sR,    \
-                                                  gamma, avec, sv, Bhat, p, scal, gpart, ntiles); \
+                                                  gamma, avec, sv, Bhat, p, scal, gpart, ntiles, nsplit); \
     break;
     NG(4) NG(8) NG(12) NG(16) NG(20) NG(24) NG(28) NG(32) NG(36) NG(40) NG(44) NG(48) NG(52) NG(56) NG(60) NG(64)
 #undef NG
@@ -873,17 +881,26 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
     else NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, st, launches, w.gemm_cta_cap));
     const int ntiles = NI * (NI + 1) / 2;
     const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + 8 * (w.dpad + 2) + MGP_EXP_TAB_DOUBLES) * sizeof(double);
-    dim3 grid(ntiles, B);
+    // CTAs per tile: up to 4 while the launch still fits the machine (2 CTAs per SM); gpart holds
+    // ntiles x 4 rows per matrix whatever nsplit is
+    int nsplit = 1, sm_count = 148;
+    {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    while (nsplit < 4 && (int64_t)ntiles * B * nsplit < 2 * sm_count) nsplit *= 2;
+    dim3 grid(ntiles * nsplit, B);
     if (w.corr == MGP_CORR_SE)
       NL_TRY(grad_dispatch<0>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
-                              sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles));
+                              sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles, nsplit));
     else if (w.corr == MGP_CORR_MATERN32)
       NL_TRY(grad_dispatch<1>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
-                              sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles));
+                              sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles, nsplit));
     else
       NL_TRY(grad_dispatch<2>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
-                              sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles));
-    k_nll_grad_final<<<B, 1024, 0, st>>>(w.gpart, ntiles, w.dpad + 2, w.n_par, w.mode, w.scal,
+                              sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles, nsplit));
+    k_nll_grad_final<<<B, 1024, 0, st>>>(w.gpart, ntiles * 4, w.dpad + 2, w.n_par, w.mode, w.scal,
                                         w.status, w.out_grad);
     NL_TRY(cudaGetLastError());
     (*launches) += 2;
