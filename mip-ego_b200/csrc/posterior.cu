@@ -351,6 +351,29 @@ __device__ __forceinline__ void slab_mma_upto(int rt1, double (&acc)[8][4][2], c
   }
 }
 
+// One 32-k stage inside the diagonal 128x128 block for consumer row parity WR: slab js of stage DL skips
+// the row tiles above the diagonal, rt0 = (4 DL + js - WR + 1) / 2.  With DL and WR as template parameters
+// the four slabs are straight-line code, so the fragment loads of a slab are issued under the DMMAs of the
+// one before (the loop over js with a switch per slab left the tensor pipe waiting for the loads at the head
+// of every slab: 40 % of the stages at C2 lie in diagonal blocks).
+template <int DL, int WR>
+__device__ __forceinline__ void diag_stage(double (&acc)[8][4][2], const double *as, const double *bs, int wc,
+                                           int lane) {
+#pragma unroll
+  for (int js = 0; js < 4; js++) {
+    constexpr int base = 4 * DL - WR + 1;
+    const int rt0c = (base + js) >> 1;   // compile-time after unrolling
+    if (rt0c == 0) slab_mma<0>(acc, as + js * 1024, bs + js * 1024, WR, wc, lane);
+    else if (rt0c == 1) slab_mma<1>(acc, as + js * 1024, bs + js * 1024, WR, wc, lane);
+    else if (rt0c == 2) slab_mma<2>(acc, as + js * 1024, bs + js * 1024, WR, wc, lane);
+    else if (rt0c == 3) slab_mma<3>(acc, as + js * 1024, bs + js * 1024, WR, wc, lane);
+    else if (rt0c == 4) slab_mma<4>(acc, as + js * 1024, bs + js * 1024, WR, wc, lane);
+    else if (rt0c == 5) slab_mma<5>(acc, as + js * 1024, bs + js * 1024, WR, wc, lane);
+    else if (rt0c == 6) slab_mma<6>(acc, as + js * 1024, bs + js * 1024, WR, wc, lane);
+    else if (rt0c == 7) slab_mma<7>(acc, as + js * 1024, bs + js * 1024, WR, wc, lane);
+  }
+}
+
 // Item order: candidate blocks in groups of G = gridDim.x, inside a group the row blocks in decreasing
 // cost, candidate block innermost.  Dealt round-robin, CTA w of a full group therefore walks ALL row
 // blocks of ONE candidate block (g G + w) one after the other and finds its r tile, which it read from
@@ -462,21 +485,15 @@ __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
         // diagonal block: tiles above the diagonal (i8 < jl) are zero.  Row tiles are interleaved
         // between the two row-warps (i8 = 2 rt + wr), so both warps of every SM sub-partition
         // keep the same amount of work; rt0 = smallest rt with 2 rt + wr >= jl.
-#pragma unroll 1
-        for (int js = 0; js < 4; js++) {
-          const int rt0 = (4 * dl + js - wr + 1) >> 1;
-          const double *a_s = as + js * 1024, *b_s = bs + js * 1024;
-          switch (rt0) {
-            case 0: slab_mma<0>(acc, a_s, b_s, wr, wc, lane); break;
-            case 1: slab_mma<1>(acc, a_s, b_s, wr, wc, lane); break;
-            case 2: slab_mma<2>(acc, a_s, b_s, wr, wc, lane); break;
-            case 3: slab_mma<3>(acc, a_s, b_s, wr, wc, lane); break;
-            case 4: slab_mma<4>(acc, a_s, b_s, wr, wc, lane); break;
-            case 5: slab_mma<5>(acc, a_s, b_s, wr, wc, lane); break;
-            case 6: slab_mma<6>(acc, a_s, b_s, wr, wc, lane); break;
-            case 7: slab_mma<7>(acc, a_s, b_s, wr, wc, lane); break;
-            default: break;
-          }
+        switch (2 * dl + wr) {
+          case 0: diag_stage<0, 0>(acc, as, bs, wc, lane); break;
+          case 1: diag_stage<0, 1>(acc, as, bs, wc, lane); break;
+          case 2: diag_stage<1, 0>(acc, as, bs, wc, lane); break;
+          case 3: diag_stage<1, 1>(acc, as, bs, wc, lane); break;
+          case 4: diag_stage<2, 0>(acc, as, bs, wc, lane); break;
+          case 5: diag_stage<2, 1>(acc, as, bs, wc, lane); break;
+          case 6: diag_stage<3, 0>(acc, as, bs, wc, lane); break;
+          default: diag_stage<3, 1>(acc, as, bs, wc, lane); break;
         }
       }
       __syncwarp();
