@@ -222,6 +222,8 @@ int mgp_allgather_f64_dev(mgp_t *h, const double *d_send, int64_t count, double 
  * reference's indexing of its derivative tensor (entry 0 = derivative w.r.t. the first feature's
  * theta; set it before the first likelihood call); "small_path" = 0 disables the matrix-vector path
  * for <= 8 candidates; "nll_groups", "gemm_cta_cap": scheduling of batched likelihoods (0 = automatic);
+ * "trtri_rowwise" = -1 (automatic: n <= 2048), 0, 1: form L^-1 block row by block row on a second stream
+ * while the Cholesky factorisation runs instead of by recursive doubling afterwards;
  * "nll_graphs" = 0 issues every batched likelihood launch by launch (default 1: the launch sequence of
  * a batch shape is captured in a CUDA graph at its second use and replayed with one cudaGraphLaunch;
  * not used on the legacy default stream);
