@@ -69,14 +69,16 @@ __device__ __forceinline__ double feature_scale(double theta) { return CORR == 2
 template <int CORR>
 __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int npad, int dpad,
                                                  const double *params, int n_par, int mode,
-                                                 double noise_var, double *R, int64_t sR, int bi0) {
+                                                 double noise_var, double *R, int64_t sR, int bi0, int nsplit) {
   extern __shared__ __align__(16) double sm[];
   double *xjT = sm;               // [dpad][XP]  rows of tile bi
   double *xkT = sm + dpad * XP;   // [dpad][XP]  rows of tile bj
   double *th = xkT + dpad * XP;   // [dpad]      theta, then the feature scales
   double *tab = th + dpad;        // exp table (mgp_common.cuh)
   __shared__ int s_anyzero;
-  const int bj = blockIdx.x, bi = blockIdx.y + bi0, b = blockIdx.z;
+  // nsplit CTAs share a tile (16 / nsplit of its 16 row groups each): with few small matrices one CTA per
+  // tile leaves SMs idle, and this kernel is the head of the fit's serial chain
+  const int bj = blockIdx.x, bi = blockIdx.y / nsplit + bi0, part = blockIdx.y % nsplit, b = blockIdx.z;
   if (bj > bi) return;
   const int tid = threadIdx.x;
   const double *par = params + (int64_t)b * n_par;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) k_build_R(const double *Xc, int n, int np
   const int gk = bj * 128 + c;
   // a thread owns one column and walks its 64 rows four at a time: per feature one load of the
   // column's coordinate and two 16-byte broadcast loads of four row coordinates feed four pairs
-  for (int q = 0; q < 16; q++) {
+  for (int q = part * (16 / nsplit); q < (part + 1) * (16 / nsplit); q++) {
     const int r = (tid >> 7) * 64 + 4 * q;
     double S[4] = {0.0, 0.0, 0.0, 0.0};
     if (scaled) {
@@ -766,10 +768,12 @@ cudaError_t launch_build_R(const NllWork &w, int bi0, cudaStream_t st) {
   const int64_t sM = (int64_t)w.npad * w.npad;
   if (bi0 < 0 || bi0 >= NI) return cudaErrorInvalidValue;
   const size_t smem = (size_t)(2 * w.dpad * XP + w.dpad + MGP_EXP_TAB_DOUBLES) * sizeof(double);
-  dim3 grid(NI, NI - bi0, w.B);
-  static size_t smem_set[MGP_MAX_DEVICES] = {};
-  int dev = 0;
+  int dev = 0, sm_count = 148, nsplit = 1;
   cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  while (nsplit < 4 && (int64_t)NI * (NI - bi0 + 1) / 2 * w.B * nsplit < 2 * sm_count) nsplit *= 2;
+  dim3 grid(NI, (NI - bi0) * nsplit, w.B);
+  static size_t smem_set[MGP_MAX_DEVICES] = {};
   dev = dev < 0 || dev >= MGP_MAX_DEVICES ? 0 : dev;
   if (smem > smem_set[dev]) {   // the opt-in only ever needs to grow
     cudaFuncSetAttribute(k_build_R<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -778,11 +782,11 @@ cudaError_t launch_build_R(const NllWork &w, int bi0, cudaStream_t st) {
     smem_set[dev] = smem;
   }
   if (w.corr == MGP_CORR_SE)
-    k_build_R<0><<<grid, 256, smem, st>>>(w.Xc, w.n, w.npad, w.dpad, w.params, w.n_par, w.mode, w.noise_var, w.R, sM, bi0);
+    k_build_R<0><<<grid, 256, smem, st>>>(w.Xc, w.n, w.npad, w.dpad, w.params, w.n_par, w.mode, w.noise_var, w.R, sM, bi0, nsplit);
   else if (w.corr == MGP_CORR_MATERN32)
-    k_build_R<1><<<grid, 256, smem, st>>>(w.Xc, w.n, w.npad, w.dpad, w.params, w.n_par, w.mode, w.noise_var, w.R, sM, bi0);
+    k_build_R<1><<<grid, 256, smem, st>>>(w.Xc, w.n, w.npad, w.dpad, w.params, w.n_par, w.mode, w.noise_var, w.R, sM, bi0, nsplit);
   else if (w.corr == MGP_CORR_ABSEXP)
-    k_build_R<2><<<grid, 256, smem, st>>>(w.Xc, w.n, w.npad, w.dpad, w.params, w.n_par, w.mode, w.noise_var, w.R, sM, bi0);
+    k_build_R<2><<<grid, 256, smem, st>>>(w.Xc, w.n, w.npad, w.dpad, w.params, w.n_par, w.mode, w.noise_var, w.R, sM, bi0, nsplit);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

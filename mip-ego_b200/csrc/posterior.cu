@@ -334,19 +334,25 @@ __device__ __forceinline__ void slab_mma(double (&acc)[8][4][2], const double *a
     for (int ct = 0; ct < 4; ct++) dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt].y, b[ct].y);
 }
 
-// Last row block of a matrix whose size is not a multiple of 128: the row tiles that hold only
-// padding (zero rows of the packed operand) are skipped -- again by a warp-uniform branch.
-__device__ __forceinline__ void slab_mma_upto(int rt1, double (&acc)[8][4][2], const double *a_s,
-                                              const double *b_s, int wr, int wc, int lane) {
+// A whole 32-k stage (four slabs, straight-line code) for a warp whose last row tiles are padding: at
+// n = 500 the odd-parity warps of the last row block own 7 valid row tiles, and that row block has the
+// longest items.
+template <int RT1>
+__device__ __forceinline__ void stage_rt1(double (&acc)[8][4][2], const double *as, const double *bs, int wr,
+                                          int wc, int lane) {
+#pragma unroll
+  for (int js = 0; js < 4; js++) slab_mma<0, RT1>(acc, as + js * 1024, bs + js * 1024, wr, wc, lane);
+}
+__device__ __forceinline__ void stage_upto(int rt1, double (&acc)[8][4][2], const double *as, const double *bs,
+                                           int wr, int wc, int lane) {
   switch (rt1) {
-    case 1: slab_mma<0, 1>(acc, a_s, b_s, wr, wc, lane); break;
-    case 2: slab_mma<0, 2>(acc, a_s, b_s, wr, wc, lane); break;
-    case 3: slab_mma<0, 3>(acc, a_s, b_s, wr, wc, lane); break;
-    case 4: slab_mma<0, 4>(acc, a_s, b_s, wr, wc, lane); break;
-    case 5: slab_mma<0, 5>(acc, a_s, b_s, wr, wc, lane); break;
-    case 6: slab_mma<0, 6>(acc, a_s, b_s, wr, wc, lane); break;
-    case 7: slab_mma<0, 7>(acc, a_s, b_s, wr, wc, lane); break;
-    case 8: slab_mma<0, 8>(acc, a_s, b_s, wr, wc, lane); break;
+    case 1: stage_rt1<1>(acc, as, bs, wr, wc, lane); break;
+    case 2: stage_rt1<2>(acc, as, bs, wr, wc, lane); break;
+    case 3: stage_rt1<3>(acc, as, bs, wr, wc, lane); break;
+    case 4: stage_rt1<4>(acc, as, bs, wr, wc, lane); break;
+    case 5: stage_rt1<5>(acc, as, bs, wr, wc, lane); break;
+    case 6: stage_rt1<6>(acc, as, bs, wr, wc, lane); break;
+    case 7: stage_rt1<7>(acc, as, bs, wr, wc, lane); break;
     default: break;
   }
 }
@@ -478,8 +484,7 @@ __global__ void __launch_bounds__(384, 1) k_trmm(TrmmParams p) {
 #pragma unroll
           for (int js = 0; js < 4; js++) slab_mma<0>(acc, as + js * 1024, bs + js * 1024, wr, wc, lane);
         } else {
-#pragma unroll 1
-          for (int js = 0; js < 4; js++) slab_mma_upto(rt1, acc, as + js * 1024, bs + js * 1024, wr, wc, lane);
+          stage_upto(rt1, acc, as, bs, wr, wc, lane);
         }
       } else {
         // diagonal block: tiles above the diagonal (i8 < jl) are zero.  Row tiles are interleaved
