@@ -180,10 +180,11 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
     return id;
   };
   auto k_range = [&](const TileCoord &t, int &klo, int &nk) {
-    int khi = g.K;
+    const int inner = t.z % g.n_inner;
+    int khi = (inner == 0 && g.K0 > 0) ? g.K0 : g.K;
     klo = 0;
     if (g.kmode & 1) klo = t.colblk * 128;
-    if (g.kmode & 4) klo = max(klo, t.rowblk * 128);
+    if (g.kmode & 4) klo = max(klo, t.rowblk * 128 - inner * g.koff_in);
     if (g.kmode & 2) khi = min(khi, (t.rowblk + 1) * 128);
     nk = max(0, (khi - klo) / GK);
   };
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(GEMM_CONSUMERS + GEMM_PRODUCERS, 1) k_dgemm(Ge
     k_range(t, klo, nk);
     const int rbase = wr * (MT / 2);
     const bool tri_lo = (g.kmode & 2) && (t.rowblk + 1) * 128 <= g.K && nk >= 8;
-    const bool tri_hi = (g.kmode & 4) && klo == t.rowblk * 128 && nk >= 8;
+    const bool tri_hi = (g.kmode & 4) && klo == t.rowblk * 128 - inner * g.koff_in && nk >= 8;
     const bool tri_b = (g.kmode & 1) && klo == t.colblk * 128 && nk >= 8;
     // diagonal output tile of a symmetric product: 0 = compute everything, 1..4 = stair (mma_stage),
     // 5 = this warp's part lies entirely above the diagonal
@@ -1428,6 +1429,24 @@ cudaError_t lauum_blocked(const double *Minv, double *Rinv, int npad, int64_t sM
   g.C = Rinv; g.ldc = npad;
   g.M = g.N = g.K = npad; g.alpha = 1.0; g.beta = 0.0; g.kmode = 4; g.lower_only = 1;
   g.n_inner = 1; g.n_outer = batch;
+  g.sA_out = g.sB_out = g.sC_out = sMat;
+  (*launches)++;
+  return launch_dgemm(g, st);
+}
+
+cudaError_t lauum_split(const double *Minv, double *Rinv_a, double *Rinv_b, int npad, int64_t sMat, int batch,
+                        cudaStream_t st, int64_t *launches, int cta_cap) {
+  const int NI = npad / 128, Kh = (NI / 2) * 128;
+  GemmDesc g = {};
+  g.cta_cap = cta_cap;
+  g.A = Minv; g.lda = npad; g.ta = 1;
+  g.B = Minv; g.ldb = npad; g.tb = 1;
+  g.C = Rinv_a; g.ldc = npad;
+  g.M = g.N = npad; g.K = npad - Kh; g.K0 = Kh; g.koff_in = Kh;
+  g.alpha = 1.0; g.beta = 0.0; g.kmode = 4; g.lower_only = 1;
+  g.n_inner = 2; g.n_outer = batch;
+  g.sA_in = g.sB_in = (int64_t)Kh * npad;
+  g.sC_in = (int64_t)(((intptr_t)Rinv_b - (intptr_t)Rinv_a) / (intptr_t)sizeof(double));
   g.sA_out = g.sB_out = g.sC_out = sMat;
   (*launches)++;
   return launch_dgemm(g, st);

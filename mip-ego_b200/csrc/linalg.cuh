@@ -20,6 +20,10 @@ struct GemmDesc {
   int order;   // tile hand-out order (longest k first): 0/1 rows ascending, 2 rows descending, 3 columns ascending
   int n_inner, n_outer;
   int64_t sA_in, sB_in, sC_in, sA_out, sB_out, sC_out;
+  // Split of the k range over the inner batch index (0 = off): inner i works on the operands shifted by
+  // sA_in / sB_in = i * koff_in rows of k, so its triangular start (kmode 4) is rowblk*128 - i*koff_in, and
+  // inner 0 stops at K0 instead of K.  Used to cut M^T M into two halves of k that run side by side.
+  int koff_in, K0;
   // Upper bound on the CTAs of this launch (0 = one per SM): leaves SMs to the kernels of other
   // streams when several batch groups run concurrently.  Per launch, so that two handles (or two
   // host threads) never see each other's setting.
@@ -62,6 +66,12 @@ cudaError_t trtri_blocked(const double *L, double *Minv, double *T, int npad, in
 // Rinv(lower tiles) = Minv^T Minv.
 cudaError_t lauum_blocked(const double *Minv, double *Rinv, int npad, int64_t sMat, int batch,
                           cudaStream_t st, int64_t *launches, int cta_cap = 0);
+
+// The same product as two halves of the k range side by side in ONE launch: Rinv_a + Rinv_b = Minv^T Minv
+// (lower tiles).  For few small matrices M^T M is bound by its longest tile (k = n on one SM); the halves
+// have k <= n / 2 + 64.  The consumer (gradient contraction) adds the two.
+cudaError_t lauum_split(const double *Minv, double *Rinv_a, double *Rinv_b, int npad, int64_t sMat, int batch,
+                        cudaStream_t st, int64_t *launches, int cta_cap = 0);
 
 // y = M x (trans == 0) or y = M^T x (trans == 1), M lower-triangular row-major npad x npad.
 // x == nullptr means the all-ones vector restricted to the first n entries.

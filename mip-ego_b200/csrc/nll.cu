@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) k_nll_scalars(const double *L, int npad, 
 template <int CORR, int DP>
 __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, int npad,
                                                   const double *params, int n_par, int mode,
-                                                  const double *Rinv, int64_t sR,
+                                                  const double *Rinv, const double *Rinv2, int64_t sR,
                                                   const double *gamma, const double *avec, int64_t sv,
                                                   const double *Bhat, int p,
                                                   const double *scal, double *gpart, int ntiles, int nsplit) {
@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
   const double s_div = scal[(int64_t)b * SC_N + SC_S];
   const double coefa = scal[(int64_t)b * SC_N + SC_COEFA];
   const double *Rb = Rinv + b * sR;
+  const double *Rb2 = Rinv2 ? Rinv2 + b * sR : nullptr;   // R^-1 given as the sum of two halves (lauum_split)
   const double *gm = gamma + b * sv;
   const double *av = avec + b * sv;
   double acc[DP + 2];
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(256, 2) k_nll_grad(const double *Xc, int n, in
       const int gj = bi * 128 + r + u;
       const bool on = gj < n && gj >= gk;
       rinv4[u] = on ? __ldg(Rb + (int64_t)gj * npad + gk) : 0.0;
+      if (Rb2 && on) rinv4[u] += __ldg(Rb2 + (int64_t)gj * npad + gk);
       gj4[u] = on ? __ldg(gm + gj) : 0.0;
     }
     double S[4] = {0.0, 0.0, 0.0, 0.0};
@@ -688,7 +690,7 @@ __global__ void k_iso_gather(const double *Gfull, int B, int n_short, int n_full
 template <int CORR>
 cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, const double *Xc, int n,
                           int npad, const double *params, int n_par, int mode, const double *Rinv,
-                          int64_t sR, const double *gamma, const double *avec, int64_t sv,
+                          const double *Rinv2, int64_t sR, const double *gamma, const double *avec, int64_t sv,
                           const double *Bhat, int p, const double *scal, double *gpart, int ntiles, int nsplit) {
   switch (dpad) {
 #define NG(D)                                                                                   \
@@ -698,7 +700,7 @@ cudaError_t grad_dispatch(int dpad, dim3 grid, size_t smem, cudaStream_t st, con
       cudaFuncSetAttribute(k_nll_grad<CORR, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                            (int)smem);                                                          \
   }                                                                                             \
-    k_nll_grad<CORR, D><<<grid, 256, smem, st>>>(Xc, n, npad, params, n_par, mode, Rinv, sR,    \
+    k_nll_grad<CORR, D><<<grid, 256, smem, st>>>(Xc, n, npad, params, n_par, mode, Rinv, Rinv2, sR, \
                                                   gamma, avec, sv, Bhat, p, scal, gpart, ntiles, nsplit); \
     break;
     NG(4) NG(8) NG(12) NG(16) NG(20) NG(24) NG(28) NG(32) NG(36) NG(40) NG(44) NG(48) NG(52) NG(56) NG(60) NG(64)
@@ -831,10 +833,15 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
   const bool general = w.p > 1 && w.ordinary;   // p basis functions with estimated coefficients
   // M^T M (needed by the gradient only) depends on nothing below: beside the vector chain on the side stream
   const bool side_lauum = w.side && w.eval_grad && !general;
+  const bool split_lauum = side_lauum && !w.have_L && NI >= 2 && NI <= 8;
+  const double *rinv2 = split_lauum ? w.R : nullptr;
   if (side_lauum) {
     NL_TRY(cudaEventRecord(w.ev_side_fork, st));
     NL_TRY(cudaStreamWaitEvent(w.side, w.ev_side_fork, 0));
-    NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, w.side, launches, w.gemm_cta_cap));
+    // n <= 1024: bound by the longest tile (k = n on one SM) -> two halves of k side by side, the second
+    // into the R workspace (dead since the factorisation); the gradient kernel adds them
+    if (split_lauum) NL_TRY(lauum_split(w.M, w.T, w.R, npad, sM, B, w.side, launches, w.gemm_cta_cap));
+    else NL_TRY(lauum_blocked(w.M, w.T, npad, sM, B, w.side, launches, w.gemm_cta_cap));
     NL_TRY(cudaEventRecord(w.ev_side_join, w.side));
   }
   if (!general) {
@@ -896,13 +903,13 @@ cudaError_t nll_pipeline(const NllWork &w, cudaStream_t st, int64_t *launches, i
     while (nsplit < 4 && (int64_t)ntiles * B * nsplit < 2 * sm_count) nsplit *= 2;
     dim3 grid(ntiles * nsplit, B);
     if (w.corr == MGP_CORR_SE)
-      NL_TRY(grad_dispatch<0>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
+      NL_TRY(grad_dispatch<0>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T, rinv2,
                               sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles, nsplit));
     else if (w.corr == MGP_CORR_MATERN32)
-      NL_TRY(grad_dispatch<1>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
+      NL_TRY(grad_dispatch<1>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T, rinv2,
                               sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles, nsplit));
     else
-      NL_TRY(grad_dispatch<2>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T,
+      NL_TRY(grad_dispatch<2>(w.dpad, grid, smem, st, w.Xc, n, npad, w.params, w.n_par, w.mode, w.T, rinv2,
                               sM, gamma, w.avec, npad, w.Bhat, w.p, w.scal, w.gpart, ntiles, nsplit));
     k_nll_grad_final<<<B, 1024, 0, st>>>(w.gpart, ntiles * 4, w.dpad + 2, w.n_par, w.mode, w.scal,
                                         w.status, w.out_grad);
